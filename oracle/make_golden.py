@@ -1,0 +1,299 @@
+"""Generate golden vectors for the oracle by running the UNMODIFIED reference (imported from /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):   python oracle/make_golden.py
+Outputs go to tests/golden/*.npz (small) and are committed, together with this script.
+
+What is pinned (reference classes exercised -> golden file):
+  model.BayesianRelationClassifier / FlatRelationClassifier / BayesianHead (full size, fp32)  -> head_*.npz
+  train_utils.evaluate_one_direction + evaluator.Evaluator + Evaluator_Top3 (PredCLS loop)     -> predcls_*.npz
+  evaluator.Evaluator (predcls=False) + utils.match_target_sgd (SGDET/SGCLS loop)              -> sgdet_*.npz
+  evaluator.Evaluator.iou / utils.compare_object_cat truth tables                              -> tables.npz
+
+The PredCLS/SGDET driver loops live inside `evaluate.eval_pc/eval_sgd` (which also build DDP, DETR and a
+DataLoader), so they cannot be called; the loop body here follows evaluate.py:132-183 / :382-446 and calls the
+reference's own `evaluate_one_direction`, `Evaluator.accumulate`, `accumulate_target`, `compute`.
+H1: `torch.argsort` is patched to `stable=True` while the reference computes (reference source untouched).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("HIERCOM_REFERENCE", "/root/reference")
+OUT = os.path.join(REPO, "tests", "golden")
+sys.path.insert(0, REPO)
+sys.path.insert(0, REF)
+sys.modules.setdefault("torchmetrics", types.ModuleType("torchmetrics"))
+os.chdir(REF)
+
+import evaluator as ref_evaluator   # noqa: E402
+import model as ref_model           # noqa: E402
+import train_utils as ref_train_utils  # noqa: E402
+import utils as ref_utils           # noqa: E402
+
+from scene_graph_commonsense_b200 import synthetic  # noqa: E402
+from tests.golden_cases import PREDCLS_CASES, SGDET_CASES  # noqa: E402
+
+_orig_argsort = torch.argsort
+
+
+def _stable_argsort(x, dim=-1, descending=False, stable=False):
+    return _orig_argsort(x, dim=dim, descending=descending, stable=True)
+
+
+class FakeClassifier:
+    """Stands in for the DDP-wrapped relation head inside evaluate_one_direction: returns table-driven scores."""
+
+    def __init__(self, batch, splits, hierar, **kw):
+        self.fn = synthetic.batch_score_fn(batch, splits, **kw)
+        self.splits, self.hierar = splits, hierar
+        self.ctx = None
+
+    def __call__(self, h_sub, h_obj, c1, c2, s1, s2, rank, *a):
+        rel, sup, conn = self.fn(h_sub, h_obj, c1, c2, s1, s2, self.ctx)
+        conn = conn.view(-1, 1)
+        if not self.hierar:
+            return rel, conn, None, None
+        G, P = self.splits[0], self.splits[1]
+        return rel[:, :G], rel[:, G:G + P], rel[:, G + P:], sup, conn, None, None
+
+
+def masks_of(boxes, fs=32):
+    m = torch.zeros(boxes.shape[0], fs, fs, dtype=torch.uint8)
+    for j in range(boxes.shape[0]):
+        m[j, int(boxes[j][2]):int(boxes[j][3]), int(boxes[j][0]):int(boxes[j][1])] = 1
+    return m
+
+
+def ref_iou_mask(gm, em):
+    """evaluate.py:150-154 verbatim semantics."""
+    joint_intersect = torch.logical_or(gm, em)
+    joint_union = torch.logical_and(gm, em)
+    joint_iou = (torch.sum(torch.sum(joint_intersect, dim=-1), dim=-1) / torch.sum(torch.sum(joint_union, dim=-1), dim=-1)).flatten()
+    joint_iou[torch.isinf(joint_iou)] = 0
+    return joint_iou > 0
+
+
+def run_predcls(batch, args, Recall, Recall_top3, clf):
+    """evaluate.py:111-183 loop body around the reference's evaluate_one_direction."""
+    masks = [masks_of(s.bbox) for s in batch]
+    relationships = [s.relationships for s in batch]
+    subj_or_obj = [s.subj_or_obj for s in batch]
+    relations_target, direction_target = [], []
+    num_graph_iter = torch.as_tensor([len(m) for m in masks]) - 1
+    for graph_iter in range(int(max(num_graph_iter))):
+        keep = torch.nonzero(num_graph_iter > graph_iter).view(-1)
+        relations_target.append(torch.vstack([relationships[i][graph_iter] for i in keep]).T)
+        direction_target.append(torch.vstack([subj_or_obj[i][graph_iter] for i in keep]).T)
+    num_graph_iter = torch.as_tensor([len(m) for m in masks])
+    stats = np.zeros(5)
+    for graph_iter in range(int(max(num_graph_iter))):
+        keep = torch.nonzero(num_graph_iter > graph_iter).view(-1)
+        gm = torch.stack([masks[i][graph_iter].unsqueeze(0) for i in keep])
+        cat_g = torch.tensor([batch[i].categories[graph_iter] for i in keep])
+        sp_g = [batch[i].super_categories[graph_iter] for i in keep]
+        bb_g = torch.stack([batch[i].bbox[graph_iter] for i in keep])
+        for edge_iter in range(graph_iter):
+            em = torch.stack([masks[i][edge_iter].unsqueeze(0) for i in keep])
+            cat_e = torch.tensor([batch[i].categories[edge_iter] for i in keep])
+            sp_e = [batch[i].super_categories[edge_iter] for i in keep]
+            bb_e = torch.stack([batch[i].bbox[edge_iter] for i in keep])
+            iou_mask = ref_iou_mask(gm, em)
+            if torch.sum(iou_mask) == 0:
+                continue
+            clf.ctx = (keep, graph_iter, edge_iter)
+            r = ref_train_utils.evaluate_one_direction(clf, args, None, None, cat_g, cat_e, sp_g, sp_e, bb_g, bb_e, iou_mask, 'cpu',
+                                                       graph_iter, edge_iter, keep, Recall, Recall_top3, relations_target,
+                                                       direction_target, 0, 1, first_direction=True)
+            stats += np.array([float(x) for x in r])
+            clf.ctx = (keep, edge_iter, graph_iter)
+            r = ref_train_utils.evaluate_one_direction(clf, args, None, None, cat_e, cat_g, sp_e, sp_g, bb_e, bb_g, iou_mask, 'cpu',
+                                                       graph_iter, edge_iter, keep, Recall, Recall_top3, relations_target,
+                                                       direction_target, 0, 1, first_direction=False)
+            stats += np.array([float(x) for x in r])
+    return stats
+
+
+def ev_counters(ev):
+    def block(hits, pc, n, npc):
+        return np.concatenate([[hits[k] for k in (20, 50, 100)], np.concatenate([pc[k].numpy() for k in (20, 50, 100)]),
+                               [n], npc.numpy()])
+    return np.concatenate([block(ev.result_dict, ev.result_per_class, ev.num_connected_target, ev.num_conn_target_per_class),
+                           block(ev.result_dict_zs, ev.result_per_class_zs, ev.num_connected_target_zs,
+                                 ev.num_conn_target_per_class_zs)]).astype(np.int64)
+
+
+def t3_counters(ev):
+    K = (20, 50, 100)
+    return np.concatenate([[ev.result_dict[k] for k in K], np.concatenate([ev.result_per_class[k].numpy() for k in K]),
+                           [ev.result_dict_top1[k] for k in K], np.concatenate([ev.result_per_class_top1[k].numpy() for k in K]),
+                           [ev.num_connected_target], ev.num_conn_target_per_class.numpy()]).astype(np.int64)
+
+
+def flat_metrics(m):
+    out = []
+    for x in m:
+        if x is None:
+            continue
+        for v in x:
+            out.append(np.atleast_1d(np.asarray(v, dtype=np.float64)))
+    return np.concatenate(out)
+
+
+def install_cs(ev, cs):
+    """cs = None keeps the shipped .pt sets; otherwise (seed, frac_aligned, frac_violated) installs dense synthetic
+    sets by attribute assignment (the reference only ever does `tuple in dict`, evaluator.py:191-192)."""
+    if cs is None or ev.commonsense_aligned_triplets is None:
+        return
+    al, vi = synthetic.synthetic_cs_keys(*cs)
+    unpack = lambda k: (int(k) // 7500, (int(k) // 150) % 50, int(k) % 150)
+    ev.commonsense_aligned_triplets = {unpack(k): 1 for k in al}
+    ev.commonsense_violated_triplets = {unpack(k): 1 for k in vi}
+
+
+def gen_predcls():
+    for name, c in PREDCLS_CASES.items():
+        args = synthetic.reference_args(run_mode=c["run_mode"], hierar=c["hierar"])
+        samples = synthetic.make_batch(c["ids"], c["n"], with_maps=False, p_rel=0.5)
+        Recall = ref_evaluator.Evaluator(args=args, num_classes=50, iou_thresh=0.5, top_k=[20, 50, 100])
+        install_cs(Recall, c.get("cs"))
+        Recall_top3 = ref_evaluator.Evaluator_Top3(args=args, num_classes=50, iou_thresh=0.5, top_k=[20, 50, 100]) if c["hierar"] else None
+        stats = np.zeros(5)
+        torch.argsort = _stable_argsort
+        try:
+            for w in c.get("windows", [list(range(len(samples)))]):
+                batch = [samples[i] for i in w]
+                clf = FakeClassifier(batch, (15, 11, 24), c["hierar"], **c["kw"])
+                stats += run_predcls(batch, args, Recall, Recall_top3, clf)
+                m = Recall.compute(per_class=True)
+                if Recall_top3 is not None:
+                    m3 = Recall_top3.compute(per_class=True)
+                    Recall_top3.clear_data()
+                Recall.clear_data()
+        finally:
+            torch.argsort = _orig_argsort
+        out = dict(ev=ev_counters(Recall), metrics=flat_metrics(m), stats=stats)
+        if Recall_top3 is not None:
+            out["t3"] = t3_counters(Recall_top3)
+            out["metrics3"] = flat_metrics(m3)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+        print(name, "hits", out["ev"][:3], "ngt", out["ev"][153], "t3", out.get("t3", np.zeros(3))[:3])
+
+
+def gen_sgdet():
+    for name, c in SGDET_CASES.items():
+        args = synthetic.reference_args(run_mode=c["run_mode"], hierar=True)
+        prel = c.get("p_rel", [0.5] * len(c["ids"]))
+        batch = [synthetic.make_sgdet_image(i, g, p, p_rel=pr, with_maps=False)
+                 for i, g, p, pr in zip(c["ids"], c["n_gt"], c["n_prop"], prel)]
+        Recall = ref_evaluator.Evaluator(args=args, num_classes=50, iou_thresh=0.5, top_k=[20, 50, 100])
+        install_cs(Recall, c.get("cs"))
+        clf = FakeClassifier(batch, (15, 11, 24), True, gain=3.0)
+        masks = [masks_of(s.bbox_pred) for s in batch]
+        n_iter = torch.as_tensor([len(m) for m in masks])
+        torch.argsort = _stable_argsort
+        try:
+            for g in range(int(max(n_iter))):
+                keep = torch.nonzero(n_iter > g).view(-1)
+                gm = torch.stack([masks[i][g].unsqueeze(0) for i in keep])
+                cg = torch.tensor([batch[i].categories_pred[g] for i in keep])
+                bg = torch.stack([batch[i].bbox_pred[g] for i in keep])
+                fg = torch.hstack([batch[i].cat_conf_pred[g] for i in keep])
+                for e in range(g):
+                    em = torch.stack([masks[i][e].unsqueeze(0) for i in keep])
+                    ce = torch.tensor([batch[i].categories_pred[e] for i in keep])
+                    be = torch.stack([batch[i].bbox_pred[e] for i in keep])
+                    fe = torch.hstack([batch[i].cat_conf_pred[e] for i in keep])
+                    iou_mask = ref_iou_mask(gm, em)
+                    if torch.sum(iou_mask) == 0:
+                        continue
+                    for first in (True, False):
+                        clf.ctx = (keep, g, e) if first else (keep, e, g)
+                        r1, r2, r3, sup, conn, _, _ = clf(None, None, None, None, None, None, 'cpu')
+                        relation = torch.cat((r1, r2, r3), dim=1)
+                        a = (cg, ce, bg, be, fg, fe) if first else (ce, cg, be, bg, fe, fg)
+                        Recall.accumulate(keep, relation, None, sup, torch.log(torch.sigmoid(conn[:, 0])),
+                                          a[0], a[1], None, None, a[2], a[3], None, None, iou_mask, False, a[4], a[5])
+            tg = ref_utils.match_target_sgd('cpu', [s.relationships for s in batch], [s.subj_or_obj for s in batch],
+                                            [s.categories for s in batch], [s.bbox for s in batch])
+            cat_s, cat_o, bb_s, bb_o, rel_t = tg
+            Recall.accumulate_target(rel_t, cat_s, cat_o, bb_s, bb_o)
+            m = Recall.compute(per_class=True, predcls=False)
+        finally:
+            torch.argsort = _orig_argsort
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), ev=ev_counters(Recall), metrics=flat_metrics(m))
+        print(name, "hits", ev_counters(Recall)[:3], "ngt", ev_counters(Recall)[153])
+
+
+def gen_head():
+    """Full-size fp32 head forward through the reference modules on a handful of directed pairs."""
+    torch.set_num_threads(os.cpu_count())
+    s = synthetic.make_image(900, 5)
+    pairs = [(1, 0), (0, 1), (3, 2), (2, 3), (4, 1), (1, 4)]
+    m = masks_of(s.bbox).float()
+    hs = torch.stack([torch.cat((s.feat * m[a], s.depth * m[a]), 0) for a, b in pairs])
+    ho = torch.stack([torch.cat((s.feat * m[b], s.depth * m[b]), 0) for a, b in pairs])
+    c1 = torch.stack([s.categories[a] for a, b in pairs])
+    c2 = torch.stack([s.categories[b] for a, b in pairs])
+    s1 = [s.super_categories[a] for a, b in pairs]
+    s2 = [s.super_categories[b] for a, b in pairs]
+    args = synthetic.reference_args()
+    out = {}
+    for tag, gain in (("init", 1.0), ("trained", 40.0)):
+        sd = synthetic.head_state_dict(seed=0, logit_gain=gain)
+        net = ref_model.BayesianRelationClassifier(args=args, input_dim=128, feature_size=32, num_classes=150, num_super_classes=17,
+                                                   num_geometric=15, num_possessive=11, num_semantic=24)
+        net.load_state_dict(sd)
+        net.eval()
+        with torch.no_grad():
+            r1, r2, r3, sup, conn, pred, _ = net(hs, ho, c1, c2, s1, s2, 'cpu')
+        out["hier_%s_relation" % tag] = torch.cat((r1, r2, r3), 1).numpy()
+        out["hier_%s_super" % tag] = sup.numpy()
+        out["hier_%s_conn" % tag] = conn.numpy()
+        out["hier_%s_pred" % tag] = pred.numpy()
+        print("head", tag, "logit range", float(r1.min()), float(r1.max()))
+    sdf = synthetic.head_state_dict(seed=1, flat=True)
+    netf = ref_model.FlatRelationClassifier(args=args, input_dim=128, output_dim=50, feature_size=32, num_classes=150)
+    netf.load_state_dict(sdf)
+    netf.eval()
+    with torch.no_grad():
+        rel, conn, pred, _ = netf(hs, ho, c1, c2, s1, s2, 'cpu')
+    out["flat_relation"], out["flat_conn"] = rel.numpy(), conn.numpy()
+    bh = ref_model.BayesianHead(input_dim=512)
+    sdh = {k: v for k, v in synthetic.head_state_dict(seed=2, logit_gain=20.0).items() if k.startswith(("fc3_", "fc5"))}
+    bh.load_state_dict(sdh)
+    g = torch.Generator().manual_seed(5)
+    h = torch.randn(16, 512, generator=g)
+    with torch.no_grad():
+        b1, b2, b3, bs = bh(h)
+    out["bhead_relation"], out["bhead_super"] = torch.cat((b1, b2, b3), 1).numpy(), bs.numpy()
+    np.savez_compressed(os.path.join(OUT, "head.npz"), **out)
+
+
+def gen_tables():
+    args = synthetic.reference_args(run_mode="eval")
+    ev = ref_evaluator.Evaluator(args=args, num_classes=50, iou_thresh=0.5, top_k=[20, 50, 100])
+    g = torch.Generator().manual_seed(11)
+    boxes = torch.randint(-3, 36, (400, 2, 4), generator=g).float() + torch.rand(400, 2, 4, generator=g)
+    boxes[:100] = torch.randint(0, 33, (100, 2, 4), generator=g).float()
+    boxes[200:, 1] = boxes[200:, 0] + torch.randint(-2, 3, (200, 4), generator=g).float()   # correlated pairs
+    iou = np.array([float(ev.iou(b[0], b[1])) for b in boxes])
+    syn = np.array([[ref_utils.compare_object_cat(a, b) for b in range(150)] for a in range(150)], dtype=np.uint8)
+    np.savez_compressed(os.path.join(OUT, "tables.npz"), boxes=boxes.numpy(), iou=iou, synonyms=syn)
+    print("tables: iou>=.5 count", int((iou >= 0.5).sum()))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["tables", "predcls", "sgdet", "head"]
+    if "tables" in which:
+        gen_tables()
+    if "predcls" in which:
+        gen_predcls()
+    if "sgdet" in which:
+        gen_sgdet()
+    if "head" in which:
+        gen_head()

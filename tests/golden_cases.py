@@ -1,0 +1,23 @@
+"""Case tables shared by oracle/make_golden.py (which runs the real reference) and the tests that replay them."""
+
+PREDCLS_CASES = {
+    # name: (image ids, boxes per image, run_mode, hierar, score kwargs, batches)
+    "pc_cs_single20": dict(ids=[0], n=[20], run_mode="eval_cs", hierar=True, kw=dict(gain=3.0)),
+    "pc_cs_ragged": dict(ids=[10, 11, 12, 13, 14, 15], n=[2, 16, 7, 3, 12, 9], run_mode="eval_cs", hierar=True, kw=dict(gain=3.0)),
+    "pc_cs_dense": dict(ids=[16, 17, 18, 19], n=[12, 5, 17, 9], run_mode="eval_cs", hierar=True, kw=dict(gain=3.0), cs=(3, 0.5, 0.1)),
+    "pc_plain_ragged": dict(ids=[20, 21, 22, 23], n=[5, 11, 8, 14], run_mode="eval", hierar=True, kw=dict(gain=3.0)),
+    "pc_plain_ties": dict(ids=[30, 31, 32], n=[9, 13, 6], run_mode="eval", hierar=True, kw=dict(gain=1.0, tie_quantum=0.5)),
+    "pc_cs_ties": dict(ids=[33, 34], n=[15, 10], run_mode="eval_cs", hierar=True, kw=dict(gain=1.0, tie_quantum=1.0), cs=(4, 0.6, 0.05)),
+    "pc_flat": dict(ids=[40, 41, 42], n=[8, 12, 4], run_mode="eval", hierar=False, kw=dict(gain=3.0)),
+    "pc_flat_cs": dict(ids=[43, 44], n=[10, 6], run_mode="eval_cs", hierar=False, kw=dict(gain=3.0), cs=(5, 0.5, 0.1)),
+    "pc_two_windows": dict(ids=[50, 51, 52, 53, 54, 55], n=[6, 9, 12, 5, 10, 7], run_mode="eval_cs", hierar=True,
+                           kw=dict(gain=3.0), windows=[[0, 1, 2], [3, 4, 5]], cs=(6, 0.5, 0.1)),
+    "pc_cfg2_slice": dict(ids=[60, 61], n=[40, 40], run_mode="eval_cs", hierar=True, kw=dict(gain=3.0)),
+}
+
+
+SGDET_CASES = {
+    "sgd_cs": dict(ids=[70, 71, 72], n_gt=[6, 9, 4], n_prop=[14, 20, 9], run_mode="eval_cs", cs=(7, 0.5, 0.1)),
+    "sgd_plain": dict(ids=[73, 74], n_gt=[8, 5], n_prop=[18, 12], run_mode="eval"),
+    "sgd_nogt": dict(ids=[75, 76], n_gt=[2, 7], n_prop=[6, 15], run_mode="eval", p_rel=[0.0, 0.6]),
+}
