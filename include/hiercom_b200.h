@@ -1,0 +1,198 @@
+/* hiercom_b200 - C ABI of the B200-native HIERCOM relation-prediction hot path.
+ *
+ * Drop-in boundary: plain pointers + sizes + a CUDA stream in, status code out.  Every pointer
+ * named "device" is a device pointer owned by the caller (the PyTorch caching allocator in the Python host);
+ * kernels never allocate.  All entry points are asynchronous on `stream` unless noted, re-entrant, and return
+ * HC_OK or a negative HC_E_* code; `hc_last_error()` returns the text for the calling thread.  There is no CPU
+ * fallback: on a device that is not sm_100 every compute entry point returns HC_E_ARCH.
+ *
+ * Citations are into the reference repository (bowen-upenn/scene_graph_commonsense @ 3388036f).
+ */
+#ifndef HIERCOM_B200_H_
+#define HIERCOM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HC_ABI_VERSION 1
+
+#define HC_OK 0
+#define HC_E_SHAPE (-1) /* bad size / unsupported shape          */
+#define HC_E_ALIGN (-2) /* pointer or stride not 16-byte aligned */
+#define HC_E_ARCH (-3)  /* current device is not sm_100          */
+#define HC_E_CUDA (-4)  /* CUDA runtime / driver error           */
+#define HC_E_NULL (-5)  /* required pointer is NULL              */
+
+#define HC_NUM_OBJ 150
+#define HC_NUM_PRED_MAX 64
+#define HC_TRIPLET_SPACE (150 * 50 * 150)
+#define HC_BITMAP_WORDS ((HC_TRIPLET_SPACE + 31) / 32)
+#define HC_TOP_MAX 128 /* largest supported top-K cut (reference uses 100) */
+
+typedef void* hc_stream_t; /* cudaStream_t */
+
+const char* hc_last_error(void);
+int hc_abi_version(void);
+/* HC_OK iff the current CUDA device is compute capability 10.x */
+int hc_device_check(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * R9 (host) - commonsense sets -> one "passes the filter" bitmap: bit(key) = key in aligned AND key not in
+ * violated, key = (s*50+p)*150+o.  Replaces the two python dict lookups per candidate of
+ * evaluator.py:189-194,261-266 (and train_utils.py:53-54).  HOST function, synchronous.
+ */
+int hc_cs_bitmap_build(const int64_t* aligned_keys, int64_t n_aligned, const int64_t* violated_keys,
+                       int64_t n_violated, uint32_t* bitmap_out /* host, HC_BITMAP_WORDS words */);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * R1 + R2 + R4 - rectangular masks, two-pass ordered-pair enumeration and the overlap pre-filter
+ * (evaluate.py:111-116,132-156; train_test.py:365-410).  Images are CSR segments of `boxes`
+ * (int32 xmin,xmax,ymin,ymax on the feature grid, already truncated toward zero like `int()`).
+ *
+ * For image i with N_i boxes, unordered pairs (g,e), e<g are visited in the reference's loop order
+ * t = g(g-1)/2 + e.  ov(i,g,e) = masks overlap.  Skip rule:
+ *   group_id == NULL ("per_image", = reference at batch_size 1): keep iff ov(i,g,e)
+ *   group_id != NULL ("batch"): keep iff ANY image j of the same group with N_j > g has ov(j,g,e)
+ * Each kept pair emits two directed pairs: (sub=g,obj=e) then (sub=e,obj=g), with
+ *   pair_ov  = ov(i,g,e)                                       (iou_mask, evaluate.py:154)
+ *   pair_gt  = rel_tri[t] if dir_tri[t] == 1 (first) / == 0 (second) else -1   (train_utils.py:169-187)
+ *   pair_rel = rel_tri[t] (undirected label, optional output, used by hc_connectivity_stats)
+ * Outputs must be sized for sum_i N_i(N_i-1) entries; `total_out[0]` receives the number written.
+ * Workspaces: ws_ov [sum T_i] bytes, ws_any [n_groups*max_tri] bytes (batch mode), ws_counts [n_images].
+ */
+int hc_pairs_enumerate(const int32_t* boxes, const int32_t* box_offsets, int32_t n_images,
+                       const int32_t* group_id, int32_t n_groups, int32_t max_tri, const int32_t* rel_tri,
+                       const int8_t* dir_tri, const int32_t* tri_offsets, int32_t feature_size, uint8_t* ws_ov,
+                       uint8_t* ws_any, int32_t* ws_counts, int32_t* pair_offsets, int32_t* pair_sub,
+                       int32_t* pair_obj, int32_t* pair_img, uint8_t* pair_ov, int32_t* pair_gt,
+                       int32_t* pair_rel, int32_t* total_out, hc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * R3 (fused away) + R5/R6 dense contractions - one tcgen05/TMEM kernel, bf16 operands, fp32 accumulate.
+ *
+ *   out[m, n] = epilogue( sum_k A[m,k] * B[n,k] )        B is [N,K] row-major ("K-major"), bf16
+ *
+ * mode HC_GEMM_PLAIN : A is [M,K] row-major bf16 with row stride lda (elements).
+ * mode HC_GEMM_CONV3 : implicit 3x3 / pad 1 / stride 1 convolution.  A is an NHWC activation tensor
+ *     [n_img, H, W, c_total] bf16; input channels [c_base, c_base+c_in) are used; M = n_img*H*W output pixels,
+ *     K = 9*c_in with k = (ky*3+kx)*c_in + c (B must be packed in that order).  H, W multiples of 16.
+ * epilogue HC_EPI_BF16      : out bf16 [M, ldc] (+col offset c_off): act(acc + bias)
+ *          HC_EPI_F32       : out f32  [M, ldc]: acc (+ bias if non-NULL)
+ *          HC_EPI_POOL_BF16 : conv only: 2x2/stride-2 max-pool of relu(acc + bias) -> NHWC bf16
+ *                             [n_img, H/2, W/2, ldc] (model.py:143-146 conv+ReLU+maxpool)
+ * Requirements: K % 64 == 0, N % 128 == 0, all bases 16-byte aligned, lda/ldc/c_total multiples of 8.
+ */
+#define HC_GEMM_PLAIN 0
+#define HC_GEMM_CONV3 1
+#define HC_EPI_BF16 0
+#define HC_EPI_F32 1
+#define HC_EPI_POOL_BF16 2
+#define HC_ACT_NONE 0
+#define HC_ACT_RELU 1
+#define HC_ACT_TANH 2
+
+typedef struct hc_gemm_desc {
+  const void* a;     /* device, bf16 */
+  const void* b;     /* device, bf16 [N,K] */
+  const float* bias; /* device, f32 [N] or NULL */
+  void* out;         /* device */
+  int64_t m, n, k;
+  int64_t lda;       /* PLAIN: A row stride in elements */
+  int64_t ldc;       /* output row stride in elements */
+  int64_t c_off;     /* output column offset in elements */
+  int32_t mode, epilogue, act;
+  int32_t n_img, h, w, c_total, c_base, c_in; /* CONV3 */
+  int32_t group_m;   /* tile rasterisation: m-blocks per band (0 = default) */
+  int32_t m_sub;     /* 128-row sub-tiles per CTA tile: 1 or 2 (0 = default) */
+} hc_gemm_desc;
+
+int hc_tc_gemm(const hc_gemm_desc* desc, hc_stream_t stream);
+
+/* [B,C0,hw] f32 (+ optional [B,C1,hw] f32) NCHW maps -> [B*hw, k_pad] bf16 pixel-major rows, zero padded
+ * (the A operand of the 1x1 convolutions, model.py:139-140; also packs the legacy pre-masked [bs,257,32,32]). */
+int hc_pack_pixels(const float* src0, int32_t c0, const float* src1, int32_t c1, int32_t n_img, int32_t hw,
+                   int32_t k_pad, void* out_bf16, hc_stream_t stream);
+
+/* R3: per-box masked conv1 activations.  tanh(conv1(x*mask)) == mask ? tanh(conv1(x)) : tanh(bias)
+ * (train_test.py:391,398 + model.py:139-140).  t_img [n_img, fs*fs, C] bf16,
+ * fill [C] bf16 = tanh(bias), out [n_box, fs, fs, C] bf16. */
+int hc_box_select(const void* t_img, const int32_t* boxes, const int32_t* box_img, int32_t n_box, int32_t fs,
+                  int32_t channels, const void* fill, void* out, hc_stream_t stream);
+
+/* model.py:143-144 after the subject/object split of conv2_1:
+ * out[p] = maxpool2x2(relu(U[pair_sub[p]] + V[pair_obj[p]] + bias)),  U,V [n_box, fs, fs, C] bf16,
+ * out [n_pairs, fs/2, fs/2, C] bf16. */
+int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub,
+                      const int32_t* pair_obj, int32_t n_pairs, int32_t fs, int32_t channels, void* out,
+                      hc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * R6 tail + R7 - label-embedding add, fc2 bias + ReLU, fc3_x / fc4 / fc5 heads and the Bayesian hierarchical
+ * log-softmax (model.py:152-168,175-184; flat variant model.py:97-101).
+ *   pred = relu(fc2_raw + fc2_bias + E[c_sub] + E[150+c_obj] + sum E[300+s_sub] + sum E[317+s_obj])
+ *   hier : super = log_softmax(fc5 pred); rel_k = log_softmax(fc3_k pred / T_k) + super[k]; conn = fc4 pred
+ *   flat : relation = fc3 pred (raw logits), conn = fc4 pred
+ * emb is fc2.weight[:, 4096:].T, f32 [n_emb, hidden].  w_heads rows: hier [fc3_1; fc3_2; fc3_3; fc4; fc5],
+ * flat [fc3; fc4].  row_sub/row_obj index box_cat / box_super ([n_box,4] int8, -1 padded; NULL = no
+ * super-class columns, model.py:125-128).  logsig = log(sigmoid(conn)) (train_utils.py:190).
+ * fc2_bias == NULL: fc2_raw already is the hidden vector - no bias/embedding/ReLU (BayesianHead, model.py:24-34).
+ */
+int hc_hier_head(const float* fc2_raw, int64_t ld_raw, int32_t n_rows, int32_t hidden, const float* fc2_bias,
+                 const float* emb, int32_t num_obj, int32_t num_super, const int32_t* row_sub,
+                 const int32_t* row_obj, const int32_t* box_cat, const int8_t* box_super, const float* w_heads,
+                 const float* b_heads, int32_t n_geo, int32_t n_pos, int32_t n_sem, int32_t flat, float t1,
+                 float t2, float t3, float* relation, float* super_rel, float* connectivity, float* logsig,
+                 float* pred_out, hc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * R8 + R9 (+ R10's connectivity add) - candidate construction (evaluator.py:124-138,157-179,231-266,646-649).
+ * Per row r and super-category k: conf = max(relation[r, seg_k]) (+ conf_sub[r] + conf_obj[r] when non-NULL),
+ * label = first argmax + offset_k; conf = -inf if !row_ov[r]; conf = -inf if pass_bitmap != NULL and
+ * (cat_sub,label,cat_obj) does not pass; finally conf += logsig[r] (evaluator.py:292).
+ * cand arrays hold K = (hier ? 3 : 1) entries per row, index r*K + k (layout 0) or k*n_rows + r (layout 1,
+ * the reference's per-call append order).  t3_conf[r] = max_k conf_k with only the overlap mask
+ * (Evaluator_Top3, no commonsense filter) + logsig; t3_super[r] = argmax(super_rel[r]).
+ */
+int hc_candidates(const float* relation, int64_t ld_rel, int32_t n_rows, int32_t n_geo, int32_t n_pos,
+                  int32_t n_sem, int32_t hier, const uint8_t* row_ov, const float* logsig, const float* conf_sub,
+                  const float* conf_obj, const int32_t* row_sub, const int32_t* row_obj, const int32_t* box_cat,
+                  const uint32_t* pass_bitmap, const float* super_rel, float* cand_conf, int32_t* cand_label,
+                  float* t3_conf, uint8_t* t3_super, int32_t layout, hc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * R10-R13 - per-image top-K selection under (confidence desc, candidate index asc), first-match scan of
+ * every GT triplet, integer hit / GT counters (evaluator.py:294-356 and :704-766).
+ * Image i owns candidates [cand_offsets[i], cand_offsets[i+1]) and GT slots [gt_offsets[i], gt_offsets[i+1]).
+ * Candidate c belongs to row cand_row[c] (NULL: c / K); a row's subject/object are entries row_sub/row_obj of
+ * the pred tables (pred_cat, pred_box[,4] = int xmin,xmax,ymin,ymax); GT slot g references gt tables the
+ * same way; gt_label == -1 slots are skipped.  synonyms NULL: exact category equality (PredCLS), else
+ * utils.compare_object_cat truth table [num_obj*num_obj].  zs_bitmap: zero-shot triplet set or NULL.
+ * mode 0: Evaluator counters (layout tables.EV_*, 408 slots), mode 1: Evaluator_Top3 (357 slots):
+ * one candidate per row (k_per_row == 1, cand_label unused), t3_labels [n_rows*3] holds the three per-head
+ * labels of each row (= hc_candidates' cand_label in layout 0) and t3_super its argmax super-category.
+ * topk_out (optional) [n_images, top_max] receives the selected candidate ids in rank order, -1 padded.
+ */
+int hc_topk_match(const int32_t* cand_offsets, int32_t n_images, const float* cand_conf,
+                  const int32_t* cand_label, const int32_t* cand_row, int32_t k_per_row, const int32_t* row_sub,
+                  const int32_t* row_obj, const int32_t* pred_cat, const int32_t* pred_box,
+                  const int32_t* gt_offsets, const int32_t* gt_label, const int32_t* gt_sub,
+                  const int32_t* gt_obj, const int32_t* gt_cat, const int32_t* gt_box, const uint8_t* synonyms,
+                  int32_t num_obj, int32_t num_pred, const uint32_t* zs_bitmap, int32_t feature_size,
+                  double iou_thresh, int32_t top_max, int32_t k0, int32_t k1, int32_t k2, int32_t mode,
+                  const int32_t* t3_labels, const uint8_t* t3_super, unsigned long long* counters,
+                  int32_t* topk_out, hc_stream_t stream);
+
+/* train_utils.py:169-183 side statistics over directed rows: stats[0..4] += num_not_connected, num_connected,
+ * num_connected_pred (sigmoid(conn) >= 0.5), connectivity_precision (#pred-connected rows whose undirected GT
+ * label != -1), connectivity_recall (sum round(sigmoid(conn)) over connected rows). */
+int hc_connectivity_stats(const float* connectivity, const int32_t* row_gt_directed,
+                          const int32_t* row_gt_undirected, int32_t n_rows, unsigned long long* stats,
+                          hc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIERCOM_B200_H_ */

@@ -1,0 +1,104 @@
+"""ctypes binding of libhiercom_b200.so (the C ABI in include/hiercom_b200.h).
+
+The library is built in-tree by `scene_graph_commonsense_b200.build`; it is the ONLY implementation of the hot path:
+if it is missing, or the device is not sm_100, calls raise - there is no CPU or PyTorch fallback.
+"""
+import ctypes as C
+import os
+
+import torch
+
+from . import build as _build
+
+HC_OK = 0
+ERRORS = {-1: "HC_E_SHAPE", -2: "HC_E_ALIGN", -3: "HC_E_ARCH", -4: "HC_E_CUDA", -5: "HC_E_NULL"}
+
+GEMM_PLAIN, GEMM_CONV3 = 0, 1
+EPI_BF16, EPI_F32, EPI_POOL_BF16 = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p),
+                ("m", C.c_int64), ("n", C.c_int64), ("k", C.c_int64),
+                ("lda", C.c_int64), ("ldc", C.c_int64), ("c_off", C.c_int64),
+                ("mode", C.c_int32), ("epilogue", C.c_int32), ("act", C.c_int32),
+                ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("c_total", C.c_int32), ("c_base", C.c_int32), ("c_in", C.c_int32),
+                ("group_m", C.c_int32), ("m_sub", C.c_int32)]
+
+
+_P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
+
+SIGNATURES = {
+    "hc_last_error": (C.c_char_p, []),
+    "hc_abi_version": (C.c_int, []),
+    "hc_device_check": (C.c_int, []),
+    "hc_cs_bitmap_build": (C.c_int, [_P, _I64, _P, _I64, _P]),
+    "hc_pairs_enumerate": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "hc_tc_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
+    "hc_pack_pixels": (C.c_int, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "hc_box_select": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
+    "hc_hier_head": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32,
+                               _F, _F, _F, _P, _P, _P, _P, _P, _P]),
+    "hc_candidates": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                _I32, _P]),
+    "hc_topk_match": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _I32,
+                                _D, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "hc_connectivity_stats": (C.c_int, [_P, _P, _P, _I32, _P, _P]),
+}
+
+_lib = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load(build_if_missing=False):
+    """Load (once) and return the ctypes library.  Raises if the shared object is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        if build_if_missing:
+            _build.build()
+        else:
+            raise RuntimeError("hiercom_b200: %s is missing - run `python -m scene_graph_commonsense_b200.build` "
+                               "(there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here means the .so does not export the ABI
+        fn.restype = res
+        fn.argtypes = args
+    if lib.hc_abi_version() != 1:
+        raise RuntimeError("hiercom_b200: ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != HC_OK:
+        msg = load().hc_last_error().decode("utf-8", "replace")
+        raise RuntimeError("hiercom_b200 %s failed: %s (%s)" % (what, ERRORS.get(rc, rc), msg))
+
+
+def ptr(t):
+    """Device (or host) pointer of a tensor / numpy array, None -> NULL."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return t.data_ptr() if t.numel() else None
+    return t.ctypes.data
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("hiercom_b200: all operands must be CUDA tensors - this path has no CPU implementation")

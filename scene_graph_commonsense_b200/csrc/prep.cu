@@ -1,0 +1,141 @@
+// HBM-bound layout / gather stages around the dense kernels (R3 and the conv2 split):
+//   pack_pixels     NCHW f32 maps -> pixel-major bf16 rows (A operand of the 1x1 convolutions)
+//   box_select      per-box masked conv1 activations without ever materialising feature*mask
+//   pair_relu_pool  relu(U[sub] + V[obj] + b) + 2x2 max-pool per directed pair
+// All three are pure streaming kernels: 16-byte vector accesses, channel index fastest so a warp touches
+// 512 contiguous bytes.
+#include "hc_common.cuh"
+
+namespace hc {
+
+__global__ void pack_pixels_kernel(const float* __restrict__ src0, int c0, const float* __restrict__ src1, int c1, int hw, int k_pad,
+                                   __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z;
+  const int p0 = blockIdx.x * 32, ch0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = ch0 + i, p = p0 + threadIdx.x;
+    float v = 0.0f;
+    if (p < hw) {
+      if (c < c0) v = src0[((size_t)img * c0 + c) * hw + p];
+      else if (c < c0 + c1) v = src1[((size_t)img * c1 + (c - c0)) * hw + p];
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int p = p0 + i, c = ch0 + threadIdx.x;
+    if (p < hw && c < k_pad) out[((size_t)img * hw + p) * k_pad + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+
+__global__ void box_select_kernel(const uint4* __restrict__ t_img, const int4* __restrict__ boxes, const int* __restrict__ box_img,
+                                  long long total_vec, int fs, int cvec, const uint4* __restrict__ fill, uint4* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    int x = (int)(pix % fs);
+    int y = (int)((pix / fs) % fs);
+    int box = (int)(pix / ((long long)fs * fs));
+    Rect r = rect_of(boxes[box], fs);
+    bool inside = x >= r.x0 && x < r.x1 && y >= r.y0 && y < r.y1;
+    out[i] = inside ? t_img[((long long)box_img[box] * fs * fs + (long long)y * fs + x) * cvec + cv] : fill[cv];
+  }
+}
+
+__device__ __forceinline__ void add8(float (&acc)[8], uint4 a, uint4 b, const float (&bias)[8]) {
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 fa = __bfloat1622float2(pa[k]), fb = __bfloat1622float2(pb[k]);
+    acc[2 * k] = fmaxf(acc[2 * k], fa.x + fb.x + bias[2 * k]);
+    acc[2 * k + 1] = fmaxf(acc[2 * k + 1], fa.y + fb.y + bias[2 * k + 1]);
+  }
+}
+
+__global__ void pair_relu_pool_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const float* __restrict__ bias,
+                                      const int* __restrict__ pair_sub, const int* __restrict__ pair_obj, long long total_vec, int fs,
+                                      int cvec, uint4* __restrict__ out) {
+  const int hp = fs / 2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    int cv = (int)(i % cvec);
+    long long pix = i / cvec;
+    int px = (int)(pix % hp);
+    int py = (int)((pix / hp) % hp);
+    int pr = (int)(pix / ((long long)hp * hp));
+    const long long su = (long long)pair_sub[pr] * fs * fs, so = (long long)pair_obj[pr] * fs * fs;
+    float b[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[k] = __ldg(bias + cv * 8 + k);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.0f;            // relu folded in: max(0, ...)
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        long long off = ((long long)(2 * py + dy) * fs + (2 * px + dx)) * cvec + cv;
+        add8(acc, __ldg(u + su * cvec + off), __ldg(v + so * cvec + off), b);
+      }
+    uint4 o;
+    __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) po[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
+    out[i] = o;
+  }
+}
+
+}  // namespace hc
+
+using namespace hc;
+
+static int stream_grid(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = (long long)num_sms() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+extern "C" int hc_pack_pixels(const float* src0, int32_t c0, const float* src1, int32_t c1, int32_t n_img, int32_t hw, int32_t k_pad,
+                              void* out_bf16, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(src0 && out_bf16, HC_E_NULL, "hc_pack_pixels: NULL pointer");
+  HC_REQUIRE(n_img > 0 && hw > 0 && c0 > 0 && c1 >= 0 && k_pad >= c0 + c1, HC_E_SHAPE, "hc_pack_pixels: bad sizes");
+  HC_REQUIRE(c1 == 0 || src1, HC_E_NULL, "hc_pack_pixels: src1 is NULL but c1 > 0");
+  HC_REQUIRE(n_img <= 65535, HC_E_SHAPE, "hc_pack_pixels: more than 65535 images per call");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  dim3 grid((hw + 31) / 32, (k_pad + 31) / 32, n_img), block(32, 8);
+  pack_pixels_kernel<<<grid, block, 0, stream>>>(src0, c0, src1, c1, hw, k_pad, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return cuda_status("hc_pack_pixels");
+}
+
+extern "C" int hc_box_select(const void* t_img, const int32_t* boxes, const int32_t* box_img, int32_t n_box, int32_t fs,
+                             int32_t channels, const void* fill, void* out, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(t_img && boxes && box_img && fill && out, HC_E_NULL, "hc_box_select: NULL pointer");
+  HC_REQUIRE(n_box > 0 && fs > 0 && channels > 0 && channels % 8 == 0, HC_E_SHAPE, "hc_box_select: channels must be a multiple of 8");
+  HC_REQUIRE(aligned16(t_img) && aligned16(boxes) && aligned16(fill) && aligned16(out), HC_E_ALIGN, "hc_box_select: 16-byte alignment");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  long long total = (long long)n_box * fs * fs * (channels / 8);
+  box_select_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(t_img),
+                                                                 reinterpret_cast<const int4*>(boxes), box_img, total, fs, channels / 8,
+                                                                 reinterpret_cast<const uint4*>(fill), reinterpret_cast<uint4*>(out));
+  return cuda_status("hc_box_select");
+}
+
+extern "C" int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub, const int32_t* pair_obj,
+                                 int32_t n_pairs, int32_t fs, int32_t channels, void* out, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(u && v && bias && pair_sub && pair_obj && out, HC_E_NULL, "hc_pair_relu_pool: NULL pointer");
+  HC_REQUIRE(n_pairs > 0 && fs > 0 && fs % 2 == 0 && channels % 8 == 0, HC_E_SHAPE, "hc_pair_relu_pool: bad sizes");
+  HC_REQUIRE(aligned16(u) && aligned16(v) && aligned16(out), HC_E_ALIGN, "hc_pair_relu_pool: 16-byte alignment");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  long long total = (long long)n_pairs * (fs / 2) * (fs / 2) * (channels / 8);
+  pair_relu_pool_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
+                                                                     bias, pair_sub, pair_obj, total, fs, channels / 8,
+                                                                     reinterpret_cast<uint4*>(out));
+  return cuda_status("hc_pair_relu_pool");
+}

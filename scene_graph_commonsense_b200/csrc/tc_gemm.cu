@@ -1,0 +1,504 @@
+// tcgen05 / TMEM / TMA dense contraction kernel for the relation head (sm_100a).
+//
+//   out[m,n] = epilogue( sum_k A[m,k] * B[n,k] ),  bf16 operands, fp32 accumulation in tensor memory.
+//
+// One persistent, warp-specialised kernel serves every dense stage of model.py:138-150,175:
+//   plain GEMM      (1x1 convolutions as pixel GEMMs, fc1, fc2; SGB post_cat)
+//   implicit conv   (3x3/pad 1 convolutions: the A tile of tap (ky,kx) is ONE 4-D TMA box of the NHWC
+//                    activation tensor shifted by (ky-1,kx-1); TMA zero-fills the padding halo, so no
+//                    im2col buffer ever exists)
+// CTA = 6 warps: warp 0 TMA producer, warp 1 tcgen05.mma issuer (+TMEM owner), warps 2-5 epilogue
+// (TMEM -> registers -> fused bias/activation/2x2-max-pool -> global).  Pipelines: smem full/empty ring
+// (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// CTA tile = (MS*128) x BN: MS 128-row sub-tiles share every B stage (halves L2->smem weight traffic for MS=2).
+#include <cuda.h>
+
+#include "hc_common.cuh"
+
+namespace hc {
+namespace tc {
+
+constexpr int BM = 128;          // UMMA M
+constexpr int BK = 64;           // K per pipeline stage: 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;
+constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
+
+template <int BN, int MS>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = MS * A_SUB_BYTES + B_BYTES;
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int ACC_COLS = MS * BN;
+  static constexpr int ACC_STAGES = TMEM_COLS / ACC_COLS;
+  static constexpr int BAR_BYTES = (2 * STAGES + 2 * ACC_STAGES) * 8 + 16;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static_assert(STAGES >= 2, "pipeline too shallow");
+  static_assert(ACC_STAGES >= 1, "accumulators do not fit TMEM");
+};
+
+struct Params {
+  int M, N, K;
+  int mode;                      // HC_GEMM_PLAIN / HC_GEMM_CONV3
+  int H, W, c_in, c_base;        // conv
+  int tiles_x, tiles_y;          // conv: spatial tiles per image (16 wide, 8*MS tall)
+  int tiles_m, tiles_n, group_m;
+  int epi, act;
+  long long ldc, c_off;
+  const float* bias;
+  void* out;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout [61,64))
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                 // leading byte offset (unused for swizzled K-major), canonical value
+  d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=BN
+template <int BN>
+__device__ __forceinline__ uint32_t umma_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == HC_ACT_RELU) return fmaxf(x, 0.0f);
+  if (act == HC_ACT_TANH) return tanhf(x);
+  return x;
+}
+
+// tile id -> (m block, n block): bands of `group_m` m-blocks; inside a band the n index is the slow one, so a
+// wave of consecutive tile ids shares few B column-panels and a bounded set of A row-panels through L2.
+__device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_blk, int& n_blk) {
+  int per_band = p.group_m * p.tiles_n;
+  int band = tile / per_band;
+  int in = tile - band * per_band;
+  int gm = min(p.group_m, p.tiles_m - band * p.group_m);
+  m_blk = band * p.group_m + in % gm;
+  n_blk = in / gm;
+}
+
+// =============================================================================================== kernel
+template <int BN, int MS>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using C = Cfg<BN, MS>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + C::ACC_STAGES + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 2 * C::ACC_STAGES);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < C::ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cblks = (p.mode == HC_GEMM_CONV3) ? p.c_in / BK : 1;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(p, tile, m_blk, n_blk);
+        int img = 0, y0 = 0, x0 = 0;
+        if (p.mode == HC_GEMM_CONV3) {
+          int per_img = p.tiles_x * p.tiles_y;
+          img = m_blk / per_img;
+          int r = m_blk - img * per_img;
+          y0 = (r / p.tiles_x) * (8 * MS);
+          x0 = (r % p.tiles_x) * 16;
+        }
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t b_dst = a_dst + MS * A_SUB_BYTES;
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if (p.mode == HC_GEMM_CONV3) {
+            int tap = kb / cblks, cb = kb - tap * cblks;
+            int ky = tap / 3, kx = tap - ky * 3;
+#pragma unroll
+            for (int j = 0; j < MS; ++j)
+              tma_load_4d(a_dst + j * A_SUB_BYTES, &tmap_a, full_bar(stage), p.c_base + cb * BK, x0 + kx - 1,
+                          y0 + 8 * j + ky - 1, img);
+          } else {
+#pragma unroll
+            for (int j = 0; j < MS; ++j)
+              tma_load_2d(a_dst + j * A_SUB_BYTES, &tmap_a, full_bar(stage), kb * BK, (m_blk * MS + j) * BM);
+          }
+          tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc<BN>();
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator stage
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);              // TMA bytes of this stage have landed
+          tc_fence_after();
+          const uint32_t a_src = smem_base + stage * C::STAGE_BYTES;
+          const uint64_t bdesc = umma_desc_sw128(a_src + MS * A_SUB_BYTES);
+#pragma unroll
+          for (int j = 0; j < MS; ++j) {
+            const uint64_t adesc = umma_desc_sw128(a_src + j * A_SUB_BYTES);
+            const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_COLS + j * BN);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)         // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
+              umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));                  // smem slot free once these MMAs retire
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 2..5
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int row_in_tile = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int m_blk, n_blk;
+      tile_coords(p, tile, m_blk, n_blk);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int n0 = n_blk * BN;
+#pragma unroll 1
+      for (int j = 0; j < MS; ++j) {
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + j * BN + ch * 32), r);
+          const int col0 = n0 + ch * 32;
+          if (p.epi == HC_EPI_POOL_BF16) {
+            // rows of a sub-tile are pixels (yl, xl) = (row/16, row%16); this warp holds yl in {2q, 2q+1}.
+            // 2x2 max-pool partners are lane^1 (x) and lane^16 (y): butterfly reduce-scatter, after which the
+            // lane with bits (ybit, xbit) owns the pooled maximum of columns [ybit*16 + xbit*8, +8).
+            const int ybit = (lane >> 4) & 1, xbit = lane & 1;
+            float h[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float mine = __uint_as_float(ybit ? r[16 + i] : r[i]);
+              float send = __uint_as_float(ybit ? r[i] : r[16 + i]);
+              h[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 16));
+            }
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float mine = xbit ? h[8 + i] : h[i];
+              float send = xbit ? h[i] : h[8 + i];
+              o[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 1));
+            }
+            const int cbase = col0 + ybit * 16 + xbit * 8;
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float a = fmaxf(o[2 * i] + __ldg(p.bias + cbase + 2 * i), 0.0f);
+              float b = fmaxf(o[2 * i + 1] + __ldg(p.bias + cbase + 2 * i + 1), 0.0f);
+              w[i] = pack_bf16(a, b);
+            }
+            int per_img = p.tiles_x * p.tiles_y;
+            int img = m_blk / per_img;
+            int rr = m_blk - img * per_img;
+            int py = ((rr / p.tiles_x) * (8 * MS) + 8 * j) / 2 + q;      // pooled row
+            int px = ((rr % p.tiles_x) * 16) / 2 + ((lane & 15) >> 1);   // pooled col
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                 (((long long)img * (p.H / 2) + py) * (p.W / 2) + px) * p.ldc + p.c_off + cbase;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+          } else {
+            long long row;
+            bool valid;
+            if (p.mode == HC_GEMM_CONV3) {
+              int per_img = p.tiles_x * p.tiles_y;
+              int img = m_blk / per_img;
+              int rr = m_blk - img * per_img;
+              int y = (rr / p.tiles_x) * (8 * MS) + 8 * j + (row_in_tile >> 4);
+              int x = (rr % p.tiles_x) * 16 + (row_in_tile & 15);
+              row = ((long long)img * p.H + y) * p.W + x;
+              valid = true;
+            } else {
+              row = (long long)(m_blk * MS + j) * BM + row_in_tile;
+              valid = row < p.M;
+            }
+            if (valid) {
+              if (p.epi == HC_EPI_F32) {
+                float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + p.c_off + col0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  float4 v;
+                  v.x = __uint_as_float(r[4 * i]); v.y = __uint_as_float(r[4 * i + 1]);
+                  v.z = __uint_as_float(r[4 * i + 2]); v.w = __uint_as_float(r[4 * i + 3]);
+                  if (p.bias) {
+                    v.x += __ldg(p.bias + col0 + 4 * i); v.y += __ldg(p.bias + col0 + 4 * i + 1);
+                    v.z += __ldg(p.bias + col0 + 4 * i + 2); v.w += __ldg(p.bias + col0 + 4 * i + 3);
+                  }
+                  *reinterpret_cast<float4*>(dst + 4 * i) = v;
+                }
+              } else {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + p.c_off + col0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  uint32_t w[4];
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    int c = 8 * i + 2 * t;
+                    float a = __uint_as_float(r[c]), b = __uint_as_float(r[c + 1]);
+                    if (p.bias) { a += __ldg(p.bias + col0 + c); b += __ldg(p.bias + col0 + c + 1); }
+                    w[t] = pack_bf16(apply_act(a, p.act), apply_act(b, p.act));
+                  }
+                  *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+  }
+}
+
+// =============================================================================================== host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                    const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(HC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_last_error, sizeof(g_last_error), "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    return HC_E_CUDA;
+  }
+  return HC_OK;
+}
+
+template <int BN, int MS>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+  using C = Cfg<BN, MS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+      return cuda_status("cudaFuncSetAttribute(tc_gemm_kernel)");
+    configured = true;
+  }
+  int tiles = p.tiles_m * p.tiles_n;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  tc_gemm_kernel<BN, MS><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  return cuda_status("tc_gemm_kernel launch");
+}
+
+}  // namespace tc
+}  // namespace hc
+
+using namespace hc;
+
+extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(d != nullptr, HC_E_NULL, "hc_tc_gemm: desc is NULL");
+  HC_REQUIRE(d->a && d->b && d->out, HC_E_NULL, "hc_tc_gemm: a/b/out must be non-NULL");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  HC_REQUIRE(d->m > 0 && d->n > 0 && d->k > 0, HC_E_SHAPE, "hc_tc_gemm: m,n,k must be positive");
+  HC_REQUIRE(d->k % tc::BK == 0, HC_E_SHAPE, "hc_tc_gemm: K must be a multiple of 64");
+  HC_REQUIRE(d->n % 128 == 0, HC_E_SHAPE, "hc_tc_gemm: N must be a multiple of 128");
+  HC_REQUIRE(aligned16(d->a) && aligned16(d->b) && aligned16(d->out), HC_E_ALIGN, "hc_tc_gemm: a/b/out must be 16-byte aligned");
+  HC_REQUIRE(d->ldc % 8 == 0 && d->c_off % 8 == 0, HC_E_ALIGN, "hc_tc_gemm: ldc and c_off must be multiples of 8");
+  HC_REQUIRE(d->epilogue >= 0 && d->epilogue <= 2, HC_E_SHAPE, "hc_tc_gemm: unknown epilogue");
+  HC_REQUIRE(d->epilogue != HC_EPI_POOL_BF16 || (d->mode == HC_GEMM_CONV3 && d->bias), HC_E_SHAPE,
+             "hc_tc_gemm: pooled epilogue needs conv mode and a bias");
+  HC_REQUIRE(d->m < (1ll << 31) && d->n < (1ll << 31) && d->k < (1ll << 31), HC_E_SHAPE, "hc_tc_gemm: dims exceed int32");
+
+  const int BN = (d->n % 256 == 0) ? 256 : 128;
+  int MS = d->m_sub ? d->m_sub : 1;
+  HC_REQUIRE(MS == 1 || MS == 2, HC_E_SHAPE, "hc_tc_gemm: m_sub must be 1 or 2");
+
+  tc::Params p;
+  memset(&p, 0, sizeof(p));
+  p.M = (int)d->m; p.N = (int)d->n; p.K = (int)d->k;
+  p.mode = d->mode; p.epi = d->epilogue; p.act = d->act;
+  p.ldc = d->ldc; p.c_off = d->c_off; p.bias = d->bias; p.out = d->out;
+  p.tiles_n = p.N / BN;
+
+  CUtensorMap ta, tb;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)d->k, (cuuint64_t)d->n};
+    cuuint64_t str[1] = {(cuuint64_t)d->k * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)BN};
+    rc = tc::make_map(&tb, d->b, 2, dims, str, box);
+    if (rc != HC_OK) return rc;
+  }
+  if (d->mode == HC_GEMM_CONV3) {
+    HC_REQUIRE(d->h > 0 && d->w > 0 && d->n_img > 0, HC_E_SHAPE, "hc_tc_gemm: conv needs n_img,h,w");
+    HC_REQUIRE(d->w % 16 == 0 && d->h % (8 * MS) == 0, HC_E_SHAPE, "hc_tc_gemm: conv H,W must be multiples of the 16x8 tile");
+    HC_REQUIRE(d->c_in % tc::BK == 0 && d->c_total % 8 == 0 && d->c_base % 8 == 0 && d->c_base + d->c_in <= d->c_total, HC_E_SHAPE,
+               "hc_tc_gemm: conv channel slice must be 64-aligned inside c_total");
+    HC_REQUIRE(d->k == 9ll * d->c_in, HC_E_SHAPE, "hc_tc_gemm: conv needs K == 9*c_in");
+    HC_REQUIRE(d->m == (int64_t)d->n_img * d->h * d->w, HC_E_SHAPE, "hc_tc_gemm: conv needs M == n_img*H*W");
+    HC_REQUIRE(d->epilogue != HC_EPI_POOL_BF16 || (d->h % 2 == 0 && d->w % 2 == 0), HC_E_SHAPE, "hc_tc_gemm: pooling needs even H,W");
+    p.H = d->h; p.W = d->w; p.c_in = d->c_in; p.c_base = d->c_base;
+    p.tiles_x = d->w / 16; p.tiles_y = d->h / (8 * MS);
+    p.tiles_m = d->n_img * p.tiles_x * p.tiles_y;
+    cuuint64_t dims[4] = {(cuuint64_t)d->c_total, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n_img};
+    cuuint64_t str[3] = {(cuuint64_t)d->c_total * 2, (cuuint64_t)d->w * d->c_total * 2, (cuuint64_t)d->h * d->w * d->c_total * 2};
+    cuuint32_t box[4] = {(cuuint32_t)tc::BK, 16, 8, 1};
+    rc = tc::make_map(&ta, d->a, 4, dims, str, box);
+    if (rc != HC_OK) return rc;
+  } else {
+    HC_REQUIRE(d->mode == HC_GEMM_PLAIN, HC_E_SHAPE, "hc_tc_gemm: unknown mode");
+    HC_REQUIRE(d->lda >= d->k && d->lda % 8 == 0, HC_E_ALIGN, "hc_tc_gemm: lda must be >= K and a multiple of 8");
+    p.tiles_m = (int)((d->m + tc::BM * MS - 1) / (tc::BM * MS));
+    cuuint64_t dims[2] = {(cuuint64_t)d->k, (cuuint64_t)d->m};
+    cuuint64_t str[1] = {(cuuint64_t)d->lda * 2};
+    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
+    rc = tc::make_map(&ta, d->a, 2, dims, str, box);
+    if (rc != HC_OK) return rc;
+  }
+  p.group_m = d->group_m > 0 ? d->group_m : 1;
+  if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
+
+  if (BN == 256 && MS == 1) return tc::launch<256, 1>(ta, tb, p, stream);
+  if (BN == 256 && MS == 2) return tc::launch<256, 2>(ta, tb, p, stream);
+  if (BN == 128 && MS == 1) return tc::launch<128, 1>(ta, tb, p, stream);
+  return tc::launch<128, 2>(ta, tb, p, stream);
+}

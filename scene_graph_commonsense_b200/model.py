@@ -1,0 +1,248 @@
+"""Drop-in twins of the reference's relation-head modules (reference model.py), backed by the sm_100a kernels.
+
+Same class names, constructor arguments, parameter names/shapes (so `load_state_dict(torch.load('HierRelationModel_*.pth'))`
+works, with or without DDP's `module.` prefix) and the same forward signature / return tuple:
+
+  BayesianRelationClassifier.forward(h_sub, h_obj, c1, c2, s1, s2, rank, h_sub_aug=None, h_obj_aug=None)
+      -> (relation_1 [B,G], relation_2 [B,P], relation_3 [B,S], super_relation [B,3], connectivity [B,1], pred [B,512], pred_aug)
+  FlatRelationClassifier.forward(...) -> (relation [B,50], connectivity [B,1], pred, pred_aug)        (model.py:94-102)
+  BayesianHead.forward(h) -> (relation_1, relation_2, relation_3, super_relation)                     (model.py:24-34)
+
+The nn.Conv2d / nn.Linear children are parameter containers only; forward never calls them.  Weights are re-packed
+once (bf16, GEMM-friendly layouts) into a `PackedHead`, lazily and again whenever a parameter changes.
+Inference only (eval-mode semantics: dropout is the identity); there is no CPU path.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, GEMM_CONV3, GEMM_PLAIN
+
+K1_PAD = 320      # 257 input channels of the 1x1 convolutions, zero padded to a multiple of 64
+HIDDEN = 512
+
+
+def strip_module_prefix(state_dict):
+    """utils.py:207-214 - checkpoints are saved from the DDP wrapper, keys carry a `module.` prefix."""
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+
+
+def supers_to_table(s_list, device):
+    """list of 1..4 super-class id tensors (utils.py:136-149 input format) -> int8 [n,4], -1 padded."""
+    out = torch.full((len(s_list), 4), -1, dtype=torch.int8)
+    for r, s in enumerate(s_list):
+        vals = [int(v) for v in (s.tolist() if hasattr(s, "tolist") else list(s))][:4]
+        for j, v in enumerate(vals):
+            out[r, j] = v
+    return out.to(device)
+
+
+class PackedHead:
+    """Device-resident, kernel-ready copies of the relation-head weights.
+
+    conv1_x [128,257,1,1]  -> w1 bf16 [256, 320] (rows 0-127 conv1_1, 128-255 conv1_2), b1 f32 [256], fill = tanh(b1) bf16
+    conv2_1 [512,256,3,3]  -> w2 bf16 [512, 9*256] (k = tap*256 + c); w2s / w2o bf16 [512, 9*128] subject / object halves
+    conv3_1 [1024,512,3,3] -> w3 bf16 [1024, 9*512]
+    fc1 [4096, 65536]      -> columns permuted from NCHW flatten (c*64 + y*8 + x) to pixel-major ((y*8+x)*1024 + c)
+    fc2 [512, 4096+L]      -> w_fc2 bf16 [512,4096]; emb f32 [L,512] = the label columns, transposed
+    heads                  -> w_heads f32 [G+P+S+1+3, 512] = [fc3_1; fc3_2; fc3_3; fc4; fc5] (flat: [fc3; fc4])
+    """
+
+    def __init__(self, sd, device, flat=False):
+        sd = strip_module_prefix(sd)
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("hiercom_b200: the relation head runs on CUDA only")
+        f32 = lambda t: t.detach().to(dev, torch.float32)
+        bf = lambda t: t.to(torch.bfloat16).contiguous()
+        c = sd["conv1_1.weight"].shape[0]
+        if c != 128 or sd["fc1.weight"].shape[1] != 65536:
+            raise RuntimeError("hiercom_b200: kernels are built for hidden_dim=128, feature_size=32 (config.yaml:30,35)")
+        w1 = torch.zeros(2 * c, K1_PAD, device=dev)
+        w1[:c, :2 * c + 1] = f32(sd["conv1_1.weight"]).view(c, -1)
+        w1[c:, :2 * c + 1] = f32(sd["conv1_2.weight"]).view(c, -1)
+        self.w1 = bf(w1)
+        self.b1 = torch.cat((f32(sd["conv1_1.bias"]), f32(sd["conv1_2.bias"]))).contiguous()
+        self.fill = bf(torch.tanh(self.b1))
+        w2 = f32(sd["conv2_1.weight"])                                   # [512, 256, 3, 3]
+        self.w2 = bf(w2.permute(0, 2, 3, 1).reshape(w2.shape[0], -1))
+        self.w2s = bf(w2[:, :c].permute(0, 2, 3, 1).reshape(w2.shape[0], -1))
+        self.w2o = bf(w2[:, c:].permute(0, 2, 3, 1).reshape(w2.shape[0], -1))
+        self.b2 = f32(sd["conv2_1.bias"]).contiguous()
+        w3 = f32(sd["conv3_1.weight"])
+        self.w3 = bf(w3.permute(0, 2, 3, 1).reshape(w3.shape[0], -1))
+        self.b3 = f32(sd["conv3_1.bias"]).contiguous()
+        wf = sd["fc1.weight"].detach().to(dev)                           # [4096, 1024*64] NCHW-flatten columns
+        self.w_fc1 = bf(wf.view(4096, 1024, 64).permute(0, 2, 1).reshape(4096, 65536))
+        del wf
+        self.b_fc1 = f32(sd["fc1.bias"]).contiguous()
+        w_fc2 = f32(sd["fc2.weight"])
+        self.w_fc2 = bf(w_fc2[:, :4096])
+        self.emb = w_fc2[:, 4096:].t().contiguous()                      # [L, 512]
+        self.has_super = self.emb.shape[0] > 300
+        self.b_fc2 = f32(sd["fc2.bias"]).contiguous()
+        self.flat = flat
+        if flat:
+            self.splits = (sd["fc3.weight"].shape[0], 0, 0)
+            heads = [sd["fc3.weight"], sd["fc4.weight"]]
+            biases = [sd["fc3.bias"], sd["fc4.bias"]]
+        else:
+            self.splits = tuple(sd["fc3_%d.weight" % k].shape[0] for k in (1, 2, 3))
+            heads = [sd["fc3_1.weight"], sd["fc3_2.weight"], sd["fc3_3.weight"], sd["fc4.weight"], sd["fc5.weight"]]
+            biases = [sd["fc3_1.bias"], sd["fc3_2.bias"], sd["fc3_3.bias"], sd["fc4.bias"], sd["fc5.bias"]]
+        self.w_heads = torch.cat([f32(w) for w in heads]).contiguous()
+        self.b_heads = torch.cat([f32(b) for b in biases]).contiguous()
+        self.device = dev
+
+    # ---------------------------------------------------------------------------- dense stages (model.py:138-150,175)
+    def conv3_fc(self, p2, m_sub=2):
+        """conv3_1+ReLU+pool -> fc1+ReLU -> fc2 (raw, fp32) on pooled conv2 activations p2 [n,16,16,512] bf16."""
+        n = p2.shape[0]
+        dev = p2.device
+        p3 = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev)
+        ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
+                    n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub)
+        h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=dev)
+        ops.tc_gemm(p3, self.w_fc1, h1, n, 4096, 65536, bias=self.b_fc1, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU,
+                    group_m=37, m_sub=2 if n > 128 else 1)
+        raw = torch.empty(n, HIDDEN, dtype=torch.float32, device=dev)
+        ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8)
+        return raw
+
+    def legacy_hidden(self, h_sub, h_obj):
+        """model.py:138-150 on pre-masked [bs,257,32,32] inputs -> fc2 pre-activation of the feature part [bs,512]."""
+        bs = h_sub.shape[0]
+        dev = h_sub.device
+        a = torch.empty(bs, 32, 32, 256, dtype=torch.bfloat16, device=dev)
+        for role, h in enumerate((h_sub, h_obj)):
+            x = ops.pack_pixels(h.to(torch.float32), None, K1_PAD)
+            ops.tc_gemm(x, self.w1[128 * role:128 * (role + 1)], a, bs * 1024, 128, K1_PAD, bias=self.b1[128 * role:128 * (role + 1)],
+                        lda=K1_PAD, ldc=256, c_off=128 * role, epilogue=EPI_BF16, act=ACT_TANH)
+        p2 = torch.empty(bs, 16, 16, 512, dtype=torch.bfloat16, device=dev)
+        ops.tc_gemm(a, self.w2, p2, bs * 1024, 512, 9 * 256, bias=self.b2, ldc=512, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
+                    n_img=bs, h=32, w=32, c_total=256, c_base=0, c_in=256, group_m=1, m_sub=2)
+        return self.conv3_fc(p2)
+
+    def heads(self, raw, row_sub, row_obj, box_cat, box_super, temps=(1.0, 1.0, 1.0), want_pred=False):
+        return ops.hier_head(raw, self.b_fc2, self.emb, row_sub, row_obj, box_cat, box_super if self.has_super else None,
+                             self.w_heads, self.b_heads, self.splits, flat=self.flat, temps=temps, want_pred=want_pred)
+
+
+class _HeadBase(nn.Module):
+    def _build_trunk(self, args, input_dim, feature_size, num_classes, num_super_classes):
+        self.input_dim = input_dim
+        self.num_classes = num_classes
+        self.num_super_classes = num_super_classes
+        self.conv1_1 = nn.Conv2d(2 * input_dim + 1, input_dim, kernel_size=1, stride=1, padding=0)
+        self.conv1_2 = nn.Conv2d(2 * input_dim + 1, input_dim, kernel_size=1, stride=1, padding=0)
+        self.conv2_1 = nn.Conv2d(2 * input_dim, 4 * input_dim, kernel_size=3, stride=1, padding=1)
+        self.conv3_1 = nn.Conv2d(4 * input_dim, 8 * input_dim, kernel_size=3, stride=1, padding=1)
+        self.dropout1 = nn.Dropout(p=0.5)
+        self.dropout2 = nn.Dropout(p=0.5)
+        self.maxpool = nn.MaxPool2d(kernel_size=2, stride=2)
+        self.fc1 = nn.Linear(8 * input_dim * (feature_size // 4) ** 2, 4096)
+        if args['dataset']['dataset'] == 'vg':
+            self.fc2 = nn.Linear(4096 + 2 * (num_classes + num_super_classes), 512)
+        else:
+            self.fc2 = nn.Linear(4096 + 2 * num_classes, 512)
+        self._packed = None
+        self._packed_versions = None
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._packed = None
+        return super().load_state_dict(strip_module_prefix(state_dict), strict=strict, **kw)
+
+    def packed(self):
+        """Kernel-ready weights; rebuilt when any parameter tensor has been modified or moved."""
+        versions = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed is None or versions != self._packed_versions:
+            dev = next(self.parameters()).device
+            self._packed = PackedHead(self.state_dict(), dev, flat=self._flat)
+            self._packed_versions = versions
+        return self._packed
+
+    def _legacy_forward(self, h_sub, h_obj, c1, c2, s1, s2):
+        pk = self.packed()
+        dev = h_sub.device
+        bs = h_sub.shape[0]
+        raw = pk.legacy_hidden(h_sub, h_obj)
+        box_cat = torch.stack((c1.to(dev, torch.int32), c2.to(dev, torch.int32)), dim=1).reshape(-1).contiguous()
+        box_super = None
+        if s1 is not None and pk.has_super:
+            box_super = torch.stack((supers_to_table(s1, dev), supers_to_table(s2, dev)), dim=1).reshape(-1, 4).contiguous()
+        elif pk.has_super:
+            box_super = torch.full((2 * bs, 4), -1, dtype=torch.int8, device=dev)
+        row_sub = torch.arange(0, 2 * bs, 2, dtype=torch.int32, device=dev)
+        row_obj = row_sub + 1
+        temps = (float(getattr(self, "T1", 1)), float(getattr(self, "T2", 1)), float(getattr(self, "T3", 1)))
+        return pk.heads(raw, row_sub, row_obj, box_cat, box_super, temps=temps, want_pred=True)
+
+
+class BayesianRelationClassifier(_HeadBase):
+    """reference model.py:105-186."""
+    _flat = False
+
+    def __init__(self, args, input_dim=128, feature_size=32, num_classes=150, num_super_classes=17, num_geometric=15,
+                 num_possessive=11, num_semantic=24, T1=1, T2=1, T3=1):
+        super().__init__()
+        self._build_trunk(args, input_dim, feature_size, num_classes, num_super_classes)
+        self.fc3_1 = nn.Linear(512, num_geometric)
+        self.fc3_2 = nn.Linear(512, num_possessive)
+        self.fc3_3 = nn.Linear(512, num_semantic)
+        self.fc4 = nn.Linear(512, 1)
+        self.fc5 = nn.Linear(512, 3)
+        self.T1, self.T2, self.T3 = T1, T2, T3
+
+    @torch.no_grad()
+    def forward(self, h_sub, h_obj, c1, c2, s1, s2, rank, h_sub_aug=None, h_obj_aug=None):
+        relation, sup, conn, _, pred = self._legacy_forward(h_sub, h_obj, c1, c2, s1, s2)
+        pred_aug = None
+        if h_sub_aug is not None:
+            pred_aug = self._legacy_forward(h_sub_aug, h_obj_aug, c1, c2, s1, s2)[4]
+        g, p = self.fc3_1.out_features, self.fc3_2.out_features
+        return relation[:, :g], relation[:, g:g + p], relation[:, g + p:], sup, conn.view(-1, 1), pred, pred_aug
+
+
+class FlatRelationClassifier(_HeadBase):
+    """reference model.py:37-102 (flat ablation)."""
+    _flat = True
+
+    def __init__(self, args, input_dim=128, output_dim=50, feature_size=32, num_classes=150, num_super_classes=17):
+        super().__init__()
+        self._build_trunk(args, input_dim, feature_size, num_classes, num_super_classes)
+        self.fc3 = nn.Linear(512, output_dim)
+        self.fc4 = nn.Linear(512, 1)
+
+    @torch.no_grad()
+    def forward(self, h_sub, h_obj, c1, c2, s1, s2, rank, h_sub_aug=None, h_obj_aug=None, one_hot=True):
+        relation, _, conn, _, pred = self._legacy_forward(h_sub, h_obj, c1, c2, s1, s2)
+        pred_aug = None
+        if h_sub_aug is not None:
+            pred_aug = self._legacy_forward(h_sub_aug, h_obj_aug, c1, c2, s1, s2)[4]
+        return relation, conn.view(-1, 1), pred, pred_aug
+
+
+class BayesianHead(nn.Module):
+    """reference model.py:9-34 - the hierarchical head alone (512 -> G/P/S/3)."""
+
+    def __init__(self, input_dim=512, num_geometric=15, num_possessive=11, num_semantic=24, T1=1, T2=1, T3=1):
+        super().__init__()
+        self.fc3_1 = nn.Linear(input_dim, num_geometric)
+        self.fc3_2 = nn.Linear(input_dim, num_possessive)
+        self.fc3_3 = nn.Linear(input_dim, num_semantic)
+        self.fc5 = nn.Linear(input_dim, 3)
+        self.T1, self.T2, self.T3 = T1, T2, T3
+
+    @torch.no_grad()
+    def forward(self, h):
+        if h.shape[1] != HIDDEN:
+            raise RuntimeError("hiercom_b200: BayesianHead kernels are built for input_dim=512")
+        dev = h.device
+        z = lambda *s: torch.zeros(*s, device=dev)
+        w = torch.cat((self.fc3_1.weight, self.fc3_2.weight, self.fc3_3.weight, z(1, HIDDEN), self.fc5.weight)).float().contiguous()
+        b = torch.cat((self.fc3_1.bias, self.fc3_2.bias, self.fc3_3.bias, z(1), self.fc5.bias)).float().contiguous()
+        splits = (self.fc3_1.out_features, self.fc3_2.out_features, self.fc3_3.out_features)
+        rel, sup, _, _, _ = ops.hier_head(h.float().contiguous(), None, None, None, None, None, None, w, b, splits,
+                                          temps=(float(self.T1), float(self.T2), float(self.T3)))
+        g, p = splits[0], splits[1]
+        return rel[:, :g], rel[:, g:g + p], rel[:, g + p:], sup

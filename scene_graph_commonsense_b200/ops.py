@@ -1,0 +1,172 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/hiercom_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every computation below is a hand-written sm_100a
+kernel reached through ctypes.  `LAUNCHES` counts kernel launches issued through this module (bench.py reports it).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, tables
+from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, GEMM_CONV3, GEMM_PLAIN, check, ptr,
+                   require_cuda, stream_ptr)
+
+LAUNCHES = {"n": 0}
+
+
+def _count(n=1):
+    LAUNCHES["n"] += n
+
+
+def cs_bitmap_build(aligned_keys, violated_keys):
+    """Host: packed key arrays -> uint32[BITMAP_WORDS] pass bitmap (numpy)."""
+    al = np.ascontiguousarray(np.asarray(aligned_keys, dtype=np.int64))
+    vi = np.ascontiguousarray(np.asarray(violated_keys, dtype=np.int64))
+    out = np.zeros(tables.BITMAP_WORDS, dtype=np.uint32)
+    check(_lib.load().hc_cs_bitmap_build(ptr(al) if al.size else None, al.size, ptr(vi) if vi.size else None, vi.size,
+                                         out.ctypes.data), "hc_cs_bitmap_build")
+    return out
+
+
+def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tri=None, group_id=None, n_groups=0,
+                    max_tri=0, feature_size=32):
+    """R1/R2/R4.  `p_max` = sum_i N_i(N_i-1) (host int, known from the CSR the caller built).  Returns a dict of
+    device arrays trimmed to the number of surviving directed pairs (one 4-byte D2H read of the total)."""
+    require_cuda(boxes, box_offsets, tri_offsets, rel_tri, dir_tri, group_id)
+    dev = boxes.device
+    n_images = box_offsets.numel() - 1
+    ws_ov = torch.empty(max(p_max // 2, 1), dtype=torch.uint8, device=dev)
+    ws_any = torch.empty(max(n_groups * max_tri, 1), dtype=torch.uint8, device=dev) if group_id is not None else None
+    ws_counts = torch.empty(n_images, dtype=torch.int32, device=dev)
+    pair_offsets = torch.empty(n_images + 1, dtype=torch.int32, device=dev)
+    i32 = lambda: torch.empty(max(p_max, 1), dtype=torch.int32, device=dev)
+    pair_sub, pair_obj, pair_img, pair_gt, pair_rel = i32(), i32(), i32(), i32(), i32()
+    pair_ov = torch.empty(max(p_max, 1), dtype=torch.uint8, device=dev)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(_lib.load().hc_pairs_enumerate(ptr(boxes), ptr(box_offsets), n_images, ptr(group_id), n_groups, max_tri,
+                                         ptr(rel_tri), ptr(dir_tri), ptr(tri_offsets), feature_size, ptr(ws_ov),
+                                         ptr(ws_any), ptr(ws_counts), ptr(pair_offsets), ptr(pair_sub), ptr(pair_obj),
+                                         ptr(pair_img), ptr(pair_ov), ptr(pair_gt), ptr(pair_rel), ptr(total),
+                                         stream_ptr()), "hc_pairs_enumerate")
+    _count(4)
+    n = int(total.item())
+    return dict(n=n, offsets=pair_offsets, sub=pair_sub[:n], obj=pair_obj[:n], img=pair_img[:n], ov=pair_ov[:n],
+                gt=pair_gt[:n], rel=pair_rel[:n])
+
+
+def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16,
+            act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0):
+    """out = epilogue(A @ B^T) on tcgen05 (see include/hiercom_b200.h hc_tc_gemm)."""
+    require_cuda(a, b, out, bias)
+    d = _lib.GemmDesc()
+    d.a, d.b, d.bias, d.out = ptr(a), ptr(b), ptr(bias), ptr(out)
+    d.m, d.n, d.k = m, n, k
+    d.lda, d.ldc, d.c_off = lda, (ldc if ldc is not None else n), c_off
+    d.mode, d.epilogue, d.act = mode, epilogue, act
+    d.n_img, d.h, d.w, d.c_total, d.c_base, d.c_in = n_img, h, w, c_total, c_base, c_in
+    d.group_m, d.m_sub = group_m, m_sub
+    check(_lib.load().hc_tc_gemm(C.byref(d), stream_ptr()), "hc_tc_gemm")
+    _count()
+    return out
+
+
+def pack_pixels(src0, src1, k_pad, out=None):
+    """[B,C0,H,W] (+[B,C1,H,W]) f32 -> [B*H*W, k_pad] bf16."""
+    require_cuda(src0, src1)
+    src0 = src0.contiguous()
+    b, c0 = src0.shape[0], src0.shape[1]
+    hw = src0.shape[2] * src0.shape[3]
+    c1 = 0
+    if src1 is not None:
+        src1 = src1.contiguous()
+        c1 = src1.shape[1]
+    if out is None:
+        out = torch.empty(b * hw, k_pad, dtype=torch.bfloat16, device=src0.device)
+    check(_lib.load().hc_pack_pixels(ptr(src0), c0, ptr(src1), c1, b, hw, k_pad, ptr(out), stream_ptr()), "hc_pack_pixels")
+    _count()
+    return out
+
+
+def box_select(t_img, boxes, box_img, fill, fs=32, out=None):
+    require_cuda(t_img, boxes, box_img, fill)
+    n_box, ch = boxes.shape[0], t_img.shape[-1]
+    if out is None:
+        out = torch.empty(n_box, fs, fs, ch, dtype=torch.bfloat16, device=t_img.device)
+    check(_lib.load().hc_box_select(ptr(t_img), ptr(boxes), ptr(box_img), n_box, fs, ch, ptr(fill), ptr(out), stream_ptr()),
+          "hc_box_select")
+    _count()
+    return out
+
+
+def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None):
+    require_cuda(u, v, bias, pair_sub, pair_obj)
+    n, ch = pair_sub.numel(), u.shape[-1]
+    if out is None:
+        out = torch.empty(n, fs // 2, fs // 2, ch, dtype=torch.bfloat16, device=u.device)
+    check(_lib.load().hc_pair_relu_pool(ptr(u), ptr(v), ptr(bias), ptr(pair_sub), ptr(pair_obj), n, fs, ch, ptr(out),
+                                        stream_ptr()), "hc_pair_relu_pool")
+    _count()
+    return out
+
+
+def hier_head(fc2_raw, fc2_bias, emb, row_sub, row_obj, box_cat, box_super, w_heads, b_heads, splits, flat=False,
+              temps=(1.0, 1.0, 1.0), num_obj=150, num_super=17, want_pred=False):
+    require_cuda(fc2_raw, fc2_bias, emb, row_sub, row_obj, box_cat, box_super, w_heads, b_heads)
+    n, hidden = fc2_raw.shape
+    dev = fc2_raw.device
+    r = sum(splits)
+    relation = torch.empty(n, r, dtype=torch.float32, device=dev)
+    sup = None if flat else torch.empty(n, 3, dtype=torch.float32, device=dev)
+    conn = torch.empty(n, dtype=torch.float32, device=dev)
+    logsig = torch.empty(n, dtype=torch.float32, device=dev)
+    pred = torch.empty(n, hidden, dtype=torch.float32, device=dev) if want_pred else None
+    check(_lib.load().hc_hier_head(ptr(fc2_raw), fc2_raw.stride(0), n, hidden, ptr(fc2_bias), ptr(emb), num_obj, num_super,
+                                   ptr(row_sub), ptr(row_obj), ptr(box_cat), ptr(box_super), ptr(w_heads), ptr(b_heads),
+                                   splits[0], splits[1], splits[2], int(flat), temps[0], temps[1], temps[2], ptr(relation),
+                                   ptr(sup), ptr(conn), ptr(logsig), ptr(pred), stream_ptr()), "hc_hier_head")
+    _count()
+    return relation, sup, conn, logsig, pred
+
+
+def candidates(relation, splits, hier, row_ov, logsig, row_sub, row_obj, box_cat, pass_bitmap=None, super_rel=None,
+               conf_sub=None, conf_obj=None, layout=0, want_top3=False):
+    require_cuda(relation, row_ov, logsig, row_sub, row_obj, box_cat, pass_bitmap, super_rel, conf_sub, conf_obj)
+    n = relation.shape[0]
+    dev = relation.device
+    k = 3 if hier else 1
+    cand_conf = torch.empty(n * k, dtype=torch.float32, device=dev)
+    cand_label = torch.empty(n * k, dtype=torch.int32, device=dev)
+    t3_conf = torch.empty(n, dtype=torch.float32, device=dev) if want_top3 else None
+    t3_super = torch.empty(n, dtype=torch.uint8, device=dev) if want_top3 else None
+    check(_lib.load().hc_candidates(ptr(relation), relation.stride(0), n, splits[0], splits[1], splits[2], int(hier),
+                                    ptr(row_ov), ptr(logsig), ptr(conf_sub), ptr(conf_obj), ptr(row_sub), ptr(row_obj),
+                                    ptr(box_cat), ptr(pass_bitmap), ptr(super_rel), ptr(cand_conf), ptr(cand_label),
+                                    ptr(t3_conf), ptr(t3_super), layout, stream_ptr()), "hc_candidates")
+    _count()
+    return cand_conf, cand_label, t3_conf, t3_super
+
+
+def topk_match(cand_offsets, cand_conf, cand_label, k_per_row, row_sub, row_obj, pred_cat, pred_box, gt_offsets, gt_label,
+               gt_sub, gt_obj, gt_cat, gt_box, counters, *, cand_row=None, synonyms=None, zs_bitmap=None, mode=0,
+               t3_labels=None, t3_super=None, feature_size=32, iou_thresh=0.5, top_k=tables.TOP_K, want_topk=False):
+    require_cuda(cand_offsets, cand_conf, cand_label, row_sub, row_obj, pred_cat, pred_box, gt_offsets, gt_label, gt_sub,
+                 gt_obj, gt_cat, gt_box, counters, cand_row, synonyms, zs_bitmap, t3_labels, t3_super)
+    n_images = cand_offsets.numel() - 1
+    top_max = int(top_k[-1])
+    topk_out = torch.empty(n_images, top_max, dtype=torch.int32, device=cand_conf.device) if want_topk else None
+    check(_lib.load().hc_topk_match(ptr(cand_offsets), n_images, ptr(cand_conf), ptr(cand_label), ptr(cand_row), k_per_row,
+                                    ptr(row_sub), ptr(row_obj), ptr(pred_cat), ptr(pred_box), ptr(gt_offsets), ptr(gt_label),
+                                    ptr(gt_sub), ptr(gt_obj), ptr(gt_cat), ptr(gt_box), ptr(synonyms), tables.NUM_OBJ,
+                                    tables.NUM_PRED, ptr(zs_bitmap), feature_size, float(iou_thresh), top_max, int(top_k[0]),
+                                    int(top_k[1]), int(top_k[2]), mode, ptr(t3_labels), ptr(t3_super), ptr(counters),
+                                    ptr(topk_out), stream_ptr()), "hc_topk_match")
+    _count()
+    return topk_out
+
+
+def connectivity_stats(connectivity, gt_directed, gt_undirected, stats):
+    require_cuda(connectivity, gt_directed, gt_undirected, stats)
+    check(_lib.load().hc_connectivity_stats(ptr(connectivity), ptr(gt_directed), ptr(gt_undirected), connectivity.numel(),
+                                            ptr(stats), stream_ptr()), "hc_connectivity_stats")
+    _count()

@@ -1,0 +1,271 @@
+"""Batched entry point of the relation path: whole images in, integer Recall counters out.
+
+Replaces the reference's per-(graph_iter, edge_iter, direction) host loop (evaluate.py:132-217: ~40 tiny launches and
+several host syncs per directed pair) with ~20 launches per *batch*:
+
+  pairs_enumerate                       R1 R2 R4   evaluate.py:111-116,132-156
+  pack_pixels -> conv1 GEMM (+tanh)     R5         model.py:139-140, once per IMAGE (1x1 conv commutes with the 0/1 mask)
+  box_select                            R3         train_test.py:391,398 (feature*mask never materialised)
+  conv2 subject/object half convs       R5         model.py:143, once per BOX (conv2_1 is linear before the ReLU)
+  per pair chunk: pair_relu_pool -> conv3+ReLU+pool -> fc1+ReLU -> fc2      model.py:143-150,175
+  hier_head                             R6 R7      model.py:152-168,176-184
+  candidates                            R8 R9      evaluator.py:157-179,231-266
+  topk_match (Evaluator, Evaluator_Top3)  R10-R13  evaluator.py:294-356,704-766
+  connectivity_stats                               train_utils.py:169-183
+
+Data layout in HBM: CSR over images (box_offsets, tri_offsets, pair offsets); activations NHWC bf16 so the channel
+index is the GEMM K index and a TMA box row; all counters int64 in one 765-slot vector (tables.EV_* / T3_*).
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import ops, tables
+from ._lib import ACT_NONE, ACT_TANH, EPI_BF16, GEMM_CONV3
+from .model import K1_PAD, PackedHead
+
+
+@dataclass
+class DeviceBatch:
+    """One evaluation window on the device.  Built from host samples by `from_samples` (pinned staging + async H2D)."""
+    feat: torch.Tensor            # f32 [B,256,32,32]
+    depth: torch.Tensor           # f32 [B,1,32,32]
+    boxes: torch.Tensor           # int32 [nbox,4] (xmin,xmax,ymin,ymax), truncated toward zero
+    box_offsets: torch.Tensor     # int32 [B+1]
+    box_img: torch.Tensor         # int32 [nbox]
+    cats: torch.Tensor            # int32 [nbox]
+    supers: torch.Tensor          # int8  [nbox,4]
+    tri_offsets: torch.Tensor     # int32 [B+1]
+    rel_tri: Optional[torch.Tensor]   # int32 [sum T_i]  relationships[g-1][e] at t = g(g-1)/2+e
+    dir_tri: Optional[torch.Tensor]   # int8  [sum T_i]  subj_or_obj[g-1][e]
+    group_id: Optional[torch.Tensor]  # int32 [B] lock-step batch of each image ("batch" skip mode) or None
+    n_groups: int
+    max_tri: int
+    p_max: int                    # sum_i N_i(N_i-1)
+    h2d_bytes: int
+    # SGDET/SGCLS extras
+    conf: Optional[torch.Tensor] = None        # f32 [nbox] object-label confidences
+    gt: Optional[dict] = None                  # flat GT triplet tables (targets.flat_targets_sgd)
+
+    @property
+    def n_images(self):
+        return self.box_offsets.numel() - 1
+
+
+def _stage(arr, device, pinned):
+    t = torch.from_numpy(np.ascontiguousarray(arr))
+    if pinned:
+        t = t.pin_memory()
+    return t.to(device, non_blocking=pinned), t.numel() * t.element_size()
+
+
+def batch_from_samples(samples, device, skip_mode="batch", group_size=None, sgdet=False, pinned=True, with_maps=True):
+    """Host lists (reference dataloader tuple shape, dataloader.py:159-165) -> DeviceBatch."""
+    n_img = len(samples)
+    boxes_l = [(s.bbox_pred if sgdet else s.bbox) for s in samples]
+    counts = np.array([b.shape[0] for b in boxes_l], dtype=np.int64)
+    box_offsets = np.concatenate(([0], np.cumsum(counts))).astype(np.int32)
+    tri = counts * (counts - 1) // 2
+    tri_offsets = np.concatenate(([0], np.cumsum(tri))).astype(np.int32)
+    boxes = np.concatenate([b.numpy() for b in boxes_l]).astype(np.int32)      # float -> int32 truncates toward zero == int()
+    cats_l = [(s.categories_pred if sgdet else s.categories) for s in samples]
+    cats = np.concatenate([c.numpy() for c in cats_l]).astype(np.int32)
+    sup_l = [(s.super_categories_pred if sgdet else s.super_categories) for s in samples]
+    supers = -np.ones((int(counts.sum()), 4), dtype=np.int8)
+    r = 0
+    for lst in sup_l:
+        for sc in lst:
+            v = np.asarray(sc, dtype=np.int64)[:4]
+            supers[r, :len(v)] = v
+            r += 1
+    box_img = np.repeat(np.arange(n_img, dtype=np.int32), counts)
+    total = 0
+    put = lambda a: _stage(a, device, pinned)
+    d = {}
+    for name, arr in (("boxes", boxes), ("box_offsets", box_offsets), ("box_img", box_img), ("cats", cats), ("supers", supers),
+                      ("tri_offsets", tri_offsets)):
+        d[name], nb = put(arr)
+        total += nb
+    rel_tri = dir_tri = None
+    if not sgdet:
+        rel = np.concatenate([np.concatenate([r_.numpy() for r_ in s.relationships]) if len(s.relationships) else np.zeros(0, np.int64)
+                              for s in samples]).astype(np.int32)
+        dr = np.concatenate([np.concatenate([r_.numpy() for r_ in s.subj_or_obj]) if len(s.subj_or_obj) else np.zeros(0, np.float32)
+                             for s in samples]).astype(np.int8)
+        rel_tri, nb = put(rel)
+        total += nb
+        dir_tri, nb = put(dr)
+        total += nb
+    group_id, n_groups = None, 0
+    if skip_mode == "batch":
+        gs = group_size or n_img
+        gid = (np.arange(n_img) // gs).astype(np.int32)
+        n_groups = int(gid.max()) + 1
+        group_id, nb = put(gid)
+        total += nb
+    elif skip_mode != "per_image":
+        raise ValueError("skip_mode must be 'batch' or 'per_image'")
+    if with_maps:
+        feat_h = torch.stack([s.feat for s in samples])
+        depth_h = torch.stack([s.depth for s in samples])
+        if pinned:
+            feat_h, depth_h = feat_h.pin_memory(), depth_h.pin_memory()
+        feat, depth = feat_h.to(device, non_blocking=pinned), depth_h.to(device, non_blocking=pinned)
+        total += feat_h.numel() * 4 + depth_h.numel() * 4
+    else:
+        feat = depth = None
+    b = DeviceBatch(feat, depth, d["boxes"], d["box_offsets"], d["box_img"], d["cats"], d["supers"], d["tri_offsets"], rel_tri,
+                    dir_tri, group_id, n_groups, int(tri.max()) if len(tri) else 0, int((counts * (counts - 1)).sum()), total)
+    if sgdet:
+        b.conf, nb = put(np.concatenate([s.cat_conf_pred.numpy() for s in samples]).astype(np.float32))
+        b.h2d_bytes += nb
+        from .targets import flat_targets_sgd
+        gt_host = flat_targets_sgd(samples)
+        b.gt = {}
+        for k, v in gt_host.items():
+            b.gt[k], nb = put(v)
+            b.h2d_bytes += nb
+    return b
+
+
+class RelationPipeline:
+    """pairs -> head -> candidates -> top-K -> counters for whole batches (the batched entry point of SURVEY §8b)."""
+
+    def __init__(self, packed: Optional[PackedHead], device, commonsense=True, aligned_keys=None, violated_keys=None,
+                 top_k=tables.TOP_K, iou_thresh=0.5, feature_size=32, chunk_pairs=16384, predcls=True, conv3_m_sub=2,
+                 hier=None, splits=None):
+        self.packed = packed
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("hiercom_b200: RelationPipeline needs a CUDA device (no CPU fallback)")
+        self.top_k = tuple(int(k) for k in top_k)
+        self.iou_thresh = float(iou_thresh)
+        self.fs = feature_size
+        self.chunk_pairs = int(chunk_pairs)
+        self.predcls = predcls
+        self.conv3_m_sub = conv3_m_sub
+        self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
+        self.hier = (not packed.flat if packed is not None else True) if hier is None else bool(hier)
+        self.pass_bitmap = None
+        if commonsense:
+            bm = ops.cs_bitmap_build(tables.commonsense_aligned_keys() if aligned_keys is None else aligned_keys,
+                                     tables.commonsense_violated_keys() if violated_keys is None else violated_keys)
+            self.pass_bitmap = torch.from_numpy(bm.view(np.int32)).to(self.device)
+        self.zs_bitmap = torch.from_numpy(tables.keys_to_bitmap(tables.zero_shot_keys()).view(np.int32)).to(self.device)
+        self.synonyms = None if predcls else torch.from_numpy(tables.object_synonym_matrix()).to(self.device)
+        self.counters = torch.zeros(tables.COUNTER_SIZE, dtype=torch.int64, device=self.device)
+        self.stats = torch.zeros(5, dtype=torch.int64, device=self.device)
+
+    # ------------------------------------------------------------------------------------------------ stages
+    def enumerate_pairs(self, b: DeviceBatch):
+        return ops.pairs_enumerate(b.boxes, b.box_offsets, b.tri_offsets, b.p_max, b.rel_tri, b.dir_tri, b.group_id, b.n_groups,
+                                   b.max_tri, self.fs)
+
+    def box_features(self, b: DeviceBatch):
+        """Per-image conv1 (+tanh), per-box mask select, per-box conv2 halves -> U, V [nbox,32,32,512] bf16."""
+        pk, fs = self.packed, self.fs
+        n_img, n_box = b.n_images, b.boxes.shape[0]
+        x = ops.pack_pixels(b.feat, b.depth, K1_PAD)
+        t = torch.empty(n_img * fs * fs, 256, dtype=torch.bfloat16, device=self.device)
+        ops.tc_gemm(x, pk.w1, t, n_img * fs * fs, 256, K1_PAD, bias=pk.b1, lda=K1_PAD, ldc=256, epilogue=EPI_BF16, act=ACT_TANH,
+                    group_m=8)
+        abox = ops.box_select(t, b.boxes, b.box_img, pk.fill, fs)
+        u = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=self.device)
+        v = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=self.device)
+        for out, w, base in ((u, pk.w2s, 0), (v, pk.w2o, 128)):
+            ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, ldc=512, mode=GEMM_CONV3, epilogue=EPI_BF16, act=ACT_NONE,
+                        n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=2)
+        return u, v
+
+    def forward_pairs(self, b: DeviceBatch, pairs):
+        """R3,R5-R7 for every directed pair of the batch -> (relation [P,R], super [P,3], connectivity [P], logsig [P])."""
+        pk = self.packed
+        n = pairs["n"]
+        u, v = self.box_features(b)
+        raw = torch.empty(n, 512, dtype=torch.float32, device=self.device)
+        for s in range(0, n, self.chunk_pairs):
+            e = min(n, s + self.chunk_pairs)
+            p2 = ops.pair_relu_pool(u, v, pk.b2, pairs["sub"][s:e], pairs["obj"][s:e], self.fs)
+            raw[s:e] = pk.conv3_fc(p2, m_sub=self.conv3_m_sub)
+            del p2
+        relation, sup, conn, logsig, _ = pk.heads(raw, pairs["sub"], pairs["obj"], b.cats, b.supers)
+        return relation, sup, conn, logsig
+
+    def evaluate(self, b: DeviceBatch, pairs, relation, sup, conn_logsig, connectivity=None, want_topk=False):
+        """R8-R13 on given scores (bit-exact stage: identical scores in -> identical counters out)."""
+        n = pairs["n"]
+        if n == 0:
+            return None
+        hier = self.hier
+        k = 3 if hier else 1
+        want_t3 = hier and self.predcls
+        cand_conf, cand_label, t3_conf, t3_super = ops.candidates(
+            relation, self.splits, hier, pairs["ov"], conn_logsig, pairs["sub"], pairs["obj"], b.cats, self.pass_bitmap, sup,
+            conf_sub=None if b.conf is None else b.conf[pairs["sub"].long()],
+            conf_obj=None if b.conf is None else b.conf[pairs["obj"].long()], want_top3=want_t3)
+        if self.predcls:
+            gt = dict(offsets=pairs["offsets"], label=pairs["gt"], sub=pairs["sub"], obj=pairs["obj"], cat=b.cats, box=b.boxes)
+        else:
+            gt = b.gt
+        cand_offsets = (pairs["offsets"] * k).contiguous()
+        ev = self.counters[:tables.EV_SIZE]
+        topk = ops.topk_match(cand_offsets, cand_conf, cand_label, k, pairs["sub"], pairs["obj"], b.cats, b.boxes, gt["offsets"],
+                              gt["label"], gt["sub"], gt["obj"], gt["cat"], gt["box"], ev, synonyms=self.synonyms,
+                              zs_bitmap=self.zs_bitmap, mode=0, feature_size=self.fs, iou_thresh=self.iou_thresh, top_k=self.top_k,
+                              want_topk=want_topk)
+        topk3 = None
+        if want_t3:
+            t3 = self.counters[tables.EV_SIZE:]
+            topk3 = ops.topk_match(pairs["offsets"], t3_conf, None, 1, pairs["sub"], pairs["obj"], b.cats, b.boxes, gt["offsets"],
+                                   gt["label"], gt["sub"], gt["obj"], gt["cat"], gt["box"], t3, mode=1, t3_labels=cand_label,
+                                   t3_super=t3_super, feature_size=self.fs, iou_thresh=self.iou_thresh, top_k=self.top_k,
+                                   want_topk=want_topk)
+        if connectivity is not None and self.predcls:
+            ops.connectivity_stats(connectivity, pairs["gt"], pairs["rel"], self.stats)
+        return dict(cand_conf=cand_conf, cand_label=cand_label, t3_conf=t3_conf, topk=topk, topk3=topk3)
+
+    def step(self, b: DeviceBatch):
+        """One pass of the hot path over one batch; returns the number of directed pairs processed."""
+        pairs = self.enumerate_pairs(b)
+        if pairs["n"] == 0:
+            return 0
+        relation, sup, conn, logsig = self.forward_pairs(b, pairs)
+        self.evaluate(b, pairs, relation, sup, logsig, connectivity=conn)
+        return pairs["n"]
+
+    # ------------------------------------------------------------------------------------------------ results
+    def reset(self):
+        self.counters.zero_()
+        self.stats.zero_()
+
+    def metrics(self, counters=None):
+        c = (self.counters if counters is None else counters).cpu().numpy()
+        return metrics_from_counters(c, self.top_k)
+
+
+def _recall_block(c, top_k):
+    """evaluator.py:358-365: R@k in Python floats, mR@k = float32 nanmean over predicates."""
+    nk = len(top_k)
+    hits = c[:nk].astype(np.float64)
+    hits_pc = c[nk:nk + nk * tables.NUM_PRED].reshape(nk, tables.NUM_PRED)
+    n = float(c[nk + nk * tables.NUM_PRED])
+    n_pc = c[nk + nk * tables.NUM_PRED + 1:nk + nk * tables.NUM_PRED + 1 + tables.NUM_PRED]
+    recall = [float(hits[i]) / max(n, 1e-3) for i in range(nk)]
+    per_class = [torch.as_tensor(hits_pc[i], dtype=torch.float32) / torch.as_tensor(n_pc, dtype=torch.float32) for i in range(nk)]
+    mean_recall = [torch.nanmean(r) for r in per_class]
+    return recall, per_class, mean_recall
+
+
+def metrics_from_counters(c, top_k=tables.TOP_K):
+    """765-slot int64 counter vector -> the reference's return tuples:
+    Evaluator.compute 6-tuple (evaluator.py:367) and Evaluator_Top3.compute 3-tuple (:773)."""
+    c = np.asarray(c, dtype=np.int64)
+    ev = _recall_block(c[:tables.EV_BLOCK], top_k) + _recall_block(c[tables.EV_BLOCK:tables.EV_SIZE], top_k)
+    t3c = c[tables.EV_SIZE:]
+    nk = len(top_k)
+    t3_block = np.concatenate((t3c[tables.T3_HITS:tables.T3_TOP1], t3c[tables.T3_NGT:tables.T3_SIZE]))
+    t3 = _recall_block(t3_block, top_k)
+    t3_top1 = np.concatenate((t3c[tables.T3_TOP1:tables.T3_NGT], t3c[tables.T3_NGT:tables.T3_SIZE]))
+    return dict(evaluator=ev, top3=t3, top3_top1=_recall_block(t3_top1, top_k))

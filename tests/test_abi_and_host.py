@@ -1,0 +1,172 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/hiercom_b200.h declares, the product never
+touches the oracle or a CPU fallback, and the host-side logic (tables, targets, metrics, sharding, gloo all-reduce)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hiercom_oracle as O
+from scene_graph_commonsense_b200 import _lib, build, synthetic, tables, targets
+from scene_graph_commonsense_b200 import dist as hdist
+from tests import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "hiercom_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(hc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    build.build()
+    lib = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+        assert n in _lib.SIGNATURES, "ctypes binding missing for " + n
+    assert lib.hc_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.library_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (hc_[a-z0-9_]+)", out))
+    assert exported == set(names)
+
+
+def test_library_is_sm100a_tcgen05_code():
+    build.build()
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.library_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic + " missing: the dense kernel is not on the tcgen05/TMA path"
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    lib = _lib.load()
+    assert lib.hc_device_check() == -4
+    assert b"no CPU fallback" in lib.hc_last_error()
+    from scene_graph_commonsense_b200 import ops, pipeline
+    with pytest.raises(RuntimeError):
+        ops.tc_gemm(torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(128, 64, dtype=torch.bfloat16), torch.zeros(128, 128), 128, 128, 64, lda=64)
+    with pytest.raises(RuntimeError):
+        pipeline.RelationPipeline(None, "cpu")
+
+
+def test_product_never_imports_the_oracle_or_reference():
+    pkg = os.path.join(ROOT, "scene_graph_commonsense_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+                assert "hiercom_oracle" not in src, f
+                assert "/root/reference" not in src or f == "convert_reference_data.py", f
+
+
+def test_bitmap_build_matches_numpy_and_dict_semantics():
+    from scene_graph_commonsense_b200 import ops
+    al, vi = tables.commonsense_aligned_keys(), tables.commonsense_violated_keys()
+    assert len(al) == 20884 and len(vi) == 1524 and len(np.intersect1d(al, vi)) == 403
+    bm = ops.cs_bitmap_build(al, vi)
+    np.testing.assert_array_equal(bm, tables.commonsense_pass_bitmap())
+    passing = set(al.tolist()) - set(vi.tolist())
+    bits = np.unpackbits(bm.view(np.uint8), bitorder="little")
+    assert int(bits.sum()) == len(passing)
+    rng = np.random.default_rng(0)
+    for k in rng.integers(0, tables.TRIPLET_SPACE, 2000):
+        assert bool(bits[k]) == (int(k) in passing)
+    with pytest.raises(RuntimeError, match="HC_E_SHAPE"):
+        ops.cs_bitmap_build(np.array([tables.TRIPLET_SPACE]), np.zeros(0, np.int64))
+    assert len(tables.zero_shot_keys()) == 4314
+    assert len(np.intersect1d(tables.zero_shot_keys(), tables.train_triplet_keys())) == 0   # evaluator.py:342 assert
+
+
+def test_flat_targets_sgd_matches_oracle_restatement():
+    batch = [synthetic.make_sgdet_image(i, a, b, p_rel=pr, with_maps=False) for i, a, b, pr in ((1, 6, 9, 0.5), (2, 2, 5, 0.0), (3, 9, 12, 0.7))]
+    got = targets.flat_targets_sgd(batch)
+    rel, cs, co, bs_, bo_ = O.match_target_sgd(batch)
+    base = np.concatenate(([0], np.cumsum([len(s.categories) for s in batch])))
+    for i in range(3):
+        seg = slice(got["offsets"][i], got["offsets"][i + 1])
+        if rel[i] is None:
+            assert seg.start == seg.stop
+            continue
+        np.testing.assert_array_equal(got["label"][seg], rel[i])
+        np.testing.assert_array_equal(got["cat"][got["sub"][seg]], cs[i])
+        np.testing.assert_array_equal(got["cat"][got["obj"][seg]], co[i])
+        np.testing.assert_array_equal(got["box"][got["sub"][seg]], bs_[i])
+        np.testing.assert_array_equal(got["box"][got["obj"][seg]], bo_[i])
+        assert (got["sub"][seg] >= base[i]).all() and (got["sub"][seg] < base[i + 1]).all()
+
+
+def test_metrics_from_counters_matches_oracle_float_ops():
+    from scene_graph_commonsense_b200 import pipeline
+    case = dict(ids=[10, 11, 12], n=[9, 12, 7], run_mode="eval", hierar=True, kw=dict(gain=3.0))
+    ev, t3, m, m3, _, _ = helpers.replay_predcls_case(case)
+    c = np.concatenate((ev.counters(), t3.counters()))
+    got = pipeline.metrics_from_counters(c)
+    np.testing.assert_array_equal(helpers.flat_metrics(got["evaluator"]), helpers.flat_metrics(m))
+    np.testing.assert_array_equal(helpers.flat_metrics(got["top3"]), helpers.flat_metrics(m3))
+
+
+def test_synthetic_inputs_are_deterministic_per_image_id():
+    a = synthetic.make_batch([5, 6, 7], [6, 4, 9], base_seed=3)
+    b = synthetic.make_batch([7, 5], [9, 6], base_seed=3)
+    assert torch.equal(a[2].feat, b[0].feat) and torch.equal(a[0].bbox, b[1].bbox)
+    assert all(torch.equal(x, y) for x, y in zip(a[2].relationships, b[0].relationships))
+    assert a[0].bbox.dtype == torch.int32 and int(a[0].bbox.max()) <= 32 and int(a[0].bbox.min()) >= 0
+    area = (a[2].bbox[:, 1] - a[2].bbox[:, 0]) * (a[2].bbox[:, 3] - a[2].bbox[:, 2])
+    assert (area[:-1] >= area[1:]).all()                            # area-descending like dataset_utils.py:117
+    sd1, sd2 = synthetic.head_state_dict(seed=1, input_dim=16, feature_size=8), synthetic.head_state_dict(seed=1, input_dim=16, feature_size=8)
+    assert all(torch.equal(sd1[k], sd2[k]) for k in sd1)
+
+
+def test_sharding_is_round_robin_and_covers_every_image():
+    ids = list(range(23))
+    shards = [hdist.shard_image_ids(ids, r, 4) for r in range(4)]
+    assert sorted(sum(shards, [])) == ids and shards[1][:3] == [1, 5, 9]
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+from scene_graph_commonsense_b200 import dist as hdist, synthetic, tables
+from tests import helpers
+rank, local, world = hdist.init_from_env(backend="gloo")
+ids = list(range(400, 410)); ns = [6, 9, 4, 12, 7, 10, 3, 8, 11, 5]
+mine = hdist.shard_image_ids(list(zip(ids, ns)), rank, world)
+case = dict(ids=[i for i, _ in mine], n=[n for _, n in mine], run_mode="eval_cs", hierar=True, kw=dict(gain=3.0), cs=(2, 0.5, 0.1),
+            windows=[[j] for j in range(len(mine))])
+ev, t3, *_ = helpers.replay_predcls_case(case)
+c = torch.from_numpy(np.concatenate((ev.counters(), t3.counters())))
+hdist.allreduce_counters(c)
+t = hdist.max_over_ranks(float(rank + 1), "cpu")
+if rank == 0:
+    np.save(os.environ["OUT"], c.numpy()); assert t == float(world)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharded_counts_equal_single_process(tmp_path):
+    """World-size-2 `gloo` run of the N>1 host path: shard images round-robin, per-image skip mode, one integer
+    all-reduce -> identical counters (hence identical R@K / mR@K) to the single-process run."""
+    out = str(tmp_path / "c.npy")
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER % dict(root=ROOT))
+    env = dict(os.environ, OUT=out, OMP_NUM_THREADS="2")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29631", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ids = list(range(400, 410)); ns = [6, 9, 4, 12, 7, 10, 3, 8, 11, 5]
+    case = dict(ids=ids, n=ns, run_mode="eval_cs", hierar=True, kw=dict(gain=3.0), cs=(2, 0.5, 0.1), windows=[[j] for j in range(10)])
+    ev, t3, *_ = helpers.replay_predcls_case(case)
+    single = np.concatenate((ev.counters(), t3.counters()))
+    np.testing.assert_array_equal(np.load(out), single)
+    assert single[tables.EV_NGT] > 0
