@@ -282,6 +282,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           uint32_t r[32];
+          __syncwarp();                                    // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + j * BN + ch * 32), r);
           const int col0 = n0 + ch * 32;
           if (p.epi == HC_EPI_POOL_BF16) {

@@ -101,12 +101,12 @@ class PackedHead:
         dev = p2.device
         p3 = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev)
         ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
-                    n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub)
+                    n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag="conv3")
         h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=dev)
         ops.tc_gemm(p3, self.w_fc1, h1, n, 4096, 65536, bias=self.b_fc1, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU,
-                    group_m=37, m_sub=2 if n > 128 else 1)
+                    group_m=37, m_sub=2 if n > 128 else 1, tag="fc1")
         raw = torch.empty(n, HIDDEN, dtype=torch.float32, device=dev)
-        ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8)
+        ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8, tag="fc2")
         return raw
 
     def legacy_hidden(self, h_sub, h_obj):

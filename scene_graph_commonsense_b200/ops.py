@@ -13,10 +13,31 @@ from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF1
                    require_cuda, stream_ptr)
 
 LAUNCHES = {"n": 0}
+PROFILE = {"on": False, "events": []}     # bench.py: CUDA-event timing of tagged launches on the launching stream
 
 
 def _count(n=1):
     LAUNCHES["n"] += n
+
+
+class _timed:
+    """Brackets one launch with CUDA events on the current stream when PROFILE['on'] (no host sync)."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if PROFILE["on"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE["on"]:
+            self.e1.record()
+            PROFILE["events"].append((self.tag, self.e0, self.e1))
+        return False
 
 
 def cs_bitmap_build(aligned_keys, violated_keys):
@@ -56,7 +77,7 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 
 
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16,
-            act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0):
+            act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm"):
     """out = epilogue(A @ B^T) on tcgen05 (see include/hiercom_b200.h hc_tc_gemm)."""
     require_cuda(a, b, out, bias)
     d = _lib.GemmDesc()
@@ -66,7 +87,8 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     d.mode, d.epilogue, d.act = mode, epilogue, act
     d.n_img, d.h, d.w, d.c_total, d.c_base, d.c_in = n_img, h, w, c_total, c_base, c_in
     d.group_m, d.m_sub = group_m, m_sub
-    check(_lib.load().hc_tc_gemm(C.byref(d), stream_ptr()), "hc_tc_gemm")
+    with _timed(tag):
+        check(_lib.load().hc_tc_gemm(C.byref(d), stream_ptr()), "hc_tc_gemm")
     _count()
     return out
 

@@ -54,24 +54,45 @@ class DeviceBatch:
         return self.box_offsets.numel() - 1
 
 
-def _stage(arr, device, pinned):
-    t = torch.from_numpy(np.ascontiguousarray(arr))
-    if pinned:
-        t = t.pin_memory()
-    return t.to(device, non_blocking=pinned), t.numel() * t.element_size()
+class HostBatch:
+    """Pinned host staging of one evaluation window (what a data loader hands over): numpy/torch CPU buffers only.
+    `to_device` issues the async H2D copies; `h2d_bytes` is the exact number of bytes they move."""
+
+    def __init__(self, arrays, meta, pinned=True):
+        self.meta = meta
+        self.t = {}
+        for k, v in arrays.items():
+            if v is None:
+                self.t[k] = None
+                continue
+            t = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(v))
+            self.t[k] = t.pin_memory() if pinned else t
+        self.pinned = pinned
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.t.values() if t is not None)
+
+    def to_device(self, device):
+        d = {k: (None if t is None else t.to(device, non_blocking=self.pinned)) for k, t in self.t.items()}
+        m = self.meta
+        gt = None
+        if d.get("gt_offsets") is not None:
+            gt = dict(offsets=d["gt_offsets"], label=d["gt_label"], sub=d["gt_sub"], obj=d["gt_obj"], cat=d["gt_cat"], box=d["gt_box"])
+        return DeviceBatch(d.get("feat"), d.get("depth"), d["boxes"], d["box_offsets"], d["box_img"], d["cats"], d["supers"],
+                           d["tri_offsets"], d.get("rel_tri"), d.get("dir_tri"), d.get("group_id"), m["n_groups"], m["max_tri"],
+                           m["p_max"], self.h2d_bytes, conf=d.get("conf"), gt=gt)
 
 
-def batch_from_samples(samples, device, skip_mode="batch", group_size=None, sgdet=False, pinned=True, with_maps=True):
-    """Host lists (reference dataloader tuple shape, dataloader.py:159-165) -> DeviceBatch."""
+def host_batch_from_samples(samples, skip_mode="batch", group_size=None, sgdet=False, pinned=True, with_maps=True):
+    """Host lists (reference dataloader tuple shape, dataloader.py:159-165) -> HostBatch (CSR packing, no device work)."""
     n_img = len(samples)
     boxes_l = [(s.bbox_pred if sgdet else s.bbox) for s in samples]
     counts = np.array([b.shape[0] for b in boxes_l], dtype=np.int64)
-    box_offsets = np.concatenate(([0], np.cumsum(counts))).astype(np.int32)
     tri = counts * (counts - 1) // 2
-    tri_offsets = np.concatenate(([0], np.cumsum(tri))).astype(np.int32)
-    boxes = np.concatenate([b.numpy() for b in boxes_l]).astype(np.int32)      # float -> int32 truncates toward zero == int()
+    arrays = {}
+    arrays["box_offsets"] = np.concatenate(([0], np.cumsum(counts))).astype(np.int32)
+    arrays["tri_offsets"] = np.concatenate(([0], np.cumsum(tri))).astype(np.int32)
+    arrays["boxes"] = np.concatenate([b.numpy() for b in boxes_l]).astype(np.int32)   # float -> int32 truncates toward zero == int()
     cats_l = [(s.categories_pred if sgdet else s.categories) for s in samples]
-    cats = np.concatenate([c.numpy() for c in cats_l]).astype(np.int32)
+    arrays["cats"] = np.concatenate([c.numpy() for c in cats_l]).astype(np.int32)
     sup_l = [(s.super_categories_pred if sgdet else s.super_categories) for s in samples]
     supers = -np.ones((int(counts.sum()), 4), dtype=np.int8)
     r = 0
@@ -80,54 +101,35 @@ def batch_from_samples(samples, device, skip_mode="batch", group_size=None, sgde
             v = np.asarray(sc, dtype=np.int64)[:4]
             supers[r, :len(v)] = v
             r += 1
-    box_img = np.repeat(np.arange(n_img, dtype=np.int32), counts)
-    total = 0
-    put = lambda a: _stage(a, device, pinned)
-    d = {}
-    for name, arr in (("boxes", boxes), ("box_offsets", box_offsets), ("box_img", box_img), ("cats", cats), ("supers", supers),
-                      ("tri_offsets", tri_offsets)):
-        d[name], nb = put(arr)
-        total += nb
-    rel_tri = dir_tri = None
+    arrays["supers"] = supers
+    arrays["box_img"] = np.repeat(np.arange(n_img, dtype=np.int32), counts)
     if not sgdet:
-        rel = np.concatenate([np.concatenate([r_.numpy() for r_ in s.relationships]) if len(s.relationships) else np.zeros(0, np.int64)
-                              for s in samples]).astype(np.int32)
-        dr = np.concatenate([np.concatenate([r_.numpy() for r_ in s.subj_or_obj]) if len(s.subj_or_obj) else np.zeros(0, np.float32)
-                             for s in samples]).astype(np.int8)
-        rel_tri, nb = put(rel)
-        total += nb
-        dir_tri, nb = put(dr)
-        total += nb
-    group_id, n_groups = None, 0
+        arrays["rel_tri"] = np.concatenate([np.concatenate([r_.numpy() for r_ in s.relationships]) if len(s.relationships)
+                                            else np.zeros(0, np.int64) for s in samples]).astype(np.int32)
+        arrays["dir_tri"] = np.concatenate([np.concatenate([r_.numpy() for r_ in s.subj_or_obj]) if len(s.subj_or_obj)
+                                            else np.zeros(0, np.float32) for s in samples]).astype(np.int8)
+    n_groups = 0
     if skip_mode == "batch":
         gs = group_size or n_img
         gid = (np.arange(n_img) // gs).astype(np.int32)
         n_groups = int(gid.max()) + 1
-        group_id, nb = put(gid)
-        total += nb
+        arrays["group_id"] = gid
     elif skip_mode != "per_image":
         raise ValueError("skip_mode must be 'batch' or 'per_image'")
     if with_maps:
-        feat_h = torch.stack([s.feat for s in samples])
-        depth_h = torch.stack([s.depth for s in samples])
-        if pinned:
-            feat_h, depth_h = feat_h.pin_memory(), depth_h.pin_memory()
-        feat, depth = feat_h.to(device, non_blocking=pinned), depth_h.to(device, non_blocking=pinned)
-        total += feat_h.numel() * 4 + depth_h.numel() * 4
-    else:
-        feat = depth = None
-    b = DeviceBatch(feat, depth, d["boxes"], d["box_offsets"], d["box_img"], d["cats"], d["supers"], d["tri_offsets"], rel_tri,
-                    dir_tri, group_id, n_groups, int(tri.max()) if len(tri) else 0, int((counts * (counts - 1)).sum()), total)
+        arrays["feat"] = torch.stack([s.feat for s in samples])
+        arrays["depth"] = torch.stack([s.depth for s in samples])
     if sgdet:
-        b.conf, nb = put(np.concatenate([s.cat_conf_pred.numpy() for s in samples]).astype(np.float32))
-        b.h2d_bytes += nb
+        arrays["conf"] = np.concatenate([s.cat_conf_pred.numpy() for s in samples]).astype(np.float32)
         from .targets import flat_targets_sgd
-        gt_host = flat_targets_sgd(samples)
-        b.gt = {}
-        for k, v in gt_host.items():
-            b.gt[k], nb = put(v)
-            b.h2d_bytes += nb
-    return b
+        for k, v in flat_targets_sgd(samples).items():
+            arrays["gt_" + k] = v
+    meta = dict(n_groups=n_groups, max_tri=int(tri.max()) if len(tri) else 0, p_max=int((counts * (counts - 1)).sum()))
+    return HostBatch(arrays, meta, pinned)
+
+
+def batch_from_samples(samples, device, skip_mode="batch", group_size=None, sgdet=False, pinned=True, with_maps=True):
+    return host_batch_from_samples(samples, skip_mode, group_size, sgdet, pinned, with_maps).to_device(device)
 
 
 class RelationPipeline:
@@ -170,13 +172,13 @@ class RelationPipeline:
         x = ops.pack_pixels(b.feat, b.depth, K1_PAD)
         t = torch.empty(n_img * fs * fs, 256, dtype=torch.bfloat16, device=self.device)
         ops.tc_gemm(x, pk.w1, t, n_img * fs * fs, 256, K1_PAD, bias=pk.b1, lda=K1_PAD, ldc=256, epilogue=EPI_BF16, act=ACT_TANH,
-                    group_m=8)
+                    group_m=8, tag="conv1")
         abox = ops.box_select(t, b.boxes, b.box_img, pk.fill, fs)
         u = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=self.device)
         v = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=self.device)
         for out, w, base in ((u, pk.w2s, 0), (v, pk.w2o, 128)):
             ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, ldc=512, mode=GEMM_CONV3, epilogue=EPI_BF16, act=ACT_NONE,
-                        n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=2)
+                        n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=2, tag="conv2_half")
         return u, v
 
     def forward_pairs(self, b: DeviceBatch, pairs):
