@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -160,7 +160,8 @@ def run_ours(args):
     sd = synthetic.head_state_dict(seed=0, logit_gain=40.0)
     packed = model.PackedHead(sd, dev)
     del sd
-    pipe = pipeline.RelationPipeline(packed, dev, commonsense=True, chunk_pairs=args.chunk_pairs, conv3_m_sub=args.conv3_m_sub)
+    pipe = pipeline.RelationPipeline(packed, dev, commonsense=True, chunk_pairs=args.chunk_pairs, conv3_m_sub=args.conv3_m_sub,
+                                     overlap=not args.no_overlap)
     samples = make_samples(rank)
     host = pipeline.host_batch_from_samples(samples, skip_mode="batch")
     del samples
@@ -268,7 +269,8 @@ def run_ours(args):
                                "reference batch skip rule" % (IMAGES_PER_GPU, BOXES, pairs_step),
                    "parallelism": "images sharded over %d GPU(s), one int64[765] all-reduce per step" % world,
                    "l2": "no explicit flush: each step streams >10 GB of activations/weights (>> 126 MB L2)",
-                   "weights": "random init, trained-scale logits (seed 0)", "chunk_pairs": args.chunk_pairs},
+                   "weights": "random init, trained-scale logits (seed 0)", "chunk_pairs": args.chunk_pairs,
+                   "pool_gemm_overlap": not args.no_overlap, "conv3_m_sub": args.conv3_m_sub},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes * world,
                 "d2h_bytes_per_step": (tables.COUNTER_SIZE * 8 + 4) * world, "ms_per_step": t_e2e / args.steps * 1e3},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof,
@@ -283,12 +285,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk-pairs", type=int, default=16384)
     ap.add_argument("--conv3-m-sub", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -129,6 +129,18 @@ int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int
                       const int32_t* pair_obj, int32_t n_pairs, int32_t fs, int32_t channels, void* out,
                       hc_stream_t stream);
 
+/* Same stage for pair lists produced by hc_pairs_enumerate, tiled as an outer sum over the boxes of an image: a
+ * thread block keeps the U tiles of 4 subject boxes in registers and streams every object box's V tile once, so
+ * reads per pair drop from 2 MiB to ~0.3 MiB.  lut [n_box, n_max] int32 maps (subject box, local object index) to
+ * the directed pair index (-1 = pair skipped); built by hc_pair_lut_build.  Processes images [img0, img0+n_img)
+ * and writes out[p - pair_base] for pair_base <= p < pair_base + chunk_pairs. */
+int hc_pair_lut_build(const int32_t* pair_sub, const int32_t* pair_obj, const int32_t* pair_img,
+                      const int32_t* box_offsets, int32_t n_pairs, int32_t n_box, int32_t n_max, int32_t* lut,
+                      hc_stream_t stream);
+int hc_pair_relu_pool_tiled(const void* u, const void* v, const float* bias, const int32_t* box_offsets,
+                            const int32_t* lut, int32_t n_max, int32_t img0, int32_t n_img, int32_t pair_base,
+                            int32_t chunk_pairs, int32_t fs, int32_t channels, void* out, hc_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * R6 tail + R7 - label-embedding add, fc2 bias + ReLU, fc3_x / fc4 / fc5 heads and the Bayesian hierarchical
  * log-softmax (model.py:152-168,175-184; flat variant model.py:97-101).

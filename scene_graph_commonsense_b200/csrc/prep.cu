@@ -49,8 +49,8 @@ __device__ __forceinline__ void add8(float (&acc)[8], uint4 a, uint4 b, const fl
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     float2 fa = __bfloat1622float2(pa[k]), fb = __bfloat1622float2(pb[k]);
-    acc[2 * k] = fmaxf(acc[2 * k], fa.x + fb.x + bias[2 * k]);
-    acc[2 * k + 1] = fmaxf(acc[2 * k + 1], fa.y + fb.y + bias[2 * k + 1]);
+    acc[2 * k] = fmaxf(acc[2 * k], fa.x + (fb.x + bias[2 * k]));          // same association as the tiled kernel
+    acc[2 * k + 1] = fmaxf(acc[2 * k + 1], fa.y + (fb.y + bias[2 * k + 1]));
   }
 }
 
@@ -83,6 +83,112 @@ __global__ void pair_relu_pool_kernel(const uint4* __restrict__ u, const uint4* 
 #pragma unroll
     for (int k = 0; k < 4; ++k) po[k] = __floats2bfloat162_rn(acc[2 * k], acc[2 * k + 1]);
     out[i] = o;
+  }
+}
+
+// ---- tiled variant: out[(a,b)] = pool(relu(U[a] + V[b] + bias)) is an OUTER SUM over the boxes of one image, so a thread
+// keeps the U tiles of TA subject boxes in registers (packed bf16) and streams V[b] of every object box once:
+// L2/HBM reads per pair drop from 2 MiB to ~(1/TA + 1/N) MiB.  Output rows are found through a (subject box, local
+// object index) -> directed-pair-index table built from the enumerated pair list.
+constexpr int PP_TA = 4;
+
+__global__ void pair_lut_kernel(const int* __restrict__ pair_sub, const int* __restrict__ pair_obj, const int* __restrict__ pair_img,
+                                const int* __restrict__ box_off, int n_pairs, int n_max, int* __restrict__ lut) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs; p += gridDim.x * blockDim.x)
+    lut[(long long)pair_sub[p] * n_max + (pair_obj[p] - box_off[pair_img[p]])] = p;
+}
+
+__device__ __forceinline__ void unpack8(uint4 a, float (&f)[8]) {
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    f[2 * k] = __uint_as_float(w[k] << 16);            // bf16 -> f32 is a 16-bit shift
+    f[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+  }
+}
+
+// same conversion, but opaque to loop-invariant code motion: the U tiles must stay PACKED in registers across the
+// object loop (hoisting the unpack would need 128 live floats per thread and spill)
+__device__ __forceinline__ void unpack8_pinned(uint4 a, float (&f)[8]) {
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    uint32_t lo, hi;
+    asm volatile("shl.b32 %0, %1, 16;" : "=r"(lo) : "r"(w[k]));
+    asm volatile("and.b32 %0, %1, 0xFFFF0000;" : "=r"(hi) : "r"(w[k]));
+    f[2 * k] = __uint_as_float(lo);
+    f[2 * k + 1] = __uint_as_float(hi);
+  }
+}
+
+__global__ void __launch_bounds__(128, 4)
+pair_relu_pool_tiled_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const float* __restrict__ bias,
+                            const int* __restrict__ box_off, const int* __restrict__ lut, int n_max, int img0, int pair_base,
+                            int chunk_pairs, int fs, int cvec, int tiles_per_img, int slabs, uint4* __restrict__ out) {
+  // grid = (slabs, tiles_per_img, images of the chunk); block = 128 consecutive (pooled pixel, channel vector) slots
+  const int img = img0 + blockIdx.z;
+  const int b0 = box_off[img], n = box_off[img + 1] - b0;
+  const int a0 = blockIdx.y * PP_TA;
+  if (a0 >= n) return;
+  const int hp = fs / 2;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cv = slot % cvec;
+  const int pix = slot / cvec;
+  const int px = pix % hp, py = pix / hp;
+  if (py >= hp) return;
+  float bia[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) bia[k] = __ldg(bias + cv * 8 + k);
+  uint4 ua[PP_TA][4];
+#pragma unroll
+  for (int t = 0; t < PP_TA; ++t) {
+    const int a = min(a0 + t, n - 1);
+    const long long base = (long long)(b0 + a) * fs * fs;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      ua[t][q] = __ldg(u + (base + (long long)(2 * py + (q >> 1)) * fs + (2 * px + (q & 1))) * cvec + cv);
+  }
+  for (int b = 0; b < n; ++b) {
+    int prow[PP_TA];
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < PP_TA; ++t) {
+      int p = (a0 + t < n) ? __ldg(lut + (long long)(b0 + a0 + t) * n_max + b) : -1;
+      p = (p >= 0) ? p - pair_base : -1;
+      if (p >= chunk_pairs) p = -1;
+      prow[t] = p;
+      any |= p >= 0;
+    }
+    if (!any) continue;                                  // block-uniform (lut entries do not depend on the thread)
+    const long long vb = (long long)(b0 + b) * fs * fs;
+    float acc[PP_TA][8];
+#pragma unroll
+    for (int t = 0; t < PP_TA; ++t)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[t][k] = 0.0f;       // relu folded in: max(0, ...)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float vf[8];
+      unpack8(__ldg(v + (vb + (long long)(2 * py + (q >> 1)) * fs + (2 * px + (q & 1))) * cvec + cv), vf);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) vf[k] += bia[k];
+#pragma unroll
+      for (int t = 0; t < PP_TA; ++t) {
+        float uf[8];
+        unpack8_pinned(ua[t][q], uf);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[t][k] = fmaxf(acc[t][k], uf[k] + vf[k]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < PP_TA; ++t) {
+      if (prow[t] < 0) continue;
+      uint4 o;
+      __nv_bfloat162* po = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) po[k] = __floats2bfloat162_rn(acc[t][2 * k], acc[t][2 * k + 1]);
+      out[((long long)prow[t] * hp * hp + pix) * cvec + cv] = o;
+    }
   }
 }
 
@@ -138,4 +244,36 @@ extern "C" int hc_pair_relu_pool(const void* u, const void* v, const float* bias
                                                                      bias, pair_sub, pair_obj, total, fs, channels / 8,
                                                                      reinterpret_cast<uint4*>(out));
   return cuda_status("hc_pair_relu_pool");
+}
+
+extern "C" int hc_pair_lut_build(const int32_t* pair_sub, const int32_t* pair_obj, const int32_t* pair_img, const int32_t* box_offsets,
+                                 int32_t n_pairs, int32_t n_box, int32_t n_max, int32_t* lut, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(pair_sub && pair_obj && pair_img && box_offsets && lut, HC_E_NULL, "hc_pair_lut_build: NULL pointer");
+  HC_REQUIRE(n_box > 0 && n_max > 0 && n_pairs >= 0, HC_E_SHAPE, "hc_pair_lut_build: bad sizes");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  cudaMemsetAsync(lut, 0xFF, sizeof(int32_t) * (size_t)n_box * n_max, stream);      // -1
+  if (n_pairs > 0) pair_lut_kernel<<<stream_grid(n_pairs, 256), 256, 0, stream>>>(pair_sub, pair_obj, pair_img, box_offsets, n_pairs, n_max, lut);
+  return cuda_status("hc_pair_lut_build");
+}
+
+extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float* bias, const int32_t* box_offsets, const int32_t* lut,
+                                       int32_t n_max, int32_t img0, int32_t n_img, int32_t pair_base, int32_t chunk_pairs, int32_t fs,
+                                       int32_t channels, void* out, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(u && v && bias && box_offsets && lut && out, HC_E_NULL, "hc_pair_relu_pool_tiled: NULL pointer");
+  HC_REQUIRE(n_img > 0 && n_img <= 65535 && n_max > 0 && chunk_pairs > 0 && fs > 0 && fs % 2 == 0 && channels % 8 == 0, HC_E_SHAPE,
+             "hc_pair_relu_pool_tiled: bad sizes");
+  HC_REQUIRE(aligned16(u) && aligned16(v) && aligned16(out), HC_E_ALIGN, "hc_pair_relu_pool_tiled: 16-byte alignment");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  const int cvec = channels / 8, hp = fs / 2;
+  const int slots = hp * hp * cvec;
+  HC_REQUIRE(slots % 128 == 0, HC_E_SHAPE, "hc_pair_relu_pool_tiled: (fs/2)^2 * channels/8 must be a multiple of 128");
+  dim3 grid(slots / 128, (n_max + PP_TA - 1) / PP_TA, n_img);
+  pair_relu_pool_tiled_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v), bias,
+                                                        box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec, grid.y, grid.x,
+                                                        reinterpret_cast<uint4*>(out));
+  return cuda_status("hc_pair_relu_pool_tiled");
 }

@@ -95,9 +95,9 @@ class PackedHead:
         self.device = dev
 
     # ---------------------------------------------------------------------------- dense stages (model.py:138-150,175)
-    def conv3_fc(self, p2, m_sub=2):
-        """conv3_1+ReLU+pool -> fc1+ReLU -> fc2 (raw, fp32) on pooled conv2 activations p2 [n,16,16,512] bf16."""
-        n = p2.shape[0]
+    def conv3_fc(self, p2, m_sub=2, raw=None, n=None):
+        """conv3_1+ReLU+pool -> fc1+ReLU -> fc2 (raw, fp32) on pooled conv2 activations p2 [>=n,16,16,512] bf16."""
+        n = p2.shape[0] if n is None else n
         dev = p2.device
         p3 = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev)
         ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
@@ -105,7 +105,8 @@ class PackedHead:
         h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=dev)
         ops.tc_gemm(p3, self.w_fc1, h1, n, 4096, 65536, bias=self.b_fc1, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU,
                     group_m=37, m_sub=2 if n > 128 else 1, tag="fc1")
-        raw = torch.empty(n, HIDDEN, dtype=torch.float32, device=dev)
+        if raw is None:
+            raw = torch.empty(n, HIDDEN, dtype=torch.float32, device=dev)
         ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8, tag="fc2")
         return raw
 

@@ -71,8 +71,9 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
                                          ptr(pair_img), ptr(pair_ov), ptr(pair_gt), ptr(pair_rel), ptr(total),
                                          stream_ptr()), "hc_pairs_enumerate")
     _count(4)
-    n = int(total.item())
-    return dict(n=n, offsets=pair_offsets, sub=pair_sub[:n], obj=pair_obj[:n], img=pair_img[:n], ov=pair_ov[:n],
+    offsets_host = pair_offsets.cpu()                 # [B+1] ints: the one D2H sync of the step (sizes the GEMM launches)
+    n = int(offsets_host[-1])
+    return dict(n=n, offsets=pair_offsets, offsets_host=offsets_host.numpy(), sub=pair_sub[:n], obj=pair_obj[:n], img=pair_img[:n], ov=pair_ov[:n],
                 gt=pair_gt[:n], rel=pair_rel[:n])
 
 
@@ -126,8 +127,30 @@ def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None):
     n, ch = pair_sub.numel(), u.shape[-1]
     if out is None:
         out = torch.empty(n, fs // 2, fs // 2, ch, dtype=torch.bfloat16, device=u.device)
-    check(_lib.load().hc_pair_relu_pool(ptr(u), ptr(v), ptr(bias), ptr(pair_sub), ptr(pair_obj), n, fs, ch, ptr(out),
-                                        stream_ptr()), "hc_pair_relu_pool")
+    with _timed("pair_pool"):
+        check(_lib.load().hc_pair_relu_pool(ptr(u), ptr(v), ptr(bias), ptr(pair_sub), ptr(pair_obj), n, fs, ch, ptr(out),
+                                            stream_ptr()), "hc_pair_relu_pool")
+    _count()
+    return out
+
+
+def pair_lut_build(pair_sub, pair_obj, pair_img, box_offsets, n_box, n_max):
+    require_cuda(pair_sub, pair_obj, pair_img, box_offsets)
+    lut = torch.empty(n_box, n_max, dtype=torch.int32, device=box_offsets.device)
+    check(_lib.load().hc_pair_lut_build(ptr(pair_sub), ptr(pair_obj), ptr(pair_img), ptr(box_offsets), pair_sub.numel(), n_box, n_max,
+                                        ptr(lut), stream_ptr()), "hc_pair_lut_build")
+    _count(1)
+    return lut
+
+
+def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None):
+    require_cuda(u, v, bias, box_offsets, lut)
+    ch = u.shape[-1]
+    if out is None:
+        out = torch.empty(chunk_pairs, fs // 2, fs // 2, ch, dtype=torch.bfloat16, device=u.device)
+    with _timed("pair_pool"):
+        check(_lib.load().hc_pair_relu_pool_tiled(ptr(u), ptr(v), ptr(bias), ptr(box_offsets), ptr(lut), lut.shape[1], img0, n_img,
+                                                  pair_base, chunk_pairs, fs, ch, ptr(out), stream_ptr()), "hc_pair_relu_pool_tiled")
     _count()
     return out
 

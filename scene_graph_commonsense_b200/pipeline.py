@@ -47,6 +47,7 @@ class DeviceBatch:
     h2d_bytes: int
     # SGDET/SGCLS extras
     conf: Optional[torch.Tensor] = None        # f32 [nbox] object-label confidences
+    box_offsets_host: Optional[np.ndarray] = None
     gt: Optional[dict] = None                  # flat GT triplet tables (targets.flat_targets_sgd)
 
     @property
@@ -78,7 +79,8 @@ class HostBatch:
             gt = dict(offsets=d["gt_offsets"], label=d["gt_label"], sub=d["gt_sub"], obj=d["gt_obj"], cat=d["gt_cat"], box=d["gt_box"])
         return DeviceBatch(d.get("feat"), d.get("depth"), d["boxes"], d["box_offsets"], d["box_img"], d["cats"], d["supers"],
                            d["tri_offsets"], d.get("rel_tri"), d.get("dir_tri"), d.get("group_id"), m["n_groups"], m["max_tri"],
-                           m["p_max"], self.h2d_bytes, conf=d.get("conf"), gt=gt)
+                           m["p_max"], self.h2d_bytes, conf=d.get("conf"), gt=gt,
+                           box_offsets_host=self.t["box_offsets"].numpy())
 
 
 def host_batch_from_samples(samples, skip_mode="batch", group_size=None, sgdet=False, pinned=True, with_maps=True):
@@ -137,7 +139,7 @@ class RelationPipeline:
 
     def __init__(self, packed: Optional[PackedHead], device, commonsense=True, aligned_keys=None, violated_keys=None,
                  top_k=tables.TOP_K, iou_thresh=0.5, feature_size=32, chunk_pairs=16384, predcls=True, conv3_m_sub=2,
-                 hier=None, splits=None):
+                 hier=None, splits=None, overlap=True):
         self.packed = packed
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -148,6 +150,7 @@ class RelationPipeline:
         self.chunk_pairs = int(chunk_pairs)
         self.predcls = predcls
         self.conv3_m_sub = conv3_m_sub
+        self.overlap = overlap
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
         self.hier = (not packed.flat if packed is not None else True) if hier is None else bool(hier)
         self.pass_bitmap = None
@@ -181,19 +184,72 @@ class RelationPipeline:
                         n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=2, tag="conv2_half")
         return u, v
 
+    def _image_chunks(self, offsets_host):
+        """Greedy image-aligned chunks of at most `chunk_pairs` directed pairs: (img0, n_img, pair_base, n_pairs)."""
+        chunks, i, n_img = [], 0, len(offsets_host) - 1
+        while i < n_img:
+            j = i + 1
+            while j < n_img and offsets_host[j + 1] - offsets_host[i] <= self.chunk_pairs:
+                j += 1
+            if offsets_host[j] > offsets_host[i]:
+                chunks.append((i, j - i, int(offsets_host[i]), int(offsets_host[j] - offsets_host[i])))
+            i = j
+        return chunks
+
     def forward_pairs(self, b: DeviceBatch, pairs):
-        """R3,R5-R7 for every directed pair of the batch -> (relation [P,R], super [P,3], connectivity [P], logsig [P])."""
+        """R3,R5-R7 for every directed pair of the batch -> (relation [P,R], super [P,3], connectivity [P], logsig [P]).
+        Pair lists from `enumerate_pairs` take the tiled outer-sum pooling kernel on image-aligned chunks, with the
+        pooling of chunk k+1 overlapped (second stream) with the tensor-core GEMMs of chunk k; arbitrary pair lists
+        (no `offsets_host`) take the generic gather kernel."""
         pk = self.packed
         n = pairs["n"]
         u, v = self.box_features(b)
         raw = torch.empty(n, 512, dtype=torch.float32, device=self.device)
-        for s in range(0, n, self.chunk_pairs):
-            e = min(n, s + self.chunk_pairs)
-            p2 = ops.pair_relu_pool(u, v, pk.b2, pairs["sub"][s:e], pairs["obj"][s:e], self.fs)
-            raw[s:e] = pk.conv3_fc(p2, m_sub=self.conv3_m_sub)
-            del p2
+        if "offsets_host" not in pairs:
+            for s in range(0, n, self.chunk_pairs):
+                e = min(n, s + self.chunk_pairs)
+                p2 = ops.pair_relu_pool(u, v, pk.b2, pairs["sub"][s:e], pairs["obj"][s:e], self.fs)
+                pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e])
+                del p2
+        else:
+            n_box = b.boxes.shape[0]
+            n_max = int(np.max(np.diff(b.box_offsets_host))) if b.box_offsets_host is not None else int(
+                (b.box_offsets[1:] - b.box_offsets[:-1]).max().item())
+            lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
+            chunks = self._image_chunks(pairs["offsets_host"])
+            cap = max(c[3] for c in chunks)
+            bufs = [torch.empty(cap, self.fs // 2, self.fs // 2, 512, dtype=torch.bfloat16, device=self.device)
+                    for _ in range(2 if self.overlap and len(chunks) > 1 else 1)]
+            main = torch.cuda.current_stream()
+            side = self._side_stream() if len(bufs) == 2 else main
+            ready = torch.cuda.Event()
+            ready.record(main)
+            gemm_done = []
+            for k, (img0, n_img, base, cnt) in enumerate(chunks):
+                buf = bufs[k % len(bufs)]
+                with torch.cuda.stream(side):
+                    if side is not main:
+                        side.wait_event(ready)
+                        if k >= 2:
+                            side.wait_event(gemm_done[k - 2])          # buffer free again
+                    ops.pair_relu_pool_tiled(u, v, pk.b2, b.box_offsets, lut, img0, n_img, base, cnt, self.fs, out=buf)
+                    pooled = torch.cuda.Event()
+                    pooled.record(side)
+                if side is not main:
+                    main.wait_event(pooled)
+                pk.conv3_fc(buf, m_sub=self.conv3_m_sub, raw=raw[base:base + cnt], n=cnt)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                gemm_done.append(ev)
+            if side is not main:
+                main.wait_stream(side)
         relation, sup, conn, logsig, _ = pk.heads(raw, pairs["sub"], pairs["obj"], b.cats, b.supers)
         return relation, sup, conn, logsig
+
+    def _side_stream(self):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     def evaluate(self, b: DeviceBatch, pairs, relation, sup, conn_logsig, connectivity=None, want_topk=False):
         """R8-R13 on given scores (bit-exact stage: identical scores in -> identical counters out)."""

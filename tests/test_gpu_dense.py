@@ -111,7 +111,7 @@ def test_pack_pixels_and_box_select_and_pair_pool():
     ps = torch.tensor([0, 3, 2, 1, 1], dtype=torch.int32, device="cuda")
     po = torch.tensor([1, 0, 2, 3, 0], dtype=torch.int32, device="cuda")
     got = ops.pair_relu_pool(u, v, bias, ps, po)
-    s = torch.relu(u[ps.long()].float() + v[po.long()].float() + bias)
+    s = torch.relu(u[ps.long()].float() + (v[po.long()].float() + bias))
     ref = F.max_pool2d(s.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).to(torch.bfloat16)
     assert torch.equal(got, ref)
 
@@ -125,3 +125,28 @@ def test_shape_errors_are_reported_not_swallowed():
         ops.tc_gemm(a, b, out, 128, 128, 100, lda=100, epilogue=ops.EPI_F32)
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         ops.tc_gemm(a.cpu(), b, out, 128, 128, 64, lda=64, epilogue=ops.EPI_F32)
+
+
+@pytest.mark.parametrize("mode", ["batch", "per_image"])
+def test_tiled_pair_pool_equals_gather_kernel_on_enumerated_pairs(mode):
+    """The outer-sum tiled pooling kernel (LUT-addressed, image-aligned chunks, second stream) writes exactly what the
+    generic per-pair gather kernel writes, including when the skip rule removes pairs."""
+    from scene_graph_commonsense_b200 import pipeline, synthetic
+    ops = _ops()
+    samples = synthetic.make_batch([500, 501, 502, 503], [7, 12, 2, 9], with_maps=False)
+    b = pipeline.batch_from_samples(samples, "cuda", skip_mode=mode, with_maps=False)
+    pipe = pipeline.RelationPipeline(None, "cuda", commonsense=False, chunk_pairs=150)
+    pairs = pipe.enumerate_pairs(b)
+    assert pairs["n"] > 0
+    n_box = b.boxes.shape[0]
+    u, v = _rand((n_box, 32, 32, 512), 31).to(torch.bfloat16), _rand((n_box, 32, 32, 512), 32).to(torch.bfloat16)
+    bias = _rand((512,), 33)
+    ref = ops.pair_relu_pool(u, v, bias, pairs["sub"], pairs["obj"])
+    lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, 12)
+    chunks = pipe._image_chunks(pairs["offsets_host"])
+    assert len(chunks) >= 2 and sum(c[3] for c in chunks) == pairs["n"]
+    for img0, n_img, base, cnt in chunks:
+        out = torch.full((cnt + 3, 16, 16, 512), 7.0, dtype=torch.bfloat16, device="cuda")
+        ops.pair_relu_pool_tiled(u, v, bias, b.box_offsets, lut, img0, n_img, base, cnt, out=out)
+        assert torch.equal(out[:cnt], ref[base:base + cnt])
+        assert (out[cnt:] == 7.0).all()
