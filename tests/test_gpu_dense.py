@@ -135,7 +135,7 @@ def test_tiled_pair_pool_equals_gather_kernel_on_enumerated_pairs(mode):
     ops = _ops()
     samples = synthetic.make_batch([500, 501, 502, 503], [7, 12, 2, 9], with_maps=False)
     b = pipeline.batch_from_samples(samples, "cuda", skip_mode=mode, with_maps=False)
-    pipe = pipeline.RelationPipeline(None, "cuda", commonsense=False, chunk_pairs=150)
+    pipe = pipeline.RelationPipeline(None, "cuda", commonsense=False, chunk_pairs=60)
     pairs = pipe.enumerate_pairs(b)
     assert pairs["n"] > 0
     n_box = b.boxes.shape[0]
