@@ -145,7 +145,7 @@ def run_reference(args):
                        "sample": sample},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ======================================================================================================= our arm
@@ -279,10 +279,22 @@ def run_ours(args):
         "recall": {"R@20/50/100": m["evaluator"][0], "mR@20/50/100": [float(x) for x in m["evaluator"][2]]},
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL banners ...) was sent to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                      # C-level stdout writers (NCCL "version" banner) must not pollute the JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -297,6 +309,10 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+        import torch.distributed as tdist
+        if tdist.is_available() and tdist.is_initialized():
+            tdist.barrier()
+            tdist.destroy_process_group()
 
 
 if __name__ == "__main__":

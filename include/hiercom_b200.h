@@ -107,6 +107,8 @@ typedef struct hc_gemm_desc {
   int32_t n_img, h, w, c_total, c_base, c_in; /* CONV3 */
   int32_t group_m;   /* tile rasterisation: m-blocks per band (0 = default) */
   int32_t m_sub;     /* 128-row sub-tiles per CTA tile: 1 or 2 (0 = default) */
+  const float* mul;  /* optional f32 [M, ld_mul]: out = act(acc + bias) * mul (PLAIN, non-pooled); SGB `* union_features` */
+  int64_t ld_mul;
 } hc_gemm_desc;
 
 int hc_tc_gemm(const hc_gemm_desc* desc, hc_stream_t stream);
@@ -197,12 +199,54 @@ int hc_topk_match(const int32_t* cand_offsets, int32_t n_images, const float* ca
                   const int32_t* t3_labels, const uint8_t* t3_super, unsigned long long* counters,
                   int32_t* topk_out, hc_stream_t stream);
 
+/* Selection only: topk_out [n_images, top_max] = image-local candidate ids ordered by (confidence desc, index asc),
+ * -1 padded (the prefix of `torch.sort(descending=True, stable=True)`; evaluator.py:304, inference.py:282). */
+int hc_topk_select(const int32_t* cand_offsets, int32_t n_images, const float* cand_conf, int32_t top_max,
+                   int32_t* topk_out, hc_stream_t stream);
+
 /* train_utils.py:169-183 side statistics over directed rows: stats[0..4] += num_not_connected, num_connected,
  * num_connected_pred (sigmoid(conn) >= 0.5), connectivity_precision (#pred-connected rows whose undirected GT
  * label != -1), connectivity_recall (sum round(sigmoid(conn)) over connected rows). */
 int hc_connectivity_stats(const float* connectivity, const int32_t* row_gt_directed,
                           const int32_t* row_gt_undirected, int32_t n_rows, unsigned long long* stats,
                           hc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * R14 / N1 - Scene-Graph-Benchmark plug-and-play twin (PredCLS, config 5).  Dense stages use hc_tc_gemm:
+ * post_cat (1024 -> 4096) with `mul = union_features` (roi_relation_predictors.py:421-427) and the BayesHead
+ * (4096 -> 15/11/24/4 raw logits, model_motifs_hierarchical.py:22-33).
+ */
+/* prod_rep[p] = cat(head_rep[idx0], tail_rep[idx1]) (roi_relation_predictors.py:413-419); edge_rep f32
+ * [n_obj, 2*hidden] = post_emb output, pair_idx int32 [n_pairs,2] global object ids, out bf16 [n_pairs, 2*hidden]. */
+int hc_sgb_pair_gather(const float* edge_rep, const int32_t* pair_idx, int32_t n_pairs, int32_t hidden, void* out,
+                       hc_stream_t stream);
+/* frequency-bias gather + log-sum-exp super bias + hierarchical log-softmax with super indices 1..3
+ * (roi_relation_predictors.py:430-459).  logits [n, ld]: columns [0,R) heads, [R,R+4) super.  bias_table f32
+ * [num_obj^2, 51] or NULL, pair_pred int32 [n,2] object labels, label_ids int32 [R] 51-vocabulary id of each head
+ * column (:376-382).  rel f32 [n,R] log-joint, super_rel f32 [n,4]. */
+int hc_sgb_hier_softmax(const float* logits, int64_t ld, int32_t n_rows, int32_t n_geo, int32_t n_pos, int32_t n_sem,
+                        const float* bias_table, int32_t num_obj, const int32_t* pair_pred, const int32_t* label_ids,
+                        float* rel, float* super_rel, hc_stream_t stream);
+/* HierarchPostProcessor candidates (inference.py:246-281): three per pair, score = max prob * obj_score0 *
+ * obj_score1, label remapped through label_ids; image i with P_i pairs owns candidates [3*off_i, 3*off_{i+1}) in the
+ * reference's torch.cat order c = 3*off_i + k*P_i + r.  cand_row = global pair row of each candidate. */
+int hc_sgb_candidates(const float* rel, int32_t n_geo, int32_t n_pos, int32_t n_sem, const int32_t* pair_offsets,
+                      const int32_t* pair_img, const int32_t* pair_idx, const float* obj_scores,
+                      const int32_t* label_ids, int32_t n_rows, float* cand_score, int32_t* cand_label,
+                      int32_t* cand_row, hc_stream_t stream);
+/* Second (post-validator) sort restricted to the ranked window + per-image recall bookkeeping
+ * (inference.py:292-302; sgg_eval.py:56-99,347-385,528-565; boxlist_ops.py:54-90 fp32 IoU with +1).
+ * ranked int32 [n_images,128]: image-local candidate ids in first-sort order (hc_topk_match's topk_out with
+ * top_max = 128), reject uint8 [n_images,128] or NULL.  gt_rel int32 [G,3] (sub id, obj id, label) with global ids
+ * into gt_cls / gt_box (f32 xyxy); pred_cls / pred_box indexed by pair_idx.  Outputs per image:
+ * final_rank [n_images, top_max] (optional), img_hits [n,3], img_ngt [n], img_hits_pc [n,3,51], img_cnt_pc [n,51]. */
+int hc_sgb_rank_match(const int32_t* ranked, const uint8_t* reject, const int32_t* pair_offsets, int32_t n_images,
+                      const float* cand_score, const int32_t* cand_label, const int32_t* cand_row,
+                      const int32_t* pair_idx, const int32_t* pred_cls, const float* pred_box,
+                      const int32_t* gt_offsets, const int32_t* gt_rel, const int32_t* gt_cls, const float* gt_box,
+                      float iou_thresh, int32_t top_max, int32_t k0, int32_t k1, int32_t k2, int32_t* final_rank,
+                      int32_t* img_hits, int32_t* img_ngt, int32_t* img_hits_pc, int32_t* img_cnt_pc,
+                      hc_stream_t stream);
 
 #ifdef __cplusplus
 }

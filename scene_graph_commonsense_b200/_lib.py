@@ -25,7 +25,7 @@ class GemmDesc(C.Structure):
                 ("mode", C.c_int32), ("epilogue", C.c_int32), ("act", C.c_int32),
                 ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("c_total", C.c_int32), ("c_base", C.c_int32), ("c_in", C.c_int32),
-                ("group_m", C.c_int32), ("m_sub", C.c_int32)]
+                ("group_m", C.c_int32), ("m_sub", C.c_int32), ("mul", C.c_void_p), ("ld_mul", C.c_int64)]
 
 
 _P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -48,7 +48,13 @@ SIGNATURES = {
                                 _I32, _P]),
     "hc_topk_match": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _I32,
                                 _D, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "hc_topk_select": (C.c_int, [_P, _I32, _P, _I32, _P, _P]),
     "hc_connectivity_stats": (C.c_int, [_P, _P, _P, _I32, _P, _P]),
+    "hc_sgb_pair_gather": (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "hc_sgb_hier_softmax": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
+    "hc_sgb_candidates": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
+    "hc_sgb_rank_match": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32,
+                                    _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -48,6 +48,8 @@ struct Params {
   int epi, act;
   long long ldc, c_off;
   const float* bias;
+  const float* mul;              // optional elementwise multiplier [M, ld_mul] applied after bias/activation
+  long long ld_mul;
   void* out;
 };
 
@@ -347,6 +349,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     v.x += __ldg(p.bias + col0 + 4 * i); v.y += __ldg(p.bias + col0 + 4 * i + 1);
                     v.z += __ldg(p.bias + col0 + 4 * i + 2); v.w += __ldg(p.bias + col0 + 4 * i + 3);
                   }
+                  if (p.mul) {
+                    float4 mm = __ldg(reinterpret_cast<const float4*>(p.mul + row * p.ld_mul + col0 + 4 * i));
+                    v.x *= mm.x; v.y *= mm.y; v.z *= mm.z; v.w *= mm.w;
+                  }
                   *reinterpret_cast<float4*>(dst + 4 * i) = v;
                 }
               } else {
@@ -359,7 +365,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     int c = 8 * i + 2 * t;
                     float a = __uint_as_float(r[c]), b = __uint_as_float(r[c + 1]);
                     if (p.bias) { a += __ldg(p.bias + col0 + c); b += __ldg(p.bias + col0 + c + 1); }
-                    w[t] = pack_bf16(apply_act(a, p.act), apply_act(b, p.act));
+                    a = apply_act(a, p.act); b = apply_act(b, p.act);
+                    if (p.mul) {
+                      float2 mm = __ldg(reinterpret_cast<const float2*>(p.mul + row * p.ld_mul + col0 + c));
+                      a *= mm.x; b *= mm.y;
+                    }
+                    w[t] = pack_bf16(a, b);
                   }
                   *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
@@ -459,6 +470,9 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   p.M = (int)d->m; p.N = (int)d->n; p.K = (int)d->k;
   p.mode = d->mode; p.epi = d->epilogue; p.act = d->act;
   p.ldc = d->ldc; p.c_off = d->c_off; p.bias = d->bias; p.out = d->out;
+  p.mul = d->mul; p.ld_mul = d->ld_mul;
+  HC_REQUIRE(!d->mul || (d->epilogue != HC_EPI_POOL_BF16 && d->mode == HC_GEMM_PLAIN && d->ld_mul % 4 == 0 && aligned16(d->mul)), HC_E_SHAPE,
+             "hc_tc_gemm: mul needs a plain GEMM, a non-pooled epilogue and a 16-byte aligned [M, ld_mul] f32 operand");
   p.tiles_n = p.N / BN;
 
   CUtensorMap ta, tb;

@@ -47,7 +47,7 @@ topk_match_kernel(const int* __restrict__ cand_off, const float* __restrict__ ca
                   const int* __restrict__ gt_cat, const int4* __restrict__ gt_box, const uint8_t* __restrict__ synonyms, int num_obj,
                   const uint32_t* __restrict__ zs_bitmap, int fs, double iou_thresh, int top_max, int k0, int k1, int k2, int mode,
                   const int* __restrict__ t3_labels, const uint8_t* __restrict__ t3_super, unsigned long long* __restrict__ counters,
-                  int* __restrict__ topk_out) {
+                  int* __restrict__ topk_out, int select_only) {
   __shared__ int hist[256];
   __shared__ int warp_cnt[2][TK_THREADS / 32];
   __shared__ unsigned long long sel[TK_MAX];
@@ -63,7 +63,7 @@ topk_match_kernel(const int* __restrict__ cand_off, const float* __restrict__ ca
   if (topk_out)
     for (int j = tid; j < top_max; j += TK_THREADS) topk_out[(long long)img * top_max + j] = -1;
   if (C <= 0) return;                                   // image absent from torch.unique(which_in_batch) (evaluator.py:294)
-  const int g0 = gt_off[img], G = gt_off[img + 1] - g0;
+  const int g0 = select_only ? 0 : gt_off[img], G = select_only ? 0 : gt_off[img + 1] - g0;
   if (G <= 0 && !topk_out) return;
   const int n_sel = min(top_max, C);                    // evaluator.py:315-316
   const float* conf = cand_conf + c0;
@@ -138,6 +138,7 @@ topk_match_kernel(const int* __restrict__ cand_off, const float* __restrict__ ca
   for (int j = tid; j < n_sel; j += TK_THREADS) {
     int c = (int)(sel[j] & 0xFFFFFFFFu);
     if (topk_out) topk_out[(long long)img * top_max + j] = c;
+    if (select_only) continue;
     int gc = c0 + c;
     int row = cand_row ? cand_row[gc] : gc / K;
     SelMeta m;
@@ -271,6 +272,20 @@ extern "C" int hc_topk_match(const int32_t* cand_offsets, int32_t n_images, cons
   topk_match_kernel<<<n_images, TK_THREADS, 0, stream>>>(
       cand_offsets, cand_conf, cand_label, cand_row, k_per_row, row_sub, row_obj, pred_cat, reinterpret_cast<const int4*>(pred_box),
       gt_offsets, gt_label, gt_sub, gt_obj, gt_cat, reinterpret_cast<const int4*>(gt_box), synonyms, num_obj, zs_bitmap, feature_size,
-      iou_thresh, top_max, k0, k1, k2, mode, t3_labels, t3_super, counters, topk_out);
+      iou_thresh, top_max, k0, k1, k2, mode, t3_labels, t3_super, counters, topk_out, 0);
   return cuda_status("hc_topk_match");
+}
+
+extern "C" int hc_topk_select(const int32_t* cand_offsets, int32_t n_images, const float* cand_conf, int32_t top_max, int32_t* topk_out,
+                              hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(cand_offsets && cand_conf && topk_out, HC_E_NULL, "hc_topk_select: NULL pointer");
+  HC_REQUIRE(top_max >= 1 && top_max <= HC_TOP_MAX, HC_E_SHAPE, "hc_topk_select: top_max must be in [1,128]");
+  if (n_images <= 0) return HC_OK;
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  topk_match_kernel<<<n_images, TK_THREADS, 0, stream>>>(cand_offsets, cand_conf, nullptr, nullptr, 1, nullptr, nullptr, nullptr, nullptr,
+                                                         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1, nullptr, 32, 0.5,
+                                                         top_max, 0, 0, 0, 0, nullptr, nullptr, nullptr, topk_out, 1);
+  return cuda_status("hc_topk_select");
 }

@@ -78,9 +78,9 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 
 
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16,
-            act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm"):
+            act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None):
     """out = epilogue(A @ B^T) on tcgen05 (see include/hiercom_b200.h hc_tc_gemm)."""
-    require_cuda(a, b, out, bias)
+    require_cuda(a, b, out, bias, mul)
     d = _lib.GemmDesc()
     d.a, d.b, d.bias, d.out = ptr(a), ptr(b), ptr(bias), ptr(out)
     d.m, d.n, d.k = m, n, k
@@ -88,6 +88,7 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     d.mode, d.epilogue, d.act = mode, epilogue, act
     d.n_img, d.h, d.w, d.c_total, d.c_base, d.c_in = n_img, h, w, c_total, c_base, c_in
     d.group_m, d.m_sub = group_m, m_sub
+    d.mul, d.ld_mul = ptr(mul), (mul.stride(0) if mul is not None else 0)
     with _timed(tag):
         check(_lib.load().hc_tc_gemm(C.byref(d), stream_ptr()), "hc_tc_gemm")
     _count()
@@ -210,8 +211,70 @@ def topk_match(cand_offsets, cand_conf, cand_label, k_per_row, row_sub, row_obj,
     return topk_out
 
 
+def topk_select(cand_offsets, cand_conf, top_max=128):
+    require_cuda(cand_offsets, cand_conf)
+    n_images = cand_offsets.numel() - 1
+    out = torch.empty(n_images, top_max, dtype=torch.int32, device=cand_conf.device)
+    check(_lib.load().hc_topk_select(ptr(cand_offsets), n_images, ptr(cand_conf), top_max, ptr(out), stream_ptr()), "hc_topk_select")
+    _count()
+    return out
+
+
 def connectivity_stats(connectivity, gt_directed, gt_undirected, stats):
     require_cuda(connectivity, gt_directed, gt_undirected, stats)
     check(_lib.load().hc_connectivity_stats(ptr(connectivity), ptr(gt_directed), ptr(gt_undirected), connectivity.numel(),
                                             ptr(stats), stream_ptr()), "hc_connectivity_stats")
     _count()
+
+
+# ------------------------------------------------------------------------------------------------------ SGB twin (R14/N1)
+def sgb_pair_gather(edge_rep, pair_idx, hidden):
+    require_cuda(edge_rep, pair_idx)
+    n = pair_idx.shape[0]
+    out = torch.empty(n, 2 * hidden, dtype=torch.bfloat16, device=edge_rep.device)
+    check(_lib.load().hc_sgb_pair_gather(ptr(edge_rep), ptr(pair_idx), n, hidden, ptr(out), stream_ptr()), "hc_sgb_pair_gather")
+    _count()
+    return out
+
+
+def sgb_hier_softmax(logits, splits, bias_table=None, num_obj=151, pair_pred=None, label_ids=None):
+    require_cuda(logits, bias_table, pair_pred, label_ids)
+    n, r = logits.shape[0], sum(splits)
+    rel = torch.empty(n, r, dtype=torch.float32, device=logits.device)
+    sup = torch.empty(n, 4, dtype=torch.float32, device=logits.device)
+    check(_lib.load().hc_sgb_hier_softmax(ptr(logits), logits.stride(0), n, splits[0], splits[1], splits[2], ptr(bias_table), num_obj,
+                                          ptr(pair_pred), ptr(label_ids), ptr(rel), ptr(sup), stream_ptr()), "hc_sgb_hier_softmax")
+    _count()
+    return rel, sup
+
+
+def sgb_candidates(rel, splits, pair_offsets, pair_img, pair_idx, obj_scores, label_ids):
+    require_cuda(rel, pair_offsets, pair_img, pair_idx, obj_scores, label_ids)
+    n = rel.shape[0]
+    dev = rel.device
+    score = torch.empty(3 * n, dtype=torch.float32, device=dev)
+    label = torch.empty(3 * n, dtype=torch.int32, device=dev)
+    row = torch.empty(3 * n, dtype=torch.int32, device=dev)
+    check(_lib.load().hc_sgb_candidates(ptr(rel), splits[0], splits[1], splits[2], ptr(pair_offsets), ptr(pair_img), ptr(pair_idx),
+                                        ptr(obj_scores), ptr(label_ids), n, ptr(score), ptr(label), ptr(row), stream_ptr()),
+          "hc_sgb_candidates")
+    _count()
+    return score, label, row
+
+
+def sgb_rank_match(ranked, reject, pair_offsets, cand_score, cand_label, cand_row, pair_idx, pred_cls, pred_box, gt_offsets, gt_rel,
+                   gt_cls, gt_box, iou_thresh=0.5, top_k=(20, 50, 100)):
+    require_cuda(ranked, reject, pair_offsets, cand_score, cand_label, cand_row, pair_idx, pred_cls, pred_box, gt_offsets, gt_rel, gt_cls,
+                 gt_box)
+    n_img = pair_offsets.numel() - 1
+    dev = cand_score.device
+    top_max = int(top_k[-1])
+    i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+    final_rank, hits, ngt, hits_pc, cnt_pc = i32(n_img, top_max), i32(n_img, 3), i32(n_img), i32(n_img, 3, 51), i32(n_img, 51)
+    check(_lib.load().hc_sgb_rank_match(ptr(ranked), ptr(reject), ptr(pair_offsets), n_img, ptr(cand_score), ptr(cand_label),
+                                        ptr(cand_row), ptr(pair_idx), ptr(pred_cls), ptr(pred_box), ptr(gt_offsets), ptr(gt_rel),
+                                        ptr(gt_cls), ptr(gt_box), float(iou_thresh), top_max, int(top_k[0]), int(top_k[1]),
+                                        int(top_k[2]), ptr(final_rank), ptr(hits), ptr(ngt), ptr(hits_pc), ptr(cnt_pc), stream_ptr()),
+          "hc_sgb_rank_match")
+    _count()
+    return final_rank, hits, ngt, hits_pc, cnt_pc

@@ -233,3 +233,44 @@ def synthetic_cs_keys(seed=0, frac_aligned=0.5, frac_violated=0.1):
     r2 = rng.random(tables.TRIPLET_SPACE)
     violated = np.nonzero(r2 < frac_violated)[0].astype(np.int64)
     return aligned, violated
+
+
+# ----------------------------------------------------------------------------------------------
+# Scene-Graph-Benchmark-shaped inputs (config 5: PredCLS Motifs tail, 512-d context, 4096-d union features, 151/51 classes)
+
+
+def sgb_state_dict(seed=0, hidden=512, pooling=4096, num_obj=151, num_rel=51, logit_gain=4.0):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(2_000_003 + int(seed))
+
+    def n(shape, std):
+        return torch.randn(shape, generator=g) * std
+    sd = {"post_emb.weight": n((2 * hidden, hidden), 10.0 * (1.0 / hidden) ** 0.5 / 8), "post_emb.bias": torch.zeros(2 * hidden),
+          "post_cat.weight": n((pooling, 2 * hidden), (2.0 / (pooling + 2 * hidden)) ** 0.5), "post_cat.bias": n((pooling,), 0.01)}
+    for name, rows in (("fc3_1", 15), ("fc3_2", 11), ("fc3_3", 24), ("fc5", 4)):
+        sd[name + ".weight"] = n((rows, pooling), logit_gain * (2.0 / (pooling + rows)) ** 0.5)
+        sd[name + ".bias"] = n((rows,), 0.1)
+    sd["freq_bias"] = torch.log_softmax(n((num_obj * num_obj, num_rel), 1.5), dim=1)
+    return sd
+
+
+def make_sgb_batch(num_objs, seed=0, hidden=512, pooling=4096, num_obj_cls=151):
+    g = torch.Generator(device="cpu")
+    g.manual_seed(3_000_017 + int(seed))
+    total = int(sum(num_objs))
+    pairs = int(sum(n * (n - 1) for n in num_objs))
+    boxes = []
+    for n in num_objs:
+        xy = torch.rand(n, 2, generator=g) * 400
+        wh = torch.rand(n, 2, generator=g) * 200 + 20
+        boxes.append(torch.cat((xy, xy + wh), dim=1).float())
+    return dict(num_objs=list(num_objs), edge_ctx=torch.randn(total, hidden, generator=g),
+                obj_labels=torch.randint(1, num_obj_cls, (total,), generator=g),
+                obj_logits=torch.randn(total, num_obj_cls, generator=g) * 2.0,
+                union_features=torch.relu(torch.randn(pairs, pooling, generator=g)), boxes=boxes)
+
+
+def sgb_validator(combined_obj_label, rel_labels, image=None, boxlist=None):
+    """Deterministic stand-in for CommonsenseValidator.query: reject (-1) when (subject + predicate + object) % 3 == 0."""
+    s = combined_obj_label[:, 0].long() + combined_obj_label[:, 1].long() + rel_labels.long()
+    return torch.where(s % 3 == 0, torch.full_like(s, -1), torch.ones_like(s))

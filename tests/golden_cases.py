@@ -21,3 +21,8 @@ SGDET_CASES = {
     "sgd_plain": dict(ids=[73, 74], n_gt=[8, 5], n_prop=[18, 12], run_mode="eval"),
     "sgd_nogt": dict(ids=[75, 76], n_gt=[2, 7], n_prop=[6, 15], run_mode="eval", p_rel=[0.0, 0.6]),
 }
+
+SGB_CASES = {
+    "sgb_case_a": dict(num_objs=[6, 9, 4, 12], seed=0),
+    "sgb_case_b": dict(num_objs=[3, 14, 2, 8, 5], seed=1, empty_gt=2),
+}
