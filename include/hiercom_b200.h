@@ -217,9 +217,15 @@ int hc_connectivity_stats(const float* connectivity, const int32_t* row_gt_direc
  * (4096 -> 15/11/24/4 raw logits, model_motifs_hierarchical.py:22-33).
  */
 /* prod_rep[p] = cat(head_rep[idx0], tail_rep[idx1]) (roi_relation_predictors.py:413-419); edge_rep f32
- * [n_obj, 2*hidden] = post_emb output, pair_idx int32 [n_pairs,2] global object ids, out bf16 [n_pairs, 2*hidden]. */
-int hc_sgb_pair_gather(const float* edge_rep, const int32_t* pair_idx, int32_t n_pairs, int32_t hidden, void* out,
-                       hc_stream_t stream);
+ * [n_obj, 2*hidden] = post_emb output, pair_idx int32 [n_pairs,2] global object ids, out bf16 [n_pairs, 2*hidden]
+ * (split = 0) or [n_pairs, 3 * 2*hidden] in the bf16x3 layout (split = 1). */
+int hc_sgb_pair_gather(const float* edge_rep, const int32_t* pair_idx, int32_t n_pairs, int32_t hidden, int32_t split,
+                       void* out, hc_stream_t stream);
+/* bf16x3 operand splitting for near-fp32 accuracy on the bf16 tensor cores: f32 [n,k] -> bf16 [n,3k] = [hi | lo | hi]
+ * with hi = bf16(x), lo = bf16(x - hi); pair it with weights packed as [W_hi | W_hi | W_lo] so that one hc_tc_gemm over
+ * K' = 3k sums A_hi*W_hi + A_lo*W_hi + A_hi*W_lo in the fp32 accumulator.  (hc_sgb_pair_gather with split = 1 emits the
+ * same layout directly.) */
+int hc_split_bf16x3(const float* in, int64_t ld, int64_t n_rows, int32_t k, void* out, hc_stream_t stream);
 /* frequency-bias gather + log-sum-exp super bias + hierarchical log-softmax with super indices 1..3
  * (roi_relation_predictors.py:430-459).  logits [n, ld]: columns [0,R) heads, [R,R+4) super.  bias_table f32
  * [num_obj^2, 51] or NULL, pair_pred int32 [n,2] object labels, label_ids int32 [R] 51-vocabulary id of each head

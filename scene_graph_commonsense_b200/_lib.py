@@ -50,7 +50,8 @@ SIGNATURES = {
                                 _D, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "hc_topk_select": (C.c_int, [_P, _I32, _P, _I32, _P, _P]),
     "hc_connectivity_stats": (C.c_int, [_P, _P, _P, _I32, _P, _P]),
-    "hc_sgb_pair_gather": (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "hc_sgb_pair_gather": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "hc_split_bf16x3": (C.c_int, [_P, _I64, _I64, _I32, _P, _P]),
     "hc_sgb_hier_softmax": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "hc_sgb_candidates": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "hc_sgb_rank_match": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32,

@@ -228,13 +228,31 @@ def connectivity_stats(connectivity, gt_directed, gt_undirected, stats):
 
 
 # ------------------------------------------------------------------------------------------------------ SGB twin (R14/N1)
-def sgb_pair_gather(edge_rep, pair_idx, hidden):
+def sgb_pair_gather(edge_rep, pair_idx, hidden, split=False):
     require_cuda(edge_rep, pair_idx)
     n = pair_idx.shape[0]
-    out = torch.empty(n, 2 * hidden, dtype=torch.bfloat16, device=edge_rep.device)
-    check(_lib.load().hc_sgb_pair_gather(ptr(edge_rep), ptr(pair_idx), n, hidden, ptr(out), stream_ptr()), "hc_sgb_pair_gather")
+    out = torch.empty(n, (3 if split else 1) * 2 * hidden, dtype=torch.bfloat16, device=edge_rep.device)
+    check(_lib.load().hc_sgb_pair_gather(ptr(edge_rep), ptr(pair_idx), n, hidden, int(split), ptr(out), stream_ptr()), "hc_sgb_pair_gather")
     _count()
     return out
+
+
+def split_bf16x3(x):
+    """f32 [n,k] -> bf16 [n,3k] = [hi | lo | hi] (A side of the bf16x3 scheme)."""
+    require_cuda(x)
+    n, k = x.shape
+    out = torch.empty(n, 3 * k, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().hc_split_bf16x3(ptr(x), x.stride(0), n, k, ptr(out), stream_ptr()), "hc_split_bf16x3")
+    _count()
+    return out
+
+
+def pack_weight_bf16x3(w):
+    """f32 [n,k] weight -> bf16 [n,3k] = [W_hi | W_hi | W_lo] (B side of the bf16x3 scheme); one-time packing (torch)."""
+    w = w.detach().float()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat((hi, hi, lo), dim=1).contiguous()
 
 
 def sgb_hier_softmax(logits, splits, bias_table=None, num_obj=151, pair_pred=None, label_ids=None):

@@ -81,21 +81,23 @@ class BayesHead(nn.Module):
             wp[:w.shape[0]] = w
             bp = torch.zeros(128, device=w.device)
             bp[:b.shape[0]] = b
-            self._packed = (wp.to(torch.bfloat16).contiguous(), bp.contiguous())
+            self._packed = (ops.pack_weight_bf16x3(wp), bp.contiguous())
             self._versions = versions
         return self._packed
 
-    def logits(self, h_bf16):
-        """[n, input_dim] bf16 -> f32 [n,128] (columns: heads then the 4 super logits, rest zero padding)."""
+    def logits(self, h):
+        """[n, input_dim] f32 -> f32 [n,128] (columns: heads then the 4 super logits, rest zero padding).
+        bf16x3 split operands on the bf16 tensor cores: ~fp32 accuracy for the 4096-long dot products."""
         w, b = self.packed()
-        n, k = h_bf16.shape
-        out = torch.empty(n, 128, dtype=torch.float32, device=h_bf16.device)
-        ops.tc_gemm(h_bf16, w, out, n, 128, k, bias=b, lda=h_bf16.stride(0), ldc=128, epilogue=EPI_F32, group_m=8, tag="bayes_head")
+        a = ops.split_bf16x3(h)
+        n, k3 = a.shape
+        out = torch.empty(n, 128, dtype=torch.float32, device=h.device)
+        ops.tc_gemm(a, w, out, n, 128, k3, bias=b, lda=k3, ldc=128, epilogue=EPI_F32, group_m=8, tag="bayes_head")
         return out
 
     @torch.no_grad()
     def forward(self, h):
-        z = self.logits(h.to(torch.bfloat16).contiguous())
+        z = self.logits(h.float().contiguous())
         g, p, s = self.splits()
         return z[:, :g], z[:, g:g + p], z[:, g + p:g + p + s], z[:, g + p + s:g + p + s + 4]
 
@@ -105,7 +107,7 @@ class BayesHeadProb(BayesHead):
 
     @torch.no_grad()
     def forward(self, h):
-        z = self.logits(h.to(torch.bfloat16).contiguous())
+        z = self.logits(h.float().contiguous())
         rel, sup = ops.sgb_hier_softmax(z, self.splits())
         g, p, _ = self.splits()
         return rel[:, :g], rel[:, g:g + p], rel[:, g + p:], sup
@@ -134,14 +136,14 @@ def hierarchical_relation_tail(edge_rep, rel_pair_idxs, num_objs, obj_preds, uni
     hidden = edge_rep.shape[1] // 2
     pair_idx, pair_off, pair_img, num_rels = global_pair_index(rel_pair_idxs, num_objs, dev)
     n = pair_idx.shape[0]
-    prod = ops.sgb_pair_gather(edge_rep.float().contiguous(), pair_idx, hidden)
+    prod = ops.sgb_pair_gather(edge_rep.float().contiguous(), pair_idx, hidden, split=True)       # [P, 3*2*hidden] bf16x3 layout
     pooling = post_cat.out_features
     if use_vision and union_features.shape[1] != pooling:
         raise NotImplementedError("union_single_not_match (up_dim) is not on the config-5 path")
-    w = post_cat.weight.detach().to(torch.bfloat16).contiguous()
-    prod_rep = torch.empty(n, pooling, dtype=torch.bfloat16, device=dev)
-    ops.tc_gemm(prod, w, prod_rep, n, pooling, 2 * hidden, bias=post_cat.bias.detach().float().contiguous(), lda=2 * hidden, ldc=pooling,
-                epilogue=EPI_BF16, mul=union_features.float().contiguous() if use_vision else None, group_m=16, m_sub=2 if n > 128 else 1,
+    w = ops.pack_weight_bf16x3(post_cat.weight)
+    prod_rep = torch.empty(n, pooling, dtype=torch.float32, device=dev)
+    ops.tc_gemm(prod, w, prod_rep, n, pooling, 6 * hidden, bias=post_cat.bias.detach().float().contiguous(), lda=6 * hidden, ldc=pooling,
+                epilogue=EPI_F32, mul=union_features.float().contiguous() if use_vision else None, group_m=16, m_sub=2 if n > 128 else 1,
                 tag="post_cat")
     logits = rel_compress.logits(prod_rep)
     pair_pred = obj_preds.to(dev, torch.int32)[pair_idx.long()].contiguous() if freq_bias_weight is not None else None

@@ -55,8 +55,7 @@ def test_bayes_head_modules_match_torch():
                 if p.dim() == 1:
                     p.normal_(0, 0.1)
         a = m(h)
-        hb = h.to(torch.bfloat16).float()
-        w = lambda l: torch.nn.functional.linear(hb, l.weight.to(torch.bfloat16).float(), l.bias)
+        w = lambda l: torch.nn.functional.linear(h.double(), l.weight.double(), l.bias.double()).float()
         z1, z2, z3, z5 = w(m.fc3_1), w(m.fc3_2), w(m.fc3_3), w(m.fc5)
         if cls is sgb.BayesHead:
             ref = (z1, z2, z3, z5)
@@ -64,7 +63,7 @@ def test_bayes_head_modules_match_torch():
             s = torch.log_softmax(z5, 1)
             ref = (torch.log_softmax(z1, 1) + s[:, 1:2], torch.log_softmax(z2, 1) + s[:, 2:3], torch.log_softmax(z3, 1) + s[:, 3:4], s)
         for x, y in zip(a, ref):
-            assert float((x - y).abs().max()) <= 2e-3
+            assert float((x - y).detach().abs().max()) <= 1e-4           # bf16x3 split operands: near-fp32 accuracy
 
 
 @pytest.mark.parametrize("name", sorted(SGB_CASES))
