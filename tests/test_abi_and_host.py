@@ -170,3 +170,46 @@ def test_two_rank_gloo_sharded_counts_equal_single_process(tmp_path):
     single = np.concatenate((ev.counters(), t3.counters()))
     np.testing.assert_array_equal(np.load(out), single)
     assert single[tables.EV_NGT] > 0
+
+
+def test_formats_annotation_pkl_to_packed_window_roundtrip(tmp_path):
+    """N3: reference-format annotation file -> dataloader transforms -> packed CSR window -> HostBatch arrays."""
+    from scene_graph_commonsense_b200 import formats, pipeline
+    s = synthetic.make_image(3, 6, p_rel=0.7)
+    inv = {v: k for k, v in enumerate(formats.RELATION_FREQ2SCAT[:-1])}           # scat id -> frequency id
+    freq_rels = [torch.as_tensor([inv[int(v)] if int(v) >= 0 else -1 for v in r]) for r in s.relationships]
+    freq_rels[0][0] = 12                                                            # 'wears' must merge into 'wearing' (4)
+    annot = dict(image_depth=s.depth, categories=s.categories, super_categories=s.super_categories, bbox=s.bbox.float() + 0.4,
+                 relationships=freq_rels, subj_or_obj=s.subj_or_obj)
+    path = str(tmp_path / "1_annotations.pkl")
+    torch.save(annot, path)
+    got = formats.load_annotation_file(path, image_id=3)
+    assert torch.equal(got.bbox, s.bbox)                                            # dataloader.py:129 bbox.int() truncation
+    assert int(got.relationships[0][0]) == formats.RELATION_FREQ2SCAT[4]
+    for a, b in zip(got.relationships[1:], s.relationships[1:]):
+        assert torch.equal(a, b)
+    too_many = dict(annot, categories=torch.zeros(21, dtype=torch.int64))
+    assert formats.sample_from_annotation(too_many) is None and formats.sample_from_annotation(dict(annot, categories=s.categories[:1])) is None
+    got.relationships[0] = s.relationships[0]
+    packed = formats.pack_window([got, got])
+    formats.save_window(str(tmp_path / "w.npz"), packed)
+    hb = formats.host_batch_from_packed(formats.load_window(str(tmp_path / "w.npz")), pinned=False)
+    ref = pipeline.host_batch_from_samples([s, s], pinned=False, with_maps=False)
+    for k in ("box_offsets", "tri_offsets", "boxes", "cats", "supers", "box_img", "rel_tri", "dir_tri", "group_id"):
+        assert torch.equal(hb.t[k], ref.t[k]), k
+    assert hb.meta == ref.meta
+    d = formats.keys_to_commonsense_dict(tables.commonsense_violated_keys()[:50])
+    np.testing.assert_array_equal(np.sort(tables.dict_to_keys(d)), np.sort(tables.commonsense_violated_keys()[:50]))
+
+
+def test_checkpoint_names_cover_both_reference_spellings(tmp_path):
+    from scene_graph_commonsense_b200 import formats
+    args = synthetic.reference_args(run_mode="eval_cs")
+    args["training"]["checkpoint_path"] = str(tmp_path) + "/"
+    names = formats.checkpoint_candidates(args, 2)
+    assert names[0].endswith("HierRelationModel_CS_motif_2_0.pth") and names[1].endswith("HierRelationModel_CS_motif2_0.pth")
+    lin = torch.nn.Linear(4, 3)
+    torch.save({"module." + k: v for k, v in lin.state_dict().items()}, names[1])     # trainer's spelling + DDP prefix
+    lin2 = torch.nn.Linear(4, 3)
+    assert formats.load_checkpoint(lin2, args, 2) == names[1]
+    assert torch.equal(lin2.weight, lin.weight)

