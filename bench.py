@@ -89,9 +89,21 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_samples(rank, n_images=IMAGES_PER_GPU, boxes=BOXES, with_maps=True):
+WORKLOADS = {
+    # name: images per GPU, boxes (proposals) per image, SGDET-style?, pair chunk
+    "cfg2": dict(images=IMAGES_PER_GPU, boxes=BOXES, sgdet=False, chunk_pairs=16384,
+                 text="cfg2: PredCLS %d images x %d boxes per GPU (%d directed pairs/GPU/step), two-pass, eval_cs, reference batch skip rule"),
+    "cfg3": dict(images=8, boxes=100, sgdet=True, chunk_pairs=20480,
+                 text="cfg3: SGDET-style %d images x %d proposals per GPU (%d directed pairs/GPU/step, 20 GT boxes/image), two-pass, "
+                      "object-confidence add, synonym matching, top-100 triplets, eval_cs, reference batch skip rule"),
+}
+
+
+def make_samples(rank, n_images=IMAGES_PER_GPU, boxes=BOXES, with_maps=True, sgdet=False):
     from scene_graph_commonsense_b200 import synthetic
     ids = [rank * n_images + i for i in range(n_images)]
+    if sgdet:
+        return [synthetic.make_sgdet_image(i, 20, boxes, base_seed=0, p_rel=0.3, with_maps=with_maps) for i in ids]
     return synthetic.make_batch(ids, boxes, base_seed=0, p_rel=0.3, with_maps=with_maps)
 
 
@@ -160,10 +172,12 @@ def run_ours(args):
     sd = synthetic.head_state_dict(seed=0, logit_gain=40.0)
     packed = model.PackedHead(sd, dev)
     del sd
-    pipe = pipeline.RelationPipeline(packed, dev, commonsense=True, chunk_pairs=args.chunk_pairs, conv3_m_sub=args.conv3_m_sub,
-                                     overlap=not args.no_overlap)
-    samples = make_samples(rank)
-    host = pipeline.host_batch_from_samples(samples, skip_mode="batch")
+    wl = WORKLOADS[args.workload]
+    chunk_pairs = args.chunk_pairs or wl["chunk_pairs"]
+    pipe = pipeline.RelationPipeline(packed, dev, commonsense=True, chunk_pairs=chunk_pairs, conv3_m_sub=args.conv3_m_sub,
+                                     overlap=not args.no_overlap, predcls=not wl["sgdet"])
+    samples = make_samples(rank, wl["images"], wl["boxes"], sgdet=wl["sgdet"])
+    host = pipeline.host_batch_from_samples(samples, skip_mode="batch", sgdet=wl["sgdet"])
     del samples
     batch = host.to_device(dev)
     torch.cuda.synchronize()
@@ -253,11 +267,11 @@ def run_ours(args):
                 "frac": achieved / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["source"] + " sustained bf16",
                 "avg_launch_ms": avg_ms, "launches_timed": len(conv3), "algorithmic_flop_per_launch": pairs_per_launch * FLOP_PAIR_CONV3}
     breakdown = {t: {"launches": len(v), "ms_per_step": float(np.sum(v)) / args.steps} for t, v in sorted(per_tag.items())}
-    flop_step = IMAGES_PER_GPU * FLOP_IMG + IMAGES_PER_GPU * BOXES * FLOP_BOX + pairs_step * FLOP_PAIR
+    flop_step = wl["images"] * FLOP_IMG + wl["images"] * wl["boxes"] * FLOP_BOX + pairs_step * FLOP_PAIR
     m = pipeline.metrics_from_counters(counters_final)
 
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2":
         v, mean_t, sample, cores = cpu_reference_run(1, 0, budget_s=20.0)
         cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
 
@@ -265,11 +279,10 @@ def run_ours(args):
         "metric": "relation_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "cfg2: PredCLS %d images x %d boxes per GPU (%d directed pairs/GPU/step), two-pass, eval_cs, "
-                               "reference batch skip rule" % (IMAGES_PER_GPU, BOXES, pairs_step),
+        "config": {"workload": wl["text"] % (wl["images"], wl["boxes"], pairs_step),
                    "parallelism": "images sharded over %d GPU(s), one int64[765] all-reduce per step" % world,
                    "l2": "no explicit flush: each step streams >10 GB of activations/weights (>> 126 MB L2)",
-                   "weights": "random init, trained-scale logits (seed 0)", "chunk_pairs": args.chunk_pairs,
+                   "weights": "random init, trained-scale logits (seed 0)", "chunk_pairs": chunk_pairs,
                    "pool_gemm_overlap": not args.no_overlap, "conv3_m_sub": args.conv3_m_sub},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes * world,
                 "d2h_bytes_per_step": (tables.COUNTER_SIZE * 8 + 4) * world, "ms_per_step": t_e2e / args.steps * 1e3},
@@ -300,7 +313,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk-pairs", type=int, default=16384)
+    ap.add_argument("--chunk-pairs", type=int, default=0, help="pairs per conv3/fc1 chunk (0 = the workload's default)")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="cfg2 = the configuration BASELINE.json's metric is quoted on (default); cfg3 = SGDET-shaped scaling case")
     ap.add_argument("--conv3-m-sub", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")

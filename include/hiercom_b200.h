@@ -254,6 +254,63 @@ int hc_sgb_rank_match(const int32_t* ranked, const uint8_t* reject, const int32_
                       int32_t* img_hits, int32_t* img_ngt, int32_t* img_hits_pc, int32_t* img_cnt_pc,
                       hc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * N2 - SGDET / SGCLS proposal front-end that feeds the path (evaluate.py:311-370 == :545-591; the reference runs it
+ * as Python loops with one device sync per element).
+ *
+ * hc_detr_proposals: DETR head outputs -> per-image NMS-ed proposal lists in padded staging + CSR offsets.
+ *   pred_logits f32 [n_images, n_queries, num_classes+1] (last class = "no object"), pred_boxes f32
+ *   [n_images, n_queries, 4] = (cx,cy,w,h) in 0..1.  Per query: softmax, has_object = argmax < num_classes
+ *   (evaluate.py:311-312), top-`topk_cat` labels/probabilities in (value desc, class asc) order (:313-316), labels
+ *   remapped through label_map int32 [num_classes+1] (dataset_utils.py:606-614, :319-323), boxes converted to
+ *   (x1,x2,y1,y2) = clamp(c -/+ size/2, 0, 1) * feature_size in fp32 (:327-334); entries whose label maps to
+ *   num_classes are dropped (:325,343-347); per-class greedy NMS with torchvision.ops.nms semantics in fp32
+ *   (suppress iff inter/(area_i+area_j-inter) > nms_thresh, visit order = confidence desc, stable) (:350-367).
+ *   Output order per image = (label asc, confidence desc, entry asc), the reference's hstack order.
+ *   E = n_queries*topk_cat <= 1024.  Workspaces ws_* and staging st_* hold n_images*E entries (boxes 4 floats each);
+ *   st_count [n_images]; box_offsets [n_images+1] receives the CSR offsets of the surviving proposals.
+ *   Deviation: an image without any object query keeps its slot with 0 proposals (the reference drops it from its
+ *   lists, misaligning them with the per-image targets).
+ * hc_proposals_pack: staging -> CSR arrays sized box_offsets[n_images]: cats int32, conf f32, box_f f32 [n,4],
+ *   box_i int32 [n,4] (int() truncation, the form hc_pairs_enumerate / hc_topk_match take), supers int8 [n,4] from
+ *   sub2super int8 [num_classes,4] (evaluate.py:368-370; NULL to skip), box_img int32 (NULL to skip).
+ */
+int hc_detr_proposals(const float* pred_logits, const float* pred_boxes, int32_t n_images, int32_t n_queries,
+                      int32_t num_classes, int32_t topk_cat, const int32_t* label_map, int32_t feature_size,
+                      double nms_thresh, int32_t* ws_label, float* ws_conf, float* ws_box, uint8_t* ws_valid,
+                      int32_t* st_label, float* st_conf, float* st_box, int32_t* st_count, int32_t* box_offsets,
+                      hc_stream_t stream);
+int hc_proposals_pack(const int32_t* st_label, const float* st_conf, const float* st_box, const int32_t* box_offsets,
+                      int32_t n_images, int32_t n_entries, const int8_t* sub2super, int32_t num_classes, int32_t* cats,
+                      float* conf, float* box_f, int32_t* box_i, int8_t* supers, int32_t* box_img, hc_stream_t stream);
+
+/* utils.py:376-422 match_object_categories (SGCLS, evaluate.py:605): for every GT box, the two proposals of largest
+ * rasterised-grid IoU (utils.py:58-74; double ratio rounded to fp32) under (IoU desc, proposal index asc); if the two
+ * IoUs are equal both labels are emitted and the GT box is repeated, else the best one; confidence = proposal
+ * confidence * IoU (fp32).  Phase 1 fills ws_idx/ws_iou [n_gt,2], out_offsets [n_images+1] and *status (device int32):
+ * 1 when an image with GT boxes has fewer than two proposals - the reference then returns (None, None, None) and
+ * skips the whole batch (utils.py:402-403, evaluate.py:606-607).  Phase 2 writes the out_offsets[n_images] rows:
+ * out_box = the (repeated) GT boxes, out_src = GT box index of each row, out_supers / out_img optional. */
+int hc_match_object_categories(const float* prop_box, const int32_t* prop_offsets, const int32_t* gt_box,
+                               const int32_t* gt_offsets, int32_t n_images, int32_t feature_size, int32_t* ws_idx,
+                               float* ws_iou, int32_t* ws_count, int32_t* out_offsets, int32_t* status,
+                               hc_stream_t stream);
+int hc_match_object_categories_fill(const int32_t* prop_cats, const float* prop_conf, const int32_t* prop_offsets,
+                                    const int32_t* gt_box, const int32_t* gt_offsets, int32_t n_images,
+                                    const int32_t* ws_idx, const float* ws_iou, const int32_t* out_offsets,
+                                    const int8_t* sub2super, int32_t num_classes, int32_t* out_cats, float* out_conf,
+                                    int32_t* out_box, int32_t* out_src, int8_t* out_supers, int32_t* out_img,
+                                    hc_stream_t stream);
+
+/* utils.py:294-352 match_target_sgd: flat GT triplet tables in the reference's (g,e) loop order from the packed
+ * triangle arrays (rel_tri / dir_tri at t = g(g-1)/2+e as in hc_pairs_enumerate): a triplet where dir == 1
+ * (g subject) or dir == 0 (e subject).  Reference quirk kept: g stops at N-2 (utils.py:312 loops over
+ * range(len(relationships[image])) = N-1 rows).  gt_label/gt_sub/gt_obj must hold sum_i T_i entries; gt_sub/gt_obj are
+ * global box ids; gt_offsets [n_images+1]. */
+int hc_targets_flat(const int8_t* dir_tri, const int32_t* rel_tri, const int32_t* tri_offsets,
+                    const int32_t* box_offsets, int32_t n_images, int32_t* ws_count, int32_t* gt_offsets,
+                    int32_t* gt_label, int32_t* gt_sub, int32_t* gt_obj, hc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,11 @@ SIGNATURES = {
     "hc_sgb_candidates": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "hc_sgb_rank_match": (C.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I32, _I32, _I32, _I32,
                                     _P, _P, _P, _P, _P, _P]),
+    "hc_detr_proposals": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _I32, _D, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "hc_proposals_pack": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "hc_match_object_categories": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "hc_match_object_categories_fill": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
+    "hc_targets_flat": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -296,3 +296,81 @@ def sgb_rank_match(ranked, reject, pair_offsets, cand_score, cand_label, cand_ro
           "hc_sgb_rank_match")
     _count()
     return final_rank, hits, ngt, hits_pc, cnt_pc
+
+
+# ------------------------------------------------------------------------------------------ proposal front-end (N2)
+def detr_proposals(pred_logits, pred_boxes, label_map, sub2super=None, num_classes=150, topk_cat=2, feature_size=32,
+                   nms_thresh=0.5):
+    """evaluate.py:311-370.  Returns CSR device arrays of the surviving proposals (one [B+1]-int D2H read sizes them)."""
+    require_cuda(pred_logits, pred_boxes, label_map, sub2super)
+    pred_logits, pred_boxes = pred_logits.contiguous().float(), pred_boxes.contiguous().float()
+    b, q = pred_logits.shape[0], pred_logits.shape[1]
+    if pred_logits.shape[2] != num_classes + 1 or tuple(pred_boxes.shape) != (b, q, 4):
+        raise RuntimeError("hiercom_b200 detr_proposals: pred_logits must be [B,Q,num_classes+1] and pred_boxes [B,Q,4]")
+    dev = pred_logits.device
+    e = q * topk_cat
+    i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+    f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    ws_label, ws_conf, ws_box, ws_valid = i32(b * e), f32(b * e), f32(b * e, 4), torch.empty(b * e, dtype=torch.uint8, device=dev)
+    st_label, st_conf, st_box, st_count, offsets = i32(b * e), f32(b * e), f32(b * e, 4), i32(b), i32(b + 1)
+    check(_lib.load().hc_detr_proposals(ptr(pred_logits), ptr(pred_boxes), b, q, num_classes, topk_cat, ptr(label_map), feature_size,
+                                        float(nms_thresh), ptr(ws_label), ptr(ws_conf), ptr(ws_box), ptr(ws_valid), ptr(st_label),
+                                        ptr(st_conf), ptr(st_box), ptr(st_count), ptr(offsets), stream_ptr()), "hc_detr_proposals")
+    _count(3)
+    offsets_host = offsets.cpu().numpy()
+    n = int(offsets_host[-1])
+    cats, conf, box_f, box_i = i32(max(n, 1)), f32(max(n, 1)), f32(max(n, 1), 4), i32(max(n, 1), 4)
+    supers = torch.empty(max(n, 1), 4, dtype=torch.int8, device=dev) if sub2super is not None else None
+    box_img = i32(max(n, 1))
+    check(_lib.load().hc_proposals_pack(ptr(st_label), ptr(st_conf), ptr(st_box), ptr(offsets), b, e, ptr(sub2super), num_classes,
+                                        ptr(cats), ptr(conf), ptr(box_f), ptr(box_i), ptr(supers), ptr(box_img), stream_ptr()),
+          "hc_proposals_pack")
+    _count()
+    return dict(n=n, offsets=offsets, offsets_host=offsets_host, cats=cats[:n], conf=conf[:n], box_f=box_f[:n], box_i=box_i[:n],
+                supers=None if supers is None else supers[:n], box_img=box_img[:n])
+
+
+def match_object_categories(prop_cats, prop_conf, prop_box, prop_offsets, gt_box, gt_offsets, sub2super=None, num_classes=150,
+                            feature_size=32):
+    """utils.py:376-422 on CSR device arrays.  Returns None when the reference would return (None, None, None)."""
+    require_cuda(prop_cats, prop_conf, prop_box, prop_offsets, gt_box, gt_offsets, sub2super)
+    dev = prop_box.device
+    b = prop_offsets.numel() - 1
+    n_gt = gt_box.shape[0]
+    i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+    ws_idx, ws_iou = i32(max(n_gt, 1), 2), torch.empty(max(n_gt, 1), 2, dtype=torch.float32, device=dev)
+    ws_count, out_offsets, status = i32(b), i32(b + 1), i32(1)
+    check(_lib.load().hc_match_object_categories(ptr(prop_box), ptr(prop_offsets), ptr(gt_box), ptr(gt_offsets), b, feature_size,
+                                                 ptr(ws_idx), ptr(ws_iou), ptr(ws_count), ptr(out_offsets), ptr(status), stream_ptr()),
+          "hc_match_object_categories")
+    _count(2)
+    host = torch.cat((out_offsets, status)).cpu().numpy()        # one D2H read: sizes + the reference's "None" condition
+    if int(host[-1]) != 0:
+        return None
+    offsets_host = host[:-1]
+    n = int(offsets_host[-1])
+    cats, conf, box, src = i32(max(n, 1)), torch.empty(max(n, 1), dtype=torch.float32, device=dev), i32(max(n, 1), 4), i32(max(n, 1))
+    supers = torch.empty(max(n, 1), 4, dtype=torch.int8, device=dev) if sub2super is not None else None
+    img = i32(max(n, 1))
+    check(_lib.load().hc_match_object_categories_fill(ptr(prop_cats), ptr(prop_conf), ptr(prop_offsets), ptr(gt_box), ptr(gt_offsets), b,
+                                                      ptr(ws_idx), ptr(ws_iou), ptr(out_offsets), ptr(sub2super), num_classes,
+                                                      ptr(cats), ptr(conf), ptr(box), ptr(src), ptr(supers), ptr(img), stream_ptr()),
+          "hc_match_object_categories_fill")
+    _count()
+    return dict(n=n, offsets=out_offsets, offsets_host=offsets_host, cats=cats[:n], conf=conf[:n], box_i=box[:n], src=src[:n],
+                supers=None if supers is None else supers[:n], box_img=img[:n])
+
+
+def targets_flat(dir_tri, rel_tri, tri_offsets, box_offsets):
+    """utils.py:294-352 on the packed triangle arrays -> (gt_offsets [B+1], label, sub, obj) device arrays; label/sub/obj are
+    over-allocated to sum T_i entries and valid up to gt_offsets[-1] (no host sync here)."""
+    require_cuda(dir_tri, rel_tri, tri_offsets, box_offsets)
+    dev = dir_tri.device
+    b = box_offsets.numel() - 1
+    cap = max(dir_tri.numel(), 1)
+    i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+    ws_count, gt_offsets, label, sub, obj = i32(b), i32(b + 1), i32(cap), i32(cap), i32(cap)
+    check(_lib.load().hc_targets_flat(ptr(dir_tri), ptr(rel_tri), ptr(tri_offsets), ptr(box_offsets), b, ptr(ws_count), ptr(gt_offsets),
+                                      ptr(label), ptr(sub), ptr(obj), stream_ptr()), "hc_targets_flat")
+    _count(3)
+    return gt_offsets, label, sub, obj

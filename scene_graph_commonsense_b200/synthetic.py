@@ -117,6 +117,47 @@ def make_sgdet_image(image_id, num_gt, num_prop, base_seed=0, p_rel=0.3, with_ma
     return s
 
 
+def make_detr_outputs(samples, num_queries=100, base_seed=0, p_noobj=0.35, p_dup=0.3, p_second_noobj=0.25,
+                      num_classes=tables.NUM_OBJ, logit_gain=6.0):
+    """Synthetic DETR head outputs for a list of GT samples (the inputs of the SGDET/SGCLS proposal front-end,
+    evaluate.py:304-332): `pred_logits` f32 [B,Q,num_classes+1] in DETR's ALPHABETICAL label space (last = no object) and
+    `pred_boxes` f32 [B,Q,4] = (cx,cy,w,h) in 0..1.  Queries are jittered copies of the image's GT boxes with the GT
+    label (mapped back to the alphabetical id) and a random runner-up label, duplicates of an earlier query (so the
+    per-class NMS has work), or "no object" queries; the runner-up of some object queries is "no object" (exercises the
+    label != 150 mask after the top-2 expansion, evaluate.py:323,341-345)."""
+    fre2alp = np.argsort(tables.alp2fre())          # inverse permutation: frequency id -> alphabetical id
+    logits = torch.empty(len(samples), num_queries, num_classes + 1)
+    boxes = torch.empty(len(samples), num_queries, 4)
+    for b, s in enumerate(samples):
+        g = _gen(base_seed + 104729, s.image_id)
+        n_gt = s.bbox.shape[0]
+        lg = torch.randn(num_queries, num_classes + 1, generator=g)
+        bx = torch.empty(num_queries, 4)
+        for q in range(num_queries):
+            r = float(torch.rand(1, generator=g))
+            if q > 0 and r < p_dup:                                   # near-duplicate of an earlier query
+                src = int(torch.randint(0, q, (1,), generator=g))
+                bx[q] = torch.clamp(bx[src] + 0.01 * torch.randn(4, generator=g), 0.02, 0.98)
+                lg[q] = lg[src] + 0.3 * torch.randn(num_classes + 1, generator=g)
+                continue
+            if n_gt > 0 and r < 1.0 - p_noobj:
+                k = int(torch.randint(0, n_gt, (1,), generator=g))
+                x0, x1, y0, y1 = [float(v) for v in s.bbox[k]]
+                box = torch.tensor([(x0 + x1) / 2, (y0 + y1) / 2, x1 - x0, y1 - y0]) / FEATURE_SIZE
+                top = int(fre2alp[int(s.categories[k])])
+            else:
+                box = torch.rand(4, generator=g) * torch.tensor([1.0, 1.0, 0.5, 0.5])
+                top = num_classes if r >= 1.0 - p_noobj else int(torch.randint(0, num_classes, (1,), generator=g))
+            bx[q] = torch.clamp(box + 0.02 * torch.randn(4, generator=g), 0.0, 1.0)
+            lg[q, top] += logit_gain
+            second = num_classes if float(torch.rand(1, generator=g)) < p_second_noobj else int(
+                torch.randint(0, num_classes, (1,), generator=g))
+            if second != top:
+                lg[q, second] += 0.6 * logit_gain
+        logits[b], boxes[b] = lg, bx
+    return logits, boxes
+
+
 def make_batch(image_ids, num_boxes, base_seed=0, p_rel=0.3, with_maps=True):
     """`num_boxes` may be an int or a per-image sequence (ragged batches)."""
     if isinstance(num_boxes, int):

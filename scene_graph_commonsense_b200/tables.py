@@ -83,6 +83,12 @@ def sub2super_table():
     return _load("sub2super.npy")
 
 
+def alp2fre():
+    """dataset_utils.object_class_alp2fre (dataset_utils.py:606-614) as int32[151]: DETR's alphabetical object label ->
+    the frequency-ordered label of the relation path; 150 ("no object") maps to itself (evaluate.py:319-323)."""
+    return _load("alp2fre.npy")
+
+
 def vg_predicate_counts():
     """utils.py:258-265 get_num_each_class_reordered (VG branch); only used to draw synthetic GT predicates."""
     return _load("vg_predicate_counts.npy")

@@ -26,3 +26,11 @@ SGB_CASES = {
     "sgb_case_a": dict(num_objs=[6, 9, 4, 12], seed=0),
     "sgb_case_b": dict(num_objs=[3, 14, 2, 8, 5], seed=1, empty_gt=2),
 }
+
+FRONTEND_CASES = {
+    # DETR outputs -> proposals (evaluate.py:309-368), match_object_categories, match_target_sgd.
+    # The reference hard-codes 100 queries (`.view(-1, 100, topk_cat)`, evaluate.py:311), so raggedness comes from p_noobj.
+    "fe_dense": dict(ids=[80, 81, 82], n_gt=[9, 14, 6], queries=100),
+    "fe_ragged": dict(ids=[83, 84, 85, 86], n_gt=[3, 12, 7, 2], queries=100, kw=dict(p_noobj=0.8, p_dup=0.45)),
+    "fe_sparse": dict(ids=[87, 88], n_gt=[5, 4], queries=100, kw=dict(p_noobj=0.96, p_dup=0.1, p_second_noobj=0.6)),
+}

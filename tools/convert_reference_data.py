@@ -10,6 +10,8 @@ Sources (reference file:line that consumes each table):
   datasets/vg_scene_graph_annot/train_triplets.pt      dict{'s_p_o'}   evaluator.py:37,342
   datasets/vg_scene_graph_annot/sub2super_cat_dict.pt  dict{c:[sc..]}  evaluate.py:288,368
   utils.get_num_each_class_reordered (VG predicate counts)             utils.py:258-265
+  dataset_utils.object_class_alp2fre (DETR alphabetical -> frequency object labels, 150 -> 150 = "no object")
+                                                                       evaluate.py:289,319-322; dataset_utils.py:606-614
 
 Key packing: key = (s*50 + p)*150 + o  with s,o in [0,150), p in [0,50).
 """
@@ -69,6 +71,15 @@ def main():
     finally:
         os.chdir(cwd)
     np.save(os.path.join(OUT, "vg_predicate_counts.npy"), freq)
+    os.chdir(REF)
+    try:
+        import dataset_utils as ref_du
+        a2f = ref_du.object_class_alp2fre()
+    finally:
+        os.chdir(cwd)
+    tab = np.array([a2f[i] for i in range(151)], dtype=np.int32)
+    assert sorted(tab.tolist()) == list(range(151)) and tab[150] == 150
+    np.save(os.path.join(OUT, "alp2fre.npy"), tab)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
