@@ -153,13 +153,18 @@ int hc_pair_relu_pool_tiled(const void* u, const void* v, const float* bias, con
  * flat [fc3; fc4].  row_sub/row_obj index box_cat / box_super ([n_box,4] int8, -1 padded; NULL = no
  * super-class columns, model.py:125-128).  logsig = log(sigmoid(conn)) (train_utils.py:190).
  * fc2_bias == NULL: fc2_raw already is the hidden vector - no bias/embedding/ReLU (BayesianHead, model.py:24-34).
+ * box_emb (optional) f32 [n_box, 2*hidden] from hc_box_label_embed: the label columns summed once per box
+ * ([as subject | as object]); when given, a row adds box_emb[row_sub][0:hidden] + box_emb[row_obj][hidden:] instead of
+ * gathering up to ten embedding rows (same sum, different fp32 association).
  */
 int hc_hier_head(const float* fc2_raw, int64_t ld_raw, int32_t n_rows, int32_t hidden, const float* fc2_bias,
                  const float* emb, int32_t num_obj, int32_t num_super, const int32_t* row_sub,
                  const int32_t* row_obj, const int32_t* box_cat, const int8_t* box_super, const float* w_heads,
                  const float* b_heads, int32_t n_geo, int32_t n_pos, int32_t n_sem, int32_t flat, float t1,
                  float t2, float t3, float* relation, float* super_rel, float* connectivity, float* logsig,
-                 float* pred_out, hc_stream_t stream);
+                 float* pred_out, const float* box_emb, hc_stream_t stream);
+int hc_box_label_embed(const float* emb, int32_t num_obj, int32_t num_super, const int32_t* box_cat,
+                       const int8_t* box_super, int32_t n_box, int32_t hidden, float* out, hc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * R8 + R9 (+ R10's connectivity add) - candidate construction (evaluator.py:124-138,157-179,231-266,646-649).

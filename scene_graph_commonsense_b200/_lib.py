@@ -43,7 +43,8 @@ SIGNATURES = {
     "hc_pair_lut_build": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "hc_pair_relu_pool_tiled": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "hc_hier_head": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32,
-                               _F, _F, _F, _P, _P, _P, _P, _P, _P]),
+                               _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
+    "hc_box_label_embed": (C.c_int, [_P, _I32, _I32, _P, _P, _I32, _I32, _P, _P]),
     "hc_candidates": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                 _I32, _P]),
     "hc_topk_match": (C.c_int, [_P, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I32, _I32, _P, _I32,

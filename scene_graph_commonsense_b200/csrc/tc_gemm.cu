@@ -13,6 +13,7 @@
 //
 // CTA tile = (MS*128) x BN: MS 128-row sub-tiles share every B stage (halves L2->smem weight traffic for MS=2).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "hc_common.cuh"
 
@@ -51,6 +52,7 @@ struct Params {
   const float* mul;              // optional elementwise multiplier [M, ld_mul] applied after bias/activation
   long long ld_mul;
   void* out;
+  int dbg_skip_a;                // TIMING EXPERIMENT ONLY (env HC_DEBUG_SKIP_A): conv A tiles are loaded for ky == 0 only -> wrong results
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -152,6 +154,33 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
+// bias + activation (+ elementwise multiplier) on one lane's 32 accumulator columns -> 64 bytes of bf16
+template <int ACT>
+__device__ __forceinline__ void store_bf16_row(const uint32_t (&r)[32], const float* __restrict__ bias, const float* __restrict__ mul,
+                                               __nv_bfloat16* __restrict__ dst) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[8 * i + t]);
+    if (bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * i), b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * i + 1);
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      if (ACT == HC_ACT_RELU) v[t] = fmaxf(v[t], 0.0f);
+      if (ACT == HC_ACT_TANH) v[t] = tanhf(v[t]);
+    }
+    if (mul) {
+      const float4 m0 = __ldg(reinterpret_cast<const float4*>(mul) + 2 * i), m1 = __ldg(reinterpret_cast<const float4*>(mul) + 2 * i + 1);
+      v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w; v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
+    }
+    *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
+                                                        pack_bf16(v[6], v[7]));
+  }
+}
+
 // tile id -> (m block, n block): bands of `group_m` m-blocks; inside a band the n index is the slow one, so a
 // wave of consecutive tile ids shares few B column-panels and a bounded set of A row-panels through L2.
 __device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_blk, int& n_blk) {
@@ -218,8 +247,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + MS * A_SUB_BYTES;
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          if (p.mode == HC_GEMM_CONV3) {
+          const bool skip_a = p.dbg_skip_a && p.mode == HC_GEMM_CONV3 && (kb / cblks) >= 3;
+          mbar_expect_tx(full_bar(stage), skip_a ? C::B_BYTES : C::STAGE_BYTES);
+          if (skip_a) {
+          } else if (p.mode == HC_GEMM_CONV3) {
             int tap = kb / cblks, cb = kb - tap * cblks;
             int ky = tap / 3, kx = tap - ky * 3;
 #pragma unroll
@@ -276,6 +307,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
       tile_coords(p, tile, m_blk, n_blk);
+      int t_img = 0, t_y0 = 0, t_x0 = 0;                  // conv: tile origin (image, first pixel row / column)
+      if (p.mode == HC_GEMM_CONV3) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        t_img = m_blk / per_img;
+        const int rr = m_blk - t_img * per_img;
+        t_y0 = (rr / p.tiles_x) * (8 * MS);
+        t_x0 = (rr % p.tiles_x) * 16;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int n0 = n_blk * BN;
@@ -314,31 +353,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               float b = fmaxf(o[2 * i + 1] + __ldg(p.bias + cbase + 2 * i + 1), 0.0f);
               w[i] = pack_bf16(a, b);
             }
-            int per_img = p.tiles_x * p.tiles_y;
-            int img = m_blk / per_img;
-            int rr = m_blk - img * per_img;
-            int py = ((rr / p.tiles_x) * (8 * MS) + 8 * j) / 2 + q;      // pooled row
-            int px = ((rr % p.tiles_x) * 16) / 2 + ((lane & 15) >> 1);   // pooled col
+            const int py = (t_y0 + 8 * j) / 2 + q;                      // pooled row
+            const int px = t_x0 / 2 + ((lane & 15) >> 1);               // pooled col
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                 (((long long)img * (p.H / 2) + py) * (p.W / 2) + px) * p.ldc + p.c_off + cbase;
+                                 (((long long)t_img * (p.H / 2) + py) * (p.W / 2) + px) * p.ldc + p.c_off + cbase;
             *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
           } else {
-            long long row;
-            bool valid;
-            if (p.mode == HC_GEMM_CONV3) {
-              int per_img = p.tiles_x * p.tiles_y;
-              int img = m_blk / per_img;
-              int rr = m_blk - img * per_img;
-              int y = (rr / p.tiles_x) * (8 * MS) + 8 * j + (row_in_tile >> 4);
-              int x = (rr % p.tiles_x) * 16 + (row_in_tile & 15);
-              row = ((long long)img * p.H + y) * p.W + x;
-              valid = true;
-            } else {
-              row = (long long)(m_blk * MS + j) * BM + row_in_tile;
-              valid = row < p.M;
-            }
-            if (valid) {
-              if (p.epi == HC_EPI_F32) {
+            // output row of tile row `tr` (plain: GEMM row; conv: NHWC pixel index), -1 when outside M
+            auto out_row = [&](int tr) -> long long {
+              if (p.mode == HC_GEMM_CONV3)
+                return ((long long)t_img * p.H + (t_y0 + 8 * j + (tr >> 4))) * p.W + (t_x0 + (tr & 15));
+              long long row = (long long)(m_blk * MS + j) * BM + tr;
+              return row < p.M ? row : -1;
+            };
+            const long long row = out_row(row_in_tile);
+            if (p.epi == HC_EPI_F32) {
+              if (row >= 0) {
                 float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + p.c_off + col0;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -346,8 +376,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   v.x = __uint_as_float(r[4 * i]); v.y = __uint_as_float(r[4 * i + 1]);
                   v.z = __uint_as_float(r[4 * i + 2]); v.w = __uint_as_float(r[4 * i + 3]);
                   if (p.bias) {
-                    v.x += __ldg(p.bias + col0 + 4 * i); v.y += __ldg(p.bias + col0 + 4 * i + 1);
-                    v.z += __ldg(p.bias + col0 + 4 * i + 2); v.w += __ldg(p.bias + col0 + 4 * i + 3);
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + i);
+                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                   }
                   if (p.mul) {
                     float4 mm = __ldg(reinterpret_cast<const float4*>(p.mul + row * p.ld_mul + col0 + 4 * i));
@@ -355,25 +385,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   }
                   *reinterpret_cast<float4*>(dst + 4 * i) = v;
                 }
-              } else {
+              }
+            } else {
+              if (row >= 0) {
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + p.c_off + col0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  uint32_t w[4];
-#pragma unroll
-                  for (int t = 0; t < 4; ++t) {
-                    int c = 8 * i + 2 * t;
-                    float a = __uint_as_float(r[c]), b = __uint_as_float(r[c + 1]);
-                    if (p.bias) { a += __ldg(p.bias + col0 + c); b += __ldg(p.bias + col0 + c + 1); }
-                    a = apply_act(a, p.act); b = apply_act(b, p.act);
-                    if (p.mul) {
-                      float2 mm = __ldg(reinterpret_cast<const float2*>(p.mul + row * p.ld_mul + col0 + c));
-                      a *= mm.x; b *= mm.y;
-                    }
-                    w[t] = pack_bf16(a, b);
-                  }
-                  *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
+                const float* mul_row = p.mul ? p.mul + row * p.ld_mul + col0 : nullptr;
+                // the activation switch is hoisted out of the element loops (a branch per element serialises the
+                // single epilogue warp of each scheduler)
+                if (p.act == HC_ACT_RELU) store_bf16_row<HC_ACT_RELU>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst);
+                else if (p.act == HC_ACT_TANH) store_bf16_row<HC_ACT_TANH>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst);
+                else store_bf16_row<HC_ACT_NONE>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst);
               }
             }
           }
@@ -456,6 +477,7 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   HC_REQUIRE(d->n % 128 == 0, HC_E_SHAPE, "hc_tc_gemm: N must be a multiple of 128");
   HC_REQUIRE(aligned16(d->a) && aligned16(d->b) && aligned16(d->out), HC_E_ALIGN, "hc_tc_gemm: a/b/out must be 16-byte aligned");
   HC_REQUIRE(d->ldc % 8 == 0 && d->c_off % 8 == 0, HC_E_ALIGN, "hc_tc_gemm: ldc and c_off must be multiples of 8");
+  HC_REQUIRE(!d->bias || aligned16(d->bias), HC_E_ALIGN, "hc_tc_gemm: bias must be 16-byte aligned");
   HC_REQUIRE(d->epilogue >= 0 && d->epilogue <= 2, HC_E_SHAPE, "hc_tc_gemm: unknown epilogue");
   HC_REQUIRE(d->epilogue != HC_EPI_POOL_BF16 || (d->mode == HC_GEMM_CONV3 && d->bias), HC_E_SHAPE,
              "hc_tc_gemm: pooled epilogue needs conv mode and a bias");
@@ -471,6 +493,11 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   p.mode = d->mode; p.epi = d->epilogue; p.act = d->act;
   p.ldc = d->ldc; p.c_off = d->c_off; p.bias = d->bias; p.out = d->out;
   p.mul = d->mul; p.ld_mul = d->ld_mul;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("HC_DEBUG_SKIP_A"); dbg = (e && e[0] == '1') ? 1 : 0; }
+    p.dbg_skip_a = dbg;
+  }
   HC_REQUIRE(!d->mul || (d->epilogue != HC_EPI_POOL_BF16 && d->mode == HC_GEMM_PLAIN && d->ld_mul % 4 == 0 && aligned16(d->mul)), HC_E_SHAPE,
              "hc_tc_gemm: mul needs a plain GEMM, a non-pooled epilogue and a 16-byte aligned [M, ld_mul] f32 operand");
   p.tiles_n = p.N / BN;

@@ -167,10 +167,18 @@ def hier_head(fc2_raw, fc2_bias, emb, row_sub, row_obj, box_cat, box_super, w_he
     conn = torch.empty(n, dtype=torch.float32, device=dev)
     logsig = torch.empty(n, dtype=torch.float32, device=dev)
     pred = torch.empty(n, hidden, dtype=torch.float32, device=dev) if want_pred else None
+    box_emb = None
+    if fc2_bias is not None:
+        # label columns of fc2 summed once per box ([as subject | as object]); a pair then adds two rows instead of <= 10
+        n_box = box_cat.numel()
+        box_emb = torch.empty(n_box, 2 * hidden, dtype=torch.float32, device=dev)
+        check(_lib.load().hc_box_label_embed(ptr(emb), num_obj, num_super, ptr(box_cat), ptr(box_super), n_box, hidden, ptr(box_emb),
+                                             stream_ptr()), "hc_box_label_embed")
+        _count()
     check(_lib.load().hc_hier_head(ptr(fc2_raw), fc2_raw.stride(0), n, hidden, ptr(fc2_bias), ptr(emb), num_obj, num_super,
                                    ptr(row_sub), ptr(row_obj), ptr(box_cat), ptr(box_super), ptr(w_heads), ptr(b_heads),
                                    splits[0], splits[1], splits[2], int(flat), temps[0], temps[1], temps[2], ptr(relation),
-                                   ptr(sup), ptr(conn), ptr(logsig), ptr(pred), stream_ptr()), "hc_hier_head")
+                                   ptr(sup), ptr(conn), ptr(logsig), ptr(pred), ptr(box_emb), stream_ptr()), "hc_hier_head")
     _count()
     return relation, sup, conn, logsig, pred
 

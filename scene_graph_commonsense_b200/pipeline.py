@@ -139,7 +139,7 @@ class RelationPipeline:
 
     def __init__(self, packed: Optional[PackedHead], device, commonsense=True, aligned_keys=None, violated_keys=None,
                  top_k=tables.TOP_K, iou_thresh=0.5, feature_size=32, chunk_pairs=16384, predcls=True, conv3_m_sub=2,
-                 hier=None, splits=None, overlap=True):
+                 hier=None, splits=None, overlap=True, conv2_m_sub=1):
         self.packed = packed
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -150,6 +150,7 @@ class RelationPipeline:
         self.chunk_pairs = int(chunk_pairs)
         self.predcls = predcls
         self.conv3_m_sub = conv3_m_sub
+        self.conv2_m_sub = conv2_m_sub      # short K (1152): 128-row tiles keep two TMEM stages, so the bf16 epilogue overlaps the next tile
         self.overlap = overlap
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
         self.hier = (not packed.flat if packed is not None else True) if hier is None else bool(hier)
@@ -181,7 +182,7 @@ class RelationPipeline:
         v = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=self.device)
         for out, w, base in ((u, pk.w2s, 0), (v, pk.w2o, 128)):
             ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, ldc=512, mode=GEMM_CONV3, epilogue=EPI_BF16, act=ACT_NONE,
-                        n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=2, tag="conv2_half")
+                        n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=self.conv2_m_sub, tag="conv2_half")
         return u, v
 
     def _image_chunks(self, offsets_host):
