@@ -126,7 +126,9 @@ int hc_box_select(const void* t_img, const int32_t* boxes, const int32_t* box_im
 
 /* model.py:143-144 after the subject/object split of conv2_1:
  * out[p] = maxpool2x2(relu(U[pair_sub[p]] + V[pair_obj[p]] + bias)),  U,V [n_box, fs, fs, C] bf16,
- * out [n_pairs, fs/2, fs/2, C] bf16. */
+ * out [n_pairs, fs/2, fs/2, C] bf16.  bias == NULL: V already includes the conv2 bias (added in fp32 in the object-half
+ * GEMM epilogue); the kernel then runs on packed bf16x2 adds/max - bit-identical to rounding the fp32 sum, 1/3 of the
+ * instructions, HBM-bound instead of issue-bound. */
 int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub,
                       const int32_t* pair_obj, int32_t n_pairs, int32_t fs, int32_t channels, void* out,
                       hc_stream_t stream);

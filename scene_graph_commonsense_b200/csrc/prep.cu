@@ -204,6 +204,104 @@ pair_relu_pool_tiled_kernel(const uint4* __restrict__ u, const uint4* __restrict
   }
 }
 
+// ---- packed-bf16 variants (bias == NULL): V already carries the conv2 bias (it is added in fp32 inside the object-half
+// GEMM epilogue before the single rounding to bf16), so a pair is  relu(max_2x2(bf16(U + V))).  add.rn.bf16x2 rounds the
+// exact sum once, which is what rounding the fp32 sum of two bf16 values gives, and rounding commutes with max and relu:
+// the result equals the fp32 formulation bit for bit while issuing ~1/3 of the instructions (2 per two elements instead of
+// unpack + add + max + repack), which is what moves the kernel from issue-bound to HBM-bound.
+__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 bf8_add(uint4 a, uint4 b) {
+  return make_uint4(bf2_add(a.x, b.x), bf2_add(a.y, b.y), bf2_add(a.z, b.z), bf2_add(a.w, b.w));
+}
+__device__ __forceinline__ uint4 bf8_max(uint4 a, uint4 b) {
+  return make_uint4(bf2_max(a.x, b.x), bf2_max(a.y, b.y), bf2_max(a.z, b.z), bf2_max(a.w, b.w));
+}
+
+__global__ void pair_relu_pool_bf16_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const int* __restrict__ pair_sub,
+                                           const int* __restrict__ pair_obj, long long total_vec, int fs, int cvec,
+                                           uint4* __restrict__ out) {
+  const int hp = fs / 2;
+  const int per_pair = hp * hp * cvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
+    const int pr = (int)(i / per_pair);
+    const int rem = (int)(i - (long long)pr * per_pair);
+    const int cv = rem % cvec, pix = rem / cvec;
+    const int px = pix % hp, py = pix / hp;
+    const long long su = (long long)pair_sub[pr] * fs * fs, so = (long long)pair_obj[pr] * fs * fs;
+    uint4 acc = make_uint4(0u, 0u, 0u, 0u);                // +0.0 in every lane: relu folded into the running max
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const long long off = ((long long)(2 * py + (q >> 1)) * fs + (2 * px + (q & 1))) * cvec + cv;
+      acc = bf8_max(acc, bf8_add(__ldg(u + su * cvec + off), __ldg(v + so * cvec + off)));
+    }
+    out[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(128, 4)
+pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const int* __restrict__ box_off,
+                                 const int* __restrict__ lut, int n_max, int img0, int pair_base, int chunk_pairs, int fs, int cvec,
+                                 uint4* __restrict__ out) {
+  // grid = (slabs, subject tiles, images of the chunk); block = 128 consecutive (pooled pixel, channel vector) slots
+  const int img = img0 + blockIdx.z;
+  const int b0 = box_off[img], n = box_off[img + 1] - b0;
+  const int a0 = blockIdx.y * PP_TA;
+  if (a0 >= n) return;
+  const int hp = fs / 2;
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cv = slot % cvec;
+  const int pix = slot / cvec;
+  const int px = pix % hp, py = pix / hp;
+  if (py >= hp) return;
+  long long qoff[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) qoff[q] = ((long long)(2 * py + (q >> 1)) * fs + (2 * px + (q & 1))) * cvec + cv;
+  uint4 ua[PP_TA][4];
+#pragma unroll
+  for (int t = 0; t < PP_TA; ++t) {
+    const long long base = (long long)(b0 + min(a0 + t, n - 1)) * fs * fs * cvec;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ua[t][q] = __ldg(u + base + qoff[q]);
+  }
+  const int* lut_row[PP_TA];
+#pragma unroll
+  for (int t = 0; t < PP_TA; ++t) lut_row[t] = lut + (long long)(b0 + min(a0 + t, n - 1)) * n_max;
+  const long long out_slot = (long long)pix * cvec + cv;
+  const long long pair_stride = (long long)hp * hp * cvec;
+  for (int b = 0; b < n; ++b) {
+    int prow[PP_TA];
+    bool any = false;
+#pragma unroll
+    for (int t = 0; t < PP_TA; ++t) {
+      int p = (a0 + t < n) ? __ldg(lut_row[t] + b) : -1;
+      p = (p >= 0) ? p - pair_base : -1;
+      if (p >= chunk_pairs) p = -1;
+      prow[t] = p;
+      any |= p >= 0;
+    }
+    if (!any) continue;                                  // block-uniform (lut entries do not depend on the thread)
+    const long long vb = (long long)(b0 + b) * fs * fs * cvec;
+    uint4 vq[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) vq[q] = __ldg(v + vb + qoff[q]);
+#pragma unroll
+    for (int t = 0; t < PP_TA; ++t) {
+      if (prow[t] < 0) continue;                         // block-uniform
+      uint4 acc = make_uint4(0u, 0u, 0u, 0u);            // relu folded into the running max
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc = bf8_max(acc, bf8_add(ua[t][q], vq[q]));
+      __stcs(out + (long long)prow[t] * pair_stride + out_slot, acc);   // streamed: next read is conv3's TMA, after the chunk
+    }
+  }
+}
+
 }  // namespace hc
 
 using namespace hc;
@@ -246,12 +344,18 @@ extern "C" int hc_box_select(const void* t_img, const int32_t* boxes, const int3
 extern "C" int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub, const int32_t* pair_obj,
                                  int32_t n_pairs, int32_t fs, int32_t channels, void* out, hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  HC_REQUIRE(u && v && bias && pair_sub && pair_obj && out, HC_E_NULL, "hc_pair_relu_pool: NULL pointer");
+  HC_REQUIRE(u && v && pair_sub && pair_obj && out, HC_E_NULL, "hc_pair_relu_pool: NULL pointer");
   HC_REQUIRE(n_pairs > 0 && fs > 0 && fs % 2 == 0 && channels % 8 == 0, HC_E_SHAPE, "hc_pair_relu_pool: bad sizes");
   HC_REQUIRE(aligned16(u) && aligned16(v) && aligned16(out), HC_E_ALIGN, "hc_pair_relu_pool: 16-byte alignment");
   int rc = hc_device_check();
   if (rc != HC_OK) return rc;
   long long total = (long long)n_pairs * (fs / 2) * (fs / 2) * (channels / 8);
+  if (!bias) {
+    pair_relu_pool_bf16_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
+                                                                            pair_sub, pair_obj, total, fs, channels / 8,
+                                                                            reinterpret_cast<uint4*>(out));
+    return cuda_status("hc_pair_relu_pool");
+  }
   pair_relu_pool_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                      bias, pair_sub, pair_obj, total, fs, channels / 8,
                                                                      reinterpret_cast<uint4*>(out));
@@ -274,7 +378,7 @@ extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float
                                        int32_t n_max, int32_t img0, int32_t n_img, int32_t pair_base, int32_t chunk_pairs, int32_t fs,
                                        int32_t channels, void* out, hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  HC_REQUIRE(u && v && bias && box_offsets && lut && out, HC_E_NULL, "hc_pair_relu_pool_tiled: NULL pointer");
+  HC_REQUIRE(u && v && box_offsets && lut && out, HC_E_NULL, "hc_pair_relu_pool_tiled: NULL pointer");
   HC_REQUIRE(n_img > 0 && n_img <= 65535 && n_max > 0 && chunk_pairs > 0 && fs > 0 && fs % 2 == 0 && channels % 8 == 0, HC_E_SHAPE,
              "hc_pair_relu_pool_tiled: bad sizes");
   HC_REQUIRE(aligned16(u) && aligned16(v) && aligned16(out), HC_E_ALIGN, "hc_pair_relu_pool_tiled: 16-byte alignment");
@@ -284,6 +388,12 @@ extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float
   const int slots = hp * hp * cvec;
   HC_REQUIRE(slots % 128 == 0, HC_E_SHAPE, "hc_pair_relu_pool_tiled: (fs/2)^2 * channels/8 must be a multiple of 128");
   dim3 grid(slots / 128, (n_max + PP_TA - 1) / PP_TA, n_img);
+  if (!bias) {
+    pair_relu_pool_tiled_bf16_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
+                                                               box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec,
+                                                               reinterpret_cast<uint4*>(out));
+    return cuda_status("hc_pair_relu_pool_tiled");
+  }
   pair_relu_pool_tiled_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v), bias,
                                                         box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec, grid.y, grid.x,
                                                         reinterpret_cast<uint4*>(out));

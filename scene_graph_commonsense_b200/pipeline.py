@@ -180,8 +180,10 @@ class RelationPipeline:
         abox = ops.box_select(t, b.boxes, b.box_img, pk.fill, fs)
         u = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=self.device)
         v = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=self.device)
-        for out, w, base in ((u, pk.w2s, 0), (v, pk.w2o, 128)):
-            ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, ldc=512, mode=GEMM_CONV3, epilogue=EPI_BF16, act=ACT_NONE,
+        # the conv2 bias rides on the object half (added in fp32 before the one rounding to bf16), so the pair stage is
+        # relu(maxpool(U[s] + V[o])) on packed bf16
+        for out, w, base, bias in ((u, pk.w2s, 0, None), (v, pk.w2o, 128, pk.b2)):
+            ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, bias=bias, ldc=512, mode=GEMM_CONV3, epilogue=EPI_BF16, act=ACT_NONE,
                         n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=self.conv2_m_sub, tag="conv2_half")
         return u, v
 
@@ -209,7 +211,7 @@ class RelationPipeline:
         if "offsets_host" not in pairs:
             for s in range(0, n, self.chunk_pairs):
                 e = min(n, s + self.chunk_pairs)
-                p2 = ops.pair_relu_pool(u, v, pk.b2, pairs["sub"][s:e], pairs["obj"][s:e], self.fs)
+                p2 = ops.pair_relu_pool(u, v, None, pairs["sub"][s:e], pairs["obj"][s:e], self.fs)
                 pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e])
                 del p2
         else:
@@ -233,7 +235,7 @@ class RelationPipeline:
                         side.wait_event(ready)
                         if k >= 2:
                             side.wait_event(gemm_done[k - 2])          # buffer free again
-                    ops.pair_relu_pool_tiled(u, v, pk.b2, b.box_offsets, lut, img0, n_img, base, cnt, self.fs, out=buf)
+                    ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, self.fs, out=buf)
                     pooled = torch.cuda.Event()
                     pooled.record(side)
                 if side is not main:

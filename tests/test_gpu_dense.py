@@ -114,6 +114,18 @@ def test_pack_pixels_and_box_select_and_pair_pool():
     s = torch.relu(u[ps.long()].float() + (v[po.long()].float() + bias))
     ref = F.max_pool2d(s.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).to(torch.bfloat16)
     assert torch.equal(got, ref)
+    # bias == None: V already carries the conv2 bias; packed bf16x2 add/max == rounding the fp32 sum, bit for bit
+    got = ops.pair_relu_pool(u, v, None, ps, po)
+    s = torch.relu((u[ps.long()].float() + v[po.long()].float()).to(torch.bfloat16).float())
+    ref = F.max_pool2d(s.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(got, ref)
+    # wide dynamic range (exponent gaps > 16 bits, exact cancellation, signed zeros) keeps the identity
+    u2 = (u.float() * torch.exp2(torch.randint(-30, 30, u.shape, device="cuda").float())).to(torch.bfloat16)
+    v2 = torch.where(torch.rand(v.shape, device="cuda") < 0.1, -u2[[1, 0, 3, 2]], v)
+    got = ops.pair_relu_pool(u2, v2, None, ps, po)
+    s = torch.relu((u2[ps.long()].float() + v2[po.long()].float()).to(torch.bfloat16).float())
+    ref = F.max_pool2d(s.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(got.float(), ref.float())            # compares values: -0.0 == +0.0
 
 
 def test_shape_errors_are_reported_not_swallowed():
@@ -127,8 +139,9 @@ def test_shape_errors_are_reported_not_swallowed():
         ops.tc_gemm(a.cpu(), b, out, 128, 128, 64, lda=64, epilogue=ops.EPI_F32)
 
 
+@pytest.mark.parametrize("with_bias", [True, False])
 @pytest.mark.parametrize("mode", ["batch", "per_image"])
-def test_tiled_pair_pool_equals_gather_kernel_on_enumerated_pairs(mode):
+def test_tiled_pair_pool_equals_gather_kernel_on_enumerated_pairs(mode, with_bias):
     """The outer-sum tiled pooling kernel (LUT-addressed, image-aligned chunks, second stream) writes exactly what the
     generic per-pair gather kernel writes, including when the skip rule removes pairs."""
     from scene_graph_commonsense_b200 import pipeline, synthetic
@@ -140,7 +153,7 @@ def test_tiled_pair_pool_equals_gather_kernel_on_enumerated_pairs(mode):
     assert pairs["n"] > 0
     n_box = b.boxes.shape[0]
     u, v = _rand((n_box, 32, 32, 512), 31).to(torch.bfloat16), _rand((n_box, 32, 32, 512), 32).to(torch.bfloat16)
-    bias = _rand((512,), 33)
+    bias = _rand((512,), 33) if with_bias else None        # None: the packed-bf16 kernels (bias folded into V upstream)
     ref = ops.pair_relu_pool(u, v, bias, pairs["sub"], pairs["obj"])
     lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, 12)
     chunks = pipe._image_chunks(pairs["offsets_host"])
