@@ -4,16 +4,17 @@
 //
 // One persistent, warp-specialised kernel serves every dense stage of model.py:138-150,175:
 //   plain GEMM      (1x1 convolutions as pixel GEMMs, fc1, fc2; SGB post_cat)
-//   implicit conv   (3x3/pad 1 convolutions: the A tile of tap (ky,kx) is ONE 4-D TMA box of the NHWC
-//                    activation tensor shifted by (ky-1,kx-1); TMA zero-fills the padding halo, so no
-//                    im2col buffer ever exists)
+//   implicit conv   (3x3/pad 1 convolutions: per (64-channel block, kx) ONE 4-D TMA box of the NHWC activation tensor,
+//                    8*MS+2 pixel rows tall and shifted by kx-1, is fetched; the three ky taps read it through
+//                    descriptor start addresses 2048 B (= one 16-pixel row = two swizzle atoms) apart, so A is
+//                    fetched 3x instead of 9x per channel block; TMA zero-fills the padding halo, so no im2col
+//                    buffer ever exists)
 // CTA = 6 warps: warp 0 TMA producer, warp 1 tcgen05.mma issuer (+TMEM owner), warps 2-5 epilogue
 // (TMEM -> registers -> fused bias/activation/2x2-max-pool -> global).  Pipelines: smem full/empty ring
 // (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // CTA tile = (MS*128) x BN: MS 128-row sub-tiles share every B stage (halves L2->smem weight traffic for MS=2).
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "hc_common.cuh"
 
@@ -34,8 +35,17 @@ struct Cfg {
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
   static constexpr int ACC_COLS = MS * BN;
   static constexpr int ACC_STAGES = TMEM_COLS / ACC_COLS;
-  static constexpr int BAR_BYTES = (2 * STAGES + 2 * ACC_STAGES) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  // implicit-conv "patch" pipeline: one A patch (8*MS+2 pixel rows x 16 pixels x 64 channels) per (channel block, kx) serves
+  // the three ky taps through descriptor row offsets, so A is fetched 3 times per channel block instead of 9
+  static constexpr int PATCH_ROWS = 8 * MS + 2;
+  static constexpr int A_PATCH_BYTES = PATCH_ROWS * 16 * 128;        // multiple of 1024 (16 pixels x 128 B = 2 swizzle atoms per row)
+  static constexpr int PA_SLOTS = 3;
+  static constexpr int PB_SLOTS = 3;
+  static constexpr int PATCH_DATA_BYTES = PA_SLOTS * A_PATCH_BYTES + PB_SLOTS * B_BYTES;
+  static constexpr int DATA_BYTES = STAGES * STAGE_BYTES > PATCH_DATA_BYTES ? STAGES * STAGE_BYTES : PATCH_DATA_BYTES;
+  static constexpr int BAR_BYTES = (2 * STAGES + 2 * ACC_STAGES + 2 * PA_SLOTS + 2 * PB_SLOTS) * 8 + 16;
+  static constexpr int SMEM_BYTES = DATA_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static_assert(A_PATCH_BYTES % 1024 == 0 && SMEM_BYTES <= 227 * 1024, "patch pipeline does not fit");
   static_assert(STAGES >= 2, "pipeline too shallow");
   static_assert(ACC_STAGES >= 1, "accumulators do not fit TMEM");
 };
@@ -52,7 +62,7 @@ struct Params {
   const float* mul;              // optional elementwise multiplier [M, ld_mul] applied after bias/activation
   long long ld_mul;
   void* out;
-  int dbg_skip_a;                // TIMING EXPERIMENT ONLY (env HC_DEBUG_SKIP_A): conv A tiles are loaded for ky == 0 only -> wrong results
+  int patch;                     // 1 = implicit-conv patch pipeline (A fetched once per (channel block, kx)), 0 = plain GEMM
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -199,12 +209,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   using C = Cfg<BN, MS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = smem_base + C::DATA_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + C::ACC_STAGES + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 2 * C::ACC_STAGES);
+  constexpr int PBAR0 = 2 * C::STAGES + 2 * C::ACC_STAGES;
+  auto pa_full = [&](int s) { return bar_base + 8u * (PBAR0 + s); };
+  auto pa_empty = [&](int s) { return bar_base + 8u * (PBAR0 + C::PA_SLOTS + s); };
+  auto pb_full = [&](int s) { return bar_base + 8u * (PBAR0 + 2 * C::PA_SLOTS + s); };
+  auto pb_empty = [&](int s) { return bar_base + 8u * (PBAR0 + 2 * C::PA_SLOTS + C::PB_SLOTS + s); };
+  const uint32_t pa_base = smem_base, pb_base = smem_base + C::PA_SLOTS * C::A_PATCH_BYTES;
+  const uint32_t tmem_slot = bar_base + 8u * (PBAR0 + 2 * C::PA_SLOTS + 2 * C::PB_SLOTS);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -215,6 +231,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < C::ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < C::PA_SLOTS; ++s) { mbar_init(pa_full(s), 1); mbar_init(pa_empty(s), 1); }
+    for (int s = 0; s < C::PB_SLOTS; ++s) { mbar_init(pb_full(s), 1); mbar_init(pb_empty(s), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -228,40 +246,46 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int cblks = (p.mode == HC_GEMM_CONV3) ? p.c_in / BK : 1;
+    if (lane == 0 && p.patch) {
+      int a_slot = 0, b_slot = 0;
+      uint32_t a_phase = 0, b_phase = 0;
+      const int cblks = p.c_in / BK;
+      const int per_img = p.tiles_x * p.tiles_y;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(p, tile, m_blk, n_blk);
-        int img = 0, y0 = 0, x0 = 0;
-        if (p.mode == HC_GEMM_CONV3) {
-          int per_img = p.tiles_x * p.tiles_y;
-          img = m_blk / per_img;
-          int r = m_blk - img * per_img;
-          y0 = (r / p.tiles_x) * (8 * MS);
-          x0 = (r % p.tiles_x) * 16;
+        const int img = m_blk / per_img;
+        const int r = m_blk - img * per_img;
+        const int y0 = (r / p.tiles_x) * (8 * MS), x0 = (r % p.tiles_x) * 16;
+        for (int cb = 0; cb < cblks; ++cb) {
+          for (int kx = 0; kx < 3; ++kx) {
+            mbar_wait(pa_empty(a_slot), a_phase ^ 1u);
+            mbar_expect_tx(pa_full(a_slot), C::A_PATCH_BYTES);
+            tma_load_4d(pa_base + a_slot * C::A_PATCH_BYTES, &tmap_a, pa_full(a_slot), p.c_base + cb * BK, x0 + kx - 1, y0 - 1, img);
+            if (++a_slot == C::PA_SLOTS) { a_slot = 0; a_phase ^= 1u; }
+            for (int ky = 0; ky < 3; ++ky) {
+              mbar_wait(pb_empty(b_slot), b_phase ^ 1u);
+              mbar_expect_tx(pb_full(b_slot), C::B_BYTES);
+              tma_load_2d(pb_base + b_slot * C::B_BYTES, &tmap_b, pb_full(b_slot), ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN);
+              if (++b_slot == C::PB_SLOTS) { b_slot = 0; b_phase ^= 1u; }
+            }
+          }
         }
+      }
+    } else if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(p, tile, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + MS * A_SUB_BYTES;
-          const bool skip_a = p.dbg_skip_a && p.mode == HC_GEMM_CONV3 && (kb / cblks) >= 3;
-          mbar_expect_tx(full_bar(stage), skip_a ? C::B_BYTES : C::STAGE_BYTES);
-          if (skip_a) {
-          } else if (p.mode == HC_GEMM_CONV3) {
-            int tap = kb / cblks, cb = kb - tap * cblks;
-            int ky = tap / 3, kx = tap - ky * 3;
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
 #pragma unroll
-            for (int j = 0; j < MS; ++j)
-              tma_load_4d(a_dst + j * A_SUB_BYTES, &tmap_a, full_bar(stage), p.c_base + cb * BK, x0 + kx - 1,
-                          y0 + 8 * j + ky - 1, img);
-          } else {
-#pragma unroll
-            for (int j = 0; j < MS; ++j)
-              tma_load_2d(a_dst + j * A_SUB_BYTES, &tmap_a, full_bar(stage), kb * BK, (m_blk * MS + j) * BM);
-          }
+          for (int j = 0; j < MS; ++j)
+            tma_load_2d(a_dst + j * A_SUB_BYTES, &tmap_a, full_bar(stage), kb * BK, (m_blk * MS + j) * BM);
           tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -270,7 +294,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && p.patch) {
+      const uint32_t idesc = umma_idesc<BN>();
+      int a_slot = 0, b_slot = 0, acc = 0;
+      uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
+      const int n_ax = (p.c_in / BK) * 3;                 // (channel block, kx) steps per tile
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        for (int ax = 0; ax < n_ax; ++ax) {
+          mbar_wait(pa_full(a_slot), a_phase);            // the A patch of this (channel block, kx) has landed
+          tc_fence_after();
+          const uint32_t a_src = pa_base + a_slot * C::A_PATCH_BYTES;
+          for (int ky = 0; ky < 3; ++ky) {
+            mbar_wait(pb_full(b_slot), b_phase);
+            tc_fence_after();
+            const uint64_t bdesc = umma_desc_sw128(pb_base + b_slot * C::B_BYTES);
+#pragma unroll
+            for (int j = 0; j < MS; ++j) {
+              // tap ky of sub-tile j starts (8j + ky) pixel rows into the patch: 16 pixels x 128 B = 2048 B per row,
+              // a whole number of 1024-byte swizzle atoms, so only the descriptor start address moves
+              const uint64_t adesc = umma_desc_sw128(a_src + (uint32_t)(8 * j + ky) * 2048u);
+              const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_COLS + j * BN);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (ax | ky | k) ? 1u : 0u);
+            }
+            umma_commit(pb_empty(b_slot));
+            if (++b_slot == C::PB_SLOTS) { b_slot = 0; b_phase ^= 1u; }
+          }
+          umma_commit(pa_empty(a_slot));                  // patch free once the MMAs of its three taps retire
+          if (ax == n_ax - 1) umma_commit(tfull_bar(acc));
+          if (++a_slot == C::PA_SLOTS) { a_slot = 0; a_phase ^= 1u; }
+        }
+        if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      }
+    } else if (lane == 0) {
       const uint32_t idesc = umma_idesc<BN>();
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -493,11 +552,7 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   p.mode = d->mode; p.epi = d->epilogue; p.act = d->act;
   p.ldc = d->ldc; p.c_off = d->c_off; p.bias = d->bias; p.out = d->out;
   p.mul = d->mul; p.ld_mul = d->ld_mul;
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("HC_DEBUG_SKIP_A"); dbg = (e && e[0] == '1') ? 1 : 0; }
-    p.dbg_skip_a = dbg;
-  }
+  p.patch = d->mode == HC_GEMM_CONV3 ? 1 : 0;
   HC_REQUIRE(!d->mul || (d->epilogue != HC_EPI_POOL_BF16 && d->mode == HC_GEMM_PLAIN && d->ld_mul % 4 == 0 && aligned16(d->mul)), HC_E_SHAPE,
              "hc_tc_gemm: mul needs a plain GEMM, a non-pooled epilogue and a 16-byte aligned [M, ld_mul] f32 operand");
   p.tiles_n = p.N / BN;
@@ -523,7 +578,7 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     p.tiles_m = d->n_img * p.tiles_x * p.tiles_y;
     cuuint64_t dims[4] = {(cuuint64_t)d->c_total, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n_img};
     cuuint64_t str[3] = {(cuuint64_t)d->c_total * 2, (cuuint64_t)d->w * d->c_total * 2, (cuuint64_t)d->h * d->w * d->c_total * 2};
-    cuuint32_t box[4] = {(cuuint32_t)tc::BK, 16, 8, 1};
+    cuuint32_t box[4] = {(cuuint32_t)tc::BK, 16, (cuuint32_t)(8 * MS + 2), 1};   // one patch serves the three ky taps
     rc = tc::make_map(&ta, d->a, 4, dims, str, box);
     if (rc != HC_OK) return rc;
   } else {
