@@ -83,6 +83,9 @@ int hc_pairs_enumerate(const int32_t* boxes, const int32_t* box_offsets, int32_t
  *          HC_EPI_F32       : out f32  [M, ldc]: acc (+ bias if non-NULL)
  *          HC_EPI_POOL_BF16 : conv only: 2x2/stride-2 max-pool of relu(acc + bias) -> NHWC bf16
  *                             [n_img, H/2, W/2, ldc] (model.py:143-146 conv+ReLU+maxpool)
+ *          HC_EPI_SPLIT3_BF16 : plain only: x = act(acc + bias) * mul written as the bf16x3 A operand of a following
+ *                             GEMM, out bf16 [M, ldc >= 3N] = [hi | lo | hi], hi = bf16(x), lo = bf16(x - hi)
+ *                             (see hc_split_bf16x3); the f32 intermediate never reaches HBM
  * Requirements: K % 64 == 0, N % 128 == 0, all bases 16-byte aligned, lda/ldc/c_total multiples of 8.
  */
 #define HC_GEMM_PLAIN 0
@@ -90,6 +93,7 @@ int hc_pairs_enumerate(const int32_t* boxes, const int32_t* box_offsets, int32_t
 #define HC_EPI_BF16 0
 #define HC_EPI_F32 1
 #define HC_EPI_POOL_BF16 2
+#define HC_EPI_SPLIT3_BF16 3
 #define HC_ACT_NONE 0
 #define HC_ACT_RELU 1
 #define HC_ACT_TANH 2

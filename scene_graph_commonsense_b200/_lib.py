@@ -14,7 +14,7 @@ HC_OK = 0
 ERRORS = {-1: "HC_E_SHAPE", -2: "HC_E_ALIGN", -3: "HC_E_ARCH", -4: "HC_E_CUDA", -5: "HC_E_NULL"}
 
 GEMM_PLAIN, GEMM_CONV3 = 0, 1
-EPI_BF16, EPI_F32, EPI_POOL_BF16 = 0, 1, 2
+EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16 = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
 

@@ -445,6 +445,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   *reinterpret_cast<float4*>(dst + 4 * i) = v;
                 }
               }
+            } else if (p.epi == HC_EPI_SPLIT3_BF16) {
+              // bf16x3 A-operand layout for a following GEMM: out[row] = [hi | lo | hi] over 3*N columns, hi = bf16(x),
+              // lo = bf16(x - hi), x = act(acc + bias) * mul - the f32 intermediate never goes to HBM
+              if (row >= 0) {
+                __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + p.c_off + col0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float v[8];
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) v[t] = __uint_as_float(r[8 * i + t]);
+                  if (p.bias) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + 2 * i);
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + 2 * i + 1);
+                    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                  }
+                  if (p.act == HC_ACT_RELU) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.0f);
+                  }
+                  if (p.mul) {
+                    const float4 m0 = __ldg(reinterpret_cast<const float4*>(p.mul + row * p.ld_mul + col0) + 2 * i);
+                    const float4 m1 = __ldg(reinterpret_cast<const float4*>(p.mul + row * p.ld_mul + col0) + 2 * i + 1);
+                    v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w; v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
+                  }
+                  uint32_t hi[4], lo[4];
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * t]), h1 = __float2bfloat16_rn(v[2 * t + 1]);
+                    hi[t] = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
+                    lo[t] = pack_bf16(v[2 * t] - __bfloat162float(h0), v[2 * t + 1] - __bfloat162float(h1));
+                  }
+                  const uint4 H = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                  *reinterpret_cast<uint4*>(dst + 8 * i) = H;
+                  *reinterpret_cast<uint4*>(dst + p.N + 8 * i) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                  *reinterpret_cast<uint4*>(dst + 2 * p.N + 8 * i) = H;
+                }
+              }
             } else {
               if (row >= 0) {
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + p.c_off + col0;
@@ -537,7 +574,9 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   HC_REQUIRE(aligned16(d->a) && aligned16(d->b) && aligned16(d->out), HC_E_ALIGN, "hc_tc_gemm: a/b/out must be 16-byte aligned");
   HC_REQUIRE(d->ldc % 8 == 0 && d->c_off % 8 == 0, HC_E_ALIGN, "hc_tc_gemm: ldc and c_off must be multiples of 8");
   HC_REQUIRE(!d->bias || aligned16(d->bias), HC_E_ALIGN, "hc_tc_gemm: bias must be 16-byte aligned");
-  HC_REQUIRE(d->epilogue >= 0 && d->epilogue <= 2, HC_E_SHAPE, "hc_tc_gemm: unknown epilogue");
+  HC_REQUIRE(d->epilogue >= 0 && d->epilogue <= 3, HC_E_SHAPE, "hc_tc_gemm: unknown epilogue");
+  HC_REQUIRE(d->epilogue != HC_EPI_SPLIT3_BF16 || (d->mode == HC_GEMM_PLAIN && d->act != HC_ACT_TANH && d->ldc >= 3 * d->n), HC_E_SHAPE,
+             "hc_tc_gemm: the bf16x3 split epilogue needs a plain GEMM, no tanh and ldc >= 3*N");
   HC_REQUIRE(d->epilogue != HC_EPI_POOL_BF16 || (d->mode == HC_GEMM_CONV3 && d->bias), HC_E_SHAPE,
              "hc_tc_gemm: pooled epilogue needs conv mode and a bias");
   HC_REQUIRE(d->m < (1ll << 31) && d->n < (1ll << 31) && d->k < (1ll << 31), HC_E_SHAPE, "hc_tc_gemm: dims exceed int32");

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib, tables
-from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, GEMM_CONV3, GEMM_PLAIN, check, ptr,
+from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16, GEMM_CONV3, GEMM_PLAIN, check, ptr,
                    require_cuda, stream_ptr)
 
 LAUNCHES = {"n": 0}

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import EPI_BF16, EPI_F32
+from ._lib import EPI_BF16, EPI_F32, EPI_SPLIT3_BF16
 
 GEO_LABEL = [1, 2, 3, 4, 5, 6, 8, 10, 22, 23, 29, 31, 32, 33, 43]                  # roi_relation_predictors.py:376
 POS_LABEL = [9, 16, 17, 20, 27, 30, 36, 42, 48, 49, 50]                             # :377
@@ -85,6 +85,14 @@ class BayesHead(nn.Module):
             self._versions = versions
         return self._packed
 
+    def logits_from_split(self, a):
+        """bf16 [n, 3*input_dim] in the bf16x3 layout (hc_split_bf16x3 / HC_EPI_SPLIT3_BF16) -> f32 [n,128] logits."""
+        w, b = self.packed()
+        n, k3 = a.shape
+        out = torch.empty(n, 128, dtype=torch.float32, device=a.device)
+        ops.tc_gemm(a, w, out, n, 128, k3, bias=b, lda=k3, ldc=128, epilogue=EPI_F32, group_m=8, tag="bayes_head")
+        return out
+
     def logits(self, h):
         """[n, input_dim] f32 -> f32 [n,128] (columns: heads then the 4 super logits, rest zero padding).
         bf16x3 split operands on the bf16 tensor cores: ~fp32 accuracy for the 4096-long dot products."""
@@ -111,6 +119,20 @@ class BayesHeadProb(BayesHead):
         rel, sup = ops.sgb_hier_softmax(z, self.splits())
         g, p, _ = self.splits()
         return rel[:, :g], rel[:, g:g + p], rel[:, g + p:], sup
+
+
+_PACKED_LINEAR = {}
+
+
+def _packed_linear(lin):
+    """bf16x3 B-side packing of an nn.Linear, cached until its parameters change (data_ptr / version)."""
+    key = id(lin)
+    ver = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
+    hit = _PACKED_LINEAR.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, ops.pack_weight_bf16x3(lin.weight), lin.bias.detach().float().contiguous())
+        _PACKED_LINEAR[key] = hit
+    return hit[1], hit[2]
 
 
 def global_pair_index(rel_pair_idxs, num_objs, device):
@@ -140,12 +162,13 @@ def hierarchical_relation_tail(edge_rep, rel_pair_idxs, num_objs, obj_preds, uni
     pooling = post_cat.out_features
     if use_vision and union_features.shape[1] != pooling:
         raise NotImplementedError("union_single_not_match (up_dim) is not on the config-5 path")
-    w = ops.pack_weight_bf16x3(post_cat.weight)
-    prod_rep = torch.empty(n, pooling, dtype=torch.float32, device=dev)
-    ops.tc_gemm(prod, w, prod_rep, n, pooling, 6 * hidden, bias=post_cat.bias.detach().float().contiguous(), lda=6 * hidden, ldc=pooling,
-                epilogue=EPI_F32, mul=union_features.float().contiguous() if use_vision else None, group_m=16, m_sub=2 if n > 128 else 1,
-                tag="post_cat")
-    logits = rel_compress.logits(prod_rep)
+    w, bias = _packed_linear(post_cat)
+    # post_cat GEMM whose epilogue applies `* union_features` and writes the bf16x3 A operand of the BayesHead GEMM directly:
+    # the f32 [P, 4096] product never goes to HBM (was: write 16 KB/pair, read it back, split, write 24 KB/pair)
+    prod3 = torch.empty(n, 3 * pooling, dtype=torch.bfloat16, device=dev)
+    ops.tc_gemm(prod, w, prod3, n, pooling, 6 * hidden, bias=bias, lda=6 * hidden, ldc=3 * pooling, epilogue=EPI_SPLIT3_BF16,
+                mul=union_features.float().contiguous() if use_vision else None, group_m=16, m_sub=1, tag="post_cat")
+    logits = rel_compress.logits_from_split(prod3)
     pair_pred = obj_preds.to(dev, torch.int32)[pair_idx.long()].contiguous() if freq_bias_weight is not None else None
     rel, sup = ops.sgb_hier_softmax(logits, rel_compress.splits(), None if freq_bias_weight is None else freq_bias_weight.float().contiguous(),
                                     NUM_OBJ_SGB, pair_pred, _label_ids(dev))
