@@ -1,15 +1,18 @@
 #!/bin/bash
-# ncu evidence for one round: (1) per-launch device time of every kernel of a short bench run,
-# (2) one --set full capture of the dominant kernels (conv3_1, fc1, fc2 of the first pair chunk).
-TAG=${1:-r01}
-OUT=gpurun_out
-mkdir -p $OUT
-timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $OUT/launches_$TAG.csv \
+# ncu evidence: (1) launch list of a short cfg2 bench, (2) --set full of the dense kernels of the first pair chunk,
+# (3) --set full of the HBM/latency-bound kernels, (4) the same for the SGB twin and the proposal front-end microbench
+TAG=${1:-r01h}
+OUT=gpurun_out; mkdir -p $OUT
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_$TAG.csv \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_bench_$TAG.log 2>&1
 echo "launch list exit $?"; wc -l $OUT/launches_$TAG.csv
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 3 -c 3 -o $OUT/prof_$TAG -f \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
-echo "full capture exit $?"; ls -la $OUT/prof_$TAG.ncu-rep
-timeout 900 ncu --set full --clock-control none -k regex:"pair_relu_pool|topk_match|hier_head|box_select|candidates" -c 6 -o $OUT/prof_small_$TAG -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_gemm_kernel -s 1 -c 6 -o $OUT/prof_dense_$TAG -f \
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_dense_$TAG.log 2>&1
+echo "dense capture exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"pair_relu_pool_tiled|topk_match|hier_head|box_select|candidates_kernel|pairs_fill|box_label" -c 8 -o $OUT/prof_small_$TAG -f \
     python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_small_$TAG.log 2>&1
 echo "small capture exit $?"
+STEPS=1 timeout 600 ncu --set full --clock-control none -k regex:"sgb_|tc_gemm" -s 14 -c 7 -o $OUT/prof_sgb_$TAG -f \
+    python tools/bench_sgb.py > $OUT/ncu_sgb_$TAG.log 2>&1
+echo "sgb capture exit $?"
+ls -la $OUT/*.ncu-rep
