@@ -1,0 +1,384 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/hiercom_b200.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every computation below is a hand-written sm_100a
+kernel reached through ctypes.  `LAUNCHES` counts kernel launches issued through this module (bench.py reports it).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, tables
+from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16, GEMM_CONV3, GEMM_PLAIN, check, ptr,
+                   require_cuda, stream_ptr)
+
+LAUNCHES = {"n": 0}
+PROFILE = {"on": False, "events": []}     # bench.py: CUDA-event timing of tagged launches on the launching stream
+
+
+def _count(n=1):
+    LAUNCHES["n"] += n
+
+
+class _timed:
+    """Brackets one launch with CUDA events on the current stream when PROFILE['on'] (no host sync)."""
+
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if PROFILE["on"]:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if PROFILE["on"]:
+            self.e1.record()
+            PROFILE["events"].append((self.tag, self.e0, self.e1))
+        return False
+
+
+def cs_bitmap_build(aligned_keys, violated_keys):
+    """Host: packed key arrays -> uint32[BITMAP_WORDS] pass bitmap (numpy)."""
+    al = np.ascontiguousarray(np.asarray(aligned_keys, dtype=np.int64))
+    vi = np.ascontiguousarray(np.asarray(violated_keys, dtype=np.int64))
+    out = np.zeros(tables.BITMAP_WORDS, dtype=np.uint32)
+    check(_lib.load().hc_cs_bitmap_build(ptr(al) if al.size else None, al.size, ptr(vi) if vi.size else None, vi.size,
+                                         out.ctypes.data), "hc_cs_bitmap_build")
+    return out
+
+
+def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tri=None, group_id=None, n_groups=0,
+                    max_tri=0, feature_size=32):
+    """R1/R2/R4.  `p_max` = sum_i N_i(N_i-1) (host int, known from the CSR the caller built).  Returns a dict of
+    device arrays trimmed to the number of surviving directed pairs (one 4-byte D2H read of the total)."""
+    require_cuda(boxes, box_offsets, tri_offsets, rel_tri, dir_tri, group_id)
+    dev = boxes.device
+    n_images = box_offsets.numel() - 1
+    ws_ov = torch.empty(max(p_max // 2, 1), dtype=torch.uint8, device=dev)
+    ws_any = torch.empty(max(n_groups * max_tri, 1), dtype=torch.uint8, device=dev) if group_id is not None else None
+    ws_counts = torch.empty(n_images, dtype=torch.int32, device=dev)
+    pair_offsets = torch.empty(n_images + 1, dtype=torch.int32, device=dev)
+    i32 = lambda: torch.empty(max(p_max, 1), dtype=torch.int32, device=dev)
+    pair_sub, pair_obj, pair_img, pair_gt, pair_rel = i32(), i32(), i32(), i32(), i32()
+    pair_ov = torch.empty(max(p_max, 1), dtype=torch.uint8, device=dev)
+    total = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(_lib.load().hc_pairs_enumerate(ptr(boxes), ptr(box_offsets), n_images, ptr(group_id), n_groups, max_tri,
+                                         ptr(rel_tri), ptr(dir_tri), ptr(tri_offsets), feature_size, ptr(ws_ov),
+                                         ptr(ws_any), ptr(ws_counts), ptr(pair_offsets), ptr(pair_sub), ptr(pair_obj),
+                                         ptr(pair_img), ptr(pair_ov), ptr(pair_gt), ptr(pair_rel), ptr(total),
+                                         stream_ptr()), "hc_pairs_enumerate")
+    _count(4)
+    offsets_host = pair_offsets.cpu()                 # [B+1] ints: the one D2H sync of the step (sizes the GEMM launches)
+    n = int(offsets_host[-1])
+    return dict(n=n, offsets=pair_offsets, offsets_host=offsets_host.numpy(), sub=pair_sub[:n], obj=pair_obj[:n], img=pair_img[:n], ov=pair_ov[:n],
+                gt=pair_gt[:n], rel=pair_rel[:n])
+
+
+def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16,
+            act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None):
+    """out = epilogue(A @ B^T) on tcgen05 (see include/hiercom_b200.h hc_tc_gemm)."""
+    require_cuda(a, b, out, bias, mul)
+    d = _lib.GemmDesc()
+    d.a, d.b, d.bias, d.out = ptr(a), ptr(b), ptr(bias), ptr(out)
+    d.m, d.n, d.k = m, n, k
+    d.lda, d.ldc, d.c_off = lda, (ldc if ldc is not None else n), c_off
+    d.mode, d.epilogue, d.act = mode, epilogue, act
+    d.n_img, d.h, d.w, d.c_total, d.c_base, d.c_in = n_img, h, w, c_total, c_base, c_in
+    d.group_m, d.m_sub = group_m, m_sub
+    d.mul, d.ld_mul = ptr(mul), (mul.stride(0) if mul is not None else 0)
+    with _timed(tag):
+        check(_lib.load().hc_tc_gemm(C.byref(d), stream_ptr()), "hc_tc_gemm")
+    _count()
+    return out
+
+
+def pack_pixels(src0, src1, k_pad, out=None):
+    """[B,C0,H,W] (+[B,C1,H,W]) f32 -> [B*H*W, k_pad] bf16."""
+    require_cuda(src0, src1)
+    src0 = src0.contiguous()
+    b, c0 = src0.shape[0], src0.shape[1]
+    hw = src0.shape[2] * src0.shape[3]
+    c1 = 0
+    if src1 is not None:
+        src1 = src1.contiguous()
+        c1 = src1.shape[1]
+    if out is None:
+        out = torch.empty(b * hw, k_pad, dtype=torch.bfloat16, device=src0.device)
+    check(_lib.load().hc_pack_pixels(ptr(src0), c0, ptr(src1), c1, b, hw, k_pad, ptr(out), stream_ptr()), "hc_pack_pixels")
+    _count()
+    return out
+
+
+def box_select(t_img, boxes, box_img, fill, fs=32, out=None):
+    require_cuda(t_img, boxes, box_img, fill)
+    n_box, ch = boxes.shape[0], t_img.shape[-1]
+    if out is None:
+        out = torch.empty(n_box, fs, fs, ch, dtype=torch.bfloat16, device=t_img.device)
+    check(_lib.load().hc_box_select(ptr(t_img), ptr(boxes), ptr(box_img), n_box, fs, ch, ptr(fill), ptr(out), stream_ptr()),
+          "hc_box_select")
+    _count()
+    return out
+
+
+def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None):
+    require_cuda(u, v, bias, pair_sub, pair_obj)
+    n, ch = pair_sub.numel(), u.shape[-1]
+    if out is None:
+        out = torch.empty(n, fs // 2, fs // 2, ch, dtype=torch.bfloat16, device=u.device)
+    with _timed("pair_pool"):
+        check(_lib.load().hc_pair_relu_pool(ptr(u), ptr(v), ptr(bias), ptr(pair_sub), ptr(pair_obj), n, fs, ch, ptr(out),
+                                            stream_ptr()), "hc_pair_relu_pool")
+    _count()
+    return out
+
+
+def pair_lut_build(pair_sub, pair_obj, pair_img, box_offsets, n_box, n_max):
+    require_cuda(pair_sub, pair_obj, pair_img, box_offsets)
+    lut = torch.empty(n_box, n_max, dtype=torch.int32, device=box_offsets.device)
+    check(_lib.load().hc_pair_lut_build(ptr(pair_sub), ptr(pair_obj), ptr(pair_img), ptr(box_offsets), pair_sub.numel(), n_box, n_max,
+                                        ptr(lut), stream_ptr()), "hc_pair_lut_build")
+    _count(1)
+    return lut
+
+
+def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None):
+    require_cuda(u, v, bias, box_offsets, lut)
+    ch = u.shape[-1]
+    if out is None:
+        out = torch.empty(chunk_pairs, fs // 2, fs // 2, ch, dtype=torch.bfloat16, device=u.device)
+    with _timed("pair_pool"):
+        check(_lib.load().hc_pair_relu_pool_tiled(ptr(u), ptr(v), ptr(bias), ptr(box_offsets), ptr(lut), lut.shape[1], img0, n_img,
+                                                  pair_base, chunk_pairs, fs, ch, ptr(out), stream_ptr()), "hc_pair_relu_pool_tiled")
+    _count()
+    return out
+
+
+def hier_head(fc2_raw, fc2_bias, emb, row_sub, row_obj, box_cat, box_super, w_heads, b_heads, splits, flat=False,
+              temps=(1.0, 1.0, 1.0), num_obj=150, num_super=17, want_pred=False):
+    require_cuda(fc2_raw, fc2_bias, emb, row_sub, row_obj, box_cat, box_super, w_heads, b_heads)
+    n, hidden = fc2_raw.shape
+    dev = fc2_raw.device
+    r = sum(splits)
+    relation = torch.empty(n, r, dtype=torch.float32, device=dev)
+    sup = None if flat else torch.empty(n, 3, dtype=torch.float32, device=dev)
+    conn = torch.empty(n, dtype=torch.float32, device=dev)
+    logsig = torch.empty(n, dtype=torch.float32, device=dev)
+    pred = torch.empty(n, hidden, dtype=torch.float32, device=dev) if want_pred else None
+    box_emb = None
+    if fc2_bias is not None:
+        # label columns of fc2 summed once per box ([as subject | as object]); a pair then adds two rows instead of <= 10
+        n_box = box_cat.numel()
+        box_emb = torch.empty(n_box, 2 * hidden, dtype=torch.float32, device=dev)
+        check(_lib.load().hc_box_label_embed(ptr(emb), num_obj, num_super, ptr(box_cat), ptr(box_super), n_box, hidden, ptr(box_emb),
+                                             stream_ptr()), "hc_box_label_embed")
+        _count()
+    check(_lib.load().hc_hier_head(ptr(fc2_raw), fc2_raw.stride(0), n, hidden, ptr(fc2_bias), ptr(emb), num_obj, num_super,
+                                   ptr(row_sub), ptr(row_obj), ptr(box_cat), ptr(box_super), ptr(w_heads), ptr(b_heads),
+                                   splits[0], splits[1], splits[2], int(flat), temps[0], temps[1], temps[2], ptr(relation),
+                                   ptr(sup), ptr(conn), ptr(logsig), ptr(pred), ptr(box_emb), stream_ptr()), "hc_hier_head")
+    _count()
+    return relation, sup, conn, logsig, pred
+
+
+def candidates(relation, splits, hier, row_ov, logsig, row_sub, row_obj, box_cat, pass_bitmap=None, super_rel=None,
+               conf_sub=None, conf_obj=None, layout=0, want_top3=False):
+    require_cuda(relation, row_ov, logsig, row_sub, row_obj, box_cat, pass_bitmap, super_rel, conf_sub, conf_obj)
+    n = relation.shape[0]
+    dev = relation.device
+    k = 3 if hier else 1
+    cand_conf = torch.empty(n * k, dtype=torch.float32, device=dev)
+    cand_label = torch.empty(n * k, dtype=torch.int32, device=dev)
+    t3_conf = torch.empty(n, dtype=torch.float32, device=dev) if want_top3 else None
+    t3_super = torch.empty(n, dtype=torch.uint8, device=dev) if want_top3 else None
+    check(_lib.load().hc_candidates(ptr(relation), relation.stride(0), n, splits[0], splits[1], splits[2], int(hier),
+                                    ptr(row_ov), ptr(logsig), ptr(conf_sub), ptr(conf_obj), ptr(row_sub), ptr(row_obj),
+                                    ptr(box_cat), ptr(pass_bitmap), ptr(super_rel), ptr(cand_conf), ptr(cand_label),
+                                    ptr(t3_conf), ptr(t3_super), layout, stream_ptr()), "hc_candidates")
+    _count()
+    return cand_conf, cand_label, t3_conf, t3_super
+
+
+def topk_match(cand_offsets, cand_conf, cand_label, k_per_row, row_sub, row_obj, pred_cat, pred_box, gt_offsets, gt_label,
+               gt_sub, gt_obj, gt_cat, gt_box, counters, *, cand_row=None, synonyms=None, zs_bitmap=None, mode=0,
+               t3_labels=None, t3_super=None, feature_size=32, iou_thresh=0.5, top_k=tables.TOP_K, want_topk=False):
+    require_cuda(cand_offsets, cand_conf, cand_label, row_sub, row_obj, pred_cat, pred_box, gt_offsets, gt_label, gt_sub,
+                 gt_obj, gt_cat, gt_box, counters, cand_row, synonyms, zs_bitmap, t3_labels, t3_super)
+    n_images = cand_offsets.numel() - 1
+    top_max = int(top_k[-1])
+    topk_out = torch.empty(n_images, top_max, dtype=torch.int32, device=cand_conf.device) if want_topk else None
+    check(_lib.load().hc_topk_match(ptr(cand_offsets), n_images, ptr(cand_conf), ptr(cand_label), ptr(cand_row), k_per_row,
+                                    ptr(row_sub), ptr(row_obj), ptr(pred_cat), ptr(pred_box), ptr(gt_offsets), ptr(gt_label),
+                                    ptr(gt_sub), ptr(gt_obj), ptr(gt_cat), ptr(gt_box), ptr(synonyms), tables.NUM_OBJ,
+                                    tables.NUM_PRED, ptr(zs_bitmap), feature_size, float(iou_thresh), top_max, int(top_k[0]),
+                                    int(top_k[1]), int(top_k[2]), mode, ptr(t3_labels), ptr(t3_super), ptr(counters),
+                                    ptr(topk_out), stream_ptr()), "hc_topk_match")
+    _count()
+    return topk_out
+
+
+def topk_select(cand_offsets, cand_conf, top_max=128):
+    require_cuda(cand_offsets, cand_conf)
+    n_images = cand_offsets.numel() - 1
+    out = torch.empty(n_images, top_max, dtype=torch.int32, device=cand_conf.device)
+    check(_lib.load().hc_topk_select(ptr(cand_offsets), n_images, ptr(cand_conf), top_max, ptr(out), stream_ptr()), "hc_topk_select")
+    _count()
+    return out
+
+
+def connectivity_stats(connectivity, gt_directed, gt_undirected, stats):
+    require_cuda(connectivity, gt_directed, gt_undirected, stats)
+    check(_lib.load().hc_connectivity_stats(ptr(connectivity), ptr(gt_directed), ptr(gt_undirected), connectivity.numel(),
+                                            ptr(stats), stream_ptr()), "hc_connectivity_stats")
+    _count()
+
+
+# ------------------------------------------------------------------------------------------------------ SGB twin (R14/N1)
+def sgb_pair_gather(edge_rep, pair_idx, hidden, split=False):
+    require_cuda(edge_rep, pair_idx)
+    n = pair_idx.shape[0]
+    out = torch.empty(n, (3 if split else 1) * 2 * hidden, dtype=torch.bfloat16, device=edge_rep.device)
+    check(_lib.load().hc_sgb_pair_gather(ptr(edge_rep), ptr(pair_idx), n, hidden, int(split), ptr(out), stream_ptr()), "hc_sgb_pair_gather")
+    _count()
+    return out
+
+
+def split_bf16x3(x):
+    """f32 [n,k] -> bf16 [n,3k] = [hi | lo | hi] (A side of the bf16x3 scheme)."""
+    require_cuda(x)
+    n, k = x.shape
+    out = torch.empty(n, 3 * k, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().hc_split_bf16x3(ptr(x), x.stride(0), n, k, ptr(out), stream_ptr()), "hc_split_bf16x3")
+    _count()
+    return out
+
+
+def pack_weight_bf16x3(w):
+    """f32 [n,k] weight -> bf16 [n,3k] = [W_hi | W_hi | W_lo] (B side of the bf16x3 scheme); one-time packing (torch)."""
+    w = w.detach().float()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    return torch.cat((hi, hi, lo), dim=1).contiguous()
+
+
+def sgb_hier_softmax(logits, splits, bias_table=None, num_obj=151, pair_pred=None, label_ids=None):
+    require_cuda(logits, bias_table, pair_pred, label_ids)
+    n, r = logits.shape[0], sum(splits)
+    rel = torch.empty(n, r, dtype=torch.float32, device=logits.device)
+    sup = torch.empty(n, 4, dtype=torch.float32, device=logits.device)
+    check(_lib.load().hc_sgb_hier_softmax(ptr(logits), logits.stride(0), n, splits[0], splits[1], splits[2], ptr(bias_table), num_obj,
+                                          ptr(pair_pred), ptr(label_ids), ptr(rel), ptr(sup), stream_ptr()), "hc_sgb_hier_softmax")
+    _count()
+    return rel, sup
+
+
+def sgb_candidates(rel, splits, pair_offsets, pair_img, pair_idx, obj_scores, label_ids):
+    require_cuda(rel, pair_offsets, pair_img, pair_idx, obj_scores, label_ids)
+    n = rel.shape[0]
+    dev = rel.device
+    score = torch.empty(3 * n, dtype=torch.float32, device=dev)
+    label = torch.empty(3 * n, dtype=torch.int32, device=dev)
+    row = torch.empty(3 * n, dtype=torch.int32, device=dev)
+    check(_lib.load().hc_sgb_candidates(ptr(rel), splits[0], splits[1], splits[2], ptr(pair_offsets), ptr(pair_img), ptr(pair_idx),
+                                        ptr(obj_scores), ptr(label_ids), n, ptr(score), ptr(label), ptr(row), stream_ptr()),
+          "hc_sgb_candidates")
+    _count()
+    return score, label, row
+
+
+def sgb_rank_match(ranked, reject, pair_offsets, cand_score, cand_label, cand_row, pair_idx, pred_cls, pred_box, gt_offsets, gt_rel,
+                   gt_cls, gt_box, iou_thresh=0.5, top_k=(20, 50, 100)):
+    require_cuda(ranked, reject, pair_offsets, cand_score, cand_label, cand_row, pair_idx, pred_cls, pred_box, gt_offsets, gt_rel, gt_cls,
+                 gt_box)
+    n_img = pair_offsets.numel() - 1
+    dev = cand_score.device
+    top_max = int(top_k[-1])
+    i32 = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+    final_rank, hits, ngt, hits_pc, cnt_pc = i32(n_img, top_max), i32(n_img, 3), i32(n_img), i32(n_img, 3, 51), i32(n_img, 51)
+    check(_lib.load().hc_sgb_rank_match(ptr(ranked), ptr(reject), ptr(pair_offsets), n_img, ptr(cand_score), ptr(cand_label),
+                                        ptr(cand_row), ptr(pair_idx), ptr(pred_cls), ptr(pred_box), ptr(gt_offsets), ptr(gt_rel),
+                                        ptr(gt_cls), ptr(gt_box), float(iou_thresh), top_max, int(top_k[0]), int(top_k[1]),
+                                        int(top_k[2]), ptr(final_rank), ptr(hits), ptr(ngt), ptr(hits_pc), ptr(cnt_pc), stream_ptr()),
+          "hc_sgb_rank_match")
+    _count()
+    return final_rank, hits, ngt, hits_pc, cnt_pc
+
+
+# ------------------------------------------------------------------------------------------ proposal front-end (N2)
+def detr_proposals(pred_logits, pred_boxes, label_map, sub2super=None, num_classes=150, topk_cat=2, feature_size=32,
+                   nms_thresh=0.5):
+    """evaluate.py:311-370.  Returns CSR device arrays of the surviving proposals (one [B+1]-int D2H read sizes them)."""
+    require_cuda(pred_logits, pred_boxes, label_map, sub2super)
+    pred_logits, pred_boxes = pred_logits.contiguous().float(), pred_boxes.contiguous().float()
+    b, q = pred_logits.shape[0], pred_logits.shape[1]
+    if pred_logits.shape[2] != num_classes + 1 or tuple(pred_boxes.shape) != (b, q, 4):
+        raise RuntimeError("hiercom_b200 detr_proposals: pred_logits must be [B,Q,num_classes+1] and pred_boxes [B,Q,4]")
+    dev = pred_logits.device
+    e = q * topk_cat
+    i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+    f32 = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    ws_label, ws_conf, ws_box, ws_valid = i32(b * e), f32(b * e), f32(b * e, 4), torch.empty(b * e, dtype=torch.uint8, device=dev)
+    st_label, st_conf, st_box, st_count, offsets = i32(b * e), f32(b * e), f32(b * e, 4), i32(b), i32(b + 1)
+    check(_lib.load().hc_detr_proposals(ptr(pred_logits), ptr(pred_boxes), b, q, num_classes, topk_cat, ptr(label_map), feature_size,
+                                        float(nms_thresh), ptr(ws_label), ptr(ws_conf), ptr(ws_box), ptr(ws_valid), ptr(st_label),
+                                        ptr(st_conf), ptr(st_box), ptr(st_count), ptr(offsets), stream_ptr()), "hc_detr_proposals")
+    _count(3)
+    offsets_host = offsets.cpu().numpy()
+    n = int(offsets_host[-1])
+    cats, conf, box_f, box_i = i32(max(n, 1)), f32(max(n, 1)), f32(max(n, 1), 4), i32(max(n, 1), 4)
+    supers = torch.empty(max(n, 1), 4, dtype=torch.int8, device=dev) if sub2super is not None else None
+    box_img = i32(max(n, 1))
+    check(_lib.load().hc_proposals_pack(ptr(st_label), ptr(st_conf), ptr(st_box), ptr(offsets), b, e, ptr(sub2super), num_classes,
+                                        ptr(cats), ptr(conf), ptr(box_f), ptr(box_i), ptr(supers), ptr(box_img), stream_ptr()),
+          "hc_proposals_pack")
+    _count()
+    return dict(n=n, offsets=offsets, offsets_host=offsets_host, cats=cats[:n], conf=conf[:n], box_f=box_f[:n], box_i=box_i[:n],
+                supers=None if supers is None else supers[:n], box_img=box_img[:n])
+
+
+def match_object_categories(prop_cats, prop_conf, prop_box, prop_offsets, gt_box, gt_offsets, sub2super=None, num_classes=150,
+                            feature_size=32):
+    """utils.py:376-422 on CSR device arrays.  Returns None when the reference would return (None, None, None)."""
+    require_cuda(prop_cats, prop_conf, prop_box, prop_offsets, gt_box, gt_offsets, sub2super)
+    dev = prop_box.device
+    b = prop_offsets.numel() - 1
+    n_gt = gt_box.shape[0]
+    i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+    ws_idx, ws_iou = i32(max(n_gt, 1), 2), torch.empty(max(n_gt, 1), 2, dtype=torch.float32, device=dev)
+    ws_count, out_offsets, status = i32(b), i32(b + 1), i32(1)
+    check(_lib.load().hc_match_object_categories(ptr(prop_box), ptr(prop_offsets), ptr(gt_box), ptr(gt_offsets), b, feature_size,
+                                                 ptr(ws_idx), ptr(ws_iou), ptr(ws_count), ptr(out_offsets), ptr(status), stream_ptr()),
+          "hc_match_object_categories")
+    _count(2)
+    host = torch.cat((out_offsets, status)).cpu().numpy()        # one D2H read: sizes + the reference's "None" condition
+    if int(host[-1]) != 0:
+        return None
+    offsets_host = host[:-1]
+    n = int(offsets_host[-1])
+    cats, conf, box, src = i32(max(n, 1)), torch.empty(max(n, 1), dtype=torch.float32, device=dev), i32(max(n, 1), 4), i32(max(n, 1))
+    supers = torch.empty(max(n, 1), 4, dtype=torch.int8, device=dev) if sub2super is not None else None
+    img = i32(max(n, 1))
+    check(_lib.load().hc_match_object_categories_fill(ptr(prop_cats), ptr(prop_conf), ptr(prop_offsets), ptr(gt_box), ptr(gt_offsets), b,
+                                                      ptr(ws_idx), ptr(ws_iou), ptr(out_offsets), ptr(sub2super), num_classes,
+                                                      ptr(cats), ptr(conf), ptr(box), ptr(src), ptr(supers), ptr(img), stream_ptr()),
+          "hc_match_object_categories_fill")
+    _count()
+    return dict(n=n, offsets=out_offsets, offsets_host=offsets_host, cats=cats[:n], conf=conf[:n], box_i=box[:n], src=src[:n],
+                supers=None if supers is None else supers[:n], box_img=img[:n])
+
+
+def targets_flat(dir_tri, rel_tri, tri_offsets, box_offsets):
+    """utils.py:294-352 on the packed triangle arrays -> (gt_offsets [B+1], label, sub, obj) device arrays; label/sub/obj are
+    over-allocated to sum T_i entries and valid up to gt_offsets[-1] (no host sync here)."""
+    require_cuda(dir_tri, rel_tri, tri_offsets, box_offsets)
+    dev = dir_tri.device
+    b = box_offsets.numel() - 1
+    cap = max(dir_tri.numel(), 1)
+    i32 = lambda *s: torch.empty(*s, dtype=torch.int32, device=dev)
+    ws_count, gt_offsets, label, sub, obj = i32(b), i32(b + 1), i32(cap), i32(cap), i32(cap)
+    check(_lib.load().hc_targets_flat(ptr(dir_tri), ptr(rel_tri), ptr(tri_offsets), ptr(box_offsets), b, ptr(ws_count), ptr(gt_offsets),
+                                      ptr(label), ptr(sub), ptr(obj), stream_ptr()), "hc_targets_flat")
+    _count(3)
+    return gt_offsets, label, sub, obj

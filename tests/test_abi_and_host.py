@@ -58,6 +58,24 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
         pipeline.RelationPipeline(None, "cpu")
 
 
+def test_torch_custom_op_layer_registers_every_kernel_entry_point_for_cuda_only():
+    """north_star: the Python modules reach the kernels through `torch.ops.hiercom.*`; no operator has a CPU kernel."""
+    from scene_graph_commonsense_b200 import ops
+    compute = {n[3:] for n in _lib.SIGNATURES} - {"last_error", "abi_version", "device_check", "cs_bitmap_build"}
+    folded = {"box_label_embed": "hier_head", "proposals_pack": "detr_proposals", "match_object_categories_fill": "match_object_categories"}
+    for name in compute:
+        op = folded.get(name, name)
+        assert op in ops.SCHEMAS, name
+        qual = "hiercom::" + op
+        assert torch._C._dispatch_has_kernel_for_dispatch_key(qual, "CUDA"), qual
+        assert not torch._C._dispatch_has_kernel_for_dispatch_key(qual, "CPU"), qual
+        assert not torch._C._dispatch_has_kernel_for_dispatch_key(qual, "CompositeImplicitAutograd"), qual
+    with pytest.raises(NotImplementedError):
+        torch.ops.hiercom.topk_select(torch.zeros(2, dtype=torch.int32), torch.zeros(4), 128)
+    # caller-owned output buffers are declared mutable in the schema
+    assert "Tensor(a!) out" in ops.SCHEMAS["tc_gemm"] and "Tensor(a!) counters" in ops.SCHEMAS["topk_match"]
+
+
 def test_product_never_imports_the_oracle_or_reference():
     pkg = os.path.join(ROOT, "scene_graph_commonsense_b200")
     for dirpath, _, files in os.walk(pkg):
