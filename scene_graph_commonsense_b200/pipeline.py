@@ -296,6 +296,42 @@ class RelationPipeline:
         self.evaluate(b, pairs, relation, sup, logsig, connectivity=conn)
         return pairs["n"]
 
+    def run(self, host_batches, before_step=None, after_step=None):
+        """Streams evaluation windows from pinned host staging: yields `(n_pairs, counters_host)` per window.  The H2D copy of
+        window k+1 is issued on a copy stream before window k's kernels are enqueued, so it rides under window k's compute;
+        every window's inputs still cross PCIe exactly once and its counters are read back (D2H) before the next window's
+        result is produced.  `before_step(self)` / `after_step(self)` hook in a counter reset / the cross-rank all-reduce."""
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy", None) is None:
+            self._copy = torch.cuda.Stream(device=self.device)
+        copy = self._copy
+        it = iter(host_batches)
+
+        def fetch():
+            hb = next(it, None)
+            if hb is None:
+                return None
+            with torch.cuda.stream(copy):
+                b = hb.to_device(self.device)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            return b, ready
+
+        nxt = fetch()
+        while nxt is not None:
+            b, ready = nxt
+            main.wait_event(ready)
+            for t in list(vars(b).values()) + list((b.gt or {}).values()):
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(main)           # allocated on the copy stream, consumed on the compute stream
+            nxt = fetch()
+            if before_step is not None:
+                before_step(self)
+            n = self.step(b)
+            if after_step is not None:
+                after_step(self)
+            yield n, self.counters.cpu()
+
     # ------------------------------------------------------------------------------------------------ results
     def reset(self):
         self.counters.zero_()

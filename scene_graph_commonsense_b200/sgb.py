@@ -27,8 +27,14 @@ NUM_OBJ_SGB = 151
 NUM_REL_SGB = 51
 
 
+_LABEL_IDS_DEV = {}
+
+
 def _label_ids(device):
-    return torch.tensor(LABEL_IDS, dtype=torch.int32, device=device)
+    key = str(device)
+    if key not in _LABEL_IDS_DEV:
+        _LABEL_IDS_DEV[key] = torch.tensor(LABEL_IDS, dtype=torch.int32, device=device)
+    return _LABEL_IDS_DEV[key]
 
 
 class SimpleBoxList:
@@ -135,15 +141,47 @@ def _packed_linear(lin):
     return hit[1], hit[2]
 
 
+class PerImage(tuple):
+    """Per-image views (what the SGB interfaces exchange) that remember the whole-batch tensor they are slices of, so the
+    next stage of this package takes `.whole` instead of re-concatenating 64 views."""
+    whole = None
+
+
+def _per_image(whole, counts):
+    out = PerImage(whole.split(counts, 0))
+    out.whole = whole
+    return out
+
+
+def _whole(parts):
+    w = getattr(parts, "whole", None)
+    return w if w is not None else torch.cat(list(parts))
+
+
+_PAIR_INDEX_CACHE = {}
+
+
 def global_pair_index(rel_pair_idxs, num_objs, device):
-    """list of [P_i,2] per-image index tensors -> (int32 [P,2] global ids, int32 [B+1] pair offsets, int32 [P] image id)."""
-    off = np.concatenate(([0], np.cumsum(num_objs)))
-    parts = [p.to(device=device, dtype=torch.int32) + int(off[i]) for i, p in enumerate(rel_pair_idxs)]
+    """list of [P_i,2] per-image index tensors -> (int32 [P,2] global ids, int32 [B+1] pair offsets, int32 [P] image id,
+    per-image pair counts).  A handful of whole-batch device ops (no per-image launches); the last result is cached on the
+    identity + version of the index tensors because the relation tail and the post-processor receive the same list."""
+    key = (tuple((p.data_ptr(), p._version, p.shape[0]) for p in rel_pair_idxs), tuple(int(n) for n in num_objs), str(device))
+    hit = _PAIR_INDEX_CACHE.get("last")
+    if hit is not None and hit[0] == key:
+        return hit[1]
     num_rels = [int(p.shape[0]) for p in rel_pair_idxs]
-    pair_off = torch.tensor(np.concatenate(([0], np.cumsum(num_rels))), dtype=torch.int32, device=device)
-    pair_img = torch.repeat_interleave(torch.arange(len(num_rels), dtype=torch.int32, device=device),
-                                       torch.tensor(num_rels, device=device))
-    return torch.cat(parts).contiguous(), pair_off, pair_img, num_rels
+    n = int(sum(num_rels))
+    obj_base = np.concatenate(([0], np.cumsum(num_objs)))[:-1]
+    host = torch.from_numpy(np.concatenate((np.concatenate(([0], np.cumsum(num_rels))), obj_base, num_rels)).astype(np.int32))
+    dev_meta = host.to(device)
+    b = len(num_rels)
+    pair_off, base, counts = dev_meta[:b + 1], dev_meta[b + 1:2 * b + 1], dev_meta[2 * b + 1:]
+    pair_img = torch.repeat_interleave(torch.arange(b, dtype=torch.int32, device=device), counts.long(), output_size=n)
+    idx = torch.cat([p for p in rel_pair_idxs]).to(device=device, dtype=torch.int32)
+    idx = (idx + base[pair_img.long()].unsqueeze(1)).contiguous()
+    out = (idx, pair_off.contiguous(), pair_img, num_rels)
+    _PAIR_INDEX_CACHE["last"] = (key, out, rel_pair_idxs)          # holds the list so the data_ptr identity stays valid
+    return out
 
 
 @torch.no_grad()
@@ -173,8 +211,10 @@ def hierarchical_relation_tail(edge_rep, rel_pair_idxs, num_objs, obj_preds, uni
     rel, sup = ops.sgb_hier_softmax(logits, rel_compress.splits(), None if freq_bias_weight is None else freq_bias_weight.float().contiguous(),
                                     NUM_OBJ_SGB, pair_pred, _label_ids(dev))
     g, p, _ = rel_compress.splits()
-    return (rel[:, :g].split(num_rels, 0), rel[:, g:g + p].split(num_rels, 0), rel[:, g + p:].split(num_rels, 0),
-            sup.split(num_rels, 0))
+    out = (_per_image(rel[:, :g], num_rels), _per_image(rel[:, g:g + p], num_rels), _per_image(rel[:, g + p:], num_rels),
+           _per_image(sup, num_rels))
+    out[0].joint = rel                                              # [P, G+P+S] as one tensor for HierarchPostProcessor.candidates
+    return out
 
 
 class HierarchPostProcessor(nn.Module):
@@ -194,13 +234,16 @@ class HierarchPostProcessor(nn.Module):
         """Object scores/labels (inference.py:214-222) and the 3P triple-score candidates (:246-281) for a whole batch."""
         dev = rel1[0].device
         num_objs = [int(l.shape[0]) for l in refine_logits]
-        logit = torch.cat(list(refine_logits)).float()
+        logit = _whole(refine_logits).float()
         prob = torch.softmax(logit, -1)
         prob[:, 0] = 0
         obj_scores, obj_pred = prob[:, 1:].max(dim=1)
         obj_pred = obj_pred + 1
         pair_idx, pair_off, pair_img, num_rels = global_pair_index(rel_pair_idxs, num_objs, dev)
-        rel = torch.cat((torch.cat(list(rel1)), torch.cat(list(rel2)), torch.cat(list(rel3))), dim=1).float().contiguous()
+        rel = getattr(rel1, "joint", None)                         # the tail's own [P,50] tensor when rel1..3 come from it
+        if rel is None or rel.shape[1] != sum(SPLITS):
+            rel = torch.cat((_whole(rel1), _whole(rel2), _whole(rel3)), dim=1)
+        rel = rel.float().contiguous()
         score, label, row = ops.sgb_candidates(rel, SPLITS, pair_off, pair_img, pair_idx, obj_scores.contiguous(), _label_ids(dev))
         return dict(score=score, label=label, row=row, rel=rel, pair_idx=pair_idx, pair_off=pair_off, pair_img=pair_img, num_rels=num_rels,
                     num_objs=num_objs, obj_scores=obj_scores, obj_pred=obj_pred)
@@ -262,22 +305,30 @@ class SGBRecall:
         local to the image; gt_classes: list of int [N_i]; gt_boxes: list of f32 [N_i,4] xyxy.  PredCLS: predictions use the
         GT boxes and labels (vg_eval.py:267-270).  reject: optional uint8 [B,128] validator verdict per first-sort rank."""
         dev = cand["score"].device
-        obj_off = np.concatenate(([0], np.cumsum(cand["num_objs"])))
-        g_off = np.concatenate(([0], np.cumsum([int(g.shape[0]) for g in gt_rels]))).astype(np.int32)
-        rel_rows = []
-        for i, g in enumerate(gt_rels):
-            g = torch.as_tensor(g).to(dev, torch.int32).view(-1, 3).clone()
-            g[:, :2] += int(obj_off[i])
-            rel_rows.append(g)
-        gt_rel = torch.cat(rel_rows).contiguous() if rel_rows else torch.zeros(0, 3, dtype=torch.int32, device=dev)
-        gt_cls = torch.cat([torch.as_tensor(c).to(dev, torch.int32) for c in gt_classes]).contiguous()
-        gt_box = torch.cat([torch.as_tensor(b).to(dev, torch.float32).view(-1, 4) for b in gt_boxes]).contiguous()
+        obj_base = np.concatenate(([0], np.cumsum(cand["num_objs"])))[:-1]
+        g_cnt = np.asarray([int(g.shape[0]) for g in gt_rels], dtype=np.int64)
+        g_off = np.concatenate(([0], np.cumsum(g_cnt))).astype(np.int32)
+        n_gt = int(g_off[-1])
+        # whole-batch packing: one cat per field, the per-image object-id base added by a gather (no per-image launches)
+        if n_gt:
+            rel_all = torch.cat([torch.as_tensor(g).view(-1, 3) for g in gt_rels])
+            add = torch.from_numpy(np.repeat(obj_base, g_cnt).astype(np.int64)).to(rel_all.device, rel_all.dtype)
+            rel_all = rel_all.clone()
+            rel_all[:, :2] += add.unsqueeze(1)
+            gt_rel = rel_all.to(dev, torch.int32).contiguous()
+        else:
+            gt_rel = torch.zeros(1, 3, dtype=torch.int32, device=dev)
+        gt_cls = torch.cat([torch.as_tensor(c) for c in gt_classes]).to(dev, torch.int32).contiguous()
+        gt_box = torch.cat([torch.as_tensor(b).view(-1, 4) for b in gt_boxes]).to(dev, torch.float32).contiguous()
         cand_off = (cand["pair_off"] * 3).contiguous()
         ranked = ops.topk_select(cand_off, cand["score"], 128)
         out = ops.sgb_rank_match(ranked, reject, cand["pair_off"], cand["score"], cand["label"], cand["row"], cand["pair_idx"], gt_cls, gt_box,
-                                 torch.from_numpy(g_off).to(dev), gt_rel if gt_rel.numel() else torch.zeros(1, 3, dtype=torch.int32, device=dev),
-                                 gt_cls, gt_box, self.iou_thresh, self.top_k)
-        final_rank, hits, ngt, hits_pc, cnt_pc = (t.cpu().numpy() for t in out)
+                                 torch.from_numpy(g_off).to(dev), gt_rel, gt_cls, gt_box, self.iou_thresh, self.top_k)
+        # one D2H read for the five int32 result tables
+        sizes = [t.numel() for t in out]
+        flat = torch.cat([t.reshape(-1) for t in out]).cpu().numpy()
+        cuts = np.cumsum(sizes)[:-1]
+        final_rank, hits, ngt, hits_pc, cnt_pc = (a.reshape(t.shape) for a, t in zip(np.split(flat, cuts), out))
         self.img_hits.append(hits); self.img_ngt.append(ngt); self.img_hits_pc.append(hits_pc); self.img_cnt_pc.append(cnt_pc)
         return final_rank, ranked
 

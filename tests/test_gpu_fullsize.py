@@ -104,3 +104,84 @@ def test_cfg1_full_image_scores_within_tolerance_of_oracle():
     # logsig is recomputed by the oracle replay with torch.log(torch.sigmoid(.)) on the same fp32 connectivity
     np.testing.assert_array_equal(c[:tables.EV_SIZE], ev.counters())
     np.testing.assert_array_equal(c[tables.EV_SIZE:], t3.counters())
+
+
+def test_streamed_windows_equal_sequential_steps():
+    """RelationPipeline.run (H2D of window k+1 prefetched on a copy stream under window k's kernels) returns, window by
+    window, exactly the counters of stepping the same windows one after the other."""
+    from scene_graph_commonsense_b200 import model, pipeline
+    sd = synthetic.head_state_dict(seed=0, logit_gain=40.0)
+    pk = model.PackedHead(sd, DEV)
+    hosts = [pipeline.host_batch_from_samples(synthetic.make_batch([880 + 3 * w, 881 + 3 * w, 882 + 3 * w][:2 + w % 2], 4 + w, p_rel=0.5))
+             for w in range(4)]
+    seq = pipeline.RelationPipeline(pk, DEV, commonsense=True)
+    want = []
+    for hb in hosts:
+        n = seq.step(hb.to_device(DEV))
+        want.append((n, seq.counters.cpu().numpy().copy()))
+    stream = pipeline.RelationPipeline(pk, DEV, commonsense=True)
+    got = [(n, c.numpy().copy()) for n, c in stream.run(iter(hosts))]
+    assert len(got) == len(want)
+    for (n0, c0), (n1, c1) in zip(want, got):
+        assert n0 == n1
+        np.testing.assert_array_equal(c0, c1)
+    assert want[-1][1][tables.EV_NGT] > 0
+    # with a reset hook every window stands alone
+    solo = pipeline.RelationPipeline(pk, DEV, commonsense=True)
+    per_window = [c.numpy().copy() for _, c in solo.run(iter(hosts), before_step=lambda p: p.reset())]
+    np.testing.assert_array_equal(np.sum(per_window, axis=0), want[-1][1])
+
+
+def test_cfg2_full_size_counters_bit_exact_vs_oracle():
+    """BASELINE config 2 in full (64 images x 40 boxes, 99 840 directed pairs, 299 520 candidates, shipped commonsense sets,
+    reference batch skip rule): every Evaluator / Evaluator_Top3 counter and the connectivity statistics equal the loop
+    oracle's on identical scores (about 15 s of CPU for the oracle)."""
+    from oracle import hiercom_oracle as O
+    from scene_graph_commonsense_b200 import pipeline
+    from tests import helpers
+    from tests.test_gpu_eval import _scores_for_pairs
+    samples = synthetic.make_batch(list(range(64)), 40, base_seed=0, with_maps=False, p_rel=0.3)
+    pipe = pipeline.RelationPipeline(None, DEV, commonsense=True)
+    b = pipeline.batch_from_samples(samples, DEV, skip_mode="batch", with_maps=False)
+    pairs = pipe.enumerate_pairs(b)
+    assert pairs["n"] == 99840
+    rel, sup, conn, logsig = _scores_for_pairs(samples, b, pairs, dict(gain=3.0))
+    pipe.evaluate(b, pairs, rel, sup, logsig, connectivity=conn)
+    ev, t3 = helpers.oracle_evaluators(dict(run_mode="eval_cs"), True)
+    stats = dict(num_not_connected=0, num_connected=0, num_connected_pred=0, connectivity_precision=0, connectivity_recall=0)
+    n = O.replay_predcls(samples, synthetic.batch_score_fn(samples, helpers.SPLITS, gain=3.0), ev, t3, stats=stats, features=False)
+    m = ev.compute(per_class=True)
+    m3 = t3.compute(per_class=True)
+    assert n == pairs["n"]
+    c = pipe.counters.cpu().numpy()
+    np.testing.assert_array_equal(c[:tables.EV_SIZE], ev.counters())
+    np.testing.assert_array_equal(c[tables.EV_SIZE:], t3.counters())
+    assert c[tables.EV_NGT] > 10000 and c[tables.EV_HITS + 2] > 0
+    got = pipe.metrics()
+    np.testing.assert_allclose(helpers.flat_metrics(got["evaluator"]), helpers.flat_metrics(m), rtol=0, atol=0, equal_nan=True)
+    np.testing.assert_allclose(helpers.flat_metrics(got["top3"]), helpers.flat_metrics(m3), rtol=0, atol=0, equal_nan=True)
+    s = pipe.stats.cpu().numpy()
+    want = [stats[k] for k in ("num_not_connected", "num_connected", "num_connected_pred", "connectivity_precision", "connectivity_recall")]
+    np.testing.assert_array_equal(s.astype(np.float64), np.asarray([float(x) for x in want]))
+
+
+def test_cfg3_full_size_sgdet_counters_bit_exact_vs_oracle():
+    """BASELINE config 3 shape (100 proposals / image = 9 900 directed pairs and 29 700 candidates per image, 20 GT boxes,
+    object-confidence add, synonym matching, top-100): counters equal the loop oracle's on identical scores."""
+    from oracle import hiercom_oracle as O
+    from scene_graph_commonsense_b200 import pipeline
+    from tests import helpers
+    from tests.test_gpu_eval import _scores_for_pairs
+    batch = [synthetic.make_sgdet_image(i, 20, 100, p_rel=0.3, with_maps=False) for i in range(400, 404)]
+    pipe = pipeline.RelationPipeline(None, DEV, commonsense=True, predcls=False)
+    b = pipeline.batch_from_samples(batch, DEV, skip_mode="batch", sgdet=True, with_maps=False)
+    pairs = pipe.enumerate_pairs(b)
+    rel, sup, conn, logsig = _scores_for_pairs(batch, b, pairs, dict(gain=3.0))
+    pipe.evaluate(b, pairs, rel, sup, logsig)
+    ev, _ = helpers.oracle_evaluators(dict(run_mode="eval_cs"), True)
+    n = O.replay_sgdet(batch, synthetic.batch_score_fn(batch, helpers.SPLITS, gain=3.0), ev, features=False)
+    ev.compute(per_class=True, predcls=False)
+    assert n == pairs["n"] and n > 30000
+    c = pipe.counters.cpu().numpy()
+    np.testing.assert_array_equal(c[:tables.EV_SIZE], ev.counters())
+    assert c[tables.EV_NGT] > 0
