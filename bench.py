@@ -93,7 +93,7 @@ WORKLOADS = {
     # name: images per GPU, boxes (proposals) per image, SGDET-style?, pair chunk
     "cfg2": dict(images=IMAGES_PER_GPU, boxes=BOXES, sgdet=False, chunk_pairs=16384,
                  text="cfg2: PredCLS %d images x %d boxes per GPU (%d directed pairs/GPU/step), two-pass, eval_cs, reference batch skip rule"),
-    "cfg3": dict(images=8, boxes=100, sgdet=True, chunk_pairs=20480,
+    "cfg3": dict(images=8, boxes=100, sgdet=True, chunk_pairs=40960,
                  text="cfg3: SGDET-style %d images x %d proposals per GPU (%d directed pairs/GPU/step, 20 GT boxes/image), two-pass, "
                       "object-confidence add, synonym matching, top-100 triplets, eval_cs, reference batch skip rule"),
 }
@@ -175,7 +175,7 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     chunk_pairs = args.chunk_pairs or wl["chunk_pairs"]
     pipe = pipeline.RelationPipeline(packed, dev, commonsense=True, chunk_pairs=chunk_pairs, conv3_m_sub=args.conv3_m_sub,
-                                     overlap=not args.no_overlap, predcls=not wl["sgdet"])
+                                     overlap=not args.no_overlap, predcls=not wl["sgdet"], chunk_policy=args.chunk_policy)
     samples = make_samples(rank, wl["images"], wl["boxes"], sgdet=wl["sgdet"])
     host = pipeline.host_batch_from_samples(samples, skip_mode="batch", sgdet=wl["sgdet"])
     del samples
@@ -281,7 +281,7 @@ def run_ours(args):
                    "parallelism": "images sharded over %d GPU(s), one int64[765] all-reduce per step" % world,
                    "l2": "no explicit flush: each step streams >10 GB of activations/weights (>> 126 MB L2)",
                    "weights": "random init, trained-scale logits (seed 0)", "chunk_pairs": chunk_pairs,
-                   "pool_gemm_overlap": not args.no_overlap, "conv3_m_sub": args.conv3_m_sub},
+                   "pool_gemm_overlap": not args.no_overlap, "conv3_m_sub": args.conv3_m_sub, "chunk_policy": args.chunk_policy},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes * world,
                 "d2h_bytes_per_step": (tables.COUNTER_SIZE * 8 + 4) * world, "ms_per_step": t_e2e / args.steps * 1e3,
                 "api": "RelationPipeline.run over pinned HostBatch windows (H2D of window k+1 issued under window k's kernels; "
@@ -319,6 +319,8 @@ def main():
     ap.add_argument("--conv3-m-sub", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--chunk-policy", default="waves", choices=["waves", "greedy"],
+                    help="waves = image-aligned chunks sized for the fc1 GEMM's wave quantisation (default); greedy = fill to the cap")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -231,3 +231,38 @@ def test_checkpoint_names_cover_both_reference_spellings(tmp_path):
     lin2 = torch.nn.Linear(4, 3)
     assert formats.load_checkpoint(lin2, args, 2) == names[1]
     assert torch.equal(lin2.weight, lin.weight)
+
+
+def test_chunk_picker_partitions_images_and_minimises_fc1_rounds():
+    """pipeline._image_chunks (host logic): image-aligned chunks partition the window, respect the pair cap (single
+    over-sized images excepted) and never cost more (fc1 rounds + exposed first pooling + launches) than plain greedy chunking at the cap."""
+    from scene_graph_commonsense_b200 import pipeline
+
+    class _P:
+        _greedy_chunks = staticmethod(pipeline.RelationPipeline._greedy_chunks)
+        _chunk_cost = staticmethod(pipeline.RelationPipeline._chunk_cost)
+        n_sm = 148
+
+    rounds = lambda ch: sum(-(-(-(-c[3] // 256) * 16) // 148) for c in ch)
+    rng = np.random.default_rng(0)
+    cases = [(16384, np.full(64, 1560)), (40960, np.full(8, 9240)), (16384, np.full(1, 380)), (100, np.zeros(3, np.int64)),
+             (5000, np.array([2, 240, 42, 6, 132, 72, 0, 380, 6000, 90]))]
+    cases += [(int(rng.integers(500, 30000)), rng.integers(0, 4000, int(rng.integers(1, 40)))) for _ in range(20)]
+    for cap, per_img in cases:
+        off = np.concatenate(([0], np.cumsum(per_img)))
+        p = _P()
+        p.chunk_pairs = cap
+        ch = pipeline.RelationPipeline._image_chunks(p, off)
+        assert sum(c[3] for c in ch) == off[-1]
+        covered = sorted((c[0], c[0] + c[1]) for c in ch)
+        for (a0, a1), (b0, b1) in zip(covered, covered[1:]):
+            assert a1 <= b0
+        for img0, n_img, base, cnt in ch:
+            assert base == off[img0] and cnt == off[img0 + n_img] - off[img0] and cnt > 0
+            assert cnt <= cap or n_img == 1 or (off[img0 + 1:img0 + n_img + 1] - off[img0:img0 + n_img] > 0).sum() == 1
+        cost = pipeline.RelationPipeline._chunk_cost
+        assert cost(ch) <= cost(pipeline.RelationPipeline._greedy_chunks(off, cap)) + 1e-9
+    p = _P()
+    p.chunk_pairs = 16384
+    ch = pipeline.RelationPipeline._image_chunks(p, np.arange(65) * 1560)
+    assert rounds(ch) == 43 and ch[0][3] == min(c[3] for c in ch)          # cfg2: 43 rounds (10-image chunks needed 45)
