@@ -34,3 +34,16 @@ FRONTEND_CASES = {
     "fe_ragged": dict(ids=[83, 84, 85, 86], n_gt=[3, 12, 7, 2], queries=100, kw=dict(p_noobj=0.8, p_dup=0.45)),
     "fe_sparse": dict(ids=[87, 88], n_gt=[5, 4], queries=100, kw=dict(p_noobj=0.96, p_dup=0.1, p_second_noobj=0.6)),
 }
+
+TRAIN_CASES = {
+    # training-side losses on the hierarchical head: train_utils.train_one_direction driven by the loop body of
+    # train_test.py:187-258.  Inputs are regenerated from seeds (synthetic.make_batch, synthetic.head_state_dict, seeded hidden
+    # vectors); the golden files hold the reference's per-call losses, the step loss and its autograd gradients.
+    "tr_hier_cs": dict(ids=[90, 91, 92], n=[5, 3, 6], run_mode="train_cs", hierar=True, cs=(8, 0.5, 0.1), gain=3.0),
+    "tr_hier_plain": dict(ids=[93, 94, 95, 96], n=[4, 7, 2, 6], run_mode="train", hierar=True, gain=3.0),
+    "tr_hier_temps": dict(ids=[97, 98, 99], n=[6, 6, 4], run_mode="train_cs", hierar=True, cs=(9, 0.3, 0.3), gain=2.0,
+                          temps=(2.0, 0.5, 1.5), p_rel=0.8),
+    "tr_hier_sparse": dict(ids=[100, 101], n=[5, 8], run_mode="train_cs", hierar=True, cs=(10, 0.9, 0.0), gain=3.0, p_rel=0.1),
+    "tr_flat_cs": dict(ids=[102, 103, 104], n=[6, 4, 5], run_mode="train_cs", hierar=False, cs=(11, 0.5, 0.1), gain=3.0),
+    "tr_flat_plain": dict(ids=[105, 106], n=[7, 3], run_mode="train", hierar=False, gain=1.0),
+}
