@@ -322,6 +322,45 @@ int hc_targets_flat(const int8_t* dir_tri, const int32_t* rel_tri, const int32_t
                     const int32_t* box_offsets, int32_t n_images, int32_t* ws_count, int32_t* gt_offsets,
                     int32_t* gt_label, int32_t* gt_sub, int32_t* gt_obj, hc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * N4 - training-side losses on the hierarchical head and their backward (train_utils.py:23-113 train_one_direction,
+ * :116-157 calculate_losses_on_relationships; criteria of train_test.py:105-117; step accumulation train_test.py:187-258).
+ * The reference evaluates the losses once per CALL (graph_iter, edge_iter, direction) over the images of the lock-step
+ * batch that own box graph_iter.  Here every directed pair is a ROW (relation [n_rows, ld_rel] = the head's joint log-probs,
+ * or raw logits for the flat head; super_rel [n_rows,3]; connectivity [n_rows]; all from hc_hier_head) and call m owns rows
+ * group_rows[group_offsets[m] : group_offsets[m+1]].  row_target = directed predicate label, -1 = not connected (:62-73).
+ *   loss_connectivity  connected rows exist: BCEWithLogits(conn[connected], 1) (it overwrites the other term, :88-90), else
+ *                      lam_not_connected * BCEWithLogits(conn[not connected], 0) (:67-68)
+ *   loss_relationship  hier: NLL(super[connected], super target) + sum_k NLLLoss(weight)(rel_k[connected_k], t - off_k);
+ *                      flat: CrossEntropyLoss(weight)(relation[connected], t)
+ *   loss_commonsense   bitmaps non-NULL (run_mode 'train_cs'): p = max softmax(rel_k) for each (row, k), triplet
+ *                      (cat_sub, argmax + off_k, cat_obj): lam_cs_weak * mean(p[not in aligned]) + lam_cs_strong *
+ *                      mean(p[in violated]) (:36-60); aligned_bitmap / violated_bitmap are plain membership bitmaps over keys
+ *                      (s*50+p)*150+o (hc_cs_bitmap_build(keys, n, NULL, 0, out) builds one)
+ * group_loss [n_groups,3] = (relationship, connectivity, commonsense) of each call, as train_one_direction returns them.
+ * total [4]: total[0] = sum_m group_weight[m] * (rel_m + lam_conn*conn_m + lam_cs*cs_m) - with group_weight[m] = M - m this
+ * is the reference's step loss, whose running-sum accumulation (`losses += loss_relationship + ...` with cumulative operands,
+ * train_test.py:219-230) weights call m by the number of calls that follow it; total[1..3] = sum_m group_weight[m] * each part.
+ * d_logits (optional) [n_rows, ld_dl]: gradient of total[0] with respect to the head's pre-softmax outputs in hc_hier_head's
+ * w_heads row order (hier: fc3_1 | fc3_2 | fc3_3 | fc4 | fc5; flat: fc3 | fc4); rows in no call get zeros.
+ * No float atomics: losses and gradients are bit-reproducible.
+ */
+int hc_hier_loss(const float* relation, int64_t ld_rel, const float* super_rel, const float* connectivity, int32_t n_rows,
+                 int32_t n_geo, int32_t n_pos, int32_t n_sem, int32_t hier, float t1, float t2, float t3,
+                 const int32_t* row_target, const int32_t* group_offsets, const int32_t* group_rows, int32_t n_groups,
+                 const float* group_weight, const float* class_weight, const uint32_t* aligned_bitmap,
+                 const uint32_t* violated_bitmap, const int32_t* row_sub, const int32_t* row_obj, const int32_t* box_cat,
+                 float lam_conn, float lam_not_connected, float lam_cs, float lam_cs_weak, float lam_cs_strong,
+                 float* group_loss, float* total, float* d_logits, int32_t ld_dl, hc_stream_t stream);
+
+/* Backward of the heads fc3_x / fc4 / fc5 (model.py:171-183; what autograd does for the reference):
+ *   d_pred [n_rows,512] = scale * d_logits @ w_heads,  d_w [n_out,512] = scale * d_logits^T @ pred,  d_b [n_out] = scale * sum_r.
+ * scale: device scalar (the upstream gradient of the step loss) or NULL = 1.  d_pred and/or (d_w, d_b) may be NULL.
+ * ws: parts * n_out * 513 floats of workspace for the two-stage weight-gradient sum (fixed order, no atomics). */
+int hc_hier_head_bwd(const float* d_logits, int32_t ld_dl, const float* pred, int64_t ld_pred, int32_t n_rows, int32_t n_out,
+                     const float* w_heads, const float* scale, float* d_pred, float* d_w, float* d_b, float* ws,
+                     int32_t parts, hc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

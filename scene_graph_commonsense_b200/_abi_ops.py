@@ -382,3 +382,45 @@ def targets_flat(dir_tri, rel_tri, tri_offsets, box_offsets):
                                       ptr(label), ptr(sub), ptr(obj), stream_ptr()), "hc_targets_flat")
     _count(3)
     return gt_offsets, label, sub, obj
+
+
+def hier_loss(relation, super_rel, connectivity, row_target, group_offsets, group_rows, group_weight, class_weight, splits, hier=True,
+              temps=(1.0, 1.0, 1.0), aligned_bitmap=None, violated_bitmap=None, row_sub=None, row_obj=None, box_cat=None,
+              lambdas=(0.1, 1.0, 1.0, 0.1, 10.0), want_grad=True):
+    """N4: per-call training losses + gradient with respect to the head's logits (include/hiercom_b200.h hc_hier_loss).
+    lambdas = (connectivity, not_connected, commonsense, cs_weak, cs_strong).  Returns (group_loss [M,3], total [4], d_logits)."""
+    require_cuda(relation, super_rel, connectivity, row_target, group_offsets, group_rows, group_weight, class_weight, aligned_bitmap,
+                 violated_bitmap, row_sub, row_obj, box_cat)
+    n = relation.shape[0]
+    dev = relation.device
+    m = group_offsets.numel() - 1
+    n_out = sum(splits) + (4 if hier else 1)
+    group_loss = torch.empty(m, 3, dtype=torch.float32, device=dev)
+    total = torch.empty(4, dtype=torch.float32, device=dev)
+    d_logits = torch.empty(n, n_out, dtype=torch.float32, device=dev) if want_grad else None
+    check(_lib.load().hc_hier_loss(ptr(relation), relation.stride(0), ptr(super_rel), ptr(connectivity), n, splits[0], splits[1], splits[2],
+                                   int(hier), temps[0], temps[1], temps[2], ptr(row_target), ptr(group_offsets), ptr(group_rows), m,
+                                   ptr(group_weight), ptr(class_weight), ptr(aligned_bitmap), ptr(violated_bitmap), ptr(row_sub),
+                                   ptr(row_obj), ptr(box_cat), lambdas[0], lambdas[1], lambdas[2], lambdas[3], lambdas[4],
+                                   ptr(group_loss), ptr(total), ptr(d_logits), n_out, stream_ptr()), "hc_hier_loss")
+    _count(2)
+    return group_loss, total, d_logits
+
+
+def hier_head_bwd(d_logits, pred, w_heads, scale=None, want_pred=True, want_weights=True):
+    """Backward of fc3_x / fc4 / fc5: (d_pred [n,512], d_w [n_out,512], d_b [n_out]) (hc_hier_head_bwd)."""
+    require_cuda(d_logits, pred, w_heads, scale)
+    n, n_out = d_logits.shape
+    dev = d_logits.device
+    d_pred = torch.empty(n, pred.shape[1], dtype=torch.float32, device=dev) if want_pred else None
+    d_w = d_b = ws = None
+    parts = 0
+    if want_weights:
+        parts = max(1, min(148, (n + 63) // 64))
+        d_w = torch.empty(n_out, pred.shape[1], dtype=torch.float32, device=dev)
+        d_b = torch.empty(n_out, dtype=torch.float32, device=dev)
+        ws = torch.empty(parts * n_out * (pred.shape[1] + 1), dtype=torch.float32, device=dev)
+    check(_lib.load().hc_hier_head_bwd(ptr(d_logits), d_logits.stride(0), ptr(pred), pred.stride(0), n, n_out, ptr(w_heads), ptr(scale),
+                                       ptr(d_pred), ptr(d_w), ptr(d_b), ptr(ws), parts, stream_ptr()), "hc_hier_head_bwd")
+    _count(int(want_pred) + 2 * int(want_weights))
+    return d_pred, d_w, d_b

@@ -62,6 +62,9 @@ SIGNATURES = {
     "hc_match_object_categories": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "hc_match_object_categories_fill": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "hc_targets_flat": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
+    "hc_hier_loss": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _F, _F, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P,
+                               _P, _F, _F, _F, _F, _F, _P, _P, _P, _I32, _P]),
+    "hc_hier_head_bwd": (C.c_int, [_P, _I32, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P]),
 }
 
 _lib = None

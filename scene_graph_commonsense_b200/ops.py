@@ -149,6 +149,40 @@ def hier_head(fc2_raw, fc2_bias, emb, row_sub, row_obj, box_cat, box_super, w_he
     return relation, (None if flat else sup), conn, logsig, (pred if want_pred else None)
 
 
+# ------------------------------------------------------------------------------------------------ N4 training losses + head backward
+@_op("hier_loss", "(Tensor relation, Tensor? super_rel, Tensor connectivity, Tensor row_target, Tensor group_offsets, Tensor group_rows, "
+     "Tensor group_weight, Tensor class_weight, int[] splits, bool hier, float[] temps, Tensor? aligned_bitmap, Tensor? violated_bitmap, "
+     "Tensor? row_sub, Tensor? row_obj, Tensor? box_cat, float[] lambdas, bool want_grad) -> (Tensor, Tensor, Tensor)")
+def _hier_loss(relation, super_rel, connectivity, row_target, group_offsets, group_rows, group_weight, class_weight, splits, hier, temps,
+               aligned_bitmap, violated_bitmap, row_sub, row_obj, box_cat, lambdas, want_grad):
+    gl, total, dl = _A.hier_loss(relation, super_rel, connectivity, row_target, group_offsets, group_rows, group_weight, class_weight,
+                                 tuple(splits), hier, tuple(temps), aligned_bitmap, violated_bitmap, row_sub, row_obj, box_cat,
+                                 tuple(lambdas), want_grad)
+    return gl, total, _some(dl, relation)
+
+
+def hier_loss(relation, super_rel, connectivity, row_target, group_offsets, group_rows, group_weight, class_weight, splits, hier=True,
+              temps=(1.0, 1.0, 1.0), aligned_bitmap=None, violated_bitmap=None, row_sub=None, row_obj=None, box_cat=None,
+              lambdas=(0.1, 1.0, 1.0, 0.1, 10.0), want_grad=True):
+    """Per-call training losses of train_utils.train_one_direction + d(step loss)/d(head logits) (hc_hier_loss)."""
+    gl, total, dl = _call("hier_loss")(relation, super_rel, connectivity, row_target, group_offsets, group_rows, group_weight, class_weight,
+                                       list(splits), bool(hier), [float(t) for t in temps], aligned_bitmap, violated_bitmap, row_sub,
+                                       row_obj, box_cat, [float(x) for x in lambdas], bool(want_grad))
+    return gl, total, (dl if want_grad else None)
+
+
+@_op("hier_head_bwd", "(Tensor d_logits, Tensor pred, Tensor w_heads, Tensor? scale, bool want_pred, bool want_weights) "
+     "-> (Tensor, Tensor, Tensor)")
+def _hier_head_bwd(d_logits, pred, w_heads, scale, want_pred, want_weights):
+    d_pred, d_w, d_b = _A.hier_head_bwd(d_logits, pred, w_heads, scale, want_pred, want_weights)
+    return _some(d_pred, pred), _some(d_w, pred), _some(d_b, pred)
+
+
+def hier_head_bwd(d_logits, pred, w_heads, scale=None, want_pred=True, want_weights=True):
+    d_pred, d_w, d_b = _call("hier_head_bwd")(d_logits, pred, w_heads, scale, bool(want_pred), bool(want_weights))
+    return (d_pred if want_pred else None), (d_w if want_weights else None), (d_b if want_weights else None)
+
+
 # ------------------------------------------------------------------------------------------------ R8/R9/R10 candidates
 @_op("candidates", "(Tensor relation, int[] splits, bool hier, Tensor row_ov, Tensor logsig, Tensor row_sub, Tensor row_obj, "
      "Tensor box_cat, Tensor? pass_bitmap, Tensor? super_rel, Tensor? conf_sub, Tensor? conf_obj, int layout, bool want_top3) "

@@ -266,3 +266,28 @@ def test_chunk_picker_partitions_images_and_minimises_fc1_rounds():
     p.chunk_pairs = 16384
     ch = pipeline.RelationPipeline._image_chunks(p, np.arange(65) * 1560)
     assert rounds(ch) == 43 and ch[0][3] == min(c[3] for c in ch)          # cfg2: 43 rounds (10-image chunks needed 45)
+
+
+def test_training_rows_packing_matches_loop_layout():
+    """losses.training_rows_host (vectorised) == the loop restatement of train_test.py:189-258's call structure."""
+    from oracle import train_oracle as TO
+    from scene_graph_commonsense_b200 import losses
+    from tests.golden_cases import TRAIN_CASES
+    from tests.helpers import train_case_inputs
+    for name in ("tr_hier_plain", "tr_hier_sparse"):
+        inp = train_case_inputs(TRAIN_CASES[name])
+        s = inp["samples"]
+        cat = lambda lst: np.concatenate([np.concatenate([np.asarray(r) for r in x]) for x in lst if len(x)])
+        h = losses.training_rows_host(inp["counts"], cat([x.relationships for x in s]), cat([x.subj_or_obj for x in s]))
+        assert np.array_equal(h["row_sub"], inp["row_sub"]) and np.array_equal(h["row_obj"], inp["row_obj"])
+        assert np.array_equal(h["row_target"], inp["target"])
+        groups = inp["groups"]
+        assert len(h["group_weight"]) == len(groups)
+        for m, rows in enumerate(groups):
+            assert h["group_rows"][h["group_offsets"][m]:h["group_offsets"][m + 1]].tolist() == rows.tolist()
+        assert h["group_weight"].tolist() == list(range(len(groups), 0, -1))
+    # two lock-step batches in one window: weights restart per batch
+    h = losses.training_rows_host([3, 2, 4, 2], np.zeros(3 + 1 + 6 + 1, np.int64), -np.ones(11, np.int64), group_size=2)
+    assert len(h["group_weight"]) == 6 + 12 and h["group_weight"][:6].tolist() == [6, 5, 4, 3, 2, 1] and h["group_weight"][6] == 12
+    g, e = losses.tri_decode(np.arange(0, 5000))
+    assert np.array_equal(g * (g - 1) // 2 + e, np.arange(5000)) and (e < g).all() and (e >= 0).all()
