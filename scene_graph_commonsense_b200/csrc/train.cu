@@ -200,8 +200,10 @@ __global__ void loss_total_kernel(const float* __restrict__ group_loss, const fl
 }
 
 // d_pred[r, :] = scale * sum_j d_logits[r, j] W[j, :].  Persistent CTAs keep W (n_out x 512 f32 <= 128 KB) in shared memory;
-// a warp owns two rows at a time and a lane 16 of the 512 columns (4 float4), so one LDS.128 feeds 8 FMAs.
+// a warp owns BWD_RB rows at a time and a lane 16 of the 512 columns (4 float4), so one LDS.128 feeds 4 * BWD_RB FMAs (with fewer
+// rows per warp the kernel is bound by shared-memory bandwidth: an LDS.128 occupies the 128 B/clk port for 4 cycles).
 constexpr int BWD_THREADS = 512;
+constexpr int BWD_RB = 4;
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 head_bwd_dpred_kernel(const float* __restrict__ d_logits, int ld_dl, int n_rows, int n_out, const float* __restrict__ w_heads,
                       const float* __restrict__ scale, float* __restrict__ d_pred) {
@@ -212,28 +214,38 @@ head_bwd_dpred_kernel(const float* __restrict__ d_logits, int ld_dl, int n_rows,
   __syncthreads();
   const float sc = scale ? __ldg(scale) : 1.0f;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (long long row0 = ((long long)blockIdx.x * nw + wid) * 2; row0 < n_rows; row0 += (long long)gridDim.x * nw * 2) {
-    const long long ra = row0, rb = min(row0 + 1, (long long)n_rows - 1);
-    const float a0 = lane < n_out ? d_logits[ra * ld_dl + lane] : 0.f, a1 = lane + 32 < n_out ? d_logits[ra * ld_dl + lane + 32] : 0.f;
-    const float b0 = lane < n_out ? d_logits[rb * ld_dl + lane] : 0.f, b1 = lane + 32 < n_out ? d_logits[rb * ld_dl + lane + 32] : 0.f;
-    float4 xa[4], xb[4];
+  for (long long row0 = ((long long)blockIdx.x * nw + wid) * BWD_RB; row0 < n_rows; row0 += (long long)gridDim.x * nw * BWD_RB) {
+    float c0[BWD_RB], c1[BWD_RB];
+    float4 x[BWD_RB][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { xa[i] = make_float4(0.f, 0.f, 0.f, 0.f); xb[i] = xa[i]; }
+    for (int r = 0; r < BWD_RB; ++r) {
+      const long long row = min(row0 + r, (long long)n_rows - 1);       // tail rows are recomputed, never stored
+      c0[r] = lane < n_out ? d_logits[row * ld_dl + lane] : 0.f;
+      c1[r] = lane + 32 < n_out ? d_logits[row * ld_dl + lane + 32] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) x[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     for (int j = 0; j < n_out; ++j) {
-      const float ca = __shfl_sync(0xffffffffu, j < 32 ? a0 : a1, j & 31);
-      const float cb = __shfl_sync(0xffffffffu, j < 32 ? b0 : b1, j & 31);
+      float c[BWD_RB];
+#pragma unroll
+      for (int r = 0; r < BWD_RB; ++r) c[r] = __shfl_sync(0xffffffffu, j < 32 ? c0[r] : c1[r], j & 31);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const float4 w = reinterpret_cast<const float4*>(w_s + j * TR_HIDDEN)[lane + 32 * i];
-        xa[i].x = fmaf(ca, w.x, xa[i].x); xa[i].y = fmaf(ca, w.y, xa[i].y); xa[i].z = fmaf(ca, w.z, xa[i].z); xa[i].w = fmaf(ca, w.w, xa[i].w);
-        xb[i].x = fmaf(cb, w.x, xb[i].x); xb[i].y = fmaf(cb, w.y, xb[i].y); xb[i].z = fmaf(cb, w.z, xb[i].z); xb[i].w = fmaf(cb, w.w, xb[i].w);
+#pragma unroll
+        for (int r = 0; r < BWD_RB; ++r) {
+          x[r][i].x = fmaf(c[r], w.x, x[r][i].x); x[r][i].y = fmaf(c[r], w.y, x[r][i].y);
+          x[r][i].z = fmaf(c[r], w.z, x[r][i].z); x[r][i].w = fmaf(c[r], w.w, x[r][i].w);
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      reinterpret_cast<float4*>(d_pred + ra * TR_HIDDEN)[lane + 32 * i] = make_float4(xa[i].x * sc, xa[i].y * sc, xa[i].z * sc, xa[i].w * sc);
-      if (row0 + 1 < n_rows)
-        reinterpret_cast<float4*>(d_pred + rb * TR_HIDDEN)[lane + 32 * i] = make_float4(xb[i].x * sc, xb[i].y * sc, xb[i].z * sc, xb[i].w * sc);
+    for (int r = 0; r < BWD_RB; ++r) {
+      if (row0 + r >= n_rows) break;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        reinterpret_cast<float4*>(d_pred + (row0 + r) * TR_HIDDEN)[lane + 32 * i] =
+            make_float4(x[r][i].x * sc, x[r][i].y * sc, x[r][i].z * sc, x[r][i].w * sc);
     }
   }
 }
@@ -260,15 +272,20 @@ head_bwd_dw_kernel(const float* __restrict__ d_logits, int ld_dl, const float* _
       dl_s[rr][j] = (rr < nr && j < n_out) ? d_logits[(base + rr) * ld_dl + j] : 0.f;
     }
     __syncthreads();
-    for (int rr = 0; rr < nr; ++rr) {
-      const float p = pred[(base + rr) * ld_pred + c];
+    for (int r4 = 0; r4 < nr; r4 += 4) {                          // 4 global loads in flight before their 256 FMAs
+      float p[4];
 #pragma unroll
-      for (int j = 0; j < TR_MAX_OUT; j += 4) {                 // broadcast LDS.128: 4 coefficients per shared-memory read
-        const float4 d = *reinterpret_cast<const float4*>(&dl_s[rr][j]);
-        acc[j] = fmaf(d.x, p, acc[j]); acc[j + 1] = fmaf(d.y, p, acc[j + 1]);
-        acc[j + 2] = fmaf(d.z, p, acc[j + 2]); acc[j + 3] = fmaf(d.w, p, acc[j + 3]);
+      for (int u = 0; u < 4; ++u) p[u] = r4 + u < nr ? pred[(base + r4 + u) * ld_pred + c] : 0.f;   // rows >= nr: dl_s holds zeros
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < TR_MAX_OUT; j += 4) {               // broadcast LDS.128: 4 coefficients per shared-memory read
+          const float4 d = *reinterpret_cast<const float4*>(&dl_s[r4 + u][j]);
+          acc[j] = fmaf(d.x, p[u], acc[j]); acc[j + 1] = fmaf(d.y, p[u], acc[j + 1]);
+          acc[j + 2] = fmaf(d.z, p[u], acc[j + 2]); acc[j + 3] = fmaf(d.w, p[u], acc[j + 3]);
+        }
+        if (c < TR_MAX_OUT) accb += dl_s[r4 + u][c];
       }
-      if (c < TR_MAX_OUT) accb += dl_s[rr][c];
     }
   }
   float* out = ws_w + (long long)blockIdx.x * n_out * TR_HIDDEN;
@@ -350,7 +367,7 @@ extern "C" int hc_hier_head_bwd(const float* d_logits, int32_t ld_dl, const floa
         return cuda_status("cudaFuncSetAttribute(head_bwd_dpred_kernel)");
       configured = true;
     }
-    const int rows_per_cta = (BWD_THREADS / 32) * 2;
+    const int rows_per_cta = (BWD_THREADS / 32) * BWD_RB;
     int grid = (n_rows + rows_per_cta - 1) / rows_per_cta;
     if (grid > num_sms()) grid = num_sms();
     head_bwd_dpred_kernel<<<grid, BWD_THREADS, (size_t)n_out * TR_HIDDEN * sizeof(float), stream>>>(d_logits, ld_dl, n_rows, n_out, w_heads,

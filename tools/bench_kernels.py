@@ -177,6 +177,50 @@ def run_frontend(dev, iters, peak, results, n_images):
                     "frac_of_hbm_peak": by / (med * 1e-3) / 1e9 / peak, "note": "%d proposals kept" % p.n})
 
 
+def run_train(n_images, dev, iters, peak, results, tag):
+    """N4 training-side kernels: per-call losses + d_logits (450 B/row), head backward (d_logits + pred in, d_pred out: 4 312 B/row)."""
+    from scene_graph_commonsense_b200 import losses
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    base = synthetic.make_batch(list(range(64)), 40, with_maps=False, p_rel=0.3)
+    samples = [base[i % 64] for i in range(n_images)]
+    rows = losses.training_rows(samples, dev, group_size=64)
+    args = synthetic.reference_args(run_mode="train_cs", hierar=True)
+    crit = losses.RelationLoss(args, dev)
+    sd = synthetic.head_state_dict(seed=0, logit_gain=3.0)
+    f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+    names = ("fc3_1", "fc3_2", "fc3_3", "fc4", "fc5")
+    w_heads = torch.cat([f32(sd[k + ".weight"]) for k in names]).contiguous()
+    b_heads = torch.cat([f32(sd[k + ".bias"]) for k in names]).contiguous()
+    del sd
+    P = rows.n_rows
+    pred = torch.relu(torch.randn(P, 512, device=dev))
+    relation, sup, conn, _, _ = ops.hier_head(pred, None, None, None, None, None, None, w_heads, b_heads, (15, 11, 24))
+    out = {}
+
+    def loss():
+        out["l"] = ops.hier_loss(relation, sup, conn, rows.row_target, rows.group_offsets, rows.group_rows, rows.group_weight,
+                                 crit.class_weight, (15, 11, 24), True, (1.0, 1.0, 1.0), crit.aligned, crit.violated, rows.row_sub,
+                                 rows.row_obj, rows.box_cat, crit.lambdas)
+
+    def rec(name, bytes_alg, fn, note=""):
+        med, best = timeit(fn, iters, flush)
+        results.append({"kernel": name, "size": tag, "algorithmic_bytes": int(bytes_alg), "ms_median": med, "ms_min": best,
+                        "gbs": bytes_alg / (med * 1e-3) / 1e9, "frac_of_hbm_peak": bytes_alg / (med * 1e-3) / 1e9 / peak, "note": note})
+
+    rec("hier_loss (memset + hier_loss_kernel + loss_total_kernel)", P * 450, loss,
+        "%d calls; per-call commonsense penalty + connectivity BCE + hierarchical NLL and d(step loss)/d(logits)" % rows.n_groups)
+    d_logits = out["l"][2]
+    rec("hier_head_bwd (d_pred + two-stage d_W/d_b)", P * 4312, lambda: ops.hier_head_bwd(d_logits, pred, w_heads),
+        "fp32 SIMT: 2 x 2*54*512 FLOP per row")
+    r = results[-1]
+    r["fp32_tflops"] = P * 4 * 512 * 54 / (r["ms_median"] * 1e-3) / 1e12
+    rec("hier_head_bwd: d_pred only", P * (216 + 2048), lambda: ops.hier_head_bwd(d_logits, pred, w_heads, want_weights=False))
+    results[-1]["fp32_tflops"] = P * 2 * 512 * 54 / (results[-1]["ms_median"] * 1e-3) / 1e12
+    rec("hier_head_bwd: d_W / d_b only", P * (216 + 2048), lambda: ops.hier_head_bwd(d_logits, pred, w_heads, want_pred=False))
+    results[-1]["fp32_tflops"] = P * 2 * 512 * 54 / (results[-1]["ms_median"] * 1e-3) / 1e12
+    return P
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=20)
@@ -191,6 +235,8 @@ def main():
     run_gather(dev, args.iters, peak, results)
     run_frontend(dev, args.iters, peak, results, 64)
     run_frontend(dev, args.iters, peak, results, 4096)
+    run_train(64, dev, args.iters, peak, results, "training step, 64 images x 40 boxes (99 840 rows, 1 560 calls)")
+    run_train(args.scale_images, dev, max(args.iters // 2, 5), peak, results, "training, %d images x 40 boxes" % args.scale_images)
     print(json.dumps({"hbm_peak_gbs": peak, "peak_source": src, "pairs_cfg2": p_small, "pairs_scaled": p_big,
                       "timing": "CUDA events on the launching stream, median of N launches after 3 warm-ups, 256 MB L2 flush between launches",
                       "kernels": results}, indent=1))
