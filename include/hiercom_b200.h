@@ -79,6 +79,11 @@ int hc_pairs_enumerate(const int32_t* boxes, const int32_t* box_offsets, int32_t
  * mode HC_GEMM_CONV3 : implicit 3x3 / pad 1 / stride 1 convolution.  A is an NHWC activation tensor
  *     [n_img, H, W, c_total] bf16; input channels [c_base, c_base+c_in) are used; M = n_img*H*W output pixels,
  *     K = 9*c_in with k = (ky*3+kx)*c_in + c (B must be packed in that order).  H, W multiples of 16.
+ * mode HC_GEMM_CONV3_BLOCKS : the same convolution evaluated only on a device-side WORK LIST of 8-pixel-wide, `block_rows`-tall
+ *     (8 or 4) output blocks: `blocks[i] = img << 8 | (y0/2) << 4 | (x0/2)` (even origins), `n_blocks[0]` entries (read on the
+ *     device: no host round trip).  Pooled epilogue only; output pixels outside the listed blocks are NOT written (the caller
+ *     pre-fills them, see hc_conv3_active_blocks / hc_broadcast_rows).  Same K order as HC_GEMM_CONV3: listed pixels are
+ *     bit-identical to the dense result.
  * epilogue HC_EPI_BF16      : out bf16 [M, ldc] (+col offset c_off): act(acc + bias)
  *          HC_EPI_F32       : out f32  [M, ldc]: acc (+ bias if non-NULL)
  *          HC_EPI_POOL_BF16 : conv only: 2x2/stride-2 max-pool of relu(acc + bias) -> NHWC bf16
@@ -90,6 +95,7 @@ int hc_pairs_enumerate(const int32_t* boxes, const int32_t* box_offsets, int32_t
  */
 #define HC_GEMM_PLAIN 0
 #define HC_GEMM_CONV3 1
+#define HC_GEMM_CONV3_BLOCKS 2
 #define HC_EPI_BF16 0
 #define HC_EPI_F32 1
 #define HC_EPI_POOL_BF16 2
@@ -113,9 +119,28 @@ typedef struct hc_gemm_desc {
   int32_t m_sub;     /* 128-row sub-tiles per CTA tile: 1 or 2 (0 = default) */
   const float* mul;  /* optional f32 [M, ld_mul]: out = act(acc + bias) * mul (PLAIN, non-pooled); SGB `* union_features` */
   int64_t ld_mul;
+  const int32_t* blocks;   /* CONV3_BLOCKS: device work list */
+  const int32_t* n_blocks; /* CONV3_BLOCKS: device scalar, number of entries */
+  int32_t block_rows;      /* CONV3_BLOCKS: 8 or 4 */
 } hc_gemm_desc;
 
 int hc_tc_gemm(const hc_gemm_desc* desc, hc_stream_t stream);
+
+/* R3/R5 - which part of conv3_1's output a directed pair actually has to compute.
+ * `feature*mask` (train_test.py:391,398) leaves tanh(conv1_x.bias) outside a box, so every activation after it equals a
+ * weights-only BACKGROUND wherever the receptive field misses both boxes (model.py:139-146: 3x3 conv, 2x2 pool, 3x3 conv, 2x2
+ * pool).  For a box [lo,hi) on the 32-grid the pooled conv3_1 output (8-grid "cells") can differ from the background only in
+ * cells [ (max(0,(lo-1)>>1) - 1 clamped) >> 1 , (min(15, min(15, hi>>1) + 1)) >> 1 ] per axis; a pair's active set is the union of
+ * its two boxes' cell rectangles.  This entry point covers that set greedily (first uncovered cell in row-major order, block
+ * origin clamped into the map) with blocks of 4 x (block_rows/2) cells = 8 x block_rows conv3 pixels and writes the work list
+ * HC_GEMM_CONV3_BLOCKS consumes: blocks[i] = local_pair << 8 | cell_y << 4 | cell_x, pairs in order, n_blocks[0] = count.
+ * `blocks` must hold n_pairs * 64 / (2*block_rows) entries.  feature_size must be 32.  One CTA, deterministic order. */
+int hc_conv3_active_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
+                           int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream);
+
+/* out[i, :] = src[:] for i < n_rows (row_bytes a multiple of 16; both 16-byte aligned): pre-fills the pooled conv3_1 output of
+ * every pair with the background before HC_GEMM_CONV3_BLOCKS overwrites the active blocks. */
+int hc_broadcast_rows(const void* src, int64_t row_bytes, int64_t n_rows, void* out, hc_stream_t stream);
 
 /* [B,C0,hw] f32 (+ optional [B,C1,hw] f32) NCHW maps -> [B*hw, k_pad] bf16 pixel-major rows, zero padded
  * (the A operand of the 1x1 convolutions, model.py:139-140; also packs the legacy pre-masked [bs,257,32,32]). */

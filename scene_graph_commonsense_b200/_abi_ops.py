@@ -9,8 +9,8 @@ import numpy as np
 import torch
 
 from . import _lib, tables
-from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16, GEMM_CONV3, GEMM_PLAIN, check, ptr,
-                   require_cuda, stream_ptr)
+from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16, GEMM_CONV3, GEMM_CONV3_BLOCKS,
+                   GEMM_PLAIN, check, ptr, require_cuda, stream_ptr)
 
 LAUNCHES = {"n": 0}
 PROFILE = {"on": False, "events": []}     # bench.py: CUDA-event timing of tagged launches on the launching stream
@@ -78,9 +78,10 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 
 
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16,
-            act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None):
+            act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None,
+            blocks=None, n_blocks=None, block_rows=0):
     """out = epilogue(A @ B^T) on tcgen05 (see include/hiercom_b200.h hc_tc_gemm)."""
-    require_cuda(a, b, out, bias, mul)
+    require_cuda(a, b, out, bias, mul, blocks, n_blocks)
     d = _lib.GemmDesc()
     d.a, d.b, d.bias, d.out = ptr(a), ptr(b), ptr(bias), ptr(out)
     d.m, d.n, d.k = m, n, k
@@ -89,8 +90,39 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     d.n_img, d.h, d.w, d.c_total, d.c_base, d.c_in = n_img, h, w, c_total, c_base, c_in
     d.group_m, d.m_sub = group_m, m_sub
     d.mul, d.ld_mul = ptr(mul), (mul.stride(0) if mul is not None else 0)
+    d.blocks, d.n_blocks, d.block_rows = ptr(blocks), ptr(n_blocks), block_rows
     with _timed(tag):
         check(_lib.load().hc_tc_gemm(C.byref(d), stream_ptr()), "hc_tc_gemm")
+    _count()
+    return out
+
+
+def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=None, n_blocks=None):
+    """Work list of the block-sparse conv3_1 for the given directed pairs (include/hiercom_b200.h hc_conv3_active_blocks).
+    Returns (blocks int32 [n_pairs * 32 / block_rows], n_blocks int32 [1]); both stay on the device."""
+    require_cuda(boxes, pair_sub, pair_obj, blocks, n_blocks)
+    n = pair_sub.numel()
+    cap = max(n * (32 // block_rows), 1)
+    if blocks is None:
+        blocks = torch.empty(cap, dtype=torch.int32, device=boxes.device)
+    if n_blocks is None:
+        n_blocks = torch.empty(1, dtype=torch.int32, device=boxes.device)
+    if blocks.numel() < cap:
+        raise RuntimeError("hiercom_b200: conv3_active_blocks needs room for %d work-list entries" % cap)
+    check(_lib.load().hc_conv3_active_blocks(ptr(boxes), ptr(pair_sub), ptr(pair_obj), n, fs, block_rows, ptr(blocks), ptr(n_blocks),
+                                             stream_ptr()), "hc_conv3_active_blocks")
+    _count()
+    return blocks, n_blocks
+
+
+def broadcast_rows(src, n_rows, out):
+    """out[i] = src for i < n_rows (the background pre-fill of the pooled conv3_1 output)."""
+    require_cuda(src, out)
+    row_bytes = src.numel() * src.element_size()
+    if out.numel() * out.element_size() < n_rows * row_bytes or not src.is_contiguous() or not out.is_contiguous():
+        raise RuntimeError("hiercom_b200: broadcast_rows needs contiguous operands and room for n_rows copies")
+    with _timed("p3_fill"):
+        check(_lib.load().hc_broadcast_rows(ptr(src), row_bytes, n_rows, ptr(out), stream_ptr()), "hc_broadcast_rows")
     _count()
     return out
 

@@ -13,7 +13,7 @@ from . import build as _build
 HC_OK = 0
 ERRORS = {-1: "HC_E_SHAPE", -2: "HC_E_ALIGN", -3: "HC_E_ARCH", -4: "HC_E_CUDA", -5: "HC_E_NULL"}
 
-GEMM_PLAIN, GEMM_CONV3 = 0, 1
+GEMM_PLAIN, GEMM_CONV3, GEMM_CONV3_BLOCKS = 0, 1, 2
 EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16 = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
@@ -25,7 +25,8 @@ class GemmDesc(C.Structure):
                 ("mode", C.c_int32), ("epilogue", C.c_int32), ("act", C.c_int32),
                 ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("c_total", C.c_int32), ("c_base", C.c_int32), ("c_in", C.c_int32),
-                ("group_m", C.c_int32), ("m_sub", C.c_int32), ("mul", C.c_void_p), ("ld_mul", C.c_int64)]
+                ("group_m", C.c_int32), ("m_sub", C.c_int32), ("mul", C.c_void_p), ("ld_mul", C.c_int64),
+                ("blocks", C.c_void_p), ("n_blocks", C.c_void_p), ("block_rows", C.c_int32)]
 
 
 _P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -37,6 +38,8 @@ SIGNATURES = {
     "hc_cs_bitmap_build": (C.c_int, [_P, _I64, _P, _I64, _P]),
     "hc_pairs_enumerate": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hc_tc_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
+    "hc_conv3_active_blocks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "hc_broadcast_rows": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "hc_pack_pixels": (C.c_int, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "hc_box_select": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),

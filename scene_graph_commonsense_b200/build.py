@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhiercom_b200.so")
-SOURCES = ["abi.cu", "pairs.cu", "prep.cu", "head.cu", "topk.cu", "sgb.cu", "frontend.cu", "train.cu", "tc_gemm.cu"]
+SOURCES = ["abi.cu", "pairs.cu", "prep.cu", "blocks.cu", "head.cu", "topk.cu", "sgb.cu", "frontend.cu", "train.cu", "tc_gemm.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math=false"]
 

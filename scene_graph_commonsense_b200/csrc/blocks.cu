@@ -1,0 +1,128 @@
+// Active-region work list for the block-sparse conv3_1 (HC_GEMM_CONV3_BLOCKS) and the background pre-fill of its output.
+//
+// train_test.py:391,398 multiplies the feature map by a rectangular box mask, so after conv1_x + tanh every pixel outside the
+// box holds tanh(bias): a constant of the WEIGHTS.  Each later stage (3x3 conv, 2x2 pool, 3x3 conv, 2x2 pool, model.py:143-146)
+// grows the region that can differ from that weights-only background by its receptive field; outside it the pooled conv3_1
+// output of every pair equals one [8,8,1024] tensor computed once per checkpoint.  The GEMM therefore only has to visit the
+// dilated footprint of the pair's two boxes; everything else is a broadcast copy.
+#include "hc_common.cuh"
+
+namespace hc {
+
+// box interval [lo,hi) on the 32-grid -> half-open interval of 8-grid cells whose pooled conv3_1 output may differ from background
+__device__ __forceinline__ void active_cells(int lo, int hi, int& a, int& b) {
+  if (hi <= lo) { a = b = 0; return; }
+  int qlo = max(0, (lo - 1) >> 1), qhi = min(15, hi >> 1);      // pooled conv2 pixels touched by the box +-1 (arithmetic shift: -1>>1 = -1)
+  qlo = max(0, qlo - 1); qhi = min(15, qhi + 1);                // +-1 again: conv3_1's 3x3 window
+  a = qlo >> 1; b = (qhi >> 1) + 1;
+}
+
+__device__ __forceinline__ unsigned long long cell_mask(const Rect& r) {
+  int xa, xb, ya, yb;
+  active_cells(r.x0, r.x1, xa, xb);
+  active_cells(r.y0, r.y1, ya, yb);
+  if (xb <= xa || yb <= ya) return 0ull;
+  const unsigned long long rowbits = ((1ull << (xb - xa)) - 1ull) << xa;
+  const unsigned long long rows = (yb - ya >= 8) ? ~0ull : (((1ull << (8 * (yb - ya))) - 1ull) << (8 * ya));
+  return (0x0101010101010101ull & rows) * rowbits;
+}
+
+// greedy cover with blocks of 4 x hc cells; emit(entry) is called once per block, returns the count
+template <typename F>
+__device__ __forceinline__ int cover_greedy(unsigned long long m, int hc, F emit) {
+  int n = 0;
+  const unsigned long long rows = (hc == 4) ? 0x01010101ull : 0x0101ull;
+  while (m) {
+    const int bit = __ffsll((long long)m) - 1;
+    const int y = min(bit >> 3, 8 - hc), x = min(bit & 7, 4);
+    m &= ~((rows * 0xFull) << (8 * y + x));
+    emit((y << 4) | x);
+    ++n;
+  }
+  return n;
+}
+
+// the greedy cover can need one block more than the aligned tiling of the whole map (two staggered rectangles): never emit
+// more than the dense 2 x (8/hc) tiling, so a pair costs at most what the dense kernel would
+template <typename F>
+__device__ __forceinline__ int cover(unsigned long long m, int hc, F emit) {
+  const int full = 2 * (8 / hc);
+  if (cover_greedy(m, hc, [](int) {}) <= full) return cover_greedy(m, hc, emit);
+  for (int y = 0; y < 8; y += hc)
+    for (int x = 0; x < 8; x += 4) emit((y << 4) | x);
+  return full;
+}
+
+__global__ void __launch_bounds__(1024)
+conv3_blocks_kernel(const int4* __restrict__ boxes, const int* __restrict__ pair_sub, const int* __restrict__ pair_obj, int n_pairs, int fs,
+                    int hc, int* __restrict__ blocks, int* __restrict__ n_blocks) {
+  __shared__ int s_scan[1024];
+  const int t = threadIdx.x;
+  const int per = (n_pairs + 1023) / 1024;
+  const int p0 = min(n_pairs, t * per), p1 = min(n_pairs, p0 + per);
+  int cnt = 0;
+  for (int p = p0; p < p1; ++p) {
+    const unsigned long long m = cell_mask(rect_of(__ldg(boxes + pair_sub[p]), fs)) | cell_mask(rect_of(__ldg(boxes + pair_obj[p]), fs));
+    cnt += cover(m, hc, [](int) {});
+  }
+  s_scan[t] = cnt;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {                          // inclusive Hillis-Steele scan over the 1024 per-thread counts
+    const int v = t >= d ? s_scan[t - d] : 0;
+    __syncthreads();
+    s_scan[t] += v;
+    __syncthreads();
+  }
+  int o = s_scan[t] - cnt;
+  if (t == 1023) n_blocks[0] = s_scan[t];
+  for (int p = p0; p < p1; ++p) {
+    const unsigned long long m = cell_mask(rect_of(__ldg(boxes + pair_sub[p]), fs)) | cell_mask(rect_of(__ldg(boxes + pair_obj[p]), fs));
+    cover(m, hc, [&](int e) { blocks[o++] = (p << 8) | e; });
+  }
+}
+
+// a thread owns one 16-byte column of the row: one load, then a streaming store per destination row
+__global__ void broadcast_rows_kernel(const uint4* __restrict__ src, long long row_vecs, long long n_rows, uint4* __restrict__ out) {
+  const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= row_vecs) return;
+  const uint4 v = __ldg(src + c);
+  for (long long r = blockIdx.y; r < n_rows; r += gridDim.y) __stcs(out + r * row_vecs + c, v);
+}
+
+}  // namespace hc
+
+using namespace hc;
+
+extern "C" int hc_conv3_active_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
+                                      int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(n_blocks && (n_pairs <= 0 || (boxes && pair_sub && pair_obj && blocks)), HC_E_NULL, "hc_conv3_active_blocks: NULL operand");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  HC_REQUIRE(feature_size == 32, HC_E_SHAPE, "hc_conv3_active_blocks: built for feature_size 32 (8x8 pooled conv3 cells)");
+  HC_REQUIRE(block_rows == 8 || block_rows == 4, HC_E_SHAPE, "hc_conv3_active_blocks: block_rows must be 8 or 4");
+  HC_REQUIRE(n_pairs >= 0 && n_pairs < (1 << 23), HC_E_SHAPE, "hc_conv3_active_blocks: n_pairs must be below 2^23");
+  HC_REQUIRE(aligned16(boxes), HC_E_ALIGN, "hc_conv3_active_blocks: boxes must be 16-byte aligned");   // n_pairs == 0 still writes n_blocks = 0
+  conv3_blocks_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const int4*>(boxes), pair_sub, pair_obj, n_pairs, feature_size, block_rows / 2,
+                                              blocks, n_blocks);
+  return cuda_status("conv3_blocks_kernel launch");
+}
+
+extern "C" int hc_broadcast_rows(const void* src, int64_t row_bytes, int64_t n_rows, void* out, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(src && out, HC_E_NULL, "hc_broadcast_rows: NULL operand");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  HC_REQUIRE(row_bytes > 0 && row_bytes % 16 == 0 && n_rows >= 0, HC_E_SHAPE, "hc_broadcast_rows: row_bytes must be a positive multiple of 16");
+  HC_REQUIRE(aligned16(src) && aligned16(out), HC_E_ALIGN, "hc_broadcast_rows: src/out must be 16-byte aligned");
+  if (n_rows == 0) return HC_OK;
+  const long long row_vecs = row_bytes / 16;
+  const long long gx = (row_vecs + 255) / 256;
+  HC_REQUIRE(gx < (1ll << 31), HC_E_SHAPE, "hc_broadcast_rows: row too long");
+  long long gy = ((long long)num_sms() * 16 + gx - 1) / gx;
+  if (gy > n_rows) gy = n_rows;
+  if (gy > 65535) gy = 65535;
+  broadcast_rows_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), row_vecs, n_rows,
+                                                                            reinterpret_cast<uint4*>(out));
+  return cuda_status("broadcast_rows_kernel launch");
+}

@@ -9,6 +9,9 @@
 //                    descriptor start addresses 2048 B (= one 16-pixel row = two swizzle atoms) apart, so A is
 //                    fetched 3x instead of 9x per channel block; TMA zero-fills the padding halo, so no im2col
 //                    buffer ever exists)
+//   block-sparse conv (the same 3x3 convolution restricted to a WORK LIST of 8 x {8,4}-pixel blocks: a 128-row sub-tile is
+//                    assembled from 2 or 4 blocks of possibly different images, one 4-D TMA box per block and tap; used for
+//                    conv3_1, whose output equals a weights-only background outside the dilated footprint of the two boxes)
 // CTA = 6 warps: warp 0 TMA producer, warp 1 tcgen05.mma issuer (+TMEM owner), warps 2-5 epilogue
 // (TMEM -> registers -> fused bias/activation/2x2-max-pool -> global).  Pipelines: smem full/empty ring
 // (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -63,6 +66,9 @@ struct Params {
   long long ld_mul;
   void* out;
   int patch;                     // 1 = implicit-conv patch pipeline (A fetched once per (channel block, kx)), 0 = plain GEMM
+  const int* blocks;             // HC_GEMM_CONV3_BLOCKS: work list, entry = img << 8 | (y0/2) << 4 | (x0/2)
+  const int* n_blocks;           // device scalar: entries in the work list
+  int blk_h;                     // pixel rows per block (8 or 4); blocks are 8 pixels wide
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -193,11 +199,11 @@ __device__ __forceinline__ void store_bf16_row(const uint32_t (&r)[32], const fl
 
 // tile id -> (m block, n block): bands of `group_m` m-blocks; inside a band the n index is the slow one, so a
 // wave of consecutive tile ids shares few B column-panels and a bounded set of A row-panels through L2.
-__device__ __forceinline__ void tile_coords(const Params& p, int tile, int& m_blk, int& n_blk) {
+__device__ __forceinline__ void tile_coords(const Params& p, int tiles_m, int tile, int& m_blk, int& n_blk) {
   int per_band = p.group_m * p.tiles_n;
   int band = tile / per_band;
   int in = tile - band * per_band;
-  int gm = min(p.group_m, p.tiles_m - band * p.group_m);
+  int gm = min(p.group_m, tiles_m - band * p.group_m);
   m_blk = band * p.group_m + in % gm;
   n_blk = in / gm;
 }
@@ -225,7 +231,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  // block-sparse conv: the number of M tiles comes from the device-side work-list length (no host round trip)
+  const bool blk_mode = p.mode == HC_GEMM_CONV3_BLOCKS;
+  const int blk_per_sub = blk_mode ? BM / (8 * p.blk_h) : 1;        // blocks per 128-row sub-tile (2 or 4)
+  const int n_blocks = blk_mode ? __ldg(p.n_blocks) : 0;
+  const int tiles_m = blk_mode ? (n_blocks + MS * blk_per_sub - 1) / (MS * blk_per_sub) : p.tiles_m;
+  const int num_tiles = tiles_m * p.tiles_n;
   const int num_kb = p.K / BK;
 
   if (warp == 0 && lane == 0) {
@@ -253,7 +264,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int per_img = p.tiles_x * p.tiles_y;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
-        tile_coords(p, tile, m_blk, n_blk);
+        tile_coords(p, tiles_m, tile, m_blk, n_blk);
         const int img = m_blk / per_img;
         const int r = m_blk - img * per_img;
         const int y0 = (r / p.tiles_x) * (8 * MS), x0 = (r % p.tiles_x) * 16;
@@ -272,12 +283,43 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
+    } else if (lane == 0 && blk_mode) {
+      // one stage per (channel block, kx, ky) - the K order of the patch pipeline, so results are bit-identical to the dense
+      // kernel; every block of the tile contributes one {64 ch, 8 x, blk_h y} box shifted by the tap (TMA zero-fills the halo)
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cblks = p.c_in / BK;
+      const int nblk = MS * blk_per_sub;
+      const uint32_t blk_bytes = (uint32_t)(8 * p.blk_h) * 128u;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int m_blk, n_blk;
+        tile_coords(p, tiles_m, tile, m_blk, n_blk);
+        int e[MS * 4];
+#pragma unroll
+        for (int i = 0; i < MS * 4; ++i) e[i] = i < nblk ? __ldg(p.blocks + min(m_blk * nblk + i, n_blocks - 1)) : 0;
+        for (int cb = 0; cb < cblks; ++cb) {
+          for (int kx = 0; kx < 3; ++kx) {
+            for (int ky = 0; ky < 3; ++ky) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+              mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+#pragma unroll
+              for (int i = 0; i < MS * 4; ++i)
+                if (i < nblk)
+                  tma_load_4d(a_dst + i * blk_bytes, &tmap_a, full_bar(stage), p.c_base + cb * BK, 2 * (e[i] & 15) + kx - 1,
+                              2 * ((e[i] >> 4) & 15) + ky - 1, e[i] >> 8);
+              tma_load_2d(a_dst + MS * A_SUB_BYTES, &tmap_b, full_bar(stage), ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN);
+              if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
     } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
-        tile_coords(p, tile, m_blk, n_blk);
+        tile_coords(p, tiles_m, tile, m_blk, n_blk);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
@@ -365,9 +407,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int m_blk, n_blk;
-      tile_coords(p, tile, m_blk, n_blk);
+      tile_coords(p, tiles_m, tile, m_blk, n_blk);
       int t_img = 0, t_y0 = 0, t_x0 = 0;                  // conv: tile origin (image, first pixel row / column)
-      if (p.mode == HC_GEMM_CONV3) {
+      if (p.mode == HC_GEMM_CONV3) {   // dense conv only; block mode decodes its origin per warp below
         const int per_img = p.tiles_x * p.tiles_y;
         t_img = m_blk / per_img;
         const int rr = m_blk - t_img * per_img;
@@ -389,13 +431,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // rows of a sub-tile are pixels (yl, xl) = (row/16, row%16); this warp holds yl in {2q, 2q+1}.
             // 2x2 max-pool partners are lane^1 (x) and lane^16 (y): butterfly reduce-scatter, after which the
             // lane with bits (ybit, xbit) owns the pooled maximum of columns [ybit*16 + xbit*8, +8).
-            const int ybit = (lane >> 4) & 1, xbit = lane & 1;
+            // (block mode: rows of a block are pixels (yl, xl) = (row/8, row%8), so the y partner is lane^8)
+            const int ysh = blk_mode ? 3 : 4;
+            const int ybit = (lane >> ysh) & 1, xbit = lane & 1;
             float h[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               float mine = __uint_as_float(ybit ? r[16 + i] : r[i]);
               float send = __uint_as_float(ybit ? r[i] : r[16 + i]);
-              h[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 16));
+              h[i] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, send, 1 << ysh));
             }
             float o[8];
 #pragma unroll
@@ -412,10 +456,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               float b = fmaxf(o[2 * i + 1] + __ldg(p.bias + cbase + 2 * i + 1), 0.0f);
               w[i] = pack_bf16(a, b);
             }
-            const int py = (t_y0 + 8 * j) / 2 + q;                      // pooled row
-            const int px = t_x0 / 2 + ((lane & 15) >> 1);               // pooled col
+            int py = (t_y0 + 8 * j) / 2 + q;                            // pooled row
+            int px = t_x0 / 2 + ((lane & 15) >> 1);                     // pooled col
+            int o_img = t_img;
+            if (blk_mode) {
+              // this warp's 32 rows lie in block (32q / rows_per_block) of sub-tile j, (32q % rows_per_block) / 8 pixel rows in
+              const int rows_pb = 8 * p.blk_h;
+              const int bi = j * blk_per_sub + (q * 32) / rows_pb;
+              const int e = __ldg(p.blocks + min((m_blk * MS * blk_per_sub) + bi, n_blocks - 1));
+              o_img = e >> 8;
+              py = ((e >> 4) & 15) + ((((q * 32) % rows_pb) >> 3) >> 1) + (lane >> 4);
+              px = (e & 15) + ((lane & 7) >> 1);
+            }
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                 (((long long)t_img * (p.H / 2) + py) * (p.W / 2) + px) * p.ldc + p.c_off + cbase;
+                                 (((long long)o_img * (p.H / 2) + py) * (p.W / 2) + px) * p.ldc + p.c_off + cbase;
             *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
           } else {
             // output row of tile row `tr` (plain: GEMM row; conv: NHWC pixel index), -1 when outside M
@@ -552,7 +606,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
     configured = true;
   }
   int tiles = p.tiles_m * p.tiles_n;
-  int grid = tiles < num_sms() ? tiles : num_sms();
+  int grid = (p.mode == HC_GEMM_CONV3_BLOCKS || tiles >= num_sms()) ? num_sms() : tiles;   // block mode: tile count lives on the device
   tc_gemm_kernel<BN, MS><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   return cuda_status("tc_gemm_kernel launch");
 }
@@ -577,8 +631,11 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   HC_REQUIRE(d->epilogue >= 0 && d->epilogue <= 3, HC_E_SHAPE, "hc_tc_gemm: unknown epilogue");
   HC_REQUIRE(d->epilogue != HC_EPI_SPLIT3_BF16 || (d->mode == HC_GEMM_PLAIN && d->act != HC_ACT_TANH && d->ldc >= 3 * d->n), HC_E_SHAPE,
              "hc_tc_gemm: the bf16x3 split epilogue needs a plain GEMM, no tanh and ldc >= 3*N");
-  HC_REQUIRE(d->epilogue != HC_EPI_POOL_BF16 || (d->mode == HC_GEMM_CONV3 && d->bias), HC_E_SHAPE,
+  HC_REQUIRE(d->epilogue != HC_EPI_POOL_BF16 || ((d->mode == HC_GEMM_CONV3 || d->mode == HC_GEMM_CONV3_BLOCKS) && d->bias), HC_E_SHAPE,
              "hc_tc_gemm: pooled epilogue needs conv mode and a bias");
+  HC_REQUIRE(d->mode != HC_GEMM_CONV3_BLOCKS ||
+                 (d->epilogue == HC_EPI_POOL_BF16 && d->blocks && d->n_blocks && (d->block_rows == 8 || d->block_rows == 4)),
+             HC_E_SHAPE, "hc_tc_gemm: block-sparse conv needs the pooled epilogue, a work list and block_rows in {4, 8}");
   HC_REQUIRE(d->m < (1ll << 31) && d->n < (1ll << 31) && d->k < (1ll << 31), HC_E_SHAPE, "hc_tc_gemm: dims exceed int32");
 
   const int BN = (d->n % 256 == 0) ? 256 : 128;
@@ -592,6 +649,7 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   p.ldc = d->ldc; p.c_off = d->c_off; p.bias = d->bias; p.out = d->out;
   p.mul = d->mul; p.ld_mul = d->ld_mul;
   p.patch = d->mode == HC_GEMM_CONV3 ? 1 : 0;
+  p.blocks = d->blocks; p.n_blocks = d->n_blocks; p.blk_h = d->block_rows;
   HC_REQUIRE(!d->mul || (d->epilogue != HC_EPI_POOL_BF16 && d->mode == HC_GEMM_PLAIN && d->ld_mul % 4 == 0 && aligned16(d->mul)), HC_E_SHAPE,
              "hc_tc_gemm: mul needs a plain GEMM, a non-pooled epilogue and a 16-byte aligned [M, ld_mul] f32 operand");
   p.tiles_n = p.N / BN;
@@ -604,9 +662,12 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     rc = tc::make_map(&tb, d->b, 2, dims, str, box);
     if (rc != HC_OK) return rc;
   }
-  if (d->mode == HC_GEMM_CONV3) {
+  const bool blk = d->mode == HC_GEMM_CONV3_BLOCKS;
+  if (d->mode == HC_GEMM_CONV3 || blk) {
     HC_REQUIRE(d->h > 0 && d->w > 0 && d->n_img > 0, HC_E_SHAPE, "hc_tc_gemm: conv needs n_img,h,w");
-    HC_REQUIRE(d->w % 16 == 0 && d->h % (8 * MS) == 0, HC_E_SHAPE, "hc_tc_gemm: conv H,W must be multiples of the 16x8 tile");
+    HC_REQUIRE(blk ? (d->w >= 8 && d->w <= 32 && d->h >= d->block_rows && d->h <= 32 && d->n_img < (1 << 23))
+                   : (d->w % 16 == 0 && d->h % (8 * MS) == 0),
+               HC_E_SHAPE, "hc_tc_gemm: conv H,W must be multiples of the 16x8 tile (block mode: 8 <= W,H <= 32, n_img < 2^23)");
     HC_REQUIRE(d->c_in % tc::BK == 0 && d->c_total % 8 == 0 && d->c_base % 8 == 0 && d->c_base + d->c_in <= d->c_total, HC_E_SHAPE,
                "hc_tc_gemm: conv channel slice must be 64-aligned inside c_total");
     HC_REQUIRE(d->k == 9ll * d->c_in, HC_E_SHAPE, "hc_tc_gemm: conv needs K == 9*c_in");
@@ -617,7 +678,8 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     p.tiles_m = d->n_img * p.tiles_x * p.tiles_y;
     cuuint64_t dims[4] = {(cuuint64_t)d->c_total, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n_img};
     cuuint64_t str[3] = {(cuuint64_t)d->c_total * 2, (cuuint64_t)d->w * d->c_total * 2, (cuuint64_t)d->h * d->w * d->c_total * 2};
-    cuuint32_t box[4] = {(cuuint32_t)tc::BK, 16, (cuuint32_t)(8 * MS + 2), 1};   // one patch serves the three ky taps
+    // dense: one patch serves the three ky taps; block mode: one {64 ch, 8 x, block_rows y} box per block and tap
+    cuuint32_t box[4] = {(cuuint32_t)tc::BK, blk ? 8u : 16u, (cuuint32_t)(blk ? d->block_rows : 8 * MS + 2), 1};
     rc = tc::make_map(&ta, d->a, 4, dims, str, box);
     if (rc != HC_OK) return rc;
   } else {
@@ -631,7 +693,8 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     if (rc != HC_OK) return rc;
   }
   p.group_m = d->group_m > 0 ? d->group_m : 1;
-  if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
+  if (blk) p.group_m = 1;                 // the 4 N tiles of an M tile run side by side and share its blocks through L2
+  else if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
 
   if (BN == 256 && MS == 1) return tc::launch<256, 1>(ta, tb, p, stream);
   if (BN == 256 && MS == 2) return tc::launch<256, 2>(ta, tb, p, stream);

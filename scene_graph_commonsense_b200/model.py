@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, GEMM_CONV3, GEMM_PLAIN
+from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, GEMM_CONV3, GEMM_CONV3_BLOCKS, GEMM_PLAIN
 
 K1_PAD = 320      # 257 input channels of the 1x1 convolutions, zero padded to a multiple of 64
 HIDDEN = 512
@@ -93,15 +93,53 @@ class PackedHead:
         self.w_heads = torch.cat([f32(w) for w in heads]).contiguous()
         self.b_heads = torch.cat([f32(b) for b in biases]).contiguous()
         self.device = dev
+        self._p3_bg = None
 
     # ---------------------------------------------------------------------------- dense stages (model.py:138-150,175)
-    def conv3_fc(self, p2, m_sub=2, raw=None, n=None):
-        """conv3_1+ReLU+pool -> fc1+ReLU -> fc2 (raw, fp32) on pooled conv2 activations p2 [>=n,16,16,512] bf16."""
+    def conv2_halves(self, abox, m_sub=1):
+        """conv2_1 split into its subject / object input halves (linear before the ReLU, model.py:143): abox [n,32,32,256] bf16
+        (subject channels 0-127, object 128-255) -> U, V [n,32,32,512] bf16.  The conv2 bias rides on the object half (added in
+        fp32 before the one rounding to bf16), so the pair stage is relu(maxpool(U[s] + V[o])) on packed bf16."""
+        n_box, fs = abox.shape[0], abox.shape[1]
+        u = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device)
+        v = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device)
+        for out, w, base, bias in ((u, self.w2s, 0, None), (v, self.w2o, 128, self.b2)):
+            ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, bias=bias, ldc=512, mode=GEMM_CONV3, epilogue=EPI_BF16, act=ACT_NONE,
+                        n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=m_sub, tag="conv2_half")
+        return u, v
+
+    def p3_background(self):
+        """Pooled conv3_1 output [1,8,8,1024] bf16 of a pair whose two box masks are empty: tanh(conv1 bias) everywhere
+        (train_test.py:391,398 zero the map outside the box) pushed through the same kernels as real pairs, so a real pair's
+        output equals it bit for bit wherever the receptive field misses both boxes.  Weights-only: computed once."""
+        if self._p3_bg is None:
+            fs = 32
+            abox = self.fill.view(1, 1, 1, -1).expand(1, fs, fs, self.fill.numel()).contiguous()
+            u, v = self.conv2_halves(abox)
+            zero = torch.zeros(1, dtype=torch.int32, device=self.device)
+            p2 = ops.pair_relu_pool(u, v, None, zero, zero, fs)
+            p3 = torch.empty(1, 8, 8, 1024, dtype=torch.bfloat16, device=self.device)
+            ops.tc_gemm(p2, self.w3, p3, 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
+                        n_img=1, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=2, tag="conv3_bg")
+            self._p3_bg = p3
+        return self._p3_bg
+
+    def conv3_fc(self, p2, m_sub=2, raw=None, n=None, blocks=None, n_blocks=None, block_rows=0, p3=None):
+        """conv3_1+ReLU+pool -> fc1+ReLU -> fc2 (raw, fp32) on pooled conv2 activations p2 [>=n,16,16,512] bf16.
+        With a work list (`ops.conv3_active_blocks`) conv3_1 visits only the listed blocks of each pair; the rest of its output is
+        the background (`p3`, if given, is a buffer the caller has ALREADY pre-filled with it)."""
         n = p2.shape[0] if n is None else n
         dev = p2.device
-        p3 = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev)
-        ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
-                    n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag="conv3")
+        if blocks is None:
+            p3 = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev)
+            ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
+                        n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag="conv3")
+        else:
+            if p3 is None:
+                p3 = ops.broadcast_rows(self.p3_background(), n, torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev))
+            ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_BF16,
+                        n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag="conv3", blocks=blocks,
+                        n_blocks=n_blocks, block_rows=block_rows)
         h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=dev)
         ops.tc_gemm(p3, self.w_fc1, h1, n, 4096, 65536, bias=self.b_fc1, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU,
                     group_m=37, m_sub=2 if n > 128 else 1, tag="fc1")

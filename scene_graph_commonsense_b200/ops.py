@@ -13,7 +13,7 @@ from . import _abi_ops as _A
 from . import tables
 from ._abi_ops import LAUNCHES, PROFILE, cs_bitmap_build, pack_weight_bf16x3  # noqa: F401  (host-side helpers, no kernel)
 from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16, GEMM_CONV3,  # noqa: F401
-                   GEMM_PLAIN)
+                   GEMM_CONV3_BLOCKS, GEMM_PLAIN)
 
 NAMESPACE = "hiercom"
 _LIB = torch.library.Library(NAMESPACE, "DEF")
@@ -58,18 +58,47 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 # ------------------------------------------------------------------------------------------------ R5/R6 dense contractions
 @_op("tc_gemm", "(Tensor a, Tensor b, Tensor(a!) out, int m, int n, int k, Tensor? bias, Tensor? mul, int lda, int ldc, int c_off, "
      "int mode, int epilogue, int act, int n_img, int h, int w, int c_total, int c_base, int c_in, int group_m, int m_sub, "
-     "str tag) -> ()")
+     "str tag, Tensor? blocks, Tensor? n_blocks, int block_rows) -> ()")
 def _tc_gemm(a, b, out, m, n, k, bias, mul, lda, ldc, c_off, mode, epilogue, act, n_img, h, w, c_total, c_base, c_in, group_m, m_sub,
-             tag):
+             tag, blocks, n_blocks, block_rows):
     _A.tc_gemm(a, b, out, m, n, k, bias=bias, lda=lda, ldc=ldc, c_off=c_off, mode=mode, epilogue=epilogue, act=act, n_img=n_img, h=h,
-               w=w, c_total=c_total, c_base=c_base, c_in=c_in, group_m=group_m, m_sub=m_sub, tag=tag, mul=mul)
+               w=w, c_total=c_total, c_base=c_base, c_in=c_in, group_m=group_m, m_sub=m_sub, tag=tag, mul=mul, blocks=blocks,
+               n_blocks=n_blocks, block_rows=block_rows)
 
 
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16, act=ACT_NONE, n_img=0,
-            h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None):
+            h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None, blocks=None, n_blocks=None,
+            block_rows=0):
     """out = epilogue(A @ B^T) on tcgen05 (include/hiercom_b200.h hc_tc_gemm)."""
     _call("tc_gemm")(a, b, out, m, n, k, bias, mul, lda, n if ldc is None else ldc, c_off, mode, epilogue, act, n_img, h, w, c_total,
-                     c_base, c_in, group_m, m_sub, tag)
+                     c_base, c_in, group_m, m_sub, tag, blocks, n_blocks, block_rows)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ block-sparse conv3_1 support
+@_op("conv3_active_blocks", "(Tensor boxes, Tensor pair_sub, Tensor pair_obj, int block_rows, int fs, Tensor(a!) blocks, "
+     "Tensor(b!) n_blocks) -> ()")
+def _conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks):
+    _A.conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks=blocks, n_blocks=n_blocks)
+
+
+def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=None, n_blocks=None):
+    """Device work list (blocks, n_blocks) of the conv3_1 output blocks a set of directed pairs has to compute."""
+    if blocks is None:
+        blocks = torch.empty(max(pair_sub.numel() * (32 // block_rows), 1), dtype=torch.int32, device=boxes.device)
+    if n_blocks is None:
+        n_blocks = torch.empty(1, dtype=torch.int32, device=boxes.device)
+    _call("conv3_active_blocks")(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks)
+    return blocks, n_blocks
+
+
+@_op("broadcast_rows", "(Tensor src, int n_rows, Tensor(a!) out) -> ()")
+def _broadcast_rows(src, n_rows, out):
+    _A.broadcast_rows(src, n_rows, out)
+
+
+def broadcast_rows(src, n_rows, out):
+    _call("broadcast_rows")(src, n_rows, out)
     return out
 
 

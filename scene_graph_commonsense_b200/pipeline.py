@@ -139,7 +139,7 @@ class RelationPipeline:
 
     def __init__(self, packed: Optional[PackedHead], device, commonsense=True, aligned_keys=None, violated_keys=None,
                  top_k=tables.TOP_K, iou_thresh=0.5, feature_size=32, chunk_pairs=16384, predcls=True, conv3_m_sub=2,
-                 hier=None, splits=None, overlap=True, conv2_m_sub=1, chunk_policy="waves"):
+                 hier=None, splits=None, overlap=True, conv2_m_sub=1, chunk_policy="waves", conv3_block_rows=4):
         self.packed = packed
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -153,6 +153,12 @@ class RelationPipeline:
         self.conv3_m_sub = conv3_m_sub
         self.conv2_m_sub = conv2_m_sub      # short K (1152): 128-row tiles keep two TMEM stages, so the bf16 epilogue overlaps the next tile
         self.overlap = overlap
+        # 0: dense conv3_1.  8 / 4: block-sparse conv3_1 - only 8 x {8,4}-pixel blocks that meet the dilated footprint of the
+        # pair's two boxes are computed, the rest of the pooled output is a broadcast of the weights-only background
+        if conv3_block_rows not in (0, 4, 8):
+            raise ValueError("conv3_block_rows must be 0 (dense), 8 or 4")
+        self.conv3_block_rows = int(conv3_block_rows)
+        self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
         self.hier = (not packed.flat if packed is not None else True) if hier is None else bool(hier)
         self.pass_bitmap = None
@@ -180,14 +186,7 @@ class RelationPipeline:
         ops.tc_gemm(x, pk.w1, t, n_img * fs * fs, 256, K1_PAD, bias=pk.b1, lda=K1_PAD, ldc=256, epilogue=EPI_BF16, act=ACT_TANH,
                     group_m=8, tag="conv1")
         abox = ops.box_select(t, b.boxes, b.box_img, pk.fill, fs)
-        u = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=self.device)
-        v = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=self.device)
-        # the conv2 bias rides on the object half (added in fp32 before the one rounding to bf16), so the pair stage is
-        # relu(maxpool(U[s] + V[o])) on packed bf16
-        for out, w, base, bias in ((u, pk.w2s, 0, None), (v, pk.w2o, 128, pk.b2)):
-            ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, bias=bias, ldc=512, mode=GEMM_CONV3, epilogue=EPI_BF16, act=ACT_NONE,
-                        n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=self.conv2_m_sub, tag="conv2_half")
-        return u, v
+        return pk.conv2_halves(abox, m_sub=self.conv2_m_sub)
 
     @staticmethod
     def _greedy_chunks(offsets_host, cap):
@@ -248,12 +247,20 @@ class RelationPipeline:
         n = pairs["n"]
         u, v = self.box_features(b)
         raw = torch.empty(n, 512, dtype=torch.float32, device=self.device)
+        br = self.conv3_block_rows
         if "offsets_host" not in pairs:
-            for s in range(0, n, self.chunk_pairs):
+            starts = list(range(0, n, self.chunk_pairs))
+            nblk = torch.zeros(max(len(starts), 1), dtype=torch.int32, device=self.device) if br else None
+            for k, s in enumerate(starts):
                 e = min(n, s + self.chunk_pairs)
                 p2 = ops.pair_relu_pool(u, v, None, pairs["sub"][s:e], pairs["obj"][s:e], self.fs)
-                pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e])
+                if br:
+                    blocks, _ = ops.conv3_active_blocks(b.boxes, pairs["sub"][s:e], pairs["obj"][s:e], br, self.fs, n_blocks=nblk[k:k + 1])
+                    pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e], blocks=blocks, n_blocks=nblk[k:k + 1], block_rows=br)
+                else:
+                    pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e])
                 del p2
+            self.last_n_blocks = nblk
         else:
             n_box = b.boxes.shape[0]
             n_max = int(np.max(np.diff(b.box_offsets_host))) if b.box_offsets_host is not None else int(
@@ -263,6 +270,12 @@ class RelationPipeline:
             cap = max(c[3] for c in chunks)
             bufs = [torch.empty(cap, self.fs // 2, self.fs // 2, 512, dtype=torch.bfloat16, device=self.device)
                     for _ in range(2 if self.overlap and len(chunks) > 1 else 1)]
+            if br:      # per buffer: the work list and the background-filled pooled conv3_1 output
+                blk_bufs = [torch.empty(cap * (32 // br), dtype=torch.int32, device=self.device) for _ in bufs]
+                p3_bufs = [torch.empty(cap, 8, 8, 1024, dtype=torch.bfloat16, device=self.device) for _ in bufs]
+                nblk = torch.zeros(len(chunks), dtype=torch.int32, device=self.device)
+                p3_bg = pk.p3_background()
+                self.last_n_blocks = nblk
             main = torch.cuda.current_stream()
             side = self._side_stream() if len(bufs) == 2 else main
             ready = torch.cuda.Event()
@@ -276,11 +289,19 @@ class RelationPipeline:
                         if k >= 2:
                             side.wait_event(gemm_done[k - 2])          # buffer free again
                     ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, self.fs, out=buf)
+                    if br:
+                        ops.conv3_active_blocks(b.boxes, pairs["sub"][base:base + cnt], pairs["obj"][base:base + cnt], br, self.fs,
+                                                blocks=blk_bufs[k % len(bufs)], n_blocks=nblk[k:k + 1])
+                        ops.broadcast_rows(p3_bg, cnt, p3_bufs[k % len(bufs)])
                     pooled = torch.cuda.Event()
                     pooled.record(side)
                 if side is not main:
                     main.wait_event(pooled)
-                pk.conv3_fc(buf, m_sub=self.conv3_m_sub, raw=raw[base:base + cnt], n=cnt)
+                if br:
+                    pk.conv3_fc(buf, m_sub=self.conv3_m_sub, raw=raw[base:base + cnt], n=cnt, blocks=blk_bufs[k % len(bufs)],
+                                n_blocks=nblk[k:k + 1], block_rows=br, p3=p3_bufs[k % len(bufs)])
+                else:
+                    pk.conv3_fc(buf, m_sub=self.conv3_m_sub, raw=raw[base:base + cnt], n=cnt)
                 ev = torch.cuda.Event()
                 ev.record(main)
                 gemm_done.append(ev)

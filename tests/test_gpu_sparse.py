@@ -1,0 +1,144 @@
+"""GPU tests of the block-sparse conv3_1 (HC_GEMM_CONV3_BLOCKS): the work list covers the dilated footprint of each pair's
+two boxes, and the sparse path (background broadcast + listed blocks) reproduces the dense path BIT FOR BIT - the reference
+(model.py:138-150 on `feature*mask`, train_test.py:391,398) is dense, so equality with the dense kernels is the parity bar."""
+import numpy as np
+import pytest
+import torch
+
+from scene_graph_commonsense_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+# (xmin, xmax, ymin, ymax) on the 32-grid: corners, borders, 1-pixel, empty, inverted, whole map, negative (Python slice wrap)
+EDGE_BOXES = [(0, 32, 0, 32), (0, 1, 0, 1), (31, 32, 31, 32), (0, 4, 28, 32), (5, 5, 3, 9), (9, 3, 2, 7), (14, 18, 14, 18),
+              (0, 32, 15, 17), (15, 17, 0, 32), (-4, 32, 3, 12), (1, 3, 1, 3), (2, 30, 2, 30), (7, 9, 20, 31), (30, 32, 0, 2)]
+
+
+def _cells_1d(lo, hi):
+    """include/hiercom_b200.h hc_conv3_active_blocks: box interval [lo,hi) -> 8-grid cells that can differ from the background."""
+    if hi <= lo:
+        return 0, 0
+    qlo, qhi = max(0, (lo - 1) // 2), min(15, hi // 2)
+    qlo, qhi = max(0, qlo - 1), min(15, qhi + 1)
+    return qlo // 2, qhi // 2 + 1
+
+
+def _slice_bound(v, size=32):
+    if v < 0:
+        v = max(v + size, 0)
+    return min(v, size)
+
+
+def _cell_mask(box):
+    x0, x1, y0, y1 = (_slice_bound(int(v)) for v in box)
+    x1, y1 = max(x1, x0), max(y1, y0)
+    m = np.zeros((8, 8), bool)
+    xa, xb = _cells_1d(x0, x1)
+    ya, yb = _cells_1d(y0, y1)
+    if xb > xa and yb > ya:
+        m[ya:yb, xa:xb] = True
+    return m
+
+
+def _random_boxes(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    b = synthetic.make_boxes(g, n).to(torch.int32)
+    k = min(len(EDGE_BOXES), n)
+    b[:k] = torch.tensor(EDGE_BOXES[:k], dtype=torch.int32)
+    return b
+
+
+@pytest.mark.parametrize("block_rows", [8, 4])
+def test_work_list_covers_active_cells(block_rows):
+    from scene_graph_commonsense_b200 import ops
+    boxes = _random_boxes(40, 5)
+    n_box = boxes.shape[0]
+    sub, obj = np.nonzero(~np.eye(n_box, dtype=bool))
+    blocks, n_blocks = ops.conv3_active_blocks(boxes.to(DEV), torch.from_numpy(sub.astype(np.int32)).to(DEV),
+                                               torch.from_numpy(obj.astype(np.int32)).to(DEV), block_rows)
+    nb = int(n_blocks.item())
+    e = blocks[:nb].cpu().numpy()
+    pair, cy, cx = e >> 8, (e >> 4) & 15, e & 15
+    hc = block_rows // 2
+    assert (np.diff(pair) >= 0).all() and pair.max() < len(sub)                  # pairs in order
+    assert (cx <= 4).all() and (cy <= 8 - hc).all()                              # blocks stay inside the 16 x 16 map
+    counts = np.bincount(pair, minlength=len(sub))
+    assert counts.max() <= 32 // block_rows                                      # never more than the dense tiling
+    cover = np.zeros((len(sub), 8, 8), bool)
+    for p, y, x in zip(pair, cy, cx):
+        cover[p, y:y + hc, x:x + 4] = True
+    masks = np.stack([_cell_mask(b) for b in boxes.numpy()])
+    want = masks[sub] | masks[obj]
+    assert not (want & ~cover).any()
+    assert (counts[~want.reshape(len(sub), -1).any(1)] == 0).all()               # two empty boxes: nothing to compute
+    # an empty pair list is a no-op with n_blocks == 0
+    z = torch.zeros(0, dtype=torch.int32, device=DEV)
+    _, n0 = ops.conv3_active_blocks(boxes.to(DEV), z, z, block_rows)
+    assert int(n0.item()) == 0
+
+
+def _packed(seed=0, gain=1.0):
+    from scene_graph_commonsense_b200 import model
+    return model.PackedHead(synthetic.head_state_dict(seed=seed, logit_gain=gain), DEV)
+
+
+@pytest.mark.parametrize("block_rows,m_sub", [(8, 2), (4, 2), (8, 1), (4, 1)])
+def test_sparse_conv3_equals_dense_bit_for_bit(block_rows, m_sub):
+    """conv3_1 + ReLU + pool on the listed blocks over a background pre-fill == the dense kernel, every bf16 bit."""
+    from scene_graph_commonsense_b200 import ops
+    from scene_graph_commonsense_b200._lib import EPI_POOL_BF16, GEMM_CONV3, GEMM_CONV3_BLOCKS
+    pk = _packed()
+    boxes = _random_boxes(20, 11).to(DEV)
+    n_box = boxes.shape[0]
+    g = torch.Generator().manual_seed(3)
+    t_img = torch.tanh(torch.randn(1, 32 * 32, 256, generator=g)).to(torch.bfloat16).to(DEV)
+    abox = ops.box_select(t_img, boxes, torch.zeros(n_box, dtype=torch.int32, device=DEV), pk.fill, 32)
+    u, v = pk.conv2_halves(abox)
+    sub, obj = np.nonzero(~np.eye(n_box, dtype=bool))
+    keep = np.random.default_rng(0).permutation(len(sub))[:150]
+    keep[:14] = np.arange(14)                                                   # (0,1) .. : the whole-map box against every edge box
+    sub_t = torch.from_numpy(sub[keep].astype(np.int32)).to(DEV)
+    obj_t = torch.from_numpy(obj[keep].astype(np.int32)).to(DEV)
+    n = sub_t.numel()
+    p2 = ops.pair_relu_pool(u, v, None, sub_t, obj_t, 32)
+    dense = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=DEV)
+    ops.tc_gemm(p2, pk.w3, dense, n * 256, 1024, 9 * 512, bias=pk.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16, n_img=n, h=16,
+                w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=2)
+    blocks, n_blocks = ops.conv3_active_blocks(boxes, sub_t, obj_t, block_rows)
+    sparse = ops.broadcast_rows(pk.p3_background(), n, torch.empty_like(dense))
+    assert torch.equal(sparse[n - 1], pk.p3_background()[0])
+    ops.tc_gemm(p2, pk.w3, sparse, n * 256, 1024, 9 * 512, bias=pk.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_BF16, n_img=n,
+                h=16, w=16, c_total=512, c_base=0, c_in=512, m_sub=m_sub, blocks=blocks, n_blocks=n_blocks, block_rows=block_rows)
+    torch.cuda.synchronize()
+    nb = int(n_blocks.item())
+    assert 0 < nb < n * (32 // block_rows)                                       # the list is really sparse on these boxes
+    bad = (dense.view(torch.int16) != sparse.view(torch.int16)).flatten(1).any(1).nonzero().flatten().tolist()
+    assert not bad, "pairs %s differ (boxes %s)" % (bad[:5], [(int(sub[keep][i]), int(obj[keep][i])) for i in bad[:5]])
+    # the background really is what a box-free pair produces, and it is not trivially zero
+    assert float(pk.p3_background().float().abs().max()) > 0
+
+
+@pytest.mark.parametrize("block_rows", [8, 4])
+def test_pipeline_sparse_equals_dense(block_rows):
+    """Whole forward (chunked + overlapped, and the generic pair-list path): identical raw head outputs and counters."""
+    from scene_graph_commonsense_b200 import pipeline
+    pk = _packed(gain=40.0)
+    samples = synthetic.make_batch([70, 71, 72, 73, 74], [9, 1, 12, 7, 10], p_rel=0.5)
+    samples[0].bbox[:6] = torch.tensor(EDGE_BOXES[:6], dtype=samples[0].bbox.dtype)
+    outs = []
+    for br in (0, block_rows):
+        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=120, conv3_block_rows=br)
+        b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
+        pairs = pipe.enumerate_pairs(b)
+        rel, sup, conn, logsig = pipe.forward_pairs(b, pairs)
+        pipe.evaluate(b, pairs, rel, sup, logsig, connectivity=conn)
+        generic = {k: val for k, val in pairs.items() if k != "offsets_host"}
+        rel_g = pipe.forward_pairs(b, generic)[0]
+        torch.cuda.synchronize()
+        outs.append((rel.clone(), sup.clone(), conn.clone(), pipe.counters.clone(), rel_g.clone()))
+        if br:
+            assert pipe.last_n_blocks is not None and int(pipe.last_n_blocks.sum()) > 0
+    for a, c in zip(outs[0], outs[1]):
+        assert torch.equal(a, c)
+    assert torch.equal(outs[0][0], outs[0][4])
