@@ -30,6 +30,7 @@ BOXES = 40
 FLOP_IMG = 134_742_016            # conv1_1 + conv1_2 once per image
 FLOP_BOX = 2_415_919_104          # subject-half + object-half of conv2_1 once per box
 FLOP_PAIR_CONV3 = 2_415_919_104
+FLOP_PAIR_FC1 = 536_870_912          # 2 * 65536 * 4096
 FLOP_PAIR = 2_957_039_616         # conv3_1 + fc1 + fc2(dense) + heads per directed pair
 
 
@@ -89,7 +90,9 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-CONV3_MODES = {"dense": 0, "blocks8": 8, "blocks4": 4}      # --conv3: dense kernel, or block-sparse with 8x8 / 8x4-pixel blocks
+# --conv3: dense kernel; block-sparse over the cells EITHER box of a pair reaches (8x8 / 8x4-pixel blocks); or "shared": per pair
+# only the cells BOTH boxes reach, the rest taken from per-box maps computed once per box (block_rows, shared)
+CONV3_MODES = {"dense": (0, False), "blocks8": (8, False), "blocks4": (4, False), "shared8": (8, True), "shared4": (4, True)}
 
 WORKLOADS = {
     # name: images per GPU, boxes (proposals) per image, SGDET-style?, pair chunk
@@ -178,7 +181,7 @@ def run_ours(args):
     chunk_pairs = args.chunk_pairs or wl["chunk_pairs"]
     pipe = pipeline.RelationPipeline(packed, dev, commonsense=True, chunk_pairs=chunk_pairs, conv3_m_sub=args.conv3_m_sub,
                                      overlap=not args.no_overlap, predcls=not wl["sgdet"], chunk_policy=args.chunk_policy,
-                                     conv3_block_rows=CONV3_MODES[args.conv3])
+                                     conv3_block_rows=CONV3_MODES[args.conv3][0], conv3_shared=CONV3_MODES[args.conv3][1])
     samples = make_samples(rank, wl["images"], wl["boxes"], sgdet=wl["sgdet"])
     host = pipeline.host_batch_from_samples(samples, skip_mode="batch", sgdet=wl["sgdet"])
     del samples
@@ -253,30 +256,44 @@ def run_ours(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (conv3_1 implicit GEMM), live CUDA-event timing inside the timed region
+    # ---- roofline of the dominant kernel (the tensor-core GEMM with the most time in the step: conv3_1 or fc1), live
+    # CUDA-event timing inside the timed region
     conv3 = per_tag.get("conv3", [])
-    n_chunks = max(len(conv3) // max(args.steps, 1), 1)
-    pairs_per_launch = pairs_step / n_chunks
-    roof = None
+    fc1 = per_tag.get("fc1", [])
     conv3_exec_frac = 1.0           # executed / dense-equivalent FLOPs of conv3_1 (block-sparse mode visits only listed blocks)
     if blocks_step is not None:
         conv3_exec_frac = blocks_step * 8 * pipe.conv3_block_rows / (pairs_step * 256.0)
-    if conv3:
-        avg_ms = float(np.mean(conv3))
-        achieved = conv3_exec_frac * pairs_per_launch * FLOP_PAIR_CONV3 / (avg_ms * 1e-3) / 1e12
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "conv3_dram_bytes.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+
+    def roof_of(name, times, flop_step_kernel, extra):
+        if not times:
+            return None
+        total_ms = float(np.sum(times))
+        achieved = flop_step_kernel * args.steps / (total_ms * 1e-3) / 1e12
+        r = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+             "frac": achieved / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
+             "avg_launch_ms": total_ms / len(times), "launches_timed": len(times), "ms_per_step": total_ms / args.steps,
+             "algorithmic_flop_per_launch": flop_step_kernel * args.steps / len(times)}
+        r.update(extra)
+        return r
+
+    conv3_times = conv3 + per_tag.get("conv3_box", [])
+    roof_conv3 = roof_of("tc_gemm_kernel<256,%d> conv3_1 implicit GEMM + bias/ReLU/maxpool epilogue (%s)" % (args.conv3_m_sub, args.conv3),
+                         conv3_times, conv3_exec_frac * pairs_step * FLOP_PAIR_CONV3,
+                         {"note": "achieved counts EXECUTED FLOPs (listed blocks only, per-pair and per-box launches); "
+                                  "dense-equivalent = achieved / executed_fraction",
+                          "executed_fraction": conv3_exec_frac} if blocks_step is not None else {})
+    if roof_conv3 is not None:
         if blocks_step is not None:
-            traffic = None          # the committed ncu DRAM figure is the dense kernel's
-        roof = {"kernel": "tc_gemm_kernel<256,%d> conv3_1 implicit GEMM + bias/ReLU/maxpool epilogue (%s)" % (args.conv3_m_sub, args.conv3),
-                "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / pk["bf16_sustained"], "traffic": traffic, "peak_source": pk["source"] + " sustained bf16",
-                "avg_launch_ms": avg_ms, "launches_timed": len(conv3),
-                "algorithmic_flop_per_launch": conv3_exec_frac * pairs_per_launch * FLOP_PAIR_CONV3,
-                "note": "achieved counts EXECUTED FLOPs (listed blocks only); dense-equivalent = achieved / executed_fraction",
-                "executed_fraction": conv3_exec_frac, "dense_equivalent_tflops": achieved / conv3_exec_frac}
+            roof_conv3["dense_equivalent_tflops"] = roof_conv3["achieved"] / conv3_exec_frac
+        else:
+            tp = os.path.join(ROOT, "profiles", "conv3_dram_bytes.json")    # the committed ncu DRAM figure is the dense kernel's
+            if os.path.exists(tp):
+                roof_conv3["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
+    roof_fc1 = roof_of("tc_gemm_kernel<256,2> fc1 [pairs,65536] x [65536,4096] + bias/ReLU epilogue", fc1, pairs_step * FLOP_PAIR_FC1, {})
+    roofs = [r for r in (roof_conv3, roof_fc1) if r is not None]
+    roofs.sort(key=lambda r: -r["ms_per_step"])
+    roof = roofs[0] if roofs else None
+    roof_second = roofs[1] if len(roofs) > 1 else None
     breakdown = {t: {"launches": len(v), "ms_per_step": float(np.sum(v)) / args.steps} for t, v in sorted(per_tag.items())}
     flop_dense = wl["images"] * FLOP_IMG + wl["images"] * wl["boxes"] * FLOP_BOX + pairs_step * FLOP_PAIR
     flop_step = flop_dense - (1.0 - conv3_exec_frac) * pairs_step * FLOP_PAIR_CONV3      # FLOPs actually executed
@@ -301,7 +318,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": (tables.COUNTER_SIZE * 8 + 4) * world, "ms_per_step": t_e2e / args.steps * 1e3,
                 "api": "RelationPipeline.run over pinned HostBatch windows (H2D of window k+1 issued under window k's kernels; "
                        "counters read back after every window)"},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_second": roof_second,
         "step_tensor_frac": flop_step / (t_max / args.steps) / 1e12 / pk["bf16_sustained"],
         "algorithmic_tflop_per_step": flop_dense / 1e12, "executed_tflop_per_step": flop_step / 1e12,
         "conv3_blocks_per_step": blocks_step, "kernel_breakdown": breakdown,
@@ -333,7 +350,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="cfg2 = the configuration BASELINE.json's metric is quoted on (default); cfg3 = SGDET-shaped scaling case")
     ap.add_argument("--conv3-m-sub", type=int, default=2)
-    ap.add_argument("--conv3", default="blocks4", choices=sorted(CONV3_MODES),
+    ap.add_argument("--conv3", default="shared4", choices=sorted(CONV3_MODES),
                     help="conv3_1 kernel: dense, or block-sparse over the dilated footprint of each pair's boxes (bit-identical output)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")

@@ -138,6 +138,22 @@ int hc_tc_gemm(const hc_gemm_desc* desc, hc_stream_t stream);
 int hc_conv3_active_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
                            int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream);
 
+/* Shared-footprint variant (the default): a pooled conv3_1 cell that only the SUBJECT's box reaches equals the same cell of the
+ * pair (subject, empty box), one only the OBJECT's box reaches equals (empty box, object) - both are per-BOX maps, computed once
+ * per box of the window instead of once per pair (model.py:143-146 see the object only through its masked features,
+ * train_test.py:391,398).  Only the cells BOTH boxes reach depend on the pair: hc_conv3_shared_blocks lists the cover of that
+ * intersection (same cover, same entry format and capacity as hc_conv3_active_blocks). */
+int hc_conv3_shared_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
+                           int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream);
+
+/* out[p] ([8,8,1024] bf16 per pair) = per cell: sub_maps[pair_sub[p]] where only the subject's box reaches the cell,
+ * obj_maps[pair_obj[p]] where only the object's box does, `background` where neither does; cells both reach are NOT written
+ * (HC_GEMM_CONV3_BLOCKS over hc_conv3_shared_blocks' list writes them afterwards on the same stream).  sub_maps / obj_maps:
+ * [n_box,8,8,1024] bf16 = pooled conv3_1 output of (box, empty) / (empty, box); background: [8,8,1024] bf16. */
+int hc_p3_assemble(const void* background, const void* sub_maps, const void* obj_maps, const int32_t* boxes,
+                   const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs, int32_t feature_size, void* out,
+                   hc_stream_t stream);
+
 /* out[i, :] = src[:] for i < n_rows (row_bytes a multiple of 16; both 16-byte aligned): pre-fills the pooled conv3_1 output of
  * every pair with the background before HC_GEMM_CONV3_BLOCKS overwrites the active blocks. */
 int hc_broadcast_rows(const void* src, int64_t row_bytes, int64_t n_rows, void* out, hc_stream_t stream);

@@ -97,8 +97,9 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     return out
 
 
-def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=None, n_blocks=None):
-    """Work list of the block-sparse conv3_1 for the given directed pairs (include/hiercom_b200.h hc_conv3_active_blocks).
+def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=None, n_blocks=None, shared=False):
+    """Work list of the block-sparse conv3_1 for the given directed pairs (include/hiercom_b200.h hc_conv3_active_blocks;
+    shared=True: hc_conv3_shared_blocks, only the cells both boxes reach).
     Returns (blocks int32 [n_pairs * 32 / block_rows], n_blocks int32 [1]); both stay on the device."""
     require_cuda(boxes, pair_sub, pair_obj, blocks, n_blocks)
     n = pair_sub.numel()
@@ -109,10 +110,27 @@ def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=N
         n_blocks = torch.empty(1, dtype=torch.int32, device=boxes.device)
     if blocks.numel() < cap:
         raise RuntimeError("hiercom_b200: conv3_active_blocks needs room for %d work-list entries" % cap)
-    check(_lib.load().hc_conv3_active_blocks(ptr(boxes), ptr(pair_sub), ptr(pair_obj), n, fs, block_rows, ptr(blocks), ptr(n_blocks),
-                                             stream_ptr()), "hc_conv3_active_blocks")
+    name = "hc_conv3_shared_blocks" if shared else "hc_conv3_active_blocks"
+    check(getattr(_lib.load(), name)(ptr(boxes), ptr(pair_sub), ptr(pair_obj), n, fs, block_rows, ptr(blocks), ptr(n_blocks), stream_ptr()),
+          name)
     _count()
     return blocks, n_blocks
+
+
+def p3_assemble(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, fs=32):
+    """Pooled conv3_1 output of every pair outside the cells both boxes reach (include/hiercom_b200.h hc_p3_assemble)."""
+    require_cuda(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out)
+    n = pair_sub.numel()
+    cell_map = 8 * 8 * 1024
+    if (background.numel() != cell_map or sub_maps.numel() % cell_map or obj_maps.numel() != sub_maps.numel() or out.numel() < n * cell_map
+            or any(t.dtype != torch.bfloat16 or not t.is_contiguous() for t in (background, sub_maps, obj_maps, out))
+            or sub_maps.numel() // cell_map < boxes.shape[0]):
+        raise RuntimeError("hiercom_b200: p3_assemble needs contiguous bf16 [*,8,8,1024] maps (one per box) and room for n_pairs rows")
+    with _timed("p3_fill"):
+        check(_lib.load().hc_p3_assemble(ptr(background), ptr(sub_maps), ptr(obj_maps), ptr(boxes), ptr(pair_sub), ptr(pair_obj), n, fs,
+                                         ptr(out), stream_ptr()), "hc_p3_assemble")
+    _count()
+    return out
 
 
 def broadcast_rows(src, n_rows, out):

@@ -39,6 +39,8 @@ SIGNATURES = {
     "hc_pairs_enumerate": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hc_tc_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
     "hc_conv3_active_blocks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "hc_conv3_shared_blocks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "hc_p3_assemble": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P]),
     "hc_broadcast_rows": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "hc_pack_pixels": (C.c_int, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "hc_box_select": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),

@@ -55,16 +55,18 @@ __device__ __forceinline__ int cover(unsigned long long m, int hc, F emit) {
 
 __global__ void __launch_bounds__(1024)
 conv3_blocks_kernel(const int4* __restrict__ boxes, const int* __restrict__ pair_sub, const int* __restrict__ pair_obj, int n_pairs, int fs,
-                    int hc, int* __restrict__ blocks, int* __restrict__ n_blocks) {
+                    int hc, bool both, int* __restrict__ blocks, int* __restrict__ n_blocks) {
   __shared__ int s_scan[1024];
   const int t = threadIdx.x;
   const int per = (n_pairs + 1023) / 1024;
   const int p0 = min(n_pairs, t * per), p1 = min(n_pairs, p0 + per);
   int cnt = 0;
-  for (int p = p0; p < p1; ++p) {
-    const unsigned long long m = cell_mask(rect_of(__ldg(boxes + pair_sub[p]), fs)) | cell_mask(rect_of(__ldg(boxes + pair_obj[p]), fs));
-    cnt += cover(m, hc, [](int) {});
-  }
+  // both: only the cells BOTH boxes can reach (everything else comes from per-box maps, see p3_assemble_kernel)
+  auto pair_mask = [&](int p) {
+    const unsigned long long ms = cell_mask(rect_of(__ldg(boxes + pair_sub[p]), fs)), mo = cell_mask(rect_of(__ldg(boxes + pair_obj[p]), fs));
+    return both ? (ms & mo) : (ms | mo);
+  };
+  for (int p = p0; p < p1; ++p) cnt += cover(pair_mask(p), hc, [](int) {});
   s_scan[t] = cnt;
   __syncthreads();
   for (int d = 1; d < 1024; d <<= 1) {                          // inclusive Hillis-Steele scan over the 1024 per-thread counts
@@ -75,9 +77,31 @@ conv3_blocks_kernel(const int4* __restrict__ boxes, const int* __restrict__ pair
   }
   int o = s_scan[t] - cnt;
   if (t == 1023) n_blocks[0] = s_scan[t];
-  for (int p = p0; p < p1; ++p) {
-    const unsigned long long m = cell_mask(rect_of(__ldg(boxes + pair_sub[p]), fs)) | cell_mask(rect_of(__ldg(boxes + pair_obj[p]), fs));
-    cover(m, hc, [&](int e) { blocks[o++] = (p << 8) | e; });
+  for (int p = p0; p < p1; ++p) cover(pair_mask(p), hc, [&](int e) { blocks[o++] = (p << 8) | e; });
+}
+
+// Pooled conv3_1 output of a pair outside the cells both boxes reach: a cell only the subject's box reaches equals the map of
+// the pair (subject, EMPTY box), one only the object's box reaches equals (EMPTY box, object), the rest is the background.
+// One CTA per pair; a cell is 1024 channels = 128 uint4, so 256 threads move two cells per iteration.  Cells both boxes
+// reach are left alone: the work list of hc_conv3_shared_blocks covers them and HC_GEMM_CONV3_BLOCKS writes them afterwards.
+__global__ void __launch_bounds__(256)
+p3_assemble_kernel(const uint4* __restrict__ bg, const uint4* __restrict__ sub_maps, const uint4* __restrict__ obj_maps,
+                   const int4* __restrict__ boxes, const int* __restrict__ pair_sub, const int* __restrict__ pair_obj, int n_pairs, int fs,
+                   uint4* __restrict__ out) {
+  const int lane128 = threadIdx.x & 127, half = threadIdx.x >> 7;
+  for (int p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+    const int s = pair_sub[p], o = pair_obj[p];
+    const unsigned long long ms = cell_mask(rect_of(__ldg(boxes + s), fs)), mo = cell_mask(rect_of(__ldg(boxes + o), fs));
+    const uint4* ps = sub_maps + (long long)s * 8192;
+    const uint4* po = obj_maps + (long long)o * 8192;
+    uint4* dst = out + (long long)p * 8192;
+#pragma unroll 4
+    for (int c = half; c < 64; c += 2) {
+      const bool in_s = (ms >> c) & 1ull, in_o = (mo >> c) & 1ull;
+      if (in_s && in_o) continue;
+      const uint4* src = in_s ? ps : (in_o ? po : bg);
+      __stcs(dst + c * 128 + lane128, __ldg(src + c * 128 + lane128));
+    }
   }
 }
 
@@ -93,8 +117,8 @@ __global__ void broadcast_rows_kernel(const uint4* __restrict__ src, long long r
 
 using namespace hc;
 
-extern "C" int hc_conv3_active_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
-                                      int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream_) {
+static int conv3_blocks_list(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs, int32_t feature_size,
+                             int32_t block_rows, bool both, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(n_blocks && (n_pairs <= 0 || (boxes && pair_sub && pair_obj && blocks)), HC_E_NULL, "hc_conv3_active_blocks: NULL operand");
   int rc = hc_device_check();
@@ -104,8 +128,37 @@ extern "C" int hc_conv3_active_blocks(const int32_t* boxes, const int32_t* pair_
   HC_REQUIRE(n_pairs >= 0 && n_pairs < (1 << 23), HC_E_SHAPE, "hc_conv3_active_blocks: n_pairs must be below 2^23");
   HC_REQUIRE(aligned16(boxes), HC_E_ALIGN, "hc_conv3_active_blocks: boxes must be 16-byte aligned");   // n_pairs == 0 still writes n_blocks = 0
   conv3_blocks_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const int4*>(boxes), pair_sub, pair_obj, n_pairs, feature_size, block_rows / 2,
-                                              blocks, n_blocks);
+                                              both, blocks, n_blocks);
   return cuda_status("conv3_blocks_kernel launch");
+}
+
+extern "C" int hc_conv3_active_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
+                                      int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream_) {
+  return conv3_blocks_list(boxes, pair_sub, pair_obj, n_pairs, feature_size, block_rows, false, blocks, n_blocks, stream_);
+}
+
+extern "C" int hc_conv3_shared_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
+                                      int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream_) {
+  return conv3_blocks_list(boxes, pair_sub, pair_obj, n_pairs, feature_size, block_rows, true, blocks, n_blocks, stream_);
+}
+
+extern "C" int hc_p3_assemble(const void* background, const void* sub_maps, const void* obj_maps, const int32_t* boxes,
+                              const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs, int32_t feature_size, void* out,
+                              hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(n_pairs <= 0 || (background && sub_maps && obj_maps && boxes && pair_sub && pair_obj && out), HC_E_NULL,
+             "hc_p3_assemble: NULL operand");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  HC_REQUIRE(feature_size == 32, HC_E_SHAPE, "hc_p3_assemble: built for feature_size 32 (8x8 pooled conv3 cells of 1024 channels)");
+  HC_REQUIRE(aligned16(background) && aligned16(sub_maps) && aligned16(obj_maps) && aligned16(boxes) && aligned16(out), HC_E_ALIGN,
+             "hc_p3_assemble: operands must be 16-byte aligned");
+  if (n_pairs <= 0) return HC_OK;
+  const int grid = n_pairs < num_sms() * 8 ? n_pairs : num_sms() * 8;
+  p3_assemble_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(background), reinterpret_cast<const uint4*>(sub_maps),
+                                               reinterpret_cast<const uint4*>(obj_maps), reinterpret_cast<const int4*>(boxes), pair_sub,
+                                               pair_obj, n_pairs, feature_size, reinterpret_cast<uint4*>(out));
+  return cuda_status("p3_assemble_kernel launch");
 }
 
 extern "C" int hc_broadcast_rows(const void* src, int64_t row_bytes, int64_t n_rows, void* out, hc_stream_t stream_) {

@@ -124,6 +124,13 @@ class PackedHead:
             self._p3_bg = p3
         return self._p3_bg
 
+    def conv3_blocks(self, p2, p3, n, blocks, n_blocks, block_rows, m_sub=2, tag="conv3"):
+        """conv3_1+ReLU+pool on the listed blocks of p2 [>=n,16,16,512] into the PRE-FILLED p3 [>=n,8,8,1024]."""
+        ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_BF16,
+                    n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag=tag, blocks=blocks,
+                    n_blocks=n_blocks, block_rows=block_rows)
+        return p3
+
     def conv3_fc(self, p2, m_sub=2, raw=None, n=None, blocks=None, n_blocks=None, block_rows=0, p3=None):
         """conv3_1+ReLU+pool -> fc1+ReLU -> fc2 (raw, fp32) on pooled conv2 activations p2 [>=n,16,16,512] bf16.
         With a work list (`ops.conv3_active_blocks`) conv3_1 visits only the listed blocks of each pair; the rest of its output is
@@ -137,9 +144,7 @@ class PackedHead:
         else:
             if p3 is None:
                 p3 = ops.broadcast_rows(self.p3_background(), n, torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev))
-            ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_BF16,
-                        n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag="conv3", blocks=blocks,
-                        n_blocks=n_blocks, block_rows=block_rows)
+            self.conv3_blocks(p2, p3, n, blocks, n_blocks, block_rows, m_sub=m_sub)
         h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=dev)
         ops.tc_gemm(p3, self.w_fc1, h1, n, 4096, 65536, bias=self.b_fc1, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU,
                     group_m=37, m_sub=2 if n > 128 else 1, tag="fc1")

@@ -92,6 +92,33 @@ def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=N
     return blocks, n_blocks
 
 
+@_op("conv3_shared_blocks", "(Tensor boxes, Tensor pair_sub, Tensor pair_obj, int block_rows, int fs, Tensor(a!) blocks, "
+     "Tensor(b!) n_blocks) -> ()")
+def _conv3_shared_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks):
+    _A.conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks=blocks, n_blocks=n_blocks, shared=True)
+
+
+def conv3_shared_blocks(boxes, pair_sub, pair_obj, block_rows=4, fs=32, blocks=None, n_blocks=None):
+    """Device work list of the conv3_1 output blocks that depend on BOTH boxes of a pair (the rest comes from `p3_assemble`)."""
+    if blocks is None:
+        blocks = torch.empty(max(pair_sub.numel() * (32 // block_rows), 1), dtype=torch.int32, device=boxes.device)
+    if n_blocks is None:
+        n_blocks = torch.empty(1, dtype=torch.int32, device=boxes.device)
+    _call("conv3_shared_blocks")(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks)
+    return blocks, n_blocks
+
+
+@_op("p3_assemble", "(Tensor background, Tensor sub_maps, Tensor obj_maps, Tensor boxes, Tensor pair_sub, Tensor pair_obj, "
+     "Tensor(a!) out, int fs) -> ()")
+def _p3_assemble(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, fs):
+    _A.p3_assemble(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, fs)
+
+
+def p3_assemble(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, fs=32):
+    _call("p3_assemble")(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, fs)
+    return out
+
+
 @_op("broadcast_rows", "(Tensor src, int n_rows, Tensor(a!) out) -> ()")
 def _broadcast_rows(src, n_rows, out):
     _A.broadcast_rows(src, n_rows, out)

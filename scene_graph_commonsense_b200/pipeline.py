@@ -139,7 +139,7 @@ class RelationPipeline:
 
     def __init__(self, packed: Optional[PackedHead], device, commonsense=True, aligned_keys=None, violated_keys=None,
                  top_k=tables.TOP_K, iou_thresh=0.5, feature_size=32, chunk_pairs=16384, predcls=True, conv3_m_sub=2,
-                 hier=None, splits=None, overlap=True, conv2_m_sub=1, chunk_policy="waves", conv3_block_rows=4):
+                 hier=None, splits=None, overlap=True, conv2_m_sub=1, chunk_policy="waves", conv3_block_rows=4, conv3_shared=True):
         self.packed = packed
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -158,6 +158,10 @@ class RelationPipeline:
         if conv3_block_rows not in (0, 4, 8):
             raise ValueError("conv3_block_rows must be 0 (dense), 8 or 4")
         self.conv3_block_rows = int(conv3_block_rows)
+        # block-sparse only.  True: a cell of the pooled conv3_1 output that only ONE box of the pair reaches is taken from that
+        # box's own map ((box, empty) / (empty, box), computed once per box of the window), so a pair computes only the cells
+        # BOTH boxes reach.  False: every cell either box reaches is computed per pair.  Same bits either way.
+        self.conv3_shared = bool(conv3_shared) and self.conv3_block_rows > 0
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
         self.hier = (not packed.flat if packed is not None else True) if hier is None else bool(hier)
@@ -177,16 +181,40 @@ class RelationPipeline:
         return ops.pairs_enumerate(b.boxes, b.box_offsets, b.tri_offsets, b.p_max, b.rel_tri, b.dir_tri, b.group_id, b.n_groups,
                                    b.max_tri, self.fs)
 
-    def box_features(self, b: DeviceBatch):
+    def box_features(self, b: DeviceBatch, boxes=None, box_img=None):
         """Per-image conv1 (+tanh), per-box mask select, per-box conv2 halves -> U, V [nbox,32,32,512] bf16."""
         pk, fs = self.packed, self.fs
-        n_img, n_box = b.n_images, b.boxes.shape[0]
+        n_img = b.n_images
+        boxes = b.boxes if boxes is None else boxes
+        box_img = b.box_img if box_img is None else box_img
         x = ops.pack_pixels(b.feat, b.depth, K1_PAD)
         t = torch.empty(n_img * fs * fs, 256, dtype=torch.bfloat16, device=self.device)
         ops.tc_gemm(x, pk.w1, t, n_img * fs * fs, 256, K1_PAD, bias=pk.b1, lda=K1_PAD, ldc=256, epilogue=EPI_BF16, act=ACT_TANH,
                     group_m=8, tag="conv1")
-        abox = ops.box_select(t, b.boxes, b.box_img, pk.fill, fs)
+        abox = ops.box_select(t, boxes, box_img, pk.fill, fs)
         return pk.conv2_halves(abox, m_sub=self.conv2_m_sub)
+
+    def box_maps(self, boxes_x, u, v):
+        """Pooled conv3_1 output of every box of the window paired with the EMPTY box (the last row of boxes_x / u / v):
+        -> sub_maps = (box, empty), obj_maps = (empty, box), each [n_box,8,8,1024] bf16, and the work-list lengths.  A real
+        pair's output equals sub_maps[s] in the cells only its subject's box reaches and obj_maps[o] in those only its object's
+        box reaches (bit for bit: same kernels, same operands inside the receptive field)."""
+        pk, br = self.packed, self.conv3_block_rows
+        n_box = boxes_x.shape[0] - 1
+        idx = torch.arange(n_box, dtype=torch.int32, device=self.device)
+        empty = torch.full((n_box,), n_box, dtype=torch.int32, device=self.device)
+        sub, obj = torch.cat((idx, empty)), torch.cat((empty, idx))
+        maps = torch.empty(2 * n_box, 8, 8, 1024, dtype=torch.bfloat16, device=self.device)
+        starts = list(range(0, 2 * n_box, self.chunk_pairs))
+        nblk = torch.zeros(max(len(starts), 1), dtype=torch.int32, device=self.device)
+        for k, s in enumerate(starts):
+            e = min(2 * n_box, s + self.chunk_pairs)
+            p2 = ops.pair_relu_pool(u, v, None, sub[s:e], obj[s:e], self.fs)
+            blocks, _ = ops.conv3_active_blocks(boxes_x, sub[s:e], obj[s:e], br, self.fs, n_blocks=nblk[k:k + 1])
+            ops.broadcast_rows(pk.p3_background(), e - s, maps[s:e])
+            pk.conv3_blocks(p2, maps[s:e], e - s, blocks, nblk[k:k + 1], br, m_sub=self.conv3_m_sub, tag="conv3_box")
+            del p2
+        return maps[:n_box], maps[n_box:], nblk
 
     @staticmethod
     def _greedy_chunks(offsets_host, cap):
@@ -245,9 +273,26 @@ class RelationPipeline:
         (no `offsets_host`) take the generic gather kernel."""
         pk = self.packed
         n = pairs["n"]
-        u, v = self.box_features(b)
+        br, shared = self.conv3_block_rows, self.conv3_shared
+        if shared:      # one more box per window: the empty one (all background), partner of every box in `box_maps`
+            boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))
+            u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))))
+            p3_bg = pk.p3_background()
+            sub_maps, obj_maps, nblk_box = self.box_maps(boxes_x, u, v)
+            list_blocks = ops.conv3_shared_blocks
+        else:
+            u, v = self.box_features(b)
+            nblk_box = None
+            list_blocks = ops.conv3_active_blocks
+
+        def prefill(p3, sub, obj, cnt):
+            """everything of the pooled conv3_1 output that the work list will not write"""
+            if shared:
+                ops.p3_assemble(p3_bg, sub_maps, obj_maps, b.boxes, sub, obj, p3)
+            else:
+                ops.broadcast_rows(p3_bg, cnt, p3)
+
         raw = torch.empty(n, 512, dtype=torch.float32, device=self.device)
-        br = self.conv3_block_rows
         if "offsets_host" not in pairs:
             starts = list(range(0, n, self.chunk_pairs))
             nblk = torch.zeros(max(len(starts), 1), dtype=torch.int32, device=self.device) if br else None
@@ -255,12 +300,17 @@ class RelationPipeline:
                 e = min(n, s + self.chunk_pairs)
                 p2 = ops.pair_relu_pool(u, v, None, pairs["sub"][s:e], pairs["obj"][s:e], self.fs)
                 if br:
-                    blocks, _ = ops.conv3_active_blocks(b.boxes, pairs["sub"][s:e], pairs["obj"][s:e], br, self.fs, n_blocks=nblk[k:k + 1])
-                    pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e], blocks=blocks, n_blocks=nblk[k:k + 1], block_rows=br)
+                    blocks, _ = list_blocks(b.boxes, pairs["sub"][s:e], pairs["obj"][s:e], br, self.fs, n_blocks=nblk[k:k + 1])
+                    p3 = None
+                    if shared:
+                        p3 = torch.empty(e - s, 8, 8, 1024, dtype=torch.bfloat16, device=self.device)
+                        prefill(p3, pairs["sub"][s:e], pairs["obj"][s:e], e - s)
+                    pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e], blocks=blocks, n_blocks=nblk[k:k + 1], block_rows=br, p3=p3)
+                    del p3
                 else:
                     pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e])
                 del p2
-            self.last_n_blocks = nblk
+            self.last_n_blocks = nblk if nblk_box is None else torch.cat((nblk, nblk_box))
         else:
             n_box = b.boxes.shape[0]
             n_max = int(np.max(np.diff(b.box_offsets_host))) if b.box_offsets_host is not None else int(
@@ -275,7 +325,6 @@ class RelationPipeline:
                 p3_bufs = [torch.empty(cap, 8, 8, 1024, dtype=torch.bfloat16, device=self.device) for _ in bufs]
                 nblk = torch.zeros(len(chunks), dtype=torch.int32, device=self.device)
                 p3_bg = pk.p3_background()
-                self.last_n_blocks = nblk
             main = torch.cuda.current_stream()
             side = self._side_stream() if len(bufs) == 2 else main
             ready = torch.cuda.Event()
@@ -290,9 +339,9 @@ class RelationPipeline:
                             side.wait_event(gemm_done[k - 2])          # buffer free again
                     ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, self.fs, out=buf)
                     if br:
-                        ops.conv3_active_blocks(b.boxes, pairs["sub"][base:base + cnt], pairs["obj"][base:base + cnt], br, self.fs,
-                                                blocks=blk_bufs[k % len(bufs)], n_blocks=nblk[k:k + 1])
-                        ops.broadcast_rows(p3_bg, cnt, p3_bufs[k % len(bufs)])
+                        list_blocks(b.boxes, pairs["sub"][base:base + cnt], pairs["obj"][base:base + cnt], br, self.fs,
+                                    blocks=blk_bufs[k % len(bufs)], n_blocks=nblk[k:k + 1])
+                        prefill(p3_bufs[k % len(bufs)], pairs["sub"][base:base + cnt], pairs["obj"][base:base + cnt], cnt)
                     pooled = torch.cuda.Event()
                     pooled.record(side)
                 if side is not main:
@@ -307,6 +356,8 @@ class RelationPipeline:
                 gemm_done.append(ev)
             if side is not main:
                 main.wait_stream(side)
+            if br:
+                self.last_n_blocks = nblk if nblk_box is None else torch.cat((nblk, nblk_box))
         relation, sup, conn, logsig, _ = pk.heads(raw, pairs["sub"], pairs["obj"], b.cats, b.supers)
         return relation, sup, conn, logsig
 

@@ -1,5 +1,6 @@
 """GPU tests of the block-sparse conv3_1 (HC_GEMM_CONV3_BLOCKS): the work list covers the dilated footprint of each pair's
-two boxes, and the sparse path (background broadcast + listed blocks) reproduces the dense path BIT FOR BIT - the reference
+two boxes (or, shared-footprint mode, only the cells BOTH boxes reach - the rest is assembled from per-box maps), and the sparse
+path (pre-fill + listed blocks) reproduces the dense path BIT FOR BIT - the reference
 (model.py:138-150 on `feature*mask`, train_test.py:391,398) is dense, so equality with the dense kernels is the parity bar."""
 import numpy as np
 import pytest
@@ -120,7 +121,63 @@ def test_sparse_conv3_equals_dense_bit_for_bit(block_rows, m_sub):
 
 
 @pytest.mark.parametrize("block_rows", [8, 4])
-def test_pipeline_sparse_equals_dense(block_rows):
+def test_shared_list_and_assembly_equal_dense_bit_for_bit(block_rows):
+    """Shared-footprint path: per-box maps ((box, empty) / (empty, box)) + background assembled per pair, conv3_1 only on the
+    cover of the cells BOTH boxes reach == the dense kernel on every pair, every bf16 bit; the list covers the intersection."""
+    from scene_graph_commonsense_b200 import ops
+    from scene_graph_commonsense_b200._lib import EPI_POOL_BF16, GEMM_CONV3
+    pk = _packed()
+    boxes = _random_boxes(24, 17)
+    n_box = boxes.shape[0]
+    boxes_x = torch.cat((boxes, boxes.new_zeros(1, 4))).to(DEV)
+    g = torch.Generator().manual_seed(4)
+    t_img = torch.tanh(torch.randn(1, 32 * 32, 256, generator=g)).to(torch.bfloat16).to(DEV)
+    abox = ops.box_select(t_img, boxes_x, torch.zeros(n_box + 1, dtype=torch.int32, device=DEV), pk.fill, 32)
+    u, v = pk.conv2_halves(abox)
+    sub, obj = np.nonzero(~np.eye(n_box, dtype=bool))
+    sub_t = torch.from_numpy(sub.astype(np.int32)).to(DEV)
+    obj_t = torch.from_numpy(obj.astype(np.int32)).to(DEV)
+    n = sub_t.numel()
+    p2 = ops.pair_relu_pool(u, v, None, sub_t, obj_t, 32)
+    dense = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=DEV)
+    ops.tc_gemm(p2, pk.w3, dense, n * 256, 1024, 9 * 512, bias=pk.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16, n_img=n, h=16,
+                w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=2)
+    # per-box maps through the same kernels
+    idx = torch.arange(n_box, dtype=torch.int32, device=DEV)
+    emp = torch.full((n_box,), n_box, dtype=torch.int32, device=DEV)
+    s1, o1 = torch.cat((idx, emp)), torch.cat((emp, idx))
+    p2b = ops.pair_relu_pool(u, v, None, s1, o1, 32)
+    blk1, nb1 = ops.conv3_active_blocks(boxes_x, s1, o1, block_rows)
+    maps = ops.broadcast_rows(pk.p3_background(), 2 * n_box, torch.empty(2 * n_box, 8, 8, 1024, dtype=torch.bfloat16, device=DEV))
+    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows)
+    # work list = cover of the intersection
+    blocks, n_blocks = ops.conv3_shared_blocks(boxes_x, sub_t, obj_t, block_rows)
+    nb = int(n_blocks.item())
+    e = blocks[:nb].cpu().numpy()
+    pair, cy, cx = e >> 8, (e >> 4) & 15, e & 15
+    hc = block_rows // 2
+    cover = np.zeros((n, 8, 8), bool)
+    for p, y, x in zip(pair, cy, cx):
+        cover[p, y:y + hc, x:x + 4] = True
+    masks = np.stack([_cell_mask(b) for b in boxes.numpy()])
+    want = masks[sub] & masks[obj]
+    assert not (want & ~cover).any()
+    assert (np.bincount(pair, minlength=n)[~want.reshape(n, -1).any(1)] == 0).all()    # disjoint reach: nothing per pair
+    _, nb_union = ops.conv3_active_blocks(boxes_x, sub_t, obj_t, block_rows)
+    assert 0 < nb < int(nb_union.item())
+    # assembly (poisoned buffer: every cell must be written by the assembly or by the listed blocks)
+    out = torch.full((n, 8, 8, 1024), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.p3_assemble(pk.p3_background(), maps[:n_box], maps[n_box:], boxes_x[:n_box], sub_t, obj_t, out)
+    written = ~torch.isnan(out.float()).flatten(2).any(2).cpu().numpy()          # [n, 8, 8] cells the assembly wrote
+    assert (written == ~want).all()
+    pk.conv3_blocks(p2, out, n, blocks, n_blocks, block_rows)
+    torch.cuda.synchronize()
+    bad = (dense.view(torch.int16) != out.view(torch.int16)).flatten(1).any(1).nonzero().flatten().tolist()
+    assert not bad, "pairs %s differ (boxes %s)" % (bad[:5], [(int(sub[i]), int(obj[i])) for i in bad[:5]])
+
+
+@pytest.mark.parametrize("block_rows,shared", [(8, False), (4, False), (8, True), (4, True)])
+def test_pipeline_sparse_equals_dense(block_rows, shared):
     """Whole forward (chunked + overlapped, and the generic pair-list path): identical raw head outputs and counters."""
     from scene_graph_commonsense_b200 import pipeline
     pk = _packed(gain=40.0)
@@ -128,7 +185,7 @@ def test_pipeline_sparse_equals_dense(block_rows):
     samples[0].bbox[:6] = torch.tensor(EDGE_BOXES[:6], dtype=samples[0].bbox.dtype)
     outs = []
     for br in (0, block_rows):
-        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=120, conv3_block_rows=br)
+        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=120, conv3_block_rows=br, conv3_shared=shared)
         b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
         pairs = pipe.enumerate_pairs(b)
         rel, sup, conn, logsig = pipe.forward_pairs(b, pairs)

@@ -4,7 +4,7 @@ TAG=${1:-r01u}
 OUT=gpurun_out; mkdir -p $OUT
 echo "== pytest sparse"; timeout 600 python -m pytest tests/test_gpu_sparse.py -q -x --timeout=300 > $OUT/pytest_sparse_$TAG.log 2>&1; rc=$?; echo "pytest exit $rc"; tail -30 $OUT/pytest_sparse_$TAG.log
 if [ $rc -ne 0 ]; then exit $rc; fi
-for mode in dense blocks8 blocks4; do
+for mode in ${MODES:-blocks4 shared8 shared4}; do
   echo "== bench $mode"; timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --conv3 $mode > $OUT/bench_${mode}_$TAG.json 2> $OUT/bench_${mode}_$TAG.err; echo "exit $?"
   python - <<PY
 import json
