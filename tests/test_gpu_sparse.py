@@ -168,7 +168,7 @@ def test_shared_list_and_assembly_equal_dense_bit_for_bit(block_rows):
     # assembly (poisoned buffer: every cell must be written by the assembly or by the listed blocks)
     out = torch.full((n, 8, 8, 1024), float("nan"), dtype=torch.bfloat16, device=DEV)
     ops.p3_assemble(pk.p3_background(), maps[:n_box], maps[n_box:], boxes_x[:n_box], sub_t, obj_t, out)
-    written = ~torch.isnan(out.float()).flatten(2).any(2).cpu().numpy()          # [n, 8, 8] cells the assembly wrote
+    written = ~torch.isnan(out.float()).any(3).cpu().numpy()          # [n, 8, 8] cells the assembly wrote
     assert (written == ~want).all()
     pk.conv3_blocks(p2, out, n, blocks, n_blocks, block_rows)
     torch.cuda.synchronize()
