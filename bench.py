@@ -181,7 +181,8 @@ def run_ours(args):
     chunk_pairs = args.chunk_pairs or wl["chunk_pairs"]
     pipe = pipeline.RelationPipeline(packed, dev, commonsense=True, chunk_pairs=chunk_pairs, conv3_m_sub=args.conv3_m_sub,
                                      overlap=not args.no_overlap, predcls=not wl["sgdet"], chunk_policy=args.chunk_policy,
-                                     conv3_block_rows=CONV3_MODES[args.conv3][0], conv3_shared=CONV3_MODES[args.conv3][1])
+                                     conv3_block_rows=CONV3_MODES[args.conv3][0], conv3_shared=CONV3_MODES[args.conv3][1],
+                                     fc1_shared=args.fc1 == "shared")
     samples = make_samples(rank, wl["images"], wl["boxes"], sgdet=wl["sgdet"])
     host = pipeline.host_batch_from_samples(samples, skip_mode="batch", sgdet=wl["sgdet"])
     del samples
@@ -236,6 +237,13 @@ def run_ours(args):
     # block-sparse conv3_1: work-list lengths of the last step (read back AFTER the timed region)
     blocks_step = int(pipe.last_n_blocks.sum().item()) if pipe.conv3_block_rows and pipe.last_n_blocks is not None else None
 
+    # shared-footprint fc1: K cells visited per 256-row tile of the last step (read back AFTER the timed region)
+    fc1_exec_frac, fc1_cells = 1.0, None
+    if pipe.fc1_shared and pipe.last_k_masks is not None:
+        fc1_cells = int(np.unpackbits(pipe.last_k_masks.cpu().numpy().view(np.uint8)).sum())
+        fc1_exec_frac = fc1_cells * 256.0 / (pairs_step * 64.0)
+    n_box_step = wl["images"] * wl["boxes"]
+
     per_tag = {}
     for tag, a, b in ops.PROFILE["events"]:
         per_tag.setdefault(tag, []).append(a.elapsed_time(b))
@@ -289,7 +297,16 @@ def run_ours(args):
             tp = os.path.join(ROOT, "profiles", "conv3_dram_bytes.json")    # the committed ncu DRAM figure is the dense kernel's
             if os.path.exists(tp):
                 roof_conv3["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
-    roof_fc1 = roof_of("tc_gemm_kernel<256,2> fc1 [pairs,65536] x [65536,4096] + bias/ReLU epilogue", fc1, pairs_step * FLOP_PAIR_FC1, {})
+    fc1_times = fc1 + per_tag.get("fc1_box", [])
+    fc1_box_flop = (2 * n_box_step + 1) * FLOP_PAIR_FC1 if pipe.fc1_shared else 0        # per-box fc1 rows (dense)
+    roof_fc1 = roof_of("tc_gemm_kernel<256,2> fc1 [pairs,65536] x [65536,4096] + bias/ReLU epilogue (%s)" % (args.fc1 if pipe.fc1_shared else "dense"),
+                       fc1_times, fc1_exec_frac * pairs_step * FLOP_PAIR_FC1 + fc1_box_flop,
+                       {"note": "achieved counts EXECUTED FLOPs: the K cells each 256-row tile visits (pair launch) + the dense per-box "
+                                "rows; dense-equivalent = achieved / executed_fraction",
+                        "executed_fraction": (fc1_exec_frac * pairs_step * FLOP_PAIR_FC1 + fc1_box_flop) / (pairs_step * FLOP_PAIR_FC1)}
+                       if pipe.fc1_shared else {})
+    if roof_fc1 is not None and pipe.fc1_shared:
+        roof_fc1["dense_equivalent_tflops"] = roof_fc1["achieved"] / roof_fc1["executed_fraction"]
     roofs = [r for r in (roof_conv3, roof_fc1) if r is not None]
     roofs.sort(key=lambda r: -r["ms_per_step"])
     roof = roofs[0] if roofs else None
@@ -297,6 +314,7 @@ def run_ours(args):
     breakdown = {t: {"launches": len(v), "ms_per_step": float(np.sum(v)) / args.steps} for t, v in sorted(per_tag.items())}
     flop_dense = wl["images"] * FLOP_IMG + wl["images"] * wl["boxes"] * FLOP_BOX + pairs_step * FLOP_PAIR
     flop_step = flop_dense - (1.0 - conv3_exec_frac) * pairs_step * FLOP_PAIR_CONV3      # FLOPs actually executed
+    flop_step += fc1_box_flop - (1.0 - fc1_exec_frac) * pairs_step * FLOP_PAIR_FC1
     m = pipeline.metrics_from_counters(counters_final)
 
     cpu = None
@@ -313,7 +331,7 @@ def run_ours(args):
                    "l2": "no explicit flush: each step streams >10 GB of activations/weights (>> 126 MB L2)",
                    "weights": "random init, trained-scale logits (seed 0)", "chunk_pairs": chunk_pairs,
                    "pool_gemm_overlap": not args.no_overlap, "conv3_m_sub": args.conv3_m_sub, "chunk_policy": args.chunk_policy,
-                   "conv3": args.conv3},
+                   "conv3": args.conv3, "fc1": args.fc1 if pipe.fc1_shared else "dense"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes * world,
                 "d2h_bytes_per_step": (tables.COUNTER_SIZE * 8 + 4) * world, "ms_per_step": t_e2e / args.steps * 1e3,
                 "api": "RelationPipeline.run over pinned HostBatch windows (H2D of window k+1 issued under window k's kernels; "
@@ -321,7 +339,7 @@ def run_ours(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_second": roof_second,
         "step_tensor_frac": flop_step / (t_max / args.steps) / 1e12 / pk["bf16_sustained"],
         "algorithmic_tflop_per_step": flop_dense / 1e12, "executed_tflop_per_step": flop_step / 1e12,
-        "conv3_blocks_per_step": blocks_step, "kernel_breakdown": breakdown,
+        "conv3_blocks_per_step": blocks_step, "fc1_cells_per_step": fc1_cells, "kernel_breakdown": breakdown,
         "recall": {"R@20/50/100": m["evaluator"][0], "mR@20/50/100": [float(x) for x in m["evaluator"][2]]},
         "cpu_baseline": cpu,
     }
@@ -352,6 +370,9 @@ def main():
     ap.add_argument("--conv3-m-sub", type=int, default=2)
     ap.add_argument("--conv3", default="shared4", choices=sorted(CONV3_MODES),
                     help="conv3_1 kernel: dense, or block-sparse over the dilated footprint of each pair's boxes (bit-identical output)")
+    ap.add_argument("--fc1", default="shared", choices=["shared", "dense"],
+                    help="shared = fc1 as per-box rows + a K-cell-sparse GEMM over the cells both boxes reach (needs --conv3 shared*); "
+                         "dense = fc1 over the assembled conv3_1 output")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--chunk-policy", default="waves", choices=["waves", "greedy"],

@@ -91,6 +91,18 @@ int hc_pairs_enumerate(const int32_t* boxes, const int32_t* box_offsets, int32_t
  *          HC_EPI_SPLIT3_BF16 : plain only: x = act(acc + bias) * mul written as the bf16x3 A operand of a following
  *                             GEMM, out bf16 [M, ldc >= 3N] = [hi | lo | hi], hi = bf16(x), lo = bf16(x - hi)
  *                             (see hc_split_bf16x3); the f32 intermediate never reaches HBM
+ *          HC_EPI_POOL_DIFF_BF16 : CONV3_BLOCKS only: with x = the HC_EPI_POOL_BF16 value (rounded to bf16) of local pair i,
+ *                             writes d = (x - diff_sub[pair_sub[i]]) - (diff_obj[pair_obj[i]] - diff_bg) (fp32, then bf16) into row
+ *                             pair_row[i] of out [rows, H/2, W/2, ldc]; diff_* are pooled maps of the same layout.  d is exactly 0
+ *                             in a cell that only one box of the pair (or none) reaches - the operand of the K-cell-sparse fc1 below.
+ * K-cell-sparse PLAIN GEMM (k_masks != NULL): the K axis is cut into K / k_cell <= 64 cells; bit c of k_masks[t] says that some row
+ *     of CTA M tile t (m_sub*128 rows) is non-zero in cell c, and only those cells' K blocks are visited, in ascending order.  The
+ *     caller guarantees A is ZERO in every (row, cell) of a visited cell the row does not use, so the result equals the dense GEMM
+ *     bit for bit per row, whatever tile the row sits in.  A tile with an empty mask skips the tensor core altogether.
+ *     (model.py:149 fc1 is linear: fc1(p3) = fc1(sub map) + fc1(obj map) - fc1(background) + fc1(d), and d is zero outside the cells
+ *     both boxes reach - hc_pair_cell_keys / hc_tile_cell_masks below build the row order and the masks.)
+ * add_a/add_b (EPI_BF16, PLAIN): act(acc + bias + add_a[add_a_rows[r]] + add_b[add_b_rows[r]]), f32 tables [*, ld_add].
+ * out_rows (PLAIN, no mul): GEMM row r is written to output row out_rows[r] (a permutation; NULL = identity).
  * Requirements: K % 64 == 0, N % 128 == 0, all bases 16-byte aligned, lda/ldc/c_total multiples of 8.
  */
 #define HC_GEMM_PLAIN 0
@@ -100,6 +112,7 @@ int hc_pairs_enumerate(const int32_t* boxes, const int32_t* box_offsets, int32_t
 #define HC_EPI_F32 1
 #define HC_EPI_POOL_BF16 2
 #define HC_EPI_SPLIT3_BF16 3
+#define HC_EPI_POOL_DIFF_BF16 4
 #define HC_ACT_NONE 0
 #define HC_ACT_RELU 1
 #define HC_ACT_TANH 2
@@ -122,6 +135,20 @@ typedef struct hc_gemm_desc {
   const int32_t* blocks;   /* CONV3_BLOCKS: device work list */
   const int32_t* n_blocks; /* CONV3_BLOCKS: device scalar, number of entries */
   int32_t block_rows;      /* CONV3_BLOCKS: 8 or 4 */
+  const uint64_t* k_masks; /* PLAIN: per CTA M tile, bitmap of visited K cells (NULL = dense) */
+  int64_t k_cell;          /* PLAIN + k_masks: K elements per cell (multiple of 64, K / k_cell <= 64) */
+  const float* add_a;      /* EPI_BF16 row gathers, both or neither */
+  const int32_t* add_a_rows;
+  const float* add_b;
+  const int32_t* add_b_rows;
+  int64_t ld_add;
+  const int32_t* out_rows; /* PLAIN: output row per GEMM row (NULL = identity) */
+  const void* diff_sub;    /* HC_EPI_POOL_DIFF_BF16: bf16 [n_sub, H/2, W/2, ldc] */
+  const void* diff_obj;    /*                        bf16 [n_obj, H/2, W/2, ldc] */
+  const void* diff_bg;     /*                        bf16 [H/2, W/2, ldc] */
+  const int32_t* pair_sub; /*                        per local pair: row of diff_sub */
+  const int32_t* pair_obj; /*                        per local pair: row of diff_obj */
+  const int32_t* pair_row; /*                        per local pair: output row */
 } hc_gemm_desc;
 
 int hc_tc_gemm(const hc_gemm_desc* desc, hc_stream_t stream);
@@ -157,6 +184,21 @@ int hc_p3_assemble(const void* background, const void* sub_maps, const void* obj
 /* out[i, :] = src[:] for i < n_rows (row_bytes a multiple of 16; both 16-byte aligned): pre-fills the pooled conv3_1 output of
  * every pair with the background before HC_GEMM_CONV3_BLOCKS overwrites the active blocks. */
 int hc_broadcast_rows(const void* src, int64_t row_bytes, int64_t n_rows, void* out, hc_stream_t stream);
+
+/* model.py:149 - shared-footprint fc1 (the K-cell-sparse mode of hc_tc_gemm).  fc1 is linear, and the pooled conv3_1 output of a
+ * pair differs from "subject map + object map - background" (hc_p3_assemble) only in the 8-grid cells BOTH boxes reach, a
+ * rectangle of cells.  hc_pair_cell_keys writes a sort key of that rectangle per directed pair, ((y0*8 + y1)*8 + x0)*8 + x1 with
+ * inclusive cell bounds, 4096 when the boxes share no cell: sorting rows by it makes the rows of a GEMM tile share their cells.
+ * hc_tile_cell_masks ORs the cell masks of every `rows_per_tile` consecutive sorted rows (row_sub / row_obj = box ids in sorted
+ * order) into masks[tile] - the `k_masks` of hc_tc_gemm (rows_per_tile = m_sub*128).  hc_cells_zero zeroes, in every row of the
+ * operand out [n_rows, n_cells, cell_bytes], the cells its tile's mask visits; HC_EPI_POOL_DIFF_BF16 then overwrites the cells the
+ * pair computes.  feature_size must be 32. */
+int hc_pair_cell_keys(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs, int32_t feature_size,
+                      int32_t* keys, hc_stream_t stream);
+int hc_tile_cell_masks(const int32_t* boxes, const int32_t* row_sub, const int32_t* row_obj, int32_t n_rows, int32_t feature_size,
+                       int32_t rows_per_tile, uint64_t* masks, hc_stream_t stream);
+int hc_cells_zero(const uint64_t* masks, int32_t rows_per_tile, int64_t n_rows, int32_t n_cells, int64_t cell_bytes, void* out,
+                  hc_stream_t stream);
 
 /* [B,C0,hw] f32 (+ optional [B,C1,hw] f32) NCHW maps -> [B*hw, k_pad] bf16 pixel-major rows, zero padded
  * (the A operand of the 1x1 convolutions, model.py:139-140; also packs the legacy pre-masked [bs,257,32,32]). */

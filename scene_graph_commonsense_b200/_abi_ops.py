@@ -9,8 +9,8 @@ import numpy as np
 import torch
 
 from . import _lib, tables
-from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16, GEMM_CONV3, GEMM_CONV3_BLOCKS,
-                   GEMM_PLAIN, check, ptr, require_cuda, stream_ptr)
+from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_POOL_DIFF_BF16, EPI_SPLIT3_BF16, GEMM_CONV3,  # noqa: F401
+                   GEMM_CONV3_BLOCKS, GEMM_PLAIN, check, ptr, require_cuda, stream_ptr)
 
 LAUNCHES = {"n": 0}
 PROFILE = {"on": False, "events": []}     # bench.py: CUDA-event timing of tagged launches on the launching stream
@@ -79,9 +79,18 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16,
             act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None,
-            blocks=None, n_blocks=None, block_rows=0):
+            blocks=None, n_blocks=None, block_rows=0, k_masks=None, k_cell=0, add_a=None, add_a_rows=None, add_b=None, add_b_rows=None,
+            out_rows=None, diff_sub=None, diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None):
     """out = epilogue(A @ B^T) on tcgen05 (see include/hiercom_b200.h hc_tc_gemm)."""
-    require_cuda(a, b, out, bias, mul, blocks, n_blocks)
+    require_cuda(a, b, out, bias, mul, blocks, n_blocks, k_masks, add_a, add_a_rows, add_b, add_b_rows, out_rows, diff_sub, diff_obj, diff_bg,
+                 pair_sub, pair_obj, pair_row)
+    for t, dt in ((k_masks, torch.int64), (add_a, torch.float32), (add_b, torch.float32), (add_a_rows, torch.int32), (add_b_rows, torch.int32),
+                  (out_rows, torch.int32), (diff_sub, torch.bfloat16), (diff_obj, torch.bfloat16), (diff_bg, torch.bfloat16),
+                  (pair_sub, torch.int32), (pair_obj, torch.int32), (pair_row, torch.int32)):
+        if t is not None and (t.dtype != dt or not t.is_contiguous()):
+            raise RuntimeError("hiercom_b200: tc_gemm side operand must be a contiguous %s tensor" % dt)
+    if add_a is not None and (add_b is None or add_a.stride(0) != add_b.stride(0)):
+        raise RuntimeError("hiercom_b200: tc_gemm add_a / add_b must come together with the same row stride")
     d = _lib.GemmDesc()
     d.a, d.b, d.bias, d.out = ptr(a), ptr(b), ptr(bias), ptr(out)
     d.m, d.n, d.k = m, n, k
@@ -91,6 +100,12 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     d.group_m, d.m_sub = group_m, m_sub
     d.mul, d.ld_mul = ptr(mul), (mul.stride(0) if mul is not None else 0)
     d.blocks, d.n_blocks, d.block_rows = ptr(blocks), ptr(n_blocks), block_rows
+    d.k_masks, d.k_cell = ptr(k_masks), k_cell
+    d.add_a, d.add_a_rows, d.add_b, d.add_b_rows = ptr(add_a), ptr(add_a_rows), ptr(add_b), ptr(add_b_rows)
+    d.ld_add = add_a.stride(0) if add_a is not None else 0
+    d.out_rows = ptr(out_rows)
+    d.diff_sub, d.diff_obj, d.diff_bg = ptr(diff_sub), ptr(diff_obj), ptr(diff_bg)
+    d.pair_sub, d.pair_obj, d.pair_row = ptr(pair_sub), ptr(pair_obj), ptr(pair_row)
     with _timed(tag):
         check(_lib.load().hc_tc_gemm(C.byref(d), stream_ptr()), "hc_tc_gemm")
     _count()
@@ -115,6 +130,40 @@ def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=N
           name)
     _count()
     return blocks, n_blocks
+
+
+def pair_cell_keys(boxes, pair_sub, pair_obj, fs=32):
+    """Sort key (int32 [n]) of the cell rectangle both boxes of each directed pair reach (include/hiercom_b200.h hc_pair_cell_keys)."""
+    require_cuda(boxes, pair_sub, pair_obj)
+    n = pair_sub.numel()
+    keys = torch.empty(n, dtype=torch.int32, device=boxes.device)
+    check(_lib.load().hc_pair_cell_keys(ptr(boxes), ptr(pair_sub), ptr(pair_obj), n, fs, ptr(keys), stream_ptr()), "hc_pair_cell_keys")
+    _count()
+    return keys
+
+
+def tile_cell_masks(boxes, row_sub, row_obj, rows_per_tile, fs=32):
+    """int64 [ceil(n / rows_per_tile)] bitmaps: union over each tile's rows of the cells both boxes reach (hc_tile_cell_masks)."""
+    require_cuda(boxes, row_sub, row_obj)
+    n = row_sub.numel()
+    masks = torch.zeros(max(-(-n // rows_per_tile), 1), dtype=torch.int64, device=boxes.device)
+    check(_lib.load().hc_tile_cell_masks(ptr(boxes), ptr(row_sub), ptr(row_obj), n, fs, rows_per_tile, ptr(masks), stream_ptr()),
+          "hc_tile_cell_masks")
+    _count()
+    return masks
+
+
+def cells_zero(masks, rows_per_tile, n_rows, out):
+    """Zero, in every row of out [>= n_rows, n_cells, cell], the cells its tile's mask visits (hc_cells_zero)."""
+    require_cuda(masks, out)
+    if out.dim() != 3 or not out.is_contiguous() or out.shape[0] < n_rows or masks.dtype != torch.int64 or \
+            masks.numel() * rows_per_tile < n_rows:
+        raise RuntimeError("hiercom_b200: cells_zero needs a contiguous [rows, cells, cell] operand and one int64 mask per tile")
+    with _timed("d_zero"):
+        check(_lib.load().hc_cells_zero(ptr(masks), rows_per_tile, n_rows, out.shape[1], out.shape[2] * out.element_size(), ptr(out),
+                                        stream_ptr()), "hc_cells_zero")
+    _count()
+    return out
 
 
 def p3_assemble(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, fs=32):

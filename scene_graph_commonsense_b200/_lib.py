@@ -14,7 +14,7 @@ HC_OK = 0
 ERRORS = {-1: "HC_E_SHAPE", -2: "HC_E_ALIGN", -3: "HC_E_ARCH", -4: "HC_E_CUDA", -5: "HC_E_NULL"}
 
 GEMM_PLAIN, GEMM_CONV3, GEMM_CONV3_BLOCKS = 0, 1, 2
-EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16 = 0, 1, 2, 3
+EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16, EPI_POOL_DIFF_BF16 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
 
 
@@ -26,7 +26,12 @@ class GemmDesc(C.Structure):
                 ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("c_total", C.c_int32), ("c_base", C.c_int32), ("c_in", C.c_int32),
                 ("group_m", C.c_int32), ("m_sub", C.c_int32), ("mul", C.c_void_p), ("ld_mul", C.c_int64),
-                ("blocks", C.c_void_p), ("n_blocks", C.c_void_p), ("block_rows", C.c_int32)]
+                ("blocks", C.c_void_p), ("n_blocks", C.c_void_p), ("block_rows", C.c_int32),
+                ("k_masks", C.c_void_p), ("k_cell", C.c_int64),
+                ("add_a", C.c_void_p), ("add_a_rows", C.c_void_p), ("add_b", C.c_void_p), ("add_b_rows", C.c_void_p), ("ld_add", C.c_int64),
+                ("out_rows", C.c_void_p),
+                ("diff_sub", C.c_void_p), ("diff_obj", C.c_void_p), ("diff_bg", C.c_void_p),
+                ("pair_sub", C.c_void_p), ("pair_obj", C.c_void_p), ("pair_row", C.c_void_p)]
 
 
 _P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
@@ -42,6 +47,9 @@ SIGNATURES = {
     "hc_conv3_shared_blocks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "hc_p3_assemble": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P]),
     "hc_broadcast_rows": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "hc_pair_cell_keys": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P]),
+    "hc_tile_cell_masks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P]),
+    "hc_cells_zero": (C.c_int, [_P, _I32, _I64, _I32, _I64, _P, _P]),
     "hc_pack_pixels": (C.c_int, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "hc_box_select": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),

@@ -113,6 +113,53 @@ __global__ void broadcast_rows_kernel(const uint4* __restrict__ src, long long r
   for (long long r = blockIdx.y; r < n_rows; r += gridDim.y) __stcs(out + r * row_vecs + c, v);
 }
 
+
+// ---- shared-footprint fc1: row order, per-tile K-cell masks, zero fill of the operand --------------------------------------------
+// A directed pair's fc1 operand d (HC_EPI_POOL_DIFF_BF16) is non-zero only in the cells BOTH boxes reach - the intersection of two
+// cell rectangles, itself a rectangle.  Rows are sorted by that rectangle so the 256 rows of a CTA M tile share most of their
+// cells; the tile's mask is the union.  key = ((y0*8 + y1)*8 + x0)*8 + x1 (inclusive cell bounds), pairs with no common cell last.
+__global__ void pair_cell_keys_kernel(const int4* __restrict__ boxes, const int* __restrict__ pair_sub, const int* __restrict__ pair_obj,
+                                      int n_pairs, int fs, int* __restrict__ keys) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const unsigned long long m = cell_mask(rect_of(__ldg(boxes + pair_sub[p]), fs)) & cell_mask(rect_of(__ldg(boxes + pair_obj[p]), fs));
+  int key = 4096;
+  if (m) {
+    const int lo = __ffsll((long long)m) - 1, hi = 63 - __clzll((long long)m);      // first / last set cell of a rectangle = its corners
+    key = ((((lo >> 3) << 3 | (hi >> 3)) << 3 | (lo & 7)) << 3) | (hi & 7);
+  }
+  keys[p] = key;
+}
+
+// one warp per tile of `rows_per_tile` sorted rows: OR of the rows' cell masks
+__global__ void tile_cell_masks_kernel(const int4* __restrict__ boxes, const int* __restrict__ row_sub, const int* __restrict__ row_obj,
+                                       int n_rows, int fs, int rows_per_tile, int n_tiles, unsigned long long* __restrict__ masks) {
+  const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (tile >= n_tiles) return;
+  unsigned long long m = 0ull;
+  const int r1 = min(n_rows, (tile + 1) * rows_per_tile);
+  for (int r = tile * rows_per_tile + lane; r < r1; r += 32)
+    m |= cell_mask(rect_of(__ldg(boxes + row_sub[r]), fs)) & cell_mask(rect_of(__ldg(boxes + row_obj[r]), fs));
+#pragma unroll
+  for (int d = 16; d; d >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, d);
+  if (lane == 0) masks[tile] = m;
+}
+
+// zero every cell of a row that its tile's mask visits (the difference epilogue then overwrites the cells the pair itself computes);
+// cells outside the mask are never read.  One CTA per row, a cell = `cell_vecs` uint4.
+__global__ void __launch_bounds__(128)
+cells_zero_kernel(const unsigned long long* __restrict__ masks, int rows_per_tile, long long n_rows, int n_cells, int cell_vecs,
+                  uint4* __restrict__ out) {
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long long r = blockIdx.x; r < n_rows; r += gridDim.x) {
+    uint4* dst = out + r * (long long)n_cells * cell_vecs;
+    for (unsigned long long m = __ldg(masks + r / rows_per_tile); m; m &= m - 1) {
+      const int c = __ffsll((long long)m) - 1;
+      for (int i = threadIdx.x; i < cell_vecs; i += blockDim.x) dst[(long long)c * cell_vecs + i] = z;
+    }
+  }
+}
+
 }  // namespace hc
 
 using namespace hc;
@@ -178,4 +225,51 @@ extern "C" int hc_broadcast_rows(const void* src, int64_t row_bytes, int64_t n_r
   broadcast_rows_kernel<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), row_vecs, n_rows,
                                                                             reinterpret_cast<uint4*>(out));
   return cuda_status("broadcast_rows_kernel launch");
+}
+
+extern "C" int hc_pair_cell_keys(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs, int32_t feature_size,
+                                 int32_t* keys, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(n_pairs <= 0 || (boxes && pair_sub && pair_obj && keys), HC_E_NULL, "hc_pair_cell_keys: NULL operand");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  HC_REQUIRE(feature_size == 32, HC_E_SHAPE, "hc_pair_cell_keys: built for feature_size 32 (8x8 pooled conv3 cells)");
+  HC_REQUIRE(aligned16(boxes), HC_E_ALIGN, "hc_pair_cell_keys: boxes must be 16-byte aligned");
+  if (n_pairs <= 0) return HC_OK;
+  pair_cell_keys_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const int4*>(boxes), pair_sub, pair_obj, n_pairs,
+                                                                   feature_size, keys);
+  return cuda_status("pair_cell_keys_kernel launch");
+}
+
+extern "C" int hc_tile_cell_masks(const int32_t* boxes, const int32_t* row_sub, const int32_t* row_obj, int32_t n_rows, int32_t feature_size,
+                                  int32_t rows_per_tile, uint64_t* masks, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(n_rows <= 0 || (boxes && row_sub && row_obj && masks), HC_E_NULL, "hc_tile_cell_masks: NULL operand");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  HC_REQUIRE(feature_size == 32, HC_E_SHAPE, "hc_tile_cell_masks: built for feature_size 32 (8x8 pooled conv3 cells)");
+  HC_REQUIRE(rows_per_tile > 0, HC_E_SHAPE, "hc_tile_cell_masks: rows_per_tile must be positive");
+  HC_REQUIRE(aligned16(boxes), HC_E_ALIGN, "hc_tile_cell_masks: boxes must be 16-byte aligned");
+  if (n_rows <= 0) return HC_OK;
+  const int n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
+  tile_cell_masks_kernel<<<(n_tiles + 7) / 8, 256, 0, stream>>>(reinterpret_cast<const int4*>(boxes), row_sub, row_obj, n_rows, feature_size,
+                                                                rows_per_tile, n_tiles, reinterpret_cast<unsigned long long*>(masks));
+  return cuda_status("tile_cell_masks_kernel launch");
+}
+
+extern "C" int hc_cells_zero(const uint64_t* masks, int32_t rows_per_tile, int64_t n_rows, int32_t n_cells, int64_t cell_bytes, void* out,
+                             hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(n_rows <= 0 || (masks && out), HC_E_NULL, "hc_cells_zero: NULL operand");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  HC_REQUIRE(rows_per_tile > 0 && n_cells > 0 && n_cells <= 64 && cell_bytes > 0 && cell_bytes % 16 == 0, HC_E_SHAPE,
+             "hc_cells_zero: 1..64 cells of a positive multiple of 16 bytes");
+  HC_REQUIRE(aligned16(out), HC_E_ALIGN, "hc_cells_zero: out must be 16-byte aligned");
+  if (n_rows <= 0) return HC_OK;
+  const long long cap = (long long)num_sms() * 16;
+  cells_zero_kernel<<<(unsigned)(n_rows < cap ? n_rows : cap), 128, 0, stream>>>(reinterpret_cast<const unsigned long long*>(masks),
+                                                                                rows_per_tile, n_rows, n_cells, (int)(cell_bytes / 16),
+                                                                                reinterpret_cast<uint4*>(out));
+  return cuda_status("cells_zero_kernel launch");
 }

@@ -12,6 +12,9 @@
 //   block-sparse conv (the same 3x3 convolution restricted to a WORK LIST of 8 x {8,4}-pixel blocks: a 128-row sub-tile is
 //                    assembled from 2 or 4 blocks of possibly different images, one 4-D TMA box per block and tap; used for
 //                    conv3_1, whose output equals a weights-only background outside the dilated footprint of the two boxes)
+//   K-cell-sparse GEMM (plain GEMM whose K axis is cut into <= 64 cells; every CTA M tile carries a 64-bit mask of the cells in which
+//                    ANY of its rows is non-zero and visits only those K blocks - exact, because the skipped operand is zero; used
+//                    for fc1 over the cells both boxes of a pair reach, with per-box fc1 rows gathered in the epilogue)
 // CTA = 6 warps: warp 0 TMA producer, warp 1 tcgen05.mma issuer (+TMEM owner), warps 2-5 epilogue
 // (TMEM -> registers -> fused bias/activation/2x2-max-pool -> global).  Pipelines: smem full/empty ring
 // (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -69,6 +72,17 @@ struct Params {
   const int* blocks;             // HC_GEMM_CONV3_BLOCKS: work list, entry = img << 8 | (y0/2) << 4 | (x0/2)
   const int* n_blocks;           // device scalar: entries in the work list
   int blk_h;                     // pixel rows per block (8 or 4); blocks are 8 pixels wide
+  // K-cell-sparse plain GEMM: bit c of k_masks[CTA m tile] set = K blocks [c*k_cell_kb, (c+1)*k_cell_kb) are visited
+  const unsigned long long* k_masks;
+  int k_cell_kb;
+  // EPI_BF16 row gathers: act(acc + bias + add_a[add_a_rows[row]] + add_b[add_b_rows[row]])
+  const float* add_a; const int* add_a_rows;
+  const float* add_b; const int* add_b_rows;
+  long long ld_add;
+  const int* out_rows;           // plain GEMM: output row of GEMM row r (NULL = r)
+  // HC_EPI_POOL_DIFF_BF16 (block mode): out[pair_row[pair]] = (x - diff_sub[pair_sub[pair]]) - (diff_obj[pair_obj[pair]] - diff_bg)
+  const __nv_bfloat16* diff_sub; const __nv_bfloat16* diff_obj; const __nv_bfloat16* diff_bg;
+  const int* pair_sub; const int* pair_obj; const int* pair_row;
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -320,7 +334,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(p, tiles_m, tile, m_blk, n_blk);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        auto load_kb = [&](int kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_dst = a_dst + MS * A_SUB_BYTES;
@@ -330,6 +344,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             tma_load_2d(a_dst + j * A_SUB_BYTES, &tmap_a, full_bar(stage), kb * BK, (m_blk * MS + j) * BM);
           tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        };
+        if (p.k_masks) {
+          // K-cell-sparse: only the K cells some row of this M tile is non-zero in (ascending cell order)
+          for (unsigned long long km = __ldg(p.k_masks + m_blk); km; km &= km - 1) {
+            const int kb0 = (__ffsll((long long)km) - 1) * p.k_cell_kb;
+            for (int i = 0; i < p.k_cell_kb; ++i) load_kb(kb0 + i);
+          }
+        } else {
+          for (int kb = 0; kb < num_kb; ++kb) load_kb(kb);
         }
       }
     }
@@ -378,7 +401,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator stage
         tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
+        uint32_t started = 0;                             // 0 until the first MMA of the tile (which overwrites the accumulator)
+        auto mma_kb = [&]() {
           mbar_wait(full_bar(stage), phase);              // TMA bytes of this stage have landed
           tc_fence_after();
           const uint32_t a_src = smem_base + stage * C::STAGE_BYTES;
@@ -389,12 +413,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_COLS + j * BN);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)         // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
-              umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) ? 1u : 0u);
+              umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (started | k) ? 1u : 0u);
           }
+          started = 1;
           umma_commit(empty_bar(stage));                  // smem slot free once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        };
+        if (p.k_masks) {
+          int m_blk, n_blk;
+          tile_coords(p, tiles_m, tile, m_blk, n_blk);
+          const int n_cells = __popcll(__ldg(p.k_masks + m_blk));
+          for (int i = 0; i < n_cells * p.k_cell_kb; ++i) mma_kb();
+        } else {
+          for (int kb = 0; kb < num_kb; ++kb) mma_kb();
         }
+        // accumulator complete once the MMAs above retire; an empty cell mask issued none: plain arrive, the epilogue substitutes zeros
+        if (started) umma_commit(tfull_bar(acc));
+        else mbar_arrive(tfull_bar(acc));
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -419,6 +454,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int n0 = n_blk * BN;
+      // K-cell-sparse tile with an empty cell mask: no MMA ran, the accumulator is all zeros by definition
+      const bool no_acc = p.k_masks != nullptr && __ldg(p.k_masks + m_blk) == 0ull;
 #pragma unroll 1
       for (int j = 0; j < MS; ++j) {
 #pragma unroll 1
@@ -426,8 +463,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           uint32_t r[32];
           __syncwarp();                                    // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + j * BN + ch * 32), r);
+          if (no_acc) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0u;
+          }
           const int col0 = n0 + ch * 32;
-          if (p.epi == HC_EPI_POOL_BF16) {
+          if (p.epi == HC_EPI_POOL_BF16 || p.epi == HC_EPI_POOL_DIFF_BF16) {
             // rows of a sub-tile are pixels (yl, xl) = (row/16, row%16); this warp holds yl in {2q, 2q+1}.
             // 2x2 max-pool partners are lane^1 (x) and lane^16 (y): butterfly reduce-scatter, after which the
             // lane with bits (ybit, xbit) owns the pooled maximum of columns [ybit*16 + xbit*8, +8).
@@ -468,9 +509,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               py = ((e >> 4) & 15) + ((((q * 32) % rows_pb) >> 3) >> 1) + (lane >> 4);
               px = (e & 15) + ((lane & 7) >> 1);
             }
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                                 (((long long)o_img * (p.H / 2) + py) * (p.W / 2) + px) * p.ldc + p.c_off + cbase;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (p.epi == HC_EPI_POOL_DIFF_BF16) {
+              // shared-footprint fc1 operand: what this pair's cell adds to the sum of its two per-box maps,
+              //   d = (x - sub_map[s]) - (obj_map[o] - background), x already rounded to bf16 like the maps;
+              // exactly 0 wherever only one box (or none) reaches the cell, because x then equals that map bit for bit
+              const long long map_elems = (long long)(p.H / 2) * (p.W / 2) * p.ldc;
+              const long long cell_off = ((long long)py * (p.W / 2) + px) * p.ldc + p.c_off + cbase;
+              const uint4 S = __ldg(reinterpret_cast<const uint4*>(p.diff_sub + (long long)__ldg(p.pair_sub + o_img) * map_elems + cell_off));
+              const uint4 O = __ldg(reinterpret_cast<const uint4*>(p.diff_obj + (long long)__ldg(p.pair_obj + o_img) * map_elems + cell_off));
+              const uint4 G = __ldg(reinterpret_cast<const uint4*>(p.diff_bg + cell_off));
+              const uint32_t sv[4] = {S.x, S.y, S.z, S.w}, ov[4] = {O.x, O.y, O.z, O.w}, gv[4] = {G.x, G.y, G.z, G.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+                const float2 sf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sv[i]));
+                const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ov[i]));
+                const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gv[i]));
+                w[i] = pack_bf16(__fsub_rn(__fsub_rn(xf.x, sf.x), __fsub_rn(of.x, gf.x)), __fsub_rn(__fsub_rn(xf.y, sf.y), __fsub_rn(of.y, gf.y)));
+              }
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)__ldg(p.pair_row + o_img) * map_elems + cell_off;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            } else {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                                   (((long long)o_img * (p.H / 2) + py) * (p.W / 2) + px) * p.ldc + p.c_off + cbase;
+              *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
           } else {
             // output row of tile row `tr` (plain: GEMM row; conv: NHWC pixel index), -1 when outside M
             auto out_row = [&](int tr) -> long long {
@@ -479,7 +542,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               long long row = (long long)(m_blk * MS + j) * BM + tr;
               return row < p.M ? row : -1;
             };
-            const long long row = out_row(row_in_tile);
+            const long long grow = out_row(row_in_tile);          // GEMM row (indexes mul / the row gathers)
+            const long long row = (grow >= 0 && p.out_rows) ? (long long)__ldg(p.out_rows + grow) : grow;   // output row
             if (p.epi == HC_EPI_F32) {
               if (row >= 0) {
                 float* dst = reinterpret_cast<float*>(p.out) + row * p.ldc + p.c_off + col0;
@@ -493,7 +557,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
                   }
                   if (p.mul) {
-                    float4 mm = __ldg(reinterpret_cast<const float4*>(p.mul + row * p.ld_mul + col0 + 4 * i));
+                    float4 mm = __ldg(reinterpret_cast<const float4*>(p.mul + grow * p.ld_mul + col0 + 4 * i));
                     v.x *= mm.x; v.y *= mm.y; v.z *= mm.z; v.w *= mm.w;
                   }
                   *reinterpret_cast<float4*>(dst + 4 * i) = v;
@@ -519,8 +583,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                     for (int t = 0; t < 8; ++t) v[t] = fmaxf(v[t], 0.0f);
                   }
                   if (p.mul) {
-                    const float4 m0 = __ldg(reinterpret_cast<const float4*>(p.mul + row * p.ld_mul + col0) + 2 * i);
-                    const float4 m1 = __ldg(reinterpret_cast<const float4*>(p.mul + row * p.ld_mul + col0) + 2 * i + 1);
+                    const float4 m0 = __ldg(reinterpret_cast<const float4*>(p.mul + grow * p.ld_mul + col0) + 2 * i);
+                    const float4 m1 = __ldg(reinterpret_cast<const float4*>(p.mul + grow * p.ld_mul + col0) + 2 * i + 1);
                     v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w; v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
                   }
                   uint32_t hi[4], lo[4];
@@ -539,7 +603,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             } else {
               if (row >= 0) {
                 __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + p.c_off + col0;
-                const float* mul_row = p.mul ? p.mul + row * p.ld_mul + col0 : nullptr;
+                const float* mul_row = p.mul ? p.mul + grow * p.ld_mul + col0 : nullptr;
+                if (p.add_a) {
+                  // shared-footprint fc1: the per-box fc1 rows of this pair's subject and object join the accumulator in fp32
+                  const float* ra = p.add_a + (long long)__ldg(p.add_a_rows + grow) * p.ld_add + col0;
+                  const float* rb = p.add_b + (long long)__ldg(p.add_b_rows + grow) * p.ld_add + col0;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(ra) + i), b4 = __ldg(reinterpret_cast<const float4*>(rb) + i);
+                    r[4 * i] = __float_as_uint(__uint_as_float(r[4 * i]) + (a4.x + b4.x));
+                    r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + (a4.y + b4.y));
+                    r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + (a4.z + b4.z));
+                    r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + (a4.w + b4.w));
+                  }
+                }
                 // the activation switch is hoisted out of the element loops (a branch per element serialises the
                 // single epilogue warp of each scheduler)
                 if (p.act == HC_ACT_RELU) store_bf16_row<HC_ACT_RELU>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst);
@@ -628,14 +705,26 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   HC_REQUIRE(aligned16(d->a) && aligned16(d->b) && aligned16(d->out), HC_E_ALIGN, "hc_tc_gemm: a/b/out must be 16-byte aligned");
   HC_REQUIRE(d->ldc % 8 == 0 && d->c_off % 8 == 0, HC_E_ALIGN, "hc_tc_gemm: ldc and c_off must be multiples of 8");
   HC_REQUIRE(!d->bias || aligned16(d->bias), HC_E_ALIGN, "hc_tc_gemm: bias must be 16-byte aligned");
-  HC_REQUIRE(d->epilogue >= 0 && d->epilogue <= 3, HC_E_SHAPE, "hc_tc_gemm: unknown epilogue");
+  HC_REQUIRE(d->epilogue >= 0 && d->epilogue <= 4, HC_E_SHAPE, "hc_tc_gemm: unknown epilogue");
   HC_REQUIRE(d->epilogue != HC_EPI_SPLIT3_BF16 || (d->mode == HC_GEMM_PLAIN && d->act != HC_ACT_TANH && d->ldc >= 3 * d->n), HC_E_SHAPE,
              "hc_tc_gemm: the bf16x3 split epilogue needs a plain GEMM, no tanh and ldc >= 3*N");
-  HC_REQUIRE(d->epilogue != HC_EPI_POOL_BF16 || ((d->mode == HC_GEMM_CONV3 || d->mode == HC_GEMM_CONV3_BLOCKS) && d->bias), HC_E_SHAPE,
+  const bool pooled = d->epilogue == HC_EPI_POOL_BF16 || d->epilogue == HC_EPI_POOL_DIFF_BF16;
+  HC_REQUIRE(!pooled || ((d->mode == HC_GEMM_CONV3 || d->mode == HC_GEMM_CONV3_BLOCKS) && d->bias), HC_E_SHAPE,
              "hc_tc_gemm: pooled epilogue needs conv mode and a bias");
-  HC_REQUIRE(d->mode != HC_GEMM_CONV3_BLOCKS ||
-                 (d->epilogue == HC_EPI_POOL_BF16 && d->blocks && d->n_blocks && (d->block_rows == 8 || d->block_rows == 4)),
+  HC_REQUIRE(d->mode != HC_GEMM_CONV3_BLOCKS || (pooled && d->blocks && d->n_blocks && (d->block_rows == 8 || d->block_rows == 4)),
              HC_E_SHAPE, "hc_tc_gemm: block-sparse conv needs the pooled epilogue, a work list and block_rows in {4, 8}");
+  HC_REQUIRE(d->epilogue != HC_EPI_POOL_DIFF_BF16 ||
+                 (d->mode == HC_GEMM_CONV3_BLOCKS && d->diff_sub && d->diff_obj && d->diff_bg && d->pair_sub && d->pair_obj && d->pair_row &&
+                  aligned16(d->diff_sub) && aligned16(d->diff_obj) && aligned16(d->diff_bg)),
+             HC_E_SHAPE, "hc_tc_gemm: the pooled-difference epilogue needs block mode, three 16-byte aligned maps and the three pair index arrays");
+  HC_REQUIRE(!d->k_masks || (d->mode == HC_GEMM_PLAIN && d->k_cell > 0 && d->k_cell % tc::BK == 0 && d->k % d->k_cell == 0 && d->k / d->k_cell <= 64),
+             HC_E_SHAPE, "hc_tc_gemm: k_masks needs a plain GEMM and k_cell a multiple of 64 with K / k_cell <= 64");
+  HC_REQUIRE((!d->add_a && !d->add_b) || (d->add_a && d->add_b && d->add_a_rows && d->add_b_rows && d->mode == HC_GEMM_PLAIN &&
+                                          d->epilogue == HC_EPI_BF16 && d->ld_add % 4 == 0 && d->ld_add >= d->n && aligned16(d->add_a) &&
+                                          aligned16(d->add_b)),
+             HC_E_SHAPE, "hc_tc_gemm: row gathers need a plain bf16-epilogue GEMM, both f32 tables (16-byte aligned, ld_add % 4 == 0) and both index arrays");
+  HC_REQUIRE(!d->out_rows || (d->mode == HC_GEMM_PLAIN && !d->mul && d->epilogue != HC_EPI_SPLIT3_BF16), HC_E_SHAPE,
+             "hc_tc_gemm: out_rows needs a plain GEMM without mul and a bf16 / f32 epilogue");
   HC_REQUIRE(d->m < (1ll << 31) && d->n < (1ll << 31) && d->k < (1ll << 31), HC_E_SHAPE, "hc_tc_gemm: dims exceed int32");
 
   const int BN = (d->n % 256 == 0) ? 256 : 128;
@@ -650,7 +739,13 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   p.mul = d->mul; p.ld_mul = d->ld_mul;
   p.patch = d->mode == HC_GEMM_CONV3 ? 1 : 0;
   p.blocks = d->blocks; p.n_blocks = d->n_blocks; p.blk_h = d->block_rows;
-  HC_REQUIRE(!d->mul || (d->epilogue != HC_EPI_POOL_BF16 && d->mode == HC_GEMM_PLAIN && d->ld_mul % 4 == 0 && aligned16(d->mul)), HC_E_SHAPE,
+  p.k_masks = reinterpret_cast<const unsigned long long*>(d->k_masks); p.k_cell_kb = d->k_masks ? (int)(d->k_cell / tc::BK) : 0;
+  p.add_a = d->add_a; p.add_a_rows = d->add_a_rows; p.add_b = d->add_b; p.add_b_rows = d->add_b_rows; p.ld_add = d->ld_add;
+  p.out_rows = d->out_rows;
+  p.diff_sub = reinterpret_cast<const __nv_bfloat16*>(d->diff_sub); p.diff_obj = reinterpret_cast<const __nv_bfloat16*>(d->diff_obj);
+  p.diff_bg = reinterpret_cast<const __nv_bfloat16*>(d->diff_bg);
+  p.pair_sub = d->pair_sub; p.pair_obj = d->pair_obj; p.pair_row = d->pair_row;
+  HC_REQUIRE(!d->mul || (!pooled && d->mode == HC_GEMM_PLAIN && d->ld_mul % 4 == 0 && aligned16(d->mul)), HC_E_SHAPE,
              "hc_tc_gemm: mul needs a plain GEMM, a non-pooled epilogue and a 16-byte aligned [M, ld_mul] f32 operand");
   p.tiles_n = p.N / BN;
 
@@ -672,7 +767,7 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
                "hc_tc_gemm: conv channel slice must be 64-aligned inside c_total");
     HC_REQUIRE(d->k == 9ll * d->c_in, HC_E_SHAPE, "hc_tc_gemm: conv needs K == 9*c_in");
     HC_REQUIRE(d->m == (int64_t)d->n_img * d->h * d->w, HC_E_SHAPE, "hc_tc_gemm: conv needs M == n_img*H*W");
-    HC_REQUIRE(d->epilogue != HC_EPI_POOL_BF16 || (d->h % 2 == 0 && d->w % 2 == 0), HC_E_SHAPE, "hc_tc_gemm: pooling needs even H,W");
+    HC_REQUIRE(!pooled || (d->h % 2 == 0 && d->w % 2 == 0), HC_E_SHAPE, "hc_tc_gemm: pooling needs even H,W");
     p.H = d->h; p.W = d->w; p.c_in = d->c_in; p.c_base = d->c_base;
     p.tiles_x = d->w / 16; p.tiles_y = d->h / (8 * MS);
     p.tiles_m = d->n_img * p.tiles_x * p.tiles_y;

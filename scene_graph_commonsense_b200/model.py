@@ -16,7 +16,8 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, GEMM_CONV3, GEMM_CONV3_BLOCKS, GEMM_PLAIN
+from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_POOL_DIFF_BF16, GEMM_CONV3, GEMM_CONV3_BLOCKS,
+                   GEMM_PLAIN)
 
 K1_PAD = 320      # 257 input channels of the 1x1 convolutions, zero padded to a multiple of 64
 HIDDEN = 512
@@ -130,6 +131,32 @@ class PackedHead:
                     n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag=tag, blocks=blocks,
                     n_blocks=n_blocks, block_rows=block_rows)
         return p3
+
+    def conv3_diff(self, p2, d, n, blocks, n_blocks, block_rows, sub_maps, obj_maps, pair_sub, pair_obj, pair_row, m_sub=2, tag="conv3"):
+        """conv3_1+ReLU+pool on the listed blocks of p2 [>=n,16,16,512]; local pair i's cells go to row pair_row[i] of d [rows,8,8,1024]
+        as the DIFFERENCE to its per-box maps, (x - sub_maps[pair_sub[i]]) - (obj_maps[pair_obj[i]] - background): the operand of
+        the shared-footprint fc1 (`fc1_shared_fc2`), exactly zero wherever only one box of the pair reaches."""
+        ops.tc_gemm(p2, self.w3, d, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_DIFF_BF16,
+                    n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag=tag, blocks=blocks,
+                    n_blocks=n_blocks, block_rows=block_rows, diff_sub=sub_maps, diff_obj=obj_maps, diff_bg=self.p3_background(),
+                    pair_sub=pair_sub, pair_obj=pair_obj, pair_row=pair_row)
+        return d
+
+    def fc1_rows(self, maps, n):
+        """fc1 WITHOUT bias / activation of n pooled maps [n,8,8,1024] bf16 -> f32 [n,4096] (the per-box terms of the shared fc1)."""
+        out = torch.empty(n, 4096, dtype=torch.float32, device=maps.device)
+        ops.tc_gemm(maps, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=37, m_sub=2 if n > 128 else 1,
+                    tag="fc1_box")
+        return out
+
+    def fc1_shared_fc2(self, d, n, k_masks, f_sub, f_obj, row_sub, row_obj, bias_eff, out_rows, raw):
+        """model.py:149,175 on the difference operand d [n,8,8,1024] (rows in sorted order, zero outside the cells both boxes reach):
+        h1 = relu(d @ W1^T [only the cells in the tile's mask] + f_sub[row_sub] + f_obj[row_obj] + bias_eff), raw[out_rows] = h1 @ W2^T."""
+        h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=d.device)
+        ops.tc_gemm(d, self.w_fc1, h1, n, 4096, 65536, bias=bias_eff, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU, group_m=37,
+                    m_sub=2, tag="fc1", k_masks=k_masks, k_cell=1024, add_a=f_sub, add_a_rows=row_sub, add_b=f_obj, add_b_rows=row_obj)
+        ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8, tag="fc2", out_rows=out_rows)
+        return raw
 
     def conv3_fc(self, p2, m_sub=2, raw=None, n=None, blocks=None, n_blocks=None, block_rows=0, p3=None):
         """conv3_1+ReLU+pool -> fc1+ReLU -> fc2 (raw, fp32) on pooled conv2 activations p2 [>=n,16,16,512] bf16.

@@ -12,8 +12,8 @@ import torch
 from . import _abi_ops as _A
 from . import tables
 from ._abi_ops import LAUNCHES, PROFILE, cs_bitmap_build, pack_weight_bf16x3  # noqa: F401  (host-side helpers, no kernel)
-from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_SPLIT3_BF16, GEMM_CONV3,  # noqa: F401
-                   GEMM_CONV3_BLOCKS, GEMM_PLAIN)
+from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_BF16, EPI_F32, EPI_POOL_BF16, EPI_POOL_DIFF_BF16, EPI_SPLIT3_BF16,  # noqa: F401
+                   GEMM_CONV3, GEMM_CONV3_BLOCKS, GEMM_PLAIN)
 
 NAMESPACE = "hiercom"
 _LIB = torch.library.Library(NAMESPACE, "DEF")
@@ -58,20 +58,27 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 # ------------------------------------------------------------------------------------------------ R5/R6 dense contractions
 @_op("tc_gemm", "(Tensor a, Tensor b, Tensor(a!) out, int m, int n, int k, Tensor? bias, Tensor? mul, int lda, int ldc, int c_off, "
      "int mode, int epilogue, int act, int n_img, int h, int w, int c_total, int c_base, int c_in, int group_m, int m_sub, "
-     "str tag, Tensor? blocks, Tensor? n_blocks, int block_rows) -> ()")
+     "str tag, Tensor? blocks, Tensor? n_blocks, int block_rows, Tensor? k_masks, int k_cell, Tensor? add_a, Tensor? add_a_rows, "
+     "Tensor? add_b, Tensor? add_b_rows, Tensor? out_rows, Tensor? diff_sub, Tensor? diff_obj, Tensor? diff_bg, Tensor? pair_sub, "
+     "Tensor? pair_obj, Tensor? pair_row) -> ()")
 def _tc_gemm(a, b, out, m, n, k, bias, mul, lda, ldc, c_off, mode, epilogue, act, n_img, h, w, c_total, c_base, c_in, group_m, m_sub,
-             tag, blocks, n_blocks, block_rows):
+             tag, blocks, n_blocks, block_rows, k_masks, k_cell, add_a, add_a_rows, add_b, add_b_rows, out_rows, diff_sub, diff_obj,
+             diff_bg, pair_sub, pair_obj, pair_row):
     _A.tc_gemm(a, b, out, m, n, k, bias=bias, lda=lda, ldc=ldc, c_off=c_off, mode=mode, epilogue=epilogue, act=act, n_img=n_img, h=h,
                w=w, c_total=c_total, c_base=c_base, c_in=c_in, group_m=group_m, m_sub=m_sub, tag=tag, mul=mul, blocks=blocks,
-               n_blocks=n_blocks, block_rows=block_rows)
+               n_blocks=n_blocks, block_rows=block_rows, k_masks=k_masks, k_cell=k_cell, add_a=add_a, add_a_rows=add_a_rows, add_b=add_b,
+               add_b_rows=add_b_rows, out_rows=out_rows, diff_sub=diff_sub, diff_obj=diff_obj, diff_bg=diff_bg, pair_sub=pair_sub,
+               pair_obj=pair_obj, pair_row=pair_row)
 
 
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16, act=ACT_NONE, n_img=0,
             h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None, blocks=None, n_blocks=None,
-            block_rows=0):
+            block_rows=0, k_masks=None, k_cell=0, add_a=None, add_a_rows=None, add_b=None, add_b_rows=None, out_rows=None, diff_sub=None,
+            diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None):
     """out = epilogue(A @ B^T) on tcgen05 (include/hiercom_b200.h hc_tc_gemm)."""
     _call("tc_gemm")(a, b, out, m, n, k, bias, mul, lda, n if ldc is None else ldc, c_off, mode, epilogue, act, n_img, h, w, c_total,
-                     c_base, c_in, group_m, m_sub, tag, blocks, n_blocks, block_rows)
+                     c_base, c_in, group_m, m_sub, tag, blocks, n_blocks, block_rows, k_masks, k_cell, add_a, add_a_rows, add_b, add_b_rows,
+                     out_rows, diff_sub, diff_obj, diff_bg, pair_sub, pair_obj, pair_row)
     return out
 
 
@@ -116,6 +123,36 @@ def _p3_assemble(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out,
 
 def p3_assemble(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, fs=32):
     _call("p3_assemble")(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, fs)
+    return out
+
+
+@_op("pair_cell_keys", "(Tensor boxes, Tensor pair_sub, Tensor pair_obj, int fs) -> Tensor")
+def _pair_cell_keys(boxes, pair_sub, pair_obj, fs):
+    return _A.pair_cell_keys(boxes, pair_sub, pair_obj, fs)
+
+
+def pair_cell_keys(boxes, pair_sub, pair_obj, fs=32):
+    """Sort key of the cell rectangle both boxes of each directed pair reach (row order of the shared-footprint fc1)."""
+    return _call("pair_cell_keys")(boxes, pair_sub, pair_obj, fs)
+
+
+@_op("tile_cell_masks", "(Tensor boxes, Tensor row_sub, Tensor row_obj, int rows_per_tile, int fs) -> Tensor")
+def _tile_cell_masks(boxes, row_sub, row_obj, rows_per_tile, fs):
+    return _A.tile_cell_masks(boxes, row_sub, row_obj, rows_per_tile, fs)
+
+
+def tile_cell_masks(boxes, row_sub, row_obj, rows_per_tile, fs=32):
+    """Per GEMM tile of `rows_per_tile` sorted rows: int64 bitmap of the K cells the tile visits (`k_masks` of tc_gemm)."""
+    return _call("tile_cell_masks")(boxes, row_sub, row_obj, rows_per_tile, fs)
+
+
+@_op("cells_zero", "(Tensor masks, int rows_per_tile, int n_rows, Tensor(a!) out) -> ()")
+def _cells_zero(masks, rows_per_tile, n_rows, out):
+    _A.cells_zero(masks, rows_per_tile, n_rows, out)
+
+
+def cells_zero(masks, rows_per_tile, n_rows, out):
+    _call("cells_zero")(masks, rows_per_tile, n_rows, out)
     return out
 
 

@@ -139,7 +139,8 @@ class RelationPipeline:
 
     def __init__(self, packed: Optional[PackedHead], device, commonsense=True, aligned_keys=None, violated_keys=None,
                  top_k=tables.TOP_K, iou_thresh=0.5, feature_size=32, chunk_pairs=16384, predcls=True, conv3_m_sub=2,
-                 hier=None, splits=None, overlap=True, conv2_m_sub=1, chunk_policy="waves", conv3_block_rows=4, conv3_shared=True):
+                 hier=None, splits=None, overlap=True, conv2_m_sub=1, chunk_policy="waves", conv3_block_rows=4, conv3_shared=True,
+                 fc1_shared=True):
         self.packed = packed
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -162,7 +163,13 @@ class RelationPipeline:
         # box's own map ((box, empty) / (empty, box), computed once per box of the window), so a pair computes only the cells
         # BOTH boxes reach.  False: every cell either box reaches is computed per pair.  Same bits either way.
         self.conv3_shared = bool(conv3_shared) and self.conv3_block_rows > 0
+        # shared-footprint fc1 (needs conv3_shared): fc1 is linear, so fc1(pair) = fc1(subject map) + fc1(object map) - fc1(background)
+        # + fc1(d), d = the pair's conv3_1 output minus those maps, non-zero only in the cells BOTH boxes reach.  Rows are sorted by
+        # that cell rectangle and the GEMM visits, per 256-row tile, only the K cells some row of the tile uses (exact: the skipped
+        # operand is zero).  Same sums up to fp32 rounding order and one bf16 rounding of d - not bit-identical to the dense fc1.
+        self.fc1_shared = bool(fc1_shared) and self.conv3_shared
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
+        self.last_k_masks = None             # int64 [n_tiles] device tensor: K-cell masks of the last shared fc1
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
         self.hier = (not packed.flat if packed is not None else True) if hier is None else bool(hier)
         self.pass_bitmap = None
@@ -194,7 +201,7 @@ class RelationPipeline:
         abox = ops.box_select(t, boxes, box_img, pk.fill, fs)
         return pk.conv2_halves(abox, m_sub=self.conv2_m_sub)
 
-    def box_maps(self, boxes_x, u, v):
+    def box_maps(self, boxes_x, u, v, with_background_row=False):
         """Pooled conv3_1 output of every box of the window paired with the EMPTY box (the last row of boxes_x / u / v):
         -> sub_maps = (box, empty), obj_maps = (empty, box), each [n_box,8,8,1024] bf16, and the work-list lengths.  A real
         pair's output equals sub_maps[s] in the cells only its subject's box reaches and obj_maps[o] in those only its object's
@@ -204,7 +211,9 @@ class RelationPipeline:
         idx = torch.arange(n_box, dtype=torch.int32, device=self.device)
         empty = torch.full((n_box,), n_box, dtype=torch.int32, device=self.device)
         sub, obj = torch.cat((idx, empty)), torch.cat((empty, idx))
-        maps = torch.empty(2 * n_box, 8, 8, 1024, dtype=torch.bfloat16, device=self.device)
+        maps = torch.empty(2 * n_box + (1 if with_background_row else 0), 8, 8, 1024, dtype=torch.bfloat16, device=self.device)
+        if with_background_row:             # row 2*n_box = the background itself (its fc1 row is the "- fc1(background)" term)
+            maps[2 * n_box:].copy_(pk.p3_background())
         starts = list(range(0, 2 * n_box, self.chunk_pairs))
         nblk = torch.zeros(max(len(starts), 1), dtype=torch.int32, device=self.device)
         for k, s in enumerate(starts):
@@ -214,6 +223,8 @@ class RelationPipeline:
             ops.broadcast_rows(pk.p3_background(), e - s, maps[s:e])
             pk.conv3_blocks(p2, maps[s:e], e - s, blocks, nblk[k:k + 1], br, m_sub=self.conv3_m_sub, tag="conv3_box")
             del p2
+        if with_background_row:
+            return maps, nblk
         return maps[:n_box], maps[n_box:], nblk
 
     @staticmethod
@@ -274,6 +285,8 @@ class RelationPipeline:
         pk = self.packed
         n = pairs["n"]
         br, shared = self.conv3_block_rows, self.conv3_shared
+        if self.fc1_shared and n > 0:
+            return self._forward_pairs_fc1_shared(b, pairs)
         if shared:      # one more box per window: the empty one (all background), partner of every box in `box_maps`
             boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))
             u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))))
@@ -358,6 +371,78 @@ class RelationPipeline:
                 main.wait_stream(side)
             if br:
                 self.last_n_blocks = nblk if nblk_box is None else torch.cat((nblk, nblk_box))
+        relation, sup, conn, logsig, _ = pk.heads(raw, pairs["sub"], pairs["obj"], b.cats, b.supers)
+        return relation, sup, conn, logsig
+
+    def _forward_pairs_fc1_shared(self, b: DeviceBatch, pairs):
+        """`forward_pairs` with the shared-footprint fc1: per-box conv3_1 maps and their fc1 rows once per box; per pair only the
+        conv3_1 blocks covering the cells both boxes reach, written as differences into the sorted operand d; ONE K-cell-sparse fc1
+        + fc2 over all pairs of the window; raw comes back in pair order through the fc2 epilogue's row map."""
+        pk, fs, br = self.packed, self.fs, self.conv3_block_rows
+        n, n_box = pairs["n"], b.boxes.shape[0]
+        dev = self.device
+        boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))      # + the empty box (all background), partner of every box
+        u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))))
+        maps, nblk_box = self.box_maps(boxes_x, u, v, with_background_row=True)
+        sub_maps, obj_maps = maps[:n_box], maps[n_box:2 * n_box]
+        f_box = pk.fc1_rows(maps, 2 * n_box + 1)                     # fc1 (no bias) of (box, empty), (empty, box), background
+        bias_eff = (pk.b_fc1 - f_box[2 * n_box]).contiguous()
+        # row order of the fc1 operand: pairs sorted by the cell rectangle both boxes reach (pairs with none last)
+        keys = ops.pair_cell_keys(b.boxes, pairs["sub"], pairs["obj"], fs)
+        perm64 = torch.sort(keys, stable=True)[1]                    # sorted row -> pair
+        perm = perm64.to(torch.int32)
+        row_of = torch.empty_like(perm)
+        row_of[perm64] = torch.arange(n, dtype=torch.int32, device=dev)
+        row_sub, row_obj = pairs["sub"][perm64].contiguous(), pairs["obj"][perm64].contiguous()
+        masks = ops.tile_cell_masks(b.boxes, row_sub, row_obj, 256, fs)
+        d = torch.empty(n, 64, 1024, dtype=torch.bfloat16, device=dev)
+        ops.cells_zero(masks, 256, n, d)
+        tiled = "offsets_host" in pairs
+        if tiled:
+            n_max = int(np.max(np.diff(b.box_offsets_host))) if b.box_offsets_host is not None else int(
+                (b.box_offsets[1:] - b.box_offsets[:-1]).max().item())
+            lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
+            chunks = self._image_chunks(pairs["offsets_host"])
+        else:
+            chunks = [(0, 0, s, min(n, s + self.chunk_pairs) - s) for s in range(0, n, self.chunk_pairs)]
+        cap = max(c[3] for c in chunks)
+        two = self.overlap and len(chunks) > 1
+        bufs = [torch.empty(cap, fs // 2, fs // 2, 512, dtype=torch.bfloat16, device=dev) for _ in range(2 if two else 1)]
+        blk_bufs = [torch.empty(cap * (32 // br), dtype=torch.int32, device=dev) for _ in bufs]
+        nblk = torch.zeros(len(chunks), dtype=torch.int32, device=dev)
+        main = torch.cuda.current_stream()
+        side = self._side_stream() if two else main
+        ready = torch.cuda.Event()
+        ready.record(main)
+        gemm_done = []
+        for k, (img0, n_img, base, cnt) in enumerate(chunks):
+            buf, blk = bufs[k % len(bufs)], blk_bufs[k % len(bufs)]
+            sub_k, obj_k = pairs["sub"][base:base + cnt], pairs["obj"][base:base + cnt]
+            with torch.cuda.stream(side):
+                if side is not main:
+                    side.wait_event(ready)
+                    if k >= 2:
+                        side.wait_event(gemm_done[k - 2])              # buffer free again
+                if tiled:
+                    ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, fs, out=buf)
+                else:
+                    ops.pair_relu_pool(u, v, None, sub_k, obj_k, fs, out=buf)
+                ops.conv3_shared_blocks(b.boxes, sub_k, obj_k, br, fs, blocks=blk, n_blocks=nblk[k:k + 1])
+                pooled = torch.cuda.Event()
+                pooled.record(side)
+            if side is not main:
+                main.wait_event(pooled)
+            pk.conv3_diff(buf, d, cnt, blk, nblk[k:k + 1], br, sub_maps, obj_maps, sub_k, obj_k, row_of[base:base + cnt],
+                          m_sub=self.conv3_m_sub)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            gemm_done.append(ev)
+        if side is not main:
+            main.wait_stream(side)
+        raw = torch.empty(n, 512, dtype=torch.float32, device=dev)
+        pk.fc1_shared_fc2(d, n, masks, f_box[:n_box], f_box[n_box:], row_sub, row_obj, bias_eff, perm, raw)
+        self.last_n_blocks = torch.cat((nblk, nblk_box))
+        self.last_k_masks = masks
         relation, sup, conn, logsig, _ = pk.heads(raw, pairs["sub"], pairs["obj"], b.cats, b.supers)
         return relation, sup, conn, logsig
 

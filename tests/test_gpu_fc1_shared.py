@@ -1,0 +1,159 @@
+"""GPU tests of the shared-footprint fc1: fc1 (model.py:149) is linear, so a pair's fc1 = fc1(subject map) + fc1(object map)
+- fc1(background) + fc1(d), d = the pair's pooled conv3_1 output minus those maps (zero outside the cells both boxes reach), and
+the GEMM over d visits only the K cells a tile's rows use.  Bars: the K-cell-sparse GEMM equals the dense GEMM on the same operand
+bit for bit; the difference epilogue equals the fp32 formula on the dense kernel's output bit for bit; the whole path stays within
+north_star's 2e-3 on joint probabilities of the dense path, whose parity with the fp32 reference tests/test_gpu_model.py holds."""
+import numpy as np
+import pytest
+import torch
+
+from scene_graph_commonsense_b200 import synthetic
+from tests.test_gpu_sparse import EDGE_BOXES, _cell_mask, _packed, _random_boxes
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("m,with_tables", [(700, False), (700, True), (100, True), (1024, True)])
+def test_k_cell_sparse_gemm_equals_dense_bit_for_bit(m, with_tables):
+    from scene_graph_commonsense_b200 import ops
+    from scene_graph_commonsense_b200._lib import ACT_RELU, EPI_BF16, EPI_F32
+    g = torch.Generator().manual_seed(m)
+    n_cells, cell, n = 16, 128, 512
+    k = n_cells * cell
+    a = torch.randn(m, n_cells, cell, generator=g)
+    use = torch.rand(m, n_cells, generator=g) < 0.25
+    use[256:512] = False                                   # a whole 256-row tile with nothing to do
+    if m > 600:
+        use[600:, :] = False
+        use[600:, 3] = True
+    a = (a * use[:, :, None]).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n, k, generator=g) / 16).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    n_tiles = -(-m // 256)
+    masks = torch.zeros(n_tiles, dtype=torch.int64)
+    for t in range(n_tiles):
+        bits = use[256 * t:256 * (t + 1)].any(0)
+        masks[t] = int(sum(1 << c for c in range(n_cells) if bits[c]))
+    assert int(masks[1]) == 0 if n_tiles > 1 else True
+    masks = masks.to(DEV)
+    kw = {}
+    if with_tables:
+        fa, fb = torch.randn(37, n, generator=g).to(DEV), torch.randn(41, n, generator=g).to(DEV)
+        ia = torch.randint(0, 37, (m,), generator=g, dtype=torch.int32).to(DEV)
+        ib = torch.randint(0, 41, (m,), generator=g, dtype=torch.int32).to(DEV)
+        kw = dict(add_a=fa, add_a_rows=ia, add_b=fb, add_b_rows=ib)
+    outs = []
+    for km in (None, masks):
+        o = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.tc_gemm(a, w, o, m, n, k, bias=bias, lda=k, ldc=n, epilogue=EPI_BF16, act=ACT_RELU, group_m=3, m_sub=2,
+                    k_masks=km, k_cell=cell if km is not None else 0, **kw)
+        outs.append(o)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+    ref = a.float().view(m, k) @ w.float().t() + bias
+    if with_tables:
+        ref = ref + fa[ia.long()] + fb[ib.long()]
+    ref = torch.relu(ref)
+    assert float((outs[1].float() - ref).abs().max()) <= 0.02 * float(ref.abs().max()) + 1e-2
+    # row map of the f32 epilogue (fc2 writes raw back in pair order)
+    perm = torch.randperm(m, generator=g).to(torch.int32).to(DEV)
+    o1 = torch.empty(m, n, dtype=torch.float32, device=DEV)
+    o2 = torch.full((m, n), float("nan"), dtype=torch.float32, device=DEV)
+    ops.tc_gemm(a, w, o1, m, n, k, lda=k, ldc=n, epilogue=EPI_F32, m_sub=2)
+    ops.tc_gemm(a, w, o2, m, n, k, lda=k, ldc=n, epilogue=EPI_F32, m_sub=2, out_rows=perm, k_masks=masks, k_cell=cell)
+    torch.cuda.synchronize()
+    assert torch.equal(o2[perm.long()], o1)
+
+
+@pytest.mark.parametrize("block_rows", [8, 4])
+def test_difference_epilogue_and_keys(block_rows):
+    """HC_EPI_POOL_DIFF_BF16 == (x - sub_map) - (obj_map - background) on the dense kernel's x, bit for bit, at row pair_row[i]; zero in
+    every covered cell that only one box reaches; keys / tile masks describe the cell rectangles both boxes reach."""
+    from scene_graph_commonsense_b200 import ops
+    from scene_graph_commonsense_b200._lib import EPI_POOL_BF16, GEMM_CONV3
+    pk = _packed()
+    boxes = _random_boxes(24, 17)
+    n_box = boxes.shape[0]
+    boxes_x = torch.cat((boxes, boxes.new_zeros(1, 4))).to(DEV)
+    g = torch.Generator().manual_seed(4)
+    t_img = torch.tanh(torch.randn(1, 32 * 32, 256, generator=g)).to(torch.bfloat16).to(DEV)
+    abox = ops.box_select(t_img, boxes_x, torch.zeros(n_box + 1, dtype=torch.int32, device=DEV), pk.fill, 32)
+    u, v = pk.conv2_halves(abox)
+    sub, obj = np.nonzero(~np.eye(n_box, dtype=bool))
+    sub_t = torch.from_numpy(sub.astype(np.int32)).to(DEV)
+    obj_t = torch.from_numpy(obj.astype(np.int32)).to(DEV)
+    n = sub_t.numel()
+    p2 = ops.pair_relu_pool(u, v, None, sub_t, obj_t, 32)
+    dense = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=DEV)
+    ops.tc_gemm(p2, pk.w3, dense, n * 256, 1024, 9 * 512, bias=pk.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16, n_img=n, h=16,
+                w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=2)
+    idx = torch.arange(n_box, dtype=torch.int32, device=DEV)
+    emp = torch.full((n_box,), n_box, dtype=torch.int32, device=DEV)
+    s1, o1 = torch.cat((idx, emp)), torch.cat((emp, idx))
+    p2b = ops.pair_relu_pool(u, v, None, s1, o1, 32)
+    blk1, nb1 = ops.conv3_active_blocks(boxes_x, s1, o1, block_rows)
+    maps = ops.broadcast_rows(pk.p3_background(), 2 * n_box, torch.empty(2 * n_box, 8, 8, 1024, dtype=torch.bfloat16, device=DEV))
+    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows)
+    sub_maps, obj_maps, bg = maps[:n_box], maps[n_box:], pk.p3_background()
+    # keys and sorted order
+    keys = ops.pair_cell_keys(boxes_x, sub_t, obj_t).cpu().numpy()
+    masks_np = np.stack([_cell_mask(b) for b in boxes.numpy()])
+    want = masks_np[sub] & masks_np[obj]                                       # [n, 8, 8]
+    for p in range(n):
+        if not want[p].any():
+            assert keys[p] == 4096
+        else:
+            ys, xs = np.nonzero(want[p].any(1))[0], np.nonzero(want[p].any(0))[0]
+            assert keys[p] == ((ys[0] * 8 + ys[-1]) * 8 + xs[0]) * 8 + xs[-1]
+    perm = torch.sort(torch.from_numpy(keys).to(DEV), stable=True)[1]
+    row_of = torch.empty(n, dtype=torch.int32, device=DEV)
+    row_of[perm] = torch.arange(n, dtype=torch.int32, device=DEV)
+    tm = ops.tile_cell_masks(boxes_x, sub_t[perm].contiguous(), obj_t[perm].contiguous(), 256).cpu().numpy()
+    order = perm.cpu().numpy()
+    for t in range(len(tm)):
+        bits = want[order[256 * t:256 * (t + 1)]].any(0).reshape(-1)
+        assert int(tm[t]) == int(sum(1 << c for c in range(64) if bits[c])) - (1 << 64 if bits[63] else 0)
+    # difference epilogue into a poisoned, then tile-zeroed buffer
+    d = torch.full((n, 64, 1024), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.cells_zero(torch.from_numpy(tm).to(DEV), 256, n, d)
+    blocks, n_blocks = ops.conv3_shared_blocks(boxes_x, sub_t, obj_t, block_rows)
+    pk.conv3_diff(p2, d.view(n, 8, 8, 1024), n, blocks, n_blocks, block_rows, sub_maps, obj_maps, sub_t, obj_t, row_of)
+    torch.cuda.synchronize()
+    ref = ((dense.float() - sub_maps[sub_t.long()].float()) - (obj_maps[obj_t.long()].float() - bg.float())).to(torch.bfloat16)
+    got = d.view(n, 8, 8, 1024)[row_of.long()]                                 # back in pair order
+    want_t = torch.from_numpy(want).to(DEV)
+    tile_bits = torch.from_numpy(np.stack([[(int(tm[t]) >> c) & 1 for c in range(64)] for t in range(len(tm))]).astype(bool)).to(DEV)
+    visited = tile_bits[(row_of.long() // 256)].view(n, 8, 8)                   # cells the GEMM will read for this pair's row
+    assert not torch.isnan(got.float())[visited].any()                         # every visited cell was written (zero fill or epilogue)
+    both = want_t[..., None].expand_as(ref)
+    assert torch.equal(got[both].view(torch.int16), ref[both].view(torch.int16))
+    only_visited = (visited & ~want_t)[..., None].expand_as(ref)
+    assert float(got[only_visited].float().abs().max()) == 0.0                 # one-box / background cells: exactly zero
+    assert float(ref[~both].float().abs().max()) == 0.0                        # and the dense formula agrees they are zero
+
+
+@pytest.mark.parametrize("tiled", [True, False])
+def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled):
+    """Whole forward, chunked and overlapped: joint probabilities within 2e-3 of the dense path (north_star's fp tolerance)."""
+    from scene_graph_commonsense_b200 import pipeline
+    pk = _packed(gain=40.0)
+    samples = synthetic.make_batch([70, 71, 72, 73, 74, 75], [9, 1, 12, 7, 10, 40], p_rel=0.5)
+    samples[0].bbox[:6] = torch.tensor(EDGE_BOXES[:6], dtype=samples[0].bbox.dtype)
+    outs = []
+    for fc1_shared in (False, True):
+        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=700, conv3_block_rows=4, conv3_shared=True,
+                                         fc1_shared=fc1_shared)
+        b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
+        pairs = pipe.enumerate_pairs(b)
+        if not tiled:
+            pairs = {k: val for k, val in pairs.items() if k != "offsets_host"}
+        rel, sup, conn, logsig = pipe.forward_pairs(b, pairs)
+        torch.cuda.synchronize()
+        outs.append((rel.clone(), sup.clone(), conn.clone()))
+        if fc1_shared:
+            assert pipe.last_k_masks is not None and pipe.last_k_masks.numel() == -(-pairs["n"] // 256)
+    (rel0, sup0, conn0), (rel1, sup1, conn1) = outs
+    assert float((rel0.exp() - rel1.exp()).abs().max()) <= 2e-3
+    assert float((sup0.exp() - sup1.exp()).abs().max()) <= 2e-3
+    assert float((torch.sigmoid(conn0) - torch.sigmoid(conn1)).abs().max()) <= 2e-3

@@ -185,7 +185,7 @@ def test_pipeline_sparse_equals_dense(block_rows, shared):
     samples[0].bbox[:6] = torch.tensor(EDGE_BOXES[:6], dtype=samples[0].bbox.dtype)
     outs = []
     for br in (0, block_rows):
-        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=120, conv3_block_rows=br, conv3_shared=shared)
+        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=120, conv3_block_rows=br, conv3_shared=shared, fc1_shared=False)
         b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
         pairs = pipe.enumerate_pairs(b)
         rel, sup, conn, logsig = pipe.forward_pairs(b, pairs)
