@@ -92,7 +92,8 @@ class ClockSampler:
 
 # --conv3: dense kernel; block-sparse over the cells EITHER box of a pair reaches (8x8 / 8x4-pixel blocks); or "shared": per pair
 # only the cells BOTH boxes reach, the rest taken from per-box maps computed once per box (block_rows, shared)
-CONV3_MODES = {"dense": (0, False), "blocks8": (8, False), "blocks4": (4, False), "shared8": (8, True), "shared4": (4, True)}
+CONV3_MODES = {"dense": (0, False, 8), "blocks8": (8, False, 8), "blocks4": (4, False, 8), "shared8": (8, True, 8), "shared4": (4, True, 8),
+               "shared44": (4, True, 4)}       # name: (block rows, shared footprint, block columns) in conv3 pixels
 
 WORKLOADS = {
     # name: images per GPU, boxes (proposals) per image, SGDET-style?, pair chunk
@@ -182,7 +183,7 @@ def run_ours(args):
     pipe = pipeline.RelationPipeline(packed, dev, commonsense=True, chunk_pairs=chunk_pairs, conv3_m_sub=args.conv3_m_sub,
                                      overlap=not args.no_overlap, predcls=not wl["sgdet"], chunk_policy=args.chunk_policy,
                                      conv3_block_rows=CONV3_MODES[args.conv3][0], conv3_shared=CONV3_MODES[args.conv3][1],
-                                     fc1_shared=args.fc1 == "shared")
+                                     fc1_shared=args.fc1 == "shared", conv3_block_cols=CONV3_MODES[args.conv3][2])
     samples = make_samples(rank, wl["images"], wl["boxes"], sgdet=wl["sgdet"])
     host = pipeline.host_batch_from_samples(samples, skip_mode="batch", sgdet=wl["sgdet"])
     del samples
@@ -270,7 +271,7 @@ def run_ours(args):
     fc1 = per_tag.get("fc1", [])
     conv3_exec_frac = 1.0           # executed / dense-equivalent FLOPs of conv3_1 (block-sparse mode visits only listed blocks)
     if blocks_step is not None:
-        conv3_exec_frac = blocks_step * 8 * pipe.conv3_block_rows / (pairs_step * 256.0)
+        conv3_exec_frac = blocks_step * pipe.conv3_block_cols * pipe.conv3_block_rows / (pairs_step * 256.0)
 
     def roof_of(name, times, flop_step_kernel, extra):
         if not times:
@@ -368,7 +369,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="cfg2 = the configuration BASELINE.json's metric is quoted on (default); cfg3 = SGDET-shaped scaling case")
     ap.add_argument("--conv3-m-sub", type=int, default=2)
-    ap.add_argument("--conv3", default="shared4", choices=sorted(CONV3_MODES),
+    ap.add_argument("--conv3", default="shared44", choices=sorted(CONV3_MODES),
                     help="conv3_1 kernel: dense, or block-sparse over the dilated footprint of each pair's boxes (bit-identical output)")
     ap.add_argument("--fc1", default="shared", choices=["shared", "dense"],
                     help="shared = fc1 as per-box rows + a K-cell-sparse GEMM over the cells both boxes reach (needs --conv3 shared*); "

@@ -135,6 +135,7 @@ typedef struct hc_gemm_desc {
   const int32_t* blocks;   /* CONV3_BLOCKS: device work list */
   const int32_t* n_blocks; /* CONV3_BLOCKS: device scalar, number of entries */
   int32_t block_rows;      /* CONV3_BLOCKS: 8 or 4 */
+  int32_t block_cols;      /* CONV3_BLOCKS: 8 (or 0), or 4 with block_rows 4 */
   const uint64_t* k_masks; /* PLAIN: per CTA M tile, bitmap of visited K cells (NULL = dense) */
   int64_t k_cell;          /* PLAIN + k_masks: K elements per cell (multiple of 64, K / k_cell <= 64) */
   const float* add_a;      /* EPI_BF16 row gathers, both or neither */
@@ -161,9 +162,12 @@ int hc_tc_gemm(const hc_gemm_desc* desc, hc_stream_t stream);
  * its two boxes' cell rectangles.  This entry point covers that set greedily (first uncovered cell in row-major order, block
  * origin clamped into the map) with blocks of 4 x (block_rows/2) cells = 8 x block_rows conv3 pixels and writes the work list
  * HC_GEMM_CONV3_BLOCKS consumes: blocks[i] = local_pair << 8 | cell_y << 4 | cell_x, pairs in order, n_blocks[0] = count.
- * `blocks` must hold n_pairs * 64 / (2*block_rows) entries.  feature_size must be 32.  One CTA, deterministic order. */
+ * block_cols (0 = 8) is the block width in conv3 pixels: blocks are 8x8, 8x4 or 4x4 pixels (block_cols x block_rows) = 4x4, 4x2 or
+ * 2x2 cells; smaller blocks hug the cell rectangle more tightly (fewer computed pixels, more TMA boxes per tile).
+ * `blocks` must hold n_pairs * 256 / (block_rows*block_cols) entries.  feature_size must be 32.  One CTA, deterministic order. */
 int hc_conv3_active_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
-                           int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream);
+                           int32_t feature_size, int32_t block_rows, int32_t block_cols, int32_t* blocks, int32_t* n_blocks,
+                           hc_stream_t stream);
 
 /* Shared-footprint variant (the default): a pooled conv3_1 cell that only the SUBJECT's box reaches equals the same cell of the
  * pair (subject, empty box), one only the OBJECT's box reaches equals (empty box, object) - both are per-BOX maps, computed once
@@ -171,7 +175,8 @@ int hc_conv3_active_blocks(const int32_t* boxes, const int32_t* pair_sub, const 
  * train_test.py:391,398).  Only the cells BOTH boxes reach depend on the pair: hc_conv3_shared_blocks lists the cover of that
  * intersection (same cover, same entry format and capacity as hc_conv3_active_blocks). */
 int hc_conv3_shared_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
-                           int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream);
+                           int32_t feature_size, int32_t block_rows, int32_t block_cols, int32_t* blocks, int32_t* n_blocks,
+                           hc_stream_t stream);
 
 /* out[p] ([8,8,1024] bf16 per pair) = per cell: sub_maps[pair_sub[p]] where only the subject's box reaches the cell,
  * obj_maps[pair_obj[p]] where only the object's box does, `background` where neither does; cells both reach are NOT written

@@ -79,7 +79,7 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16,
             act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None,
-            blocks=None, n_blocks=None, block_rows=0, k_masks=None, k_cell=0, add_a=None, add_a_rows=None, add_b=None, add_b_rows=None,
+            blocks=None, n_blocks=None, block_rows=0, block_cols=0, k_masks=None, k_cell=0, add_a=None, add_a_rows=None, add_b=None, add_b_rows=None,
             out_rows=None, diff_sub=None, diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None):
     """out = epilogue(A @ B^T) on tcgen05 (see include/hiercom_b200.h hc_tc_gemm)."""
     require_cuda(a, b, out, bias, mul, blocks, n_blocks, k_masks, add_a, add_a_rows, add_b, add_b_rows, out_rows, diff_sub, diff_obj, diff_bg,
@@ -99,7 +99,7 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     d.n_img, d.h, d.w, d.c_total, d.c_base, d.c_in = n_img, h, w, c_total, c_base, c_in
     d.group_m, d.m_sub = group_m, m_sub
     d.mul, d.ld_mul = ptr(mul), (mul.stride(0) if mul is not None else 0)
-    d.blocks, d.n_blocks, d.block_rows = ptr(blocks), ptr(n_blocks), block_rows
+    d.blocks, d.n_blocks, d.block_rows, d.block_cols = ptr(blocks), ptr(n_blocks), block_rows, block_cols
     d.k_masks, d.k_cell = ptr(k_masks), k_cell
     d.add_a, d.add_a_rows, d.add_b, d.add_b_rows = ptr(add_a), ptr(add_a_rows), ptr(add_b), ptr(add_b_rows)
     d.ld_add = add_a.stride(0) if add_a is not None else 0
@@ -112,13 +112,13 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     return out
 
 
-def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=None, n_blocks=None, shared=False):
+def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=None, n_blocks=None, shared=False, block_cols=8):
     """Work list of the block-sparse conv3_1 for the given directed pairs (include/hiercom_b200.h hc_conv3_active_blocks;
     shared=True: hc_conv3_shared_blocks, only the cells both boxes reach).
     Returns (blocks int32 [n_pairs * 32 / block_rows], n_blocks int32 [1]); both stay on the device."""
     require_cuda(boxes, pair_sub, pair_obj, blocks, n_blocks)
     n = pair_sub.numel()
-    cap = max(n * (32 // block_rows), 1)
+    cap = max(n * (256 // (block_rows * (block_cols or 8))), 1)
     if blocks is None:
         blocks = torch.empty(cap, dtype=torch.int32, device=boxes.device)
     if n_blocks is None:
@@ -126,7 +126,7 @@ def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=N
     if blocks.numel() < cap:
         raise RuntimeError("hiercom_b200: conv3_active_blocks needs room for %d work-list entries" % cap)
     name = "hc_conv3_shared_blocks" if shared else "hc_conv3_active_blocks"
-    check(getattr(_lib.load(), name)(ptr(boxes), ptr(pair_sub), ptr(pair_obj), n, fs, block_rows, ptr(blocks), ptr(n_blocks), stream_ptr()),
+    check(getattr(_lib.load(), name)(ptr(boxes), ptr(pair_sub), ptr(pair_obj), n, fs, block_rows, block_cols, ptr(blocks), ptr(n_blocks), stream_ptr()),
           name)
     _count()
     return blocks, n_blocks

@@ -26,7 +26,7 @@ class GemmDesc(C.Structure):
                 ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("c_total", C.c_int32), ("c_base", C.c_int32), ("c_in", C.c_int32),
                 ("group_m", C.c_int32), ("m_sub", C.c_int32), ("mul", C.c_void_p), ("ld_mul", C.c_int64),
-                ("blocks", C.c_void_p), ("n_blocks", C.c_void_p), ("block_rows", C.c_int32),
+                ("blocks", C.c_void_p), ("n_blocks", C.c_void_p), ("block_rows", C.c_int32), ("block_cols", C.c_int32),
                 ("k_masks", C.c_void_p), ("k_cell", C.c_int64),
                 ("add_a", C.c_void_p), ("add_a_rows", C.c_void_p), ("add_b", C.c_void_p), ("add_b_rows", C.c_void_p), ("ld_add", C.c_int64),
                 ("out_rows", C.c_void_p),
@@ -43,8 +43,8 @@ SIGNATURES = {
     "hc_cs_bitmap_build": (C.c_int, [_P, _I64, _P, _I64, _P]),
     "hc_pairs_enumerate": (C.c_int, [_P, _P, _I32, _P, _I32, _I32, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "hc_tc_gemm": (C.c_int, [C.POINTER(GemmDesc), _P]),
-    "hc_conv3_active_blocks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
-    "hc_conv3_shared_blocks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
+    "hc_conv3_active_blocks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "hc_conv3_shared_blocks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "hc_p3_assemble": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P]),
     "hc_broadcast_rows": (C.c_int, [_P, _I64, _I64, _P, _P]),
     "hc_pair_cell_keys": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P]),

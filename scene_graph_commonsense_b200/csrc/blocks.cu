@@ -27,15 +27,16 @@ __device__ __forceinline__ unsigned long long cell_mask(const Rect& r) {
   return (0x0101010101010101ull & rows) * rowbits;
 }
 
-// greedy cover with blocks of 4 x hc cells; emit(entry) is called once per block, returns the count
+// greedy cover with blocks of wc x hc cells (wide x tall); emit(entry) is called once per block, returns the count
 template <typename F>
-__device__ __forceinline__ int cover_greedy(unsigned long long m, int hc, F emit) {
+__device__ __forceinline__ int cover_greedy(unsigned long long m, int hc, int wc, F emit) {
   int n = 0;
   const unsigned long long rows = (hc == 4) ? 0x01010101ull : 0x0101ull;
+  const unsigned long long cols = (1ull << wc) - 1ull;
   while (m) {
     const int bit = __ffsll((long long)m) - 1;
-    const int y = min(bit >> 3, 8 - hc), x = min(bit & 7, 4);
-    m &= ~((rows * 0xFull) << (8 * y + x));
+    const int y = min(bit >> 3, 8 - hc), x = min(bit & 7, 8 - wc);
+    m &= ~((rows * cols) << (8 * y + x));
     emit((y << 4) | x);
     ++n;
   }
@@ -45,17 +46,17 @@ __device__ __forceinline__ int cover_greedy(unsigned long long m, int hc, F emit
 // the greedy cover can need one block more than the aligned tiling of the whole map (two staggered rectangles): never emit
 // more than the dense 2 x (8/hc) tiling, so a pair costs at most what the dense kernel would
 template <typename F>
-__device__ __forceinline__ int cover(unsigned long long m, int hc, F emit) {
-  const int full = 2 * (8 / hc);
-  if (cover_greedy(m, hc, [](int) {}) <= full) return cover_greedy(m, hc, emit);
+__device__ __forceinline__ int cover(unsigned long long m, int hc, int wc, F emit) {
+  const int full = (8 / wc) * (8 / hc);
+  if (cover_greedy(m, hc, wc, [](int) {}) <= full) return cover_greedy(m, hc, wc, emit);
   for (int y = 0; y < 8; y += hc)
-    for (int x = 0; x < 8; x += 4) emit((y << 4) | x);
+    for (int x = 0; x < 8; x += wc) emit((y << 4) | x);
   return full;
 }
 
 __global__ void __launch_bounds__(1024)
 conv3_blocks_kernel(const int4* __restrict__ boxes, const int* __restrict__ pair_sub, const int* __restrict__ pair_obj, int n_pairs, int fs,
-                    int hc, bool both, int* __restrict__ blocks, int* __restrict__ n_blocks) {
+                    int hc, int wc, bool both, int* __restrict__ blocks, int* __restrict__ n_blocks) {
   __shared__ int s_scan[1024];
   const int t = threadIdx.x;
   const int per = (n_pairs + 1023) / 1024;
@@ -66,7 +67,7 @@ conv3_blocks_kernel(const int4* __restrict__ boxes, const int* __restrict__ pair
     const unsigned long long ms = cell_mask(rect_of(__ldg(boxes + pair_sub[p]), fs)), mo = cell_mask(rect_of(__ldg(boxes + pair_obj[p]), fs));
     return both ? (ms & mo) : (ms | mo);
   };
-  for (int p = p0; p < p1; ++p) cnt += cover(pair_mask(p), hc, [](int) {});
+  for (int p = p0; p < p1; ++p) cnt += cover(pair_mask(p), hc, wc, [](int) {});
   s_scan[t] = cnt;
   __syncthreads();
   for (int d = 1; d < 1024; d <<= 1) {                          // inclusive Hillis-Steele scan over the 1024 per-thread counts
@@ -77,7 +78,7 @@ conv3_blocks_kernel(const int4* __restrict__ boxes, const int* __restrict__ pair
   }
   int o = s_scan[t] - cnt;
   if (t == 1023) n_blocks[0] = s_scan[t];
-  for (int p = p0; p < p1; ++p) cover(pair_mask(p), hc, [&](int e) { blocks[o++] = (p << 8) | e; });
+  for (int p = p0; p < p1; ++p) cover(pair_mask(p), hc, wc, [&](int e) { blocks[o++] = (p << 8) | e; });
 }
 
 // Pooled conv3_1 output of a pair outside the cells both boxes reach: a cell only the subject's box reaches equals the map of
@@ -165,28 +166,32 @@ cells_zero_kernel(const unsigned long long* __restrict__ masks, int rows_per_til
 using namespace hc;
 
 static int conv3_blocks_list(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs, int32_t feature_size,
-                             int32_t block_rows, bool both, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream_) {
+                             int32_t block_rows, int32_t block_cols, bool both, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(n_blocks && (n_pairs <= 0 || (boxes && pair_sub && pair_obj && blocks)), HC_E_NULL, "hc_conv3_active_blocks: NULL operand");
   int rc = hc_device_check();
   if (rc != HC_OK) return rc;
   HC_REQUIRE(feature_size == 32, HC_E_SHAPE, "hc_conv3_active_blocks: built for feature_size 32 (8x8 pooled conv3 cells)");
-  HC_REQUIRE(block_rows == 8 || block_rows == 4, HC_E_SHAPE, "hc_conv3_active_blocks: block_rows must be 8 or 4");
+  if (block_cols == 0) block_cols = 8;
+  HC_REQUIRE((block_rows == 8 || block_rows == 4) && (block_cols == 8 || (block_cols == 4 && block_rows == 4)), HC_E_SHAPE,
+             "hc_conv3_active_blocks: blocks are 8x8, 8x4 or 4x4 pixels (block_cols x block_rows)");
   HC_REQUIRE(n_pairs >= 0 && n_pairs < (1 << 23), HC_E_SHAPE, "hc_conv3_active_blocks: n_pairs must be below 2^23");
   HC_REQUIRE(aligned16(boxes), HC_E_ALIGN, "hc_conv3_active_blocks: boxes must be 16-byte aligned");   // n_pairs == 0 still writes n_blocks = 0
   conv3_blocks_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const int4*>(boxes), pair_sub, pair_obj, n_pairs, feature_size, block_rows / 2,
-                                              both, blocks, n_blocks);
+                                              block_cols / 2, both, blocks, n_blocks);
   return cuda_status("conv3_blocks_kernel launch");
 }
 
 extern "C" int hc_conv3_active_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
-                                      int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream_) {
-  return conv3_blocks_list(boxes, pair_sub, pair_obj, n_pairs, feature_size, block_rows, false, blocks, n_blocks, stream_);
+                                      int32_t feature_size, int32_t block_rows, int32_t block_cols, int32_t* blocks, int32_t* n_blocks,
+                                      hc_stream_t stream_) {
+  return conv3_blocks_list(boxes, pair_sub, pair_obj, n_pairs, feature_size, block_rows, block_cols, false, blocks, n_blocks, stream_);
 }
 
 extern "C" int hc_conv3_shared_blocks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs,
-                                      int32_t feature_size, int32_t block_rows, int32_t* blocks, int32_t* n_blocks, hc_stream_t stream_) {
-  return conv3_blocks_list(boxes, pair_sub, pair_obj, n_pairs, feature_size, block_rows, true, blocks, n_blocks, stream_);
+                                      int32_t feature_size, int32_t block_rows, int32_t block_cols, int32_t* blocks, int32_t* n_blocks,
+                                      hc_stream_t stream_) {
+  return conv3_blocks_list(boxes, pair_sub, pair_obj, n_pairs, feature_size, block_rows, block_cols, true, blocks, n_blocks, stream_);
 }
 
 extern "C" int hc_p3_assemble(const void* background, const void* sub_maps, const void* obj_maps, const int32_t* boxes,

@@ -71,7 +71,8 @@ struct Params {
   int patch;                     // 1 = implicit-conv patch pipeline (A fetched once per (channel block, kx)), 0 = plain GEMM
   const int* blocks;             // HC_GEMM_CONV3_BLOCKS: work list, entry = img << 8 | (y0/2) << 4 | (x0/2)
   const int* n_blocks;           // device scalar: entries in the work list
-  int blk_h;                     // pixel rows per block (8 or 4); blocks are 8 pixels wide
+  int blk_h;                     // pixel rows per block (8 or 4)
+  int blk_w;                     // pixel columns per block (8 or 4)
   // K-cell-sparse plain GEMM: bit c of k_masks[CTA m tile] set = K blocks [c*k_cell_kb, (c+1)*k_cell_kb) are visited
   const unsigned long long* k_masks;
   int k_cell_kb;
@@ -247,7 +248,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   // block-sparse conv: the number of M tiles comes from the device-side work-list length (no host round trip)
   const bool blk_mode = p.mode == HC_GEMM_CONV3_BLOCKS;
-  const int blk_per_sub = blk_mode ? BM / (8 * p.blk_h) : 1;        // blocks per 128-row sub-tile (2 or 4)
+  const int blk_per_sub = blk_mode ? BM / (p.blk_w * p.blk_h) : 1;  // blocks per 128-row sub-tile (2, 4 or 8)
   const int n_blocks = blk_mode ? __ldg(p.n_blocks) : 0;
   const int tiles_m = blk_mode ? (n_blocks + MS * blk_per_sub - 1) / (MS * blk_per_sub) : p.tiles_m;
   const int num_tiles = tiles_m * p.tiles_n;
@@ -299,18 +300,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     } else if (lane == 0 && blk_mode) {
       // one stage per (channel block, kx, ky) - the K order of the patch pipeline, so results are bit-identical to the dense
-      // kernel; every block of the tile contributes one {64 ch, 8 x, blk_h y} box shifted by the tap (TMA zero-fills the halo)
+      // kernel; every block of the tile contributes one {64 ch, blk_w x, blk_h y} box shifted by the tap (TMA zero-fills the halo)
       int stage = 0;
       uint32_t phase = 0;
       const int cblks = p.c_in / BK;
       const int nblk = MS * blk_per_sub;
-      const uint32_t blk_bytes = (uint32_t)(8 * p.blk_h) * 128u;
+      const uint32_t blk_bytes = (uint32_t)(p.blk_w * p.blk_h) * 128u;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(p, tiles_m, tile, m_blk, n_blk);
-        int e[MS * 4];
+        int e[MS * 8];
 #pragma unroll
-        for (int i = 0; i < MS * 4; ++i) e[i] = i < nblk ? __ldg(p.blocks + min(m_blk * nblk + i, n_blocks - 1)) : 0;
+        for (int i = 0; i < MS * 8; ++i) e[i] = i < nblk ? __ldg(p.blocks + min(m_blk * nblk + i, n_blocks - 1)) : 0;
         for (int cb = 0; cb < cblks; ++cb) {
           for (int kx = 0; kx < 3; ++kx) {
             for (int ky = 0; ky < 3; ++ky) {
@@ -318,7 +319,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
               mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
 #pragma unroll
-              for (int i = 0; i < MS * 4; ++i)
+              for (int i = 0; i < MS * 8; ++i)
                 if (i < nblk)
                   tma_load_4d(a_dst + i * blk_bytes, &tmap_a, full_bar(stage), p.c_base + cb * BK, 2 * (e[i] & 15) + kx - 1,
                               2 * ((e[i] >> 4) & 15) + ky - 1, e[i] >> 8);
@@ -472,8 +473,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             // rows of a sub-tile are pixels (yl, xl) = (row/16, row%16); this warp holds yl in {2q, 2q+1}.
             // 2x2 max-pool partners are lane^1 (x) and lane^16 (y): butterfly reduce-scatter, after which the
             // lane with bits (ybit, xbit) owns the pooled maximum of columns [ybit*16 + xbit*8, +8).
-            // (block mode: rows of a block are pixels (yl, xl) = (row/8, row%8), so the y partner is lane^8)
-            const int ysh = blk_mode ? 3 : 4;
+            // (block mode: rows of a block are pixels (yl, xl) = (row / blk_w, row % blk_w), so the y partner is lane ^ blk_w)
+            const int ysh = blk_mode ? (p.blk_w == 8 ? 3 : 2) : 4;
             const int ybit = (lane >> ysh) & 1, xbit = lane & 1;
             float h[16];
 #pragma unroll
@@ -501,13 +502,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             int px = t_x0 / 2 + ((lane & 15) >> 1);                     // pooled col
             int o_img = t_img;
             if (blk_mode) {
-              // this warp's 32 rows lie in block (32q / rows_per_block) of sub-tile j, (32q % rows_per_block) / 8 pixel rows in
-              const int rows_pb = 8 * p.blk_h;
-              const int bi = j * blk_per_sub + (q * 32) / rows_pb;
+              // this lane's row sits in block (row / rows_per_block) of sub-tile j (a warp spans 1 or 2 blocks), at pixel
+              // (yl, xl) = (r / blk_w, r % blk_w) of it, r = row % rows_per_block
+              const int rows_pb = p.blk_w * p.blk_h;
+              const int row_s = q * 32 + lane;
+              const int bi = j * blk_per_sub + row_s / rows_pb;
+              const int rb = row_s % rows_pb;
               const int e = __ldg(p.blocks + min((m_blk * MS * blk_per_sub) + bi, n_blocks - 1));
               o_img = e >> 8;
-              py = ((e >> 4) & 15) + ((((q * 32) % rows_pb) >> 3) >> 1) + (lane >> 4);
-              px = (e & 15) + ((lane & 7) >> 1);
+              py = ((e >> 4) & 15) + ((rb / p.blk_w) >> 1);
+              px = (e & 15) + ((rb % p.blk_w) >> 1);
             }
             if (p.epi == HC_EPI_POOL_DIFF_BF16) {
               // shared-footprint fc1 operand: what this pair's cell adds to the sum of its two per-box maps,
@@ -711,8 +715,10 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   const bool pooled = d->epilogue == HC_EPI_POOL_BF16 || d->epilogue == HC_EPI_POOL_DIFF_BF16;
   HC_REQUIRE(!pooled || ((d->mode == HC_GEMM_CONV3 || d->mode == HC_GEMM_CONV3_BLOCKS) && d->bias), HC_E_SHAPE,
              "hc_tc_gemm: pooled epilogue needs conv mode and a bias");
-  HC_REQUIRE(d->mode != HC_GEMM_CONV3_BLOCKS || (pooled && d->blocks && d->n_blocks && (d->block_rows == 8 || d->block_rows == 4)),
-             HC_E_SHAPE, "hc_tc_gemm: block-sparse conv needs the pooled epilogue, a work list and block_rows in {4, 8}");
+  const int blk_w = d->block_cols ? d->block_cols : 8;
+  HC_REQUIRE(d->mode != HC_GEMM_CONV3_BLOCKS || (pooled && d->blocks && d->n_blocks && (d->block_rows == 8 || d->block_rows == 4) &&
+                                                 (blk_w == 8 || (blk_w == 4 && d->block_rows == 4))),
+             HC_E_SHAPE, "hc_tc_gemm: block-sparse conv needs the pooled epilogue, a work list and 8x8, 8x4 or 4x4-pixel blocks");
   HC_REQUIRE(d->epilogue != HC_EPI_POOL_DIFF_BF16 ||
                  (d->mode == HC_GEMM_CONV3_BLOCKS && d->diff_sub && d->diff_obj && d->diff_bg && d->pair_sub && d->pair_obj && d->pair_row &&
                   aligned16(d->diff_sub) && aligned16(d->diff_obj) && aligned16(d->diff_bg)),
@@ -738,7 +744,7 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   p.ldc = d->ldc; p.c_off = d->c_off; p.bias = d->bias; p.out = d->out;
   p.mul = d->mul; p.ld_mul = d->ld_mul;
   p.patch = d->mode == HC_GEMM_CONV3 ? 1 : 0;
-  p.blocks = d->blocks; p.n_blocks = d->n_blocks; p.blk_h = d->block_rows;
+  p.blocks = d->blocks; p.n_blocks = d->n_blocks; p.blk_h = d->block_rows; p.blk_w = blk_w;
   p.k_masks = reinterpret_cast<const unsigned long long*>(d->k_masks); p.k_cell_kb = d->k_masks ? (int)(d->k_cell / tc::BK) : 0;
   p.add_a = d->add_a; p.add_a_rows = d->add_a_rows; p.add_b = d->add_b; p.add_b_rows = d->add_b_rows; p.ld_add = d->ld_add;
   p.out_rows = d->out_rows;
@@ -773,8 +779,8 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     p.tiles_m = d->n_img * p.tiles_x * p.tiles_y;
     cuuint64_t dims[4] = {(cuuint64_t)d->c_total, (cuuint64_t)d->w, (cuuint64_t)d->h, (cuuint64_t)d->n_img};
     cuuint64_t str[3] = {(cuuint64_t)d->c_total * 2, (cuuint64_t)d->w * d->c_total * 2, (cuuint64_t)d->h * d->w * d->c_total * 2};
-    // dense: one patch serves the three ky taps; block mode: one {64 ch, 8 x, block_rows y} box per block and tap
-    cuuint32_t box[4] = {(cuuint32_t)tc::BK, blk ? 8u : 16u, (cuuint32_t)(blk ? d->block_rows : 8 * MS + 2), 1};
+    // dense: one patch serves the three ky taps; block mode: one {64 ch, block_cols x, block_rows y} box per block and tap
+    cuuint32_t box[4] = {(cuuint32_t)tc::BK, blk ? (cuuint32_t)blk_w : 16u, (cuuint32_t)(blk ? d->block_rows : 8 * MS + 2), 1};
     rc = tc::make_map(&ta, d->a, 4, dims, str, box);
     if (rc != HC_OK) return rc;
   } else {

@@ -125,20 +125,21 @@ class PackedHead:
             self._p3_bg = p3
         return self._p3_bg
 
-    def conv3_blocks(self, p2, p3, n, blocks, n_blocks, block_rows, m_sub=2, tag="conv3"):
+    def conv3_blocks(self, p2, p3, n, blocks, n_blocks, block_rows, m_sub=2, tag="conv3", block_cols=8):
         """conv3_1+ReLU+pool on the listed blocks of p2 [>=n,16,16,512] into the PRE-FILLED p3 [>=n,8,8,1024]."""
         ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_BF16,
                     n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag=tag, blocks=blocks,
-                    n_blocks=n_blocks, block_rows=block_rows)
+                    n_blocks=n_blocks, block_rows=block_rows, block_cols=block_cols)
         return p3
 
-    def conv3_diff(self, p2, d, n, blocks, n_blocks, block_rows, sub_maps, obj_maps, pair_sub, pair_obj, pair_row, m_sub=2, tag="conv3"):
+    def conv3_diff(self, p2, d, n, blocks, n_blocks, block_rows, sub_maps, obj_maps, pair_sub, pair_obj, pair_row, m_sub=2, tag="conv3",
+                   block_cols=8):
         """conv3_1+ReLU+pool on the listed blocks of p2 [>=n,16,16,512]; local pair i's cells go to row pair_row[i] of d [rows,8,8,1024]
         as the DIFFERENCE to its per-box maps, (x - sub_maps[pair_sub[i]]) - (obj_maps[pair_obj[i]] - background): the operand of
         the shared-footprint fc1 (`fc1_shared_fc2`), exactly zero wherever only one box of the pair reaches."""
         ops.tc_gemm(p2, self.w3, d, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_DIFF_BF16,
                     n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag=tag, blocks=blocks,
-                    n_blocks=n_blocks, block_rows=block_rows, diff_sub=sub_maps, diff_obj=obj_maps, diff_bg=self.p3_background(),
+                    n_blocks=n_blocks, block_rows=block_rows, block_cols=block_cols, diff_sub=sub_maps, diff_obj=obj_maps, diff_bg=self.p3_background(),
                     pair_sub=pair_sub, pair_obj=pair_obj, pair_row=pair_row)
         return d
 
@@ -158,7 +159,7 @@ class PackedHead:
         ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8, tag="fc2", out_rows=out_rows)
         return raw
 
-    def conv3_fc(self, p2, m_sub=2, raw=None, n=None, blocks=None, n_blocks=None, block_rows=0, p3=None):
+    def conv3_fc(self, p2, m_sub=2, raw=None, n=None, blocks=None, n_blocks=None, block_rows=0, p3=None, block_cols=8):
         """conv3_1+ReLU+pool -> fc1+ReLU -> fc2 (raw, fp32) on pooled conv2 activations p2 [>=n,16,16,512] bf16.
         With a work list (`ops.conv3_active_blocks`) conv3_1 visits only the listed blocks of each pair; the rest of its output is
         the background (`p3`, if given, is a buffer the caller has ALREADY pre-filled with it)."""
@@ -171,7 +172,7 @@ class PackedHead:
         else:
             if p3 is None:
                 p3 = ops.broadcast_rows(self.p3_background(), n, torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev))
-            self.conv3_blocks(p2, p3, n, blocks, n_blocks, block_rows, m_sub=m_sub)
+            self.conv3_blocks(p2, p3, n, blocks, n_blocks, block_rows, m_sub=m_sub, block_cols=block_cols)
         h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=dev)
         ops.tc_gemm(p3, self.w_fc1, h1, n, 4096, 65536, bias=self.b_fc1, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU,
                     group_m=37, m_sub=2 if n > 128 else 1, tag="fc1")

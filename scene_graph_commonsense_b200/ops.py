@@ -58,60 +58,60 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 # ------------------------------------------------------------------------------------------------ R5/R6 dense contractions
 @_op("tc_gemm", "(Tensor a, Tensor b, Tensor(a!) out, int m, int n, int k, Tensor? bias, Tensor? mul, int lda, int ldc, int c_off, "
      "int mode, int epilogue, int act, int n_img, int h, int w, int c_total, int c_base, int c_in, int group_m, int m_sub, "
-     "str tag, Tensor? blocks, Tensor? n_blocks, int block_rows, Tensor? k_masks, int k_cell, Tensor? add_a, Tensor? add_a_rows, "
+     "str tag, Tensor? blocks, Tensor? n_blocks, int block_rows, int block_cols, Tensor? k_masks, int k_cell, Tensor? add_a, Tensor? add_a_rows, "
      "Tensor? add_b, Tensor? add_b_rows, Tensor? out_rows, Tensor? diff_sub, Tensor? diff_obj, Tensor? diff_bg, Tensor? pair_sub, "
      "Tensor? pair_obj, Tensor? pair_row) -> ()")
 def _tc_gemm(a, b, out, m, n, k, bias, mul, lda, ldc, c_off, mode, epilogue, act, n_img, h, w, c_total, c_base, c_in, group_m, m_sub,
-             tag, blocks, n_blocks, block_rows, k_masks, k_cell, add_a, add_a_rows, add_b, add_b_rows, out_rows, diff_sub, diff_obj,
+             tag, blocks, n_blocks, block_rows, block_cols, k_masks, k_cell, add_a, add_a_rows, add_b, add_b_rows, out_rows, diff_sub, diff_obj,
              diff_bg, pair_sub, pair_obj, pair_row):
     _A.tc_gemm(a, b, out, m, n, k, bias=bias, lda=lda, ldc=ldc, c_off=c_off, mode=mode, epilogue=epilogue, act=act, n_img=n_img, h=h,
                w=w, c_total=c_total, c_base=c_base, c_in=c_in, group_m=group_m, m_sub=m_sub, tag=tag, mul=mul, blocks=blocks,
-               n_blocks=n_blocks, block_rows=block_rows, k_masks=k_masks, k_cell=k_cell, add_a=add_a, add_a_rows=add_a_rows, add_b=add_b,
+               n_blocks=n_blocks, block_rows=block_rows, block_cols=block_cols, k_masks=k_masks, k_cell=k_cell, add_a=add_a, add_a_rows=add_a_rows, add_b=add_b,
                add_b_rows=add_b_rows, out_rows=out_rows, diff_sub=diff_sub, diff_obj=diff_obj, diff_bg=diff_bg, pair_sub=pair_sub,
                pair_obj=pair_obj, pair_row=pair_row)
 
 
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16, act=ACT_NONE, n_img=0,
             h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None, blocks=None, n_blocks=None,
-            block_rows=0, k_masks=None, k_cell=0, add_a=None, add_a_rows=None, add_b=None, add_b_rows=None, out_rows=None, diff_sub=None,
+            block_rows=0, block_cols=0, k_masks=None, k_cell=0, add_a=None, add_a_rows=None, add_b=None, add_b_rows=None, out_rows=None, diff_sub=None,
             diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None):
     """out = epilogue(A @ B^T) on tcgen05 (include/hiercom_b200.h hc_tc_gemm)."""
     _call("tc_gemm")(a, b, out, m, n, k, bias, mul, lda, n if ldc is None else ldc, c_off, mode, epilogue, act, n_img, h, w, c_total,
-                     c_base, c_in, group_m, m_sub, tag, blocks, n_blocks, block_rows, k_masks, k_cell, add_a, add_a_rows, add_b, add_b_rows,
+                     c_base, c_in, group_m, m_sub, tag, blocks, n_blocks, block_rows, block_cols, k_masks, k_cell, add_a, add_a_rows, add_b, add_b_rows,
                      out_rows, diff_sub, diff_obj, diff_bg, pair_sub, pair_obj, pair_row)
     return out
 
 
 # ------------------------------------------------------------------------------------------------ block-sparse conv3_1 support
 @_op("conv3_active_blocks", "(Tensor boxes, Tensor pair_sub, Tensor pair_obj, int block_rows, int fs, Tensor(a!) blocks, "
-     "Tensor(b!) n_blocks) -> ()")
-def _conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks):
-    _A.conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks=blocks, n_blocks=n_blocks)
+     "Tensor(b!) n_blocks, int block_cols) -> ()")
+def _conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks, block_cols):
+    _A.conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks=blocks, n_blocks=n_blocks, block_cols=block_cols)
 
 
-def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=None, n_blocks=None):
+def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=None, n_blocks=None, block_cols=8):
     """Device work list (blocks, n_blocks) of the conv3_1 output blocks a set of directed pairs has to compute."""
     if blocks is None:
-        blocks = torch.empty(max(pair_sub.numel() * (32 // block_rows), 1), dtype=torch.int32, device=boxes.device)
+        blocks = torch.empty(max(pair_sub.numel() * (256 // (block_rows * block_cols)), 1), dtype=torch.int32, device=boxes.device)
     if n_blocks is None:
         n_blocks = torch.empty(1, dtype=torch.int32, device=boxes.device)
-    _call("conv3_active_blocks")(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks)
+    _call("conv3_active_blocks")(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks, block_cols)
     return blocks, n_blocks
 
 
 @_op("conv3_shared_blocks", "(Tensor boxes, Tensor pair_sub, Tensor pair_obj, int block_rows, int fs, Tensor(a!) blocks, "
-     "Tensor(b!) n_blocks) -> ()")
-def _conv3_shared_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks):
-    _A.conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks=blocks, n_blocks=n_blocks, shared=True)
+     "Tensor(b!) n_blocks, int block_cols) -> ()")
+def _conv3_shared_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks, block_cols):
+    _A.conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows, fs, blocks=blocks, n_blocks=n_blocks, shared=True, block_cols=block_cols)
 
 
-def conv3_shared_blocks(boxes, pair_sub, pair_obj, block_rows=4, fs=32, blocks=None, n_blocks=None):
+def conv3_shared_blocks(boxes, pair_sub, pair_obj, block_rows=4, fs=32, blocks=None, n_blocks=None, block_cols=8):
     """Device work list of the conv3_1 output blocks that depend on BOTH boxes of a pair (the rest comes from `p3_assemble`)."""
     if blocks is None:
-        blocks = torch.empty(max(pair_sub.numel() * (32 // block_rows), 1), dtype=torch.int32, device=boxes.device)
+        blocks = torch.empty(max(pair_sub.numel() * (256 // (block_rows * block_cols)), 1), dtype=torch.int32, device=boxes.device)
     if n_blocks is None:
         n_blocks = torch.empty(1, dtype=torch.int32, device=boxes.device)
-    _call("conv3_shared_blocks")(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks)
+    _call("conv3_shared_blocks")(boxes, pair_sub, pair_obj, block_rows, fs, blocks, n_blocks, block_cols)
     return blocks, n_blocks
 
 

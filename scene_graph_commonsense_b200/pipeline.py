@@ -140,7 +140,7 @@ class RelationPipeline:
     def __init__(self, packed: Optional[PackedHead], device, commonsense=True, aligned_keys=None, violated_keys=None,
                  top_k=tables.TOP_K, iou_thresh=0.5, feature_size=32, chunk_pairs=16384, predcls=True, conv3_m_sub=2,
                  hier=None, splits=None, overlap=True, conv2_m_sub=1, chunk_policy="waves", conv3_block_rows=4, conv3_shared=True,
-                 fc1_shared=True):
+                 fc1_shared=True, conv3_block_cols=4):
         self.packed = packed
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -159,6 +159,8 @@ class RelationPipeline:
         if conv3_block_rows not in (0, 4, 8):
             raise ValueError("conv3_block_rows must be 0 (dense), 8 or 4")
         self.conv3_block_rows = int(conv3_block_rows)
+        # block width in conv3 pixels: 8, or 4 (with 4 rows: 2 x 2-cell blocks hug the cell rectangles more tightly)
+        self.conv3_block_cols = 4 if (int(conv3_block_cols) == 4 and self.conv3_block_rows == 4) else 8
         # block-sparse only.  True: a cell of the pooled conv3_1 output that only ONE box of the pair reaches is taken from that
         # box's own map ((box, empty) / (empty, box), computed once per box of the window), so a pair computes only the cells
         # BOTH boxes reach.  False: every cell either box reaches is computed per pair.  Same bits either way.
@@ -206,7 +208,7 @@ class RelationPipeline:
         -> sub_maps = (box, empty), obj_maps = (empty, box), each [n_box,8,8,1024] bf16, and the work-list lengths.  A real
         pair's output equals sub_maps[s] in the cells only its subject's box reaches and obj_maps[o] in those only its object's
         box reaches (bit for bit: same kernels, same operands inside the receptive field)."""
-        pk, br = self.packed, self.conv3_block_rows
+        pk, br, bc = self.packed, self.conv3_block_rows, self.conv3_block_cols
         n_box = boxes_x.shape[0] - 1
         idx = torch.arange(n_box, dtype=torch.int32, device=self.device)
         empty = torch.full((n_box,), n_box, dtype=torch.int32, device=self.device)
@@ -219,9 +221,9 @@ class RelationPipeline:
         for k, s in enumerate(starts):
             e = min(2 * n_box, s + self.chunk_pairs)
             p2 = ops.pair_relu_pool(u, v, None, sub[s:e], obj[s:e], self.fs)
-            blocks, _ = ops.conv3_active_blocks(boxes_x, sub[s:e], obj[s:e], br, self.fs, n_blocks=nblk[k:k + 1])
+            blocks, _ = ops.conv3_active_blocks(boxes_x, sub[s:e], obj[s:e], br, self.fs, n_blocks=nblk[k:k + 1], block_cols=bc)
             ops.broadcast_rows(pk.p3_background(), e - s, maps[s:e])
-            pk.conv3_blocks(p2, maps[s:e], e - s, blocks, nblk[k:k + 1], br, m_sub=self.conv3_m_sub, tag="conv3_box")
+            pk.conv3_blocks(p2, maps[s:e], e - s, blocks, nblk[k:k + 1], br, m_sub=self.conv3_m_sub, tag="conv3_box", block_cols=bc)
             del p2
         if with_background_row:
             return maps, nblk
@@ -284,7 +286,7 @@ class RelationPipeline:
         (no `offsets_host`) take the generic gather kernel."""
         pk = self.packed
         n = pairs["n"]
-        br, shared = self.conv3_block_rows, self.conv3_shared
+        br, bc, shared = self.conv3_block_rows, self.conv3_block_cols, self.conv3_shared
         if self.fc1_shared and n > 0:
             return self._forward_pairs_fc1_shared(b, pairs)
         if shared:      # one more box per window: the empty one (all background), partner of every box in `box_maps`
@@ -313,12 +315,13 @@ class RelationPipeline:
                 e = min(n, s + self.chunk_pairs)
                 p2 = ops.pair_relu_pool(u, v, None, pairs["sub"][s:e], pairs["obj"][s:e], self.fs)
                 if br:
-                    blocks, _ = list_blocks(b.boxes, pairs["sub"][s:e], pairs["obj"][s:e], br, self.fs, n_blocks=nblk[k:k + 1])
+                    blocks, _ = list_blocks(b.boxes, pairs["sub"][s:e], pairs["obj"][s:e], br, self.fs, n_blocks=nblk[k:k + 1], block_cols=bc)
                     p3 = None
                     if shared:
                         p3 = torch.empty(e - s, 8, 8, 1024, dtype=torch.bfloat16, device=self.device)
                         prefill(p3, pairs["sub"][s:e], pairs["obj"][s:e], e - s)
-                    pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e], blocks=blocks, n_blocks=nblk[k:k + 1], block_rows=br, p3=p3)
+                    pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e], blocks=blocks, n_blocks=nblk[k:k + 1], block_rows=br, p3=p3,
+                                block_cols=bc)
                     del p3
                 else:
                     pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e])
@@ -334,7 +337,7 @@ class RelationPipeline:
             bufs = [torch.empty(cap, self.fs // 2, self.fs // 2, 512, dtype=torch.bfloat16, device=self.device)
                     for _ in range(2 if self.overlap and len(chunks) > 1 else 1)]
             if br:      # per buffer: the work list and the background-filled pooled conv3_1 output
-                blk_bufs = [torch.empty(cap * (32 // br), dtype=torch.int32, device=self.device) for _ in bufs]
+                blk_bufs = [torch.empty(cap * (256 // (br * bc)), dtype=torch.int32, device=self.device) for _ in bufs]
                 p3_bufs = [torch.empty(cap, 8, 8, 1024, dtype=torch.bfloat16, device=self.device) for _ in bufs]
                 nblk = torch.zeros(len(chunks), dtype=torch.int32, device=self.device)
                 p3_bg = pk.p3_background()
@@ -353,7 +356,7 @@ class RelationPipeline:
                     ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, self.fs, out=buf)
                     if br:
                         list_blocks(b.boxes, pairs["sub"][base:base + cnt], pairs["obj"][base:base + cnt], br, self.fs,
-                                    blocks=blk_bufs[k % len(bufs)], n_blocks=nblk[k:k + 1])
+                                    blocks=blk_bufs[k % len(bufs)], n_blocks=nblk[k:k + 1], block_cols=bc)
                         prefill(p3_bufs[k % len(bufs)], pairs["sub"][base:base + cnt], pairs["obj"][base:base + cnt], cnt)
                     pooled = torch.cuda.Event()
                     pooled.record(side)
@@ -361,7 +364,7 @@ class RelationPipeline:
                     main.wait_event(pooled)
                 if br:
                     pk.conv3_fc(buf, m_sub=self.conv3_m_sub, raw=raw[base:base + cnt], n=cnt, blocks=blk_bufs[k % len(bufs)],
-                                n_blocks=nblk[k:k + 1], block_rows=br, p3=p3_bufs[k % len(bufs)])
+                                n_blocks=nblk[k:k + 1], block_rows=br, p3=p3_bufs[k % len(bufs)], block_cols=bc)
                 else:
                     pk.conv3_fc(buf, m_sub=self.conv3_m_sub, raw=raw[base:base + cnt], n=cnt)
                 ev = torch.cuda.Event()
@@ -378,7 +381,7 @@ class RelationPipeline:
         """`forward_pairs` with the shared-footprint fc1: per-box conv3_1 maps and their fc1 rows once per box; per pair only the
         conv3_1 blocks covering the cells both boxes reach, written as differences into the sorted operand d; ONE K-cell-sparse fc1
         + fc2 over all pairs of the window; raw comes back in pair order through the fc2 epilogue's row map."""
-        pk, fs, br = self.packed, self.fs, self.conv3_block_rows
+        pk, fs, br, bc = self.packed, self.fs, self.conv3_block_rows, self.conv3_block_cols
         n, n_box = pairs["n"], b.boxes.shape[0]
         dev = self.device
         boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))      # + the empty box (all background), partner of every box
@@ -408,7 +411,7 @@ class RelationPipeline:
         cap = max(c[3] for c in chunks)
         two = self.overlap and len(chunks) > 1
         bufs = [torch.empty(cap, fs // 2, fs // 2, 512, dtype=torch.bfloat16, device=dev) for _ in range(2 if two else 1)]
-        blk_bufs = [torch.empty(cap * (32 // br), dtype=torch.int32, device=dev) for _ in bufs]
+        blk_bufs = [torch.empty(cap * (256 // (br * bc)), dtype=torch.int32, device=dev) for _ in bufs]
         nblk = torch.zeros(len(chunks), dtype=torch.int32, device=dev)
         main = torch.cuda.current_stream()
         side = self._side_stream() if two else main
@@ -427,13 +430,13 @@ class RelationPipeline:
                     ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, fs, out=buf)
                 else:
                     ops.pair_relu_pool(u, v, None, sub_k, obj_k, fs, out=buf)
-                ops.conv3_shared_blocks(b.boxes, sub_k, obj_k, br, fs, blocks=blk, n_blocks=nblk[k:k + 1])
+                ops.conv3_shared_blocks(b.boxes, sub_k, obj_k, br, fs, blocks=blk, n_blocks=nblk[k:k + 1], block_cols=bc)
                 pooled = torch.cuda.Event()
                 pooled.record(side)
             if side is not main:
                 main.wait_event(pooled)
             pk.conv3_diff(buf, d, cnt, blk, nblk[k:k + 1], br, sub_maps, obj_maps, sub_k, obj_k, row_of[base:base + cnt],
-                          m_sub=self.conv3_m_sub)
+                          m_sub=self.conv3_m_sub, block_cols=bc)
             ev = torch.cuda.Event()
             ev.record(main)
             gemm_done.append(ev)

@@ -66,8 +66,8 @@ def test_k_cell_sparse_gemm_equals_dense_bit_for_bit(m, with_tables):
     assert torch.equal(o2[perm.long()], o1)
 
 
-@pytest.mark.parametrize("block_rows", [8, 4])
-def test_difference_epilogue_and_keys(block_rows):
+@pytest.mark.parametrize("block_rows,block_cols", [(8, 8), (4, 8), (4, 4)])
+def test_difference_epilogue_and_keys(block_rows, block_cols):
     """HC_EPI_POOL_DIFF_BF16 == (x - sub_map) - (obj_map - background) on the dense kernel's x, bit for bit, at row pair_row[i]; zero in
     every covered cell that only one box reaches; keys / tile masks describe the cell rectangles both boxes reach."""
     from scene_graph_commonsense_b200 import ops
@@ -92,9 +92,9 @@ def test_difference_epilogue_and_keys(block_rows):
     emp = torch.full((n_box,), n_box, dtype=torch.int32, device=DEV)
     s1, o1 = torch.cat((idx, emp)), torch.cat((emp, idx))
     p2b = ops.pair_relu_pool(u, v, None, s1, o1, 32)
-    blk1, nb1 = ops.conv3_active_blocks(boxes_x, s1, o1, block_rows)
+    blk1, nb1 = ops.conv3_active_blocks(boxes_x, s1, o1, block_rows, block_cols=block_cols)
     maps = ops.broadcast_rows(pk.p3_background(), 2 * n_box, torch.empty(2 * n_box, 8, 8, 1024, dtype=torch.bfloat16, device=DEV))
-    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows)
+    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows, block_cols=block_cols)
     sub_maps, obj_maps, bg = maps[:n_box], maps[n_box:], pk.p3_background()
     # keys and sorted order
     keys = ops.pair_cell_keys(boxes_x, sub_t, obj_t).cpu().numpy()
@@ -117,8 +117,9 @@ def test_difference_epilogue_and_keys(block_rows):
     # difference epilogue into a poisoned, then tile-zeroed buffer
     d = torch.full((n, 64, 1024), float("nan"), dtype=torch.bfloat16, device=DEV)
     ops.cells_zero(torch.from_numpy(tm).to(DEV), 256, n, d)
-    blocks, n_blocks = ops.conv3_shared_blocks(boxes_x, sub_t, obj_t, block_rows)
-    pk.conv3_diff(p2, d.view(n, 8, 8, 1024), n, blocks, n_blocks, block_rows, sub_maps, obj_maps, sub_t, obj_t, row_of)
+    blocks, n_blocks = ops.conv3_shared_blocks(boxes_x, sub_t, obj_t, block_rows, block_cols=block_cols)
+    pk.conv3_diff(p2, d.view(n, 8, 8, 1024), n, blocks, n_blocks, block_rows, sub_maps, obj_maps, sub_t, obj_t, row_of,
+                  block_cols=block_cols)
     torch.cuda.synchronize()
     ref = ((dense.float() - sub_maps[sub_t.long()].float()) - (obj_maps[obj_t.long()].float() - bg.float())).to(torch.bfloat16)
     got = d.view(n, 8, 8, 1024)[row_of.long()]                                 # back in pair order
@@ -133,8 +134,8 @@ def test_difference_epilogue_and_keys(block_rows):
     assert float(ref[~both].float().abs().max()) == 0.0                        # and the dense formula agrees they are zero
 
 
-@pytest.mark.parametrize("tiled", [True, False])
-def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled):
+@pytest.mark.parametrize("tiled,block_cols", [(True, 4), (False, 4), (True, 8)])
+def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled, block_cols):
     """Whole forward, chunked and overlapped: joint probabilities within 2e-3 of the dense path (north_star's fp tolerance)."""
     from scene_graph_commonsense_b200 import pipeline
     pk = _packed(gain=40.0)
@@ -143,7 +144,7 @@ def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled):
     outs = []
     for fc1_shared in (False, True):
         pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=700, conv3_block_rows=4, conv3_shared=True,
-                                         fc1_shared=fc1_shared)
+                                         fc1_shared=fc1_shared, conv3_block_cols=block_cols)
         b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
         pairs = pipe.enumerate_pairs(b)
         if not tiled:

@@ -50,32 +50,35 @@ def _random_boxes(n, seed):
     return b
 
 
-@pytest.mark.parametrize("block_rows", [8, 4])
-def test_work_list_covers_active_cells(block_rows):
+SHAPES = [(8, 8), (4, 8), (4, 4)]           # (block_rows, block_cols) in conv3 pixels
+
+
+@pytest.mark.parametrize("block_rows,block_cols", SHAPES)
+def test_work_list_covers_active_cells(block_rows, block_cols):
     from scene_graph_commonsense_b200 import ops
     boxes = _random_boxes(40, 5)
     n_box = boxes.shape[0]
     sub, obj = np.nonzero(~np.eye(n_box, dtype=bool))
     blocks, n_blocks = ops.conv3_active_blocks(boxes.to(DEV), torch.from_numpy(sub.astype(np.int32)).to(DEV),
-                                               torch.from_numpy(obj.astype(np.int32)).to(DEV), block_rows)
+                                               torch.from_numpy(obj.astype(np.int32)).to(DEV), block_rows, block_cols=block_cols)
     nb = int(n_blocks.item())
     e = blocks[:nb].cpu().numpy()
     pair, cy, cx = e >> 8, (e >> 4) & 15, e & 15
-    hc = block_rows // 2
+    hc, wc = block_rows // 2, block_cols // 2
     assert (np.diff(pair) >= 0).all() and pair.max() < len(sub)                  # pairs in order
-    assert (cx <= 4).all() and (cy <= 8 - hc).all()                              # blocks stay inside the 16 x 16 map
+    assert (cx <= 8 - wc).all() and (cy <= 8 - hc).all()                         # blocks stay inside the 16 x 16 map
     counts = np.bincount(pair, minlength=len(sub))
-    assert counts.max() <= 32 // block_rows                                      # never more than the dense tiling
+    assert counts.max() <= 256 // (block_rows * block_cols)                      # never more than the dense tiling
     cover = np.zeros((len(sub), 8, 8), bool)
     for p, y, x in zip(pair, cy, cx):
-        cover[p, y:y + hc, x:x + 4] = True
+        cover[p, y:y + hc, x:x + wc] = True
     masks = np.stack([_cell_mask(b) for b in boxes.numpy()])
     want = masks[sub] | masks[obj]
     assert not (want & ~cover).any()
     assert (counts[~want.reshape(len(sub), -1).any(1)] == 0).all()               # two empty boxes: nothing to compute
     # an empty pair list is a no-op with n_blocks == 0
     z = torch.zeros(0, dtype=torch.int32, device=DEV)
-    _, n0 = ops.conv3_active_blocks(boxes.to(DEV), z, z, block_rows)
+    _, n0 = ops.conv3_active_blocks(boxes.to(DEV), z, z, block_rows, block_cols=block_cols)
     assert int(n0.item()) == 0
 
 
@@ -84,8 +87,8 @@ def _packed(seed=0, gain=1.0):
     return model.PackedHead(synthetic.head_state_dict(seed=seed, logit_gain=gain), DEV)
 
 
-@pytest.mark.parametrize("block_rows,m_sub", [(8, 2), (4, 2), (8, 1), (4, 1)])
-def test_sparse_conv3_equals_dense_bit_for_bit(block_rows, m_sub):
+@pytest.mark.parametrize("block_rows,m_sub,block_cols", [(8, 2, 8), (4, 2, 8), (8, 1, 8), (4, 1, 8), (4, 2, 4), (4, 1, 4)])
+def test_sparse_conv3_equals_dense_bit_for_bit(block_rows, m_sub, block_cols):
     """conv3_1 + ReLU + pool on the listed blocks over a background pre-fill == the dense kernel, every bf16 bit."""
     from scene_graph_commonsense_b200 import ops
     from scene_graph_commonsense_b200._lib import EPI_POOL_BF16, GEMM_CONV3, GEMM_CONV3_BLOCKS
@@ -106,22 +109,23 @@ def test_sparse_conv3_equals_dense_bit_for_bit(block_rows, m_sub):
     dense = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=DEV)
     ops.tc_gemm(p2, pk.w3, dense, n * 256, 1024, 9 * 512, bias=pk.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16, n_img=n, h=16,
                 w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=2)
-    blocks, n_blocks = ops.conv3_active_blocks(boxes, sub_t, obj_t, block_rows)
+    blocks, n_blocks = ops.conv3_active_blocks(boxes, sub_t, obj_t, block_rows, block_cols=block_cols)
     sparse = ops.broadcast_rows(pk.p3_background(), n, torch.empty_like(dense))
     assert torch.equal(sparse[n - 1], pk.p3_background()[0])
     ops.tc_gemm(p2, pk.w3, sparse, n * 256, 1024, 9 * 512, bias=pk.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_BF16, n_img=n,
-                h=16, w=16, c_total=512, c_base=0, c_in=512, m_sub=m_sub, blocks=blocks, n_blocks=n_blocks, block_rows=block_rows)
+                h=16, w=16, c_total=512, c_base=0, c_in=512, m_sub=m_sub, blocks=blocks, n_blocks=n_blocks, block_rows=block_rows,
+                block_cols=block_cols)
     torch.cuda.synchronize()
     nb = int(n_blocks.item())
-    assert 0 < nb < n * (32 // block_rows)                                       # the list is really sparse on these boxes
+    assert 0 < nb < n * (256 // (block_rows * block_cols))                                       # the list is really sparse on these boxes
     bad = (dense.view(torch.int16) != sparse.view(torch.int16)).flatten(1).any(1).nonzero().flatten().tolist()
     assert not bad, "pairs %s differ (boxes %s)" % (bad[:5], [(int(sub[keep][i]), int(obj[keep][i])) for i in bad[:5]])
     # the background really is what a box-free pair produces, and it is not trivially zero
     assert float(pk.p3_background().float().abs().max()) > 0
 
 
-@pytest.mark.parametrize("block_rows", [8, 4])
-def test_shared_list_and_assembly_equal_dense_bit_for_bit(block_rows):
+@pytest.mark.parametrize("block_rows,block_cols", SHAPES)
+def test_shared_list_and_assembly_equal_dense_bit_for_bit(block_rows, block_cols):
     """Shared-footprint path: per-box maps ((box, empty) / (empty, box)) + background assembled per pair, conv3_1 only on the
     cover of the cells BOTH boxes reach == the dense kernel on every pair, every bf16 bit; the list covers the intersection."""
     from scene_graph_commonsense_b200 import ops
@@ -147,37 +151,37 @@ def test_shared_list_and_assembly_equal_dense_bit_for_bit(block_rows):
     emp = torch.full((n_box,), n_box, dtype=torch.int32, device=DEV)
     s1, o1 = torch.cat((idx, emp)), torch.cat((emp, idx))
     p2b = ops.pair_relu_pool(u, v, None, s1, o1, 32)
-    blk1, nb1 = ops.conv3_active_blocks(boxes_x, s1, o1, block_rows)
+    blk1, nb1 = ops.conv3_active_blocks(boxes_x, s1, o1, block_rows, block_cols=block_cols)
     maps = ops.broadcast_rows(pk.p3_background(), 2 * n_box, torch.empty(2 * n_box, 8, 8, 1024, dtype=torch.bfloat16, device=DEV))
-    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows)
+    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows, block_cols=block_cols)
     # work list = cover of the intersection
-    blocks, n_blocks = ops.conv3_shared_blocks(boxes_x, sub_t, obj_t, block_rows)
+    blocks, n_blocks = ops.conv3_shared_blocks(boxes_x, sub_t, obj_t, block_rows, block_cols=block_cols)
     nb = int(n_blocks.item())
     e = blocks[:nb].cpu().numpy()
     pair, cy, cx = e >> 8, (e >> 4) & 15, e & 15
-    hc = block_rows // 2
+    hc, wc = block_rows // 2, block_cols // 2
     cover = np.zeros((n, 8, 8), bool)
     for p, y, x in zip(pair, cy, cx):
-        cover[p, y:y + hc, x:x + 4] = True
+        cover[p, y:y + hc, x:x + wc] = True
     masks = np.stack([_cell_mask(b) for b in boxes.numpy()])
     want = masks[sub] & masks[obj]
     assert not (want & ~cover).any()
     assert (np.bincount(pair, minlength=n)[~want.reshape(n, -1).any(1)] == 0).all()    # disjoint reach: nothing per pair
-    _, nb_union = ops.conv3_active_blocks(boxes_x, sub_t, obj_t, block_rows)
+    _, nb_union = ops.conv3_active_blocks(boxes_x, sub_t, obj_t, block_rows, block_cols=block_cols)
     assert 0 < nb < int(nb_union.item())
     # assembly (poisoned buffer: every cell must be written by the assembly or by the listed blocks)
     out = torch.full((n, 8, 8, 1024), float("nan"), dtype=torch.bfloat16, device=DEV)
     ops.p3_assemble(pk.p3_background(), maps[:n_box], maps[n_box:], boxes_x[:n_box], sub_t, obj_t, out)
     written = ~torch.isnan(out.float()).any(3).cpu().numpy()          # [n, 8, 8] cells the assembly wrote
     assert (written == ~want).all()
-    pk.conv3_blocks(p2, out, n, blocks, n_blocks, block_rows)
+    pk.conv3_blocks(p2, out, n, blocks, n_blocks, block_rows, block_cols=block_cols)
     torch.cuda.synchronize()
     bad = (dense.view(torch.int16) != out.view(torch.int16)).flatten(1).any(1).nonzero().flatten().tolist()
     assert not bad, "pairs %s differ (boxes %s)" % (bad[:5], [(int(sub[i]), int(obj[i])) for i in bad[:5]])
 
 
-@pytest.mark.parametrize("block_rows,shared", [(8, False), (4, False), (8, True), (4, True)])
-def test_pipeline_sparse_equals_dense(block_rows, shared):
+@pytest.mark.parametrize("block_rows,shared,block_cols", [(8, False, 8), (4, False, 8), (8, True, 8), (4, True, 8), (4, False, 4), (4, True, 4)])
+def test_pipeline_sparse_equals_dense(block_rows, shared, block_cols):
     """Whole forward (chunked + overlapped, and the generic pair-list path): identical raw head outputs and counters."""
     from scene_graph_commonsense_b200 import pipeline
     pk = _packed(gain=40.0)
@@ -185,7 +189,8 @@ def test_pipeline_sparse_equals_dense(block_rows, shared):
     samples[0].bbox[:6] = torch.tensor(EDGE_BOXES[:6], dtype=samples[0].bbox.dtype)
     outs = []
     for br in (0, block_rows):
-        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=120, conv3_block_rows=br, conv3_shared=shared, fc1_shared=False)
+        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=120, conv3_block_rows=br, conv3_shared=shared, fc1_shared=False,
+                                         conv3_block_cols=block_cols)
         b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
         pairs = pipe.enumerate_pairs(b)
         rel, sup, conn, logsig = pipe.forward_pairs(b, pairs)
