@@ -298,9 +298,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
-    } else if (lane == 0 && blk_mode) {
+    } else if (blk_mode) {
       // one stage per (channel block, kx, ky) - the K order of the patch pipeline, so results are bit-identical to the dense
-      // kernel; every block of the tile contributes one {64 ch, blk_w x, blk_h y} box shifted by the tap (TMA zero-fills the halo)
+      // kernel; every block of the tile contributes one {64 ch, blk_w x, blk_h y} box shifted by the tap (TMA zero-fills the halo).
+      // The whole warp runs the loop: lane 0 waits for the slot and posts the byte count, then lane i issues the box of block i
+      // and the last lane the weight tile, so the up to 17 TMA instructions of a stage issue side by side instead of in a chain.
       int stage = 0;
       uint32_t phase = 0;
       const int cblks = p.c_in / BK;
@@ -309,21 +311,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(p, tiles_m, tile, m_blk, n_blk);
-        int e[MS * 8];
-#pragma unroll
-        for (int i = 0; i < MS * 8; ++i) e[i] = i < nblk ? __ldg(p.blocks + min(m_blk * nblk + i, n_blocks - 1)) : 0;
+        const int e = lane < nblk ? __ldg(p.blocks + min(m_blk * nblk + lane, n_blocks - 1)) : 0;
+        const int ex = 2 * (e & 15) - 1, ey = 2 * ((e >> 4) & 15) - 1, eimg = e >> 8;
         for (int cb = 0; cb < cblks; ++cb) {
           for (int kx = 0; kx < 3; ++kx) {
             for (int ky = 0; ky < 3; ++ky) {
-              mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
-              mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-#pragma unroll
-              for (int i = 0; i < MS * 8; ++i)
-                if (i < nblk)
-                  tma_load_4d(a_dst + i * blk_bytes, &tmap_a, full_bar(stage), p.c_base + cb * BK, 2 * (e[i] & 15) + kx - 1,
-                              2 * ((e[i] >> 4) & 15) + ky - 1, e[i] >> 8);
-              tma_load_2d(a_dst + MS * A_SUB_BYTES, &tmap_b, full_bar(stage), ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN);
+              if (lane == 0) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+              }
+              __syncwarp();
+              if (lane < nblk)
+                tma_load_4d(a_dst + lane * blk_bytes, &tmap_a, full_bar(stage), p.c_base + cb * BK, ex + kx, ey + ky, eimg);
+              else if (lane == 31)
+                tma_load_2d(a_dst + MS * A_SUB_BYTES, &tmap_b, full_bar(stage), ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN);
               if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
             }
           }

@@ -12,6 +12,8 @@ The nn.Conv2d / nn.Linear children are parameter containers only; forward never 
 once (bf16, GEMM-friendly layouts) into a `PackedHead`, lazily and again whenever a parameter changes.
 Inference only (eval-mode semantics: dropout is the identity); there is no CPU path.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -150,11 +152,16 @@ class PackedHead:
                     tag="fc1_box")
         return out
 
-    def fc1_shared_fc2(self, d, n, k_masks, f_sub, f_obj, row_sub, row_obj, bias_eff, out_rows, raw):
+    def fc1_shared_fc2(self, d, n, k_masks, f_sub, f_obj, row_sub, row_obj, bias_eff, out_rows, raw, group_m=None):
         """model.py:149,175 on the difference operand d [n,8,8,1024] (rows in sorted order, zero outside the cells both boxes reach):
         h1 = relu(d @ W1^T [only the cells in the tile's mask] + f_sub[row_sub] + f_obj[row_obj] + bias_eff), raw[out_rows] = h1 @ W2^T."""
         h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=d.device)
-        ops.tc_gemm(d, self.w_fc1, h1, n, 4096, 65536, bias=bias_eff, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU, group_m=37,
+        # rasterisation: a band of 9 M tiles x all 16 N tiles = 144 CTAs run together.  The rows are sorted by cell rectangle, so the
+        # 9 tiles walk (nearly) the same K cells in step: each weight panel and each operand tile comes out of HBM once per band
+        # and is shared through L2 (bands of 37 x 4 re-read the operand 4x and thrashed L2: 38.9 GB of DRAM reads per launch, ncu r01y)
+        if group_m is None:
+            group_m = int(os.environ.get("HC_FC1_GROUP_M", "9"))
+        ops.tc_gemm(d, self.w_fc1, h1, n, 4096, 65536, bias=bias_eff, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU, group_m=group_m,
                     m_sub=2, tag="fc1", k_masks=k_masks, k_cell=1024, add_a=f_sub, add_a_rows=row_sub, add_b=f_obj, add_b_rows=row_obj)
         ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8, tag="fc2", out_rows=out_rows)
         return raw
