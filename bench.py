@@ -294,6 +294,13 @@ def run_ours(args):
     if roof_conv3 is not None:
         if blocks_step is not None:
             roof_conv3["dense_equivalent_tflops"] = roof_conv3["achieved"] / conv3_exec_frac
+            tp = os.path.join(ROOT, "profiles", "ncu_summary_r01y.json")      # committed ncu --set full capture of the default path
+            if os.path.exists(tp) and args.conv3 == "shared44" and pipe.fc1_shared and args.workload == "cfg2":
+                for r in json.load(open(tp)).get("launches", []):
+                    if r.get("what", "").startswith("conv3_1 difference epilogue, full chunk"):
+                        roof_conv3["traffic"] = r.get("dram_bytes_per_launch")
+                        roof_conv3["traffic_note"] = ("dram__bytes_read+write of one full-chunk launch (3.58 ms under ncu, 12 480 pairs); "
+                                                      "the kernel is bound by L2->SM delivery (35.2 GB per launch through xbar->L1), not DRAM")
         else:
             tp = os.path.join(ROOT, "profiles", "conv3_dram_bytes.json")    # the committed ncu DRAM figure is the dense kernel's
             if os.path.exists(tp):
