@@ -170,6 +170,7 @@ class RelationPipeline:
         # that cell rectangle and the GEMM visits, per 256-row tile, only the K cells some row of the tile uses (exact: the skipped
         # operand is zero).  Same sums up to fp32 rounding order and one bf16 rounding of d - not bit-identical to the dense fc1.
         self.fc1_shared = bool(fc1_shared) and self.conv3_shared
+        self.fc1_window_pairs = 262144       # pairs per shared-fc1 window: its operand is 128 KB per pair (32 GB at the cap)
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.last_k_masks = None             # int64 [n_tiles] device tensor: K-cell masks of the last shared fc1
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
@@ -380,34 +381,61 @@ class RelationPipeline:
     def _forward_pairs_fc1_shared(self, b: DeviceBatch, pairs):
         """`forward_pairs` with the shared-footprint fc1: per-box conv3_1 maps and their fc1 rows once per box; per pair only the
         conv3_1 blocks covering the cells both boxes reach, written as differences into the sorted operand d; ONE K-cell-sparse fc1
-        + fc2 over all pairs of the window; raw comes back in pair order through the fc2 epilogue's row map."""
-        pk, fs, br, bc = self.packed, self.fs, self.conv3_block_rows, self.conv3_block_cols
+        + fc2 over all pairs of a window; raw comes back in pair order through the fc2 epilogue's row map.  The operand is 128 KB
+        per pair (only the visited cells are touched), so batches beyond `fc1_window_pairs` are cut into image-aligned windows."""
+        pk, fs = self.packed, self.fs
         n, n_box = pairs["n"], b.boxes.shape[0]
         dev = self.device
         boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))      # + the empty box (all background), partner of every box
         u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))))
         maps, nblk_box = self.box_maps(boxes_x, u, v, with_background_row=True)
-        sub_maps, obj_maps = maps[:n_box], maps[n_box:2 * n_box]
         f_box = pk.fc1_rows(maps, 2 * n_box + 1)                     # fc1 (no bias) of (box, empty), (empty, box), background
         bias_eff = (pk.b_fc1 - f_box[2 * n_box]).contiguous()
-        # row order of the fc1 operand: pairs sorted by the cell rectangle both boxes reach (pairs with none last)
-        keys = ops.pair_cell_keys(b.boxes, pairs["sub"], pairs["obj"], fs)
-        perm64 = torch.sort(keys, stable=True)[1]                    # sorted row -> pair
-        perm = perm64.to(torch.int32)
-        row_of = torch.empty_like(perm)
-        row_of[perm64] = torch.arange(n, dtype=torch.int32, device=dev)
-        row_sub, row_obj = pairs["sub"][perm64].contiguous(), pairs["obj"][perm64].contiguous()
-        masks = ops.tile_cell_masks(b.boxes, row_sub, row_obj, 256, fs)
-        d = torch.empty(n, 64, 1024, dtype=torch.bfloat16, device=dev)
-        ops.cells_zero(masks, 256, n, d)
+        raw = torch.empty(n, 512, dtype=torch.float32, device=dev)
         tiled = "offsets_host" in pairs
+        lut = None
         if tiled:
+            off = pairs["offsets_host"]
             n_max = int(np.max(np.diff(b.box_offsets_host))) if b.box_offsets_host is not None else int(
                 (b.box_offsets[1:] - b.box_offsets[:-1]).max().item())
             lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
-            chunks = self._image_chunks(pairs["offsets_host"])
+            windows = []                                             # (first image, pair range) of each window
+            for img0, n_img, base, cnt in self._greedy_chunks(off, self.fc1_window_pairs):
+                chunks = [(img0 + c[0], c[1], c[2], c[3]) for c in self._image_chunks(off[img0:img0 + n_img + 1])]
+                windows.append((base, base + cnt, chunks))
         else:
-            chunks = [(0, 0, s, min(n, s + self.chunk_pairs) - s) for s in range(0, n, self.chunk_pairs)]
+            windows = []
+            for w0 in range(0, n, self.fc1_window_pairs):
+                w1 = min(n, w0 + self.fc1_window_pairs)
+                windows.append((w0, w1, [(0, 0, s, min(w1, s + self.chunk_pairs) - s) for s in range(w0, w1, self.chunk_pairs)]))
+        nblks, masks_all = [], []
+        for w0, w1, chunks in windows:
+            nblk, masks = self._fc1_shared_window(b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw)
+            nblks.append(nblk)
+            masks_all.append(masks)
+        self.last_n_blocks = torch.cat(nblks + [nblk_box])
+        self.last_k_masks = torch.cat(masks_all)
+        relation, sup, conn, logsig, _ = pk.heads(raw, pairs["sub"], pairs["obj"], b.cats, b.supers)
+        return relation, sup, conn, logsig
+
+    def _fc1_shared_window(self, b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw):
+        """Pairs [w0, w1) of the batch: sort, conv3_1 differences chunk by chunk (pooling of chunk k+1 under the GEMM of chunk k),
+        then one K-cell-sparse fc1 + fc2 into raw[w0:w1]."""
+        pk, fs, br, bc = self.packed, self.fs, self.conv3_block_rows, self.conv3_block_cols
+        dev = self.device
+        n, n_box = w1 - w0, b.boxes.shape[0]
+        sub_w, obj_w = pairs["sub"][w0:w1], pairs["obj"][w0:w1]
+        sub_maps, obj_maps = maps[:n_box], maps[n_box:2 * n_box]
+        # row order of the fc1 operand: pairs sorted by the cell rectangle both boxes reach (pairs with none last)
+        keys = ops.pair_cell_keys(b.boxes, sub_w, obj_w, fs)
+        perm64 = torch.sort(keys, stable=True)[1]                    # sorted row -> pair (window-local)
+        perm = perm64.to(torch.int32)
+        row_of = torch.empty_like(perm)
+        row_of[perm64] = torch.arange(n, dtype=torch.int32, device=dev)
+        row_sub, row_obj = sub_w[perm64].contiguous(), obj_w[perm64].contiguous()
+        masks = ops.tile_cell_masks(b.boxes, row_sub, row_obj, 256, fs)
+        d = torch.empty(n, 64, 1024, dtype=torch.bfloat16, device=dev)
+        ops.cells_zero(masks, 256, n, d)
         cap = max(c[3] for c in chunks)
         two = self.overlap and len(chunks) > 1
         bufs = [torch.empty(cap, fs // 2, fs // 2, 512, dtype=torch.bfloat16, device=dev) for _ in range(2 if two else 1)]
@@ -426,7 +454,7 @@ class RelationPipeline:
                     side.wait_event(ready)
                     if k >= 2:
                         side.wait_event(gemm_done[k - 2])              # buffer free again
-                if tiled:
+                if lut is not None:
                     ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, fs, out=buf)
                 else:
                     ops.pair_relu_pool(u, v, None, sub_k, obj_k, fs, out=buf)
@@ -435,19 +463,15 @@ class RelationPipeline:
                 pooled.record(side)
             if side is not main:
                 main.wait_event(pooled)
-            pk.conv3_diff(buf, d, cnt, blk, nblk[k:k + 1], br, sub_maps, obj_maps, sub_k, obj_k, row_of[base:base + cnt],
+            pk.conv3_diff(buf, d, cnt, blk, nblk[k:k + 1], br, sub_maps, obj_maps, sub_k, obj_k, row_of[base - w0:base - w0 + cnt],
                           m_sub=self.conv3_m_sub, block_cols=bc)
             ev = torch.cuda.Event()
             ev.record(main)
             gemm_done.append(ev)
         if side is not main:
             main.wait_stream(side)
-        raw = torch.empty(n, 512, dtype=torch.float32, device=dev)
-        pk.fc1_shared_fc2(d, n, masks, f_box[:n_box], f_box[n_box:], row_sub, row_obj, bias_eff, perm, raw)
-        self.last_n_blocks = torch.cat((nblk, nblk_box))
-        self.last_k_masks = masks
-        relation, sup, conn, logsig, _ = pk.heads(raw, pairs["sub"], pairs["obj"], b.cats, b.supers)
-        return relation, sup, conn, logsig
+        pk.fc1_shared_fc2(d, n, masks, f_box[:n_box], f_box[n_box:], row_sub, row_obj, bias_eff, perm, raw[w0:w1])
+        return nblk, masks
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:

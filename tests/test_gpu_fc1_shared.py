@@ -158,3 +158,27 @@ def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled, block_cols):
     assert float((rel0.exp() - rel1.exp()).abs().max()) <= 2e-3
     assert float((sup0.exp() - sup1.exp()).abs().max()) <= 2e-3
     assert float((torch.sigmoid(conn0) - torch.sigmoid(conn1)).abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize("tiled", [True, False])
+def test_fc1_windows_are_bit_identical_to_one_window(tiled):
+    """A batch cut into several shared-fc1 windows (operand bounded at 128 KB per pair) gives the same bits as one window: a row's
+    GEMM result does not depend on the tile, the sort order or the window it lands in."""
+    from scene_graph_commonsense_b200 import pipeline
+    pk = _packed(gain=40.0)
+    samples = synthetic.make_batch([80, 81, 82, 83, 84], [11, 14, 3, 16, 9], p_rel=0.5)
+    outs = []
+    for cap in (262144, 250):
+        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=130)
+        pipe.fc1_window_pairs = cap
+        b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
+        pairs = pipe.enumerate_pairs(b)
+        if not tiled:
+            pairs = {k: val for k, val in pairs.items() if k != "offsets_host"}
+        rel, sup, conn, logsig = pipe.forward_pairs(b, pairs)
+        pipe.evaluate(b, pairs, rel, sup, logsig, connectivity=conn)
+        torch.cuda.synchronize()
+        outs.append((rel.clone(), sup.clone(), conn.clone(), pipe.counters.clone(), int(pipe.last_k_masks.numel())))
+    assert outs[1][4] > outs[0][4]                       # really several windows
+    for a, c in zip(outs[0][:4], outs[1][:4]):
+        assert torch.equal(a, c)
