@@ -72,6 +72,35 @@ def run_size(n_images, n_boxes, dev, iters, peak, results, tag):
     rec("pairs_enumerate (4 kernels + 1 D2H of offsets)", n_box * 16 + n_tri * 5 + P * 21, lambda: pipe.enumerate_pairs(b),
         "includes the [B+1]-int D2H read that sizes the dense launches")
 
+    # shared-footprint bookkeeping: sort keys, per-tile K-cell masks, conv3_1 work list of one chunk, operand zero fill
+    out_fp = {}
+
+    def keys():
+        out_fp["keys"] = ops.pair_cell_keys(b.boxes, pairs["sub"], pairs["obj"])
+
+    rec("pair_cell_keys_kernel", P * 12 + n_box * 16, keys, "cell rectangle both boxes reach -> sort key; read 2 box ids, write 1 key per pair")
+    perm = torch.sort(out_fp["keys"], stable=True)[1]
+    row_sub, row_obj = pairs["sub"][perm].contiguous(), pairs["obj"][perm].contiguous()
+
+    def masks():
+        out_fp["masks"] = ops.tile_cell_masks(b.boxes, row_sub, row_obj, 256)
+
+    rec("tile_cell_masks_kernel", P * 8 + (P // 256 + 1) * 8 + n_box * 16, masks, "one warp per 256-row GEMM tile: OR of the rows' cell masks")
+    cn = min(P, 12480)
+    blk = torch.empty(cn * 16, dtype=torch.int32, device=dev)
+    nb = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.conv3_shared_blocks(b.boxes, pairs["sub"][:cn], pairs["obj"][:cn], 4, 32, blocks=blk, n_blocks=nb, block_cols=4)
+    rec("conv3_blocks_kernel (shared footprint, 4x4-pixel blocks, one 12 480-pair chunk)", cn * 8 + int(nb.item()) * 4,
+        lambda: ops.conv3_shared_blocks(b.boxes, pairs["sub"][:cn], pairs["obj"][:cn], 4, 32, blocks=blk, n_blocks=nb, block_cols=4),
+        "ONE CTA (deterministic order, device-side count): latency-sized, runs on the pooling stream")
+    if P <= 200000:
+        d = torch.empty(P, 64, 1024, dtype=torch.bfloat16, device=dev)
+        cells = int(np.unpackbits(out_fp["masks"].cpu().numpy().view(np.uint8)).sum())
+        rec("cells_zero_kernel", cells * 256 * 2048, lambda: ops.cells_zero(out_fp["masks"], 256, P, d),
+            "zero fill of the visited cells of the fc1 difference operand (%d cells x 256 rows x 2 KB)" % cells)
+        del d
+    del blk, row_sub, row_obj, perm
+
     # R6/R7 hierarchical head: read raw 2 KiB/pair + labels, write relation 200 + super 12 + conn 4 + logsig 4
     sd = synthetic.head_state_dict(seed=0, logit_gain=40.0)
     f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
