@@ -26,7 +26,7 @@ class GemmDesc(C.Structure):
                 ("n_img", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("c_total", C.c_int32), ("c_base", C.c_int32), ("c_in", C.c_int32),
                 ("group_m", C.c_int32), ("m_sub", C.c_int32), ("mul", C.c_void_p), ("ld_mul", C.c_int64),
-                ("blocks", C.c_void_p), ("n_blocks", C.c_void_p), ("block_rows", C.c_int32), ("block_cols", C.c_int32),
+                ("blocks", C.c_void_p), ("n_blocks", C.c_void_p), ("block_rows", C.c_int32), ("block_cols", C.c_int32), ("cta_pairs", C.c_int32),
                 ("k_masks", C.c_void_p), ("k_cell", C.c_int64),
                 ("add_a", C.c_void_p), ("add_a_rows", C.c_void_p), ("add_b", C.c_void_p), ("add_b_rows", C.c_void_p), ("ld_add", C.c_int64),
                 ("out_rows", C.c_void_p),

@@ -21,6 +21,7 @@
 //
 // CTA tile = (MS*128) x BN: MS 128-row sub-tiles share every B stage (halves L2->smem weight traffic for MS=2).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "hc_common.cuh"
 
@@ -73,6 +74,7 @@ struct Params {
   const int* n_blocks;           // device scalar: entries in the work list
   int blk_h;                     // pixel rows per block (8 or 4)
   int blk_w;                     // pixel columns per block (8 or 4)
+  int cl2;                       // block mode: CTA pairs (cluster of 2) on two M tiles of one N tile share the weight tile by TMA multicast
   // K-cell-sparse plain GEMM: bit c of k_masks[CTA m tile] set = K blocks [c*k_cell_kb, (c+1)*k_cell_kb) are visited
   const unsigned long long* k_masks;
   int k_cell_kb;
@@ -121,6 +123,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// half of a B tile to BOTH CTAs of the pair: lands at the same offset in each CTA's shared memory, complete_tx on each CTA's barrier
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(tmap), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
@@ -155,6 +173,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "}" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
+}
+// the same arrival on the barrier at this offset in every CTA of `mask` (frees a pipeline slot that a peer's multicast writes into)
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -214,7 +237,12 @@ __device__ __forceinline__ void store_bf16_row(const uint32_t (&r)[32], const fl
 
 // tile id -> (m block, n block): bands of `group_m` m-blocks; inside a band the n index is the slow one, so a
 // wave of consecutive tile ids shares few B column-panels and a bounded set of A row-panels through L2.
-__device__ __forceinline__ void tile_coords(const Params& p, int tiles_m, int tile, int& m_blk, int& n_blk) {
+__device__ __forceinline__ void tile_coords(const Params& p, int tiles_m, int tile, int& m_blk, int& n_blk, int rank = 0) {
+  if (p.cl2) {                    // CTA pair: M tiles (2t, 2t+1) of one N tile; the 4 N tiles of a pair of M tiles are consecutive
+    m_blk = (tile / p.tiles_n) * 2 + rank;
+    n_blk = tile % p.tiles_n;
+    return;
+  }
   int per_band = p.group_m * p.tiles_n;
   int band = tile / per_band;
   int in = tile - band * per_band;
@@ -226,7 +254,8 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tiles_m, int ti
 // =============================================================================================== kernel
 template <int BN, int MS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_bh, const Params p) {
   using C = Cfg<BN, MS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
@@ -251,11 +280,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int blk_per_sub = blk_mode ? BM / (p.blk_w * p.blk_h) : 1;  // blocks per 128-row sub-tile (2, 4 or 8)
   const int n_blocks = blk_mode ? __ldg(p.n_blocks) : 0;
   const int tiles_m = blk_mode ? (n_blocks + MS * blk_per_sub - 1) / (MS * blk_per_sub) : p.tiles_m;
-  const int num_tiles = tiles_m * p.tiles_n;
+  // CTA pairs (p.cl2): both CTAs walk the same sequence of pair tiles, so their pipelines run in lock step
+  const int rank = p.cl2 ? (int)cluster_ctarank() : 0;
+  const int num_tiles = p.cl2 ? ((tiles_m + 1) / 2) * p.tiles_n : tiles_m * p.tiles_n;
+  const int tile0 = p.cl2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = p.cl2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int num_kb = p.K / BK;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.cl2 ? 2 : 1); }   // pair: both MMA warps free a slot
     for (int s = 0; s < C::ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
     for (int s = 0; s < C::PA_SLOTS; ++s) { mbar_init(pa_full(s), 1); mbar_init(pa_empty(s), 1); }
     for (int s = 0; s < C::PB_SLOTS; ++s) { mbar_init(pb_full(s), 1); mbar_init(pb_empty(s), 1); }
@@ -267,6 +300,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cl2) cluster_sync_all();          // the peer's barriers exist before any multicast / remote arrive can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -277,9 +311,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t a_phase = 0, b_phase = 0;
       const int cblks = p.c_in / BK;
       const int per_img = p.tiles_x * p.tiles_y;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         int m_blk, n_blk;
-        tile_coords(p, tiles_m, tile, m_blk, n_blk);
+        tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
         const int img = m_blk / per_img;
         const int r = m_blk - img * per_img;
         const int y0 = (r / p.tiles_x) * (8 * MS), x0 = (r % p.tiles_x) * 16;
@@ -308,9 +342,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int cblks = p.c_in / BK;
       const int nblk = MS * blk_per_sub;
       const uint32_t blk_bytes = (uint32_t)(p.blk_w * p.blk_h) * 128u;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         int m_blk, n_blk;
-        tile_coords(p, tiles_m, tile, m_blk, n_blk);
+        tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
         const int e = lane < nblk ? __ldg(p.blocks + min(m_blk * nblk + lane, n_blocks - 1)) : 0;
         const int ex = 2 * (e & 15) - 1, ey = 2 * ((e >> 4) & 15) - 1, eimg = e >> 8;
         for (int cb = 0; cb < cblks; ++cb) {
@@ -324,8 +358,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               __syncwarp();
               if (lane < nblk)
                 tma_load_4d(a_dst + lane * blk_bytes, &tmap_a, full_bar(stage), p.c_base + cb * BK, ex + kx, ey + ky, eimg);
-              else if (lane == 31)
-                tma_load_2d(a_dst + MS * A_SUB_BYTES, &tmap_b, full_bar(stage), ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN);
+              else if (lane == 31) {
+                if (p.cl2)     // this CTA fetches its half of the weight tile for both CTAs of the pair
+                  tma_load_2d_mc(a_dst + MS * A_SUB_BYTES + (uint32_t)rank * (C::B_BYTES / 2), &tmap_bh, full_bar(stage),
+                                 ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN + rank * (BN / 2), (uint16_t)3);
+                else
+                  tma_load_2d(a_dst + MS * A_SUB_BYTES, &tmap_b, full_bar(stage), ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN);
+              }
               if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
             }
           }
@@ -334,9 +373,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         int m_blk, n_blk;
-        tile_coords(p, tiles_m, tile, m_blk, n_blk);
+        tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
         auto load_kb = [&](int kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
@@ -367,7 +406,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int a_slot = 0, b_slot = 0, acc = 0;
       uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
       const int n_ax = (p.c_in / BK) * 3;                 // (channel block, kx) steps per tile
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         for (int ax = 0; ax < n_ax; ++ax) {
@@ -401,7 +440,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t idesc = umma_idesc<BN>();
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator stage
         tc_fence_after();
         uint32_t started = 0;                             // 0 until the first MMA of the tile (which overwrites the accumulator)
@@ -419,12 +458,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (started | k) ? 1u : 0u);
           }
           started = 1;
-          umma_commit(empty_bar(stage));                  // smem slot free once these MMAs retire
+          if (p.cl2) umma_commit_mc(empty_bar(stage), (uint16_t)3);   // the slot is written by both CTAs' multicasts: free it in both
+          else umma_commit(empty_bar(stage));             // smem slot free once these MMAs retire
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         };
         if (p.k_masks) {
           int m_blk, n_blk;
-          tile_coords(p, tiles_m, tile, m_blk, n_blk);
+          tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
           const int n_cells = __popcll(__ldg(p.k_masks + m_blk));
           for (int i = 0; i < n_cells * p.k_cell_kb; ++i) mma_kb();
         } else {
@@ -443,9 +483,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       int m_blk, n_blk;
-      tile_coords(p, tiles_m, tile, m_blk, n_blk);
+      tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
       int t_img = 0, t_y0 = 0, t_x0 = 0;                  // conv: tile origin (image, first pixel row / column)
       if (p.mode == HC_GEMM_CONV3) {   // dense conv only; block mode decodes its origin per warp below
         const int per_img = p.tiles_x * p.tiles_y;
@@ -642,6 +682,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (p.cl2) cluster_sync_all();          // no CTA leaves while its peer can still multicast into it or arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
@@ -680,7 +721,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
 }
 
 template <int BN, int MS>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const Params& p, cudaStream_t stream) {
   using C = Cfg<BN, MS>;
   static bool configured = false;
   if (!configured) {
@@ -690,7 +731,22 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p,
   }
   int tiles = p.tiles_m * p.tiles_n;
   int grid = (p.mode == HC_GEMM_CONV3_BLOCKS || tiles >= num_sms()) ? num_sms() : tiles;   // block mode: tile count lives on the device
-  tc_gemm_kernel<BN, MS><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  if (p.cl2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(grid & ~1));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MS>, ta, tb, tbh, p) != cudaSuccess) return cuda_status("tc_gemm_kernel cluster launch");
+    return cuda_status("tc_gemm_kernel cluster launch");
+  }
+  tc_gemm_kernel<BN, MS><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tb, p);
   return cuda_status("tc_gemm_kernel launch");
 }
 
@@ -757,12 +813,15 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
              "hc_tc_gemm: mul needs a plain GEMM, a non-pooled epilogue and a 16-byte aligned [M, ld_mul] f32 operand");
   p.tiles_n = p.N / BN;
 
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tbh;
   {
     cuuint64_t dims[2] = {(cuuint64_t)d->k, (cuuint64_t)d->n};
     cuuint64_t str[1] = {(cuuint64_t)d->k * 2};
     cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)BN};
     rc = tc::make_map(&tb, d->b, 2, dims, str, box);
+    if (rc != HC_OK) return rc;
+    box[1] = (cuuint32_t)(BN / 2);            // half tile: what one CTA of a pair multicasts
+    rc = tc::make_map(&tbh, d->b, 2, dims, str, box);
     if (rc != HC_OK) return rc;
   }
   const bool blk = d->mode == HC_GEMM_CONV3_BLOCKS;
@@ -799,8 +858,14 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   if (blk) p.group_m = 1;                 // the 4 N tiles of an M tile run side by side and share its blocks through L2
   else if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
 
-  if (BN == 256 && MS == 1) return tc::launch<256, 1>(ta, tb, p, stream);
-  if (BN == 256 && MS == 2) return tc::launch<256, 2>(ta, tb, p, stream);
-  if (BN == 128 && MS == 1) return tc::launch<128, 1>(ta, tb, p, stream);
-  return tc::launch<128, 2>(ta, tb, p, stream);
+  // block mode: CTA pairs sharing the weight tile by TMA multicast (d->cta_pairs; HC_CONV3_PAIRS=0/1 overrides for A/B runs)
+  if (blk) {
+    static int env_pairs = -2;
+    if (env_pairs == -2) { const char* e = getenv("HC_CONV3_PAIRS"); env_pairs = e ? atoi(e) : -1; }
+    p.cl2 = (env_pairs >= 0 ? env_pairs : d->cta_pairs) ? 1 : 0;
+  }
+  if (BN == 256 && MS == 1) return tc::launch<256, 1>(ta, tb, tbh, p, stream);
+  if (BN == 256 && MS == 2) return tc::launch<256, 2>(ta, tb, tbh, p, stream);
+  if (BN == 128 && MS == 1) return tc::launch<128, 1>(ta, tb, tbh, p, stream);
+  return tc::launch<128, 2>(ta, tb, tbh, p, stream);
 }
