@@ -168,7 +168,7 @@ def test_fc1_windows_are_bit_identical_to_one_window(tiled):
     pk = _packed(gain=40.0)
     samples = synthetic.make_batch([80, 81, 82, 83, 84], [11, 14, 3, 16, 9], p_rel=0.5)
     outs = []
-    for cap in (262144, 250):
+    for cap in (262144, 40):
         pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=130)
         pipe.fc1_window_pairs = cap
         b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")

@@ -6,7 +6,7 @@ echo "== pytest sparse + fc1_shared with CTA pairs"
 HC_CONV3_PAIRS=1 timeout -s KILL 420 python -m pytest tests/test_gpu_sparse.py tests/test_gpu_fc1_shared.py -q -x --timeout=300 > $OUT/pytest_pairs_$TAG.log 2>&1; rc=$?; echo "pytest exit $rc"; tail -15 $OUT/pytest_pairs_$TAG.log
 nvidia-smi --query-gpu=name,memory.used --format=csv,noheader
 if [ $rc -ne 0 ]; then exit $rc; fi
-for mode in 1 0 1; do
+for mode in 1 0 1 0; do
   echo "== bench HC_CONV3_PAIRS=$mode"
   HC_CONV3_PAIRS=$mode timeout -s KILL 300 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > $OUT/bench_pairs${mode}_$TAG.json 2> $OUT/bench_pairs${mode}_$TAG.err; echo "exit $?"
   python - <<PY
