@@ -236,7 +236,14 @@ int hc_pair_lut_build(const int32_t* pair_sub, const int32_t* pair_obj, const in
                       hc_stream_t stream);
 int hc_pair_relu_pool_tiled(const void* u, const void* v, const float* bias, const int32_t* box_offsets,
                             const int32_t* lut, int32_t n_max, int32_t img0, int32_t n_img, int32_t pair_base,
-                            int32_t chunk_pairs, int32_t fs, int32_t channels, void* out, hc_stream_t stream);
+                            int32_t chunk_pairs, int32_t fs, int32_t channels, const uint64_t* cover, void* out, hc_stream_t stream);
+
+/* Footprint-aware pooling: masks[p] = the 8x8-grid cells covered by the blocks hc_conv3_active_blocks (shared = 0) or
+ * hc_conv3_shared_blocks (shared = 1) lists for pair p (same cover function).  Passed as `cover` (chunk-local, bias == NULL,
+ * feature_size 32) to hc_pair_relu_pool_tiled, a pooled pixel of a pair is written only if a listed conv3_1 block reads it (block +
+ * 1-pixel halo); HC_GEMM_CONV3_BLOCKS never reads the others.  cover == NULL writes every pixel. */
+int hc_pair_cover_masks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs, int32_t feature_size,
+                        int32_t block_rows, int32_t block_cols, int32_t shared, uint64_t* masks, hc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * R6 tail + R7 - label-embedding add, fc2 bias + ReLU, fc3_x / fc4 / fc5 heads and the Bayesian hierarchical

@@ -243,14 +243,30 @@ def pair_lut_build(pair_sub, pair_obj, pair_img, box_offsets, n_box, n_max):
     return lut
 
 
-def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None):
-    require_cuda(u, v, bias, box_offsets, lut)
+def pair_cover_masks(boxes, pair_sub, pair_obj, block_rows, block_cols, shared, fs=32, out=None):
+    """int64 [n] bitmaps of the 8x8-grid cells the listed conv3_1 blocks of each pair cover (include/hiercom_b200.h hc_pair_cover_masks)."""
+    require_cuda(boxes, pair_sub, pair_obj, out)
+    n = pair_sub.numel()
+    if out is None:
+        out = torch.empty(max(n, 1), dtype=torch.int64, device=boxes.device)
+    if out.dtype != torch.int64 or out.numel() < n or not out.is_contiguous():
+        raise RuntimeError("hiercom_b200: pair_cover_masks needs a contiguous int64 output with one word per pair")
+    check(_lib.load().hc_pair_cover_masks(ptr(boxes), ptr(pair_sub), ptr(pair_obj), n, fs, block_rows, block_cols, 1 if shared else 0,
+                                          ptr(out), stream_ptr()), "hc_pair_cover_masks")
+    _count()
+    return out
+
+
+def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None, cover=None):
+    require_cuda(u, v, bias, box_offsets, lut, cover)
+    if cover is not None and (cover.dtype != torch.int64 or cover.numel() < chunk_pairs or not cover.is_contiguous()):
+        raise RuntimeError("hiercom_b200: pair_relu_pool_tiled cover must be a contiguous int64 tensor with one word per pair of the chunk")
     ch = u.shape[-1]
     if out is None:
         out = torch.empty(chunk_pairs, fs // 2, fs // 2, ch, dtype=torch.bfloat16, device=u.device)
     with _timed("pair_pool"):
         check(_lib.load().hc_pair_relu_pool_tiled(ptr(u), ptr(v), ptr(bias), ptr(box_offsets), ptr(lut), lut.shape[1], img0, n_img,
-                                                  pair_base, chunk_pairs, fs, ch, ptr(out), stream_ptr()), "hc_pair_relu_pool_tiled")
+                                                  pair_base, chunk_pairs, fs, ch, ptr(cover), ptr(out), stream_ptr()), "hc_pair_relu_pool_tiled")
     _count()
     return out
 

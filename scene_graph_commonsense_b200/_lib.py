@@ -54,7 +54,8 @@ SIGNATURES = {
     "hc_box_select": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
     "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "hc_pair_lut_build": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
-    "hc_pair_relu_pool_tiled": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "hc_pair_relu_pool_tiled": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "hc_pair_cover_masks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "hc_hier_head": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32,
                                _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     "hc_box_label_embed": (C.c_int, [_P, _I32, _I32, _P, _P, _I32, _I32, _P, _P]),

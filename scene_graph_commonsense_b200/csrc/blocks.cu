@@ -81,6 +81,20 @@ conv3_blocks_kernel(const int4* __restrict__ boxes, const int* __restrict__ pair
   for (int p = p0; p < p1; ++p) cover(pair_mask(p), hc, wc, [&](int e) { blocks[o++] = (p << 8) | e; });
 }
 
+// cells covered by the blocks conv3_blocks_kernel lists for each pair (same cover function, so the two can never disagree): the
+// tiled pooling kernel writes a pooled conv2 pixel of a pair only if a listed block reads it (block + 1-pixel halo)
+__global__ void pair_cover_masks_kernel(const int4* __restrict__ boxes, const int* __restrict__ pair_sub, const int* __restrict__ pair_obj,
+                                        int n_pairs, int fs, int hc, int wc, bool both, unsigned long long* __restrict__ masks) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const unsigned long long ms = cell_mask(rect_of(__ldg(boxes + pair_sub[p]), fs)), mo = cell_mask(rect_of(__ldg(boxes + pair_obj[p]), fs));
+  const unsigned long long rows = (hc == 4) ? 0x01010101ull : ((hc == 2) ? 0x0101ull : 0x01ull);
+  const unsigned long long blk = rows * ((1ull << wc) - 1ull);
+  unsigned long long c = 0ull;
+  cover(both ? (ms & mo) : (ms | mo), hc, wc, [&](int e) { c |= blk << (8 * (e >> 4) + (e & 15)); });
+  masks[p] = c;
+}
+
 // Pooled conv3_1 output of a pair outside the cells both boxes reach: a cell only the subject's box reaches equals the map of
 // the pair (subject, EMPTY box), one only the object's box reaches equals (EMPTY box, object), the rest is the background.
 // One CTA per pair; a cell is 1024 channels = 128 uint4, so 256 threads move two cells per iteration.  Cells both boxes
@@ -277,4 +291,22 @@ extern "C" int hc_cells_zero(const uint64_t* masks, int32_t rows_per_tile, int64
                                                                                 rows_per_tile, n_rows, n_cells, (int)(cell_bytes / 16),
                                                                                 reinterpret_cast<uint4*>(out));
   return cuda_status("cells_zero_kernel launch");
+}
+
+extern "C" int hc_pair_cover_masks(const int32_t* boxes, const int32_t* pair_sub, const int32_t* pair_obj, int32_t n_pairs, int32_t feature_size,
+                                   int32_t block_rows, int32_t block_cols, int32_t shared, uint64_t* masks, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(n_pairs <= 0 || (boxes && pair_sub && pair_obj && masks), HC_E_NULL, "hc_pair_cover_masks: NULL operand");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  HC_REQUIRE(feature_size == 32, HC_E_SHAPE, "hc_pair_cover_masks: built for feature_size 32 (8x8 pooled conv3 cells)");
+  if (block_cols == 0) block_cols = 8;
+  HC_REQUIRE((block_rows == 8 || block_rows == 4) && (block_cols == 8 || (block_cols == 4 && block_rows == 4)), HC_E_SHAPE,
+             "hc_pair_cover_masks: blocks are 8x8, 8x4 or 4x4 pixels (block_cols x block_rows)");
+  HC_REQUIRE(aligned16(boxes), HC_E_ALIGN, "hc_pair_cover_masks: boxes must be 16-byte aligned");
+  if (n_pairs <= 0) return HC_OK;
+  pair_cover_masks_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const int4*>(boxes), pair_sub, pair_obj, n_pairs,
+                                                                     feature_size, block_rows / 2, block_cols / 2, shared != 0,
+                                                                     reinterpret_cast<unsigned long long*>(masks));
+  return cuda_status("pair_cover_masks_kernel launch");
 }

@@ -248,7 +248,7 @@ __global__ void pair_relu_pool_bf16_kernel(const uint4* __restrict__ u, const ui
 __global__ void __launch_bounds__(128, 4)
 pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const int* __restrict__ box_off,
                                  const int* __restrict__ lut, int n_max, int img0, int pair_base, int chunk_pairs, int fs, int cvec,
-                                 uint4* __restrict__ out) {
+                                 const unsigned long long* __restrict__ cover, uint4* __restrict__ out) {
   // grid = (slabs, subject tiles, images of the chunk); block = 128 consecutive (pooled pixel, channel vector) slots
   const int img = img0 + blockIdx.z;
   const int b0 = box_off[img], n = box_off[img + 1] - b0;
@@ -275,6 +275,15 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
   for (int t = 0; t < PP_TA; ++t) lut_row[t] = lut + (long long)(b0 + min(a0 + t, n - 1)) * n_max;
   const long long out_slot = (long long)pix * cvec + cv;
   const long long pair_stride = (long long)hp * hp * cvec;
+  // cover (optional): per pair of the chunk, the 8x8-grid cells its listed conv3_1 blocks cover.  This pooled pixel is read by
+  // a block iff one of the cells its 3x3 neighbourhood touches is covered (fs = 32: a cell is 2 x 2 pooled pixels); warp-uniform.
+  unsigned long long nbr = ~0ull;
+  if (cover) {
+    const int cy0 = max(py - 1, 0) >> 1, cy1 = min(py + 1, hp - 1) >> 1, cx0 = max(px - 1, 0) >> 1, cx1 = min(px + 1, hp - 1) >> 1;
+    nbr = 0ull;
+    for (int cy = cy0; cy <= cy1; ++cy)
+      for (int cx = cx0; cx <= cx1; ++cx) nbr |= 1ull << (8 * cy + cx);
+  }
   for (int b = 0; b < n; ++b) {
     int prow[PP_TA];
     bool any = false;
@@ -294,6 +303,7 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
 #pragma unroll
     for (int t = 0; t < PP_TA; ++t) {
       if (prow[t] < 0) continue;                         // block-uniform
+      if (cover && !(__ldg(cover + prow[t]) & nbr)) continue;   // no listed conv3_1 block reads this pixel of this pair
       uint4 acc = make_uint4(0u, 0u, 0u, 0u);            // relu folded into the running max
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc = bf8_max(acc, bf8_add(ua[t][q], vq[q]));
@@ -376,7 +386,7 @@ extern "C" int hc_pair_lut_build(const int32_t* pair_sub, const int32_t* pair_ob
 
 extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float* bias, const int32_t* box_offsets, const int32_t* lut,
                                        int32_t n_max, int32_t img0, int32_t n_img, int32_t pair_base, int32_t chunk_pairs, int32_t fs,
-                                       int32_t channels, void* out, hc_stream_t stream_) {
+                                       int32_t channels, const uint64_t* cover, void* out, hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(u && v && box_offsets && lut && out, HC_E_NULL, "hc_pair_relu_pool_tiled: NULL pointer");
   HC_REQUIRE(n_img > 0 && n_img <= 65535 && n_max > 0 && chunk_pairs > 0 && fs > 0 && fs % 2 == 0 && channels % 8 == 0, HC_E_SHAPE,
@@ -387,13 +397,15 @@ extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float
   const int cvec = channels / 8, hp = fs / 2;
   const int slots = hp * hp * cvec;
   HC_REQUIRE(slots % 128 == 0, HC_E_SHAPE, "hc_pair_relu_pool_tiled: (fs/2)^2 * channels/8 must be a multiple of 128");
+  HC_REQUIRE(!cover || fs == 32, HC_E_SHAPE, "hc_pair_relu_pool_tiled: the footprint cover is defined on the 8x8 cell grid of feature_size 32");
   dim3 grid(slots / 128, (n_max + PP_TA - 1) / PP_TA, n_img);
   if (!bias) {
     pair_relu_pool_tiled_bf16_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec,
-                                                               reinterpret_cast<uint4*>(out));
+                                                               reinterpret_cast<const unsigned long long*>(cover), reinterpret_cast<uint4*>(out));
     return cuda_status("hc_pair_relu_pool_tiled");
   }
+  HC_REQUIRE(!cover, HC_E_SHAPE, "hc_pair_relu_pool_tiled: the footprint cover needs the packed path (bias == NULL)");
   pair_relu_pool_tiled_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v), bias,
                                                         box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec, grid.y, grid.x,
                                                         reinterpret_cast<uint4*>(out));

@@ -210,16 +210,31 @@ def pair_lut_build(pair_sub, pair_obj, pair_img, box_offsets, n_box, n_max):
     return _call("pair_lut_build")(pair_sub, pair_obj, pair_img, box_offsets, n_box, n_max)
 
 
+@_op("pair_cover_masks", "(Tensor boxes, Tensor pair_sub, Tensor pair_obj, int block_rows, int block_cols, bool shared, int fs, "
+     "Tensor(a!) out) -> ()")
+def _pair_cover_masks(boxes, pair_sub, pair_obj, block_rows, block_cols, shared, fs, out):
+    _A.pair_cover_masks(boxes, pair_sub, pair_obj, block_rows, block_cols, shared, fs, out=out)
+
+
+def pair_cover_masks(boxes, pair_sub, pair_obj, block_rows, block_cols, shared, fs=32, out=None):
+    """Per pair: int64 bitmap of the cells its listed conv3_1 blocks cover (the `cover` of `pair_relu_pool_tiled`)."""
+    if out is None:
+        out = torch.empty(max(pair_sub.numel(), 1), dtype=torch.int64, device=boxes.device)
+    _call("pair_cover_masks")(boxes, pair_sub, pair_obj, block_rows, block_cols, shared, fs, out)
+    return out
+
+
 @_op("pair_relu_pool_tiled", "(Tensor u, Tensor v, Tensor? bias, Tensor box_offsets, Tensor lut, int img0, int n_img, int pair_base, "
-     "int chunk_pairs, int fs, Tensor(a!) out) -> ()")
-def _pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out):
-    _A.pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out=out)
+     "int chunk_pairs, int fs, Tensor(a!) out, Tensor? cover) -> ()")
+def _pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out, cover):
+    _A.pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out=out, cover=cover)
 
 
-def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None):
+def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None, cover=None):
+    """`cover` (int64 per pair of the chunk, `pair_cover_masks`): write only the pooled pixels a listed conv3_1 block reads."""
     if out is None:
         out = torch.empty(chunk_pairs, fs // 2, fs // 2, u.shape[-1], dtype=torch.bfloat16, device=u.device)
-    _call("pair_relu_pool_tiled")(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out)
+    _call("pair_relu_pool_tiled")(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out, cover)
     return out
 
 

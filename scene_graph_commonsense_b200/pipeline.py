@@ -16,6 +16,7 @@ several host syncs per directed pair) with ~20 launches per *batch*:
 Data layout in HBM: CSR over images (box_offsets, tri_offsets, pair offsets); activations NHWC bf16 so the channel
 index is the GEMM K index and a TMA box row; all counters int64 in one 765-slot vector (tables.EV_* / T3_*).
 """
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -171,6 +172,10 @@ class RelationPipeline:
         # operand is zero).  Same sums up to fp32 rounding order and one bf16 rounding of d - not bit-identical to the dense fc1.
         self.fc1_shared = bool(fc1_shared) and self.conv3_shared
         self.fc1_window_pairs = 262144       # pairs per shared-fc1 window: its operand is 128 KB per pair (32 GB at the cap)
+        # shared-fc1 path: the tiled pooling writes a pooled conv2 pixel of a pair only if one of the pair's listed conv3_1 blocks
+        # reads it (block + 1-pixel halo, `ops.pair_cover_masks`) - the rest of the buffer is never read
+        self.pool_footprint = os.environ.get("HC_POOL_FOOTPRINT", "1") != "0"
+        self.debug_poison = False
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.last_k_masks = None             # int64 [n_tiles] device tensor: K-cell masks of the last shared fc1
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
@@ -440,6 +445,7 @@ class RelationPipeline:
         two = self.overlap and len(chunks) > 1
         bufs = [torch.empty(cap, fs // 2, fs // 2, 512, dtype=torch.bfloat16, device=dev) for _ in range(2 if two else 1)]
         blk_bufs = [torch.empty(cap * (256 // (br * bc)), dtype=torch.int32, device=dev) for _ in bufs]
+        cov_bufs = [torch.empty(cap, dtype=torch.int64, device=dev) for _ in bufs]
         nblk = torch.zeros(len(chunks), dtype=torch.int32, device=dev)
         main = torch.cuda.current_stream()
         side = self._side_stream() if two else main
@@ -454,8 +460,13 @@ class RelationPipeline:
                     side.wait_event(ready)
                     if k >= 2:
                         side.wait_event(gemm_done[k - 2])              # buffer free again
+                if self.debug_poison:            # tests: anything conv3_1 reads that the pooling did not write shows up as NaN
+                    buf.fill_(float("nan"))
                 if lut is not None:
-                    ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, fs, out=buf)
+                    cover = None
+                    if self.pool_footprint:      # only the pooled pixels a listed block reads (block + halo)
+                        cover = ops.pair_cover_masks(b.boxes, sub_k, obj_k, br, bc, True, fs, out=cov_bufs[k % len(bufs)])
+                    ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, fs, out=buf, cover=cover)
                 else:
                     ops.pair_relu_pool(u, v, None, sub_k, obj_k, fs, out=buf)
                 ops.conv3_shared_blocks(b.boxes, sub_k, obj_k, br, fs, blocks=blk, n_blocks=nblk[k:k + 1], block_cols=bc)

@@ -145,6 +145,7 @@ def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled, block_cols):
     for fc1_shared in (False, True):
         pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=700, conv3_block_rows=4, conv3_shared=True,
                                          fc1_shared=fc1_shared, conv3_block_cols=block_cols)
+        pipe.debug_poison = True                  # footprint-aware pooling: a pixel conv3_1 reads but nobody wrote would be NaN
         b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
         pairs = pipe.enumerate_pairs(b)
         if not tiled:
@@ -155,6 +156,7 @@ def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled, block_cols):
         if fc1_shared:
             assert pipe.last_k_masks is not None and pipe.last_k_masks.numel() == -(-pairs["n"] // 256)
     (rel0, sup0, conn0), (rel1, sup1, conn1) = outs
+    assert not torch.isnan(rel1).any() and not torch.isnan(conn1).any()
     assert float((rel0.exp() - rel1.exp()).abs().max()) <= 2e-3
     assert float((sup0.exp() - sup1.exp()).abs().max()) <= 2e-3
     assert float((torch.sigmoid(conn0) - torch.sigmoid(conn1)).abs().max()) <= 2e-3
@@ -182,3 +184,42 @@ def test_fc1_windows_are_bit_identical_to_one_window(tiled):
     assert outs[1][4] > outs[0][4]                       # really several windows
     for a, c in zip(outs[0][:4], outs[1][:4]):
         assert torch.equal(a, c)
+
+
+@pytest.mark.parametrize("block_rows,block_cols,shared", [(4, 4, True), (4, 8, True), (8, 8, False)])
+def test_footprint_pooling_writes_exactly_what_the_blocks_read(block_rows, block_cols, shared):
+    """`pair_cover_masks` == the union of the listed blocks of each pair; the tiled pooling with `cover` writes exactly the pooled
+    pixels within one pixel of a covered cell, with the values of the full pooling."""
+    from scene_graph_commonsense_b200 import ops, pipeline
+    pk = _packed()
+    samples = synthetic.make_batch([90, 91], [12, 9], p_rel=0.5)
+    samples[0].bbox[:6] = torch.tensor(EDGE_BOXES[:6], dtype=samples[0].bbox.dtype)
+    pipe = pipeline.RelationPipeline(pk, DEV, commonsense=False)
+    b = pipeline.batch_from_samples(samples, DEV, skip_mode="batch")
+    pairs = pipe.enumerate_pairs(b)
+    n = pairs["n"]
+    u, v = pipe.box_features(b)
+    lister = ops.conv3_shared_blocks if shared else ops.conv3_active_blocks
+    blocks, n_blocks = lister(b.boxes, pairs["sub"], pairs["obj"], block_rows, block_cols=block_cols)
+    e = blocks[:int(n_blocks.item())].cpu().numpy()
+    want = np.zeros((n, 8, 8), bool)
+    for p, y, x in zip(e >> 8, (e >> 4) & 15, e & 15):
+        want[p, y:y + block_rows // 2, x:x + block_cols // 2] = True
+    cover = ops.pair_cover_masks(b.boxes, pairs["sub"], pairs["obj"], block_rows, block_cols, shared)
+    got = cover[:n].cpu().numpy()
+    bits = ((got[:, None].astype(np.uint64) >> np.arange(64, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool).reshape(n, 8, 8)
+    assert (bits == want).all()
+    n_box = b.boxes.shape[0]
+    n_max = int(np.max(np.diff(b.box_offsets_host)))
+    lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
+    full = ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, 0, 2, 0, n)
+    part = torch.full_like(full, float("nan"))
+    ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, 0, 2, 0, n, out=part, cover=cover)
+    torch.cuda.synchronize()
+    need = np.zeros((n, 16, 16), bool)              # pooled pixels within one pixel of a covered cell
+    for p, cy, cx in zip(*np.nonzero(want)):
+        need[p, max(2 * cy - 1, 0):2 * cy + 3, max(2 * cx - 1, 0):2 * cx + 3] = True
+    written = ~torch.isnan(part.float()).any(3).cpu().numpy()
+    assert (written == need).all()
+    m = torch.from_numpy(need).to(DEV)
+    assert torch.equal(part[m].view(torch.int16), full[m].view(torch.int16))
