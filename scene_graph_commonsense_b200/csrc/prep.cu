@@ -168,10 +168,13 @@ pair_relu_pool_tiled_kernel(const uint4* __restrict__ u, const uint4* __restrict
       int p = (a0 + t < n) ? __ldg(lut + (long long)(b0 + a0 + t) * n_max + b) : -1;
       p = (p >= 0) ? p - pair_base : -1;
       if (p >= chunk_pairs) p = -1;
+      // footprint cover: the four words are loaded side by side (independent), and a pair none of whose listed conv3_1 blocks
+      // reads this pixel is dropped here, before the object tile is fetched (warp-uniform: a warp holds one pixel)
+      if (cover && p >= 0 && !(__ldg(cover + p) & nbr)) p = -1;
       prow[t] = p;
       any |= p >= 0;
     }
-    if (!any) continue;                                  // block-uniform (lut entries do not depend on the thread)
+    if (!any) continue;                                  // uniform per warp (lut / cover entries do not depend on the lane)
     const long long vb = (long long)(b0 + b) * fs * fs;
     float acc[PP_TA][8];
 #pragma unroll
@@ -292,18 +295,20 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
       int p = (a0 + t < n) ? __ldg(lut_row[t] + b) : -1;
       p = (p >= 0) ? p - pair_base : -1;
       if (p >= chunk_pairs) p = -1;
+      // footprint cover: the four words are loaded side by side (independent), and a pair none of whose listed conv3_1 blocks
+      // reads this pixel is dropped here, before the object tile is fetched (warp-uniform: a warp holds one pixel)
+      if (cover && p >= 0 && !(__ldg(cover + p) & nbr)) p = -1;
       prow[t] = p;
       any |= p >= 0;
     }
-    if (!any) continue;                                  // block-uniform (lut entries do not depend on the thread)
+    if (!any) continue;                                  // uniform per warp (lut / cover entries do not depend on the lane)
     const long long vb = (long long)(b0 + b) * fs * fs * cvec;
     uint4 vq[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) vq[q] = __ldg(v + vb + qoff[q]);
 #pragma unroll
     for (int t = 0; t < PP_TA; ++t) {
-      if (prow[t] < 0) continue;                         // block-uniform
-      if (cover && !(__ldg(cover + prow[t]) & nbr)) continue;   // no listed conv3_1 block reads this pixel of this pair
+      if (prow[t] < 0) continue;                         // warp-uniform
       uint4 acc = make_uint4(0u, 0u, 0u, 0u);            // relu folded into the running max
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc = bf8_max(acc, bf8_add(ua[t][q], vq[q]));
