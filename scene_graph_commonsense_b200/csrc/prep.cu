@@ -168,13 +168,10 @@ pair_relu_pool_tiled_kernel(const uint4* __restrict__ u, const uint4* __restrict
       int p = (a0 + t < n) ? __ldg(lut + (long long)(b0 + a0 + t) * n_max + b) : -1;
       p = (p >= 0) ? p - pair_base : -1;
       if (p >= chunk_pairs) p = -1;
-      // footprint cover: the four words are loaded side by side (independent), and a pair none of whose listed conv3_1 blocks
-      // reads this pixel is dropped here, before the object tile is fetched (warp-uniform: a warp holds one pixel)
-      if (cover && p >= 0 && !(__ldg(cover + p) & nbr)) p = -1;
       prow[t] = p;
       any |= p >= 0;
     }
-    if (!any) continue;                                  // uniform per warp (lut / cover entries do not depend on the lane)
+    if (!any) continue;                                  // block-uniform (lut entries do not depend on the thread)
     const long long vb = (long long)(b0 + b) * fs * fs;
     float acc[PP_TA][8];
 #pragma unroll

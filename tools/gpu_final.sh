@@ -12,3 +12,6 @@ echo "== launch list"; timeout 600 ncu --metrics gpu__time_duration.sum --clock-
 if [ -z "$NO_REF" ]; then
 echo "== bench reference arm"; timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "exit $?"; head -c 900 $OUT/bench_ref_$TAG.json
 fi
+if [ -n "$KERNELS" ]; then
+echo "== per-kernel bench"; timeout 600 python tools/bench_kernels.py > $OUT/kernels_$TAG.json 2> $OUT/kernels_$TAG.err; echo "exit $?"; tail -2 $OUT/kernels_$TAG.err
+fi
