@@ -176,6 +176,7 @@ class RelationPipeline:
         # reads it (block + 1-pixel halo, `ops.pair_cover_masks`) - the rest of the buffer is never read
         self.pool_footprint = os.environ.get("HC_POOL_FOOTPRINT", "1") != "0"
         self.debug_poison = False
+        self.early_pool = os.environ.get("HC_EARLY_POOL", "1") != "0"     # first chunks' pooling starts under the per-box stages
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.last_k_masks = None             # int64 [n_tiles] device tensor: K-cell masks of the last shared fc1
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
@@ -391,12 +392,6 @@ class RelationPipeline:
         pk, fs = self.packed, self.fs
         n, n_box = pairs["n"], b.boxes.shape[0]
         dev = self.device
-        boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))      # + the empty box (all background), partner of every box
-        u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))))
-        maps, nblk_box = self.box_maps(boxes_x, u, v, with_background_row=True)
-        f_box = pk.fc1_rows(maps, 2 * n_box + 1)                     # fc1 (no bias) of (box, empty), (empty, box), background
-        bias_eff = (pk.b_fc1 - f_box[2 * n_box]).contiguous()
-        raw = torch.empty(n, 512, dtype=torch.float32, device=dev)
         tiled = "offsets_host" in pairs
         lut = None
         if tiled:
@@ -404,7 +399,7 @@ class RelationPipeline:
             n_max = int(np.max(np.diff(b.box_offsets_host))) if b.box_offsets_host is not None else int(
                 (b.box_offsets[1:] - b.box_offsets[:-1]).max().item())
             lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
-            windows = []                                             # (first image, pair range) of each window
+            windows = []                                             # (pair range, chunks) of each window
             for img0, n_img, base, cnt in self._greedy_chunks(off, self.fc1_window_pairs):
                 chunks = [(img0 + c[0], c[1], c[2], c[3]) for c in self._image_chunks(off[img0:img0 + n_img + 1])]
                 windows.append((base, base + cnt, chunks))
@@ -413,9 +408,21 @@ class RelationPipeline:
             for w0 in range(0, n, self.fc1_window_pairs):
                 w1 = min(n, w0 + self.fc1_window_pairs)
                 windows.append((w0, w1, [(0, 0, s, min(w1, s + self.chunk_pairs) - s) for s in range(w0, w1, self.chunk_pairs)]))
+        boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))      # + the empty box (all background), partner of every box
+        u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))))
+        # The pooling of the first chunks needs only U and V: its buffers are taken NOW (anything the allocator recycles into them
+        # was last used by work already queued on this stream) and an event lets the pooling stream start under the per-box stages
+        early = self._pool_buffers(windows[0][2])
+        uv_ready = torch.cuda.Event()
+        uv_ready.record(torch.cuda.current_stream())
+        maps, nblk_box = self.box_maps(boxes_x, u, v, with_background_row=True)
+        f_box = pk.fc1_rows(maps, 2 * n_box + 1)                     # fc1 (no bias) of (box, empty), (empty, box), background
+        bias_eff = (pk.b_fc1 - f_box[2 * n_box]).contiguous()
+        raw = torch.empty(n, 512, dtype=torch.float32, device=dev)
         nblks, masks_all = [], []
-        for w0, w1, chunks in windows:
-            nblk, masks = self._fc1_shared_window(b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw)
+        for i, (w0, w1, chunks) in enumerate(windows):
+            nblk, masks = self._fc1_shared_window(b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw,
+                                                  early if i == 0 else None, uv_ready if i == 0 and self.early_pool else None)
             nblks.append(nblk)
             masks_all.append(masks)
         self.last_n_blocks = torch.cat(nblks + [nblk_box])
@@ -423,7 +430,17 @@ class RelationPipeline:
         relation, sup, conn, logsig, _ = pk.heads(raw, pairs["sub"], pairs["obj"], b.cats, b.supers)
         return relation, sup, conn, logsig
 
-    def _fc1_shared_window(self, b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw):
+    def _pool_buffers(self, chunks):
+        """Everything the pooling stream writes for a window: pooled conv2 buffers (double-buffered), work lists, cover words, counts."""
+        fs, br, bc, dev = self.fs, self.conv3_block_rows, self.conv3_block_cols, self.device
+        cap = max(c[3] for c in chunks)
+        n_buf = 2 if self.overlap and len(chunks) > 1 else 1
+        return dict(bufs=[torch.empty(cap, fs // 2, fs // 2, 512, dtype=torch.bfloat16, device=dev) for _ in range(n_buf)],
+                    blk=[torch.empty(cap * (256 // (br * bc)), dtype=torch.int32, device=dev) for _ in range(n_buf)],
+                    cov=[torch.empty(cap, dtype=torch.int64, device=dev) for _ in range(n_buf)],
+                    nblk=torch.zeros(len(chunks), dtype=torch.int32, device=dev))
+
+    def _fc1_shared_window(self, b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw, pool=None, pool_ready=None):
         """Pairs [w0, w1) of the batch: sort, conv3_1 differences chunk by chunk (pooling of chunk k+1 under the GEMM of chunk k),
         then one K-cell-sparse fc1 + fc2 into raw[w0:w1]."""
         pk, fs, br, bc = self.packed, self.fs, self.conv3_block_rows, self.conv3_block_cols
@@ -441,16 +458,16 @@ class RelationPipeline:
         masks = ops.tile_cell_masks(b.boxes, row_sub, row_obj, 256, fs)
         d = torch.empty(n, 64, 1024, dtype=torch.bfloat16, device=dev)
         ops.cells_zero(masks, 256, n, d)
-        cap = max(c[3] for c in chunks)
-        two = self.overlap and len(chunks) > 1
-        bufs = [torch.empty(cap, fs // 2, fs // 2, 512, dtype=torch.bfloat16, device=dev) for _ in range(2 if two else 1)]
-        blk_bufs = [torch.empty(cap * (256 // (br * bc)), dtype=torch.int32, device=dev) for _ in bufs]
-        cov_bufs = [torch.empty(cap, dtype=torch.int64, device=dev) for _ in bufs]
-        nblk = torch.zeros(len(chunks), dtype=torch.int32, device=dev)
+        if pool is None:
+            pool = self._pool_buffers(chunks)
+        bufs, blk_bufs, cov_bufs, nblk = pool["bufs"], pool["blk"], pool["cov"], pool["nblk"]
+        two = len(bufs) == 2
         main = torch.cuda.current_stream()
         side = self._side_stream() if two else main
-        ready = torch.cuda.Event()
-        ready.record(main)
+        ready = pool_ready
+        if ready is None:
+            ready = torch.cuda.Event()
+            ready.record(main)
         gemm_done = []
         for k, (img0, n_img, base, cnt) in enumerate(chunks):
             buf, blk = bufs[k % len(bufs)], blk_bufs[k % len(bufs)]
