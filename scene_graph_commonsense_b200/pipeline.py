@@ -392,22 +392,12 @@ class RelationPipeline:
         pk, fs = self.packed, self.fs
         n, n_box = pairs["n"], b.boxes.shape[0]
         dev = self.device
-        tiled = "offsets_host" in pairs
         lut = None
-        if tiled:
-            off = pairs["offsets_host"]
+        if "offsets_host" in pairs:
             n_max = int(np.max(np.diff(b.box_offsets_host))) if b.box_offsets_host is not None else int(
                 (b.box_offsets[1:] - b.box_offsets[:-1]).max().item())
             lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
-            windows = []                                             # (pair range, chunks) of each window
-            for img0, n_img, base, cnt in self._greedy_chunks(off, self.fc1_window_pairs):
-                chunks = [(img0 + c[0], c[1], c[2], c[3]) for c in self._image_chunks(off[img0:img0 + n_img + 1])]
-                windows.append((base, base + cnt, chunks))
-        else:
-            windows = []
-            for w0 in range(0, n, self.fc1_window_pairs):
-                w1 = min(n, w0 + self.fc1_window_pairs)
-                windows.append((w0, w1, [(0, 0, s, min(w1, s + self.chunk_pairs) - s) for s in range(w0, w1, self.chunk_pairs)]))
+        windows = self._fc1_windows(pairs)
         boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))      # + the empty box (all background), partner of every box
         u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))))
         # The pooling of the first chunks needs only U and V: its buffers are taken NOW (anything the allocator recycles into them
@@ -429,6 +419,22 @@ class RelationPipeline:
         self.last_k_masks = torch.cat(masks_all)
         relation, sup, conn, logsig, _ = pk.heads(raw, pairs["sub"], pairs["obj"], b.cats, b.supers)
         return relation, sup, conn, logsig
+
+    def _fc1_windows(self, pairs):
+        """Host only: cut the pair list into shared-fc1 windows of at most `fc1_window_pairs` pairs (image-aligned when the list
+        came from `enumerate_pairs`) and each window into pooling / conv3_1 chunks: [(w0, w1, [(img0, n_img, pair_base, n_pairs)])]."""
+        n = pairs["n"]
+        windows = []
+        if "offsets_host" in pairs:
+            off = pairs["offsets_host"]
+            for img0, n_img, base, cnt in self._greedy_chunks(off, self.fc1_window_pairs):
+                chunks = [(img0 + c[0], c[1], c[2], c[3]) for c in self._image_chunks(off[img0:img0 + n_img + 1])]
+                windows.append((base, base + cnt, chunks))
+        else:
+            for w0 in range(0, n, self.fc1_window_pairs):
+                w1 = min(n, w0 + self.fc1_window_pairs)
+                windows.append((w0, w1, [(0, 0, s, min(w1, s + self.chunk_pairs) - s) for s in range(w0, w1, self.chunk_pairs)]))
+        return windows
 
     def _pool_buffers(self, chunks):
         """Everything the pooling stream writes for a window: pooled conv2 buffers (double-buffered), work lists, cover words, counts."""

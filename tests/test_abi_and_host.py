@@ -291,3 +291,36 @@ def test_training_rows_packing_matches_loop_layout():
     assert len(h["group_weight"]) == 6 + 12 and h["group_weight"][:6].tolist() == [6, 5, 4, 3, 2, 1] and h["group_weight"][6] == 12
     g, e = losses.tri_decode(np.arange(0, 5000))
     assert np.array_equal(g * (g - 1) // 2 + e, np.arange(5000)) and (e < g).all() and (e >= 0).all()
+
+
+def test_fc1_windows_partition_the_pair_list_image_aligned():
+    """Host logic of the shared-footprint fc1: windows tile [0, n) in order, chunks tile their window, both on image boundaries."""
+    from scene_graph_commonsense_b200.pipeline import RelationPipeline
+    pipe = RelationPipeline.__new__(RelationPipeline)
+    pipe.chunk_pairs, pipe.chunk_policy, pipe.n_sm = 5000, "waves", 148
+    rng = np.random.default_rng(3)
+    boxes = rng.integers(0, 60, size=37)
+    boxes[[4, 9]] = 0                                           # images without pairs
+    off = np.concatenate(([0], np.cumsum(boxes * (boxes - 1).clip(0)))).astype(np.int64)
+    n = int(off[-1])
+    for cap in (1 << 30, 20000, 3000):
+        pipe.fc1_window_pairs = cap
+        wins = pipe._fc1_windows({"n": n, "offsets_host": off})
+        assert wins[0][0] == 0 and wins[-1][1] == n
+        for (a0, a1, _), (b0, b1, _) in zip(wins, wins[1:]):
+            assert a1 == b0
+        for w0, w1, chunks in wins:
+            assert w0 in off and w1 in off
+            per_image = np.diff(off)[(off[:-1] >= w0) & (off[1:] <= w1)]
+            assert w1 - w0 <= cap or int((per_image > 0).sum()) == 1          # only a single image may exceed the cap
+            spans = sorted((c[2], c[2] + c[3]) for c in chunks)
+            assert spans[0][0] == w0 and spans[-1][1] == w1
+            for (x0, x1), (y0, y1) in zip(spans, spans[1:]):
+                assert x1 == y0
+            for img0, n_img, base, cnt in chunks:
+                assert off[img0] == base and off[img0 + n_img] == base + cnt and cnt > 0
+        # generic pair lists (no image structure): fixed-size ranges
+        wins = pipe._fc1_windows({"n": n})
+        assert [w[:2] for w in wins] == [(s, min(n, s + cap)) for s in range(0, n, cap)]
+        for w0, w1, chunks in wins:
+            assert [c[2] for c in chunks] == list(range(w0, w1, pipe.chunk_pairs)) and sum(c[3] for c in chunks) == w1 - w0
