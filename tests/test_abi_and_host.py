@@ -324,3 +324,77 @@ def test_fc1_windows_partition_the_pair_list_image_aligned():
         assert [w[:2] for w in wins] == [(s, min(n, s + cap)) for s in range(0, n, cap)]
         for w0, w1, chunks in wins:
             assert [c[2] for c in chunks] == list(range(w0, w1, pipe.chunk_pairs)) and sum(c[3] for c in chunks) == w1 - w0
+
+
+def test_footprint_cells_contain_the_true_dependency_set_for_every_box_interval():
+    """DESIGN 3a rests on one geometric claim: outside `active_cells(lo, hi)` the pooled conv3_1 output cannot depend on the box.
+    Brute force per axis (box masks are rectangles and every stage is separable in its support): a pixel "differs from the
+    background" inside the box; a 3x3 conv spreads that by one pixel, a 2x2 pool to the cell holding it - model.py:143-146."""
+    from tests.test_gpu_sparse import _cells_1d
+
+    def dilate(d):
+        out = d.copy()
+        out[1:] |= d[:-1]
+        out[:-1] |= d[1:]
+        return out
+
+    for lo in range(0, 33):
+        for hi in range(lo, 33):
+            differs = np.zeros(32, bool)
+            differs[lo:hi] = True                           # train_test.py:391,398: feature * mask; conv1 is 1x1 (no spread)
+            d = dilate(differs)                             # conv2_1 3x3
+            d = d.reshape(16, 2).any(1)                     # 2x2 max-pool
+            d = dilate(d)                                   # conv3_1 3x3
+            d = d.reshape(8, 2).any(1)                      # 2x2 max-pool -> the 8 cells of this axis
+            a, b = _cells_1d(lo, hi)
+            got = np.zeros(8, bool)
+            got[a:b] = True
+            assert not (d & ~got).any(), (lo, hi)
+            if hi > lo:
+                assert (d == got).all(), (lo, hi)           # and it is tight: nothing computed that could not differ
+
+
+def test_shared_footprint_decomposition_holds_for_the_reference_formulation_in_fp32():
+    """The algebra of DESIGN 3a on the REFERENCE formulation itself (train_test.py:391,398 masking + model.py:139-149 in torch fp32 on
+    the CPU, no kernel of ours involved): outside the cells both boxes reach, the pooled conv3_1 output of a pair equals the
+    (subject, empty) map, the (empty, object) map or the background - exactly - and fc1 of the pair is the sum of the three
+    per-box terms plus fc1 of a difference that is zero outside those cells."""
+    import torch.nn.functional as F
+    from tests.test_gpu_sparse import _cell_mask
+    g = torch.Generator().manual_seed(5)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    w11, b11, w12, b12 = rnd(128, 257, 1, 1) / 16, rnd(128) / 4, rnd(128, 257, 1, 1) / 16, rnd(128) / 4
+    w2, b2 = rnd(512, 256, 3, 3) / 48, rnd(512) / 4
+    w3, b3 = rnd(1024, 512, 3, 3) / 68, rnd(1024) / 4
+    feat = torch.cat((rnd(256, 32, 32), torch.rand(1, 32, 32, generator=g)))
+
+    def mask_of(box):
+        m = torch.zeros(32, 32)
+        if box is not None:
+            x0, x1, y0, y1 = box
+            m[y0:y1, x0:x1] = 1.0
+        return m
+
+    def p3(box_s, box_o):
+        hs, ho = (feat * mask_of(box_s))[None], (feat * mask_of(box_o))[None]
+        a = torch.cat((torch.tanh(F.conv2d(hs, w11, b11)), torch.tanh(F.conv2d(ho, w12, b12))), 1)
+        x = F.max_pool2d(F.relu(F.conv2d(a, w2, b2, padding=1)), 2)
+        return F.max_pool2d(F.relu(F.conv2d(x, w3, b3, padding=1)), 2)[0]            # [1024, 8, 8]
+
+    bg = p3(None, None)
+    w_fc = torch.randn(24, 1024 * 64, generator=g, dtype=torch.float64) / 256
+    cases = [((3, 12, 5, 14), (9, 20, 8, 19)), ((0, 6, 0, 6), (20, 32, 22, 32)), ((2, 30, 2, 30), (14, 18, 14, 18)),
+             ((0, 32, 15, 17), (15, 17, 0, 32)), ((5, 9, 20, 31), (6, 8, 3, 12))]
+    for bs, bo in cases:
+        pair, sub, obj = p3(bs, bo), p3(bs, None), p3(None, bo)
+        ms, mo = torch.from_numpy(_cell_mask(bs)), torch.from_numpy(_cell_mask(bo))
+        assert torch.equal(pair[:, ~ms & ~mo], bg[:, ~ms & ~mo])
+        assert torch.equal(pair[:, ms & ~mo], sub[:, ms & ~mo])
+        assert torch.equal(pair[:, ~ms & mo], obj[:, ~ms & mo])
+        assert torch.equal(sub[:, ~ms], bg[:, ~ms]) and torch.equal(obj[:, ~mo], bg[:, ~mo])
+        d = (pair - sub) - (obj - bg)
+        assert float(d[:, ~(ms & mo)].abs().max()) == 0.0 if (~(ms & mo)).any() else True
+        flat = lambda t: t.double().reshape(-1)
+        lhs = w_fc @ flat(pair)
+        rhs = w_fc @ flat(sub) + w_fc @ flat(obj) - w_fc @ flat(bg) + w_fc @ flat(d)
+        assert float((lhs - rhs).abs().max()) <= 1e-5 * max(1.0, float(lhs.abs().max()))     # d itself is rounded to fp32
