@@ -81,7 +81,7 @@ int hc_pairs_enumerate(const int32_t* boxes, const int32_t* box_offsets, int32_t
  *     K = 9*c_in with k = (ky*3+kx)*c_in + c (B must be packed in that order).  H, W multiples of 16.
  * mode HC_GEMM_CONV3_BLOCKS : the same convolution evaluated only on a device-side WORK LIST of 8-pixel-wide, `block_rows`-tall
  *     (8 or 4) output blocks: `blocks[i] = img << 8 | (y0/2) << 4 | (x0/2)` (even origins), `n_blocks[0]` entries (read on the
- *     device: no host round trip).  Pooled epilogue only; output pixels outside the listed blocks are NOT written (the caller
+ *     device: no host round trip).  Pooled epilogues or HC_EPI_BF16; output pixels outside the listed blocks are NOT written (the caller
  *     pre-fills them, see hc_conv3_active_blocks / hc_broadcast_rows).  Same K order as HC_GEMM_CONV3: listed pixels are
  *     bit-identical to the dense result.
  * epilogue HC_EPI_BF16      : out bf16 [M, ldc] (+col offset c_off): act(acc + bias)
@@ -190,6 +190,14 @@ int hc_p3_assemble(const void* background, const void* sub_maps, const void* obj
 /* out[i, :] = src[:] for i < n_rows (row_bytes a multiple of 16; both 16-byte aligned): pre-fills the pooled conv3_1 output of
  * every pair with the background before HC_GEMM_CONV3_BLOCKS overwrites the active blocks. */
 int hc_broadcast_rows(const void* src, int64_t row_bytes, int64_t n_rows, void* out, hc_stream_t stream);
+
+/* model.py:143 on the box footprint: conv2_1's per-box halves (see hc_tc_gemm) differ from the weights-only background
+ * map only within one pixel of the box rectangle.  Lists 8 x block_rows-pixel blocks (even origins, clamped into the 32 x 32 map)
+ * covering that rectangle for every box: blocks[i] = box << 8 | (y0/2) << 4 | (x0/2), n_blocks[0] = count (device side); `blocks`
+ * must hold n_box * 4 * 32 / block_rows entries.  HC_GEMM_CONV3_BLOCKS with HC_EPI_BF16 then writes the listed pixels of an output
+ * the caller pre-filled with the background (hc_broadcast_rows); listed pixels are bit-identical to the dense convolution. */
+int hc_conv2_box_blocks(const int32_t* boxes, int32_t n_box, int32_t feature_size, int32_t block_rows, int32_t* blocks,
+                        int32_t* n_blocks, hc_stream_t stream);
 
 /* model.py:149 - shared-footprint fc1 (the K-cell-sparse mode of hc_tc_gemm).  fc1 is linear, and the pooled conv3_1 output of a
  * pair differs from "subject map + object map - background" (hc_p3_assemble) only in the 8-grid cells BOTH boxes reach, a

@@ -132,6 +132,22 @@ def conv3_active_blocks(boxes, pair_sub, pair_obj, block_rows=8, fs=32, blocks=N
     return blocks, n_blocks
 
 
+def conv2_box_blocks(boxes, block_rows=4, fs=32, blocks=None, n_blocks=None):
+    """Work list of the conv2_1 halves restricted to each box's footprint (include/hiercom_b200.h hc_conv2_box_blocks)."""
+    require_cuda(boxes, blocks, n_blocks)
+    n_box = boxes.shape[0]
+    cap = max(n_box * 4 * (32 // block_rows), 1)
+    if blocks is None:
+        blocks = torch.empty(cap, dtype=torch.int32, device=boxes.device)
+    if n_blocks is None:
+        n_blocks = torch.empty(1, dtype=torch.int32, device=boxes.device)
+    if blocks.numel() < cap:
+        raise RuntimeError("hiercom_b200: conv2_box_blocks needs room for %d work-list entries" % cap)
+    check(_lib.load().hc_conv2_box_blocks(ptr(boxes), n_box, fs, block_rows, ptr(blocks), ptr(n_blocks), stream_ptr()), "hc_conv2_box_blocks")
+    _count()
+    return blocks, n_blocks
+
+
 def pair_cell_keys(boxes, pair_sub, pair_obj, fs=32):
     """Sort key (int32 [n]) of the cell rectangle both boxes of each directed pair reach (include/hiercom_b200.h hc_pair_cell_keys)."""
     require_cuda(boxes, pair_sub, pair_obj)

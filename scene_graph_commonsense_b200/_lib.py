@@ -47,6 +47,7 @@ SIGNATURES = {
     "hc_conv3_shared_blocks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "hc_p3_assemble": (C.c_int, [_P, _P, _P, _P, _P, _P, _I32, _I32, _P, _P]),
     "hc_broadcast_rows": (C.c_int, [_P, _I64, _I64, _P, _P]),
+    "hc_conv2_box_blocks": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P]),
     "hc_pair_cell_keys": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P]),
     "hc_tile_cell_masks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "hc_cells_zero": (C.c_int, [_P, _I32, _I64, _I32, _I64, _P, _P]),

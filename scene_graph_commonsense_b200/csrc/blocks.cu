@@ -95,6 +95,43 @@ __global__ void pair_cover_masks_kernel(const int4* __restrict__ boxes, const in
   masks[p] = c;
 }
 
+
+// conv2_1 halves on the BOX footprint: a box's conv2 output differs from the background map only within one pixel of the box
+// rectangle (3x3 conv of a map that equals tanh(bias) outside the box).  Work list of 8 x bh-pixel blocks (even origins, clamped
+// into the 32 x 32 map) covering that rectangle, same entry format as the conv3_1 lists; an empty box lists nothing.
+__global__ void __launch_bounds__(1024)
+conv2_blocks_kernel(const int4* __restrict__ boxes, int n_box, int fs, int bh, int* __restrict__ blocks, int* __restrict__ n_blocks) {
+  __shared__ int s_scan[1024];
+  const int t = threadIdx.x;
+  const int per = (n_box + 1023) / 1024;
+  const int b0 = min(n_box, t * per), b1 = min(n_box, b0 + per);
+  auto walk = [&](int b, auto emit) {
+    const Rect r = rect_of(__ldg(boxes + b), fs);
+    if (r.x1 <= r.x0 || r.y1 <= r.y0) return 0;
+    const int xlo = max(0, r.x0 - 1) & ~1, xhi = min(fs, r.x1 + 1), ylo = max(0, r.y0 - 1) & ~1, yhi = min(fs, r.y1 + 1);
+    int n = 0;
+    for (int y = ylo; y < yhi; y += bh)
+      for (int x = xlo; x < xhi; x += 8) {
+        emit((b << 8) | ((min(y, fs - bh) >> 1) << 4) | (min(x, fs - 8) >> 1));
+        ++n;
+      }
+    return n;
+  };
+  int cnt = 0;
+  for (int b = b0; b < b1; ++b) cnt += walk(b, [](int) {});
+  s_scan[t] = cnt;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    const int v = t >= d ? s_scan[t - d] : 0;
+    __syncthreads();
+    s_scan[t] += v;
+    __syncthreads();
+  }
+  int o = s_scan[t] - cnt;
+  if (t == 1023) n_blocks[0] = s_scan[t];
+  for (int b = b0; b < b1; ++b) walk(b, [&](int e) { blocks[o++] = e; });
+}
+
 // Pooled conv3_1 output of a pair outside the cells both boxes reach: a cell only the subject's box reaches equals the map of
 // the pair (subject, EMPTY box), one only the object's box reaches equals (EMPTY box, object), the rest is the background.
 // One CTA per pair; a cell is 1024 channels = 128 uint4, so 256 threads move two cells per iteration.  Cells both boxes
@@ -309,4 +346,18 @@ extern "C" int hc_pair_cover_masks(const int32_t* boxes, const int32_t* pair_sub
                                                                      feature_size, block_rows / 2, block_cols / 2, shared != 0,
                                                                      reinterpret_cast<unsigned long long*>(masks));
   return cuda_status("pair_cover_masks_kernel launch");
+}
+
+extern "C" int hc_conv2_box_blocks(const int32_t* boxes, int32_t n_box, int32_t feature_size, int32_t block_rows, int32_t* blocks,
+                                   int32_t* n_blocks, hc_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  HC_REQUIRE(n_blocks && (n_box <= 0 || (boxes && blocks)), HC_E_NULL, "hc_conv2_box_blocks: NULL operand");
+  int rc = hc_device_check();
+  if (rc != HC_OK) return rc;
+  HC_REQUIRE(feature_size == 32, HC_E_SHAPE, "hc_conv2_box_blocks: built for feature_size 32 (block origins are packed in 4 bits of even pixels)");
+  HC_REQUIRE(block_rows == 8 || block_rows == 4, HC_E_SHAPE, "hc_conv2_box_blocks: block_rows must be 8 or 4");
+  HC_REQUIRE(n_box >= 0 && n_box < (1 << 23), HC_E_SHAPE, "hc_conv2_box_blocks: n_box must be below 2^23");
+  HC_REQUIRE(aligned16(boxes), HC_E_ALIGN, "hc_conv2_box_blocks: boxes must be 16-byte aligned");
+  conv2_blocks_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const int4*>(boxes), n_box, feature_size, block_rows, blocks, n_blocks);
+  return cuda_status("conv2_blocks_kernel launch");
 }

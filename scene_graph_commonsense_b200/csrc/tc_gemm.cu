@@ -585,6 +585,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             auto out_row = [&](int tr) -> long long {
               if (p.mode == HC_GEMM_CONV3)
                 return ((long long)t_img * p.H + (t_y0 + 8 * j + (tr >> 4))) * p.W + (t_x0 + (tr & 15));
+              if (blk_mode) {   // un-pooled block mode: tile row -> pixel (y0 + r / blk_w, x0 + r % blk_w) of its block's image
+                const int rows_pb = p.blk_w * p.blk_h;
+                const int e = __ldg(p.blocks + min((m_blk * MS + j) * blk_per_sub + tr / rows_pb, n_blocks - 1));
+                const int rb = tr % rows_pb;
+                return ((long long)(e >> 8) * p.H + (2 * ((e >> 4) & 15) + rb / p.blk_w)) * p.W + (2 * (e & 15) + rb % p.blk_w);
+              }
               long long row = (long long)(m_blk * MS + j) * BM + tr;
               return row < p.M ? row : -1;
             };
@@ -774,9 +780,9 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   HC_REQUIRE(!pooled || ((d->mode == HC_GEMM_CONV3 || d->mode == HC_GEMM_CONV3_BLOCKS) && d->bias), HC_E_SHAPE,
              "hc_tc_gemm: pooled epilogue needs conv mode and a bias");
   const int blk_w = d->block_cols ? d->block_cols : 8;
-  HC_REQUIRE(d->mode != HC_GEMM_CONV3_BLOCKS || (pooled && d->blocks && d->n_blocks && (d->block_rows == 8 || d->block_rows == 4) &&
-                                                 (blk_w == 8 || (blk_w == 4 && d->block_rows == 4))),
-             HC_E_SHAPE, "hc_tc_gemm: block-sparse conv needs the pooled epilogue, a work list and 8x8, 8x4 or 4x4-pixel blocks");
+  HC_REQUIRE(d->mode != HC_GEMM_CONV3_BLOCKS || ((pooled || d->epilogue == HC_EPI_BF16) && d->blocks && d->n_blocks &&
+                                                 (d->block_rows == 8 || d->block_rows == 4) && (blk_w == 8 || (blk_w == 4 && d->block_rows == 4))),
+             HC_E_SHAPE, "hc_tc_gemm: block-sparse conv needs a pooled or the bf16 epilogue, a work list and 8x8, 8x4 or 4x4-pixel blocks");
   HC_REQUIRE(d->epilogue != HC_EPI_POOL_DIFF_BF16 ||
                  (d->mode == HC_GEMM_CONV3_BLOCKS && d->diff_sub && d->diff_obj && d->diff_bg && d->pair_sub && d->pair_obj && d->pair_row &&
                   aligned16(d->diff_sub) && aligned16(d->diff_obj) && aligned16(d->diff_bg)),

@@ -97,6 +97,7 @@ class PackedHead:
         self.b_heads = torch.cat([f32(b) for b in biases]).contiguous()
         self.device = dev
         self._p3_bg = None
+        self._uv_bg = None
 
     # ---------------------------------------------------------------------------- dense stages (model.py:138-150,175)
     def conv2_halves(self, abox, m_sub=1):
@@ -111,14 +112,36 @@ class PackedHead:
                         n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=m_sub, tag="conv2_half")
         return u, v
 
+    def uv_background(self):
+        """conv2_1 halves [1,32,32,512] bf16 of a box whose mask is empty (tanh(conv1 bias) everywhere): what U / V of any box equal
+        farther than one pixel from the box.  Weights-only: computed once, through the dense kernel."""
+        if self._uv_bg is None:
+            fs = 32
+            abox = self.fill.view(1, 1, 1, -1).expand(1, fs, fs, self.fill.numel()).contiguous()
+            self._uv_bg = self.conv2_halves(abox)
+        return self._uv_bg
+
+    def conv2_halves_sparse(self, abox, boxes, m_sub=1, block_rows=4):
+        """`conv2_halves` on the box footprint: U / V are pre-filled with the background maps and the implicit GEMM visits only the
+        8 x block_rows-pixel blocks within one pixel of each box (`ops.conv2_box_blocks`); bit-identical to the dense halves."""
+        n_box, fs = abox.shape[0], abox.shape[1]
+        u_bg, v_bg = self.uv_background()
+        u = ops.broadcast_rows(u_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device))
+        v = ops.broadcast_rows(v_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device))
+        blocks, n_blocks = ops.conv2_box_blocks(boxes, block_rows, fs)
+        for out, w, base, bias in ((u, self.w2s, 0, None), (v, self.w2o, 128, self.b2)):
+            ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, bias=bias, ldc=512, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_BF16, act=ACT_NONE,
+                        n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=m_sub, tag="conv2_half", blocks=blocks,
+                        n_blocks=n_blocks, block_rows=block_rows, block_cols=8)
+        return u, v
+
     def p3_background(self):
         """Pooled conv3_1 output [1,8,8,1024] bf16 of a pair whose two box masks are empty: tanh(conv1 bias) everywhere
         (train_test.py:391,398 zero the map outside the box) pushed through the same kernels as real pairs, so a real pair's
         output equals it bit for bit wherever the receptive field misses both boxes.  Weights-only: computed once."""
         if self._p3_bg is None:
             fs = 32
-            abox = self.fill.view(1, 1, 1, -1).expand(1, fs, fs, self.fill.numel()).contiguous()
-            u, v = self.conv2_halves(abox)
+            u, v = self.uv_background()
             zero = torch.zeros(1, dtype=torch.int32, device=self.device)
             p2 = ops.pair_relu_pool(u, v, None, zero, zero, fs)
             p3 = torch.empty(1, 8, 8, 1024, dtype=torch.bfloat16, device=self.device)

@@ -126,6 +126,21 @@ def p3_assemble(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, 
     return out
 
 
+@_op("conv2_box_blocks", "(Tensor boxes, int block_rows, int fs, Tensor(a!) blocks, Tensor(b!) n_blocks) -> ()")
+def _conv2_box_blocks(boxes, block_rows, fs, blocks, n_blocks):
+    _A.conv2_box_blocks(boxes, block_rows, fs, blocks=blocks, n_blocks=n_blocks)
+
+
+def conv2_box_blocks(boxes, block_rows=4, fs=32, blocks=None, n_blocks=None):
+    """Device work list (blocks, n_blocks) of the conv2_1 output blocks within one pixel of each box (everything else is background)."""
+    if blocks is None:
+        blocks = torch.empty(max(boxes.shape[0] * 4 * (32 // block_rows), 1), dtype=torch.int32, device=boxes.device)
+    if n_blocks is None:
+        n_blocks = torch.empty(1, dtype=torch.int32, device=boxes.device)
+    _call("conv2_box_blocks")(boxes, block_rows, fs, blocks, n_blocks)
+    return blocks, n_blocks
+
+
 @_op("pair_cell_keys", "(Tensor boxes, Tensor pair_sub, Tensor pair_obj, int fs) -> Tensor")
 def _pair_cell_keys(boxes, pair_sub, pair_obj, fs):
     return _A.pair_cell_keys(boxes, pair_sub, pair_obj, fs)

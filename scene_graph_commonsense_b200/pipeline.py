@@ -176,6 +176,9 @@ class RelationPipeline:
         # reads it (block + 1-pixel halo, `ops.pair_cover_masks`) - the rest of the buffer is never read
         self.pool_footprint = os.environ.get("HC_POOL_FOOTPRINT", "1") != "0"
         self.debug_poison = False
+        # conv2_1 halves only within one pixel of each box, background elsewhere (bit-identical; kernel-level parity test only so
+        # far - off until a full GPU validation and A/B, see DESIGN "what comes next")
+        self.conv2_sparse = os.environ.get("HC_CONV2_SPARSE", "0") == "1"
         self.early_pool = os.environ.get("HC_EARLY_POOL", "1") != "0"     # first chunks' pooling starts under the per-box stages
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.last_k_masks = None             # int64 [n_tiles] device tensor: K-cell masks of the last shared fc1
@@ -208,6 +211,8 @@ class RelationPipeline:
         ops.tc_gemm(x, pk.w1, t, n_img * fs * fs, 256, K1_PAD, bias=pk.b1, lda=K1_PAD, ldc=256, epilogue=EPI_BF16, act=ACT_TANH,
                     group_m=8, tag="conv1")
         abox = ops.box_select(t, boxes, box_img, pk.fill, fs)
+        if self.conv2_sparse:
+            return pk.conv2_halves_sparse(abox, boxes, m_sub=self.conv2_m_sub)
         return pk.conv2_halves(abox, m_sub=self.conv2_m_sub)
 
     def box_maps(self, boxes_x, u, v, with_background_row=False):

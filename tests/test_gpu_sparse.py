@@ -204,3 +204,39 @@ def test_pipeline_sparse_equals_dense(block_rows, shared, block_cols):
     for a, c in zip(outs[0], outs[1]):
         assert torch.equal(a, c)
     assert torch.equal(outs[0][0], outs[0][4])
+
+
+@pytest.mark.parametrize("block_rows,m_sub", [(4, 1), (8, 1), (4, 2)])
+def test_conv2_halves_on_the_box_footprint_equal_dense_bit_for_bit(block_rows, m_sub):
+    """conv2_1 halves computed only within one pixel of each box over a background pre-fill == the dense halves, every bf16 bit;
+    the work list covers the dilated box rectangle with blocks inside the map and lists nothing for an empty box."""
+    from scene_graph_commonsense_b200 import ops
+    pk = _packed()
+    boxes = _random_boxes(30, 23)
+    boxes_dev = boxes.to(DEV)
+    n_box = boxes.shape[0]
+    g = torch.Generator().manual_seed(9)
+    t_img = torch.tanh(torch.randn(2, 32 * 32, 256, generator=g)).to(torch.bfloat16).to(DEV)
+    box_img = (torch.arange(n_box, dtype=torch.int32) % 2).to(DEV)
+    abox = ops.box_select(t_img, boxes_dev, box_img, pk.fill, 32)
+    u0, v0 = pk.conv2_halves(abox, m_sub=m_sub)
+    u1, v1 = pk.conv2_halves_sparse(abox, boxes_dev, m_sub=m_sub, block_rows=block_rows)
+    torch.cuda.synchronize()
+    assert torch.equal(u0.view(torch.int16), u1.view(torch.int16))
+    assert torch.equal(v0.view(torch.int16), v1.view(torch.int16))
+    blocks, n_blocks = ops.conv2_box_blocks(boxes_dev, block_rows)
+    e = blocks[:int(n_blocks.item())].cpu().numpy()
+    box, oy, ox = e >> 8, 2 * ((e >> 4) & 15), 2 * (e & 15)
+    assert (ox + 8 <= 32).all() and (oy + block_rows <= 32).all() and (np.diff(box) >= 0).all()
+    cover = np.zeros((n_box, 32, 32), bool)
+    for b_, y, x in zip(box, oy, ox):
+        cover[b_, y:y + block_rows, x:x + 8] = True
+    for i, bx in enumerate(boxes.numpy()):
+        x0, x1, y0, y1 = (_slice_bound(int(v)) for v in bx)
+        want = np.zeros((32, 32), bool)
+        if x1 > x0 and y1 > y0:
+            want[max(y0 - 1, 0):y1 + 1, max(x0 - 1, 0):x1 + 1] = True
+        assert not (want & ~cover[i]).any()
+        if not want.any():
+            assert not cover[i].any()
+    assert 0 < len(e) < n_box * 4 * (32 // block_rows)
