@@ -176,9 +176,9 @@ class RelationPipeline:
         # reads it (block + 1-pixel halo, `ops.pair_cover_masks`) - the rest of the buffer is never read
         self.pool_footprint = os.environ.get("HC_POOL_FOOTPRINT", "1") != "0"
         self.debug_poison = False
-        # conv2_1 halves only within one pixel of each box, background elsewhere (bit-identical; kernel-level parity test only so
-        # far - off until a full GPU validation and A/B, see DESIGN "what comes next")
-        self.conv2_sparse = os.environ.get("HC_CONV2_SPARSE", "0") == "1"
+        # conv2_1 halves only within one pixel of each box, background elsewhere: bit-identical to the dense halves
+        # (tests/test_gpu_sparse.py), cfg2 step 55.5 -> 51.7 ms on one box (profiles/bench_r01N_*)
+        self.conv2_sparse = os.environ.get("HC_CONV2_SPARSE", "1") != "0"
         self.early_pool = os.environ.get("HC_EARLY_POOL", "1") != "0"     # first chunks' pooling starts under the per-box stages
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.last_k_masks = None             # int64 [n_tiles] device tensor: K-cell masks of the last shared fc1
