@@ -244,6 +244,11 @@ def run_ours(args):
         fc1_cells = int(np.unpackbits(pipe.last_k_masks.cpu().numpy().view(np.uint8)).sum())
         fc1_exec_frac = fc1_cells * 256.0 / (pairs_step * 64.0)
     n_box_step = wl["images"] * wl["boxes"]
+    # conv2_1 halves on the box footprint: listed 8 x block_rows-pixel blocks of the last step vs the 1024 pixels of every box map
+    conv2_exec_frac = 1.0
+    if getattr(pipe, "conv2_sparse", False) and packed.last_conv2_blocks is not None:
+        nb_dev, rows_c2, boxes_c2 = packed.last_conv2_blocks
+        conv2_exec_frac = int(nb_dev.item()) * 8.0 * rows_c2 / (boxes_c2 * 1024.0)
 
     per_tag = {}
     for tag, a, b in ops.PROFILE["events"]:
@@ -323,6 +328,7 @@ def run_ours(args):
     flop_dense = wl["images"] * FLOP_IMG + wl["images"] * wl["boxes"] * FLOP_BOX + pairs_step * FLOP_PAIR
     flop_step = flop_dense - (1.0 - conv3_exec_frac) * pairs_step * FLOP_PAIR_CONV3      # FLOPs actually executed
     flop_step += fc1_box_flop - (1.0 - fc1_exec_frac) * pairs_step * FLOP_PAIR_FC1
+    flop_step -= (1.0 - conv2_exec_frac) * n_box_step * FLOP_BOX
     m = pipeline.metrics_from_counters(counters_final)
 
     cpu = None
@@ -339,7 +345,8 @@ def run_ours(args):
                    "l2": "no explicit flush: each step streams >10 GB of activations/weights (>> 126 MB L2)",
                    "weights": "random init, trained-scale logits (seed 0)", "chunk_pairs": chunk_pairs,
                    "pool_gemm_overlap": not args.no_overlap, "conv3_m_sub": args.conv3_m_sub, "chunk_policy": args.chunk_policy,
-                   "conv3": args.conv3, "fc1": args.fc1 if pipe.fc1_shared else "dense"},
+                   "conv3": args.conv3, "fc1": args.fc1 if pipe.fc1_shared else "dense",
+                   "conv2": "box footprint" if getattr(pipe, "conv2_sparse", False) else "dense"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes * world,
                 "d2h_bytes_per_step": (tables.COUNTER_SIZE * 8 + 4) * world, "ms_per_step": t_e2e / args.steps * 1e3,
                 "api": "RelationPipeline.run over pinned HostBatch windows (H2D of window k+1 issued under window k's kernels; "
@@ -347,7 +354,8 @@ def run_ours(args):
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_second": roof_second,
         "step_tensor_frac": flop_step / (t_max / args.steps) / 1e12 / pk["bf16_sustained"],
         "algorithmic_tflop_per_step": flop_dense / 1e12, "executed_tflop_per_step": flop_step / 1e12,
-        "conv3_blocks_per_step": blocks_step, "fc1_cells_per_step": fc1_cells, "kernel_breakdown": breakdown,
+        "conv3_blocks_per_step": blocks_step, "fc1_cells_per_step": fc1_cells, "conv2_executed_fraction": conv2_exec_frac,
+        "kernel_breakdown": breakdown,
         "recall": {"R@20/50/100": m["evaluator"][0], "mR@20/50/100": [float(x) for x in m["evaluator"][2]]},
         "cpu_baseline": cpu,
     }

@@ -98,6 +98,7 @@ class PackedHead:
         self.device = dev
         self._p3_bg = None
         self._uv_bg = None
+        self.last_conv2_blocks = None
 
     # ---------------------------------------------------------------------------- dense stages (model.py:138-150,175)
     def conv2_halves(self, abox, m_sub=1):
@@ -129,6 +130,7 @@ class PackedHead:
         u = ops.broadcast_rows(u_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device))
         v = ops.broadcast_rows(v_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device))
         blocks, n_blocks = ops.conv2_box_blocks(boxes, block_rows, fs)
+        self.last_conv2_blocks = (n_blocks, block_rows, n_box)      # device count: bench.py reads it after the timed region
         for out, w, base, bias in ((u, self.w2s, 0, None), (v, self.w2o, 128, self.b2)):
             ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, bias=bias, ldc=512, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_BF16, act=ACT_NONE,
                         n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=m_sub, tag="conv2_half", blocks=blocks,
