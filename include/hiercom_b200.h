@@ -256,7 +256,10 @@ int hc_pair_cover_masks(const int32_t* boxes, const int32_t* pair_sub, const int
 /* ---------------------------------------------------------------------------------------------------------
  * R6 tail + R7 - label-embedding add, fc2 bias + ReLU, fc3_x / fc4 / fc5 heads and the Bayesian hierarchical
  * log-softmax (model.py:152-168,175-184; flat variant model.py:97-101).
- *   pred = relu(fc2_raw + fc2_bias + E[c_sub] + E[150+c_obj] + sum E[300+s_sub] + sum E[317+s_obj])
+ *   pred = relu(fc2_raw + fc2_bias + E[c_sub] + E[150+c_obj] + sum' E[300+s_sub] + sum' E[317+s_obj])
+ *   sum' = utils.py:136-149 `process_super_class`: the FIRST entry of the box's super-class list plus, for a list of
+ *   2..4 entries, its LAST entry (the middle entries of 3- and 4-entry lists are never added by the reference).
+ *   box_super holds the raw lists (left-packed, -1 padded); the kernels apply the rule.
  *   hier : super = log_softmax(fc5 pred); rel_k = log_softmax(fc3_k pred / T_k) + super[k]; conn = fc4 pred
  *   flat : relation = fc3 pred (raw logits), conn = fc4 pred
  * emb is fc2.weight[:, 4096:].T, f32 [n_emb, hidden].  w_heads rows: hier [fc3_1; fc3_2; fc3_3; fc4; fc5],

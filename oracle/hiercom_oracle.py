@@ -29,11 +29,15 @@ TOP_K = (20, 50, 100)
 
 
 def process_super_class(s_list, num_super_classes=17):
-    """utils.py:136-149 - list of 1..4 super-class ids per object -> multi-hot (a sum of one-hots) int64 [B,17]."""
+    """utils.py:136-149 - list of super-class ids per object -> int64 [B,17]: one_hot(s[0]) plus, for i in 1..3, one_hot(s[i])
+    added to the rows with len(s) == i + 1 ONLY (`idx = nonzero([len(s) == i + 1 ...])`, :139-141): a list of 2..4 entries
+    contributes its first and its LAST entry, the middle ones are never added; longer lists keep s[0] alone."""
     out = torch.zeros(len(s_list), num_super_classes, dtype=torch.int64)
     for r, s in enumerate(s_list):
-        for v in list(s)[:4]:
-            out[r, int(v)] += 1
+        s = [int(v) for v in s]
+        out[r, s[0]] += 1
+        if 2 <= len(s) <= 4:
+            out[r, s[-1]] += 1
     return out
 
 

@@ -26,27 +26,45 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def _stale(src, obj):
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    deps = [src, os.path.join(HERE, "..", "include", "hiercom_b200.h")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+                                                                            if f.endswith((".cuh", ".h"))]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
 def build(force=False, verbose=False):
+    """Compiles the stale sources in parallel (one nvcc per file) and links; `force` recompiles everything."""
     if not force and not needs_build():
         return LIB
-    objs = []
+    from concurrent.futures import ThreadPoolExecutor
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+    objs = [os.path.join(CSRC, src.replace(".cu", ".o")) for src in SOURCES]
+
+    def compile_one(args):
+        src, obj = args
+        if not force and not _stale(os.path.join(CSRC, src), obj):
+            return src, 0, "", ""
+        r = subprocess.run([nvcc()] + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return src, r.returncode, r.stdout, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, zip(SOURCES, objs)))
     log = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc()] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append(r.stderr)
-        if r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
+    for src, rc, out, err in results:
+        if err:
+            log.append("== %s\n%s" % (src, err))
+        if rc != 0:
+            sys.stderr.write(out + err)
             raise RuntimeError("nvcc failed on " + src)
-        objs.append(obj)
     cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    with open(os.path.join(CSRC, "ptxas.log"), "w") as f:
+    with open(os.path.join(CSRC, "ptxas.log"), "a" if not force else "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))

@@ -28,6 +28,15 @@ __device__ __forceinline__ void add_row(float4 (&x)[HEAD_HV], const float* __res
   }
 }
 
+// Super-class multi-hot of utils.py:136-149 (`process_super_class`): one_hot(s[0]) plus, for a list of 2..4 entries, one_hot of
+// its LAST entry only - `sc[idx] += one_hot(s[i])` runs over the rows with len(s) == i + 1, so the middle entries of a 3- or
+// 4-entry list are never added (13 of the 150 VG classes have 3 super-classes).  box_super rows are the raw lists, left-packed,
+// -1 padded; these two helpers pick the entries the reference sums.
+__device__ __forceinline__ int super_count(const int8_t* __restrict__ s) {
+  return (s[0] >= 0) + (s[1] >= 0) + (s[2] >= 0) + (s[3] >= 0);
+}
+__device__ __forceinline__ bool super_used(int k, int n) { return k < n && (k == 0 || k == n - 1); }
+
 // value j of a warp-distributed vector lives in lane (j & 31), register (j >> 5)
 __device__ __forceinline__ float seg_pick(float v0, float v1, int lane, int a, int b, float other) {
   float r = other;
@@ -86,11 +95,12 @@ hier_head_kernel(const float* __restrict__ raw, long long ld_raw, int n_rows, co
           add_row(x[r], emb + (long long)(num_obj + box_cat[bo]) * hidden, lane);
         }
         if (box_super && !box_emb) {
+          const int n1 = super_count(box_super + bs * 4), n2 = super_count(box_super + bo * 4);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             int s1 = box_super[bs * 4 + k], s2 = box_super[bo * 4 + k];
-            if (s1 >= 0) add_row(x[r], emb + (long long)(2 * num_obj + s1) * hidden, lane);
-            if (s2 >= 0) add_row(x[r], emb + (long long)(2 * num_obj + num_super + s2) * hidden, lane);
+            if (super_used(k, n1)) add_row(x[r], emb + (long long)(2 * num_obj + s1) * hidden, lane);
+            if (super_used(k, n2)) add_row(x[r], emb + (long long)(2 * num_obj + num_super + s2) * hidden, lane);
           }
         }
 #pragma unroll
@@ -209,10 +219,11 @@ __global__ void box_label_embed_kernel(const float* __restrict__ emb, int num_ob
     for (int i = 0; i < HEAD_HV; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     add_row(x, emb + (long long)(role * num_obj + c) * hidden, lane);
     if (box_super) {
+      const int ns = super_count(box_super + box * 4);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         int sc = box_super[box * 4 + k];
-        if (sc >= 0) add_row(x, emb + (long long)(2 * num_obj + role * num_super + sc) * hidden, lane);
+        if (super_used(k, ns)) add_row(x, emb + (long long)(2 * num_obj + role * num_super + sc) * hidden, lane);
       }
     }
 #pragma unroll

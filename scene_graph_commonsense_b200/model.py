@@ -31,10 +31,13 @@ def strip_module_prefix(state_dict):
 
 
 def supers_to_table(s_list, device):
-    """list of 1..4 super-class id tensors (utils.py:136-149 input format) -> int8 [n,4], -1 padded."""
+    """list of super-class id tensors (utils.py:136-149 input format) -> int8 [n,4], -1 padded: the RAW lists.  The kernels
+    apply the reference's summing rule (first entry + last entry of a 2..4-entry list, `head.cu` `super_used`); a list longer
+    than 4 contributes its first entry only in the reference (its `range(1, 4)` loop never matches), so only that is kept."""
     out = torch.full((len(s_list), 4), -1, dtype=torch.int8)
     for r, s in enumerate(s_list):
-        vals = [int(v) for v in (s.tolist() if hasattr(s, "tolist") else list(s))][:4]
+        vals = [int(v) for v in (s.tolist() if hasattr(s, "tolist") else list(s))]
+        vals = vals if len(vals) <= 4 else vals[:1]
         for j, v in enumerate(vals):
             out[r, j] = v
     return out.to(device)

@@ -101,7 +101,8 @@ def host_batch_from_samples(samples, skip_mode="batch", group_size=None, sgdet=F
     r = 0
     for lst in sup_l:
         for sc in lst:
-            v = np.asarray(sc, dtype=np.int64)[:4]
+            v = np.asarray(sc, dtype=np.int64)
+            v = v if len(v) <= 4 else v[:1]      # raw list; the kernels sum first + last entry like utils.py:136-149
             supers[r, :len(v)] = v
             r += 1
     arrays["supers"] = supers

@@ -99,6 +99,53 @@ def make_image(image_id, num_boxes, base_seed=0, p_rel=0.3, with_maps=True, p_fa
     return ImageSample(image_id, feat, depth, bbox, cats, supers, rels, dirs)
 
 
+def with_categories(sample, cats):
+    """The same sample with its object categories (and the super-category lists that follow from them) replaced: lets a test
+    force classes with 1, 2 and 3 super-classes (`sub2super_cat_dict.pt`: 118 / 19 / 13 of the 150) into a small image."""
+    s2s = tables.sub2super_table()
+    sample.categories = torch.as_tensor([int(c) for c in cats], dtype=torch.int64)
+    sample.super_categories = [torch.as_tensor([int(v) for v in s2s[int(c)] if v >= 0], dtype=torch.int64) for c in cats]
+    return sample
+
+
+def assign_gt_from_scores(sample, relation_of, splits=(15, 11, 24), p_model=0.8, p_top=0.5, base_seed=0):
+    """Re-labels the GT relations of `sample` from a model's own scores so that Recall@K is discriminating (hits exist, and a wrong
+    score or ranking changes them): a related unordered pair keeps its direction; with probability `p_model` its predicate
+    becomes one of the three per-super-category argmaxes of `relation_of(sub, obj)` (f32[sum(splits)] log-joints of the DIRECTED
+    pair) - the best of the three with probability `p_top`, else a uniformly chosen one - otherwise it keeps its random label.
+    Deterministic in (base_seed, image_id); modifies and returns the sample."""
+    g = _gen(base_seed + 104729, sample.image_id)
+    offs = np.concatenate(([0], np.cumsum(splits)))
+    for gi in range(1, len(sample.categories)):
+        for e in range(gi):
+            d = int(sample.subj_or_obj[gi - 1][e])
+            u = torch.rand(3, generator=g)
+            if d < 0 or float(u[0]) >= p_model:
+                continue
+            sub, obj = (gi, e) if d == 1 else (e, gi)
+            r = np.asarray(relation_of(sub, obj), dtype=np.float32)
+            arg = [int(offs[k] + np.argmax(r[offs[k]:offs[k + 1]])) for k in range(len(splits))]
+            if float(u[1]) < p_top:
+                lab = max(arg, key=lambda a: (r[a], -a))
+            else:
+                lab = arg[min(int(float(u[2]) * len(arg)), len(arg) - 1)]
+            sample.relationships[gi - 1][e] = lab
+    return sample
+
+
+WEIGHT_PRESETS = {
+    # name: (trunk_gain, logit_gain).  "init" = nn default init; "trained" = the round-1 trained-scale variant (head layers
+    # only: logit std 1.1, `pred` <= 0.09); "sharp" = He-gain trunk (`pred` O(1), max 1.8) and logit std 3.3 (SURVEY §8d, H5):
+    # the top joint probability has median 0.46 and bf16 operand rounding reaches the probabilities at full scale.
+    "init": (1.0, 1.0), "trained": (1.0, 40.0), "sharp": (6.0 ** 0.5, 16.0),
+}
+
+
+def preset_state_dict(name, seed=0, **kw):
+    tg, lg = WEIGHT_PRESETS[name]
+    return head_state_dict(seed=seed, logit_gain=lg, trunk_gain=tg, **kw)
+
+
 def make_sgdet_image(image_id, num_gt, num_prop, base_seed=0, p_rel=0.3, with_maps=True):
     """SGDET/SGCLS-shaped sample: `num_prop` float proposals; the first `num_gt` are
     jittered copies of the GT boxes with the GT label (so matches exist), the rest are random."""
@@ -170,10 +217,13 @@ def make_batch(image_ids, num_boxes, base_seed=0, p_rel=0.3, with_maps=True):
 
 
 def head_state_dict(seed=0, input_dim=128, feature_size=32, num_classes=150, num_super_classes=17,
-                    splits=(15, 11, 24), logit_gain=1.0, vg=True, flat=False, dtype=torch.float32):
+                    splits=(15, 11, 24), logit_gain=1.0, vg=True, flat=False, dtype=torch.float32, trunk_gain=1.0):
     """Weights drawn like nn.Conv2d/nn.Linear default init (U(-1/sqrt(fan_in), 1/sqrt(fan_in))) from one seeded
     generator, in a fixed key order, so the reference module, the oracle and the CUDA path all load the same
-    values.  `logit_gain` scales the final classification layers ("trained-scale" variant)."""
+    values.  `logit_gain` scales the final classification layers ("trained-scale" variant).  `trunk_gain`
+    scales the weights of conv2_1 / conv3_1 / fc1 / fc2 (default init shrinks the signal by ~2x per ReLU layer, leaving
+    `pred` at 0.08; sqrt(6) is the variance-preserving He gain, so `pred` is O(1) and bf16 rounding in the trunk reaches
+    the logits at full scale).  The random draws are identical for every gain."""
     g = torch.Generator(device="cpu")
     g.manual_seed(1_000_000_007 + int(seed))
 
@@ -189,13 +239,13 @@ def head_state_dict(seed=0, input_dim=128, feature_size=32, num_classes=150, num
     for name in ("conv1_1", "conv1_2"):
         sd[name + ".weight"] = u((c, cin, 1, 1), cin)
         sd[name + ".bias"] = u((c,), cin)
-    sd["conv2_1.weight"] = u((4 * c, 2 * c, 3, 3), 2 * c * 9)
+    sd["conv2_1.weight"] = u((4 * c, 2 * c, 3, 3), 2 * c * 9, trunk_gain)
     sd["conv2_1.bias"] = u((4 * c,), 2 * c * 9)
-    sd["conv3_1.weight"] = u((8 * c, 4 * c, 3, 3), 4 * c * 9)
+    sd["conv3_1.weight"] = u((8 * c, 4 * c, 3, 3), 4 * c * 9, trunk_gain)
     sd["conv3_1.bias"] = u((8 * c,), 4 * c * 9)
-    sd["fc1.weight"] = u((4096, fc1_in), fc1_in)
+    sd["fc1.weight"] = u((4096, fc1_in), fc1_in, trunk_gain)
     sd["fc1.bias"] = u((4096,), fc1_in)
-    sd["fc2.weight"] = u((512, fc2_in), fc2_in)
+    sd["fc2.weight"] = u((512, fc2_in), fc2_in, trunk_gain)
     sd["fc2.bias"] = u((512,), fc2_in)
     if flat:
         sd["fc3.weight"] = u((sum(splits), 512), 512, logit_gain)

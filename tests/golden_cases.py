@@ -47,3 +47,38 @@ TRAIN_CASES = {
     "tr_flat_cs": dict(ids=[102, 103, 104], n=[6, 4, 5], run_mode="train_cs", hierar=False, cs=(11, 0.5, 0.1), gain=3.0),
     "tr_flat_plain": dict(ids=[105, 106], n=[7, 3], run_mode="train", hierar=False, gain=1.0),
 }
+
+
+# Head / pipeline goldens through the REAL reference modules end to end (BayesianRelationClassifier -> evaluate_one_direction
+# -> Evaluator / Evaluator_Top3), with object classes forced to cover 1, 2 and 3 super-classes (the reference's
+# process_super_class adds only the first and the last entry of a list), an empty box, ragged sizes and the batch skip rule.
+REAL_PIPELINE_CASE = dict(ids=[110, 111, 112], n=[5, 3, 4],
+                          cats=[[7, 12, 0, 2, 20], [8, 3, 15], [25, 1, 101, 16]], run_mode="eval_cs", p_rel=0.7,
+                          empty_box=(1, 2), presets=("trained", "sharp"))
+HEAD3_CASE = dict(id=902, n=6, cats=[7, 12, 0, 2, 20, 3], pairs=[(0, 1), (1, 0), (2, 0), (0, 3), (3, 4), (5, 1), (4, 5), (2, 3)],
+                  presets=("trained", "sharp"))
+
+
+def real_pipeline_samples(case=None):
+    """The samples of REAL_PIPELINE_CASE (shared by the generator and the tests that replay it)."""
+    import torch
+    from scene_graph_commonsense_b200 import synthetic
+    case = case or REAL_PIPELINE_CASE
+    samples = [synthetic.with_categories(synthetic.make_image(i, n, p_rel=case["p_rel"]), c)
+               for i, n, c in zip(case["ids"], case["n"], case["cats"])]
+    if case.get("empty_box"):
+        i, j = case["empty_box"]
+        samples[i].bbox[j] = torch.tensor([5, 5, 9, 12], dtype=samples[i].bbox.dtype)      # xmin == xmax: an all-zero mask
+    return samples
+
+
+def install_gt(samples, flat):
+    """Writes a flat relationships array (image-major, rows g = 1..N-1, e < g) back into the samples."""
+    import torch
+    k = 0
+    for s in samples:
+        for gi in range(1, len(s.categories)):
+            s.relationships[gi - 1] = torch.as_tensor(flat[k:k + gi], dtype=s.relationships[gi - 1].dtype)
+            k += gi
+    assert k == len(flat)
+    return samples
