@@ -105,12 +105,12 @@ WORKLOADS = {
 }
 
 
-def make_samples(rank, n_images=IMAGES_PER_GPU, boxes=BOXES, with_maps=True, sgdet=False):
+def make_samples(rank, n_images=IMAGES_PER_GPU, boxes=BOXES, with_maps=True, sgdet=False, boxes_mode="small"):
     from scene_graph_commonsense_b200 import synthetic
     ids = [rank * n_images + i for i in range(n_images)]
     if sgdet:
-        return [synthetic.make_sgdet_image(i, 20, boxes, base_seed=0, p_rel=0.3, with_maps=with_maps) for i in ids]
-    return synthetic.make_batch(ids, boxes, base_seed=0, p_rel=0.3, with_maps=with_maps)
+        return [synthetic.make_sgdet_image(i, 20, boxes, base_seed=0, p_rel=0.3, with_maps=with_maps, box_mode=boxes_mode) for i in ids]
+    return synthetic.make_batch(ids, boxes, base_seed=0, p_rel=0.3, with_maps=with_maps, box_mode=boxes_mode)
 
 
 # ======================================================================================================= reference arm

@@ -91,6 +91,28 @@ class BayesHead(nn.Module):
             self._versions = versions
         return self._packed
 
+    def packed_bf16(self):
+        """Plain bf16 [128, input_dim] packing (precision="bf16": one MMA per product instead of three)."""
+        versions = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if getattr(self, "_packed1", None) is None or versions != self._versions1:
+            w = torch.cat((self.fc3_1.weight, self.fc3_2.weight, self.fc3_3.weight, self.fc5.weight)).detach().float()
+            b = torch.cat((self.fc3_1.bias, self.fc3_2.bias, self.fc3_3.bias, self.fc5.bias)).detach().float()
+            wp = torch.zeros(128, w.shape[1], device=w.device)
+            wp[:w.shape[0]] = w
+            bp = torch.zeros(128, device=w.device)
+            bp[:b.shape[0]] = b
+            self._packed1 = (wp.to(torch.bfloat16).contiguous(), bp.contiguous())
+            self._versions1 = versions
+        return self._packed1
+
+    def logits_from_bf16(self, a):
+        """bf16 [n, input_dim] -> f32 [n,128] logits with plain bf16 operands (fp32 accumulate)."""
+        w, b = self.packed_bf16()
+        n, k = a.shape
+        out = torch.empty(n, 128, dtype=torch.float32, device=a.device)
+        ops.tc_gemm(a, w, out, n, 128, k, bias=b, lda=k, ldc=128, epilogue=EPI_F32, group_m=8, tag="bayes_head")
+        return out
+
     def logits_from_split(self, a):
         """bf16 [n, 3*input_dim] in the bf16x3 layout (hc_split_bf16x3 / HC_EPI_SPLIT3_BF16) -> f32 [n,128] logits."""
         w, b = self.packed()
@@ -128,15 +150,19 @@ class BayesHeadProb(BayesHead):
 
 
 _PACKED_LINEAR = {}
+# Operand precision of the two SGB GEMMs (post_cat 1024 -> 4096, BayesHead 4096 -> 54): "bf16x3" = split operands
+# (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, ~fp32 accuracy, 3x the MMAs) or "bf16" = plain bf16 in / fp32 accumulate (north_star's format).
+DEFAULT_PRECISION = "bf16x3"
 
 
-def _packed_linear(lin):
-    """bf16x3 B-side packing of an nn.Linear, cached until its parameters change (data_ptr / version)."""
-    key = id(lin)
+def _packed_linear(lin, precision="bf16x3"):
+    """B-side packing of an nn.Linear (bf16x3 split or plain bf16), cached until its parameters change (data_ptr / version)."""
+    key = (id(lin), precision)
     ver = (lin.weight.data_ptr(), lin.weight._version, lin.bias.data_ptr(), lin.bias._version)
     hit = _PACKED_LINEAR.get(key)
     if hit is None or hit[0] != ver:
-        hit = (ver, ops.pack_weight_bf16x3(lin.weight), lin.bias.detach().float().contiguous())
+        w = ops.pack_weight_bf16x3(lin.weight) if precision == "bf16x3" else lin.weight.detach().to(torch.bfloat16).contiguous()
+        hit = (ver, w, lin.bias.detach().float().contiguous())
         _PACKED_LINEAR[key] = hit
     return hit[1], hit[2]
 
@@ -186,7 +212,7 @@ def global_pair_index(rel_pair_idxs, num_objs, device):
 
 @torch.no_grad()
 def hierarchical_relation_tail(edge_rep, rel_pair_idxs, num_objs, obj_preds, union_features, post_cat, rel_compress,
-                               freq_bias_weight=None, use_vision=True):
+                               freq_bias_weight=None, use_vision=True, precision=None):
     """roi_relation_predictors.py:400-469 after `edge_rep = self.post_emb(edge_ctx)`:
     pair gather -> post_cat -> * union_features -> BayesHead -> frequency bias -> hierarchical log-softmax.
     edge_rep f32 [sum N, 2*hidden]; obj_preds int [sum N]; union_features f32 [P, pooling_dim] (pooling_dim == MLP_HEAD_DIM,
@@ -196,17 +222,28 @@ def hierarchical_relation_tail(edge_rep, rel_pair_idxs, num_objs, obj_preds, uni
     hidden = edge_rep.shape[1] // 2
     pair_idx, pair_off, pair_img, num_rels = global_pair_index(rel_pair_idxs, num_objs, dev)
     n = pair_idx.shape[0]
-    prod = ops.sgb_pair_gather(edge_rep.float().contiguous(), pair_idx, hidden, split=True)       # [P, 3*2*hidden] bf16x3 layout
+    precision = precision or DEFAULT_PRECISION
+    if precision not in ("bf16x3", "bf16"):
+        raise ValueError("precision must be 'bf16x3' or 'bf16'")
     pooling = post_cat.out_features
     if use_vision and union_features.shape[1] != pooling:
         raise NotImplementedError("union_single_not_match (up_dim) is not on the config-5 path")
-    w, bias = _packed_linear(post_cat)
-    # post_cat GEMM whose epilogue applies `* union_features` and writes the bf16x3 A operand of the BayesHead GEMM directly:
-    # the f32 [P, 4096] product never goes to HBM (was: write 16 KB/pair, read it back, split, write 24 KB/pair)
-    prod3 = torch.empty(n, 3 * pooling, dtype=torch.bfloat16, device=dev)
-    ops.tc_gemm(prod, w, prod3, n, pooling, 6 * hidden, bias=bias, lda=6 * hidden, ldc=3 * pooling, epilogue=EPI_SPLIT3_BF16,
-                mul=union_features.float().contiguous() if use_vision else None, group_m=16, m_sub=1, tag="post_cat")
-    logits = rel_compress.logits_from_split(prod3)
+    w, bias = _packed_linear(post_cat, precision)
+    mul = union_features.float().contiguous() if use_vision else None
+    if precision == "bf16x3":
+        prod = ops.sgb_pair_gather(edge_rep.float().contiguous(), pair_idx, hidden, split=True)   # [P, 3*2*hidden] bf16x3 layout
+        # post_cat GEMM whose epilogue applies `* union_features` and writes the bf16x3 A operand of the BayesHead GEMM directly:
+        # the f32 [P, 4096] product never goes to HBM (was: write 16 KB/pair, read it back, split, write 24 KB/pair)
+        prod3 = torch.empty(n, 3 * pooling, dtype=torch.bfloat16, device=dev)
+        ops.tc_gemm(prod, w, prod3, n, pooling, 6 * hidden, bias=bias, lda=6 * hidden, ldc=3 * pooling, epilogue=EPI_SPLIT3_BF16,
+                    mul=mul, group_m=16, m_sub=1, tag="post_cat")
+        logits = rel_compress.logits_from_split(prod3)
+    else:
+        prod = ops.sgb_pair_gather(edge_rep.float().contiguous(), pair_idx, hidden, split=False)  # [P, 2*hidden] bf16
+        prod1 = torch.empty(n, pooling, dtype=torch.bfloat16, device=dev)
+        ops.tc_gemm(prod, w, prod1, n, pooling, 2 * hidden, bias=bias, lda=2 * hidden, ldc=pooling, epilogue=EPI_BF16, mul=mul,
+                    group_m=16, m_sub=1, tag="post_cat")
+        logits = rel_compress.logits_from_bf16(prod1)
     pair_pred = obj_preds.to(dev, torch.int32)[pair_idx.long()].contiguous() if freq_bias_weight is not None else None
     rel, sup = ops.sgb_hier_softmax(logits, rel_compress.splits(), None if freq_bias_weight is None else freq_bias_weight.float().contiguous(),
                                     NUM_OBJ_SGB, pair_pred, _label_ids(dev))

@@ -52,11 +52,27 @@ def _randint(g, lo, hi, n):
     return torch.randint(lo, hi + 1, (n,), generator=g, dtype=torch.int64)
 
 
-def make_boxes(g, n):
-    x0 = _randint(g, 0, 23, n)
-    y0 = _randint(g, 0, 23, n)
-    w = _randint(g, 4, 15, n)
-    h = _randint(g, 4, 15, n)
+BOX_MODES = ("small", "vg", "full")
+
+
+def make_boxes(g, n, mode="small"):
+    """Boxes on the 32-grid, largest first (the reference's loader sorts by area).  mode "small": SURVEY §8d's distribution (side
+    4..15, 9.8 % of the pooled conv3_1 cells shared by a pair); "vg": sides U{8..32} placed uniformly inside the grid (the wide
+    spread of Visual Genome boxes: parts next to whole-scene regions); "full": every box is the whole grid (nothing to skip)."""
+    if mode == "full":
+        return torch.tensor([[0, FEATURE_SIZE, 0, FEATURE_SIZE]] * n, dtype=torch.int32).reshape(n, 4)
+    if mode == "vg":
+        w = _randint(g, 8, FEATURE_SIZE, n)
+        h = _randint(g, 8, FEATURE_SIZE, n)
+        x0 = (torch.rand(n, generator=g) * (FEATURE_SIZE - w + 1).to(torch.float32)).to(torch.int64)
+        y0 = (torch.rand(n, generator=g) * (FEATURE_SIZE - h + 1).to(torch.float32)).to(torch.int64)
+    elif mode == "small":
+        x0 = _randint(g, 0, 23, n)
+        y0 = _randint(g, 0, 23, n)
+        w = _randint(g, 4, 15, n)
+        h = _randint(g, 4, 15, n)
+    else:
+        raise ValueError("box mode must be one of %s" % (BOX_MODES,))
     x1 = torch.clamp(x0 + w, max=FEATURE_SIZE)
     y1 = torch.clamp(y0 + h, max=FEATURE_SIZE)
     area = (x1 - x0) * (y1 - y0)
@@ -71,7 +87,7 @@ def favoured_pred(image_id, sub, obj, num_pred=tables.NUM_PRED):
     return (int(image_id) * 31 + int(sub) * 17 + int(obj) * 7 + 3) % num_pred
 
 
-def make_image(image_id, num_boxes, base_seed=0, p_rel=0.3, with_maps=True, p_fav=0.6):
+def make_image(image_id, num_boxes, base_seed=0, p_rel=0.3, with_maps=True, p_fav=0.6, box_mode="small"):
     g = _gen(base_seed, image_id)
     if with_maps:
         feat = torch.randn(NUM_IMG_FEATURE, FEATURE_SIZE, FEATURE_SIZE, generator=g)
@@ -79,7 +95,7 @@ def make_image(image_id, num_boxes, base_seed=0, p_rel=0.3, with_maps=True, p_fa
     else:
         feat = torch.zeros(0)
         depth = torch.zeros(0)
-    bbox = make_boxes(g, num_boxes)
+    bbox = make_boxes(g, num_boxes, box_mode)
     cats = _randint(g, 0, tables.NUM_OBJ - 1, num_boxes)
     s2s = tables.sub2super_table()
     supers = [torch.as_tensor([int(v) for v in s2s[int(c)] if v >= 0], dtype=torch.int64) for c in cats]
@@ -146,12 +162,12 @@ def preset_state_dict(name, seed=0, **kw):
     return head_state_dict(seed=seed, logit_gain=lg, trunk_gain=tg, **kw)
 
 
-def make_sgdet_image(image_id, num_gt, num_prop, base_seed=0, p_rel=0.3, with_maps=True):
+def make_sgdet_image(image_id, num_gt, num_prop, base_seed=0, p_rel=0.3, with_maps=True, box_mode="small"):
     """SGDET/SGCLS-shaped sample: `num_prop` float proposals; the first `num_gt` are
     jittered copies of the GT boxes with the GT label (so matches exist), the rest are random."""
-    s = make_image(image_id, num_gt, base_seed, p_rel, with_maps)
+    s = make_image(image_id, num_gt, base_seed, p_rel, with_maps, box_mode=box_mode)
     g = _gen(base_seed + 7919, image_id)
-    extra = make_boxes(g, max(num_prop - num_gt, 0)).to(torch.float32)
+    extra = make_boxes(g, max(num_prop - num_gt, 0), box_mode).to(torch.float32)
     base = torch.cat((s.bbox.to(torch.float32), extra), dim=0)[:num_prop]
     jitter = torch.rand(base.shape, generator=g)
     s.bbox_pred = torch.clamp(base + jitter, 0.0, float(FEATURE_SIZE))
@@ -205,11 +221,11 @@ def make_detr_outputs(samples, num_queries=100, base_seed=0, p_noobj=0.35, p_dup
     return logits, boxes
 
 
-def make_batch(image_ids, num_boxes, base_seed=0, p_rel=0.3, with_maps=True):
+def make_batch(image_ids, num_boxes, base_seed=0, p_rel=0.3, with_maps=True, box_mode="small"):
     """`num_boxes` may be an int or a per-image sequence (ragged batches)."""
     if isinstance(num_boxes, int):
         num_boxes = [num_boxes] * len(image_ids)
-    return [make_image(i, n, base_seed, p_rel, with_maps) for i, n in zip(image_ids, num_boxes)]
+    return [make_image(i, n, base_seed, p_rel, with_maps, box_mode=box_mode) for i, n in zip(image_ids, num_boxes)]
 
 
 # ----------------------------------------------------------------------------------------------

@@ -1,0 +1,151 @@
+"""Float parity of the DEFAULT (shared-footprint) pipeline against the fp32 oracle AT THE BENCHMARKED CONFIGURATIONS
+(VERDICT r1 weak 1/2): the exact cfg2 bench batch (64 images x 40 boxes, 99 840 directed pairs, batch skip rule), a cfg3
+bench batch (8 images x 100 proposals) and cfg5 (SGB tail, 64 x 40), each on >= 512 directed pairs drawn evenly from
+geometric strata (no shared cell / 1-2 / 3-15 / >= 16 shared cells / boxes on the image border / empty boxes) so the
+sorted-row, k_masks, multi-chunk and per-box-map machinery is what is being compared - not the repo's own dense path.
+
+Bars.  "trained" weights (round-1 trained-scale head, logit std 1.1): joint probabilities within 2e-3 ABSOLUTE of the fp32
+oracle, directly (north_star).  "sharp" weights (He-gain trunk, `pred` O(1), logit std 3.3): operand rounding to bf16 alone
+moves a probability by up to ~1e-2 in ANY bf16-in / fp32-accumulate implementation (oracle.parity.operand_rounded_scores is the
+reference formulation with only that rounding applied), so there the kernels are held to that implementation-independent model
+(within 2e-3 of it) and the distance to fp32 is recorded and bounded by the model's own distance.  Every run prints
+max |dP|, max relative log-prob error and the per-super argmax flip rate."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import parity as PA
+from oracle import sgb_oracle as SO
+from scene_graph_commonsense_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+PROB_TOL = 2e-3
+N_SAMPLE = int(os.environ.get("HC_PARITY_SAMPLE", "512"))
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _record(name, stats):
+    print("PARITY %s %s" % (name, json.dumps(stats)))
+    try:
+        os.makedirs(OUT, exist_ok=True)
+        with open(os.path.join(OUT, "parity_at_scale.jsonl"), "a") as f:
+            f.write(json.dumps(dict(case=name, **stats)) + "\n")
+    except OSError:
+        pass
+
+
+_HEADS = {}
+
+
+def _head(preset):
+    from scene_graph_commonsense_b200 import model
+    if preset not in _HEADS:
+        sd = synthetic.preset_state_dict(preset)
+        _HEADS[preset] = (sd, model.PackedHead(sd, DEV))
+    return _HEADS[preset]
+
+
+def _run_relation_case(name, samples, sgdet, preset, chunk_pairs, min_strata=4):
+    from scene_graph_commonsense_b200 import pipeline
+    sd, packed = _head(preset)
+    pipe = pipeline.RelationPipeline(packed, DEV, commonsense=True, chunk_pairs=chunk_pairs, predcls=not sgdet)   # bench defaults
+    assert pipe.fc1_shared and pipe.conv3_shared and pipe.conv3_block_rows == 4 and pipe.conv3_block_cols == 4
+    b = pipeline.host_batch_from_samples(samples, skip_mode="batch", sgdet=sgdet).to_device(DEV)
+    pairs = pipe.enumerate_pairs(b)
+    rel, sup, conn, logsig = pipe.forward_pairs(b, pairs)
+    torch.cuda.synchronize()
+    sub, obj, img = pairs["sub"].cpu().numpy(), pairs["obj"].cpu().numpy(), pairs["img"].cpu().numpy()
+    boxes = b.boxes.cpu().numpy()
+    off = b.box_offsets.cpu().numpy()
+    idx, strata = PA.stratified_pair_sample(boxes, sub, obj, N_SAMPLE, seed=1)
+    assert len(idx) >= min(N_SAMPLE, pairs["n"]) * 0.95
+    pair_list = [(int(img[p]), int(sub[p] - off[img[p]]), int(obj[p] - off[img[p]])) for p in idx]
+    rel_g = rel[torch.from_numpy(idx).to(DEV)].cpu().numpy()
+    sup_g = sup[torch.from_numpy(idx).to(DEV)].cpu().numpy()
+    torch.set_num_threads(os.cpu_count() or 8)
+    rel_ref, sup_ref, _ = PA.oracle_scores(samples, sd, pair_list, sgdet=sgdet)
+    st = PA.parity_stats(rel_g, rel_ref)
+    st["strata"] = {int(k): int((strata == k).sum()) for k in np.unique(strata)}
+    st["super_max_abs_dp"] = float(np.abs(np.exp(sup_g.astype(np.float64)) - np.exp(sup_ref.astype(np.float64))).max())
+    st["n_pairs_batch"], st["preset"] = int(pairs["n"]), preset
+    if preset == "trained":
+        _record(name, st)
+        assert len(st["strata"]) >= min_strata, st["strata"]
+        assert st["max_abs_dp"] <= PROB_TOL, st
+        assert st["super_max_abs_dp"] <= PROB_TOL, st
+        assert st["argmax_flip_rate"] <= 0.01, st
+        return
+    rel_emu, _, _ = PA.operand_rounded_scores(samples, sd, pair_list, sgdet=sgdet)
+    model_vs_fp32 = PA.parity_stats(rel_emu, rel_ref)
+    ours_vs_model = PA.parity_stats(rel_g, rel_emu)
+    st["bf16_operand_model_vs_fp32"] = {k: model_vs_fp32[k] for k in ("max_abs_dp", "mean_abs_dp", "argmax_flip_rate")}
+    st["ours_vs_bf16_operand_model"] = {k: ours_vs_model[k] for k in ("max_abs_dp", "mean_abs_dp", "argmax_flip_rate")}
+    _record(name, st)
+    assert st["top_joint_prob_median"] >= 0.35, st              # the weights really are sharp
+    assert ours_vs_model["max_abs_dp"] <= PROB_TOL, st          # our kernels == the bf16-operand model of the reference
+    assert st["max_abs_dp"] <= 1.25 * model_vs_fp32["max_abs_dp"] + 5e-4, st     # and no further from fp32 than that model is
+    assert st["argmax_flip_rate"] <= model_vs_fp32["argmax_flip_rate"] + 0.01, st
+
+
+@pytest.mark.parametrize("preset", ["trained", "sharp"])
+def test_cfg2_bench_batch_default_pipeline_vs_fp32_oracle(preset):
+    import bench
+    samples = bench.make_samples(0)                                  # the exact batch rank 0 benchmarks: 64 images x 40 boxes
+    _run_relation_case("cfg2_" + preset, samples, False, preset, bench.WORKLOADS["cfg2"]["chunk_pairs"])
+
+
+@pytest.mark.parametrize("preset", ["trained", "sharp"])
+def test_cfg3_bench_batch_default_pipeline_vs_fp32_oracle(preset):
+    import bench
+    wl = bench.WORKLOADS["cfg3"]
+    samples = bench.make_samples(0, wl["images"], wl["boxes"], sgdet=True)
+    _run_relation_case("cfg3_" + preset, samples, True, preset, wl["chunk_pairs"])
+
+
+def test_full_grid_boxes_take_the_same_path_and_match():
+    """The other end of the box-size distribution (VERDICT weak 4): every box covers most of the grid, so every cell is shared,
+    the work lists are the dense tiling and nothing is skipped."""
+    import bench
+    samples = bench.make_samples(0, 4, 24, boxes_mode="full")
+    _run_relation_case("full_boxes_trained", samples, False, "trained", 16384, min_strata=1)
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_cfg5_sgb_tail_vs_fp32_oracle_at_bench_size(precision):
+    from scene_graph_commonsense_b200 import sgb
+    n_img, n_obj = 64, 40
+    num_objs = [n_obj] * n_img
+    batch = synthetic.make_sgb_batch(num_objs, seed=0)
+    sd = synthetic.sgb_state_dict(seed=0)
+    post_cat = torch.nn.Linear(1024, 4096).to(DEV)
+    head = sgb.BayesHead(input_dim=4096).to(DEV)
+    with torch.no_grad():
+        post_cat.weight.copy_(sd["post_cat.weight"]); post_cat.bias.copy_(sd["post_cat.bias"])
+        for n in ("fc3_1", "fc3_2", "fc3_3", "fc5"):
+            getattr(head, n).weight.copy_(sd[n + ".weight"]); getattr(head, n).bias.copy_(sd[n + ".bias"])
+    edge_rep = torch.nn.functional.linear(batch["edge_ctx"], sd["post_emb.weight"], sd["post_emb.bias"])
+    pairs = SO.prepare_test_pairs(num_objs)
+    r1, r2, r3, sup = sgb.hierarchical_relation_tail(edge_rep.to(DEV), [p.to(DEV) for p in pairs], num_objs, batch["obj_labels"].to(DEV),
+                                                     batch["union_features"].to(DEV), post_cat, head, sd["freq_bias"].to(DEV),
+                                                     precision=precision)
+    rel_g = torch.cat((torch.cat(list(r1)), torch.cat(list(r2)), torch.cat(list(r3))), dim=1)
+    # 9 random pairs per image (576 in all) through the fp32 restatement of roi_relation_predictors.py:399-459
+    rng = np.random.default_rng(3)
+    per_img = n_obj * (n_obj - 1)
+    pick = [np.sort(rng.choice(per_img, size=9, replace=False)) for _ in range(n_img)]
+    sub_pairs = [pairs[i][torch.from_numpy(pick[i])] for i in range(n_img)]
+    rows = np.concatenate([pick[i] + i * per_img for i in range(n_img)])
+    o1, o2, o3, osup = SO.predictor_tail(sd, batch["edge_ctx"], sub_pairs, num_objs, batch["obj_labels"],
+                                         batch["union_features"][torch.from_numpy(rows)])
+    rel_ref = torch.cat((torch.cat(list(o1)), torch.cat(list(o2)), torch.cat(list(o3))), dim=1).numpy()
+    st = PA.parity_stats(rel_g[torch.from_numpy(rows).to(DEV)].cpu().numpy(), rel_ref)
+    st["precision"] = precision
+    _record("cfg5_" + precision, st)
+    if precision == "bf16x3":
+        assert st["max_abs_dp"] <= PROB_TOL, st
+    else:       # plain bf16 operands: recorded; must at least be a faithful bf16 GEMM (no gross error)
+        assert st["max_abs_dp"] <= 0.05 and st["argmax_flip_rate"] <= 0.05, st
