@@ -136,7 +136,8 @@ typedef struct hc_gemm_desc {
   const int32_t* n_blocks; /* CONV3_BLOCKS: device scalar, number of entries */
   int32_t block_rows;      /* CONV3_BLOCKS: 8 or 4 */
   int32_t block_cols;      /* CONV3_BLOCKS: 8 (or 0), or 4 with block_rows 4 */
-  int32_t cta_pairs;       /* CONV3_BLOCKS: 1 = clusters of 2 CTAs on two M tiles of one N tile share each weight tile by TMA multicast */
+  int32_t cta_pairs;       /* CONV3_BLOCKS: 1 = tcgen05 cta_group::2 - clusters of 2 CTAs on two M tiles of one N tile, UMMA M = 256
+                              across the pair, each CTA stages half of every weight tile (same K order: bit-identical results) */
   const uint64_t* k_masks; /* PLAIN: per CTA M tile, bitmap of visited K cells (NULL = dense) */
   int64_t k_cell;          /* PLAIN + k_masks: K elements per cell (multiple of 64, K / k_cell <= 64) */
   const float* add_a;      /* EPI_BF16 row gathers, both or neither */

@@ -6,12 +6,15 @@
 namespace hc {
 thread_local char g_last_error[512] = {0};
 
-static int g_checked_device = -1;
-static int g_check_result = HC_E_ARCH;
-static int g_num_sms = 0;
+static int g_check_result[HC_MAX_DEVICES];      // 0 = not checked yet, 1 = sm_100, 2 = other architecture
+static int g_sms[HC_MAX_DEVICES];
 static std::mutex g_mu;
 
-int num_sms() { return g_num_sms > 0 ? g_num_sms : 148; }
+// SM count of the CURRENT device (grid sizing of the persistent kernels); 148 before the first hc_device_check on it
+int num_sms() {
+  const int dev = current_device();
+  return (dev >= 0 && dev < HC_MAX_DEVICES && g_sms[dev] > 0) ? g_sms[dev] : 148;
+}
 }  // namespace hc
 
 using namespace hc;
@@ -20,25 +23,17 @@ extern "C" const char* hc_last_error(void) { return g_last_error; }
 extern "C" int hc_abi_version(void) { return HC_ABI_VERSION; }
 
 extern "C" int hc_device_check(void) {
-  int dev = -1;
-  if (cudaGetDevice(&dev) != cudaSuccess) {
-    cudaGetLastError();
-    return fail(HC_E_CUDA, "hc_device_check: no CUDA device (this library has no CPU fallback)");
-  }
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (dev == g_checked_device) {
-      if (g_check_result != HC_OK) fail(g_check_result, "hc_device_check: device is not sm_100 (compute capability 10.x required)");
-      return g_check_result;
-    }
+  const int dev = current_device();
+  if (dev < 0 || dev >= HC_MAX_DEVICES) return fail(HC_E_CUDA, "hc_device_check: no CUDA device (this library has no CPU fallback)");
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_check_result[dev] == 0) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return cuda_status("cudaGetDeviceProperties");
-    g_checked_device = dev;
-    g_num_sms = prop.multiProcessorCount;
-    g_check_result = (prop.major == 10) ? HC_OK : HC_E_ARCH;
-    if (g_check_result != HC_OK) fail(HC_E_ARCH, "hc_device_check: device is not sm_100 (compute capability 10.x required)");
-    return g_check_result;
+    g_sms[dev] = prop.multiProcessorCount;
+    g_check_result[dev] = (prop.major == 10) ? 1 : 2;
   }
+  if (g_check_result[dev] != 1) return fail(HC_E_ARCH, "hc_device_check: device is not sm_100 (compute capability 10.x required)");
+  return HC_OK;
 }
 
 extern "C" int hc_cs_bitmap_build(const int64_t* aligned_keys, int64_t n_aligned, const int64_t* violated_keys, int64_t n_violated,

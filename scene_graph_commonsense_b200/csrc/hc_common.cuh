@@ -36,6 +36,16 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 int num_sms();
 
+// Per-device opt-ins (cudaFuncSetAttribute for > 48 KB of dynamic shared memory) are keyed on the current device: the attribute
+// belongs to the device's context, so a process that uses a second GPU has to set it there too.  One process per GPU is the
+// supported deployment; this only keeps a multi-device process from failing with an invalid-argument launch.
+constexpr int HC_MAX_DEVICES = 64;
+inline int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return dev;
+}
+
 // ---- device helpers -----------------------------------------------------------------------------------
 // Python slice-bound semantics of `mask[int(lo):int(hi)]` on an axis of length `size`
 // (evaluate.py:115, evaluator.py:86): a negative bound wraps once, then both clamp to [0,size].

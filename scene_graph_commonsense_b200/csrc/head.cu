@@ -315,12 +315,14 @@ extern "C" int hc_hier_head(const float* fc2_raw, int64_t ld_raw, int32_t n_rows
   if (grid > num_sms()) grid = num_sms();
   const int n_out = flat ? n_geo + n_pos + n_sem + 1 : n_geo + n_pos + n_sem + 4;
   const size_t smem = ((size_t)n_out * hidden + (size_t)(HEAD_THREADS / 32) * HEAD_RB * HEAD_MAX_OUT) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[HC_MAX_DEVICES] = {};
+  const int cfg_dev = current_device();
+  if (cfg_dev < 0 || cfg_dev >= HC_MAX_DEVICES) return fail(HC_E_CUDA, "device index out of range");
+  if (!configured[cfg_dev]) {
     if (cudaFuncSetAttribute(hier_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)((HEAD_MAX_OUT * 128 * HEAD_HV + (HEAD_THREADS / 32) * HEAD_RB * HEAD_MAX_OUT) * sizeof(float))) != cudaSuccess)
       return cuda_status("cudaFuncSetAttribute(hier_head_kernel)");
-    configured = true;
+    configured[cfg_dev] = true;
   }
   hier_head_kernel<<<grid, HEAD_THREADS, smem, stream>>>(fc2_raw, ld_raw, n_rows, fc2_bias, emb, num_obj, num_super, row_sub, row_obj, box_cat,
                                              box_super, w_heads, b_heads, n_geo, n_pos, n_sem, flat, 1.0f / t1, 1.0f / t2, 1.0f / t3,

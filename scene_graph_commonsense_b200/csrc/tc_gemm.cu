@@ -40,6 +40,11 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = MS * A_SUB_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  // cta_group::2 pairs (block mode): each CTA of a pair stages its own A rows and HALF of every weight tile; the tensor cores of
+  // both SMs read the other half from the peer's shared memory, so a stage costs MS*16 KB + B_BYTES/2 of L2->SM delivery per SM
+  static constexpr int CG2_STAGE_BYTES = MS * A_SUB_BYTES + B_BYTES / 2;
+  static constexpr int CG2_STAGES = (200 * 1024) / CG2_STAGE_BYTES > 6 ? 6 : (200 * 1024) / CG2_STAGE_BYTES;
+  static constexpr int MAX_STAGES = 6;                 // barrier slots (the ring depth is a run-time choice: STAGES or CG2_STAGES)
   static constexpr int ACC_COLS = MS * BN;
   static constexpr int ACC_STAGES = TMEM_COLS / ACC_COLS;
   // implicit-conv "patch" pipeline: one A patch (8*MS+2 pixel rows x 16 pixels x 64 channels) per (channel block, kx) serves
@@ -49,8 +54,9 @@ struct Cfg {
   static constexpr int PA_SLOTS = 3;
   static constexpr int PB_SLOTS = 3;
   static constexpr int PATCH_DATA_BYTES = PA_SLOTS * A_PATCH_BYTES + PB_SLOTS * B_BYTES;
-  static constexpr int DATA_BYTES = STAGES * STAGE_BYTES > PATCH_DATA_BYTES ? STAGES * STAGE_BYTES : PATCH_DATA_BYTES;
-  static constexpr int BAR_BYTES = (2 * STAGES + 2 * ACC_STAGES + 2 * PA_SLOTS + 2 * PB_SLOTS) * 8 + 16;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES > CG2_STAGES * CG2_STAGE_BYTES ? STAGES * STAGE_BYTES : CG2_STAGES * CG2_STAGE_BYTES;
+  static constexpr int DATA_BYTES = RING_BYTES > PATCH_DATA_BYTES ? RING_BYTES : PATCH_DATA_BYTES;
+  static constexpr int BAR_BYTES = (2 * MAX_STAGES + 2 * ACC_STAGES + 2 * PA_SLOTS + 2 * PB_SLOTS) * 8 + 16;
   static constexpr int SMEM_BYTES = DATA_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
   static_assert(A_PATCH_BYTES % 1024 == 0 && SMEM_BYTES <= 227 * 1024, "patch pipeline does not fit");
   static_assert(STAGES >= 2, "pipeline too shallow");
@@ -74,7 +80,8 @@ struct Params {
   const int* n_blocks;           // device scalar: entries in the work list
   int blk_h;                     // pixel rows per block (8 or 4)
   int blk_w;                     // pixel columns per block (8 or 4)
-  int cl2;                       // block mode: CTA pairs (cluster of 2) on two M tiles of one N tile share the weight tile by TMA multicast
+  int cl2;                       // block mode: tcgen05 cta_group::2 - CTA pairs (cluster of 2) on two M tiles of one N tile, UMMA M = 256,
+                                 // each CTA stages half of every weight tile
   // K-cell-sparse plain GEMM: bit c of k_masks[CTA m tile] set = K blocks [c*k_cell_kb, (c+1)*k_cell_kb) are visited
   const unsigned long long* k_masks;
   int k_cell_kb;
@@ -123,12 +130,24 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// half of a B tile to BOTH CTAs of the pair: lands at the same offset in each CTA's shared memory, complete_tx on each CTA's barrier
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+// cta_group::2 loads: the data lands in THIS CTA's shared memory, the byte count is credited to the barrier `bar`, which may live in
+// the peer CTA (shared::cluster address) - both CTAs of a pair report to the leader's full barrier
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;      // shared::cluster address of the same offset in the EVEN CTA of the pair
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
-      "l"(tmap), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// arrive on a barrier that may live in the peer CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -158,10 +177,10 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=BN
+// cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128 (256 across a cta_group::2 pair), N=BN
 template <int BN>
-__device__ __forceinline__ uint32_t umma_idesc() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc(int m = BM) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -174,9 +193,21 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-// the same arrival on the barrier at this offset in every CTA of `mask` (frees a pipeline slot that a peer's multicast writes into)
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+// cta_group::2: issued by the leader CTA only; A rows 0-127 / 128-255 and the two halves of B come from the shared memory of the
+// even / odd CTA at the SAME offsets, the accumulator rows go to the same TMEM address in each CTA
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// arrives on the barrier at this offset in every CTA of `mask` once the pair's MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
 }
 // arrives on the mbarrier once every previously issued tcgen05.mma of this thread has completed
@@ -261,10 +292,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B atoms need 1024-byte alignment
   const uint32_t bar_base = smem_base + C::DATA_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + C::ACC_STAGES + s); };
-  constexpr int PBAR0 = 2 * C::STAGES + 2 * C::ACC_STAGES;
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::MAX_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::MAX_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::MAX_STAGES + C::ACC_STAGES + s); };
+  constexpr int PBAR0 = 2 * C::MAX_STAGES + 2 * C::ACC_STAGES;
   auto pa_full = [&](int s) { return bar_base + 8u * (PBAR0 + s); };
   auto pa_empty = [&](int s) { return bar_base + 8u * (PBAR0 + C::PA_SLOTS + s); };
   auto pb_full = [&](int s) { return bar_base + 8u * (PBAR0 + 2 * C::PA_SLOTS + s); };
@@ -280,27 +311,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int blk_per_sub = blk_mode ? BM / (p.blk_w * p.blk_h) : 1;  // blocks per 128-row sub-tile (2, 4 or 8)
   const int n_blocks = blk_mode ? __ldg(p.n_blocks) : 0;
   const int tiles_m = blk_mode ? (n_blocks + MS * blk_per_sub - 1) / (MS * blk_per_sub) : p.tiles_m;
-  // CTA pairs (p.cl2): both CTAs walk the same sequence of pair tiles, so their pipelines run in lock step
+  // CTA pairs (p.cl2, tcgen05 cta_group::2): both CTAs walk the same sequence of pair tiles; the even CTA (leader) issues the MMAs
   const int rank = p.cl2 ? (int)cluster_ctarank() : 0;
+  const int n_stages = p.cl2 ? C::CG2_STAGES : C::STAGES;
+  const uint32_t stage_bytes = p.cl2 ? (uint32_t)C::CG2_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
   const int num_tiles = p.cl2 ? ((tiles_m + 1) / 2) * p.tiles_n : tiles_m * p.tiles_n;
   const int tile0 = p.cl2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = p.cl2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int num_kb = p.K / BK;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), p.cl2 ? 2 : 1); }   // pair: both MMA warps free a slot
-    for (int s = 0; s < C::ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < C::MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    // pair: the leader's accumulator-empty barrier collects the epilogue warps of BOTH CTAs
+    for (int s = 0; s < C::ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), p.cl2 ? 8 : 4); }
     for (int s = 0; s < C::PA_SLOTS; ++s) { mbar_init(pa_full(s), 1); mbar_init(pa_empty(s), 1); }
     for (int s = 0; s < C::PB_SLOTS; ++s) { mbar_init(pb_full(s), 1); mbar_init(pb_empty(s), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (p.cl2) {      // the same warp of both CTAs of the pair
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cl2) cluster_sync_all();          // the peer's barriers exist before any multicast / remote arrive can reach them
+  if (p.cl2) cluster_sync_all();          // the peer's barriers and TMEM allocation exist before any remote arrive / pair MMA reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -350,22 +389,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int cb = 0; cb < cblks; ++cb) {
           for (int kx = 0; kx < 3; ++kx) {
             for (int ky = 0; ky < 3; ++ky) {
-              const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+              const uint32_t a_dst = smem_base + stage * stage_bytes;
               if (lane == 0) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
-                mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                // pair: the LEADER's full barrier counts the bytes of both CTAs (the peer only sends bytes, it never arrives)
+                if (!p.cl2) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                else if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * C::CG2_STAGE_BYTES);
               }
               __syncwarp();
-              if (lane < nblk)
+              if (p.cl2) {
+                const uint32_t lead_full = full_bar(stage) & PEER_BIT_MASK;
+                if (lane < nblk)
+                  tma_load_4d_cg2(a_dst + lane * blk_bytes, &tmap_a, lead_full, p.c_base + cb * BK, ex + kx, ey + ky, eimg);
+                else if (lane == 31)     // this CTA's half of the weight tile: rows [rank * BN/2, +BN/2) of the N tile
+                  tma_load_2d_cg2(a_dst + MS * A_SUB_BYTES, &tmap_bh, lead_full, ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN + rank * (BN / 2));
+              } else if (lane < nblk) {
                 tma_load_4d(a_dst + lane * blk_bytes, &tmap_a, full_bar(stage), p.c_base + cb * BK, ex + kx, ey + ky, eimg);
-              else if (lane == 31) {
-                if (p.cl2)     // this CTA fetches its half of the weight tile for both CTAs of the pair
-                  tma_load_2d_mc(a_dst + MS * A_SUB_BYTES + (uint32_t)rank * (C::B_BYTES / 2), &tmap_bh, full_bar(stage),
-                                 ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN + rank * (BN / 2), (uint16_t)3);
-                else
-                  tma_load_2d(a_dst + MS * A_SUB_BYTES, &tmap_b, full_bar(stage), ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN);
+              } else if (lane == 31) {
+                tma_load_2d(a_dst + MS * A_SUB_BYTES, &tmap_b, full_bar(stage), ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN);
               }
-              if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+              if (++stage == n_stages) { stage = 0; phase ^= 1u; }
             }
           }
         }
@@ -378,14 +421,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
         auto load_kb = [&](int kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t a_dst = smem_base + stage * stage_bytes;
           const uint32_t b_dst = a_dst + MS * A_SUB_BYTES;
           mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
 #pragma unroll
           for (int j = 0; j < MS; ++j)
             tma_load_2d(a_dst + j * A_SUB_BYTES, &tmap_a, full_bar(stage), kb * BK, (m_blk * MS + j) * BM);
           tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         };
         if (p.k_masks) {
           // K-cell-sparse: only the K cells some row of this M tile is non-zero in (ascending cell order)
@@ -436,31 +479,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         }
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
-    } else if (lane == 0) {
-      const uint32_t idesc = umma_idesc<BN>();
+    } else if (lane == 0 && rank == 0) {               // pair: only the leader CTA issues (its MMAs run on both SMs)
+      const uint32_t idesc = umma_idesc<BN>(p.cl2 ? 2 * BM : BM);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue has drained this accumulator stage
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue (of both CTAs of a pair) has drained this accumulator stage
         tc_fence_after();
         uint32_t started = 0;                             // 0 until the first MMA of the tile (which overwrites the accumulator)
         auto mma_kb = [&]() {
           mbar_wait(full_bar(stage), phase);              // TMA bytes of this stage have landed
           tc_fence_after();
-          const uint32_t a_src = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t a_src = smem_base + stage * stage_bytes;
           const uint64_t bdesc = umma_desc_sw128(a_src + MS * A_SUB_BYTES);
 #pragma unroll
           for (int j = 0; j < MS; ++j) {
             const uint64_t adesc = umma_desc_sw128(a_src + j * A_SUB_BYTES);
             const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_COLS + j * BN);
+            if (p.cl2) {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)         // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
-              umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (started | k) ? 1u : 0u);
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16_cg2(d, adesc + 2u * k, bdesc + 2u * k, idesc, (started | k) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)       // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
+                umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (started | k) ? 1u : 0u);
+            }
           }
           started = 1;
-          if (p.cl2) umma_commit_mc(empty_bar(stage), (uint16_t)3);   // the slot is written by both CTAs' multicasts: free it in both
+          if (p.cl2) umma_commit_cg2(empty_bar(stage), (uint16_t)3);  // the slot of BOTH CTAs is free once the pair's MMAs retire
           else umma_commit(empty_bar(stage));             // smem slot free once these MMAs retire
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         };
         if (p.k_masks) {
           int m_blk, n_blk;
@@ -471,7 +520,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int kb = 0; kb < num_kb; ++kb) mma_kb();
         }
         // accumulator complete once the MMAs above retire; an empty cell mask issued none: plain arrive, the epilogue substitutes zeros
-        if (started) umma_commit(tfull_bar(acc));
+        if (p.cl2) umma_commit_cg2(tfull_bar(acc), (uint16_t)3);     // both CTAs' epilogues (block mode always issues MMAs)
+        else if (started) umma_commit(tfull_bar(acc));
         else mbar_arrive(tfull_bar(acc));
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
@@ -681,16 +731,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (p.cl2) mbar_arrive_cluster(tempty_bar(acc) & PEER_BIT_MASK);    // the leader's barrier (a remote arrive for the odd CTA)
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.cl2) cluster_sync_all();          // no CTA leaves while its peer can still multicast into it or arrive on its barriers
+  if (p.cl2) cluster_sync_all();          // no CTA leaves (or frees TMEM) while the pair's MMAs / remote arrives can still reach it
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (p.cl2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -729,11 +783,14 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
 template <int BN, int MS>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const Params& p, cudaStream_t stream) {
   using C = Cfg<BN, MS>;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in is per device (context): keyed on the current device, so a process that touches a second GPU configures it too
+  static bool configured[HC_MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= HC_MAX_DEVICES) return fail(HC_E_CUDA, "tc_gemm: device index out of range");
+  if (!configured[dev]) {
     if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
       return cuda_status("cudaFuncSetAttribute(tc_gemm_kernel)");
-    configured = true;
+    configured[dev] = true;
   }
   int tiles = p.tiles_m * p.tiles_n;
   int grid = (p.mode == HC_GEMM_CONV3_BLOCKS || tiles >= num_sms()) ? num_sms() : tiles;   // block mode: tile count lives on the device
@@ -864,7 +921,8 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   if (blk) p.group_m = 1;                 // the 4 N tiles of an M tile run side by side and share its blocks through L2
   else if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
 
-  // block mode: CTA pairs sharing the weight tile by TMA multicast (d->cta_pairs; HC_CONV3_PAIRS=0/1 overrides for A/B runs)
+  // block mode: tcgen05 cta_group::2 CTA pairs (d->cta_pairs; HC_CONV3_PAIRS=0/1 overrides for A/B runs); needs m_sub * N tile == 512
+  // TMEM columns per CTA or fewer, which every configuration satisfies
   if (blk) {
     static int env_pairs = -2;
     if (env_pairs == -2) { const char* e = getenv("HC_CONV3_PAIRS"); env_pairs = e ? atoi(e) : -1; }

@@ -360,12 +360,14 @@ extern "C" int hc_hier_head_bwd(const float* d_logits, int32_t ld_dl, const floa
   int rc = hc_device_check();
   if (rc != HC_OK) return rc;
   if (d_pred) {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[HC_MAX_DEVICES] = {};
+  const int cfg_dev = current_device();
+  if (cfg_dev < 0 || cfg_dev >= HC_MAX_DEVICES) return fail(HC_E_CUDA, "device index out of range");
+    if (!configured[cfg_dev]) {
       if (cudaFuncSetAttribute(head_bwd_dpred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)(TR_MAX_OUT * TR_HIDDEN * sizeof(float))) != cudaSuccess)
         return cuda_status("cudaFuncSetAttribute(head_bwd_dpred_kernel)");
-      configured = true;
+      configured[cfg_dev] = true;
     }
     const int rows_per_cta = (BWD_THREADS / 32) * BWD_RB;
     int grid = (n_rows + rows_per_cta - 1) / rows_per_cta;

@@ -242,10 +242,14 @@ def test_hier_head_kernel_matches_torch_fp32():
     rel, sup, conn, logsig, pred = ops.hier_head(c(raw), c(sd["fc2.bias"]), c(emb), c(row_sub, torch.int32), c(row_obj, torch.int32),
                                                  c(cats, torch.int32), c(supers, torch.int8), c(w), c(bh), (15, 11, 24), want_pred=True)
     x = raw + sd["fc2.bias"] + emb[cats[row_sub]] + emb[150 + cats[row_obj]]
+    # utils.py:136-149: the first entry of a box's super-class list plus the LAST entry of a 2..4-entry list (never the middle ones)
+    n_sup = (supers >= 0).sum(1)
+    assert int((n_sup == 3).sum()) > 0
     for k in range(4):
         for role, rows, base in ((0, row_sub, 300), (1, row_obj, 317)):
             sv = supers[rows][:, k].long()
-            x = x + torch.where((sv >= 0)[:, None], emb[(base + sv.clamp(min=0))], torch.zeros(1, 512))
+            used = (sv >= 0) & ((k == 0) | (n_sup[rows] - 1 == k))
+            x = x + torch.where(used[:, None], emb[(base + sv.clamp(min=0))], torch.zeros(1, 512))
     p = torch.relu(x)
     r1, r2, r3, s_ref, c_ref = O.hier_head(sd, p)
     np.testing.assert_allclose(pred.cpu().numpy(), p.numpy(), atol=1e-5, rtol=1e-5)
