@@ -283,7 +283,9 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tiles_m, int ti
 }
 
 // =============================================================================================== kernel
-template <int BN, int MS>
+// CG2 = tcgen05 cta_group::2 CTA pairs.  A separate instantiation: a kernel that contains 2-CTA instructions can only be launched
+// with an even cluster dimension, so the single-CTA variants must not contain any.
+template <int BN, int MS, bool CG2>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_bh, const Params p) {
@@ -311,25 +313,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int blk_per_sub = blk_mode ? BM / (p.blk_w * p.blk_h) : 1;  // blocks per 128-row sub-tile (2, 4 or 8)
   const int n_blocks = blk_mode ? __ldg(p.n_blocks) : 0;
   const int tiles_m = blk_mode ? (n_blocks + MS * blk_per_sub - 1) / (MS * blk_per_sub) : p.tiles_m;
-  // CTA pairs (p.cl2, tcgen05 cta_group::2): both CTAs walk the same sequence of pair tiles; the even CTA (leader) issues the MMAs
-  const int rank = p.cl2 ? (int)cluster_ctarank() : 0;
-  const int n_stages = p.cl2 ? C::CG2_STAGES : C::STAGES;
-  const uint32_t stage_bytes = p.cl2 ? (uint32_t)C::CG2_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
-  const int num_tiles = p.cl2 ? ((tiles_m + 1) / 2) * p.tiles_n : tiles_m * p.tiles_n;
-  const int tile0 = p.cl2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = p.cl2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  // CTA pairs (CG2, tcgen05 cta_group::2): both CTAs walk the same sequence of pair tiles; the even CTA (leader) issues the MMAs
+  const int rank = CG2 ? (int)cluster_ctarank() : 0;
+  const int n_stages = CG2 ? C::CG2_STAGES : C::STAGES;
+  const uint32_t stage_bytes = CG2 ? (uint32_t)C::CG2_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
+  const int num_tiles = CG2 ? ((tiles_m + 1) / 2) * p.tiles_n : tiles_m * p.tiles_n;
+  const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int num_kb = p.K / BK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     // pair: the leader's accumulator-empty barrier collects the epilogue warps of BOTH CTAs
-    for (int s = 0; s < C::ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), p.cl2 ? 8 : 4); }
+    for (int s = 0; s < C::ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG2 ? 8 : 4); }
     for (int s = 0; s < C::PA_SLOTS; ++s) { mbar_init(pa_full(s), 1); mbar_init(pa_empty(s), 1); }
     for (int s = 0; s < C::PB_SLOTS; ++s) { mbar_init(pb_full(s), 1); mbar_init(pb_empty(s), 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    if (p.cl2) {      // the same warp of both CTAs of the pair
+    if constexpr (CG2) {      // the same warp of both CTAs of the pair
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
@@ -339,13 +341,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cl2) cluster_sync_all();          // the peer's barriers and TMEM allocation exist before any remote arrive / pair MMA reaches them
+  if constexpr (CG2) cluster_sync_all();          // the peer's barriers and TMEM allocation exist before any remote arrive / pair MMA reaches them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0 && p.patch) {
+    if (!CG2 && lane == 0 && p.patch) {      // (pair kernels are block-mode only: every tcgen05 op of a kernel uses one cta_group)
       int a_slot = 0, b_slot = 0;
       uint32_t a_phase = 0, b_phase = 0;
       const int cblks = p.c_in / BK;
@@ -393,11 +395,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (lane == 0) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 // pair: the LEADER's full barrier counts the bytes of both CTAs (the peer only sends bytes, it never arrives)
-                if (!p.cl2) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                if (!CG2) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
                 else if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * C::CG2_STAGE_BYTES);
               }
               __syncwarp();
-              if (p.cl2) {
+              if constexpr (CG2) {
                 const uint32_t lead_full = full_bar(stage) & PEER_BIT_MASK;
                 if (lane < nblk)
                   tma_load_4d_cg2(a_dst + lane * blk_bytes, &tmap_a, lead_full, p.c_base + cb * BK, ex + kx, ey + ky, eimg);
@@ -413,7 +415,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
-    } else if (lane == 0) {
+    } else if (!CG2 && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -444,7 +446,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0 && p.patch) {
+    if (!CG2 && lane == 0 && p.patch) {      // (pair kernels are block-mode only: every tcgen05 op of a kernel uses one cta_group)
       const uint32_t idesc = umma_idesc<BN>();
       int a_slot = 0, b_slot = 0, acc = 0;
       uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
@@ -480,7 +482,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     } else if (lane == 0 && rank == 0) {               // pair: only the leader CTA issues (its MMAs run on both SMs)
-      const uint32_t idesc = umma_idesc<BN>(p.cl2 ? 2 * BM : BM);
+      const uint32_t idesc = umma_idesc<BN>(CG2 ? 2 * BM : BM);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -496,7 +498,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int j = 0; j < MS; ++j) {
             const uint64_t adesc = umma_desc_sw128(a_src + j * A_SUB_BYTES);
             const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_COLS + j * BN);
-            if (p.cl2) {
+            if constexpr (CG2) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
                 umma_bf16_cg2(d, adesc + 2u * k, bdesc + 2u * k, idesc, (started | k) ? 1u : 0u);
@@ -507,7 +509,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             }
           }
           started = 1;
-          if (p.cl2) umma_commit_cg2(empty_bar(stage), (uint16_t)3);  // the slot of BOTH CTAs is free once the pair's MMAs retire
+          if constexpr (CG2) umma_commit_cg2(empty_bar(stage), (uint16_t)3);  // the slot of BOTH CTAs is free once the pair's MMAs retire
           else umma_commit(empty_bar(stage));             // smem slot free once these MMAs retire
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         };
@@ -520,7 +522,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int kb = 0; kb < num_kb; ++kb) mma_kb();
         }
         // accumulator complete once the MMAs above retire; an empty cell mask issued none: plain arrive, the epilogue substitutes zeros
-        if (p.cl2) umma_commit_cg2(tfull_bar(acc), (uint16_t)3);     // both CTAs' epilogues (block mode always issues MMAs)
+        if constexpr (CG2) umma_commit_cg2(tfull_bar(acc), (uint16_t)3);     // both CTAs' epilogues (block mode always issues MMAs)
         else if (started) umma_commit(tfull_bar(acc));
         else mbar_arrive(tfull_bar(acc));
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
@@ -732,7 +734,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (p.cl2) mbar_arrive_cluster(tempty_bar(acc) & PEER_BIT_MASK);    // the leader's barrier (a remote arrive for the odd CTA)
+        if constexpr (CG2) mbar_arrive_cluster(tempty_bar(acc) & PEER_BIT_MASK);    // the leader's barrier (a remote arrive for the odd CTA)
         else mbar_arrive(tempty_bar(acc));
       }
       if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
@@ -741,9 +743,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if (p.cl2) cluster_sync_all();          // no CTA leaves (or frees TMEM) while the pair's MMAs / remote arrives can still reach it
+  if constexpr (CG2) cluster_sync_all();          // no CTA leaves (or frees TMEM) while the pair's MMAs / remote arrives can still reach it
   if (warp == 1) {
-    if (p.cl2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if constexpr (CG2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
@@ -780,7 +782,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   return HC_OK;
 }
 
-template <int BN, int MS>
+template <int BN, int MS, bool CG2>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tbh, const Params& p, cudaStream_t stream) {
   using C = Cfg<BN, MS>;
   // the opt-in is per device (context): keyed on the current device, so a process that touches a second GPU configures it too
@@ -788,13 +790,13 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   const int dev = current_device();
   if (dev < 0 || dev >= HC_MAX_DEVICES) return fail(HC_E_CUDA, "tc_gemm: device index out of range");
   if (!configured[dev]) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_gemm_kernel<BN, MS, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES) != cudaSuccess)
       return cuda_status("cudaFuncSetAttribute(tc_gemm_kernel)");
     configured[dev] = true;
   }
   int tiles = p.tiles_m * p.tiles_n;
   int grid = (p.mode == HC_GEMM_CONV3_BLOCKS || tiles >= num_sms()) ? num_sms() : tiles;   // block mode: tile count lives on the device
-  if (p.cl2) {
+  if (CG2) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(grid & ~1));
@@ -806,10 +808,10 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MS>, ta, tb, tbh, p) != cudaSuccess) return cuda_status("tc_gemm_kernel cluster launch");
+    if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<BN, MS, CG2>, ta, tb, tbh, p) != cudaSuccess) return cuda_status("tc_gemm_kernel cluster launch");
     return cuda_status("tc_gemm_kernel cluster launch");
   }
-  tc_gemm_kernel<BN, MS><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tb, p);
+  tc_gemm_kernel<BN, MS, CG2><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, tb, p);
   return cuda_status("tc_gemm_kernel launch");
 }
 
@@ -928,8 +930,13 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     if (env_pairs == -2) { const char* e = getenv("HC_CONV3_PAIRS"); env_pairs = e ? atoi(e) : -1; }
     p.cl2 = (env_pairs >= 0 ? env_pairs : d->cta_pairs) ? 1 : 0;
   }
-  if (BN == 256 && MS == 1) return tc::launch<256, 1>(ta, tb, tbh, p, stream);
-  if (BN == 256 && MS == 2) return tc::launch<256, 2>(ta, tb, tbh, p, stream);
-  if (BN == 128 && MS == 1) return tc::launch<128, 1>(ta, tb, tbh, p, stream);
-  return tc::launch<128, 2>(ta, tb, tbh, p, stream);
+  if (p.cl2) {                            // pairs are built for the conv3_1 shape only (256-wide N tiles)
+    HC_REQUIRE(BN == 256, HC_E_SHAPE, "hc_tc_gemm: cta_pairs needs N to be a multiple of 256");
+    if (MS == 1) return tc::launch<256, 1, true>(ta, tb, tbh, p, stream);
+    return tc::launch<256, 2, true>(ta, tb, tbh, p, stream);
+  }
+  if (BN == 256 && MS == 1) return tc::launch<256, 1, false>(ta, tb, tbh, p, stream);
+  if (BN == 256 && MS == 2) return tc::launch<256, 2, false>(ta, tb, tbh, p, stream);
+  if (BN == 128 && MS == 1) return tc::launch<128, 1, false>(ta, tb, tbh, p, stream);
+  return tc::launch<128, 2, false>(ta, tb, tbh, p, stream);
 }
