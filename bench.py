@@ -190,9 +190,11 @@ def run_ours(args):
     batch = host.to_device(dev)
     torch.cuda.synchronize()
 
+    global_counters = torch.zeros_like(pipe.counters)
+
     def step_resident():
         n = pipe.step(batch)
-        hdist.allreduce_counters(pipe.counters)
+        hdist.allreduce_counters(pipe.counters, out=global_counters)      # one int64[765] all-reduce per step (C ABI / NCCL)
         return n
 
     def steps_e2e(k):
@@ -200,7 +202,7 @@ def run_ours(args):
         region (window i+1's copy is issued while window i computes), counters read back to the host after every window."""
         out = None
         for out in pipe.run((host for _ in range(k)), before_step=lambda p: p.reset(),
-                            after_step=lambda p: hdist.allreduce_counters(p.counters)):
+                            after_step=lambda p: hdist.allreduce_counters(p.counters, out=global_counters)):
             pass
         return out
 
@@ -234,7 +236,7 @@ def run_ours(args):
     t_max = hdist.max_over_ranks(t_dev, dev)
     pairs_total = hdist.sum_over_ranks(pairs_step, dev)
     value = pairs_total * args.steps / t_max
-    counters_final = pipe.counters.cpu().numpy().copy()
+    counters_final = pipe.counters.cpu().numpy().copy()                 # rank 0's own images (the recall line of the JSON)
     # block-sparse conv3_1: work-list lengths of the last step (read back AFTER the timed region)
     blocks_step = int(pipe.last_n_blocks.sum().item()) if pipe.conv3_block_rows and pipe.last_n_blocks is not None else None
 

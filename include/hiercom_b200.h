@@ -469,6 +469,38 @@ int hc_hier_head_bwd(const float* d_logits, int32_t ld_dl, const float* pred, in
                      const float* w_heads, const float* scale, float* d_pred, float* d_w, float* d_b, float* ws,
                      int32_t parts, hc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * R12 across ranks (SURVEY §8b "counts_allreduce", §8e): ONE ncclAllReduce(sum, int64) of the counter vector
+ * (765 slots: Evaluator {hits[3], hits_pc[3x50], n_gt, n_gt_pc[50]} x {normal, zero-shot} + Evaluator_Top3), in place, on
+ * `stream`.  nccl_comm is an ncclComm_t of the caller's NCCL (bound with dlopen at first use: no link-time dependency).
+ * Counters are CUMULATIVE: reduce a window's delta (or reset before the window), never the same totals twice.
+ * The reference has no cross-rank reduction (every rank writes its own JSON, utils.py:486).
+ * hc_nccl_unique_id / hc_nccl_comm_create / hc_nccl_comm_destroy wrap ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy
+ * for hosts that do not link NCCL themselves (one communicator per process, one process per GPU). */
+typedef struct HcNcclId { char internal[128]; } HcNcclId;
+int hc_counts_allreduce(void* nccl_comm, int64_t* counters, int64_t n, hc_stream_t stream);
+int hc_nccl_unique_id(HcNcclId* id_out);
+int hc_nccl_comm_create(const HcNcclId* id, int32_t n_ranks, int32_t rank, void** comm_out);
+int hc_nccl_comm_destroy(void* comm);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Sizing queries (SURVEY §8b "Ownership"): the caller owns every allocation, kernels never allocate.  Host functions,
+ * no GPU needed.  Return bytes / entries (>= 0) or a negative status.
+ *   hc_pairs_enumerate_workspace_bytes : ws_ov / ws_any / ws_counts of hc_pairs_enumerate (sum_tri = sum_i N_i(N_i-1)/2)
+ *   hc_conv3_blocks_capacity           : int32 entries of a conv3_1 work list for n_pairs directed pairs
+ *   hc_conv2_box_blocks_capacity       : int32 entries of the conv2_1 box-footprint work list
+ *   hc_relation_workspace_bytes        : every device buffer of the batched relation path for one window */
+int64_t hc_pairs_enumerate_workspace_bytes(int64_t sum_tri, int32_t n_images, int32_t n_groups, int32_t max_tri,
+                                           int64_t* ws_ov_bytes, int64_t* ws_any_bytes, int64_t* ws_counts_bytes);
+int64_t hc_conv3_blocks_capacity(int64_t n_pairs, int32_t block_rows, int32_t block_cols);
+int64_t hc_conv2_box_blocks_capacity(int64_t n_box, int32_t block_rows);
+typedef struct hc_relation_workspace {
+  int64_t pixels_packed, conv1_out, box_select, conv2_halves, pooled_conv2, work_lists, box_maps, box_fc1_rows, fc1_operand,
+      row_maps, pooled_conv3, fc1_out, fc2_raw, head_out, candidates, total;
+} hc_relation_workspace;
+int hc_relation_workspace_bytes(int32_t n_images, int64_t n_box, int64_t n_pairs, int64_t chunk_pairs, int32_t shared_fc1,
+                                hc_relation_workspace* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,13 @@ class GemmDesc(C.Structure):
                 ("pair_sub", C.c_void_p), ("pair_obj", C.c_void_p), ("pair_row", C.c_void_p)]
 
 
+class RelationWorkspace(C.Structure):
+    """hc_relation_workspace: device bytes of every buffer of the batched relation path for one window."""
+    _fields_ = [(n, C.c_int64) for n in ("pixels_packed", "conv1_out", "box_select", "conv2_halves", "pooled_conv2", "work_lists",
+                                         "box_maps", "box_fc1_rows", "fc1_operand", "row_maps", "pooled_conv3", "fc1_out", "fc2_raw",
+                                         "head_out", "candidates", "total")]
+
+
 _P, _I32, _I64, _F, _D = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 
 SIGNATURES = {
@@ -80,6 +87,14 @@ SIGNATURES = {
     "hc_hier_loss": (C.c_int, [_P, _I64, _P, _P, _I32, _I32, _I32, _I32, _I32, _F, _F, _F, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P,
                                _P, _F, _F, _F, _F, _F, _P, _P, _P, _I32, _P]),
     "hc_hier_head_bwd": (C.c_int, [_P, _I32, _P, _I64, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _P]),
+    "hc_counts_allreduce": (C.c_int, [_P, _P, _I64, _P]),
+    "hc_nccl_unique_id": (C.c_int, [_P]),
+    "hc_nccl_comm_create": (C.c_int, [_P, _I32, _I32, C.POINTER(C.c_void_p)]),
+    "hc_nccl_comm_destroy": (C.c_int, [_P]),
+    "hc_pairs_enumerate_workspace_bytes": (C.c_int64, [_I64, _I32, _I32, _I32, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "hc_conv3_blocks_capacity": (C.c_int64, [_I64, _I32, _I32]),
+    "hc_conv2_box_blocks_capacity": (C.c_int64, [_I64, _I32]),
+    "hc_relation_workspace_bytes": (C.c_int, [_I32, _I64, _I64, _I64, _I32, C.POINTER(RelationWorkspace)]),
 }
 
 _lib = None

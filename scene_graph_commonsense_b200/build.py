@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhiercom_b200.so")
-SOURCES = ["abi.cu", "pairs.cu", "prep.cu", "blocks.cu", "head.cu", "topk.cu", "sgb.cu", "frontend.cu", "train.cu", "tc_gemm.cu"]
+SOURCES = ["abi.cu", "pairs.cu", "prep.cu", "blocks.cu", "head.cu", "topk.cu", "sgb.cu", "frontend.cu", "train.cu", "comm.cu", "tc_gemm.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--use_fast_math=false"]
 
@@ -59,7 +59,7 @@ def build(force=False, verbose=False):
         if rc != 0:
             sys.stderr.write(out + err)
             raise RuntimeError("nvcc failed on " + src)
-    cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-cudart", "static"]
+    cmd = [nvcc(), "-shared", "-o", LIB] + objs + ["-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -93,6 +93,8 @@ struct Params {
   // HC_EPI_POOL_DIFF_BF16 (block mode): out[pair_row[pair]] = (x - diff_sub[pair_sub[pair]]) - (diff_obj[pair_obj[pair]] - diff_bg)
   const __nv_bfloat16* diff_sub; const __nv_bfloat16* diff_obj; const __nv_bfloat16* diff_bg;
   const int* pair_sub; const int* pair_obj; const int* pair_row;
+  int dbg;                       // TIMING EXPERIMENTS ONLY (HC_TC_DEBUG, block mode; results are garbage): 1 = skip the A boxes, 2 = skip
+                                 // the weight tile, 4 = skip the MMAs - splits a stage's time into its TMA and tensor-core parts
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -268,12 +270,7 @@ __device__ __forceinline__ void store_bf16_row(const uint32_t (&r)[32], const fl
 
 // tile id -> (m block, n block): bands of `group_m` m-blocks; inside a band the n index is the slow one, so a
 // wave of consecutive tile ids shares few B column-panels and a bounded set of A row-panels through L2.
-__device__ __forceinline__ void tile_coords(const Params& p, int tiles_m, int tile, int& m_blk, int& n_blk, int rank = 0) {
-  if (p.cl2) {                    // CTA pair: M tiles (2t, 2t+1) of one N tile; the 4 N tiles of a pair of M tiles are consecutive
-    m_blk = (tile / p.tiles_n) * 2 + rank;
-    n_blk = tile % p.tiles_n;
-    return;
-  }
+__device__ __forceinline__ void tile_coords(const Params& p, int tiles_m, int tile, int& m_blk, int& n_blk, int = 0) {
   int per_band = p.group_m * p.tiles_n;
   int band = tile / per_band;
   int in = tile - band * per_band;
@@ -317,7 +314,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int rank = CG2 ? (int)cluster_ctarank() : 0;
   const int n_stages = CG2 ? C::CG2_STAGES : C::STAGES;
   const uint32_t stage_bytes = CG2 ? (uint32_t)C::CG2_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
-  const int num_tiles = CG2 ? ((tiles_m + 1) / 2) * p.tiles_n : tiles_m * p.tiles_n;
+  // pair tile (CG2): 16 listed blocks (256 pixels, the N side, half of them staged by each CTA) x 512 output channels (the M side:
+  // 2 sub-tiles x 256 rows across the pair); a CTA keeps its 256 channels x 256 pixels in its 512 TMEM columns
+  constexpr int PAIR_BLOCKS = 16, PAIR_COUT = 2 * 2 * BM;
+  const int pair_ct = p.N / PAIR_COUT;                                 // output-channel tiles per pixel tile
+  const int num_tiles = CG2 ? ((n_blocks + PAIR_BLOCKS - 1) / PAIR_BLOCKS) * pair_ct : tiles_m * p.tiles_n;
   const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int num_kb = p.K / BK;
@@ -385,8 +386,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t blk_bytes = (uint32_t)(p.blk_w * p.blk_h) * 128u;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         int m_blk, n_blk;
-        tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
-        const int e = lane < nblk ? __ldg(p.blocks + min(m_blk * nblk + lane, n_blocks - 1)) : 0;
+        if constexpr (CG2) { m_blk = tile / pair_ct; n_blk = tile - m_blk * pair_ct; }
+        else tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
+        const int e = CG2 ? (lane < PAIR_BLOCKS / 2 ? __ldg(p.blocks + min(m_blk * PAIR_BLOCKS + rank * (PAIR_BLOCKS / 2) + lane, n_blocks - 1)) : 0)
+                          : (lane < nblk ? __ldg(p.blocks + min(m_blk * nblk + lane, n_blocks - 1)) : 0);
         const int ex = 2 * (e & 15) - 1, ey = 2 * ((e >> 4) & 15) - 1, eimg = e >> 8;
         for (int cb = 0; cb < cblks; ++cb) {
           for (int kx = 0; kx < 3; ++kx) {
@@ -395,19 +398,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (lane == 0) {
                 mbar_wait(empty_bar(stage), phase ^ 1u);
                 // pair: the LEADER's full barrier counts the bytes of both CTAs (the peer only sends bytes, it never arrives)
-                if (!CG2) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                else if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * C::CG2_STAGE_BYTES);
+                // bytes of the pixel boxes / of the weight tile(s) this CTA fetches per stage
+                const uint32_t a_bytes = (p.dbg & 1) ? 0u : (uint32_t)(CG2 ? C::B_BYTES / 2 : MS * A_SUB_BYTES);
+                const uint32_t b_bytes = (p.dbg & 2) ? 0u : (uint32_t)(CG2 ? MS * A_SUB_BYTES : C::B_BYTES);
+                if (!CG2) mbar_expect_tx(full_bar(stage), a_bytes + b_bytes);
+                else if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (a_bytes + b_bytes));
               }
               __syncwarp();
               if constexpr (CG2) {
+                // pair: lanes 0-7 fetch this CTA's 8 of the tile's 16 pixel blocks (the N-side operand: the tensor cores of BOTH SMs
+                // read all 16), lanes 30/31 this CTA's 128 output channels of weight sub-tile 0/1 (the M-side operand)
                 const uint32_t lead_full = full_bar(stage) & PEER_BIT_MASK;
-                if (lane < nblk)
-                  tma_load_4d_cg2(a_dst + lane * blk_bytes, &tmap_a, lead_full, p.c_base + cb * BK, ex + kx, ey + ky, eimg);
-                else if (lane == 31)     // this CTA's half of the weight tile: rows [rank * BN/2, +BN/2) of the N tile
-                  tma_load_2d_cg2(a_dst + MS * A_SUB_BYTES, &tmap_bh, lead_full, ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN + rank * (BN / 2));
+                if (lane < PAIR_BLOCKS / 2) {
+                  if (!(p.dbg & 1))
+                    tma_load_4d_cg2(a_dst + MS * A_SUB_BYTES + lane * blk_bytes, &tmap_a, lead_full, p.c_base + cb * BK, ex + kx, ey + ky, eimg);
+                } else if (lane >= 30 && !(p.dbg & 2)) {
+                  const int j = lane - 30;
+                  tma_load_2d_cg2(a_dst + j * A_SUB_BYTES, &tmap_bh, lead_full, ((ky * 3 + kx) * cblks + cb) * BK,
+                                  n_blk * PAIR_COUT + j * 2 * BM + rank * BM);
+                }
               } else if (lane < nblk) {
-                tma_load_4d(a_dst + lane * blk_bytes, &tmap_a, full_bar(stage), p.c_base + cb * BK, ex + kx, ey + ky, eimg);
-              } else if (lane == 31) {
+                if (!(p.dbg & 1)) tma_load_4d(a_dst + lane * blk_bytes, &tmap_a, full_bar(stage), p.c_base + cb * BK, ex + kx, ey + ky, eimg);
+              } else if (lane == 31 && !(p.dbg & 2)) {
                 tma_load_2d(a_dst + MS * A_SUB_BYTES, &tmap_b, full_bar(stage), ((ky * 3 + kx) * cblks + cb) * BK, n_blk * BN);
               }
               if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -496,6 +508,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const uint64_t bdesc = umma_desc_sw128(a_src + MS * A_SUB_BYTES);
 #pragma unroll
           for (int j = 0; j < MS; ++j) {
+            if (p.dbg & 4) break;
             const uint64_t adesc = umma_desc_sw128(a_src + j * A_SUB_BYTES);
             const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_COLS + j * BN);
             if constexpr (CG2) {
@@ -536,6 +549,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
+      if constexpr (CG2) {
+        // Pair tile, transposed roles: TMEM lanes are OUTPUT CHANNELS (this thread owns one channel of sub-tile j), columns are the
+        // 256 pixels of the tile's 16 blocks - a 4x4-pixel block is 16 consecutive columns, so the 2x2 max-pool is register-local.
+        const int m_blk = tile / pair_ct, n_blk = tile - m_blk * pair_ct;
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        const long long map_elems = (long long)(p.H / 2) * (p.W / 2) * p.ldc;
+#pragma unroll 1
+        for (int j = 0; j < MS; ++j) {
+          const int cout = n_blk * PAIR_COUT + j * 2 * BM + rank * BM + q * 32 + lane;
+          const float bias = __ldg(p.bias + cout);
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t r[32];
+            __syncwarp();
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + j * BN + ch * 32), r);
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {                 // the two blocks of this 32-column chunk (warp-uniform entries)
+              const int e = __ldg(p.blocks + min(m_blk * PAIR_BLOCKS + 2 * ch + hb, n_blocks - 1));
+              const int o_img = e >> 8, cy0 = (e >> 4) & 15, cx0 = e & 15;
+              const __nv_bfloat16* sub = nullptr; const __nv_bfloat16* obj = nullptr;
+              long long out_base;
+              if (p.epi == HC_EPI_POOL_DIFF_BF16) {
+                sub = p.diff_sub + (long long)__ldg(p.pair_sub + o_img) * map_elems;
+                obj = p.diff_obj + (long long)__ldg(p.pair_obj + o_img) * map_elems;
+                out_base = (long long)__ldg(p.pair_row + o_img) * map_elems;
+              } else {
+                out_base = (long long)o_img * map_elems;
+              }
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {                  // pooled cell (c >> 1, c & 1) of the block: pixels (2cy + dy, 2cx + dx)
+                const int i0 = 16 * hb + 8 * (c >> 1) + 2 * (c & 1);
+                const float m = fmaxf(fmaxf(__uint_as_float(r[i0]), __uint_as_float(r[i0 + 1])),
+                                      fmaxf(__uint_as_float(r[i0 + 4]), __uint_as_float(r[i0 + 5])));
+                __nv_bfloat16 x = __float2bfloat16_rn(fmaxf(m + bias, 0.0f));
+                const long long off = ((long long)(cy0 + (c >> 1)) * (p.W / 2) + (cx0 + (c & 1))) * p.ldc + p.c_off + cout;
+                if (p.epi == HC_EPI_POOL_DIFF_BF16) {
+                  // d = (x - sub_map) - (obj_map - background): see the single-CTA epilogue below (same operations, same order)
+                  const float xf = __bfloat162float(x), sf = __bfloat162float(sub[off]), of = __bfloat162float(obj[off]),
+                              gf = __bfloat162float(p.diff_bg[off]);
+                  x = __float2bfloat16_rn(__fsub_rn(__fsub_rn(xf, sf), __fsub_rn(of, gf)));
+                }
+                reinterpret_cast<__nv_bfloat16*>(p.out)[out_base + off] = x;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc) & PEER_BIT_MASK);    // the leader's barrier (a remote arrive for the odd CTA)
+        if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+        continue;
+      }
       int m_blk, n_blk;
       tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
       int t_img = 0, t_y0 = 0, t_x0 = 0;                  // conv: tile origin (image, first pixel row / column)
@@ -733,10 +799,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
-        if constexpr (CG2) mbar_arrive_cluster(tempty_bar(acc) & PEER_BIT_MASK);    // the leader's barrier (a remote arrive for the odd CTA)
-        else mbar_arrive(tempty_bar(acc));
-      }
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
       if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -928,13 +991,14 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   if (blk) {
     static int env_pairs = -2;
     if (env_pairs == -2) { const char* e = getenv("HC_CONV3_PAIRS"); env_pairs = e ? atoi(e) : -1; }
-    p.cl2 = (env_pairs >= 0 ? env_pairs : d->cta_pairs) ? 1 : 0;
+    // the pair kernel is built for conv3_1's shape: 4x4-pixel blocks, pooled epilogues, 512-channel tiles, 256-row CTA tiles
+    const bool pair_ok = pooled && blk_w == 4 && d->block_rows == 4 && d->n % 512 == 0 && MS == 2;
+    p.cl2 = (pair_ok && (env_pairs >= 0 ? env_pairs : d->cta_pairs)) ? 1 : 0;
+    static int env_dbg = -1;
+    if (env_dbg == -1) { const char* e = getenv("HC_TC_DEBUG"); env_dbg = e ? atoi(e) : 0; }
+    p.dbg = env_dbg;
   }
-  if (p.cl2) {                            // pairs are built for the conv3_1 shape only (256-wide N tiles)
-    HC_REQUIRE(BN == 256, HC_E_SHAPE, "hc_tc_gemm: cta_pairs needs N to be a multiple of 256");
-    if (MS == 1) return tc::launch<256, 1, true>(ta, tb, tbh, p, stream);
-    return tc::launch<256, 2, true>(ta, tb, tbh, p, stream);
-  }
+  if (p.cl2) return tc::launch<256, 2, true>(ta, tb, tbh, p, stream);
   if (BN == 256 && MS == 1) return tc::launch<256, 1, false>(ta, tb, tbh, p, stream);
   if (BN == 256 && MS == 2) return tc::launch<256, 2, false>(ta, tb, tbh, p, stream);
   if (BN == 128 && MS == 1) return tc::launch<128, 1, false>(ta, tb, tbh, p, stream);

@@ -476,3 +476,20 @@ def _targets_flat(dir_tri, rel_tri, tri_offsets, box_offsets):
 def targets_flat(dir_tri, rel_tri, tri_offsets, box_offsets):
     """utils.py:294-352 on the packed triangle arrays -> (gt_offsets [B+1], label, sub, obj) device arrays."""
     return _call("targets_flat")(dir_tri, rel_tri, tri_offsets, box_offsets)
+
+
+# ------------------------------------------------------------------------------------------------ R12 across ranks
+@_op("counts_allreduce", "(Tensor(a!) counters, int nccl_comm) -> ()")
+def _counts_allreduce(counters, nccl_comm):
+    from . import _lib
+    if counters.dtype != torch.int64 or not counters.is_contiguous():
+        raise RuntimeError("hiercom_b200: counters must be a contiguous int64 tensor")
+    _lib.check(_lib.load().hc_counts_allreduce(nccl_comm, counters.data_ptr(), counters.numel(), _lib.stream_ptr()), "hc_counts_allreduce")
+    _A._count()
+
+
+def counts_allreduce(counters, nccl_comm):
+    """In-place ncclAllReduce(sum, int64) of the counter vector on the current stream (hc_counts_allreduce); `nccl_comm` is the
+    ncclComm_t as an integer (dist.CounterComm owns one per process)."""
+    _call("counts_allreduce")(counters, int(nccl_comm))
+    return counters

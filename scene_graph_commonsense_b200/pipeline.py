@@ -564,7 +564,8 @@ class RelationPipeline:
         """Streams evaluation windows from pinned host staging: yields `(n_pairs, counters_host)` per window.  The H2D copy of
         window k+1 is issued on a copy stream before window k's kernels are enqueued, so it rides under window k's compute;
         every window's inputs still cross PCIe exactly once and its counters are read back (D2H) before the next window's
-        result is produced.  `before_step(self)` / `after_step(self)` hook in a counter reset / the cross-rank all-reduce."""
+        result is produced.  `before_step(self)` / `after_step(self)` hook in a counter reset / the cross-rank all-reduce (a tensor
+        returned by `after_step` - the reduced copy - is what gets read back instead of the rank-local counters)."""
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy", None) is None:
             self._copy = torch.cuda.Stream(device=self.device)
@@ -592,9 +593,12 @@ class RelationPipeline:
             if before_step is not None:
                 before_step(self)
             n = self.step(b)
+            result = self.counters
             if after_step is not None:
-                after_step(self)
-            yield n, self.counters.cpu()
+                r = after_step(self)
+                if isinstance(r, torch.Tensor):        # e.g. dist.allreduce_counters(self.counters): the GLOBAL sums are read back
+                    result = r
+            yield n, result.cpu()
 
     # ------------------------------------------------------------------------------------------------ results
     def reset(self):

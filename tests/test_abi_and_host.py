@@ -61,7 +61,9 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
 def test_torch_custom_op_layer_registers_every_kernel_entry_point_for_cuda_only():
     """north_star: the Python modules reach the kernels through `torch.ops.hiercom.*`; no operator has a CPU kernel."""
     from scene_graph_commonsense_b200 import ops
-    compute = {n[3:] for n in _lib.SIGNATURES} - {"last_error", "abi_version", "device_check", "cs_bitmap_build"}
+    host_only = {"last_error", "abi_version", "device_check", "cs_bitmap_build", "nccl_unique_id", "nccl_comm_create", "nccl_comm_destroy",
+                 "pairs_enumerate_workspace_bytes", "conv3_blocks_capacity", "conv2_box_blocks_capacity", "relation_workspace_bytes"}
+    compute = {n[3:] for n in _lib.SIGNATURES} - host_only
     folded = {"box_label_embed": "hier_head", "proposals_pack": "detr_proposals", "match_object_categories_fill": "match_object_categories"}
     for name in compute:
         op = folded.get(name, name)
@@ -164,7 +166,11 @@ case = dict(ids=[i for i, _ in mine], n=[n for _, n in mine], run_mode="eval_cs"
             windows=[[j] for j in range(len(mine))])
 ev, t3, *_ = helpers.replay_predcls_case(case)
 c = torch.from_numpy(np.concatenate((ev.counters(), t3.counters())))
-hdist.allreduce_counters(c)
+local_copy = c.clone()
+g = hdist.allreduce_counters(c)
+g2 = hdist.allreduce_counters(c)          # idempotent: the rank-local vector is never modified, a second call gives the same sums
+assert torch.equal(c, local_copy) and torch.equal(g, g2)
+c = g
 t = hdist.max_over_ranks(float(rank + 1), "cpu")
 if rank == 0:
     np.save(os.environ["OUT"], c.numpy()); assert t == float(world)
