@@ -152,6 +152,8 @@ typedef struct hc_gemm_desc {
   const int32_t* pair_sub; /*                        per local pair: row of diff_sub */
   const int32_t* pair_obj; /*                        per local pair: row of diff_obj */
   const int32_t* pair_row; /*                        per local pair: output row */
+  void* scratch;           /* cta_pairs + HC_EPI_POOL_DIFF_BF16: bf16 [n_img, H/2, W/2, ldc] work map (the pair kernel leaves the pooled
+                              values there by local pair, a second launch forms the differences); NULL = single-CTA kernel */
 } hc_gemm_desc;
 
 int hc_tc_gemm(const hc_gemm_desc* desc, hc_stream_t stream);

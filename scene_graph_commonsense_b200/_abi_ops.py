@@ -80,10 +80,10 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16,
             act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None,
             blocks=None, n_blocks=None, block_rows=0, block_cols=0, k_masks=None, k_cell=0, add_a=None, add_a_rows=None, add_b=None, add_b_rows=None,
-            out_rows=None, diff_sub=None, diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None):
+            out_rows=None, diff_sub=None, diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None, cta_pairs=0, scratch=None):
     """out = epilogue(A @ B^T) on tcgen05 (see include/hiercom_b200.h hc_tc_gemm)."""
     require_cuda(a, b, out, bias, mul, blocks, n_blocks, k_masks, add_a, add_a_rows, add_b, add_b_rows, out_rows, diff_sub, diff_obj, diff_bg,
-                 pair_sub, pair_obj, pair_row)
+                 pair_sub, pair_obj, pair_row, scratch)
     for t, dt in ((k_masks, torch.int64), (add_a, torch.float32), (add_b, torch.float32), (add_a_rows, torch.int32), (add_b_rows, torch.int32),
                   (out_rows, torch.int32), (diff_sub, torch.bfloat16), (diff_obj, torch.bfloat16), (diff_bg, torch.bfloat16),
                   (pair_sub, torch.int32), (pair_obj, torch.int32), (pair_row, torch.int32)):
@@ -106,6 +106,9 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     d.out_rows = ptr(out_rows)
     d.diff_sub, d.diff_obj, d.diff_bg = ptr(diff_sub), ptr(diff_obj), ptr(diff_bg)
     d.pair_sub, d.pair_obj, d.pair_row = ptr(pair_sub), ptr(pair_obj), ptr(pair_row)
+    d.cta_pairs, d.scratch = int(cta_pairs), ptr(scratch)
+    if scratch is not None and diff_sub is not None and scratch.numel() < n_img * (h // 2) * (w // 2) * d.ldc:
+        raise RuntimeError("hiercom_b200: tc_gemm scratch must hold n_img pooled maps")
     with _timed(tag):
         check(_lib.load().hc_tc_gemm(C.byref(d), stream_ptr()), "hc_tc_gemm")
     _count()

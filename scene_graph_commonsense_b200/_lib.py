@@ -31,7 +31,7 @@ class GemmDesc(C.Structure):
                 ("add_a", C.c_void_p), ("add_a_rows", C.c_void_p), ("add_b", C.c_void_p), ("add_b_rows", C.c_void_p), ("ld_add", C.c_int64),
                 ("out_rows", C.c_void_p),
                 ("diff_sub", C.c_void_p), ("diff_obj", C.c_void_p), ("diff_bg", C.c_void_p),
-                ("pair_sub", C.c_void_p), ("pair_obj", C.c_void_p), ("pair_row", C.c_void_p)]
+                ("pair_sub", C.c_void_p), ("pair_obj", C.c_void_p), ("pair_row", C.c_void_p), ("scratch", C.c_void_p)]
 
 
 class RelationWorkspace(C.Structure):

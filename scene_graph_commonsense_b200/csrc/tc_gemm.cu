@@ -569,28 +569,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int hb = 0; hb < 2; ++hb) {                 // the two blocks of this 32-column chunk (warp-uniform entries)
               const int e = __ldg(p.blocks + min(m_blk * PAIR_BLOCKS + 2 * ch + hb, n_blocks - 1));
               const int o_img = e >> 8, cy0 = (e >> 4) & 15, cx0 = e & 15;
-              const __nv_bfloat16* sub = nullptr; const __nv_bfloat16* obj = nullptr;
-              long long out_base;
-              if (p.epi == HC_EPI_POOL_DIFF_BF16) {
-                sub = p.diff_sub + (long long)__ldg(p.pair_sub + o_img) * map_elems;
-                obj = p.diff_obj + (long long)__ldg(p.pair_obj + o_img) * map_elems;
-                out_base = (long long)__ldg(p.pair_row + o_img) * map_elems;
-              } else {
-                out_base = (long long)o_img * map_elems;
-              }
+              // (the pooled-difference epilogue is split for pairs: this kernel writes the pooled value x by LOCAL pair into the
+              // caller's scratch map, pair_diff_kernel then forms d from coalesced 16-byte vectors - per-channel 2-byte gathers of
+              // the three maps from here cost more than the whole main loop saved)
+              const long long out_base = (long long)o_img * map_elems;
 #pragma unroll
               for (int c = 0; c < 4; ++c) {                  // pooled cell (c >> 1, c & 1) of the block: pixels (2cy + dy, 2cx + dx)
                 const int i0 = 16 * hb + 8 * (c >> 1) + 2 * (c & 1);
                 const float m = fmaxf(fmaxf(__uint_as_float(r[i0]), __uint_as_float(r[i0 + 1])),
                                       fmaxf(__uint_as_float(r[i0 + 4]), __uint_as_float(r[i0 + 5])));
-                __nv_bfloat16 x = __float2bfloat16_rn(fmaxf(m + bias, 0.0f));
+                const __nv_bfloat16 x = __float2bfloat16_rn(fmaxf(m + bias, 0.0f));
                 const long long off = ((long long)(cy0 + (c >> 1)) * (p.W / 2) + (cx0 + (c & 1))) * p.ldc + p.c_off + cout;
-                if (p.epi == HC_EPI_POOL_DIFF_BF16) {
-                  // d = (x - sub_map) - (obj_map - background): see the single-CTA epilogue below (same operations, same order)
-                  const float xf = __bfloat162float(x), sf = __bfloat162float(sub[off]), of = __bfloat162float(obj[off]),
-                              gf = __bfloat162float(p.diff_bg[off]);
-                  x = __float2bfloat16_rn(__fsub_rn(__fsub_rn(xf, sf), __fsub_rn(of, gf)));
-                }
                 reinterpret_cast<__nv_bfloat16*>(p.out)[out_base + off] = x;
               }
             }
@@ -813,6 +802,42 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
 }
 
+// Second half of HC_EPI_POOL_DIFF_BF16 for the pair kernel: for every listed block, d = (x - sub_map) - (obj_map - background) on the
+// cells of the block, x = the pooled bf16 value the pair kernel left in `scratch` (by local pair), d -> out[pair_row[pair]].  Same
+// operations in the same order as the fused single-CTA epilogue, so d is bit-identical; a cell listed twice (clamped blocks may
+// overlap) is simply written twice with the same value because x is read from the scratch map, never from `out`.
+__global__ void __launch_bounds__(256)
+pair_diff_kernel(const int* __restrict__ blocks, const int* __restrict__ n_blocks_p, const uint4* __restrict__ scratch,
+                 const uint4* __restrict__ diff_sub, const uint4* __restrict__ diff_obj, const uint4* __restrict__ diff_bg,
+                 const int* __restrict__ pair_sub, const int* __restrict__ pair_obj, const int* __restrict__ pair_row, int cells_w,
+                 int cells_h, int map_w, long long cell_vec, long long map_vec, uint4* __restrict__ out) {
+  const int n_blocks = __ldg(n_blocks_p);
+  const int per_block = cells_w * cells_h * (int)cell_vec;          // 16-byte vectors per block
+  const long long total = (long long)n_blocks * per_block;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per_block), r = (int)(i - (long long)b * per_block);
+    const int cell = r / (int)cell_vec, v = r - cell * (int)cell_vec;
+    const int e = __ldg(blocks + b);
+    const int pair = e >> 8, cy = ((e >> 4) & 15) + cell / cells_w, cx = (e & 15) + cell % cells_w;
+    const long long off = ((long long)cy * map_w + cx) * cell_vec + v;
+    const uint4 X = __ldg(scratch + (long long)pair * map_vec + off);
+    const uint4 S = __ldg(diff_sub + (long long)__ldg(pair_sub + pair) * map_vec + off);
+    const uint4 O = __ldg(diff_obj + (long long)__ldg(pair_obj + pair) * map_vec + off);
+    const uint4 G = __ldg(diff_bg + off);
+    const uint32_t xv[4] = {X.x, X.y, X.z, X.w}, sv[4] = {S.x, S.y, S.z, S.w}, ov[4] = {O.x, O.y, O.z, O.w}, gv[4] = {G.x, G.y, G.z, G.w};
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xv[k]));
+      const float2 sf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sv[k]));
+      const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ov[k]));
+      const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gv[k]));
+      w[k] = pack_bf16(__fsub_rn(__fsub_rn(xf.x, sf.x), __fsub_rn(of.x, gf.x)), __fsub_rn(__fsub_rn(xf.y, sf.y), __fsub_rn(of.y, gf.y)));
+    }
+    out[(long long)__ldg(pair_row + pair) * map_vec + off] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // =============================================================================================== host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -986,19 +1011,30 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   if (blk) p.group_m = 1;                 // the 4 N tiles of an M tile run side by side and share its blocks through L2
   else if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
 
-  // block mode: tcgen05 cta_group::2 CTA pairs (d->cta_pairs; HC_CONV3_PAIRS=0/1 overrides for A/B runs); needs m_sub * N tile == 512
+  // block mode: tcgen05 cta_group::2 CTA pairs (d->cta_pairs); needs m_sub * N tile == 512
   // TMEM columns per CTA or fewer, which every configuration satisfies
   if (blk) {
-    static int env_pairs = -2;
-    if (env_pairs == -2) { const char* e = getenv("HC_CONV3_PAIRS"); env_pairs = e ? atoi(e) : -1; }
     // the pair kernel is built for conv3_1's shape: 4x4-pixel blocks, pooled epilogues, 512-channel tiles, 256-row CTA tiles
-    const bool pair_ok = pooled && blk_w == 4 && d->block_rows == 4 && d->n % 512 == 0 && MS == 2;
-    p.cl2 = (pair_ok && (env_pairs >= 0 ? env_pairs : d->cta_pairs)) ? 1 : 0;
+    const bool diff = d->epilogue == HC_EPI_POOL_DIFF_BF16;
+    const bool pair_ok = pooled && blk_w == 4 && d->block_rows == 4 && d->n % 512 == 0 && MS == 2 && d->c_off == 0 && d->ldc == d->n &&
+                         (!diff || (d->scratch && aligned16(d->scratch)));
+    p.cl2 = (pair_ok && d->cta_pairs) ? 1 : 0;
     static int env_dbg = -1;
     if (env_dbg == -1) { const char* e = getenv("HC_TC_DEBUG"); env_dbg = e ? atoi(e) : 0; }
     p.dbg = env_dbg;
   }
-  if (p.cl2) return tc::launch<256, 2, true>(ta, tb, tbh, p, stream);
+  if (p.cl2) {
+    const bool diff = d->epilogue == HC_EPI_POOL_DIFF_BF16;
+    if (diff) p.out = d->scratch;               // pooled values by local pair; pair_diff_kernel writes the differences to d->out
+    rc = tc::launch<256, 2, true>(ta, tb, tbh, p, stream);
+    if (rc != HC_OK || !diff) return rc;
+    const long long cell_vec = d->ldc / 8, map_vec = (long long)(d->h / 2) * (d->w / 2) * cell_vec;
+    tc::pair_diff_kernel<<<num_sms() * 8, 256, 0, stream>>>(
+        d->blocks, d->n_blocks, reinterpret_cast<const uint4*>(d->scratch), reinterpret_cast<const uint4*>(d->diff_sub),
+        reinterpret_cast<const uint4*>(d->diff_obj), reinterpret_cast<const uint4*>(d->diff_bg), d->pair_sub, d->pair_obj, d->pair_row,
+        blk_w / 2, d->block_rows / 2, d->w / 2, cell_vec, map_vec, reinterpret_cast<uint4*>(d->out));
+    return cuda_status("pair_diff_kernel launch");
+  }
   if (BN == 256 && MS == 1) return tc::launch<256, 1, false>(ta, tb, tbh, p, stream);
   if (BN == 256 && MS == 2) return tc::launch<256, 2, false>(ta, tb, tbh, p, stream);
   if (BN == 128 && MS == 1) return tc::launch<128, 1, false>(ta, tb, tbh, p, stream);

@@ -155,22 +155,32 @@ class PackedHead:
             self._p3_bg = p3
         return self._p3_bg
 
-    def conv3_blocks(self, p2, p3, n, blocks, n_blocks, block_rows, m_sub=2, tag="conv3", block_cols=8):
-        """conv3_1+ReLU+pool on the listed blocks of p2 [>=n,16,16,512] into the PRE-FILLED p3 [>=n,8,8,1024]."""
+    def conv3_blocks(self, p2, p3, n, blocks, n_blocks, block_rows, m_sub=2, tag="conv3", block_cols=8, cta_pairs=0):
+        """conv3_1+ReLU+pool on the listed blocks of p2 [>=n,16,16,512] into the PRE-FILLED p3 [>=n,8,8,1024].
+        cta_pairs=1: the tcgen05 cta_group::2 pair kernel (4x4-pixel blocks; same bits)."""
         ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_BF16,
                     n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag=tag, blocks=blocks,
-                    n_blocks=n_blocks, block_rows=block_rows, block_cols=block_cols)
+                    n_blocks=n_blocks, block_rows=block_rows, block_cols=block_cols, cta_pairs=cta_pairs)
         return p3
 
+    def pair_scratch(self, n):
+        """Work map of the pair kernel's split difference epilogue: pooled conv3_1 values by local pair, [n,8,8,1024] (grown on demand,
+        reused by every launch: launches on one stream are ordered)."""
+        cur = getattr(self, "_pair_scratch", None)
+        if cur is None or cur.shape[0] < n:
+            self._pair_scratch = cur = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=self.w3.device)
+        return cur
+
     def conv3_diff(self, p2, d, n, blocks, n_blocks, block_rows, sub_maps, obj_maps, pair_sub, pair_obj, pair_row, m_sub=2, tag="conv3",
-                   block_cols=8):
+                   block_cols=8, cta_pairs=0):
         """conv3_1+ReLU+pool on the listed blocks of p2 [>=n,16,16,512]; local pair i's cells go to row pair_row[i] of d [rows,8,8,1024]
         as the DIFFERENCE to its per-box maps, (x - sub_maps[pair_sub[i]]) - (obj_maps[pair_obj[i]] - background): the operand of
         the shared-footprint fc1 (`fc1_shared_fc2`), exactly zero wherever only one box of the pair reaches."""
         ops.tc_gemm(p2, self.w3, d, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_DIFF_BF16,
                     n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag=tag, blocks=blocks,
                     n_blocks=n_blocks, block_rows=block_rows, block_cols=block_cols, diff_sub=sub_maps, diff_obj=obj_maps, diff_bg=self.p3_background(),
-                    pair_sub=pair_sub, pair_obj=pair_obj, pair_row=pair_row)
+                    pair_sub=pair_sub, pair_obj=pair_obj, pair_row=pair_row, cta_pairs=cta_pairs,
+                    scratch=self.pair_scratch(n) if cta_pairs else None)
         return d
 
     def fc1_rows(self, maps, n):

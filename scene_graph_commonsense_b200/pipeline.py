@@ -181,6 +181,9 @@ class RelationPipeline:
         # (tests/test_gpu_sparse.py), cfg2 step 55.5 -> 51.7 ms on one box (profiles/bench_r01N_*)
         self.conv2_sparse = os.environ.get("HC_CONV2_SPARSE", "1") != "0"
         self.early_pool = os.environ.get("HC_EARLY_POOL", "1") != "0"     # first chunks' pooling starts under the per-box stages
+        # conv3_1 on tcgen05 cta_group::2 CTA pairs (4x4-pixel blocks only): the pair shares the tile's pixel operand, so each SM
+        # stages half of the small TMA boxes; bit-identical to the single-CTA kernel (tests/test_gpu_sparse.py)
+        self.conv3_pairs = int(os.environ.get("HC_CONV3_PAIRS", "1")) if (self.conv3_block_rows == 4 and self.conv3_block_cols == 4) else 0
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.last_k_masks = None             # int64 [n_tiles] device tensor: K-cell masks of the last shared fc1
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
@@ -236,7 +239,8 @@ class RelationPipeline:
             p2 = ops.pair_relu_pool(u, v, None, sub[s:e], obj[s:e], self.fs)
             blocks, _ = ops.conv3_active_blocks(boxes_x, sub[s:e], obj[s:e], br, self.fs, n_blocks=nblk[k:k + 1], block_cols=bc)
             ops.broadcast_rows(pk.p3_background(), e - s, maps[s:e])
-            pk.conv3_blocks(p2, maps[s:e], e - s, blocks, nblk[k:k + 1], br, m_sub=self.conv3_m_sub, tag="conv3_box", block_cols=bc)
+            pk.conv3_blocks(p2, maps[s:e], e - s, blocks, nblk[k:k + 1], br, m_sub=self.conv3_m_sub, tag="conv3_box", block_cols=bc,
+                            cta_pairs=self.conv3_pairs)
             del p2
         if with_background_row:
             return maps, nblk
@@ -504,7 +508,7 @@ class RelationPipeline:
             if side is not main:
                 main.wait_event(pooled)
             pk.conv3_diff(buf, d, cnt, blk, nblk[k:k + 1], br, sub_maps, obj_maps, sub_k, obj_k, row_of[base - w0:base - w0 + cnt],
-                          m_sub=self.conv3_m_sub, block_cols=bc)
+                          m_sub=self.conv3_m_sub, block_cols=bc, cta_pairs=self.conv3_pairs)
             ev = torch.cuda.Event()
             ev.record(main)
             gemm_done.append(ev)

@@ -212,11 +212,13 @@ def global_pair_index(rel_pair_idxs, num_objs, device):
 
 @torch.no_grad()
 def hierarchical_relation_tail(edge_rep, rel_pair_idxs, num_objs, obj_preds, union_features, post_cat, rel_compress,
-                               freq_bias_weight=None, use_vision=True, precision=None):
+                               freq_bias_weight=None, use_vision=True, precision=None, ctx_compress=None):
     """roi_relation_predictors.py:400-469 after `edge_rep = self.post_emb(edge_ctx)`:
     pair gather -> post_cat -> * union_features -> BayesHead -> frequency bias -> hierarchical log-softmax.
     edge_rep f32 [sum N, 2*hidden]; obj_preds int [sum N]; union_features f32 [P, pooling_dim] (pooling_dim == MLP_HEAD_DIM,
     i.e. no `up_dim`, as in config 5); freq_bias_weight = FrequencyBias.obj_baseline.weight [151*151, 51] or None.
+    ctx_compress (TransformerHierPredictor, roi_relation_predictors.py:233-238): a second BayesHead over the un-gated pair
+    representation whose logits are ADDED to rel_compress's before the softmax.
     Returns (relation1_dist, relation2_dist, relation3_dist, superrelation_dist) split per image."""
     dev = edge_rep.device
     hidden = edge_rep.shape[1] // 2
@@ -244,6 +246,11 @@ def hierarchical_relation_tail(edge_rep, rel_pair_idxs, num_objs, obj_preds, uni
         ops.tc_gemm(prod, w, prod1, n, pooling, 2 * hidden, bias=bias, lda=2 * hidden, ldc=pooling, epilogue=EPI_BF16, mul=mul,
                     group_m=16, m_sub=1, tag="post_cat")
         logits = rel_compress.logits_from_bf16(prod1)
+    if ctx_compress is not None:
+        er = edge_rep.float()
+        li = pair_idx.long()
+        prod_rep = torch.cat((er[:, :hidden][li[:, 0]], er[:, hidden:][li[:, 1]]), dim=1).contiguous()     # :216-221, f32 [P, 2*hidden]
+        logits = logits + ctx_compress.logits(prod_rep)
     pair_pred = obj_preds.to(dev, torch.int32)[pair_idx.long()].contiguous() if freq_bias_weight is not None else None
     rel, sup = ops.sgb_hier_softmax(logits, rel_compress.splits(), None if freq_bias_weight is None else freq_bias_weight.float().contiguous(),
                                     NUM_OBJ_SGB, pair_pred, _label_ids(dev))
