@@ -66,8 +66,8 @@ def test_k_cell_sparse_gemm_equals_dense_bit_for_bit(m, with_tables):
     assert torch.equal(o2[perm.long()], o1)
 
 
-@pytest.mark.parametrize("block_rows,block_cols", [(8, 8), (4, 8), (4, 4)])
-def test_difference_epilogue_and_keys(block_rows, block_cols):
+@pytest.mark.parametrize("block_rows,block_cols,cta_pairs", [(8, 8, 0), (4, 8, 0), (4, 4, 0), (4, 4, 1)])
+def test_difference_epilogue_and_keys(block_rows, block_cols, cta_pairs):
     """HC_EPI_POOL_DIFF_BF16 == (x - sub_map) - (obj_map - background) on the dense kernel's x, bit for bit, at row pair_row[i]; zero in
     every covered cell that only one box reaches; keys / tile masks describe the cell rectangles both boxes reach."""
     from scene_graph_commonsense_b200 import ops
@@ -94,7 +94,7 @@ def test_difference_epilogue_and_keys(block_rows, block_cols):
     p2b = ops.pair_relu_pool(u, v, None, s1, o1, 32)
     blk1, nb1 = ops.conv3_active_blocks(boxes_x, s1, o1, block_rows, block_cols=block_cols)
     maps = ops.broadcast_rows(pk.p3_background(), 2 * n_box, torch.empty(2 * n_box, 8, 8, 1024, dtype=torch.bfloat16, device=DEV))
-    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows, block_cols=block_cols)
+    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows, block_cols=block_cols, cta_pairs=cta_pairs)
     sub_maps, obj_maps, bg = maps[:n_box], maps[n_box:], pk.p3_background()
     # keys and sorted order
     keys = ops.pair_cell_keys(boxes_x, sub_t, obj_t).cpu().numpy()
@@ -119,7 +119,7 @@ def test_difference_epilogue_and_keys(block_rows, block_cols):
     ops.cells_zero(torch.from_numpy(tm).to(DEV), 256, n, d)
     blocks, n_blocks = ops.conv3_shared_blocks(boxes_x, sub_t, obj_t, block_rows, block_cols=block_cols)
     pk.conv3_diff(p2, d.view(n, 8, 8, 1024), n, blocks, n_blocks, block_rows, sub_maps, obj_maps, sub_t, obj_t, row_of,
-                  block_cols=block_cols)
+                  block_cols=block_cols, cta_pairs=cta_pairs)
     torch.cuda.synchronize()
     ref = ((dense.float() - sub_maps[sub_t.long()].float()) - (obj_maps[obj_t.long()].float() - bg.float())).to(torch.bfloat16)
     got = d.view(n, 8, 8, 1024)[row_of.long()]                                 # back in pair order

@@ -87,9 +87,11 @@ def _packed(seed=0, gain=1.0):
     return model.PackedHead(synthetic.head_state_dict(seed=seed, logit_gain=gain), DEV)
 
 
-@pytest.mark.parametrize("block_rows,m_sub,block_cols", [(8, 2, 8), (4, 2, 8), (8, 1, 8), (4, 1, 8), (4, 2, 4), (4, 1, 4)])
-def test_sparse_conv3_equals_dense_bit_for_bit(block_rows, m_sub, block_cols):
-    """conv3_1 + ReLU + pool on the listed blocks over a background pre-fill == the dense kernel, every bf16 bit."""
+@pytest.mark.parametrize("block_rows,m_sub,block_cols,cta_pairs", [(8, 2, 8, 0), (4, 2, 8, 0), (8, 1, 8, 0), (4, 1, 8, 0), (4, 2, 4, 0),
+                                                                   (4, 1, 4, 0), (4, 2, 4, 1)])
+def test_sparse_conv3_equals_dense_bit_for_bit(block_rows, m_sub, block_cols, cta_pairs):
+    """conv3_1 + ReLU + pool on the listed blocks over a background pre-fill == the dense kernel, every bf16 bit
+    (cta_pairs=1: the tcgen05 cta_group::2 pair kernel, weights on the M side, the tile's pixels shared by the two CTAs)."""
     from scene_graph_commonsense_b200 import ops
     from scene_graph_commonsense_b200._lib import EPI_POOL_BF16, GEMM_CONV3, GEMM_CONV3_BLOCKS
     pk = _packed()
@@ -114,7 +116,7 @@ def test_sparse_conv3_equals_dense_bit_for_bit(block_rows, m_sub, block_cols):
     assert torch.equal(sparse[n - 1], pk.p3_background()[0])
     ops.tc_gemm(p2, pk.w3, sparse, n * 256, 1024, 9 * 512, bias=pk.b3, ldc=1024, mode=GEMM_CONV3_BLOCKS, epilogue=EPI_POOL_BF16, n_img=n,
                 h=16, w=16, c_total=512, c_base=0, c_in=512, m_sub=m_sub, blocks=blocks, n_blocks=n_blocks, block_rows=block_rows,
-                block_cols=block_cols)
+                block_cols=block_cols, cta_pairs=cta_pairs)
     torch.cuda.synchronize()
     nb = int(n_blocks.item())
     assert 0 < nb < n * (256 // (block_rows * block_cols))                                       # the list is really sparse on these boxes
