@@ -100,6 +100,71 @@ def build_predictor(sd, batch):
     return p.eval()
 
 
+class _CtxT(_Ctx):
+    """TransformerContext stand-in: 3-tuple (roi_relation_predictors.py:200)."""
+
+    def forward(self, roi_features, proposals, logger=None):
+        return torch.zeros(self.edge_ctx.shape[0], 151), self.obj_preds, self.edge_ctx
+
+
+class _CtxV(_Ctx):
+    """VCTreeLSTMContext stand-in: takes rel_pair_idxs, returns binary_preds last (roi_relation_predictors.py:649)."""
+
+    def forward(self, roi_features, proposals, rel_pair_idxs, logger=None):
+        return torch.zeros(self.edge_ctx.shape[0], 151), self.obj_preds, self.edge_ctx, None
+
+
+def _copy_head(head, sd, prefix=""):
+    with torch.no_grad():
+        for n in ("fc3_1", "fc3_2", "fc3_3", "fc5"):
+            getattr(head, n).weight.copy_(sd[prefix + n + ".weight"]); getattr(head, n).bias.copy_(sd[prefix + n + ".bias"])
+
+
+def build_variant(kind, sd, sd_ctx, batch):
+    """The REAL TransformerHierPredictor / VCTreeHierPredictor forward (tail after a stub context layer)."""
+    cls = {"transformer": ref_pred.TransformerHierPredictor, "vctree": ref_pred.VCTreeHierPredictor}[kind]
+    p = object.__new__(cls)
+    nn.Module.__init__(p)
+    p.attribute_on, p.use_vision, p.use_bias, p.union_single_not_match = False, True, True, False
+    p.hidden_dim, p.pooling_dim = 512, 4096
+    p.post_emb, p.post_cat = nn.Linear(512, 1024), nn.Linear(1024, 4096)
+    with torch.no_grad():
+        p.post_emb.weight.copy_(sd["post_emb.weight"]); p.post_emb.bias.copy_(sd["post_emb.bias"])
+        p.post_cat.weight.copy_(sd["post_cat.weight"]); p.post_cat.bias.copy_(sd["post_cat.bias"])
+    if kind == "transformer":
+        p.rel_compress, p.ctx_compress = ref_hier.BayesHead(4096), ref_hier.BayesHead(1024)
+        _copy_head(p.rel_compress, sd)
+        _copy_head(p.ctx_compress, sd_ctx)
+        p.context_layer = _CtxT(batch["edge_ctx"], batch["obj_labels"])
+    else:
+        p.ctx_compress = ref_hier.BayesHeadProb(4096)
+        _copy_head(p.ctx_compress, sd)
+        p.context_layer = _CtxV(batch["edge_ctx"], batch["obj_labels"])
+    return p.eval()
+
+
+def gen_variants():
+    """sgb_variants.npz: Transformer / VCTree hierarchical predictors through the real SGB forward (SGB_VARIANT_CASE)."""
+    from tests.golden_cases import SGB_VARIANT_CASE as c
+    batch = synthetic.make_sgb_batch(c["num_objs"], seed=c["seed"])
+    sd = synthetic.sgb_state_dict(seed=c["seed"])
+    sd_ctx = synthetic.sgb_state_dict(seed=c["seed"] + 100, pooling=1024)          # a BayesHead over the 1024-d pair representation
+    sampler = object.__new__(ref_sampling.RelationSampling)
+    sampler.use_gt_box, sampler.test_overlap = True, False
+    proposals = [BoxList(b, (800, 600), 'xyxy') for b in batch["boxes"]]
+    rel_pair_idxs = sampler.prepare_test_pairs('cpu', proposals)
+    out = {}
+    for kind in ("transformer", "vctree"):
+        pred = build_variant(kind, sd, sd_ctx, batch)
+        with torch.no_grad():
+            _, r1, r2, r3, sup, _ = pred(proposals, rel_pair_idxs, None, None, None, batch["union_features"], None)
+        for i in range(len(c["num_objs"])):
+            out["%s_rel_%d" % (kind, i)] = torch.cat((r1[i], r2[i], r3[i]), dim=1).numpy()
+            out["%s_sup_%d" % (kind, i)] = sup[i].numpy()
+        print("variant", kind, "max joint prob", float(torch.cat([torch.cat((a, b, c_), 1) for a, b, c_ in zip(r1, r2, r3)]).exp().max()))
+    np.savez_compressed(os.path.join(OUT, "sgb_variants.npz"), **out)
+
+
 def ref_pred_labels(which):
     from scene_graph_commonsense_b200 import sgb
     return {'geo': sgb.GEO_LABEL, 'pos': sgb.POS_LABEL, 'sem': sgb.SEM_LABEL}[which]
@@ -188,4 +253,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or "cases" in sys.argv:
+        main()
+    if len(sys.argv) < 2 or "variants" in sys.argv:
+        gen_variants()

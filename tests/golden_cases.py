@@ -27,6 +27,8 @@ SGB_CASES = {
     "sgb_case_b": dict(num_objs=[3, 14, 2, 8, 5], seed=1, empty_gt=2),
 }
 
+SGB_VARIANT_CASE = dict(num_objs=[5, 8, 3, 10], seed=2)      # TransformerHierPredictor / VCTreeHierPredictor through the real forward
+
 FRONTEND_CASES = {
     # DETR outputs -> proposals (evaluate.py:309-368), match_object_categories, match_target_sgd.
     # The reference hard-codes 100 queries (`.view(-1, 100, topk_cat)`, evaluate.py:311), so raggedness comes from p_noobj.
