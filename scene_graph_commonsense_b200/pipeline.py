@@ -296,11 +296,43 @@ class RelationPipeline:
             chunks.insert(0, chunks.pop(k))
         return chunks
 
-    def forward_pairs(self, b: DeviceBatch, pairs):
+    def forward_pairs_tensors(self, feat, depth, boxes, cats, supercats, pair_index, box_img=None):
+        """The batched entry point with the argument list of SURVEY §8(b): plain tensors instead of a DeviceBatch.
+          feat f32 [B,256,32,32], depth f32 [B,1,32,32]      DETR features / depth of the window's images (evaluate.py:103-109)
+          boxes [nbox,4] (xmin,xmax,ymin,ymax) on the 32-grid  (any numeric dtype; truncated toward zero like the reference's int())
+          cats int [nbox], supercats int8 [nbox,4] (-1 padded raw lists) or a list of id lists (utils.py:136-149 input format)
+          pair_index int [P,2] = (subject box row, object box row); box_img int [nbox] image of each box (default: one image)
+        -> (relation [P,R], super [P,3], connectivity [P], log sigmoid(connectivity) [P]) exactly as `forward_pairs`."""
+        from .model import supers_to_table
+        dev = self.device
+        boxes = torch.as_tensor(boxes).to(dev).to(torch.int32).contiguous()
+        n_box = boxes.shape[0]
+        box_img = torch.zeros(n_box, dtype=torch.int32, device=dev) if box_img is None else torch.as_tensor(box_img).to(dev, torch.int32).contiguous()
+        n_img = int(feat.shape[0])
+        counts = torch.bincount(box_img.long(), minlength=n_img)
+        box_offsets = torch.cat((counts.new_zeros(1), counts.cumsum(0))).to(torch.int32)
+        if not isinstance(supercats, torch.Tensor):
+            supercats = supers_to_table(supercats, dev)
+        pair_index = torch.as_tensor(pair_index).to(dev)
+        b = DeviceBatch(feat.to(dev, torch.float32).contiguous(), depth.to(dev, torch.float32).contiguous(), boxes, box_offsets, box_img,
+                        torch.as_tensor(cats).to(dev, torch.int32).contiguous(), supercats.to(dev, torch.int8).contiguous(),
+                        torch.zeros(n_img + 1, dtype=torch.int32, device=dev), None, None, None, 0, 0, 0, 0)
+        pairs = dict(n=int(pair_index.shape[0]), sub=pair_index[:, 0].to(torch.int32).contiguous(), obj=pair_index[:, 1].to(torch.int32).contiguous())
+        if pairs["n"] == 0:
+            r = sum(self.splits)
+            z = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)
+            return z(0, r), z(0, 3), z(0), z(0)
+        return self.forward_pairs(b, pairs)
+
+    def forward_pairs(self, b, pairs=None, *tensors, **kw):
         """R3,R5-R7 for every directed pair of the batch -> (relation [P,R], super [P,3], connectivity [P], logsig [P]).
+        Called with tensors, `forward_pairs(feat, depth, boxes, cats, supercats, pair_index[, box_img])`, it is the SURVEY §8(b)
+        signature (see `forward_pairs_tensors`).
         Pair lists from `enumerate_pairs` take the tiled outer-sum pooling kernel on image-aligned chunks, with the
         pooling of chunk k+1 overlapped (second stream) with the tensor-core GEMMs of chunk k; arbitrary pair lists
         (no `offsets_host`) take the generic gather kernel."""
+        if not isinstance(b, DeviceBatch):
+            return self.forward_pairs_tensors(b, pairs, *tensors, **kw)
         pk = self.packed
         n = pairs["n"]
         br, bc, shared = self.conv3_block_rows, self.conv3_block_cols, self.conv3_shared

@@ -77,6 +77,29 @@ def test_batched_pipeline_matches_legacy_and_oracle():
     assert np.abs(np.exp(logsig.cpu().numpy()) - np.exp(ref_ls)).max() <= PROB_TOL
 
 
+def test_forward_pairs_with_the_survey_argument_list_equals_the_batch_form():
+    """`forward_pairs(feat, depth, boxes, cats, supercats, pair_index, box_img)` == the DeviceBatch form, two images."""
+    from scene_graph_commonsense_b200 import model, pipeline
+    samples = [synthetic.make_image(903, 5), synthetic.make_image(904, 4)]
+    pk = model.PackedHead(synthetic.preset_state_dict("trained"), DEV)
+    pipe = pipeline.RelationPipeline(pk, DEV, commonsense=False)
+    b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
+    pairs = pipe.enumerate_pairs(b)
+    want = pipe.forward_pairs(b, pairs)
+    feat = torch.stack([s.feat for s in samples]).to(DEV)
+    depth = torch.stack([s.depth for s in samples]).to(DEV)
+    boxes = torch.cat([s.bbox for s in samples]).float()                   # floats are truncated like the reference's int()
+    cats = torch.cat([s.categories for s in samples])
+    supercats = [sc for s in samples for sc in s.super_categories]
+    pair_index = torch.stack((pairs["sub"], pairs["obj"]), dim=1).long()
+    box_img = torch.tensor([0] * 5 + [1] * 4)
+    got = pipe.forward_pairs(feat, depth, boxes, cats, supercats, pair_index, box_img)
+    for g, w in zip(got, want):
+        assert float((g - w).abs().max()) <= 1e-5         # same kernels; the generic pair-gather pooling vs the tiled one is bit-identical
+    empty = pipe.forward_pairs(feat, depth, boxes, cats, supercats, pair_index[:0], box_img)
+    assert empty[0].shape == (0, 50) and empty[1].shape == (0, 3)
+
+
 def test_end_to_end_step_counters_match_oracle_small():
     """cfg1-shaped: one image, 8 boxes, full model: counters of the CUDA path == oracle replay with the CUDA scores'
     own candidates is covered elsewhere; here the whole step runs and its scores stay within tolerance of the oracle
