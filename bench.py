@@ -102,7 +102,11 @@ WORKLOADS = {
     "cfg3": dict(images=8, boxes=100, sgdet=True, chunk_pairs=40960,
                  text="cfg3: SGDET-style %d images x %d proposals per GPU (%d directed pairs/GPU/step, 20 GT boxes/image), two-pass, "
                       "object-confidence add, synonym matching, top-100 triplets, eval_cs, reference batch skip rule"),
+    "cfg5": dict(images=IMAGES_PER_GPU, boxes=BOXES, sgdet=False, chunk_pairs=0,
+                 text="cfg5: SGB Motifs PredCLS tail, %d images x %d objects per GPU (%d directed pairs/GPU/step), 4096-d union features, "
+                      "51 classes, HierarchPostProcessor candidates + SGRecall/SGMeanRecall"),
 }
+FLOP_PAIR_CFG5 = 2 * 1024 * 4096 + 2 * 4096 * 54      # post_cat + BayesHead per directed pair
 
 
 def make_samples(rank, n_images=IMAGES_PER_GPU, boxes=BOXES, with_maps=True, sgdet=False, boxes_mode="small"):
@@ -114,23 +118,24 @@ def make_samples(rank, n_images=IMAGES_PER_GPU, boxes=BOXES, with_maps=True, sgd
 
 
 # ======================================================================================================= reference arm
-def cpu_reference_run(steps, warmup, budget_s=150.0, per_pair_s=0.024):
+def cpu_reference_run(steps, warmup, budget_s=150.0, per_pair_s=0.012, weights="sharp", boxes_mode="small"):
     """The reference's CPU formulation (oracle port of evaluate.py:111-217 + model.py + evaluator.py, torch fp32, all host
-    threads) on a bounded sample of cfg2: the first `imgs` images restricted to their first `nb` boxes."""
+    threads) on a bounded sample of cfg2: the first 12 images (config.yaml:53 batch_size 12, walked in lock-step exactly like
+    evaluate.py:132-183, so every head call carries up to 12 rows) restricted to their first `nb` boxes."""
     from oracle import hiercom_oracle as O
     from scene_graph_commonsense_b200 import synthetic, tables
     torch.set_num_threads(os.cpu_count() or 1)
     total_steps = max(steps + warmup, 1)
     pairs_budget = max(budget_s / total_steps / per_pair_s, 24)
-    imgs, nb = 2, 4
+    imgs, nb = 12, 3
     while imgs * (nb + 1) * nb <= pairs_budget and nb < BOXES:
         nb += 1
-    full = make_samples(0, imgs, BOXES)
+    full = make_samples(0, imgs, BOXES, boxes_mode=boxes_mode)
     batch = []
     for s in full:
         batch.append(synthetic.ImageSample(s.image_id, s.feat, s.depth, s.bbox[:nb], s.categories[:nb], s.super_categories[:nb],
                                            s.relationships[:nb - 1], s.subj_or_obj[:nb - 1]))
-    sd = synthetic.head_state_dict(seed=0, logit_gain=40.0)
+    sd = synthetic.preset_state_dict(weights)
     head_fn = O.make_head_fn(sd)
     zs = set(tables.zero_shot_keys().tolist())
     al, vi = set(tables.commonsense_aligned_keys().tolist()), set(tables.commonsense_violated_keys().tolist())
@@ -146,28 +151,141 @@ def cpu_reference_run(steps, warmup, budget_s=150.0, per_pair_s=0.024):
         if it >= warmup:
             times.append(dt)
     mean_t = float(np.mean(times))
-    sample = "%d images x first %d of %d boxes (%d directed pairs/step), replay of evaluate.py:111-217 incl. Evaluator+Top3" % (
-        imgs, nb, BOXES, pairs)
+    sample = ("%d images (one lock-step batch, config.yaml:53) x first %d of %d boxes (%d directed pairs/step), replay of "
+              "evaluate.py:111-217 incl. Evaluator+Top3; oracle port of the reference (torch fp32), not the unmodified classes: "
+              "/root/reference does not exist on the GPU box") % (imgs, nb, BOXES, pairs)
     return pairs / mean_t, mean_t, sample, torch.get_num_threads()
+
+
+def cpu_reference_run_cfg5(steps, warmup, n_img=4):
+    """cfg5 on the CPU: the fp32 restatement of roi_relation_predictors.py:399-459 + inference.py:246-302 + SGRecall for `n_img`
+    images of 40 objects per step."""
+    from oracle import sgb_oracle as SO
+    from scene_graph_commonsense_b200 import synthetic
+    torch.set_num_threads(os.cpu_count() or 1)
+    num_objs = [BOXES] * n_img
+    batch = synthetic.make_sgb_batch(num_objs, seed=0)
+    sd = synthetic.sgb_state_dict(seed=0)
+    pairs = SO.prepare_test_pairs(num_objs)
+    n_pairs = sum(int(p.shape[0]) for p in pairs)
+    logits = batch["obj_logits"].split(num_objs, 0)
+    times = []
+    for it in range(max(steps + warmup, 1)):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            r1, r2, r3, sup = SO.predictor_tail(sd, batch["edge_ctx"], pairs, num_objs, batch["obj_labels"], batch["union_features"])
+            for i in range(n_img):
+                SO.post_process_image(r1[i], r2[i], r3[i], logits[i], pairs[i])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean_t = float(np.mean(times))
+    sample = "%d images x %d objects (%d directed pairs/step): predictor tail + post-processor of the SGB oracle (torch fp32)" % (n_img, BOXES, n_pairs)
+    return n_pairs / mean_t, mean_t, sample, torch.get_num_threads()
+
+
+def parity_sample(samples, sd, relation, pairs, batch, sgdet, n=256, operand_model=False):
+    """bench.py's checker leg (the one place besides --impl reference where oracle/ runs here): the fp32 oracle on a stratified
+    sample of the directed pairs of THIS step's batch against the scores the GPU produced for them."""
+    from oracle import parity as PA
+    sub, obj, img = pairs["sub"].cpu().numpy(), pairs["obj"].cpu().numpy(), pairs["img"].cpu().numpy()
+    boxes, off = batch.boxes.cpu().numpy(), batch.box_offsets.cpu().numpy()
+    idx, strata = PA.stratified_pair_sample(boxes, sub, obj, n, seed=1)
+    pair_list = [(int(img[p]), int(sub[p] - off[img[p]]), int(obj[p] - off[img[p]])) for p in idx]
+    rel_g = relation[torch.from_numpy(idx).to(relation.device)].cpu().numpy()
+    t0 = time.perf_counter()
+    rel_ref, _, _ = PA.oracle_scores(samples, sd, pair_list, sgdet=sgdet)
+    dt = time.perf_counter() - t0
+    st = PA.parity_stats(rel_g, rel_ref)
+    out = {k: st[k] for k in ("n", "max_abs_dp", "mean_abs_dp", "max_rel_logp_err", "argmax_flip_rate", "top_joint_prob_median")}
+    out["strata"] = {int(k): int((strata == k).sum()) for k in np.unique(strata)}
+    out["oracle_pairs_per_sec"] = len(pair_list) / dt
+    out["tolerance"] = 2e-3
+    if operand_model:
+        rel_m, _, _ = PA.operand_rounded_scores(samples, sd, pair_list, sgdet=sgdet)
+        m = PA.parity_stats(rel_m, rel_ref)
+        out["bf16_operand_model_vs_fp32"] = {k: m[k] for k in ("max_abs_dp", "mean_abs_dp", "argmax_flip_rate")}
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    v, mean_t, sample, cores = cpu_reference_run(args.steps, args.warmup)
+    if args.workload == "cfg5":
+        v, mean_t, sample, cores = cpu_reference_run_cfg5(args.steps, args.warmup)
+        text = "cfg5: SGB Motifs PredCLS tail, 64 images x 40 objects per GPU (bounded sample per step)"
+    else:
+        v, mean_t, sample, cores = cpu_reference_run(args.steps, args.warmup, weights=args.weights, boxes_mode=args.boxes)
+        text = "cfg2: PredCLS 64 images x 40 boxes per GPU, two-pass, eval_cs (bounded sample per step)"
     line = {"metric": "relation_pairs_per_sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": mean_t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "cfg2: PredCLS 64 images x 40 boxes per GPU, two-pass, eval_cs (bounded sample per step)",
-                       "sample": sample},
+            "config": {"workload": text, "sample": sample, "weights": args.weights, "boxes": args.boxes},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(line)
 
 
 # ======================================================================================================= our arm
-def run_ours(args):
+def _cell_interval(lo, hi):
+    """numpy twin of `active_cells` (csrc/blocks.cu): pooled conv3_1 cells a box interval [lo, hi) of the 32-grid can reach."""
+    qlo = np.maximum(0, (lo - 1) >> 1)
+    qhi = np.minimum(15, hi >> 1)
+    qlo, qhi = np.maximum(0, qlo - 1), np.minimum(15, qhi + 1)
+    a, b = qlo >> 1, (qhi >> 1) + 1
+    empty = hi <= lo
+    return np.where(empty, 0, a), np.where(empty, 0, b)
+
+
+def minimal_flops(boxes, sub, obj, n_images):
+    """FLOPs of the footprint formulation with NOTHING wasted on block covers: conv3_1 and fc1 per pair only on the
+    pooled cells BOTH boxes reach, per box on the cells that box reaches, conv2_1 halves on the pixels within one pixel of a box,
+    conv1 per image, fc2 + heads per pair.  The denominator-independent lower bound `roofline.frac_minimal` is quoted against."""
+    b = np.clip(boxes.astype(np.int64), 0, 32)
+    xa, xb = _cell_interval(b[:, 0], b[:, 1])
+    ya, yb = _cell_interval(b[:, 2], b[:, 3])
+    degenerate = (b[:, 1] <= b[:, 0]) | (b[:, 3] <= b[:, 2])
+    xa, xb, ya, yb = (np.where(degenerate, 0, v) for v in (xa, xb, ya, yb))
+    w = np.maximum(0, np.minimum(xb[sub], xb[obj]) - np.maximum(xa[sub], xa[obj]))
+    h = np.maximum(0, np.minimum(yb[sub], yb[obj]) - np.maximum(ya[sub], ya[obj]))
+    shared_cells = float((w * h).sum())
+    box_cells = float(((xb - xa) * (yb - ya)).sum())
+    px = np.where(degenerate, 0, (np.minimum(32, b[:, 1] + 1) - np.maximum(0, b[:, 0] - 1)) * (np.minimum(32, b[:, 3] + 1) - np.maximum(0, b[:, 2] - 1)))
+    conv3_cell = 4 * (2 * 512 * 9 * 1024)                     # a pooled cell = 2 x 2 conv3_1 output pixels
+    fc1_cell = 2 * 1024 * 4096
+    conv2_px = 2 * 128 * 9 * 512
+    n_pairs = len(sub)
+    flop = n_images * FLOP_IMG + 2.0 * float(px.sum()) * conv2_px                     # conv1; conv2 halves (two roles) on the box footprint
+    flop += (shared_cells + 2.0 * box_cells) * conv3_cell                             # conv3_1: pairs + (box, empty) / (empty, box) maps
+    flop += (shared_cells + 2.0 * box_cells + 64.0) * fc1_cell                        # fc1: pairs + per-box rows + the background row
+    flop += n_pairs * (4_194_304 + 55_296)                                            # fc2 (dense 4096 -> 512) + heads
+    return flop, shared_cells / (64.0 * max(n_pairs, 1))
+
+
+def relabel_gt_from_model(pipe, samples, sgdet):
+    """Untimed setup: GT predicates are re-drawn from the model's OWN scores (synthetic.assign_gt_from_scores), so the bench's R@K
+    is discriminating (0.3-0.7 instead of chance level: a wrong score, label or ranking anywhere in the path moves it)."""
+    from scene_graph_commonsense_b200 import pipeline, synthetic
+    b = pipeline.host_batch_from_samples(samples, skip_mode="batch", sgdet=sgdet).to_device(pipe.device)
+    pairs = pipe.enumerate_pairs(b)
+    rel = pipe.forward_pairs(b, pairs)[0].cpu().numpy()
+    sub, obj, img = pairs["sub"].cpu().numpy(), pairs["obj"].cpu().numpy(), pairs["img"].cpu().numpy()
+    off = b.box_offsets.cpu().numpy()
+    row = {(int(i), int(a - off[i]), int(o - off[i])): k for k, (i, a, o) in enumerate(zip(img, sub, obj))}
+    zero = np.zeros(rel.shape[1], dtype=np.float32)
+    for i, smp in enumerate(samples):
+        synthetic.assign_gt_from_scores(smp, lambda a, o, i=i: rel[row[(i, a, o)]] if (i, a, o) in row else zero)
+    del b, pairs
+    torch.cuda.synchronize()
+    return samples
+
+
+_HEAD_CACHE = {}
+
+
+def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True):
+    """cfg2 / cfg3 through RelationPipeline -> the bench line (dict); every rank runs it, rank 0 gets the dict, the others None."""
     from scene_graph_commonsense_b200 import dist as hdist
     from scene_graph_commonsense_b200 import model, ops, pipeline, synthetic, tables
     rank, local, world = hdist.init_from_env()
@@ -175,26 +293,34 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     pk = peaks()
 
-    sd = synthetic.head_state_dict(seed=0, logit_gain=40.0)
-    packed = model.PackedHead(sd, dev)
-    del sd
-    wl = WORKLOADS[args.workload]
+    if args.weights not in _HEAD_CACHE:          # 276.7 M parameters: drawn and packed once per process (the `also` runs reuse them)
+        sd0 = synthetic.preset_state_dict(args.weights)
+        _HEAD_CACHE[args.weights] = (sd0, model.PackedHead(sd0, dev))
+    sd, packed = _HEAD_CACHE[args.weights]
+    wl = WORKLOADS[workload]
     chunk_pairs = args.chunk_pairs or wl["chunk_pairs"]
     pipe = pipeline.RelationPipeline(packed, dev, commonsense=True, chunk_pairs=chunk_pairs, conv3_m_sub=args.conv3_m_sub,
                                      overlap=not args.no_overlap, predcls=not wl["sgdet"], chunk_policy=args.chunk_policy,
                                      conv3_block_rows=CONV3_MODES[args.conv3][0], conv3_shared=CONV3_MODES[args.conv3][1],
                                      fc1_shared=args.fc1 == "shared", conv3_block_cols=CONV3_MODES[args.conv3][2])
-    samples = make_samples(rank, wl["images"], wl["boxes"], sgdet=wl["sgdet"])
+    samples = make_samples(rank, wl["images"], wl["boxes"], sgdet=wl["sgdet"], boxes_mode=args.boxes)
+    if not wl["sgdet"]:                         # (cfg3's GT triplets are copies of proposals with their own labels; left as drawn)
+        samples = relabel_gt_from_model(pipe, samples, wl["sgdet"])
     host = pipeline.host_batch_from_samples(samples, skip_mode="batch", sgdet=wl["sgdet"])
-    del samples
     batch = host.to_device(dev)
     torch.cuda.synchronize()
-
     global_counters = torch.zeros_like(pipe.counters)
+    t_host = {"enqueue": 0.0, "allreduce": []}
 
     def step_resident():
+        h0 = time.perf_counter()
         n = pipe.step(batch)
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        a0.record()
         hdist.allreduce_counters(pipe.counters, out=global_counters)      # one int64[765] all-reduce per step (C ABI / NCCL)
+        a1.record()
+        t_host["enqueue"] += time.perf_counter() - h0
+        t_host["allreduce"].append((a0, a1))
         return n
 
     def steps_e2e(k):
@@ -206,10 +332,11 @@ def run_ours(args):
             pass
         return out
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         pipe.reset()
         step_resident()
     torch.cuda.synchronize()
+    t_host["enqueue"], t_host["allreduce"] = 0.0, []
 
     # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
@@ -223,7 +350,7 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     pairs_step = 0
-    for _ in range(args.steps):
+    for _ in range(steps):
         pipe.reset()
         pairs_step = step_resident()
     e1.record()
@@ -234,134 +361,314 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     t_dev = e0.elapsed_time(e1) / 1e3
     t_max = hdist.max_over_ranks(t_dev, dev)
+    t_min = -hdist.max_over_ranks(-t_dev, dev)
     pairs_total = hdist.sum_over_ranks(pairs_step, dev)
-    value = pairs_total * args.steps / t_max
+    value = pairs_total * steps / t_max
+    allreduce_ms = float(np.mean([a.elapsed_time(b) for a, b in t_host["allreduce"]])) if t_host["allreduce"] else 0.0
     counters_final = pipe.counters.cpu().numpy().copy()                 # rank 0's own images (the recall line of the JSON)
-    # block-sparse conv3_1: work-list lengths of the last step (read back AFTER the timed region)
     blocks_step = int(pipe.last_n_blocks.sum().item()) if pipe.conv3_block_rows and pipe.last_n_blocks is not None else None
-
-    # shared-footprint fc1: K cells visited per 256-row tile of the last step (read back AFTER the timed region)
     fc1_exec_frac, fc1_cells = 1.0, None
     if pipe.fc1_shared and pipe.last_k_masks is not None:
         fc1_cells = int(np.unpackbits(pipe.last_k_masks.cpu().numpy().view(np.uint8)).sum())
         fc1_exec_frac = fc1_cells * 256.0 / (pairs_step * 64.0)
     n_box_step = wl["images"] * wl["boxes"]
-    # conv2_1 halves on the box footprint: listed 8 x block_rows-pixel blocks of the last step vs the 1024 pixels of every box map
     conv2_exec_frac = 1.0
     if getattr(pipe, "conv2_sparse", False) and packed.last_conv2_blocks is not None:
         nb_dev, rows_c2, boxes_c2 = packed.last_conv2_blocks
         conv2_exec_frac = int(nb_dev.item()) * 8.0 * rows_c2 / (boxes_c2 * 1024.0)
-
     per_tag = {}
     for tag, a, b in ops.PROFILE["events"]:
         per_tag.setdefault(tag, []).append(a.elapsed_time(b))
     ops.PROFILE["events"].clear()
 
     # ---- timed region 2: end to end through the public API with HOST buffers (H2D + D2H inside)
-    steps_e2e(max(1, min(args.warmup, 2)))
+    steps_e2e(max(1, min(warmup, 2)))
     hdist.barrier()
     torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    steps_e2e(args.steps)
+    steps_e2e(steps)
     f1.record()
     torch.cuda.synchronize()
     hdist.barrier()
     t_e2e = hdist.max_over_ranks(f0.elapsed_time(f1) / 1e3, dev)
-    e2e_value = pairs_total * args.steps / t_e2e
-
+    e2e_value = pairs_total * steps / t_e2e
     if rank != 0:
-        return
-    # ---- roofline of the dominant kernel (the tensor-core GEMM with the most time in the step: conv3_1 or fc1), live
-    # CUDA-event timing inside the timed region
+        return None
+
+    # ---- roofline of the dominant kernel (conv3_1 or fc1), live CUDA-event timing inside the timed region
+    pairs_dev = pipe.enumerate_pairs(batch)
+    sub_h, obj_h = pairs_dev["sub"].cpu().numpy(), pairs_dev["obj"].cpu().numpy()
+    flop_min, shared_frac = minimal_flops(batch.boxes.cpu().numpy(), sub_h, obj_h, wl["images"])
     conv3 = per_tag.get("conv3", [])
     fc1 = per_tag.get("fc1", [])
     conv3_exec_frac = 1.0           # executed / dense-equivalent FLOPs of conv3_1 (block-sparse mode visits only listed blocks)
     if blocks_step is not None:
         conv3_exec_frac = blocks_step * pipe.conv3_block_cols * pipe.conv3_block_rows / (pairs_step * 256.0)
 
-    def roof_of(name, times, flop_step_kernel, extra):
+    def roof_of(name, times, flop_exec, flop_algorithmic, flop_minimal, extra):
         if not times:
             return None
         total_ms = float(np.sum(times))
-        achieved = flop_step_kernel * args.steps / (total_ms * 1e-3) / 1e12
+        sec = total_ms * 1e-3 / steps
+        achieved = flop_exec / sec / 1e12
         r = {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-             "frac": achieved / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16",
-             "avg_launch_ms": total_ms / len(times), "launches_timed": len(times), "ms_per_step": total_ms / args.steps,
-             "algorithmic_flop_per_launch": flop_step_kernel * args.steps / len(times)}
+             "frac": achieved / pk["bf16_sustained"], "traffic": None, "peak_source": pk["source"] + " sustained bf16 (burst %.0f)" % pk["bf16_burst"],
+             "frac_of_burst_peak": achieved / pk["bf16_burst"],
+             "avg_launch_ms": total_ms / len(times), "launches_timed": len(times), "ms_per_step": total_ms / steps,
+             "algorithmic_flop_per_launch": flop_exec * steps / len(times),
+             # the same launch time against three FLOP counts: what the kernel EXECUTES (listed blocks / visited K cells - `frac`),
+             # the MINIMUM of the footprint formulation (cells both boxes reach, no block cover), SURVEY 8d's dense ALGORITHMIC count
+             "frac_executed": achieved / pk["bf16_sustained"],
+             "frac_minimal": flop_minimal / sec / 1e12 / pk["bf16_sustained"],
+             "frac_algorithmic_8d": flop_algorithmic / sec / 1e12 / pk["bf16_sustained"],
+             "flop_executed_per_step": flop_exec, "flop_minimal_per_step": flop_minimal, "flop_algorithmic_8d_per_step": flop_algorithmic}
         r.update(extra)
         return r
 
+    n_pairs_h = len(sub_h)
+    conv3_cell = 4 * (2 * 512 * 9 * 1024)
+    b_np = batch.boxes.cpu().numpy()
+    # minimal conv3_1 / fc1 FLOPs (pair cells both boxes reach + per-box cells), from the same geometry as `minimal_flops`
+    xa, xb = _cell_interval(np.clip(b_np[:, 0], 0, 32).astype(np.int64), np.clip(b_np[:, 1], 0, 32).astype(np.int64))
+    ya, yb = _cell_interval(np.clip(b_np[:, 2], 0, 32).astype(np.int64), np.clip(b_np[:, 3], 0, 32).astype(np.int64))
+    box_cells = float(((xb - xa) * (yb - ya)).sum())
+    shared_cells = shared_frac * 64.0 * n_pairs_h
+    conv3_min = (shared_cells + 2.0 * box_cells) * conv3_cell
+    fc1_min = (shared_cells + 2.0 * box_cells + 64.0) * (2 * 1024 * 4096)
     conv3_times = conv3 + per_tag.get("conv3_box", [])
-    roof_conv3 = roof_of("tc_gemm_kernel<256,%d> conv3_1 implicit GEMM + bias/ReLU/maxpool epilogue (%s)" % (args.conv3_m_sub, args.conv3),
-                         conv3_times, conv3_exec_frac * pairs_step * FLOP_PAIR_CONV3,
-                         {"note": "achieved counts EXECUTED FLOPs (listed blocks only, per-pair and per-box launches); "
-                                  "dense-equivalent = achieved / executed_fraction",
-                          "executed_fraction": conv3_exec_frac} if blocks_step is not None else {})
+    roof_conv3 = roof_of("tc_gemm_kernel<256,%d%s> conv3_1 implicit GEMM + bias/ReLU/maxpool epilogue (%s)" % (
+                             args.conv3_m_sub, ",cta_group::2" if getattr(pipe, "conv3_pairs", 0) else "", args.conv3),
+                         conv3_times, conv3_exec_frac * pairs_step * FLOP_PAIR_CONV3, pairs_step * FLOP_PAIR_CONV3, conv3_min,
+                         {"note": "achieved counts EXECUTED FLOPs (listed blocks only, per-pair and per-box launches)",
+                          "executed_fraction": conv3_exec_frac, "minimal_fraction": conv3_min / (pairs_step * FLOP_PAIR_CONV3)})
     if roof_conv3 is not None:
-        if blocks_step is not None:
-            roof_conv3["dense_equivalent_tflops"] = roof_conv3["achieved"] / conv3_exec_frac
-            tp = os.path.join(ROOT, "profiles", "ncu_summary_r01y.json")      # committed ncu --set full capture of the default path
-            if os.path.exists(tp) and args.conv3 == "shared44" and pipe.fc1_shared and args.workload == "cfg2":
-                for r in json.load(open(tp)).get("launches", []):
-                    if r.get("what", "").startswith("conv3_1 difference epilogue, full chunk"):
-                        roof_conv3["traffic"] = r.get("dram_bytes_per_launch")
-                        roof_conv3["traffic_note"] = ("dram__bytes_read+write of one full-chunk launch (3.58 ms under ncu, 12 480 pairs); "
-                                                      "the kernel is bound by L2->SM delivery (35.2 GB per launch through xbar->L1), not DRAM")
-        else:
-            tp = os.path.join(ROOT, "profiles", "conv3_dram_bytes.json")    # the committed ncu DRAM figure is the dense kernel's
-            if os.path.exists(tp):
-                roof_conv3["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
+        tp = os.path.join(ROOT, "profiles", "ncu_summary_r02_conv3_pairs.json")      # committed ncu --set full capture of THIS kernel
+        if os.path.exists(tp):
+            try:
+                t = json.load(open(tp))
+                roof_conv3["traffic"] = t.get("dram_bytes_per_launch")
+                roof_conv3["traffic_source"] = "profiles/ncu_summary_r02_conv3_pairs.json (ncu --set full, one full-chunk launch)"
+            except Exception:
+                pass
     fc1_times = fc1 + per_tag.get("fc1_box", [])
     fc1_box_flop = (2 * n_box_step + 1) * FLOP_PAIR_FC1 if pipe.fc1_shared else 0        # per-box fc1 rows (dense)
     roof_fc1 = roof_of("tc_gemm_kernel<256,2> fc1 [pairs,65536] x [65536,4096] + bias/ReLU epilogue (%s)" % (args.fc1 if pipe.fc1_shared else "dense"),
-                       fc1_times, fc1_exec_frac * pairs_step * FLOP_PAIR_FC1 + fc1_box_flop,
-                       {"note": "achieved counts EXECUTED FLOPs: the K cells each 256-row tile visits (pair launch) + the dense per-box "
-                                "rows; dense-equivalent = achieved / executed_fraction",
-                        "executed_fraction": (fc1_exec_frac * pairs_step * FLOP_PAIR_FC1 + fc1_box_flop) / (pairs_step * FLOP_PAIR_FC1)}
-                       if pipe.fc1_shared else {})
-    if roof_fc1 is not None and pipe.fc1_shared:
-        roof_fc1["dense_equivalent_tflops"] = roof_fc1["achieved"] / roof_fc1["executed_fraction"]
+                       fc1_times, fc1_exec_frac * pairs_step * FLOP_PAIR_FC1 + fc1_box_flop, pairs_step * FLOP_PAIR_FC1, fc1_min,
+                       {"note": "achieved counts EXECUTED FLOPs: the K cells each 256-row tile visits (pair launch) + the dense per-box rows",
+                        "executed_fraction": (fc1_exec_frac * pairs_step * FLOP_PAIR_FC1 + fc1_box_flop) / (pairs_step * FLOP_PAIR_FC1)})
     roofs = [r for r in (roof_conv3, roof_fc1) if r is not None]
     roofs.sort(key=lambda r: -r["ms_per_step"])
     roof = roofs[0] if roofs else None
     roof_second = roofs[1] if len(roofs) > 1 else None
-    breakdown = {t: {"launches": len(v), "ms_per_step": float(np.sum(v)) / args.steps} for t, v in sorted(per_tag.items())}
-    flop_dense = wl["images"] * FLOP_IMG + wl["images"] * wl["boxes"] * FLOP_BOX + pairs_step * FLOP_PAIR
+    breakdown = {t: {"launches": len(v), "ms_per_step": float(np.sum(v)) / steps} for t, v in sorted(per_tag.items())}
+    flop_dense = wl["images"] * FLOP_IMG + n_box_step * FLOP_BOX + pairs_step * FLOP_PAIR
     flop_step = flop_dense - (1.0 - conv3_exec_frac) * pairs_step * FLOP_PAIR_CONV3      # FLOPs actually executed
     flop_step += fc1_box_flop - (1.0 - fc1_exec_frac) * pairs_step * FLOP_PAIR_FC1
     flop_step -= (1.0 - conv2_exec_frac) * n_box_step * FLOP_BOX
     m = pipeline.metrics_from_counters(counters_final)
+    sec_step = t_max / steps
 
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline and args.workload == "cfg2":
-        v, mean_t, sample, cores = cpu_reference_run(1, 0, budget_s=20.0)
+    cpu = parity = None
+    if world == 1 and not args.no_cpu_baseline and workload == "cfg2" and with_cpu:
+        v, mean_t, sample, cores = cpu_reference_run(1, 0, budget_s=15.0, weights=args.weights, boxes_mode=args.boxes)
         cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+    if world == 1 and not args.no_cpu_baseline and with_parity:
+        rel = pipe.forward_pairs(batch, pairs_dev)[0]
+        parity = parity_sample(samples, sd, rel, pairs_dev, batch, wl["sgdet"], n=args.parity_pairs, operand_model=args.weights == "sharp")
+        parity["weights"] = args.weights
 
-    line = {
-        "metric": "relation_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t_max / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+    return {
+        "metric": "relation_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": wl["text"] % (wl["images"], wl["boxes"], pairs_step),
-                   "parallelism": "images sharded over %d GPU(s), one int64[765] all-reduce per step" % world,
+                   "parallelism": "images sharded over %d GPU(s), one int64[765] all-reduce per step (hc_counts_allreduce, NCCL)" % world,
                    "l2": "no explicit flush: each step streams >10 GB of activations/weights (>> 126 MB L2)",
-                   "weights": "random init, trained-scale logits (seed 0)", "chunk_pairs": chunk_pairs,
+                   "weights": "random init, preset '%s' (synthetic.WEIGHT_PRESETS: trunk gain %.3g, logit gain %.3g; seed 0)" % (
+                       (args.weights,) + synthetic.WEIGHT_PRESETS[args.weights]),
+                   "gt": "PredCLS GT predicates re-drawn from the model's own per-super argmaxes with noise (synthetic.assign_gt_from_scores)"
+                         if not wl["sgdet"] else "GT triplets = jittered copies of proposals (synthetic.make_sgdet_image)",
+                   "boxes": args.boxes, "shared_cell_fraction": shared_frac, "chunk_pairs": chunk_pairs,
                    "pool_gemm_overlap": not args.no_overlap, "conv3_m_sub": args.conv3_m_sub, "chunk_policy": args.chunk_policy,
-                   "conv3": args.conv3, "fc1": args.fc1 if pipe.fc1_shared else "dense",
+                   "conv3": args.conv3, "conv3_cta_pairs": int(getattr(pipe, "conv3_pairs", 0)), "fc1": args.fc1 if pipe.fc1_shared else "dense",
                    "conv2": "box footprint" if getattr(pipe, "conv2_sparse", False) else "dense"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes * world,
-                "d2h_bytes_per_step": (tables.COUNTER_SIZE * 8 + 4) * world, "ms_per_step": t_e2e / args.steps * 1e3,
+                "d2h_bytes_per_step": (tables.COUNTER_SIZE * 8 + 4) * world, "ms_per_step": t_e2e / steps * 1e3,
                 "api": "RelationPipeline.run over pinned HostBatch windows (H2D of window k+1 issued under window k's kernels; "
-                       "counters read back after every window)"},
+                       "the all-reduced counters are read back after every window)"},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_second": roof_second,
-        "step_tensor_frac": flop_step / (t_max / args.steps) / 1e12 / pk["bf16_sustained"],
-        "algorithmic_tflop_per_step": flop_dense / 1e12, "executed_tflop_per_step": flop_step / 1e12,
+        "step_tensor_frac": flop_step / sec_step / 1e12 / pk["bf16_sustained"],
+        "step_frac_minimal": flop_min / sec_step / 1e12 / pk["bf16_sustained"],
+        "algorithmic_tflop_per_step": flop_dense / 1e12, "executed_tflop_per_step": flop_step / 1e12, "minimal_tflop_per_step": flop_min / 1e12,
         "conv3_blocks_per_step": blocks_step, "fc1_cells_per_step": fc1_cells, "conv2_executed_fraction": conv2_exec_frac,
         "kernel_breakdown": breakdown,
-        "recall": {"R@20/50/100": m["evaluator"][0], "mR@20/50/100": [float(x) for x in m["evaluator"][2]]},
+        "per_rank": {"ms_per_step_max": t_max / steps * 1e3, "ms_per_step_min": t_min / steps * 1e3,
+                     "allreduce_ms_per_step_rank0": allreduce_ms, "host_enqueue_ms_per_step_rank0": t_host["enqueue"] / steps * 1e3},
+        "recall": {"R@20/50/100": m["evaluator"][0], "mR@20/50/100": [float(x) for x in m["evaluator"][2]],
+                   "top3_R@20/50/100": m["top3"][0], "n_gt": int(counters_final[tables.EV_NGT])},
+        "parity_sample": parity, "cpu_baseline": cpu,
+    }
+
+
+def run_cfg5(args, steps, warmup, with_cpu=True):
+    """cfg5 (SGB plug-and-play tail) -> bench line dict on rank 0.  A step = roi_relation_predictors.py:400-469 tail +
+    inference.py:246-302 candidates / ranking + sgg_eval matching for one window of 64 images x 40 objects per GPU."""
+    from scene_graph_commonsense_b200 import dist as hdist
+    from scene_graph_commonsense_b200 import ops, sgb, synthetic
+    rank, local, world = hdist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pk = peaks()
+    wl = WORKLOADS["cfg5"]
+    n_img, n_obj = wl["images"], wl["boxes"]
+    num_objs = [n_obj] * n_img
+    batch = synthetic.make_sgb_batch(num_objs, seed=rank)
+    sd = synthetic.sgb_state_dict(seed=0)
+    post_cat = torch.nn.Linear(1024, 4096).to(dev)
+    head = sgb.BayesHead(input_dim=4096).to(dev)
+    with torch.no_grad():
+        post_cat.weight.copy_(sd["post_cat.weight"]); post_cat.bias.copy_(sd["post_cat.bias"])
+        for n in ("fc3_1", "fc3_2", "fc3_3", "fc5"):
+            getattr(head, n).weight.copy_(sd[n + ".weight"]); getattr(head, n).bias.copy_(sd[n + ".bias"])
+    edge_rep_h = torch.nn.functional.linear(batch["edge_ctx"], sd["post_emb.weight"], sd["post_emb.bias"]).pin_memory()   # upstream of the path
+    union_h = batch["union_features"].pin_memory()
+    pairs = [torch.nonzero(torch.ones(n, n) - torch.eye(n)).view(-1, 2).to(dev) for n in num_objs]
+    obj_labels = batch["obj_labels"].to(dev)
+    freq = sd["freq_bias"].to(dev)
+    logits = list(batch["obj_logits"].to(dev).split(num_objs))
+    boxes = [b.to(dev) for b in batch["boxes"]]
+    g = torch.Generator().manual_seed(7)
+    n_pairs = sum(n * (n - 1) for n in num_objs)
+    gt_classes = list(obj_labels.split(num_objs))
+    post = sgb.HierarchPostProcessor(use_gt_box=True)
+    edge_rep, union = edge_rep_h.to(dev), union_h.to(dev)
+
+    def tail():
+        return sgb.hierarchical_relation_tail(edge_rep, pairs, num_objs, obj_labels, union, post_cat, head, freq, precision=args.sgb_precision)
+
+    # GT relations drawn from the model's own ranked predictions (half) and at random (half), so the recall line is discriminating
+    r1, r2, r3, sup = tail()
+    cand0 = post.candidates(r1, r2, r3, logits, pairs)
+    ranked = ops.topk_select((cand0["pair_off"] * 3).contiguous(), cand0["score"], 128).cpu().numpy()
+    pair_off = cand0["pair_off"].cpu().numpy()
+    row_h, label_h, pidx_h = cand0["row"].cpu().numpy(), cand0["label"].cpu().numpy(), cand0["pair_idx"].cpu().numpy()
+    obj_off = np.concatenate(([0], np.cumsum(num_objs)))
+    gt_rels = []
+    for i, n in enumerate(num_objs):
+        rows = []
+        for j in range(12):
+            if j % 2 == 0:
+                c = int(ranked[i][int(torch.randint(0, 60, (1,), generator=g))]) + 3 * int(pair_off[i])
+                so = pidx_h[row_h[c]] - obj_off[i]
+                rows.append([int(so[0]), int(so[1]), int(label_h[c])])
+            else:
+                a, b = torch.randperm(n, generator=g)[:2].tolist()
+                rows.append([a, b, int(torch.randint(1, 51, (1,), generator=g))])
+        gt_rels.append(torch.tensor(rows, dtype=torch.int64, device=dev))
+
+    def step():
+        r1, r2, r3, sup = tail()
+        cand = post.candidates(r1, r2, r3, logits, pairs)
+        rec = sgb.SGBRecall()
+        rec.evaluate_batch(cand, gt_rels, gt_classes, boxes)
+        return rec
+
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    hdist.barrier()
+    torch.cuda.synchronize()
+    ops.PROFILE["events"].clear()
+    ops.PROFILE["on"] = True
+    l0 = ops.LAUNCHES["n"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        rec = step()
+    e1.record()
+    torch.cuda.synchronize()
+    hdist.barrier()
+    ops.PROFILE["on"] = False
+    launches = ops.LAUNCHES["n"] - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t_max = hdist.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    pairs_total = hdist.sum_over_ranks(n_pairs, dev)
+    tags = {}
+    for tag, a, b in ops.PROFILE["events"]:
+        tags.setdefault(tag, []).append(a.elapsed_time(b))
+    ops.PROFILE["events"].clear()
+    # e2e: the two per-step inputs (post_emb output per object, union features per pair) cross PCIe inside the timed region, the
+    # recall result is read back to the host
+    def e2e_steps(k):
+        nonlocal edge_rep, union
+        res = None
+        for _ in range(k):
+            edge_rep, union = edge_rep_h.to(dev, non_blocking=True), union_h.to(dev, non_blocking=True)
+            res = step().result()
+        return res
+    e2e_steps(1)
+    hdist.barrier()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    res = e2e_steps(steps)
+    f1.record()
+    torch.cuda.synchronize()
+    hdist.barrier()
+    t_e2e = hdist.max_over_ranks(f0.elapsed_time(f1) / 1e3, dev)
+    if rank != 0:
+        return None
+    gemm_ms = sum(float(np.sum(v)) for t, v in tags.items() if t in ("post_cat", "bayes_head")) / steps
+    mma_factor = 3 if args.sgb_precision == "bf16x3" else 1
+    alg = n_pairs * FLOP_PAIR_CFG5 / (gemm_ms * 1e-3) / 1e12
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline and with_cpu:
+        v, mean_t, sample, cores = cpu_reference_run_cfg5(1, 0)
+        cpu = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample}
+    h2d = edge_rep_h.numel() * 4 + union_h.numel() * 4
+    return {
+        "metric": "relation_pairs_per_sec", "value": pairs_total * steps / t_max, "unit": "pairs/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": t_max / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (split bf16 operands, fp32 accumulate)" if mma_factor == 3 else "bf16", "data": "synthetic",
+        "config": {"workload": wl["text"] % (n_img, n_obj, n_pairs), "precision": args.sgb_precision,
+                   "precision_note": "plain bf16 operands miss the 2e-3 bar on this tail (max |dP| 8.3e-3 vs the fp32 oracle at 64 x 40, "
+                                     "tests/test_gpu_parity_at_scale.py), bf16x3 holds 4e-5: the split is what parity costs here",
+                   "l2": "inputs (1.6 GB of union features) exceed L2"},
+        "e2e": {"value": pairs_total * steps / t_e2e, "unit": "pairs/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 6 * 8 * world,
+                "ms_per_step": t_e2e / steps * 1e3, "api": "sgb.hierarchical_relation_tail + HierarchPostProcessor.candidates + SGBRecall"},
+        "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"kernel": "tc_gemm_kernel post_cat 1024->4096 (* union_features epilogue) + BayesHead 4096->54", "bound": "tensor",
+                     "achieved": alg, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": alg / pk["bf16_sustained"], "traffic": None,
+                     "executed_tflops": mma_factor * alg, "frac_executed": mma_factor * alg / pk["bf16_sustained"], "ms_per_step": gemm_ms,
+                     "note": "achieved = ALGORITHMIC FLOPs (8 830 976 per pair, SURVEY 8d); the bf16x3 split executes 3x that on the tensor pipe"},
+        "kernel_breakdown": {t: {"launches": len(v), "ms_per_step": float(np.sum(v)) / steps} for t, v in sorted(tags.items())},
+        "recall": {"R@20/50/100": [float(res["recall"][k]) for k in (20, 50, 100)], "mR@20/50/100": [float(res["mean_recall"][k]) for k in (20, 50, 100)]},
         "cpu_baseline": cpu,
     }
-    emit(line)
+
+
+def run_ours(args):
+    line = run_cfg5(args, args.steps, args.warmup) if args.workload == "cfg5" else run_relation(args, args.workload, args.steps, args.warmup)
+    also = []
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.also and world == 1 and args.workload == "cfg2":
+        # the other BASELINE configurations in front of the driver's clock: shorter runs, same timing rules
+        k, w = max(3, args.steps // 2), 3
+        for name in ("cfg3", "cfg5"):
+            try:
+                sub = run_cfg5(args, k, w, with_cpu=False) if name == "cfg5" else run_relation(args, name, k, w, with_cpu=False)
+                keep = ("value", "unit", "ms_per_step", "steps", "warmup", "dtype", "config", "e2e", "gpu_launches", "clocks", "roofline",
+                        "recall", "parity_sample")
+                also.append(dict(workload=name, **{q: sub[q] for q in keep if q in sub}))
+            except Exception as e:      # noqa: BLE001 - the headline line must survive a failing extra
+                also.append(dict(workload=name, error=repr(e)[:300]))
+    if line is not None:
+        if args.also and args.workload == "cfg2":
+            line["also"] = also
+        emit(line)
 
 
 def emit(line):
@@ -384,14 +691,22 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk-pairs", type=int, default=0, help="pairs per conv3/fc1 chunk (0 = the workload's default)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
-                    help="cfg2 = the configuration BASELINE.json's metric is quoted on (default); cfg3 = SGDET-shaped scaling case")
+                    help="cfg2 = the configuration BASELINE.json's metric is quoted on (default); cfg3 = SGDET-shaped scaling case; "
+                         "cfg5 = SGB plug-and-play tail")
     ap.add_argument("--conv3-m-sub", type=int, default=2)
     ap.add_argument("--conv3", default="shared44", choices=sorted(CONV3_MODES),
                     help="conv3_1 kernel: dense, or block-sparse over the dilated footprint of each pair's boxes (bit-identical output)")
     ap.add_argument("--fc1", default="shared", choices=["shared", "dense"],
                     help="shared = fc1 as per-box rows + a K-cell-sparse GEMM over the cells both boxes reach (needs --conv3 shared*); "
                          "dense = fc1 over the assembled conv3_1 output")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline and parity_sample)")
+    ap.add_argument("--weights", default="sharp", choices=["trained", "sharp", "init"],
+                    help="synthetic.WEIGHT_PRESETS: sharp = He-gain trunk, logit std 3.3 (default); trained = round-1 head-only scaling")
+    ap.add_argument("--boxes", default="small", choices=["small", "vg", "full"],
+                    help="box-size distribution: small = SURVEY 8d (side 4-15), vg = sides U{8..32}, full = every box is the whole grid")
+    ap.add_argument("--parity-pairs", type=int, default=256, help="directed pairs of the step's batch the fp32 oracle re-scores")
+    ap.add_argument("--sgb-precision", default="bf16x3", choices=["bf16x3", "bf16"])
+    ap.add_argument("--no-also", dest="also", action="store_false", help="do not append the short cfg3 / cfg5 runs to the default line")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--chunk-policy", default="waves", choices=["waves", "greedy"],
                     help="waves = image-aligned chunks sized for the fc1 GEMM's wave quantisation (default); greedy = fill to the cap")
