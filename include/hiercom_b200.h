@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define HC_ABI_VERSION 1
+#define HC_ABI_VERSION 2
 
 #define HC_OK 0
 #define HC_E_SHAPE (-1) /* bad size / unsupported shape          */
@@ -154,6 +154,9 @@ typedef struct hc_gemm_desc {
   const int32_t* pair_row; /*                        per local pair: output row */
   void* scratch;           /* cta_pairs + HC_EPI_POOL_DIFF_BF16: bf16 [n_img, H/2, W/2, ldc] work map (the pair kernel leaves the pooled
                               values there by local pair, a second launch forms the differences); NULL = single-CTA kernel */
+  int32_t operand_f16;     /* 16-bit operand format: 0 = bf16 (default), 1 = IEEE fp16 - A, B, the 16-bit outputs ("BF16" epilogues
+                              then write fp16, saturating at +-65504) and the difference maps.  Same tensor-core rate
+                              (tcgen05 kind::f16); 3 more mantissa bits = 8x smaller operand rounding error.  Not with SPLIT3. */
 } hc_gemm_desc;
 
 int hc_tc_gemm(const hc_gemm_desc* desc, hc_stream_t stream);
@@ -220,7 +223,7 @@ int hc_cells_zero(const uint64_t* masks, int32_t rows_per_tile, int64_t n_rows, 
 /* [B,C0,hw] f32 (+ optional [B,C1,hw] f32) NCHW maps -> [B*hw, k_pad] bf16 pixel-major rows, zero padded
  * (the A operand of the 1x1 convolutions, model.py:139-140; also packs the legacy pre-masked [bs,257,32,32]). */
 int hc_pack_pixels(const float* src0, int32_t c0, const float* src1, int32_t c1, int32_t n_img, int32_t hw,
-                   int32_t k_pad, void* out_bf16, hc_stream_t stream);
+                   int32_t k_pad, void* out_bf16, int32_t operand_f16, hc_stream_t stream);
 
 /* R3: per-box masked conv1 activations.  tanh(conv1(x*mask)) == mask ? tanh(conv1(x)) : tanh(bias)
  * (train_test.py:391,398 + model.py:139-140).  t_img [n_img, fs*fs, C] bf16,
@@ -235,7 +238,7 @@ int hc_box_select(const void* t_img, const int32_t* boxes, const int32_t* box_im
  * instructions, HBM-bound instead of issue-bound. */
 int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub,
                       const int32_t* pair_obj, int32_t n_pairs, int32_t fs, int32_t channels, void* out,
-                      hc_stream_t stream);
+                      int32_t operand_f16, hc_stream_t stream);
 
 /* Same stage for pair lists produced by hc_pairs_enumerate, tiled as an outer sum over the boxes of an image: a
  * thread block keeps the U tiles of 4 subject boxes in registers and streams every object box's V tile once, so
@@ -247,7 +250,8 @@ int hc_pair_lut_build(const int32_t* pair_sub, const int32_t* pair_obj, const in
                       hc_stream_t stream);
 int hc_pair_relu_pool_tiled(const void* u, const void* v, const float* bias, const int32_t* box_offsets,
                             const int32_t* lut, int32_t n_max, int32_t img0, int32_t n_img, int32_t pair_base,
-                            int32_t chunk_pairs, int32_t fs, int32_t channels, const uint64_t* cover, void* out, hc_stream_t stream);
+                            int32_t chunk_pairs, int32_t fs, int32_t channels, const uint64_t* cover, void* out,
+                            int32_t operand_f16, hc_stream_t stream);
 
 /* Footprint-aware pooling: masks[p] = the 8x8-grid cells covered by the blocks hc_conv3_active_blocks (shared = 0) or
  * hc_conv3_shared_blocks (shared = 1) lists for pair p (same cover function).  Passed as `cover` (chunk-local, bias == NULL,

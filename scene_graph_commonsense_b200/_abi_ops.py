@@ -16,6 +16,17 @@ LAUNCHES = {"n": 0}
 PROFILE = {"on": False, "events": []}     # bench.py: CUDA-event timing of tagged launches on the launching stream
 
 
+ACT_DTYPES = (torch.bfloat16, torch.float16)       # 16-bit operand formats of the tensor-core path (bf16 default; fp16 opt-in)
+
+
+def _f16(*tensors):
+    """1 when the 16-bit operands are fp16, 0 for bf16; all given tensors must share one of the two formats."""
+    dts = {t.dtype for t in tensors if t is not None}
+    if len(dts) != 1 or next(iter(dts)) not in ACT_DTYPES:
+        raise RuntimeError("hiercom_b200: 16-bit operands must all be bf16 or all fp16, got %s" % sorted(str(d) for d in dts))
+    return 1 if next(iter(dts)) == torch.float16 else 0
+
+
 def _count(n=1):
     LAUNCHES["n"] += n
 
@@ -85,7 +96,7 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     require_cuda(a, b, out, bias, mul, blocks, n_blocks, k_masks, add_a, add_a_rows, add_b, add_b_rows, out_rows, diff_sub, diff_obj, diff_bg,
                  pair_sub, pair_obj, pair_row, scratch)
     for t, dt in ((k_masks, torch.int64), (add_a, torch.float32), (add_b, torch.float32), (add_a_rows, torch.int32), (add_b_rows, torch.int32),
-                  (out_rows, torch.int32), (diff_sub, torch.bfloat16), (diff_obj, torch.bfloat16), (diff_bg, torch.bfloat16),
+                  (out_rows, torch.int32), (diff_sub, a.dtype), (diff_obj, a.dtype), (diff_bg, a.dtype), (scratch, a.dtype),
                   (pair_sub, torch.int32), (pair_obj, torch.int32), (pair_row, torch.int32)):
         if t is not None and (t.dtype != dt or not t.is_contiguous()):
             raise RuntimeError("hiercom_b200: tc_gemm side operand must be a contiguous %s tensor" % dt)
@@ -107,6 +118,9 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     d.diff_sub, d.diff_obj, d.diff_bg = ptr(diff_sub), ptr(diff_obj), ptr(diff_bg)
     d.pair_sub, d.pair_obj, d.pair_row = ptr(pair_sub), ptr(pair_obj), ptr(pair_row)
     d.cta_pairs, d.scratch = int(cta_pairs), ptr(scratch)
+    d.operand_f16 = _f16(a, b)
+    if d.operand_f16 and epilogue in (EPI_BF16, EPI_POOL_BF16, EPI_POOL_DIFF_BF16) and out.dtype != torch.float16:
+        raise RuntimeError("hiercom_b200: fp16 operands write fp16 outputs")
     if scratch is not None and diff_sub is not None and scratch.numel() < n_img * (h // 2) * (w // 2) * d.ldc:
         raise RuntimeError("hiercom_b200: tc_gemm scratch must hold n_img pooled maps")
     with _timed(tag):
@@ -191,7 +205,7 @@ def p3_assemble(background, sub_maps, obj_maps, boxes, pair_sub, pair_obj, out, 
     n = pair_sub.numel()
     cell_map = 8 * 8 * 1024
     if (background.numel() != cell_map or sub_maps.numel() % cell_map or obj_maps.numel() != sub_maps.numel() or out.numel() < n * cell_map
-            or any(t.dtype != torch.bfloat16 or not t.is_contiguous() for t in (background, sub_maps, obj_maps, out))
+            or any(t.dtype != background.dtype or t.dtype not in ACT_DTYPES or not t.is_contiguous() for t in (background, sub_maps, obj_maps, out))
             or sub_maps.numel() // cell_map < boxes.shape[0]):
         raise RuntimeError("hiercom_b200: p3_assemble needs contiguous bf16 [*,8,8,1024] maps (one per box) and room for n_pairs rows")
     with _timed("p3_fill"):
@@ -213,8 +227,8 @@ def broadcast_rows(src, n_rows, out):
     return out
 
 
-def pack_pixels(src0, src1, k_pad, out=None):
-    """[B,C0,H,W] (+[B,C1,H,W]) f32 -> [B*H*W, k_pad] bf16."""
+def pack_pixels(src0, src1, k_pad, out=None, dtype=torch.bfloat16):
+    """[B,C0,H,W] (+[B,C1,H,W]) f32 -> [B*H*W, k_pad] in the 16-bit operand format `dtype` (bf16 / fp16)."""
     require_cuda(src0, src1)
     src0 = src0.contiguous()
     b, c0 = src0.shape[0], src0.shape[1]
@@ -224,8 +238,8 @@ def pack_pixels(src0, src1, k_pad, out=None):
         src1 = src1.contiguous()
         c1 = src1.shape[1]
     if out is None:
-        out = torch.empty(b * hw, k_pad, dtype=torch.bfloat16, device=src0.device)
-    check(_lib.load().hc_pack_pixels(ptr(src0), c0, ptr(src1), c1, b, hw, k_pad, ptr(out), stream_ptr()), "hc_pack_pixels")
+        out = torch.empty(b * hw, k_pad, dtype=dtype, device=src0.device)
+    check(_lib.load().hc_pack_pixels(ptr(src0), c0, ptr(src1), c1, b, hw, k_pad, ptr(out), _f16(out), stream_ptr()), "hc_pack_pixels")
     _count()
     return out
 
@@ -234,7 +248,8 @@ def box_select(t_img, boxes, box_img, fill, fs=32, out=None):
     require_cuda(t_img, boxes, box_img, fill)
     n_box, ch = boxes.shape[0], t_img.shape[-1]
     if out is None:
-        out = torch.empty(n_box, fs, fs, ch, dtype=torch.bfloat16, device=t_img.device)
+        out = torch.empty(n_box, fs, fs, ch, dtype=t_img.dtype, device=t_img.device)
+    _f16(t_img, fill, out)
     check(_lib.load().hc_box_select(ptr(t_img), ptr(boxes), ptr(box_img), n_box, fs, ch, ptr(fill), ptr(out), stream_ptr()),
           "hc_box_select")
     _count()
@@ -245,10 +260,10 @@ def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None):
     require_cuda(u, v, bias, pair_sub, pair_obj)
     n, ch = pair_sub.numel(), u.shape[-1]
     if out is None:
-        out = torch.empty(n, fs // 2, fs // 2, ch, dtype=torch.bfloat16, device=u.device)
+        out = torch.empty(n, fs // 2, fs // 2, ch, dtype=u.dtype, device=u.device)
     with _timed("pair_pool"):
         check(_lib.load().hc_pair_relu_pool(ptr(u), ptr(v), ptr(bias), ptr(pair_sub), ptr(pair_obj), n, fs, ch, ptr(out),
-                                            stream_ptr()), "hc_pair_relu_pool")
+                                            _f16(u, v, out), stream_ptr()), "hc_pair_relu_pool")
     _count()
     return out
 
@@ -282,10 +297,11 @@ def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, c
         raise RuntimeError("hiercom_b200: pair_relu_pool_tiled cover must be a contiguous int64 tensor with one word per pair of the chunk")
     ch = u.shape[-1]
     if out is None:
-        out = torch.empty(chunk_pairs, fs // 2, fs // 2, ch, dtype=torch.bfloat16, device=u.device)
+        out = torch.empty(chunk_pairs, fs // 2, fs // 2, ch, dtype=u.dtype, device=u.device)
     with _timed("pair_pool"):
         check(_lib.load().hc_pair_relu_pool_tiled(ptr(u), ptr(v), ptr(bias), ptr(box_offsets), ptr(lut), lut.shape[1], img0, n_img,
-                                                  pair_base, chunk_pairs, fs, ch, ptr(cover), ptr(out), stream_ptr()), "hc_pair_relu_pool_tiled")
+                                                  pair_base, chunk_pairs, fs, ch, ptr(cover), ptr(out), _f16(u, v, out), stream_ptr()),
+              "hc_pair_relu_pool_tiled")
     _count()
     return out
 

@@ -11,6 +11,7 @@ import torch
 from . import build as _build
 
 HC_OK = 0
+ABI_VERSION = 2        # include/hiercom_b200.h HC_ABI_VERSION
 ERRORS = {-1: "HC_E_SHAPE", -2: "HC_E_ALIGN", -3: "HC_E_ARCH", -4: "HC_E_CUDA", -5: "HC_E_NULL"}
 
 GEMM_PLAIN, GEMM_CONV3, GEMM_CONV3_BLOCKS = 0, 1, 2
@@ -31,7 +32,8 @@ class GemmDesc(C.Structure):
                 ("add_a", C.c_void_p), ("add_a_rows", C.c_void_p), ("add_b", C.c_void_p), ("add_b_rows", C.c_void_p), ("ld_add", C.c_int64),
                 ("out_rows", C.c_void_p),
                 ("diff_sub", C.c_void_p), ("diff_obj", C.c_void_p), ("diff_bg", C.c_void_p),
-                ("pair_sub", C.c_void_p), ("pair_obj", C.c_void_p), ("pair_row", C.c_void_p), ("scratch", C.c_void_p)]
+                ("pair_sub", C.c_void_p), ("pair_obj", C.c_void_p), ("pair_row", C.c_void_p), ("scratch", C.c_void_p),
+                ("operand_f16", C.c_int32)]
 
 
 class RelationWorkspace(C.Structure):
@@ -58,11 +60,11 @@ SIGNATURES = {
     "hc_pair_cell_keys": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P]),
     "hc_tile_cell_masks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "hc_cells_zero": (C.c_int, [_P, _I32, _I64, _I32, _I64, _P, _P]),
-    "hc_pack_pixels": (C.c_int, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "hc_pack_pixels": (C.c_int, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "hc_box_select": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
-    "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
+    "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _I32, _P]),
     "hc_pair_lut_build": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
-    "hc_pair_relu_pool_tiled": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "hc_pair_relu_pool_tiled": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
     "hc_pair_cover_masks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "hc_hier_head": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32,
                                _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
@@ -121,7 +123,7 @@ def load(build_if_missing=False):
         fn = getattr(lib, name)          # AttributeError here means the .so does not export the ABI
         fn.restype = res
         fn.argtypes = args
-    if lib.hc_abi_version() != 1:
+    if lib.hc_abi_version() != ABI_VERSION:
         raise RuntimeError("hiercom_b200: ABI version mismatch")
     _lib = lib
     return lib

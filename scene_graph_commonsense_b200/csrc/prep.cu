@@ -4,12 +4,14 @@
 //   pair_relu_pool  relu(U[sub] + V[obj] + b) + 2x2 max-pool per directed pair
 // All three are pure streaming kernels: 16-byte vector accesses, channel index fastest so a warp touches
 // 512 contiguous bytes.
+#include <cuda_fp16.h>
+
 #include "hc_common.cuh"
 
 namespace hc {
 
 __global__ void pack_pixels_kernel(const float* __restrict__ src0, int c0, const float* __restrict__ src1, int c1, int hw, int k_pad,
-                                   __nv_bfloat16* __restrict__ out) {
+                                   unsigned short* __restrict__ out, int f16) {
   __shared__ float tile[32][33];
   const int img = blockIdx.z;
   const int p0 = blockIdx.x * 32, ch0 = blockIdx.y * 32;
@@ -25,7 +27,13 @@ __global__ void pack_pixels_kernel(const float* __restrict__ src0, int c0, const
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int p = p0 + i, c = ch0 + threadIdx.x;
-    if (p < hw && c < k_pad) out[((size_t)img * hw + p) * k_pad + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    if (p < hw && c < k_pad) {
+      const float x = tile[threadIdx.x][i];
+      unsigned short bits;
+      if (f16) { __half h = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f)); bits = *reinterpret_cast<unsigned short*>(&h); }
+      else { __nv_bfloat16 b = __float2bfloat16_rn(x); bits = *reinterpret_cast<unsigned short*>(&b); }
+      out[((size_t)img * hw + p) * k_pad + c] = bits;
+    }
   }
 }
 
@@ -209,21 +217,35 @@ pair_relu_pool_tiled_kernel(const uint4* __restrict__ u, const uint4* __restrict
 // exact sum once, which is what rounding the fp32 sum of two bf16 values gives, and rounding commutes with max and relu:
 // the result equals the fp32 formulation bit for bit while issuing ~1/3 of the instructions (2 per two elements instead of
 // unpack + add + max + repack), which is what moves the kernel from issue-bound to HBM-bound.
+// F16 = the fp16 operand format (add.rn.f16x2 / max.f16x2): the same two packed instructions per two elements
+template <bool F16>
 __device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) {
+  if (F16) {
+    __half2 r = __hadd2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
   __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
+template <bool F16>
 __device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) {
+  if (F16) {
+    __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
   __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
   return *reinterpret_cast<uint32_t*>(&r);
 }
+template <bool F16>
 __device__ __forceinline__ uint4 bf8_add(uint4 a, uint4 b) {
-  return make_uint4(bf2_add(a.x, b.x), bf2_add(a.y, b.y), bf2_add(a.z, b.z), bf2_add(a.w, b.w));
+  return make_uint4(bf2_add<F16>(a.x, b.x), bf2_add<F16>(a.y, b.y), bf2_add<F16>(a.z, b.z), bf2_add<F16>(a.w, b.w));
 }
+template <bool F16>
 __device__ __forceinline__ uint4 bf8_max(uint4 a, uint4 b) {
-  return make_uint4(bf2_max(a.x, b.x), bf2_max(a.y, b.y), bf2_max(a.z, b.z), bf2_max(a.w, b.w));
+  return make_uint4(bf2_max<F16>(a.x, b.x), bf2_max<F16>(a.y, b.y), bf2_max<F16>(a.z, b.z), bf2_max<F16>(a.w, b.w));
 }
 
+template <bool F16>
 __global__ void pair_relu_pool_bf16_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const int* __restrict__ pair_sub,
                                            const int* __restrict__ pair_obj, long long total_vec, int fs, int cvec,
                                            uint4* __restrict__ out) {
@@ -239,12 +261,13 @@ __global__ void pair_relu_pool_bf16_kernel(const uint4* __restrict__ u, const ui
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const long long off = ((long long)(2 * py + (q >> 1)) * fs + (2 * px + (q & 1))) * cvec + cv;
-      acc = bf8_max(acc, bf8_add(__ldg(u + su * cvec + off), __ldg(v + so * cvec + off)));
+      acc = bf8_max<F16>(acc, bf8_add<F16>(__ldg(u + su * cvec + off), __ldg(v + so * cvec + off)));
     }
     out[i] = acc;
   }
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(128, 4)
 pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const int* __restrict__ box_off,
                                  const int* __restrict__ lut, int n_max, int img0, int pair_base, int chunk_pairs, int fs, int cvec,
@@ -308,7 +331,7 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
       if (prow[t] < 0) continue;                         // warp-uniform
       uint4 acc = make_uint4(0u, 0u, 0u, 0u);            // relu folded into the running max
 #pragma unroll
-      for (int q = 0; q < 4; ++q) acc = bf8_max(acc, bf8_add(ua[t][q], vq[q]));
+      for (int q = 0; q < 4; ++q) acc = bf8_max<F16>(acc, bf8_add<F16>(ua[t][q], vq[q]));
       __stcs(out + (long long)prow[t] * pair_stride + out_slot, acc);   // streamed: next read is conv3's TMA, after the chunk
     }
   }
@@ -325,7 +348,7 @@ static int stream_grid(long long total, int block) {
 }
 
 extern "C" int hc_pack_pixels(const float* src0, int32_t c0, const float* src1, int32_t c1, int32_t n_img, int32_t hw, int32_t k_pad,
-                              void* out_bf16, hc_stream_t stream_) {
+                              void* out_bf16, int32_t operand_f16, hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(src0 && out_bf16, HC_E_NULL, "hc_pack_pixels: NULL pointer");
   HC_REQUIRE(n_img > 0 && hw > 0 && c0 > 0 && c1 >= 0 && k_pad >= c0 + c1, HC_E_SHAPE, "hc_pack_pixels: bad sizes");
@@ -334,7 +357,7 @@ extern "C" int hc_pack_pixels(const float* src0, int32_t c0, const float* src1, 
   int rc = hc_device_check();
   if (rc != HC_OK) return rc;
   dim3 grid((hw + 31) / 32, (k_pad + 31) / 32, n_img), block(32, 8);
-  pack_pixels_kernel<<<grid, block, 0, stream>>>(src0, c0, src1, c1, hw, k_pad, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  pack_pixels_kernel<<<grid, block, 0, stream>>>(src0, c0, src1, c1, hw, k_pad, reinterpret_cast<unsigned short*>(out_bf16), operand_f16 ? 1 : 0);
   return cuda_status("hc_pack_pixels");
 }
 
@@ -354,18 +377,24 @@ extern "C" int hc_box_select(const void* t_img, const int32_t* boxes, const int3
 }
 
 extern "C" int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub, const int32_t* pair_obj,
-                                 int32_t n_pairs, int32_t fs, int32_t channels, void* out, hc_stream_t stream_) {
+                                 int32_t n_pairs, int32_t fs, int32_t channels, void* out, int32_t operand_f16, hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(u && v && pair_sub && pair_obj && out, HC_E_NULL, "hc_pair_relu_pool: NULL pointer");
+  HC_REQUIRE(!operand_f16 || !bias, HC_E_SHAPE, "hc_pair_relu_pool: fp16 operands take the packed path (bias == NULL)");
   HC_REQUIRE(n_pairs > 0 && fs > 0 && fs % 2 == 0 && channels % 8 == 0, HC_E_SHAPE, "hc_pair_relu_pool: bad sizes");
   HC_REQUIRE(aligned16(u) && aligned16(v) && aligned16(out), HC_E_ALIGN, "hc_pair_relu_pool: 16-byte alignment");
   int rc = hc_device_check();
   if (rc != HC_OK) return rc;
   long long total = (long long)n_pairs * (fs / 2) * (fs / 2) * (channels / 8);
   if (!bias) {
-    pair_relu_pool_bf16_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
-                                                                            pair_sub, pair_obj, total, fs, channels / 8,
-                                                                            reinterpret_cast<uint4*>(out));
+    if (operand_f16)
+      pair_relu_pool_bf16_kernel<true><<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
+                                                                                    pair_sub, pair_obj, total, fs, channels / 8,
+                                                                                    reinterpret_cast<uint4*>(out));
+    else
+      pair_relu_pool_bf16_kernel<false><<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
+                                                                                     pair_sub, pair_obj, total, fs, channels / 8,
+                                                                                     reinterpret_cast<uint4*>(out));
     return cuda_status("hc_pair_relu_pool");
   }
   pair_relu_pool_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
@@ -388,9 +417,10 @@ extern "C" int hc_pair_lut_build(const int32_t* pair_sub, const int32_t* pair_ob
 
 extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float* bias, const int32_t* box_offsets, const int32_t* lut,
                                        int32_t n_max, int32_t img0, int32_t n_img, int32_t pair_base, int32_t chunk_pairs, int32_t fs,
-                                       int32_t channels, const uint64_t* cover, void* out, hc_stream_t stream_) {
+                                       int32_t channels, const uint64_t* cover, void* out, int32_t operand_f16, hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(u && v && box_offsets && lut && out, HC_E_NULL, "hc_pair_relu_pool_tiled: NULL pointer");
+  HC_REQUIRE(!operand_f16 || !bias, HC_E_SHAPE, "hc_pair_relu_pool_tiled: fp16 operands take the packed path (bias == NULL)");
   HC_REQUIRE(n_img > 0 && n_img <= 65535 && n_max > 0 && chunk_pairs > 0 && fs > 0 && fs % 2 == 0 && channels % 8 == 0, HC_E_SHAPE,
              "hc_pair_relu_pool_tiled: bad sizes");
   HC_REQUIRE(aligned16(u) && aligned16(v) && aligned16(out), HC_E_ALIGN, "hc_pair_relu_pool_tiled: 16-byte alignment");
@@ -402,9 +432,14 @@ extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float
   HC_REQUIRE(!cover || fs == 32, HC_E_SHAPE, "hc_pair_relu_pool_tiled: the footprint cover is defined on the 8x8 cell grid of feature_size 32");
   dim3 grid(slots / 128, (n_max + PP_TA - 1) / PP_TA, n_img);
   if (!bias) {
-    pair_relu_pool_tiled_bf16_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
-                                                               box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec,
-                                                               reinterpret_cast<const unsigned long long*>(cover), reinterpret_cast<uint4*>(out));
+    if (operand_f16)
+      pair_relu_pool_tiled_bf16_kernel<true><<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
+                                                                       box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec,
+                                                                       reinterpret_cast<const unsigned long long*>(cover), reinterpret_cast<uint4*>(out));
+    else
+      pair_relu_pool_tiled_bf16_kernel<false><<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
+                                                                        box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec,
+                                                                        reinterpret_cast<const unsigned long long*>(cover), reinterpret_cast<uint4*>(out));
     return cuda_status("hc_pair_relu_pool_tiled");
   }
   HC_REQUIRE(!cover, HC_E_SHAPE, "hc_pair_relu_pool_tiled: the footprint cover needs the packed path (bias == NULL)");

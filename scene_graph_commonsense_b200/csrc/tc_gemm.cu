@@ -21,6 +21,7 @@
 //
 // CTA tile = (MS*128) x BN: MS 128-row sub-tiles share every B stage (halves L2->smem weight traffic for MS=2).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "hc_common.cuh"
@@ -93,6 +94,7 @@ struct Params {
   // HC_EPI_POOL_DIFF_BF16 (block mode): out[pair_row[pair]] = (x - diff_sub[pair_sub[pair]]) - (diff_obj[pair_obj[pair]] - diff_bg)
   const __nv_bfloat16* diff_sub; const __nv_bfloat16* diff_obj; const __nv_bfloat16* diff_bg;
   const int* pair_sub; const int* pair_obj; const int* pair_row;
+  int f16;                       // operand format: 0 = bf16 (default), 1 = IEEE fp16 (A, B, 16-bit outputs and the difference maps)
   int dbg;                       // TIMING EXPERIMENTS ONLY (HC_TC_DEBUG, block mode; results are garbage): 1 = skip the A boxes, 2 = skip
                                  // the weight tile, 4 = skip the MMAs - splits a stage's time into its TMA and tensor-core parts
 };
@@ -181,8 +183,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 
 // cute::UMMA::InstrDescriptor for kind::f16: D=f32, A=B=bf16, both K-major, M=128 (256 across a cta_group::2 pair), N=BN
 template <int BN>
-__device__ __forceinline__ uint32_t umma_idesc(int m = BM) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+__device__ __forceinline__ uint32_t umma_idesc(int m = BM, int f16 = 0) {
+  const uint32_t fmt = f16 ? 0u : 1u;        // A / B format field: 0 = F16, 1 = BF16
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -234,6 +237,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 16-bit operand format of the launch: bf16, or fp16 with saturation (fp16 has 3 more mantissa bits - 8x smaller rounding error -
+// but overflows at 65504: values beyond it are clamped to the largest finite number instead of becoming inf)
+constexpr float F16_MAX = 65504.0f;
+__device__ __forceinline__ uint32_t pack16(float lo, float hi, int f16) {
+  if (f16) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -F16_MAX), F16_MAX), fminf(fmaxf(hi, -F16_MAX), F16_MAX));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  return pack_bf16(lo, hi);
+}
+__device__ __forceinline__ float2 unpack16(uint32_t w, int f16) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+__device__ __forceinline__ unsigned short cvt16(float x, int f16) {
+  if (f16) { __half h = __float2half_rn(fminf(fmaxf(x, -F16_MAX), F16_MAX)); return *reinterpret_cast<unsigned short*>(&h); }
+  __nv_bfloat16 b = __float2bfloat16_rn(x);
+  return *reinterpret_cast<unsigned short*>(&b);
+}
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == HC_ACT_RELU) return fmaxf(x, 0.0f);
@@ -244,7 +266,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // bias + activation (+ elementwise multiplier) on one lane's 32 accumulator columns -> 64 bytes of bf16
 template <int ACT>
 __device__ __forceinline__ void store_bf16_row(const uint32_t (&r)[32], const float* __restrict__ bias, const float* __restrict__ mul,
-                                               __nv_bfloat16* __restrict__ dst) {
+                                               __nv_bfloat16* __restrict__ dst, int f16) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float v[8];
@@ -263,8 +285,8 @@ __device__ __forceinline__ void store_bf16_row(const uint32_t (&r)[32], const fl
       const float4 m0 = __ldg(reinterpret_cast<const float4*>(mul) + 2 * i), m1 = __ldg(reinterpret_cast<const float4*>(mul) + 2 * i + 1);
       v[0] *= m0.x; v[1] *= m0.y; v[2] *= m0.z; v[3] *= m0.w; v[4] *= m1.x; v[5] *= m1.y; v[6] *= m1.z; v[7] *= m1.w;
     }
-    *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]),
-                                                        pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dst + 8 * i) = make_uint4(pack16(v[0], v[1], f16), pack16(v[2], v[3], f16), pack16(v[4], v[5], f16),
+                                                        pack16(v[6], v[7], f16));
   }
 }
 
@@ -459,7 +481,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (!CG2 && lane == 0 && p.patch) {      // (pair kernels are block-mode only: every tcgen05 op of a kernel uses one cta_group)
-      const uint32_t idesc = umma_idesc<BN>();
+      const uint32_t idesc = umma_idesc<BN>(BM, p.f16);
       int a_slot = 0, b_slot = 0, acc = 0;
       uint32_t a_phase = 0, b_phase = 0, acc_phase = 0;
       const int n_ax = (p.c_in / BK) * 3;                 // (channel block, kx) steps per tile
@@ -494,7 +516,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     } else if (lane == 0 && rank == 0) {               // pair: only the leader CTA issues (its MMAs run on both SMs)
-      const uint32_t idesc = umma_idesc<BN>(CG2 ? 2 * BM : BM);
+      const uint32_t idesc = umma_idesc<BN>(CG2 ? 2 * BM : BM, p.f16);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -578,9 +600,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 const int i0 = 16 * hb + 8 * (c >> 1) + 2 * (c & 1);
                 const float m = fmaxf(fmaxf(__uint_as_float(r[i0]), __uint_as_float(r[i0 + 1])),
                                       fmaxf(__uint_as_float(r[i0 + 4]), __uint_as_float(r[i0 + 5])));
-                const __nv_bfloat16 x = __float2bfloat16_rn(fmaxf(m + bias, 0.0f));
+                const unsigned short x = cvt16(fmaxf(m + bias, 0.0f), p.f16);
                 const long long off = ((long long)(cy0 + (c >> 1)) * (p.W / 2) + (cx0 + (c & 1))) * p.ldc + p.c_off + cout;
-                reinterpret_cast<__nv_bfloat16*>(p.out)[out_base + off] = x;
+                reinterpret_cast<unsigned short*>(p.out)[out_base + off] = x;
               }
             }
           }
@@ -645,7 +667,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int i = 0; i < 4; ++i) {
               float a = fmaxf(o[2 * i] + __ldg(p.bias + cbase + 2 * i), 0.0f);
               float b = fmaxf(o[2 * i + 1] + __ldg(p.bias + cbase + 2 * i + 1), 0.0f);
-              w[i] = pack_bf16(a, b);
+              w[i] = pack16(a, b, p.f16);
             }
             int py = (t_y0 + 8 * j) / 2 + q;                            // pooled row
             int px = t_x0 / 2 + ((lane & 15) >> 1);                     // pooled col
@@ -674,11 +696,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               const uint32_t sv[4] = {S.x, S.y, S.z, S.w}, ov[4] = {O.x, O.y, O.z, O.w}, gv[4] = {G.x, G.y, G.z, G.w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
-                const float2 sf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sv[i]));
-                const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ov[i]));
-                const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gv[i]));
-                w[i] = pack_bf16(__fsub_rn(__fsub_rn(xf.x, sf.x), __fsub_rn(of.x, gf.x)), __fsub_rn(__fsub_rn(xf.y, sf.y), __fsub_rn(of.y, gf.y)));
+                const float2 xf = unpack16(w[i], p.f16), sf = unpack16(sv[i], p.f16), of = unpack16(ov[i], p.f16), gf = unpack16(gv[i], p.f16);
+                w[i] = pack16(__fsub_rn(__fsub_rn(xf.x, sf.x), __fsub_rn(of.x, gf.x)), __fsub_rn(__fsub_rn(xf.y, sf.y), __fsub_rn(of.y, gf.y)), p.f16);
               }
               __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)__ldg(p.pair_row + o_img) * map_elems + cell_off;
               *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -778,9 +797,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                 }
                 // the activation switch is hoisted out of the element loops (a branch per element serialises the
                 // single epilogue warp of each scheduler)
-                if (p.act == HC_ACT_RELU) store_bf16_row<HC_ACT_RELU>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst);
-                else if (p.act == HC_ACT_TANH) store_bf16_row<HC_ACT_TANH>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst);
-                else store_bf16_row<HC_ACT_NONE>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst);
+                if (p.act == HC_ACT_RELU) store_bf16_row<HC_ACT_RELU>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst, p.f16);
+                else if (p.act == HC_ACT_TANH) store_bf16_row<HC_ACT_TANH>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst, p.f16);
+                else store_bf16_row<HC_ACT_NONE>(r, p.bias ? p.bias + col0 : nullptr, mul_row, dst, p.f16);
               }
             }
           }
@@ -810,7 +829,7 @@ __global__ void __launch_bounds__(256)
 pair_diff_kernel(const int* __restrict__ blocks, const int* __restrict__ n_blocks_p, const uint4* __restrict__ scratch,
                  const uint4* __restrict__ diff_sub, const uint4* __restrict__ diff_obj, const uint4* __restrict__ diff_bg,
                  const int* __restrict__ pair_sub, const int* __restrict__ pair_obj, const int* __restrict__ pair_row, int cells_w,
-                 int cells_h, int map_w, long long cell_vec, long long map_vec, uint4* __restrict__ out) {
+                 int cells_h, int map_w, long long cell_vec, long long map_vec, uint4* __restrict__ out, int f16) {
   const int n_blocks = __ldg(n_blocks_p);
   const int per_block = cells_w * cells_h * (int)cell_vec;          // 16-byte vectors per block
   const long long total = (long long)n_blocks * per_block;
@@ -828,11 +847,8 @@ pair_diff_kernel(const int* __restrict__ blocks, const int* __restrict__ n_block
     uint32_t w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const float2 xf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xv[k]));
-      const float2 sf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&sv[k]));
-      const float2 of = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ov[k]));
-      const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gv[k]));
-      w[k] = pack_bf16(__fsub_rn(__fsub_rn(xf.x, sf.x), __fsub_rn(of.x, gf.x)), __fsub_rn(__fsub_rn(xf.y, sf.y), __fsub_rn(of.y, gf.y)));
+      const float2 xf = unpack16(xv[k], f16), sf = unpack16(sv[k], f16), of = unpack16(ov[k], f16), gf = unpack16(gv[k], f16);
+      w[k] = pack16(__fsub_rn(__fsub_rn(xf.x, sf.x), __fsub_rn(of.x, gf.x)), __fsub_rn(__fsub_rn(xf.y, sf.y), __fsub_rn(of.y, gf.y)), f16);
     }
     out[(long long)__ldg(pair_row + pair) * map_vec + off] = make_uint4(w[0], w[1], w[2], w[3]);
   }
@@ -856,11 +872,11 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                    const cuuint32_t* box) {
+                    const cuuint32_t* box, int f16 = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(HC_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -954,6 +970,8 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   p.mode = d->mode; p.epi = d->epilogue; p.act = d->act;
   p.ldc = d->ldc; p.c_off = d->c_off; p.bias = d->bias; p.out = d->out;
   p.mul = d->mul; p.ld_mul = d->ld_mul;
+  p.f16 = d->operand_f16 ? 1 : 0;
+  HC_REQUIRE(!p.f16 || d->epilogue != HC_EPI_SPLIT3_BF16, HC_E_SHAPE, "hc_tc_gemm: the bf16x3 split epilogue is bf16-only");
   p.patch = d->mode == HC_GEMM_CONV3 ? 1 : 0;
   p.blocks = d->blocks; p.n_blocks = d->n_blocks; p.blk_h = d->block_rows; p.blk_w = blk_w;
   p.k_masks = reinterpret_cast<const unsigned long long*>(d->k_masks); p.k_cell_kb = d->k_masks ? (int)(d->k_cell / tc::BK) : 0;
@@ -971,10 +989,10 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     cuuint64_t dims[2] = {(cuuint64_t)d->k, (cuuint64_t)d->n};
     cuuint64_t str[1] = {(cuuint64_t)d->k * 2};
     cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)BN};
-    rc = tc::make_map(&tb, d->b, 2, dims, str, box);
+    rc = tc::make_map(&tb, d->b, 2, dims, str, box, d->operand_f16 ? 1 : 0);
     if (rc != HC_OK) return rc;
     box[1] = (cuuint32_t)(BN / 2);            // half tile: what one CTA of a pair multicasts
-    rc = tc::make_map(&tbh, d->b, 2, dims, str, box);
+    rc = tc::make_map(&tbh, d->b, 2, dims, str, box, d->operand_f16 ? 1 : 0);
     if (rc != HC_OK) return rc;
   }
   const bool blk = d->mode == HC_GEMM_CONV3_BLOCKS;
@@ -995,7 +1013,7 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     cuuint64_t str[3] = {(cuuint64_t)d->c_total * 2, (cuuint64_t)d->w * d->c_total * 2, (cuuint64_t)d->h * d->w * d->c_total * 2};
     // dense: one patch serves the three ky taps; block mode: one {64 ch, block_cols x, block_rows y} box per block and tap
     cuuint32_t box[4] = {(cuuint32_t)tc::BK, blk ? (cuuint32_t)blk_w : 16u, (cuuint32_t)(blk ? d->block_rows : 8 * MS + 2), 1};
-    rc = tc::make_map(&ta, d->a, 4, dims, str, box);
+    rc = tc::make_map(&ta, d->a, 4, dims, str, box, d->operand_f16 ? 1 : 0);
     if (rc != HC_OK) return rc;
   } else {
     HC_REQUIRE(d->mode == HC_GEMM_PLAIN, HC_E_SHAPE, "hc_tc_gemm: unknown mode");
@@ -1004,7 +1022,7 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     cuuint64_t dims[2] = {(cuuint64_t)d->k, (cuuint64_t)d->m};
     cuuint64_t str[1] = {(cuuint64_t)d->lda * 2};
     cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BM};
-    rc = tc::make_map(&ta, d->a, 2, dims, str, box);
+    rc = tc::make_map(&ta, d->a, 2, dims, str, box, d->operand_f16 ? 1 : 0);
     if (rc != HC_OK) return rc;
   }
   p.group_m = d->group_m > 0 ? d->group_m : 1;
@@ -1032,7 +1050,7 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
     tc::pair_diff_kernel<<<num_sms() * 8, 256, 0, stream>>>(
         d->blocks, d->n_blocks, reinterpret_cast<const uint4*>(d->scratch), reinterpret_cast<const uint4*>(d->diff_sub),
         reinterpret_cast<const uint4*>(d->diff_obj), reinterpret_cast<const uint4*>(d->diff_bg), d->pair_sub, d->pair_obj, d->pair_row,
-        blk_w / 2, d->block_rows / 2, d->w / 2, cell_vec, map_vec, reinterpret_cast<uint4*>(d->out));
+        blk_w / 2, d->block_rows / 2, d->w / 2, cell_vec, map_vec, reinterpret_cast<uint4*>(d->out), p.f16);
     return cuda_status("pair_diff_kernel launch");
   }
   if (BN == 256 && MS == 1) return tc::launch<256, 1, false>(ta, tb, tbh, p, stream);

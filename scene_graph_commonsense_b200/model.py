@@ -54,13 +54,23 @@ class PackedHead:
     heads                  -> w_heads f32 [G+P+S+1+3, 512] = [fc3_1; fc3_2; fc3_3; fc4; fc5] (flat: [fc3; fc4])
     """
 
-    def __init__(self, sd, device, flat=False):
+    def __init__(self, sd, device, flat=False, operand_dtype=torch.bfloat16):
+        """operand_dtype: the 16-bit format of every tensor-core operand and stored activation - torch.bfloat16 (default, north_star's
+        "bf16 in, fp32 accumulate") or torch.float16 (same tcgen05 kind::f16 rate, 3 more mantissa bits = 8x smaller operand
+        rounding error; stores saturate at +-65504 and weights are range-checked here)."""
         sd = strip_module_prefix(sd)
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("hiercom_b200: the relation head runs on CUDA only")
+        if operand_dtype not in (torch.bfloat16, torch.float16):
+            raise ValueError("operand_dtype must be torch.bfloat16 or torch.float16")
+        self.act_dtype = operand_dtype
         f32 = lambda t: t.detach().to(dev, torch.float32)
-        bf = lambda t: t.to(torch.bfloat16).contiguous()
+
+        def bf(t):
+            if operand_dtype == torch.float16 and float(t.abs().max()) > 6.0e4:
+                raise RuntimeError("hiercom_b200: a weight exceeds the fp16 range - use operand_dtype=torch.bfloat16 for this checkpoint")
+            return t.to(operand_dtype).contiguous()
         c = sd["conv1_1.weight"].shape[0]
         if c != 128 or sd["fc1.weight"].shape[1] != 65536:
             raise RuntimeError("hiercom_b200: kernels are built for hidden_dim=128, feature_size=32 (config.yaml:30,35)")
@@ -109,8 +119,8 @@ class PackedHead:
         (subject channels 0-127, object 128-255) -> U, V [n,32,32,512] bf16.  The conv2 bias rides on the object half (added in
         fp32 before the one rounding to bf16), so the pair stage is relu(maxpool(U[s] + V[o])) on packed bf16."""
         n_box, fs = abox.shape[0], abox.shape[1]
-        u = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device)
-        v = torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device)
+        u = torch.empty(n_box, fs, fs, 512, dtype=self.act_dtype, device=abox.device)
+        v = torch.empty(n_box, fs, fs, 512, dtype=self.act_dtype, device=abox.device)
         for out, w, base, bias in ((u, self.w2s, 0, None), (v, self.w2o, 128, self.b2)):
             ops.tc_gemm(abox, w, out, n_box * fs * fs, 512, 9 * 128, bias=bias, ldc=512, mode=GEMM_CONV3, epilogue=EPI_BF16, act=ACT_NONE,
                         n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=m_sub, tag="conv2_half")
@@ -130,8 +140,8 @@ class PackedHead:
         8 x block_rows-pixel blocks within one pixel of each box (`ops.conv2_box_blocks`); bit-identical to the dense halves."""
         n_box, fs = abox.shape[0], abox.shape[1]
         u_bg, v_bg = self.uv_background()
-        u = ops.broadcast_rows(u_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device))
-        v = ops.broadcast_rows(v_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=torch.bfloat16, device=abox.device))
+        u = ops.broadcast_rows(u_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=self.act_dtype, device=abox.device))
+        v = ops.broadcast_rows(v_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=self.act_dtype, device=abox.device))
         blocks, n_blocks = ops.conv2_box_blocks(boxes, block_rows, fs)
         self.last_conv2_blocks = (n_blocks, block_rows, n_box)      # device count: bench.py reads it after the timed region
         for out, w, base, bias in ((u, self.w2s, 0, None), (v, self.w2o, 128, self.b2)):
@@ -149,7 +159,7 @@ class PackedHead:
             u, v = self.uv_background()
             zero = torch.zeros(1, dtype=torch.int32, device=self.device)
             p2 = ops.pair_relu_pool(u, v, None, zero, zero, fs)
-            p3 = torch.empty(1, 8, 8, 1024, dtype=torch.bfloat16, device=self.device)
+            p3 = torch.empty(1, 8, 8, 1024, dtype=self.act_dtype, device=self.device)
             ops.tc_gemm(p2, self.w3, p3, 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
                         n_img=1, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=2, tag="conv3_bg")
             self._p3_bg = p3
@@ -168,7 +178,7 @@ class PackedHead:
         reused by every launch: launches on one stream are ordered)."""
         cur = getattr(self, "_pair_scratch", None)
         if cur is None or cur.shape[0] < n:
-            self._pair_scratch = cur = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=self.w3.device)
+            self._pair_scratch = cur = torch.empty(n, 8, 8, 1024, dtype=self.act_dtype, device=self.w3.device)
         return cur
 
     def conv3_diff(self, p2, d, n, blocks, n_blocks, block_rows, sub_maps, obj_maps, pair_sub, pair_obj, pair_row, m_sub=2, tag="conv3",
@@ -193,7 +203,7 @@ class PackedHead:
     def fc1_shared_fc2(self, d, n, k_masks, f_sub, f_obj, row_sub, row_obj, bias_eff, out_rows, raw, group_m=None):
         """model.py:149,175 on the difference operand d [n,8,8,1024] (rows in sorted order, zero outside the cells both boxes reach):
         h1 = relu(d @ W1^T [only the cells in the tile's mask] + f_sub[row_sub] + f_obj[row_obj] + bias_eff), raw[out_rows] = h1 @ W2^T."""
-        h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=d.device)
+        h1 = torch.empty(n, 4096, dtype=self.act_dtype, device=d.device)
         # rasterisation: a band of 9 M tiles x all 16 N tiles = 144 CTAs run together.  The rows are sorted by cell rectangle, so the
         # 9 tiles walk (nearly) the same K cells in step: each weight panel and each operand tile comes out of HBM once per band
         # and is shared through L2 (bands of 37 x 4 re-read the operand 4x and thrashed L2: 38.9 GB of DRAM reads per launch, ncu r01y)
@@ -211,14 +221,14 @@ class PackedHead:
         n = p2.shape[0] if n is None else n
         dev = p2.device
         if blocks is None:
-            p3 = torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev)
+            p3 = torch.empty(n, 8, 8, 1024, dtype=self.act_dtype, device=dev)
             ops.tc_gemm(p2, self.w3, p3, n * 256, 1024, 9 * 512, bias=self.b3, ldc=1024, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
                         n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag="conv3")
         else:
             if p3 is None:
-                p3 = ops.broadcast_rows(self.p3_background(), n, torch.empty(n, 8, 8, 1024, dtype=torch.bfloat16, device=dev))
+                p3 = ops.broadcast_rows(self.p3_background(), n, torch.empty(n, 8, 8, 1024, dtype=self.act_dtype, device=dev))
             self.conv3_blocks(p2, p3, n, blocks, n_blocks, block_rows, m_sub=m_sub, block_cols=block_cols)
-        h1 = torch.empty(n, 4096, dtype=torch.bfloat16, device=dev)
+        h1 = torch.empty(n, 4096, dtype=self.act_dtype, device=dev)
         ops.tc_gemm(p3, self.w_fc1, h1, n, 4096, 65536, bias=self.b_fc1, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU,
                     group_m=37, m_sub=2 if n > 128 else 1, tag="fc1")
         if raw is None:
@@ -230,12 +240,12 @@ class PackedHead:
         """model.py:138-150 on pre-masked [bs,257,32,32] inputs -> fc2 pre-activation of the feature part [bs,512]."""
         bs = h_sub.shape[0]
         dev = h_sub.device
-        a = torch.empty(bs, 32, 32, 256, dtype=torch.bfloat16, device=dev)
+        a = torch.empty(bs, 32, 32, 256, dtype=self.act_dtype, device=dev)
         for role, h in enumerate((h_sub, h_obj)):
-            x = ops.pack_pixels(h.to(torch.float32), None, K1_PAD)
+            x = ops.pack_pixels(h.to(torch.float32), None, K1_PAD, dtype=self.act_dtype)
             ops.tc_gemm(x, self.w1[128 * role:128 * (role + 1)], a, bs * 1024, 128, K1_PAD, bias=self.b1[128 * role:128 * (role + 1)],
                         lda=K1_PAD, ldc=256, c_off=128 * role, epilogue=EPI_BF16, act=ACT_TANH)
-        p2 = torch.empty(bs, 16, 16, 512, dtype=torch.bfloat16, device=dev)
+        p2 = torch.empty(bs, 16, 16, 512, dtype=self.act_dtype, device=dev)
         ops.tc_gemm(a, self.w2, p2, bs * 1024, 512, 9 * 256, bias=self.b2, ldc=512, mode=GEMM_CONV3, epilogue=EPI_POOL_BF16,
                     n_img=bs, h=32, w=32, c_total=256, c_base=0, c_in=256, group_m=1, m_sub=2)
         return self.conv3_fc(p2)

@@ -182,15 +182,15 @@ def broadcast_rows(src, n_rows, out):
 
 
 # ------------------------------------------------------------------------------------------------ R3 gather / pooling producers
-@_op("pack_pixels", "(Tensor src0, Tensor? src1, int k_pad) -> Tensor")
-def _pack_pixels(src0, src1, k_pad):
-    return _A.pack_pixels(src0, src1, k_pad)
+@_op("pack_pixels", "(Tensor src0, Tensor? src1, int k_pad, bool f16) -> Tensor")
+def _pack_pixels(src0, src1, k_pad, f16):
+    return _A.pack_pixels(src0, src1, k_pad, dtype=torch.float16 if f16 else torch.bfloat16)
 
 
-def pack_pixels(src0, src1, k_pad, out=None):
+def pack_pixels(src0, src1, k_pad, out=None, dtype=torch.bfloat16):
     if out is not None:
         raise RuntimeError("hiercom_b200: pack_pixels allocates its result")
-    return _call("pack_pixels")(src0, src1, k_pad)
+    return _call("pack_pixels")(src0, src1, k_pad, dtype == torch.float16)
 
 
 @_op("box_select", "(Tensor t_img, Tensor boxes, Tensor box_img, Tensor fill, int fs) -> Tensor")
@@ -211,7 +211,7 @@ def _pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs, out):
 
 def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None):
     if out is None:
-        out = torch.empty(pair_sub.numel(), fs // 2, fs // 2, u.shape[-1], dtype=torch.bfloat16, device=u.device)
+        out = torch.empty(pair_sub.numel(), fs // 2, fs // 2, u.shape[-1], dtype=u.dtype, device=u.device)
     _call("pair_relu_pool")(u, v, bias, pair_sub, pair_obj, fs, out)
     return out
 
@@ -248,7 +248,7 @@ def _pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, 
 def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None, cover=None):
     """`cover` (int64 per pair of the chunk, `pair_cover_masks`): write only the pooled pixels a listed conv3_1 block reads."""
     if out is None:
-        out = torch.empty(chunk_pairs, fs // 2, fs // 2, u.shape[-1], dtype=torch.bfloat16, device=u.device)
+        out = torch.empty(chunk_pairs, fs // 2, fs // 2, u.shape[-1], dtype=u.dtype, device=u.device)
     _call("pair_relu_pool_tiled")(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out, cover)
     return out
 

@@ -50,6 +50,7 @@ class DeviceBatch:
     conf: Optional[torch.Tensor] = None        # f32 [nbox] object-label confidences
     box_offsets_host: Optional[np.ndarray] = None
     gt: Optional[dict] = None                  # flat GT triplet tables (targets.flat_targets_sgd)
+    cover_fraction: Optional[float] = None     # host estimate: share of the conv3_1 pixels the shared-footprint work lists would visit
 
     @property
     def n_images(self):
@@ -81,7 +82,38 @@ class HostBatch:
         return DeviceBatch(d.get("feat"), d.get("depth"), d["boxes"], d["box_offsets"], d["box_img"], d["cats"], d["supers"],
                            d["tri_offsets"], d.get("rel_tri"), d.get("dir_tri"), d.get("group_id"), m["n_groups"], m["max_tri"],
                            m["p_max"], self.h2d_bytes, conf=d.get("conf"), gt=gt,
-                           box_offsets_host=self.t["box_offsets"].numpy())
+                           box_offsets_host=self.t["box_offsets"].numpy(), cover_fraction=m.get("cover_fraction"))
+
+
+def _cell_interval(lo, hi):
+    """Host twin of `active_cells` (csrc/blocks.cu): the pooled conv3_1 cells (8 per axis) a box interval [lo, hi) of the 32-grid reaches."""
+    qlo, qhi = np.maximum(0, (lo - 1) >> 1), np.minimum(15, hi >> 1)
+    qlo, qhi = np.maximum(0, qlo - 1), np.minimum(15, qhi + 1)
+    return qlo >> 1, (qhi >> 1) + 1
+
+
+def footprint_cover_fraction(boxes, box_offsets, fs=32):
+    """Host only (numpy, at batch-build time): the share of the dense conv3_1 pixels that the shared-footprint work lists of this
+    window would visit - per ordered pair of an image, the cell rectangle BOTH boxes reach covered by 2 x 2-cell blocks
+    (ceil(w/2) * ceil(h/2) blocks of 4 of the 64 cells).  Ignores the overlap skip rule (an upper bound on the pairs).  It only
+    steers a scheduling decision (`RelationPipeline.dense_above`): both formulations give the same scores."""
+    b = np.clip(np.asarray(boxes, dtype=np.int64), 0, fs)
+    empty = (b[:, 1] <= b[:, 0]) | (b[:, 3] <= b[:, 2])
+    xa, xb = _cell_interval(b[:, 0], b[:, 1])
+    ya, yb = _cell_interval(b[:, 2], b[:, 3])
+    xa, xb, ya, yb = (np.where(empty, 0, v) for v in (xa, xb, ya, yb))
+    blocks = pairs = 0
+    for i in range(len(box_offsets) - 1):
+        s, e = int(box_offsets[i]), int(box_offsets[i + 1])
+        n = e - s
+        if n < 2:
+            continue
+        w = np.maximum(0, np.minimum(xb[s:e, None], xb[None, s:e]) - np.maximum(xa[s:e, None], xa[None, s:e]))
+        h = np.maximum(0, np.minimum(yb[s:e, None], yb[None, s:e]) - np.maximum(ya[s:e, None], ya[None, s:e]))
+        t = ((w + 1) >> 1) * ((h + 1) >> 1)
+        blocks += int(t.sum() - np.trace(t))
+        pairs += n * (n - 1)
+    return blocks * 4.0 / (64.0 * pairs) if pairs else 0.0
 
 
 def host_batch_from_samples(samples, skip_mode="batch", group_size=None, sgdet=False, pinned=True, with_maps=True):
@@ -128,7 +160,8 @@ def host_batch_from_samples(samples, skip_mode="batch", group_size=None, sgdet=F
         from .targets import flat_targets_sgd
         for k, v in flat_targets_sgd(samples).items():
             arrays["gt_" + k] = v
-    meta = dict(n_groups=n_groups, max_tri=int(tri.max()) if len(tri) else 0, p_max=int((counts * (counts - 1)).sum()))
+    meta = dict(n_groups=n_groups, max_tri=int(tri.max()) if len(tri) else 0, p_max=int((counts * (counts - 1)).sum()),
+                cover_fraction=footprint_cover_fraction(arrays["boxes"], arrays["box_offsets"]))
     return HostBatch(arrays, meta, pinned)
 
 
@@ -142,8 +175,14 @@ class RelationPipeline:
     def __init__(self, packed: Optional[PackedHead], device, commonsense=True, aligned_keys=None, violated_keys=None,
                  top_k=tables.TOP_K, iou_thresh=0.5, feature_size=32, chunk_pairs=16384, predcls=True, conv3_m_sub=2,
                  hier=None, splits=None, overlap=True, conv2_m_sub=1, chunk_policy="waves", conv3_block_rows=4, conv3_shared=True,
-                 fc1_shared=True, conv3_block_cols=4):
+                 fc1_shared=True, conv3_block_cols=4, dense_above=0.85):
         self.packed = packed
+        # A window whose boxes are so large that the shared-footprint work lists would visit more than this share of the dense
+        # conv3_1 pixels (`DeviceBatch.cover_fraction`, a host estimate made when the batch is built) takes the DENSE kernels: there
+        # is nothing to skip and the per-box maps / bookkeeping only cost (measured crossover 0.88: full-grid boxes 251 ms shared
+        # vs 226 ms dense, profiles/bench_r02g_*).  Same scores either way (bit-identical conv3_1, fc1 to fp32 rounding order).
+        self.dense_above = float(dense_above)
+        self.last_path = None               # "shared" / "blocks" / "dense": the formulation the last forward_pairs took
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("hiercom_b200: RelationPipeline needs a CUDA device (no CPU fallback)")
@@ -210,8 +249,8 @@ class RelationPipeline:
         n_img = b.n_images
         boxes = b.boxes if boxes is None else boxes
         box_img = b.box_img if box_img is None else box_img
-        x = ops.pack_pixels(b.feat, b.depth, K1_PAD)
-        t = torch.empty(n_img * fs * fs, 256, dtype=torch.bfloat16, device=self.device)
+        x = ops.pack_pixels(b.feat, b.depth, K1_PAD, dtype=pk.act_dtype)
+        t = torch.empty(n_img * fs * fs, 256, dtype=self.packed.act_dtype, device=self.device)
         ops.tc_gemm(x, pk.w1, t, n_img * fs * fs, 256, K1_PAD, bias=pk.b1, lda=K1_PAD, ldc=256, epilogue=EPI_BF16, act=ACT_TANH,
                     group_m=8, tag="conv1")
         abox = ops.box_select(t, boxes, box_img, pk.fill, fs)
@@ -229,7 +268,7 @@ class RelationPipeline:
         idx = torch.arange(n_box, dtype=torch.int32, device=self.device)
         empty = torch.full((n_box,), n_box, dtype=torch.int32, device=self.device)
         sub, obj = torch.cat((idx, empty)), torch.cat((empty, idx))
-        maps = torch.empty(2 * n_box + (1 if with_background_row else 0), 8, 8, 1024, dtype=torch.bfloat16, device=self.device)
+        maps = torch.empty(2 * n_box + (1 if with_background_row else 0), 8, 8, 1024, dtype=self.packed.act_dtype, device=self.device)
         if with_background_row:             # row 2*n_box = the background itself (its fc1 row is the "- fc1(background)" term)
             maps[2 * n_box:].copy_(pk.p3_background())
         starts = list(range(0, 2 * n_box, self.chunk_pairs))
@@ -336,7 +375,11 @@ class RelationPipeline:
         pk = self.packed
         n = pairs["n"]
         br, bc, shared = self.conv3_block_rows, self.conv3_block_cols, self.conv3_shared
-        if self.fc1_shared and n > 0:
+        if br and b.cover_fraction is not None and b.cover_fraction > self.dense_above:
+            br, bc, shared = 0, 8, False                         # nothing to skip in this window: the dense kernels
+            self.last_n_blocks = self.last_k_masks = None
+        self.last_path = "dense" if not br else ("shared" if shared else "blocks")
+        if self.fc1_shared and shared and n > 0:
             return self._forward_pairs_fc1_shared(b, pairs)
         if shared:      # one more box per window: the empty one (all background), partner of every box in `box_maps`
             boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))
@@ -367,7 +410,7 @@ class RelationPipeline:
                     blocks, _ = list_blocks(b.boxes, pairs["sub"][s:e], pairs["obj"][s:e], br, self.fs, n_blocks=nblk[k:k + 1], block_cols=bc)
                     p3 = None
                     if shared:
-                        p3 = torch.empty(e - s, 8, 8, 1024, dtype=torch.bfloat16, device=self.device)
+                        p3 = torch.empty(e - s, 8, 8, 1024, dtype=self.packed.act_dtype, device=self.device)
                         prefill(p3, pairs["sub"][s:e], pairs["obj"][s:e], e - s)
                     pk.conv3_fc(p2, m_sub=self.conv3_m_sub, raw=raw[s:e], blocks=blocks, n_blocks=nblk[k:k + 1], block_rows=br, p3=p3,
                                 block_cols=bc)
@@ -383,11 +426,11 @@ class RelationPipeline:
             lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
             chunks = self._image_chunks(pairs["offsets_host"])
             cap = max(c[3] for c in chunks)
-            bufs = [torch.empty(cap, self.fs // 2, self.fs // 2, 512, dtype=torch.bfloat16, device=self.device)
+            bufs = [torch.empty(cap, self.fs // 2, self.fs // 2, 512, dtype=self.packed.act_dtype, device=self.device)
                     for _ in range(2 if self.overlap and len(chunks) > 1 else 1)]
             if br:      # per buffer: the work list and the background-filled pooled conv3_1 output
                 blk_bufs = [torch.empty(cap * (256 // (br * bc)), dtype=torch.int32, device=self.device) for _ in bufs]
-                p3_bufs = [torch.empty(cap, 8, 8, 1024, dtype=torch.bfloat16, device=self.device) for _ in bufs]
+                p3_bufs = [torch.empty(cap, 8, 8, 1024, dtype=self.packed.act_dtype, device=self.device) for _ in bufs]
                 nblk = torch.zeros(len(chunks), dtype=torch.int32, device=self.device)
                 p3_bg = pk.p3_background()
             main = torch.cuda.current_stream()
@@ -483,7 +526,7 @@ class RelationPipeline:
         fs, br, bc, dev = self.fs, self.conv3_block_rows, self.conv3_block_cols, self.device
         cap = max(c[3] for c in chunks)
         n_buf = 2 if self.overlap and len(chunks) > 1 else 1
-        return dict(bufs=[torch.empty(cap, fs // 2, fs // 2, 512, dtype=torch.bfloat16, device=dev) for _ in range(n_buf)],
+        return dict(bufs=[torch.empty(cap, fs // 2, fs // 2, 512, dtype=self.packed.act_dtype, device=dev) for _ in range(n_buf)],
                     blk=[torch.empty(cap * (256 // (br * bc)), dtype=torch.int32, device=dev) for _ in range(n_buf)],
                     cov=[torch.empty(cap, dtype=torch.int64, device=dev) for _ in range(n_buf)],
                     nblk=torch.zeros(len(chunks), dtype=torch.int32, device=dev))
@@ -504,7 +547,7 @@ class RelationPipeline:
         row_of[perm64] = torch.arange(n, dtype=torch.int32, device=dev)
         row_sub, row_obj = sub_w[perm64].contiguous(), obj_w[perm64].contiguous()
         masks = ops.tile_cell_masks(b.boxes, row_sub, row_obj, 256, fs)
-        d = torch.empty(n, 64, 1024, dtype=torch.bfloat16, device=dev)
+        d = torch.empty(n, 64, 1024, dtype=self.packed.act_dtype, device=dev)
         ops.cells_zero(masks, 256, n, d)
         if pool is None:
             pool = self._pool_buffers(chunks)

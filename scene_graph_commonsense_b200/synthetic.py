@@ -149,6 +149,29 @@ def assign_gt_from_scores(sample, relation_of, splits=(15, 11, 24), p_model=0.8,
     return sample
 
 
+def assign_gt_from_ranking(sample, ranked, p_keep=0.6, thin=1.0 / 6.0, base_seed=0):
+    """Re-draws the GT relations of `sample` around a model's own RANKED triplets so that Recall@K lands mid-range (a wrong score,
+    label, filter decision or rank anywhere in the path moves it): the relations `make_image` drew are thinned (each kept with
+    probability `thin`: p_rel 0.3 -> 0.05), then every ranked triplet `(sub, obj, label)` (image-local box rows, best first)
+    becomes GT with probability `p_keep` unless its unordered pair was already taken by a better rank (the reference's GT holds
+    one relation per unordered pair, dataset_utils.py:159-184).  Deterministic in (base_seed, image_id); modifies and returns the sample."""
+    g = _gen(base_seed + 104729, sample.image_id)
+    for gi in range(1, len(sample.categories)):
+        drop = torch.rand(gi, generator=g) >= thin
+        sample.relationships[gi - 1] = torch.where(drop, torch.full_like(sample.relationships[gi - 1], -1), sample.relationships[gi - 1])
+        sample.subj_or_obj[gi - 1] = torch.where(drop, torch.full_like(sample.subj_or_obj[gi - 1], -1.0), sample.subj_or_obj[gi - 1])
+    taken = set()
+    u = torch.rand(max(len(ranked), 1), generator=g)
+    for j, (sub, obj, lab) in enumerate(ranked):
+        hi, lo = (sub, obj) if sub > obj else (obj, sub)
+        if hi == lo or (hi, lo) in taken or float(u[j]) >= p_keep:
+            continue
+        taken.add((hi, lo))
+        sample.relationships[hi - 1][lo] = int(lab)
+        sample.subj_or_obj[hi - 1][lo] = 1.0 if sub == hi else 0.0
+    return sample
+
+
 WEIGHT_PRESETS = {
     # name: (trunk_gain, logit_gain).  "init" = nn default init; "trained" = the round-1 trained-scale variant (head layers
     # only: logit std 1.1, `pred` <= 0.09); "sharp" = He-gain trunk (`pred` O(1), max 1.8) and logit std 3.3 (SURVEY §8d, H5):

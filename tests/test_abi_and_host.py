@@ -32,7 +32,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
         assert n in _lib.SIGNATURES, "ctypes binding missing for " + n
-    assert lib.hc_abi_version() == 1
+    assert lib.hc_abi_version() == _lib.ABI_VERSION == 2
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.library_path()], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (hc_[a-z0-9_]+)", out))
     assert exported == set(names)
@@ -404,3 +404,53 @@ def test_shared_footprint_decomposition_holds_for_the_reference_formulation_in_f
         lhs = w_fc @ flat(pair)
         rhs = w_fc @ flat(sub) + w_fc @ flat(obj) - w_fc @ flat(bg) + w_fc @ flat(d)
         assert float((lhs - rhs).abs().max()) <= 1e-5 * max(1.0, float(lhs.abs().max()))     # d itself is rounded to fp32
+
+
+def test_cover_fraction_estimate_matches_brute_force_block_count_and_steers_the_dense_fallback():
+    """`pipeline.footprint_cover_fraction` (host, numpy) = the share of conv3_1 pixels the shared-footprint work lists visit,
+    counted here pair by pair with 2 x 2-cell blocks over the cell rectangle both boxes reach (oracle.parity's cell geometry)."""
+    from oracle import parity as PA
+    from scene_graph_commonsense_b200 import pipeline, synthetic
+    for mode, lo, hi in (("small", 0.10, 0.25), ("vg", 0.35, 0.80), ("full", 1.0, 1.0)):
+        samples = synthetic.make_batch([3, 4, 5], [9, 12, 1], with_maps=False, box_mode=mode)
+        hb = pipeline.host_batch_from_samples(samples, with_maps=False, pinned=False)
+        blocks = pairs = 0
+        for s in samples:
+            bx = s.bbox.numpy()
+            for i in range(len(bx)):
+                for j in range(len(bx)):
+                    if i == j:
+                        continue
+                    pairs += 1
+                    xs, ys = PA._clip_box(bx[i]), PA._clip_box(bx[j])
+                    (ax, bx_), (cx, dx) = PA._cells(xs[0], xs[1]), PA._cells(ys[0], ys[1])
+                    (ay, by), (cy, dy) = PA._cells(xs[2], xs[3]), PA._cells(ys[2], ys[3])
+                    w, h = max(0, min(bx_, dx) - max(ax, cx)), max(0, min(by, dy) - max(ay, cy))
+                    blocks += -(-w // 2) * -(-h // 2)
+        want = blocks * 4.0 / (64.0 * pairs)
+        got = hb.meta["cover_fraction"]
+        assert abs(got - want) < 1e-12, (mode, got, want)
+        assert lo <= got <= hi, (mode, got)
+    assert pipeline.footprint_cover_fraction(np.zeros((0, 4)), np.array([0])) == 0.0
+
+
+def test_gt_from_ranking_places_ranked_triplets_once_per_unordered_pair():
+    from scene_graph_commonsense_b200 import synthetic
+    s = synthetic.make_image(11, 12, with_maps=False)
+    n_before = sum(int((r >= 0).sum()) for r in s.relationships)
+    ranked = [(5, 2, 7), (2, 5, 9), (0, 3, 1), (11, 10, 49), (4, 4, 3), (1, 0, 20)]
+    s = synthetic.assign_gt_from_ranking(s, ranked, p_keep=1.0, thin=0.0)
+    got = {}
+    for gi in range(1, 12):
+        for e in range(gi):
+            if int(s.relationships[gi - 1][e]) >= 0:
+                d = int(s.subj_or_obj[gi - 1][e])
+                got[(gi, e)] = ((gi, e) if d == 1 else (e, gi)) + (int(s.relationships[gi - 1][e]),)
+    # (2,5,9) lost to the better-ranked (5,2,7) on the same unordered pair; (4,4,.) is not a pair
+    assert got == {(5, 2): (5, 2, 7), (3, 0): (0, 3, 1), (11, 10): (11, 10, 49), (1, 0): (1, 0, 20)}
+    assert all(int(d) == -1 for dd, rr in zip(s.subj_or_obj, s.relationships) for d, r in zip(dd, rr) if int(r) < 0)
+    s2 = synthetic.assign_gt_from_ranking(synthetic.make_image(11, 12, with_maps=False), ranked)          # defaults: thinned + 60 %
+    n_after = sum(int((r >= 0).sum()) for r in s2.relationships)
+    assert 0 < n_after < n_before
+    s3 = synthetic.assign_gt_from_ranking(synthetic.make_image(11, 12, with_maps=False), ranked)
+    assert all(torch.equal(a, b) for a, b in zip(s2.relationships, s3.relationships))                     # deterministic

@@ -1,0 +1,175 @@
+"""fp16 operand format of the tensor-core path (`hc_gemm_desc.operand_f16`, `PackedHead(operand_dtype=torch.float16)`): the same
+kernels with IEEE half operands / stored activations instead of bf16 - same tcgen05 kind::f16 rate, 3 more mantissa bits.
+Kernel level against torch fp32 references on the same (fp16-rounded) inputs with the tighter fp16 tolerances, saturation instead
+of inf at +-65504, bit-exact streaming kernels, and the pipeline-level identities (block-sparse == dense bit for bit, CTA pairs ==
+single CTA bit for bit, shared footprint within tolerance of dense) re-checked in this format."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hiercom_oracle as O
+from scene_graph_commonsense_b200 import synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+H = torch.float16
+
+
+def _ops():
+    from scene_graph_commonsense_b200 import ops
+    return ops
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(DEV)
+
+
+def _close(got, ref, rel, what):
+    got, ref = got.float(), ref.float()
+    scale = ref.abs().max().item() + 1e-6
+    err = (got - ref).abs().max().item()
+    assert err <= rel * scale, "%s: max abs err %.4g vs scale %.4g (limit %.3g)" % (what, err, scale, rel * scale)
+
+
+@pytest.mark.parametrize("m,n,k,m_sub", [(128, 256, 64, 1), (300, 256, 320, 1), (1000, 512, 1024, 2), (77, 128, 4096, 1)])
+def test_plain_gemm_f32_epilogue_fp16_operands(m, n, k, m_sub):
+    ops = _ops()
+    a, b, bias = _rand((m, k), 1).to(H), _rand((n, k), 2).to(H), _rand((n,), 3)
+    out = torch.full((m, n), float("nan"), device=DEV)
+    ops.tc_gemm(a, b, out, m, n, k, bias=bias, lda=k, ldc=n, epilogue=ops.EPI_F32, m_sub=m_sub, group_m=3)
+    _close(out, a.float() @ b.float().t() + bias, 2e-4, "gemm f32 (fp16 operands)")   # exact products, fp32 accumulation order only
+
+
+def test_fp16_operands_are_not_read_as_bf16():
+    """The instruction descriptor / tensor-map data type really switch: the same BITS give different results in the two formats."""
+    ops = _ops()
+    a, b = _rand((128, 64), 4).to(H), _rand((128, 64), 5).to(H)
+    out_h = torch.empty(128, 128, device=DEV)
+    out_b = torch.empty(128, 128, device=DEV)
+    ops.tc_gemm(a, b, out_h, 128, 128, 64, lda=64, ldc=128, epilogue=ops.EPI_F32)
+    ops.tc_gemm(a.view(torch.bfloat16), b.view(torch.bfloat16), out_b, 128, 128, 64, lda=64, ldc=128, epilogue=ops.EPI_F32)
+    _close(out_h, a.float() @ b.float().t(), 2e-4, "fp16 read")
+    _close(out_b, a.view(torch.bfloat16).float() @ b.view(torch.bfloat16).float().t(), 2e-3, "bf16 read of the same bits")
+    with pytest.raises(RuntimeError, match="all be bf16 or all fp16"):
+        ops.tc_gemm(a, b.view(torch.bfloat16), out_h, 128, 128, 64, lda=64, ldc=128, epilogue=ops.EPI_F32)
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "tanh"])
+def test_plain_gemm_fp16_epilogue_with_offset_and_saturation(act):
+    ops = _ops()
+    m, n, k, ldc, off = 640, 128, 320, 256, 128
+    a, b, bias = _rand((m, k), 4, 0.2).to(H), _rand((n, k), 5, 0.2).to(H), _rand((n,), 6, 0.1)
+    out = torch.zeros((m, ldc), dtype=H, device=DEV)
+    code = {"none": ops.ACT_NONE, "relu": ops.ACT_RELU, "tanh": ops.ACT_TANH}[act]
+    ops.tc_gemm(a, b, out, m, n, k, bias=bias, lda=k, ldc=ldc, c_off=off, epilogue=ops.EPI_BF16, act=code)
+    ref = a.float() @ b.float().t() + bias
+    ref = {"none": ref, "relu": torch.relu(ref), "tanh": torch.tanh(ref)}[act]
+    _close(out[:, off:], ref, 8e-4, "gemm fp16 epilogue " + act)          # one fp16 rounding: 2^-11 relative
+    assert (out[:, :off] == 0).all()
+    if act == "none":       # beyond the fp16 range the store saturates at the largest finite value instead of writing inf
+        big = torch.full((n,), 1.0e6, device=DEV)
+        big[::2] = -1.0e6
+        ops.tc_gemm(a, b, out, m, n, k, bias=big, lda=k, ldc=ldc, c_off=off, epilogue=ops.EPI_BF16, act=code)
+        assert torch.isfinite(out.float()).all()
+        assert (out[:, off::2] == -65504.0).all() and (out[:, off + 1::2] == 65504.0).all()
+    with pytest.raises(RuntimeError, match="fp16 operands write fp16 outputs"):
+        ops.tc_gemm(a, b, out.view(torch.bfloat16), m, n, k, bias=bias, lda=k, ldc=ldc, c_off=off, epilogue=ops.EPI_BF16, act=code)
+
+
+@pytest.mark.parametrize("n_img,hw,c_in,n_out,m_sub", [(4, 16, 512, 1024, 2), (3, 32, 256, 512, 2), (3, 16, 128, 256, 1)])
+def test_implicit_conv_relu_pool_fp16(n_img, hw, c_in, n_out, m_sub):
+    ops = _ops()
+    x, w, bias = _rand((n_img, hw, hw, c_in), 9, 0.5).to(H), _rand((n_out, 9 * c_in), 10, 0.05).to(H), _rand((n_out,), 11, 0.2)
+    out = torch.zeros((n_img, hw // 2, hw // 2, n_out), dtype=H, device=DEV)
+    ops.tc_gemm(x, w, out, n_img * hw * hw, n_out, 9 * c_in, bias=bias, ldc=n_out, mode=ops.GEMM_CONV3, epilogue=ops.EPI_POOL_BF16,
+                n_img=n_img, h=hw, w=hw, c_total=c_in, c_base=0, c_in=c_in, m_sub=m_sub)
+    wt = w.float().view(n_out, 3, 3, c_in).permute(0, 3, 1, 2)
+    ref = F.max_pool2d(torch.relu(F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=1)), 2, 2).permute(0, 2, 3, 1)
+    _close(out, ref, 8e-4, "conv relu pool fp16")
+
+
+def test_streaming_kernels_fp16_are_bit_exact():
+    ops = _ops()
+    feat, depth = _rand((2, 256, 32, 32), 12), _rand((2, 1, 32, 32), 13)
+    feat[0, 3, 5, 7], feat[1, 200, 0, 31] = 1.0e6, -3.0e5              # out of range: saturate, no inf
+    x = ops.pack_pixels(feat, depth, 320, dtype=H)
+    ref = torch.cat((feat, depth), 1).permute(0, 2, 3, 1).reshape(-1, 257).clamp(-65504.0, 65504.0).to(H)
+    assert x.dtype == H and torch.equal(x[:, :257], ref) and (x[:, 257:] == 0).all()
+    u, v = _rand((4, 32, 32, 512), 16).to(H), _rand((4, 32, 32, 512), 17).to(H)
+    ps = torch.tensor([0, 3, 2, 1, 1], dtype=torch.int32, device=DEV)
+    po = torch.tensor([1, 0, 2, 3, 0], dtype=torch.int32, device=DEV)
+    got = ops.pair_relu_pool(u, v, None, ps, po)                      # packed add.rn.f16x2 / max.f16x2 == rounding the fp32 sum once
+    s = torch.relu((u[ps.long()].float() + v[po.long()].float()).to(H).float())
+    ref = F.max_pool2d(s.permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1).to(H)
+    assert got.dtype == H and torch.equal(got.float(), ref.float())
+    with pytest.raises(RuntimeError):
+        ops.pair_relu_pool(u, v, _rand((512,), 18), ps, po)            # the fp32-bias variant is bf16-only
+
+
+def _pipes(sd, **kw):
+    from scene_graph_commonsense_b200 import model, pipeline
+    pk = model.PackedHead(sd, DEV, operand_dtype=H)
+    return pk, lambda **k2: pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=600, **dict(kw, **k2))
+
+
+def test_pipeline_identities_hold_in_fp16():
+    """Block-sparse conv3_1 (per-pair and shared lists) == dense bit for bit; CTA pairs == single CTA bit for bit; the
+    shared-footprint fc1 within 1e-3 of the dense path on joint probabilities - all with fp16 operands."""
+    from scene_graph_commonsense_b200 import pipeline
+    sd = synthetic.preset_state_dict("trained")
+    pk, mk = _pipes(sd)
+    samples = synthetic.make_batch([700, 701, 702], [9, 14, 5])
+    b = pipeline.batch_from_samples(samples, DEV, skip_mode="batch")
+    outs = {}
+    for name, kw in (("dense", dict(conv3_block_rows=0, conv3_shared=False, fc1_shared=False)),
+                     ("blocks", dict(conv3_block_rows=4, conv3_block_cols=4, conv3_shared=False, fc1_shared=False)),
+                     ("shared_dense_fc1", dict(conv3_block_rows=4, conv3_block_cols=4, conv3_shared=True, fc1_shared=False)),
+                     ("shared", dict())):
+        pipe = mk(**kw)
+        pairs = pipe.enumerate_pairs(b)
+        outs[name] = [t.clone() for t in pipe.forward_pairs(b, pairs)]
+    assert outs["dense"][0].shape[0] > 100
+    for name in ("blocks", "shared_dense_fc1"):
+        for x, y in zip(outs[name], outs["dense"]):
+            assert torch.equal(x, y), name
+    dp = (outs["shared"][0].double().exp() - outs["dense"][0].double().exp()).abs().max().item()
+    assert dp <= 1e-3, dp
+    pipe1 = mk()
+    pipe1.conv3_pairs = 0                                                # single-CTA block kernel
+    pairs = pipe1.enumerate_pairs(b)
+    for x, y in zip(pipe1.forward_pairs(b, pairs), outs["shared"]):
+        assert torch.equal(x, y)
+
+
+def test_small_batch_vs_fp32_oracle_fp16_sharp_weights():
+    """Every directed pair of a small batch on the SHARP weights against the fp32 oracle: 2e-3 absolute on joint probabilities,
+    directly (bf16 operands cannot hold this bar on these weights, see test_gpu_parity_at_scale)."""
+    from oracle import parity as PA
+    from scene_graph_commonsense_b200 import pipeline
+    sd = synthetic.preset_state_dict("sharp")
+    pk, mk = _pipes(sd)
+    samples = synthetic.make_batch([710, 711], [8, 6])
+    b = pipeline.batch_from_samples(samples, DEV, skip_mode="batch")
+    pipe = mk()
+    pairs = pipe.enumerate_pairs(b)
+    rel, sup, conn, logsig = pipe.forward_pairs(b, pairs)
+    sub, obj, img = pairs["sub"].cpu().numpy(), pairs["obj"].cpu().numpy(), pairs["img"].cpu().numpy()
+    off = b.box_offsets.cpu().numpy()
+    pair_list = [(int(i), int(s - off[i]), int(o - off[i])) for i, s, o in zip(img, sub, obj)]
+    rel_ref, sup_ref, conn_ref = PA.oracle_scores(samples, sd, pair_list)
+    st = PA.parity_stats(rel.cpu().numpy(), rel_ref)
+    print("PARITY small_sharp_fp16", st)
+    assert st["top_joint_prob_median"] >= 0.3
+    assert st["max_abs_dp"] <= 2e-3, st
+    assert np.abs(np.exp(sup.cpu().numpy().astype(np.float64)) - np.exp(sup_ref.astype(np.float64))).max() <= 2e-3
+
+
+def test_weights_beyond_the_fp16_range_are_refused():
+    from scene_graph_commonsense_b200 import model
+    sd = {k: v.clone() for k, v in synthetic.head_state_dict(seed=0).items()}
+    sd["conv3_1.weight"][0, 0, 0, 0] = 7.0e4
+    with pytest.raises(RuntimeError, match="fp16 range"):
+        model.PackedHead(sd, DEV, operand_dtype=H)
+    model.PackedHead(sd, DEV)                                           # bf16 takes it

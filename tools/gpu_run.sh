@@ -8,7 +8,8 @@
 #   ref                   bench.py --impl reference
 #   ab                    A/B bench lines for each "NAME|ENV|ARGS" entry of $RUNS (';'-separated)
 #   launches              ncu launch list (gpu__time_duration) of a 1-step bench -> launches_TAG.csv
-#   ncu                   ncu --set full of $NCU_K (kernel regex) skipping $NCU_S launches, $NCU_C captures, of `python $NCU_CMD`
+#   ncu[:suffix]          ncu --set full of $NCU_K (kernel regex; $NCU_EXTRA e.g. "--kernel-name-base demangled" to match template
+#                         arguments) skipping $NCU_S launches, $NCU_C captures, of `python $NCU_CMD`
 #                         -> raw CSV (gz) + summary json (+ the .ncu-rep when small)
 #   kernels               tools/bench_kernels.py
 #   sgb                   tools/bench_sgb.py
@@ -52,7 +53,7 @@ for stage in "$@"; do
           python bench.py --steps 1 --warmup 1 --no-cpu-baseline ${arg//,/ } > $OUT/ncu_bench_$TAG.log 2>&1; echo "exit $?"; wc -l $OUT/launches_$TAG.csv ;;
     ncu)
       echo "== ncu --set full -k ${NCU_K:-regex:tc_gemm_kernel} -s ${NCU_S:-0} -c ${NCU_C:-4} : python ${NCU_CMD:-bench.py --steps 1 --warmup 1 --no-cpu-baseline}"
-      timeout 900 ncu --set full --clock-control none --import-source on -k ${NCU_K:-regex:tc_gemm_kernel} -s ${NCU_S:-0} -c ${NCU_C:-4} -o /tmp/prof_${TAG}${arg} -f \
+      timeout 900 ncu --set full --clock-control none --import-source on ${NCU_EXTRA} -k "${NCU_K:-regex:tc_gemm_kernel}" -s ${NCU_S:-0} -c ${NCU_C:-4} -o /tmp/prof_${TAG}${arg} -f \
           python ${NCU_CMD:-bench.py --steps 1 --warmup 1 --no-cpu-baseline} > $OUT/ncu_${TAG}${arg}.log 2>&1; echo "capture exit $?"
       ncu -i /tmp/prof_${TAG}${arg}.ncu-rep --page raw --csv 2>/dev/null | gzip -9 > $OUT/ncu_raw_${TAG}${arg}.csv.gz
       python tools/ncu_summarize.py /tmp/prof_${TAG}${arg}.ncu-rep > $OUT/ncu_summary_${TAG}${arg}.json 2>/dev/null
