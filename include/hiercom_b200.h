@@ -343,7 +343,8 @@ int hc_connectivity_stats(const float* connectivity, const int32_t* row_gt_direc
  */
 /* prod_rep[p] = cat(head_rep[idx0], tail_rep[idx1]) (roi_relation_predictors.py:413-419); edge_rep f32
  * [n_obj, 2*hidden] = post_emb output, pair_idx int32 [n_pairs,2] global object ids, out bf16 [n_pairs, 2*hidden]
- * (split = 0) or [n_pairs, 3 * 2*hidden] in the bf16x3 layout (split = 1). */
+ * (split = 0), [n_pairs, 3 * 2*hidden] in the bf16x3 layout (split = 1), or fp16 [n_pairs, 2*hidden] saturating at +-65504
+ * (split = 2: the A operand of hc_tc_gemm with operand_f16 = 1). */
 int hc_sgb_pair_gather(const float* edge_rep, const int32_t* pair_idx, int32_t n_pairs, int32_t hidden, int32_t split,
                        void* out, hc_stream_t stream);
 /* bf16x3 operand splitting for near-fp32 accuracy on the bf16 tensor cores: f32 [n,k] -> bf16 [n,3k] = [hi | lo | hi]

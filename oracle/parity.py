@@ -8,6 +8,7 @@ tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg only.
   operand_rounded_scores   the SAME formulation with every GEMM / convolution operand (weights and layer inputs) rounded to a
                            16-bit type, fp32 accumulation - the best any "bf16 in, fp32 accumulate" implementation can do.  It is
                            NOT the reference; it separates "error of the bf16 operand format" from "error of our kernels"
+  sgb_tail_parity          config 5: a per-image random sample of the SGB tail's pairs through the fp32 restatement (sgb_oracle.predictor_tail)
   parity_stats             max |dP| on joint probabilities (north_star's 2e-3 bar), max relative log-prob error, and the fraction
                            of per-super-category argmax labels that differ
 """
@@ -145,3 +146,19 @@ def parity_stats(rel_got, rel_ref, splits=SPLITS):
                 max_rel_logp_err=float((np.abs(g - r) / np.maximum(np.abs(r), 1e-6)).max()),
                 argmax_flip_rate=flips / float(len(splits) * g.shape[0]), argmax_flips=flips,
                 top_joint_prob_median=float(np.median(top)), top1_flip_rate=float((g.argmax(1) != r.argmax(1)).mean()))
+
+
+def sgb_tail_parity(sd, batch, pairs, num_objs, rel_got, per_image=9, seed=3):
+    """Config 5 (SGB plug-and-play tail): `per_image` random directed pairs of every image through the fp32 restatement of
+    roi_relation_predictors.py:399-459 (sgb_oracle.predictor_tail) against `rel_got` = the device's [P, 50] log joint
+    probabilities (rows in the concatenated per-image pair order).  -> parity_stats dict."""
+    from . import sgb_oracle as SO
+    rng = np.random.default_rng(seed)
+    base = np.concatenate(([0], np.cumsum([int(p.shape[0]) for p in pairs])))
+    pick = [np.sort(rng.choice(int(p.shape[0]), size=min(per_image, int(p.shape[0])), replace=False)) for p in pairs]
+    sub_pairs = [pairs[i].cpu()[torch.from_numpy(pick[i])] for i in range(len(pairs))]
+    rows = np.concatenate([pick[i] + base[i] for i in range(len(pairs))])
+    o1, o2, o3, _ = SO.predictor_tail(sd, batch["edge_ctx"], sub_pairs, num_objs, batch["obj_labels"], batch["union_features"][torch.from_numpy(rows)])
+    rel_ref = torch.cat((torch.cat(list(o1)), torch.cat(list(o2)), torch.cat(list(o3))), dim=1).numpy()
+    got = rel_got[torch.from_numpy(rows).to(rel_got.device)].cpu().numpy() if isinstance(rel_got, torch.Tensor) else np.asarray(rel_got)[rows]
+    return parity_stats(got, rel_ref)

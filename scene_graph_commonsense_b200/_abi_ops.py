@@ -386,11 +386,15 @@ def connectivity_stats(connectivity, gt_directed, gt_undirected, stats):
 
 
 # ------------------------------------------------------------------------------------------------------ SGB twin (R14/N1)
-def sgb_pair_gather(edge_rep, pair_idx, hidden, split=False):
+def sgb_pair_gather(edge_rep, pair_idx, hidden, split=False, f16=False):
+    """split: the bf16x3 [hi | lo | hi] layout; f16: plain fp16 rows (the fp16 operand format of tc_gemm) instead of plain bf16."""
     require_cuda(edge_rep, pair_idx)
     n = pair_idx.shape[0]
-    out = torch.empty(n, (3 if split else 1) * 2 * hidden, dtype=torch.bfloat16, device=edge_rep.device)
-    check(_lib.load().hc_sgb_pair_gather(ptr(edge_rep), ptr(pair_idx), n, hidden, int(split), ptr(out), stream_ptr()), "hc_sgb_pair_gather")
+    if split and f16:
+        raise RuntimeError("hiercom_b200: sgb_pair_gather: the split layout is bf16-only")
+    out = torch.empty(n, (3 if split else 1) * 2 * hidden, dtype=torch.float16 if f16 else torch.bfloat16, device=edge_rep.device)
+    check(_lib.load().hc_sgb_pair_gather(ptr(edge_rep), ptr(pair_idx), n, hidden, 2 if f16 else int(split), ptr(out), stream_ptr()),
+          "hc_sgb_pair_gather")
     _count()
     return out
 

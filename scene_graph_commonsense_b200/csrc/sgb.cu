@@ -5,6 +5,8 @@
 // The dense part (post_cat 1024->4096 with the `* union_features` epilogue, BayesHead 4096->54) runs on tc_gemm_kernel.
 #include <math.h>
 
+#include <cuda_fp16.h>
+
 #include "hc_common.cuh"
 
 namespace hc {
@@ -38,7 +40,8 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& hi, uint4& lo
 }
 
 // prod_rep = cat(head_rep[idx0], tail_rep[idx1]) with edge_rep [n_obj, 2*hidden] = post_emb output viewed as (n_obj, 2, hidden).
-// split == 0: out bf16 [n, 2*hidden]; split == 1: out bf16 [n, 3 * 2*hidden] = [hi | lo | hi]
+// split == 0: out bf16 [n, 2*hidden]; split == 1: out bf16 [n, 3 * 2*hidden] = [hi | lo | hi]; split == 2: out fp16 [n, 2*hidden]
+// (saturating at +-65504: the plain-fp16 operand format of hc_tc_gemm, operand_f16 = 1)
 __global__ void sgb_pair_gather_kernel(const float* __restrict__ edge_rep, const int* __restrict__ pair_idx, long long total_vec, int hidden,
                                        int split, uint4* __restrict__ out) {
   const int vec_per_row = 2 * hidden / 8;
@@ -50,6 +53,16 @@ __global__ void sgb_pair_gather_kernel(const float* __restrict__ edge_rep, const
     const float4* src = reinterpret_cast<const float4*>(edge_rep + (long long)obj * 2 * hidden + col);
     float4 a = __ldg(src), b = __ldg(src + 1);
     const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (split == 2) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __half2 h = __floats2half2_rn(fminf(fmaxf(x[2 * k], -65504.0f), 65504.0f), fminf(fmaxf(x[2 * k + 1], -65504.0f), 65504.0f));
+        w[k] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+      continue;
+    }
     uint4 hi, lo;
     split8(x, hi, lo);
     if (!split) {
@@ -298,7 +311,8 @@ extern "C" int hc_sgb_pair_gather(const float* edge_rep, const int32_t* pair_idx
                                   hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(edge_rep && pair_idx && out, HC_E_NULL, "hc_sgb_pair_gather: NULL pointer");
-  HC_REQUIRE(n_pairs > 0 && hidden > 0 && hidden % 8 == 0, HC_E_SHAPE, "hc_sgb_pair_gather: hidden must be a multiple of 8");
+  HC_REQUIRE(n_pairs > 0 && hidden > 0 && hidden % 8 == 0 && split >= 0 && split <= 2, HC_E_SHAPE,
+             "hc_sgb_pair_gather: hidden must be a multiple of 8, split 0 (bf16), 1 (bf16x3) or 2 (fp16)");
   HC_REQUIRE(aligned16(edge_rep) && aligned16(out), HC_E_ALIGN, "hc_sgb_pair_gather: 16-byte alignment");
   int rc = hc_device_check();
   if (rc != HC_OK) return rc;

@@ -367,13 +367,13 @@ def connectivity_stats(connectivity, gt_directed, gt_undirected, stats):
 
 
 # ------------------------------------------------------------------------------------------------ R14 / N1 SGB twin
-@_op("sgb_pair_gather", "(Tensor edge_rep, Tensor pair_idx, int hidden, bool split) -> Tensor")
-def _sgb_pair_gather(edge_rep, pair_idx, hidden, split):
-    return _A.sgb_pair_gather(edge_rep, pair_idx, hidden, split)
+@_op("sgb_pair_gather", "(Tensor edge_rep, Tensor pair_idx, int hidden, bool split, bool f16) -> Tensor")
+def _sgb_pair_gather(edge_rep, pair_idx, hidden, split, f16):
+    return _A.sgb_pair_gather(edge_rep, pair_idx, hidden, split, f16)
 
 
-def sgb_pair_gather(edge_rep, pair_idx, hidden, split=False):
-    return _call("sgb_pair_gather")(edge_rep, pair_idx, hidden, bool(split))
+def sgb_pair_gather(edge_rep, pair_idx, hidden, split=False, f16=False):
+    return _call("sgb_pair_gather")(edge_rep, pair_idx, hidden, bool(split), bool(f16))
 
 
 @_op("split_bf16x3", "(Tensor x) -> Tensor")

@@ -149,10 +149,10 @@ def assign_gt_from_scores(sample, relation_of, splits=(15, 11, 24), p_model=0.8,
     return sample
 
 
-def assign_gt_from_ranking(sample, ranked, p_keep=0.6, thin=1.0 / 6.0, base_seed=0):
+def assign_gt_from_ranking(sample, ranked, p_keep=0.9, thin=0.1, base_seed=0):
     """Re-draws the GT relations of `sample` around a model's own RANKED triplets so that Recall@K lands mid-range (a wrong score,
     label, filter decision or rank anywhere in the path moves it): the relations `make_image` drew are thinned (each kept with
-    probability `thin`: p_rel 0.3 -> 0.05), then every ranked triplet `(sub, obj, label)` (image-local box rows, best first)
+    probability `thin`: p_rel 0.3 -> 0.03), then every ranked triplet `(sub, obj, label)` (image-local box rows, best first)
     becomes GT with probability `p_keep` unless its unordered pair was already taken by a better rank (the reference's GT holds
     one relation per unordered pair, dataset_utils.py:159-184).  Deterministic in (base_seed, image_id); modifies and returns the sample."""
     g = _gen(base_seed + 104729, sample.image_id)

@@ -53,7 +53,11 @@ def _head(preset, operands="bf16"):
     return sd, _HEADS[operands]
 
 
-def _run_relation_case(name, samples, sgdet, preset, chunk_pairs, min_strata=4, operands="bf16", dense_above=None, expect_path="shared"):
+def _run_relation_case(name, samples, sgdet, preset, chunk_pairs, min_strata=4, operands="bf16", dense_above=None, expect_path="shared",
+                       bar=None):
+    """bar "direct": 2e-3 absolute against the fp32 oracle; "model": no further from fp32 than the operand-rounding model of the
+    reference formulation in the same 16-bit format.  Default: direct for fp16 operands and for the trained preset."""
+    bar = bar or ("direct" if (preset == "trained" or operands == "fp16") else "model")
     from scene_graph_commonsense_b200 import pipeline
     sd, packed = _head(preset, operands)
     kw = {} if dense_above is None else dict(dense_above=dense_above)
@@ -78,18 +82,19 @@ def _run_relation_case(name, samples, sgdet, preset, chunk_pairs, min_strata=4, 
     st["strata"] = {int(k): int((strata == k).sum()) for k in np.unique(strata)}
     st["super_max_abs_dp"] = float(np.abs(np.exp(sup_g.astype(np.float64)) - np.exp(sup_ref.astype(np.float64))).max())
     st["n_pairs_batch"], st["preset"], st["operands"] = int(pairs["n"]), preset, operands
-    if preset == "trained" or operands == "fp16":
+    if bar == "direct":
         _record(name, st)
         assert len(st["strata"]) >= min_strata, st["strata"]
         assert st["max_abs_dp"] <= PROB_TOL, st
         assert st["super_max_abs_dp"] <= PROB_TOL, st
         assert st["argmax_flip_rate"] <= 0.01, st
         return
-    rel_emu, _, _ = PA.operand_rounded_scores(samples, sd, pair_list, sgdet=sgdet)
+    rel_emu, _, _ = PA.operand_rounded_scores(samples, sd, pair_list, sgdet=sgdet,
+                                              dtype=torch.float16 if operands == "fp16" else torch.bfloat16)
     model_vs_fp32 = PA.parity_stats(rel_emu, rel_ref)
     ours_vs_model = PA.parity_stats(rel_g, rel_emu)
-    st["bf16_operand_model_vs_fp32"] = {k: model_vs_fp32[k] for k in ("max_abs_dp", "mean_abs_dp", "argmax_flip_rate")}
-    st["ours_vs_bf16_operand_model"] = {k: ours_vs_model[k] for k in ("max_abs_dp", "mean_abs_dp", "argmax_flip_rate")}
+    st[operands + "_operand_model_vs_fp32"] = {k: model_vs_fp32[k] for k in ("max_abs_dp", "mean_abs_dp", "argmax_flip_rate")}
+    st["ours_vs_%s_operand_model" % operands] = {k: ours_vs_model[k] for k in ("max_abs_dp", "mean_abs_dp", "argmax_flip_rate")}
     _record(name, st)
     assert st["top_joint_prob_median"] >= 0.35, st              # the weights really are sharp
     # our kernels are no further from fp32 than the operand-rounding model of the reference formulation is (worst case and on
@@ -122,15 +127,19 @@ def test_full_grid_boxes_match_on_both_paths(preset, path):
     """The other end of the box-size distribution (VERDICT weak 4): every box covers the whole grid, so every cell is shared and
     nothing can be skipped.  By default such a window takes the DENSE kernels (`dense_above`, host estimate 1.0 > 0.85); forced
     through the shared-footprint machinery (work lists = the dense tiling, every cell through the difference operand) it gives the
-    same scores.  fp16 operands: bf16 sits AT the 2e-3 bar here on the trained weights (1.8e-3 joint / 2.2e-3 super, r02g)."""
+    same scores.  fp16 operands: bf16 sits AT the 2e-3 bar here on the trained weights (1.8e-3 joint / 2.2e-3 super, r02g).  With the
+    sharp weights whole-grid boxes push the top joint probability to a median of 0.82 and even fp16 operand rounding alone
+    reaches 4e-3 (dense and shared path alike, r02h), so that case is held to the fp16 operand-rounding model instead."""
     import bench
     samples = bench.make_samples(0, 4, 24, boxes_mode="full")
     _run_relation_case("full_boxes_%s_fp16_%s" % (preset, path), samples, False, preset, 16384, min_strata=1, operands="fp16",
-                       dense_above=2.0 if path == "shared" else None, expect_path=path)
+                       dense_above=2.0 if path == "shared" else None, expect_path=path, bar="model" if preset == "sharp" else "direct")
 
 
-@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("precision", ["bf16x3", "fp16", "bf16"])
 def test_cfg5_sgb_tail_vs_fp32_oracle_at_bench_size(precision):
+    """64 images x 40 objects (99 840 pairs), 9 random pairs per image (576 in all) through the fp32 restatement of
+    roi_relation_predictors.py:399-459.  bf16x3 (split operands) and plain fp16 hold the 2e-3 bar; plain bf16 does not (recorded)."""
     from scene_graph_commonsense_b200 import sgb
     n_img, n_obj = 64, 40
     num_objs = [n_obj] * n_img
@@ -148,19 +157,10 @@ def test_cfg5_sgb_tail_vs_fp32_oracle_at_bench_size(precision):
                                                      batch["union_features"].to(DEV), post_cat, head, sd["freq_bias"].to(DEV),
                                                      precision=precision)
     rel_g = torch.cat((torch.cat(list(r1)), torch.cat(list(r2)), torch.cat(list(r3))), dim=1)
-    # 9 random pairs per image (576 in all) through the fp32 restatement of roi_relation_predictors.py:399-459
-    rng = np.random.default_rng(3)
-    per_img = n_obj * (n_obj - 1)
-    pick = [np.sort(rng.choice(per_img, size=9, replace=False)) for _ in range(n_img)]
-    sub_pairs = [pairs[i][torch.from_numpy(pick[i])] for i in range(n_img)]
-    rows = np.concatenate([pick[i] + i * per_img for i in range(n_img)])
-    o1, o2, o3, osup = SO.predictor_tail(sd, batch["edge_ctx"], sub_pairs, num_objs, batch["obj_labels"],
-                                         batch["union_features"][torch.from_numpy(rows)])
-    rel_ref = torch.cat((torch.cat(list(o1)), torch.cat(list(o2)), torch.cat(list(o3))), dim=1).numpy()
-    st = PA.parity_stats(rel_g[torch.from_numpy(rows).to(DEV)].cpu().numpy(), rel_ref)
+    st = PA.sgb_tail_parity(sd, batch, pairs, num_objs, rel_g)
     st["precision"] = precision
     _record("cfg5_" + precision, st)
-    if precision == "bf16x3":
+    if precision in ("bf16x3", "fp16"):
         assert st["max_abs_dp"] <= PROB_TOL, st
     else:       # plain bf16 operands: recorded; must at least be a faithful bf16 GEMM (no gross error)
         assert st["max_abs_dp"] <= 0.05 and st["argmax_flip_rate"] <= 0.05, st

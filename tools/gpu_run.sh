@@ -53,7 +53,7 @@ for stage in "$@"; do
           python bench.py --steps 1 --warmup 1 --no-cpu-baseline ${arg//,/ } > $OUT/ncu_bench_$TAG.log 2>&1; echo "exit $?"; wc -l $OUT/launches_$TAG.csv ;;
     ncu)
       echo "== ncu --set full -k ${NCU_K:-regex:tc_gemm_kernel} -s ${NCU_S:-0} -c ${NCU_C:-4} : python ${NCU_CMD:-bench.py --steps 1 --warmup 1 --no-cpu-baseline}"
-      timeout 900 ncu --set full --clock-control none --import-source on ${NCU_EXTRA} -k "${NCU_K:-regex:tc_gemm_kernel}" -s ${NCU_S:-0} -c ${NCU_C:-4} -o /tmp/prof_${TAG}${arg} -f \
+      timeout ${NCU_TIMEOUT:-900} ncu --set full --clock-control none --import-source on ${NCU_EXTRA} -k "${NCU_K:-regex:tc_gemm_kernel}" -s ${NCU_S:-0} -c ${NCU_C:-4} -o /tmp/prof_${TAG}${arg} -f \
           python ${NCU_CMD:-bench.py --steps 1 --warmup 1 --no-cpu-baseline} > $OUT/ncu_${TAG}${arg}.log 2>&1; echo "capture exit $?"
       ncu -i /tmp/prof_${TAG}${arg}.ncu-rep --page raw --csv 2>/dev/null | gzip -9 > $OUT/ncu_raw_${TAG}${arg}.csv.gz
       python tools/ncu_summarize.py /tmp/prof_${TAG}${arg}.ncu-rep > $OUT/ncu_summary_${TAG}${arg}.json 2>/dev/null
