@@ -93,7 +93,7 @@ class ClockSampler:
 # --conv3: dense kernel; block-sparse over the cells EITHER box of a pair reaches (8x8 / 8x4-pixel blocks); or "shared": per pair
 # only the cells BOTH boxes reach, the rest taken from per-box maps computed once per box (block_rows, shared)
 CONV3_MODES = {"dense": (0, False, 8), "blocks8": (8, False, 8), "blocks4": (4, False, 8), "shared8": (8, True, 8), "shared4": (4, True, 8),
-               "shared44": (4, True, 4)}       # name: (block rows, shared footprint, block columns) in conv3 pixels
+               "shared44": (4, True, 4), "shared42": (2, True, 4)}       # name: (block rows, shared footprint, block columns) in conv3 pixels
 
 WORKLOADS = {
     # name: images per GPU, boxes (proposals) per image, SGDET-style?, pair chunk

@@ -31,7 +31,7 @@ __device__ __forceinline__ unsigned long long cell_mask(const Rect& r) {
 template <typename F>
 __device__ __forceinline__ int cover_greedy(unsigned long long m, int hc, int wc, F emit) {
   int n = 0;
-  const unsigned long long rows = (hc == 4) ? 0x01010101ull : 0x0101ull;
+  const unsigned long long rows = (hc == 4) ? 0x01010101ull : ((hc == 2) ? 0x0101ull : 0x01ull);
   const unsigned long long cols = (1ull << wc) - 1ull;
   while (m) {
     const int bit = __ffsll((long long)m) - 1;
@@ -224,8 +224,8 @@ static int conv3_blocks_list(const int32_t* boxes, const int32_t* pair_sub, cons
   if (rc != HC_OK) return rc;
   HC_REQUIRE(feature_size == 32, HC_E_SHAPE, "hc_conv3_active_blocks: built for feature_size 32 (8x8 pooled conv3 cells)");
   if (block_cols == 0) block_cols = 8;
-  HC_REQUIRE((block_rows == 8 || block_rows == 4) && (block_cols == 8 || (block_cols == 4 && block_rows == 4)), HC_E_SHAPE,
-             "hc_conv3_active_blocks: blocks are 8x8, 8x4 or 4x4 pixels (block_cols x block_rows)");
+  HC_REQUIRE(((block_rows == 8 || block_rows == 4) && (block_cols == 8 || (block_cols == 4 && block_rows == 4))) || (block_rows == 2 && block_cols == 4),
+             HC_E_SHAPE, "hc_conv3_active_blocks: blocks are 8x8, 8x4, 4x4 or 4x2 pixels (block_cols x block_rows)");
   HC_REQUIRE(n_pairs >= 0 && n_pairs < (1 << 23), HC_E_SHAPE, "hc_conv3_active_blocks: n_pairs must be below 2^23");
   HC_REQUIRE(aligned16(boxes), HC_E_ALIGN, "hc_conv3_active_blocks: boxes must be 16-byte aligned");   // n_pairs == 0 still writes n_blocks = 0
   conv3_blocks_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<const int4*>(boxes), pair_sub, pair_obj, n_pairs, feature_size, block_rows / 2,
@@ -338,8 +338,8 @@ extern "C" int hc_pair_cover_masks(const int32_t* boxes, const int32_t* pair_sub
   if (rc != HC_OK) return rc;
   HC_REQUIRE(feature_size == 32, HC_E_SHAPE, "hc_pair_cover_masks: built for feature_size 32 (8x8 pooled conv3 cells)");
   if (block_cols == 0) block_cols = 8;
-  HC_REQUIRE((block_rows == 8 || block_rows == 4) && (block_cols == 8 || (block_cols == 4 && block_rows == 4)), HC_E_SHAPE,
-             "hc_pair_cover_masks: blocks are 8x8, 8x4 or 4x4 pixels (block_cols x block_rows)");
+  HC_REQUIRE(((block_rows == 8 || block_rows == 4) && (block_cols == 8 || (block_cols == 4 && block_rows == 4))) || (block_rows == 2 && block_cols == 4),
+             HC_E_SHAPE, "hc_pair_cover_masks: blocks are 8x8, 8x4, 4x4 or 4x2 pixels (block_cols x block_rows)");
   HC_REQUIRE(aligned16(boxes), HC_E_ALIGN, "hc_pair_cover_masks: boxes must be 16-byte aligned");
   if (n_pairs <= 0) return HC_OK;
   pair_cover_masks_kernel<<<(n_pairs + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const int4*>(boxes), pair_sub, pair_obj, n_pairs,

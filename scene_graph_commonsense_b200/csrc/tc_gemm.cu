@@ -338,7 +338,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t stage_bytes = CG2 ? (uint32_t)C::CG2_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
   // pair tile (CG2): 16 listed blocks (256 pixels, the N side, half of them staged by each CTA) x 512 output channels (the M side:
   // 2 sub-tiles x 256 rows across the pair); a CTA keeps its 256 channels x 256 pixels in its 512 TMEM columns
-  constexpr int PAIR_BLOCKS = 16, PAIR_COUT = 2 * 2 * BM;
+  // (4x4-pixel blocks: 16 per tile, 8 staged by each CTA; 4x2-pixel blocks - one pooled cell tall: 32 per tile, 16 per CTA)
+  constexpr int PAIR_COUT = 2 * 2 * BM;
+  const int PAIR_BLOCKS = blk_mode ? 256 / (p.blk_w * p.blk_h) : 16;
   const int pair_ct = p.N / PAIR_COUT;                                 // output-channel tiles per pixel tile
   const int num_tiles = CG2 ? ((n_blocks + PAIR_BLOCKS - 1) / PAIR_BLOCKS) * pair_ct : tiles_m * p.tiles_n;
   const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -588,7 +590,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             __syncwarp();
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + j * BN + ch * 32), r);
 #pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {                 // the two blocks of this 32-column chunk (warp-uniform entries)
+            for (int hb = 0; hb < 4; ++hb) {                 // 4x2-pixel blocks: four per 32-column chunk, pixel (y, x) = column 4y + x,
+              if (p.blk_h != 2) break;                       // i.e. two pooled cells side by side
+              const int e = __ldg(p.blocks + min(m_blk * PAIR_BLOCKS + 4 * ch + hb, n_blocks - 1));
+              const int o_img = e >> 8, cy0 = (e >> 4) & 15, cx0 = e & 15;
+              const long long out_base = (long long)o_img * map_elems;
+#pragma unroll
+              for (int c = 0; c < 2; ++c) {
+                const int i0 = 8 * hb + 2 * c;
+                const float m = fmaxf(fmaxf(__uint_as_float(r[i0]), __uint_as_float(r[i0 + 1])),
+                                      fmaxf(__uint_as_float(r[i0 + 4]), __uint_as_float(r[i0 + 5])));
+                const unsigned short x = cvt16(fmaxf(m + bias, 0.0f), p.f16);
+                const long long off = ((long long)cy0 * (p.W / 2) + (cx0 + c)) * p.ldc + p.c_off + cout;
+                reinterpret_cast<unsigned short*>(p.out)[out_base + off] = x;
+              }
+            }
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {                 // 4x4-pixel blocks: the two blocks of this 32-column chunk (warp-uniform entries)
+              if (p.blk_h == 2) break;
               const int e = __ldg(p.blocks + min(m_blk * PAIR_BLOCKS + 2 * ch + hb, n_blocks - 1));
               const int o_img = e >> 8, cy0 = (e >> 4) & 15, cx0 = e & 15;
               // (the pooled-difference epilogue is split for pairs: this kernel writes the pooled value x by LOCAL pair into the
@@ -944,8 +963,9 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
              "hc_tc_gemm: pooled epilogue needs conv mode and a bias");
   const int blk_w = d->block_cols ? d->block_cols : 8;
   HC_REQUIRE(d->mode != HC_GEMM_CONV3_BLOCKS || ((pooled || d->epilogue == HC_EPI_BF16) && d->blocks && d->n_blocks &&
-                                                 (d->block_rows == 8 || d->block_rows == 4) && (blk_w == 8 || (blk_w == 4 && d->block_rows == 4))),
-             HC_E_SHAPE, "hc_tc_gemm: block-sparse conv needs a pooled or the bf16 epilogue, a work list and 8x8, 8x4 or 4x4-pixel blocks");
+                                                 (((d->block_rows == 8 || d->block_rows == 4) && (blk_w == 8 || (blk_w == 4 && d->block_rows == 4))) ||
+                                                  (blk_w == 4 && d->block_rows == 2 && d->cta_pairs))),
+             HC_E_SHAPE, "hc_tc_gemm: block-sparse conv needs a pooled or the bf16 epilogue, a work list and 8x8, 8x4, 4x4 or (CTA pairs only) 4x2-pixel blocks");
   HC_REQUIRE(d->epilogue != HC_EPI_POOL_DIFF_BF16 ||
                  (d->mode == HC_GEMM_CONV3_BLOCKS && d->diff_sub && d->diff_obj && d->diff_bg && d->pair_sub && d->pair_obj && d->pair_row &&
                   aligned16(d->diff_sub) && aligned16(d->diff_obj) && aligned16(d->diff_bg)),
@@ -1034,9 +1054,12 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   if (blk) {
     // the pair kernel is built for conv3_1's shape: 4x4-pixel blocks, pooled epilogues, 512-channel tiles, 256-row CTA tiles
     const bool diff = d->epilogue == HC_EPI_POOL_DIFF_BF16;
-    const bool pair_ok = pooled && blk_w == 4 && d->block_rows == 4 && d->n % 512 == 0 && MS == 2 && d->c_off == 0 && d->ldc == d->n &&
-                         (!diff || (d->scratch && aligned16(d->scratch)));
+    const bool pair_ok = pooled && blk_w == 4 && (d->block_rows == 4 || d->block_rows == 2) && d->n % 512 == 0 && MS == 2 && d->c_off == 0 &&
+                         d->ldc == d->n && (!diff || (d->scratch && aligned16(d->scratch)));
     p.cl2 = (pair_ok && d->cta_pairs) ? 1 : 0;
+    HC_REQUIRE(d->block_rows != 2 || p.cl2, HC_E_SHAPE,
+               "hc_tc_gemm: 4x2-pixel blocks run on the CTA-pair kernel only (pooled epilogue, m_sub 2, N % 512 == 0, c_off 0, ldc == N, scratch "
+               "for the difference epilogue)");
     static int env_dbg = -1;
     if (env_dbg == -1) { const char* e = getenv("HC_TC_DEBUG"); env_dbg = e ? atoi(e) : 0; }
     p.dbg = env_dbg;

@@ -197,11 +197,14 @@ class RelationPipeline:
         self.overlap = overlap
         # 0: dense conv3_1.  8 / 4: block-sparse conv3_1 - only 8 x {8,4}-pixel blocks that meet the dilated footprint of the
         # pair's two boxes are computed, the rest of the pooled output is a broadcast of the weights-only background
-        if conv3_block_rows not in (0, 4, 8):
-            raise ValueError("conv3_block_rows must be 0 (dense), 8 or 4")
+        if conv3_block_rows not in (0, 2, 4, 8):
+            raise ValueError("conv3_block_rows must be 0 (dense), 8, 4 or 2")
         self.conv3_block_rows = int(conv3_block_rows)
-        # block width in conv3 pixels: 8, or 4 (with 4 rows: 2 x 2-cell blocks hug the cell rectangles more tightly)
-        self.conv3_block_cols = 4 if (int(conv3_block_cols) == 4 and self.conv3_block_rows == 4) else 8
+        # block width in conv3 pixels: 8, or 4 (with 4 rows: 2 x 2-cell blocks hug the cell rectangles more tightly; with 2 rows: blocks
+        # one pooled cell tall and two wide - 11.6 % of the conv3_1 pixels at cfg2 where 2 x 2-cell blocks visit 15.2 %; CTA-pair kernel only)
+        self.conv3_block_cols = 4 if (int(conv3_block_cols) == 4 and self.conv3_block_rows in (2, 4)) else 8
+        if self.conv3_block_rows == 2 and self.conv3_block_cols != 4:
+            raise ValueError("2-row blocks are 4 pixels wide (conv3_block_cols=4)")
         # block-sparse only.  True: a cell of the pooled conv3_1 output that only ONE box of the pair reaches is taken from that
         # box's own map ((box, empty) / (empty, box), computed once per box of the window), so a pair computes only the cells
         # BOTH boxes reach.  False: every cell either box reaches is computed per pair.  Same bits either way.
@@ -222,7 +225,9 @@ class RelationPipeline:
         self.early_pool = os.environ.get("HC_EARLY_POOL", "1") != "0"     # first chunks' pooling starts under the per-box stages
         # conv3_1 on tcgen05 cta_group::2 CTA pairs (4x4-pixel blocks only): the pair shares the tile's pixel operand, so each SM
         # stages half of the small TMA boxes; bit-identical to the single-CTA kernel (tests/test_gpu_sparse.py)
-        self.conv3_pairs = int(os.environ.get("HC_CONV3_PAIRS", "1")) if (self.conv3_block_rows == 4 and self.conv3_block_cols == 4) else 0
+        self.conv3_pairs = int(os.environ.get("HC_CONV3_PAIRS", "1")) if (self.conv3_block_rows in (2, 4) and self.conv3_block_cols == 4) else 0
+        if self.conv3_block_rows == 2 and not (self.conv3_pairs and bool(conv3_shared) and bool(fc1_shared)):
+            raise ValueError("4x2-pixel blocks need the CTA-pair kernel on the shared-footprint path (conv3_shared, fc1_shared, HC_CONV3_PAIRS=1)")
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.last_k_masks = None             # int64 [n_tiles] device tensor: K-cell masks of the last shared fc1
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))

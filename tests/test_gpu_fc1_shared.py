@@ -66,7 +66,7 @@ def test_k_cell_sparse_gemm_equals_dense_bit_for_bit(m, with_tables):
     assert torch.equal(o2[perm.long()], o1)
 
 
-@pytest.mark.parametrize("block_rows,block_cols,cta_pairs", [(8, 8, 0), (4, 8, 0), (4, 4, 0), (4, 4, 1)])
+@pytest.mark.parametrize("block_rows,block_cols,cta_pairs", [(8, 8, 0), (4, 8, 0), (4, 4, 0), (4, 4, 1), (2, 4, 1)])
 def test_difference_epilogue_and_keys(block_rows, block_cols, cta_pairs):
     """HC_EPI_POOL_DIFF_BF16 == (x - sub_map) - (obj_map - background) on the dense kernel's x, bit for bit, at row pair_row[i]; zero in
     every covered cell that only one box reaches; keys / tile masks describe the cell rectangles both boxes reach."""
@@ -134,8 +134,8 @@ def test_difference_epilogue_and_keys(block_rows, block_cols, cta_pairs):
     assert float(ref[~both].float().abs().max()) == 0.0                        # and the dense formula agrees they are zero
 
 
-@pytest.mark.parametrize("tiled,block_cols", [(True, 4), (False, 4), (True, 8)])
-def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled, block_cols):
+@pytest.mark.parametrize("tiled,block_cols,block_rows", [(True, 4, 4), (False, 4, 4), (True, 8, 4), (True, 4, 2), (False, 4, 2)])
+def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled, block_cols, block_rows):
     """Whole forward, chunked and overlapped: joint probabilities within 2e-3 of the dense path (north_star's fp tolerance)."""
     from scene_graph_commonsense_b200 import pipeline
     pk = _packed(gain=40.0)
@@ -143,8 +143,8 @@ def test_pipeline_fc1_shared_within_tolerance_of_dense(tiled, block_cols):
     samples[0].bbox[:6] = torch.tensor(EDGE_BOXES[:6], dtype=samples[0].bbox.dtype)
     outs = []
     for fc1_shared in (False, True):
-        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=700, conv3_block_rows=4, conv3_shared=True,
-                                         fc1_shared=fc1_shared, conv3_block_cols=block_cols)
+        pipe = pipeline.RelationPipeline(pk, DEV, commonsense=True, chunk_pairs=700, conv3_block_rows=block_rows if fc1_shared else 4,
+                                         conv3_shared=True, fc1_shared=fc1_shared, conv3_block_cols=block_cols)
         pipe.debug_poison = True                  # footprint-aware pooling: a pixel conv3_1 reads but nobody wrote would be NaN
         b = pipeline.batch_from_samples(samples, DEV, skip_mode="per_image")
         pairs = pipe.enumerate_pairs(b)
@@ -186,7 +186,7 @@ def test_fc1_windows_are_bit_identical_to_one_window(tiled):
         assert torch.equal(a, c)
 
 
-@pytest.mark.parametrize("block_rows,block_cols,shared", [(4, 4, True), (4, 8, True), (8, 8, False)])
+@pytest.mark.parametrize("block_rows,block_cols,shared", [(4, 4, True), (4, 8, True), (8, 8, False), (2, 4, True)])
 def test_footprint_pooling_writes_exactly_what_the_blocks_read(block_rows, block_cols, shared):
     """`pair_cover_masks` == the union of the listed blocks of each pair; the tiled pooling with `cover` writes exactly the pooled
     pixels within one pixel of a covered cell, with the values of the full pooling."""

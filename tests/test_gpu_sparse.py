@@ -50,7 +50,7 @@ def _random_boxes(n, seed):
     return b
 
 
-SHAPES = [(8, 8), (4, 8), (4, 4)]           # (block_rows, block_cols) in conv3 pixels
+SHAPES = [(8, 8), (4, 8), (4, 4), (2, 4)]   # (block_rows, block_cols) in conv3 pixels; 2-row blocks run on the CTA-pair kernel only
 
 
 @pytest.mark.parametrize("block_rows,block_cols", SHAPES)
@@ -88,7 +88,7 @@ def _packed(seed=0, gain=1.0):
 
 
 @pytest.mark.parametrize("block_rows,m_sub,block_cols,cta_pairs", [(8, 2, 8, 0), (4, 2, 8, 0), (8, 1, 8, 0), (4, 1, 8, 0), (4, 2, 4, 0),
-                                                                   (4, 1, 4, 0), (4, 2, 4, 1)])
+                                                                   (4, 1, 4, 0), (4, 2, 4, 1), (2, 2, 4, 1)])
 def test_sparse_conv3_equals_dense_bit_for_bit(block_rows, m_sub, block_cols, cta_pairs):
     """conv3_1 + ReLU + pool on the listed blocks over a background pre-fill == the dense kernel, every bf16 bit
     (cta_pairs=1: the tcgen05 cta_group::2 pair kernel, weights on the M side, the tile's pixels shared by the two CTAs)."""
@@ -155,7 +155,7 @@ def test_shared_list_and_assembly_equal_dense_bit_for_bit(block_rows, block_cols
     p2b = ops.pair_relu_pool(u, v, None, s1, o1, 32)
     blk1, nb1 = ops.conv3_active_blocks(boxes_x, s1, o1, block_rows, block_cols=block_cols)
     maps = ops.broadcast_rows(pk.p3_background(), 2 * n_box, torch.empty(2 * n_box, 8, 8, 1024, dtype=torch.bfloat16, device=DEV))
-    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows, block_cols=block_cols)
+    pk.conv3_blocks(p2b, maps, 2 * n_box, blk1, nb1, block_rows, block_cols=block_cols, cta_pairs=int(block_rows == 2))
     # work list = cover of the intersection
     blocks, n_blocks = ops.conv3_shared_blocks(boxes_x, sub_t, obj_t, block_rows, block_cols=block_cols)
     nb = int(n_blocks.item())
@@ -176,7 +176,7 @@ def test_shared_list_and_assembly_equal_dense_bit_for_bit(block_rows, block_cols
     ops.p3_assemble(pk.p3_background(), maps[:n_box], maps[n_box:], boxes_x[:n_box], sub_t, obj_t, out)
     written = ~torch.isnan(out.float()).any(3).cpu().numpy()          # [n, 8, 8] cells the assembly wrote
     assert (written == ~want).all()
-    pk.conv3_blocks(p2, out, n, blocks, n_blocks, block_rows, block_cols=block_cols)
+    pk.conv3_blocks(p2, out, n, blocks, n_blocks, block_rows, block_cols=block_cols, cta_pairs=int(block_rows == 2))
     torch.cuda.synchronize()
     bad = (dense.view(torch.int16) != out.view(torch.int16)).flatten(1).any(1).nonzero().flatten().tolist()
     assert not bad, "pairs %s differ (boxes %s)" % (bad[:5], [(int(sub[i]), int(obj[i])) for i in bad[:5]])
