@@ -353,6 +353,8 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
         step_resident()
     torch.cuda.synchronize()
     t_host["enqueue"], t_host["allreduce"] = 0.0, []
+    from scene_graph_commonsense_b200 import _abi_ops
+    _abi_ops.SYNC_WAIT["s"], _abi_ops.SYNC_WAIT["n"] = 0.0, 0
 
     # ---- timed region 1: inputs resident in HBM
     sampler = ClockSampler(local)
@@ -374,6 +376,7 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
     hdist.barrier()
     ops.PROFILE["on"] = False
     launches = ops.LAUNCHES["n"] - launches0
+    sync_wait_ms, sync_reads = _abi_ops.SYNC_WAIT["s"] / steps * 1e3, _abi_ops.SYNC_WAIT["n"] / steps
     clocks = sampler.stop() if rank == 0 else None
     t_dev = e0.elapsed_time(e1) / 1e3
     t_max = hdist.max_over_ranks(t_dev, dev)
@@ -529,7 +532,12 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
         "conv3_blocks_per_step": blocks_step, "fc1_cells_per_step": fc1_cells, "conv2_executed_fraction": conv2_exec_frac,
         "kernel_breakdown": breakdown,
         "per_rank": {"ms_per_step_max": t_max / steps * 1e3, "ms_per_step_min": t_min / steps * 1e3,
-                     "allreduce_ms_per_step_rank0": allreduce_ms, "host_enqueue_ms_per_step_rank0": t_host["enqueue"] / steps * 1e3},
+                     "allreduce_ms_per_step_rank0": allreduce_ms,
+                     # host wall time inside step() per step, and how much of it was spent BLOCKED in device -> host reads (0 reads per
+                     # step when the batch carries host-counted pair offsets): the difference is the real enqueue work
+                     "host_step_ms_rank0": t_host["enqueue"] / steps * 1e3, "host_blocked_in_d2h_ms_rank0": sync_wait_ms,
+                     "d2h_syncs_per_step_rank0": sync_reads,
+                     "host_enqueue_ms_per_step_rank0": t_host["enqueue"] / steps * 1e3 - sync_wait_ms},
         "recall": {"R@20/50/100": m["evaluator"][0], "mR@20/50/100": [float(x) for x in m["evaluator"][2]],
                    "top3_R@20/50/100": m["top3"][0], "n_gt": int(counters_final[tables.EV_NGT])},
         "parity_sample": parity, "cpu_baseline": cpu,

@@ -134,10 +134,12 @@ typedef struct hc_gemm_desc {
   int64_t ld_mul;
   const int32_t* blocks;   /* CONV3_BLOCKS: device work list */
   const int32_t* n_blocks; /* CONV3_BLOCKS: device scalar, number of entries */
-  int32_t block_rows;      /* CONV3_BLOCKS: 8 or 4 */
-  int32_t block_cols;      /* CONV3_BLOCKS: 8 (or 0), or 4 with block_rows 4 */
-  int32_t cta_pairs;       /* CONV3_BLOCKS: 1 = tcgen05 cta_group::2 - clusters of 2 CTAs on two M tiles of one N tile, UMMA M = 256
-                              across the pair, each CTA stages half of every weight tile (same K order: bit-identical results) */
+  int32_t block_rows;      /* CONV3_BLOCKS: 8 or 4; 2 (blocks one pooled cell tall) with block_cols 4 and cta_pairs */
+  int32_t block_cols;      /* CONV3_BLOCKS: 8 (or 0), or 4 with block_rows 4 or 2 */
+  int32_t cta_pairs;       /* 1 = tcgen05 cta_group::2, clusters of 2 CTAs, UMMA M = 256 across the pair (same K order: bit-identical results).
+                              CONV3_BLOCKS (4-pixel-wide blocks, pooled epilogue): weights on the M side, the tile's 256 pixels shared by
+                              the pair, each CTA stages half of them.  PLAIN (N % 256 == 0, m_sub 1): a pair owns one 256 x 256 tile, each
+                              CTA staging its 128 rows of A and 128 columns of B per K step; k_masks stays per 256-row tile */
   const uint64_t* k_masks; /* PLAIN: per CTA M tile, bitmap of visited K cells (NULL = dense) */
   int64_t k_cell;          /* PLAIN + k_masks: K elements per cell (multiple of 64, K / k_cell <= 64) */
   const float* add_a;      /* EPI_BF16 row gathers, both or neither */

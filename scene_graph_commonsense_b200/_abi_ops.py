@@ -3,7 +3,9 @@
 PyTorch is plumbing here: it owns device memory and the stream; every computation below is a hand-written sm_100a
 kernel reached through ctypes.  `LAUNCHES` counts kernel launches issued through this module (bench.py reports it).
 """
+import contextlib
 import ctypes as C
+import time
 
 import numpy as np
 import torch
@@ -29,6 +31,19 @@ def _f16(*tensors):
 
 def _count(n=1):
     LAUNCHES["n"] += n
+
+
+SYNC_WAIT = {"s": 0.0, "n": 0}       # host seconds spent blocked in device -> host reads on the step path (bench.py reports it)
+
+
+@contextlib.contextmanager
+def _sync_wait():
+    t0 = time.perf_counter()
+    try:
+        yield
+    finally:
+        SYNC_WAIT["s"] += time.perf_counter() - t0
+        SYNC_WAIT["n"] += 1
 
 
 class _timed:
@@ -62,9 +77,11 @@ def cs_bitmap_build(aligned_keys, violated_keys):
 
 
 def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tri=None, group_id=None, n_groups=0,
-                    max_tri=0, feature_size=32):
+                    max_tri=0, feature_size=32, offsets_host=None):
     """R1/R2/R4.  `p_max` = sum_i N_i(N_i-1) (host int, known from the CSR the caller built).  Returns a dict of
-    device arrays trimmed to the number of surviving directed pairs (one 4-byte D2H read of the total)."""
+    device arrays trimmed to the number of surviving directed pairs.  The per-image pair offsets size the later launches on the
+    host: they are read back from the device (one small D2H sync) unless the caller already counted them (`offsets_host`, int32
+    [B+1], pipeline.host_pair_offsets) - then nothing is read back and the call returns without synchronising."""
     require_cuda(boxes, box_offsets, tri_offsets, rel_tri, dir_tri, group_id)
     dev = boxes.device
     n_images = box_offsets.numel() - 1
@@ -82,9 +99,15 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
                                          ptr(pair_img), ptr(pair_ov), ptr(pair_gt), ptr(pair_rel), ptr(total),
                                          stream_ptr()), "hc_pairs_enumerate")
     _count(4)
-    offsets_host = pair_offsets.cpu()                 # [B+1] ints: the one D2H sync of the step (sizes the GEMM launches)
+    if offsets_host is None:
+        with _sync_wait():
+            offsets_host = pair_offsets.cpu().numpy()     # [B+1] ints: the one D2H sync of the step (sizes the GEMM launches)
+    else:
+        offsets_host = np.asarray(offsets_host)
+        if offsets_host.shape != (n_images + 1,):
+            raise RuntimeError("hiercom_b200: pairs_enumerate: offsets_host must hold n_images + 1 entries")
     n = int(offsets_host[-1])
-    return dict(n=n, offsets=pair_offsets, offsets_host=offsets_host.numpy(), sub=pair_sub[:n], obj=pair_obj[:n], img=pair_img[:n], ov=pair_ov[:n],
+    return dict(n=n, offsets=pair_offsets, offsets_host=offsets_host, sub=pair_sub[:n], obj=pair_obj[:n], img=pair_img[:n], ov=pair_ov[:n],
                 gt=pair_gt[:n], rel=pair_rel[:n])
 
 

@@ -342,7 +342,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int PAIR_COUT = 2 * 2 * BM;
   const int PAIR_BLOCKS = blk_mode ? 256 / (p.blk_w * p.blk_h) : 16;
   const int pair_ct = p.N / PAIR_COUT;                                 // output-channel tiles per pixel tile
-  const int num_tiles = CG2 ? ((n_blocks + PAIR_BLOCKS - 1) / PAIR_BLOCKS) * pair_ct : tiles_m * p.tiles_n;
+  // (plain GEMM on pairs: a pair owns one 256-row M tile - 128 rows per CTA - of one N tile; p.tiles_m counts 256-row tiles)
+  const int num_tiles = CG2 ? (blk_mode ? ((n_blocks + PAIR_BLOCKS - 1) / PAIR_BLOCKS) * pair_ct : tiles_m * p.tiles_n) : tiles_m * p.tiles_n;
   const int tile0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int num_kb = p.K / BK;
@@ -451,7 +452,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
         }
       }
-    } else if (!CG2 && lane == 0) {
+    } else if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -461,11 +462,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
           const uint32_t b_dst = a_dst + MS * A_SUB_BYTES;
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if constexpr (CG2) {
+            // pair: this CTA stages ITS 128 rows of the 256-row M tile (per sub-tile) and ITS half of the weight tile's columns; the
+            // leader's full barrier counts the bytes of both CTAs (the peer only sends bytes, it never arrives)
+            const uint32_t lead_full = full_bar(stage) & PEER_BIT_MASK;
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)C::CG2_STAGE_BYTES);
 #pragma unroll
-          for (int j = 0; j < MS; ++j)
-            tma_load_2d(a_dst + j * A_SUB_BYTES, &tmap_a, full_bar(stage), kb * BK, (m_blk * MS + j) * BM);
-          tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+            for (int j = 0; j < MS; ++j)
+              tma_load_2d_cg2(a_dst + j * A_SUB_BYTES, &tmap_a, lead_full, kb * BK, ((m_blk * MS + j) * 2 + rank) * BM);
+            tma_load_2d_cg2(b_dst, &tmap_bh, lead_full, kb * BK, n_blk * BN + rank * (BN / 2));
+          } else {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+#pragma unroll
+            for (int j = 0; j < MS; ++j)
+              tma_load_2d(a_dst + j * A_SUB_BYTES, &tmap_a, full_bar(stage), kb * BK, (m_blk * MS + j) * BM);
+            tma_load_2d(b_dst, &tmap_b, full_bar(stage), kb * BK, n_blk * BN);
+          }
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
         };
         if (p.k_masks) {
@@ -559,8 +571,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int kb = 0; kb < num_kb; ++kb) mma_kb();
         }
         // accumulator complete once the MMAs above retire; an empty cell mask issued none: plain arrive, the epilogue substitutes zeros
-        if constexpr (CG2) umma_commit_cg2(tfull_bar(acc), (uint16_t)3);     // both CTAs' epilogues (block mode always issues MMAs)
-        else if (started) umma_commit(tfull_bar(acc));
+        if constexpr (CG2) {
+          if (started) umma_commit_cg2(tfull_bar(acc), (uint16_t)3);         // both CTAs' epilogues
+          else { mbar_arrive(tfull_bar(acc)); mbar_arrive_cluster((tfull_bar(acc) & PEER_BIT_MASK) | ~PEER_BIT_MASK); }   // empty cell mask: no MMA to wait for
+        } else if (started) umma_commit(tfull_bar(acc));
         else mbar_arrive(tfull_bar(acc));
         if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
@@ -573,7 +587,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_step) {
-      if constexpr (CG2) {
+      if (CG2 && blk_mode) {
         // Pair tile, transposed roles: TMEM lanes are OUTPUT CHANNELS (this thread owns one channel of sub-tile j), columns are the
         // 256 pixels of the tile's 16 blocks - a 4x4-pixel block is 16 consecutive columns, so the 2x2 max-pool is register-local.
         const int m_blk = tile / pair_ct, n_blk = tile - m_blk * pair_ct;
@@ -728,6 +742,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           } else {
             // output row of tile row `tr` (plain: GEMM row; conv: NHWC pixel index), -1 when outside M
             auto out_row = [&](int tr) -> long long {
+              if constexpr (CG2) {   // plain GEMM on a pair: this CTA holds rows [rank*128, +128) of sub-tile j of the 256-row tile
+                long long row = ((long long)(m_blk * MS + j) * 2 + rank) * BM + tr;
+                return row < p.M ? row : -1;
+              }
               if (p.mode == HC_GEMM_CONV3)
                 return ((long long)t_img * p.H + (t_y0 + 8 * j + (tr >> 4))) * p.W + (t_x0 + (tr & 15));
               if (blk_mode) {   // un-pooled block mode: tile row -> pixel (y0 + r / blk_w, x0 + r % blk_w) of its block's image
@@ -826,7 +844,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if constexpr (CG2) mbar_arrive_cluster(tempty_bar(acc) & PEER_BIT_MASK);   // the leader's barrier collects both CTAs' epilogue warps
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
   }
@@ -918,6 +939,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     configured[dev] = true;
   }
   int tiles = p.tiles_m * p.tiles_n;
+  if (CG2 && p.mode == HC_GEMM_PLAIN) tiles *= 2;                                          // a pair of CTAs per tile
   int grid = (p.mode == HC_GEMM_CONV3_BLOCKS || tiles >= num_sms()) ? num_sms() : tiles;   // block mode: tile count lives on the device
   if (CG2) {
     cudaLaunchConfig_t cfg;
@@ -1075,6 +1097,17 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
         reinterpret_cast<const uint4*>(d->diff_obj), reinterpret_cast<const uint4*>(d->diff_bg), d->pair_sub, d->pair_obj, d->pair_row,
         blk_w / 2, d->block_rows / 2, d->w / 2, cell_vec, map_vec, reinterpret_cast<uint4*>(d->out), p.f16);
     return cuda_status("pair_diff_kernel launch");
+  }
+  // plain GEMM on tcgen05 cta_group::2 pairs (d->cta_pairs, N % 256 == 0, m_sub 1): a pair owns one 256 x 256 tile, each CTA staging its 128
+  // rows of A and its 128 columns of B per K step and keeping two accumulator stages, so the chip has half as many M tiles in flight
+  // (K-cell-sparse fc1: half the distinct weight slabs streaming through L2 at a time) and the epilogue overlaps the next tile
+  if (d->mode == HC_GEMM_PLAIN && d->cta_pairs) {
+    HC_REQUIRE(BN == 256 && MS == 1 && d->epilogue != HC_EPI_SPLIT3_BF16, HC_E_SHAPE,
+               "hc_tc_gemm: plain-GEMM CTA pairs need N % 256 == 0, m_sub 1 and a bf16 / f32 epilogue");
+    p.cl2 = 1;
+    p.tiles_m = (int)((d->m + 2 * tc::BM - 1) / (2 * tc::BM));
+    if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
+    return tc::launch<256, 1, true>(ta, tb, tbh, p, stream);
   }
   if (BN == 256 && MS == 1) return tc::launch<256, 1, false>(ta, tb, tbh, p, stream);
   if (BN == 256 && MS == 2) return tc::launch<256, 2, false>(ta, tb, tbh, p, stream);

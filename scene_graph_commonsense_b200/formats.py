@@ -85,7 +85,7 @@ def load_window(path):
 
 def host_batch_from_packed(packed, feat=None, skip_mode="batch", group_size=None, pinned=True):
     """Packed window (+ the DETR feature maps `feat` [B,256,32,32], produced by reference code) -> pipeline.HostBatch."""
-    from .pipeline import HostBatch, footprint_cover_fraction
+    from .pipeline import HostBatch, footprint_cover_fraction, host_pair_offsets
     arrays = {k: packed[k] for k in ("box_offsets", "tri_offsets", "boxes", "cats", "supers", "box_img", "rel_tri", "dir_tri")}
     counts = np.diff(packed["box_offsets"]).astype(np.int64)
     n_img = len(counts)
@@ -99,7 +99,8 @@ def host_batch_from_packed(packed, feat=None, skip_mode="batch", group_size=None
         arrays["depth"] = torch.as_tensor(packed["depth"], dtype=torch.float32)
     tri = counts * (counts - 1) // 2
     meta = dict(n_groups=n_groups, max_tri=int(tri.max()) if n_img else 0, p_max=int((counts * (counts - 1)).sum()),
-                cover_fraction=footprint_cover_fraction(arrays["boxes"], arrays["box_offsets"]))
+                cover_fraction=footprint_cover_fraction(arrays["boxes"], arrays["box_offsets"]),
+                pair_offsets=host_pair_offsets(arrays["boxes"], arrays["box_offsets"], arrays.get("group_id")))
     return HostBatch(arrays, meta, pinned)
 
 

@@ -196,8 +196,9 @@ class PackedHead:
     def fc1_rows(self, maps, n):
         """fc1 WITHOUT bias / activation of n pooled maps [n,8,8,1024] bf16 -> f32 [n,4096] (the per-box terms of the shared fc1)."""
         out = torch.empty(n, 4096, dtype=torch.float32, device=maps.device)
-        ops.tc_gemm(maps, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=37, m_sub=2 if n > 128 else 1,
-                    tag="fc1_box")
+        pairs = int(os.environ.get("HC_FC1_BOX_PAIRS", "0")) if n > 128 else 0      # cta_group::2 pairs on 256-row tiles (see fc1_shared_fc2)
+        ops.tc_gemm(maps, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=int(os.environ.get("HC_FC1_BOX_GROUP_M", "37")),
+                    m_sub=1 if pairs else (2 if n > 128 else 1), tag="fc1_box", cta_pairs=pairs)
         return out
 
     def fc1_shared_fc2(self, d, n, k_masks, f_sub, f_obj, row_sub, row_obj, bias_eff, out_rows, raw, group_m=None):
@@ -207,10 +208,15 @@ class PackedHead:
         # rasterisation: a band of 9 M tiles x all 16 N tiles = 144 CTAs run together.  The rows are sorted by cell rectangle, so the
         # 9 tiles walk (nearly) the same K cells in step: each weight panel and each operand tile comes out of HBM once per band
         # and is shared through L2 (bands of 37 x 4 re-read the operand 4x and thrashed L2: 38.9 GB of DRAM reads per launch, ncu r01y)
+        # HC_FC1_PAIRS=1: tcgen05 cta_group::2 pairs - a pair of CTAs owns one 256 x 256 tile (128 rows each, half of the weight tile's
+        # columns each), so 74 tiles = 4.6 M tiles are in flight instead of 9.25: half as many distinct weight slabs stream through L2
+        # at a time (the single-CTA launch re-reads the weights from HBM for nearly every (M tile, cell): 41 GB per launch, ncu r02i)
+        pairs = int(os.environ.get("HC_FC1_PAIRS", "0"))
         if group_m is None:
-            group_m = int(os.environ.get("HC_FC1_GROUP_M", "9"))
+            group_m = int(os.environ.get("HC_FC1_GROUP_M", "4" if pairs else "9"))
         ops.tc_gemm(d, self.w_fc1, h1, n, 4096, 65536, bias=bias_eff, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU, group_m=group_m,
-                    m_sub=2, tag="fc1", k_masks=k_masks, k_cell=1024, add_a=f_sub, add_a_rows=row_sub, add_b=f_obj, add_b_rows=row_obj)
+                    m_sub=1 if pairs else 2, tag="fc1", k_masks=k_masks, k_cell=1024, add_a=f_sub, add_a_rows=row_sub, add_b=f_obj,
+                    add_b_rows=row_obj, cta_pairs=pairs)
         ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8, tag="fc2", out_rows=out_rows)
         return raw
 

@@ -7,6 +7,7 @@ The module-level functions below keep the call signatures the rest of the packag
 route every call through `torch.ops.hiercom.<name>`, so model.py, evaluator.py, pipeline.py, sgb.py and frontend.py all reach
 the kernels through the dispatcher.  Operators that fill a caller-owned buffer declare it `Tensor(a!)`.
 """
+import numpy as np
 import torch
 
 from . import _abi_ops as _A
@@ -41,16 +42,20 @@ def _some(t, like):
 
 # ------------------------------------------------------------------------------------------------ R1/R2/R4 pair enumeration
 @_op("pairs_enumerate", "(Tensor boxes, Tensor box_offsets, Tensor tri_offsets, int p_max, Tensor? rel_tri, Tensor? dir_tri, "
-     "Tensor? group_id, int n_groups, int max_tri, int feature_size) -> Tensor[]")
-def _pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri, dir_tri, group_id, n_groups, max_tri, feature_size):
-    d = _A.pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri, dir_tri, group_id, n_groups, max_tri, feature_size)
-    return [d["offsets"], torch.from_numpy(d["offsets_host"]), d["sub"], d["obj"], d["img"], d["ov"], d["gt"], d["rel"]]
+     "Tensor? group_id, int n_groups, int max_tri, int feature_size, int[]? offsets_host) -> Tensor[]")
+def _pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri, dir_tri, group_id, n_groups, max_tri, feature_size, offsets_host):
+    known = None if offsets_host is None else np.asarray(offsets_host, dtype=np.int32)
+    d = _A.pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri, dir_tri, group_id, n_groups, max_tri, feature_size, offsets_host=known)
+    return [d["offsets"], torch.from_numpy(np.ascontiguousarray(d["offsets_host"])), d["sub"], d["obj"], d["img"], d["ov"], d["gt"], d["rel"]]
 
 
 def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tri=None, group_id=None, n_groups=0, max_tri=0,
-                    feature_size=32):
+                    feature_size=32, offsets_host=None):
+    """`offsets_host` (int32 [B+1], pipeline.host_pair_offsets): the per-image pair offsets counted on the host - with them the call
+    reads nothing back from the device."""
+    known = None if offsets_host is None else [int(v) for v in offsets_host]
     off, off_host, sub, obj, img, ov, gt, rel = _call("pairs_enumerate")(boxes, box_offsets, tri_offsets, p_max, rel_tri, dir_tri,
-                                                                        group_id, n_groups, max_tri, feature_size)
+                                                                        group_id, n_groups, max_tri, feature_size, known)
     off_host = off_host.numpy()
     return dict(n=int(off_host[-1]), offsets=off, offsets_host=off_host, sub=sub, obj=obj, img=img, ov=ov, gt=gt, rel=rel)
 

@@ -51,6 +51,7 @@ class DeviceBatch:
     box_offsets_host: Optional[np.ndarray] = None
     gt: Optional[dict] = None                  # flat GT triplet tables (targets.flat_targets_sgd)
     cover_fraction: Optional[float] = None     # host estimate: share of the conv3_1 pixels the shared-footprint work lists would visit
+    pair_offsets_host: Optional[np.ndarray] = None   # int32 [B+1] directed-pair offsets counted on the host (host_pair_offsets): no D2H per step
 
     @property
     def n_images(self):
@@ -82,7 +83,8 @@ class HostBatch:
         return DeviceBatch(d.get("feat"), d.get("depth"), d["boxes"], d["box_offsets"], d["box_img"], d["cats"], d["supers"],
                            d["tri_offsets"], d.get("rel_tri"), d.get("dir_tri"), d.get("group_id"), m["n_groups"], m["max_tri"],
                            m["p_max"], self.h2d_bytes, conf=d.get("conf"), gt=gt,
-                           box_offsets_host=self.t["box_offsets"].numpy(), cover_fraction=m.get("cover_fraction"))
+                           box_offsets_host=self.t["box_offsets"].numpy(), cover_fraction=m.get("cover_fraction"),
+                           pair_offsets_host=m.get("pair_offsets"))
 
 
 def _cell_interval(lo, hi):
@@ -114,6 +116,43 @@ def footprint_cover_fraction(boxes, box_offsets, fs=32):
         blocks += int(t.sum() - np.trace(t))
         pairs += n * (n - 1)
     return blocks * 4.0 / (64.0 * pairs) if pairs else 0.0
+
+
+def host_pair_offsets(boxes, box_offsets, group_id=None, fs=32):
+    """Host twin (numpy, at batch-build time) of the COUNTING half of hc_pairs_enumerate (R1/R2/R4, evaluate.py:111-116,132-156):
+    the directed-pair CSR offsets int32 [B+1] the device will produce, so the step needs no device -> host read to size its launches.
+    A pair (g, e) of image i is overlapping iff the two rectangles - Python slice semantics of the reference's masks - intersect;
+    it survives iff it overlaps (`group_id` None: per-image rule) or overlaps in ANY image of i's lock-step group that has it (batch rule)."""
+    b = np.asarray(boxes, dtype=np.int64).reshape(-1, 4)
+
+    def sb(v):
+        v = np.where(v < 0, np.maximum(v + fs, 0), v)
+        return np.minimum(v, fs)
+
+    x0, x1, y0, y1 = sb(b[:, 0]), sb(b[:, 1]), sb(b[:, 2]), sb(b[:, 3])
+    x1, y1 = np.maximum(x1, x0), np.maximum(y1, y0)
+    n_img = len(box_offsets) - 1
+    ovs = []
+    for i in range(n_img):
+        s, e = int(box_offsets[i]), int(box_offsets[i + 1])
+        g, l = np.tril_indices(e - s, -1)                    # t = g(g-1)/2 + e in the reference's loop order (g outer, e < g)
+        w = np.minimum(x1[s + g], x1[s + l]) - np.maximum(x0[s + g], x0[s + l])
+        h = np.minimum(y1[s + g], y1[s + l]) - np.maximum(y0[s + g], y0[s + l])
+        ovs.append((w > 0) & (h > 0))
+    counts = np.zeros(n_img, dtype=np.int64)
+    if group_id is None:
+        for i, ov in enumerate(ovs):
+            counts[i] = int(ov.sum())
+    else:
+        gid = np.asarray(group_id)
+        for gval in np.unique(gid):
+            members = np.nonzero(gid == gval)[0]
+            any_t = np.zeros(max((len(ovs[i]) for i in members), default=0), dtype=bool)
+            for i in members:
+                any_t[:len(ovs[i])] |= ovs[i]
+            for i in members:
+                counts[i] = int(any_t[:len(ovs[i])].sum())
+    return np.concatenate(([0], np.cumsum(2 * counts))).astype(np.int32)
 
 
 def host_batch_from_samples(samples, skip_mode="batch", group_size=None, sgdet=False, pinned=True, with_maps=True):
@@ -161,7 +200,8 @@ def host_batch_from_samples(samples, skip_mode="batch", group_size=None, sgdet=F
         for k, v in flat_targets_sgd(samples).items():
             arrays["gt_" + k] = v
     meta = dict(n_groups=n_groups, max_tri=int(tri.max()) if len(tri) else 0, p_max=int((counts * (counts - 1)).sum()),
-                cover_fraction=footprint_cover_fraction(arrays["boxes"], arrays["box_offsets"]))
+                cover_fraction=footprint_cover_fraction(arrays["boxes"], arrays["box_offsets"]),
+                pair_offsets=host_pair_offsets(arrays["boxes"], arrays["box_offsets"], arrays.get("group_id")))
     return HostBatch(arrays, meta, pinned)
 
 
@@ -183,6 +223,7 @@ class RelationPipeline:
         # vs 226 ms dense, profiles/bench_r02g_*).  Same scores either way (bit-identical conv3_1, fc1 to fp32 rounding order).
         self.dense_above = float(dense_above)
         self.last_path = None               # "shared" / "blocks" / "dense": the formulation the last forward_pairs took
+        self.host_offsets = os.environ.get("HC_HOST_OFFSETS", "1") != "0"    # use DeviceBatch.pair_offsets_host (no D2H read per step)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("hiercom_b200: RelationPipeline needs a CUDA device (no CPU fallback)")
@@ -245,8 +286,11 @@ class RelationPipeline:
 
     # ------------------------------------------------------------------------------------------------ stages
     def enumerate_pairs(self, b: DeviceBatch):
+        """R1/R2/R4.  With `b.pair_offsets_host` (counted when the batch was built) nothing is read back from the device: the step is
+        enqueued without a host sync, so the host runs ahead of the GPU instead of idling it at every window boundary."""
+        known = b.pair_offsets_host if self.host_offsets else None
         return ops.pairs_enumerate(b.boxes, b.box_offsets, b.tri_offsets, b.p_max, b.rel_tri, b.dir_tri, b.group_id, b.n_groups,
-                                   b.max_tri, self.fs)
+                                   b.max_tri, self.fs, offsets_host=known)
 
     def box_features(self, b: DeviceBatch, boxes=None, box_img=None):
         """Per-image conv1 (+tanh), per-box mask select, per-box conv2 halves -> U, V [nbox,32,32,512] bf16."""
@@ -644,12 +688,15 @@ class RelationPipeline:
         self.evaluate(b, pairs, relation, sup, logsig, connectivity=conn)
         return pairs["n"]
 
-    def run(self, host_batches, before_step=None, after_step=None):
-        """Streams evaluation windows from pinned host staging: yields `(n_pairs, counters_host)` per window.  The H2D copy of
-        window k+1 is issued on a copy stream before window k's kernels are enqueued, so it rides under window k's compute;
-        every window's inputs still cross PCIe exactly once and its counters are read back (D2H) before the next window's
-        result is produced.  `before_step(self)` / `after_step(self)` hook in a counter reset / the cross-rank all-reduce (a tensor
-        returned by `after_step` - the reduced copy - is what gets read back instead of the rank-local counters)."""
+    def run(self, host_batches, before_step=None, after_step=None, pipelined=True):
+        """Streams evaluation windows from pinned host staging: yields `(n_pairs, counters_host)` per window, in order.  The H2D copy
+        of window k+1 is issued on a copy stream before window k's kernels are enqueued, so it rides under window k's compute;
+        every window's inputs cross PCIe exactly once and every window's counters are read back (D2H into pinned memory).
+        `pipelined`: the read-back of window k is an asynchronous copy behind its kernels and is handed out AFTER window k+1 has
+        been enqueued, so the GPU never waits for the host between windows (with `DeviceBatch.pair_offsets_host` the step itself
+        has no host sync either); `pipelined=False` reads window k back before window k+1 is enqueued.
+        `before_step(self)` / `after_step(self)` hook in a counter reset / the cross-rank all-reduce (a tensor returned by
+        `after_step` - the reduced copy - is what gets read back instead of the rank-local counters)."""
         main = torch.cuda.current_stream(self.device)
         if getattr(self, "_copy", None) is None:
             self._copy = torch.cuda.Stream(device=self.device)
@@ -666,6 +713,7 @@ class RelationPipeline:
                 ready.record(copy)
             return b, ready
 
+        pending = None                      # (n_pairs, pinned result, event) of the previous window
         nxt = fetch()
         while nxt is not None:
             b, ready = nxt
@@ -682,7 +730,20 @@ class RelationPipeline:
                 r = after_step(self)
                 if isinstance(r, torch.Tensor):        # e.g. dist.allreduce_counters(self.counters): the GLOBAL sums are read back
                     result = r
-            yield n, result.cpu()
+            if not pipelined:
+                yield n, result.cpu()
+                continue
+            host = torch.empty(result.shape, dtype=result.dtype, pin_memory=True)
+            host.copy_(result, non_blocking=True)      # stream-ordered behind this window's kernels, before the next reset
+            done = torch.cuda.Event()
+            done.record(main)
+            if pending is not None:
+                pending[2].synchronize()
+                yield pending[0], pending[1]
+            pending = (n, host, done)
+        if pending is not None:
+            pending[2].synchronize()
+            yield pending[0], pending[1]
 
     # ------------------------------------------------------------------------------------------------ results
     def reset(self):

@@ -221,7 +221,7 @@ def test_formats_annotation_pkl_to_packed_window_roundtrip(tmp_path):
     ref = pipeline.host_batch_from_samples([s, s], pinned=False, with_maps=False)
     for k in ("box_offsets", "tri_offsets", "boxes", "cats", "supers", "box_img", "rel_tri", "dir_tri", "group_id"):
         assert torch.equal(hb.t[k], ref.t[k]), k
-    assert hb.meta == ref.meta
+    assert hb.meta.keys() == ref.meta.keys() and all(np.array_equal(hb.meta[k], ref.meta[k]) for k in ref.meta)
     d = formats.keys_to_commonsense_dict(tables.commonsense_violated_keys()[:50])
     np.testing.assert_array_equal(np.sort(tables.dict_to_keys(d)), np.sort(tables.commonsense_violated_keys()[:50]))
 
@@ -454,3 +454,28 @@ def test_gt_from_ranking_places_ranked_triplets_once_per_unordered_pair():
     assert 0 < n_after < n_before
     s3 = synthetic.assign_gt_from_ranking(synthetic.make_image(11, 12, with_maps=False), ranked)
     assert all(torch.equal(a, b) for a, b in zip(s2.relationships, s3.relationships))                     # deterministic
+
+
+def test_host_pair_offsets_equal_the_oracle_enumeration_in_both_skip_modes():
+    """`pipeline.host_pair_offsets` (what lets a step run without a device -> host read) == the per-image directed-pair counts of
+    the oracle's replay of evaluate.py:132-156, for the per-image and the whole-batch skip rule, ragged images, degenerate,
+    negative and out-of-range boxes."""
+    from oracle import hiercom_oracle as O
+    from scene_graph_commonsense_b200 import pipeline, synthetic
+    samples = synthetic.make_batch([21, 22, 23, 24, 25], [9, 1, 14, 2, 7], with_maps=False)
+    samples[0].bbox[:5] = torch.tensor([(0, 32, 0, 32), (5, 5, 3, 9), (9, 3, 2, 7), (-4, 32, 3, 12), (30, 40, -2, 2)], dtype=samples[0].bbox.dtype)
+    for mode, gs in (("per_image", None), ("batch", None), ("batch", 2)):
+        hb = pipeline.host_batch_from_samples(samples, skip_mode=mode, group_size=gs, with_maps=False, pinned=False)
+        got = np.diff(hb.meta["pair_offsets"])
+        groups = [list(range(len(samples)))] if gs is None else [list(range(i, min(i + gs, len(samples)))) for i in range(0, len(samples), gs)]
+        want = np.zeros(len(samples), dtype=np.int64)
+        for grp in (groups if mode == "batch" else [[i] for i in range(len(samples))]):
+            masks = [[O.box_mask(b) for b in samples[i].bbox] for i in grp]
+            n_max = max(len(m) for m in masks)
+            for g in range(1, n_max):
+                for e in range(g):
+                    has = [k for k, m in enumerate(masks) if len(m) > g]
+                    if any(bool((masks[k][g] & masks[k][e]).any()) for k in has):
+                        for k in has:
+                            want[grp[k]] += 2
+        np.testing.assert_array_equal(got, want)

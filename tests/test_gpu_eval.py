@@ -269,3 +269,23 @@ def test_bayesian_head_module_matches_reference_golden():
     b1, b2, b3, bs = bh(h)
     np.testing.assert_allclose(torch.cat((b1, b2, b3), 1).cpu().numpy(), g["bhead_relation"], atol=2e-4, rtol=0)
     np.testing.assert_allclose(bs.cpu().numpy(), g["bhead_super"], atol=2e-4, rtol=0)
+
+
+@pytest.mark.parametrize("mode,gs", [("per_image", None), ("batch", None), ("batch", 3)])
+def test_host_counted_pair_offsets_equal_the_device_enumeration(mode, gs):
+    """The offsets `host_batch_from_samples` counts on the host (so that a step needs no device -> host read) are exactly what
+    hc_pairs_enumerate produces, and the pair lists do not depend on which of the two sized them."""
+    _, ops, pipeline = _mods()
+    samples = synthetic.make_batch([31, 32, 33, 34, 35, 36, 37], [9, 1, 14, 2, 7, 40, 11], with_maps=False)
+    samples[0].bbox[:5] = torch.tensor([(0, 32, 0, 32), (5, 5, 3, 9), (9, 3, 2, 7), (-4, 32, 3, 12), (30, 40, -2, 2)], dtype=samples[0].bbox.dtype)
+    b = pipeline.batch_from_samples(samples, DEV, skip_mode=mode, group_size=gs, with_maps=False)
+    pipe = pipeline.RelationPipeline(None, DEV, commonsense=False)
+    assert pipe.host_offsets and b.pair_offsets_host is not None
+    fast = pipe.enumerate_pairs(b)
+    pipe.host_offsets = False
+    slow = pipe.enumerate_pairs(b)
+    np.testing.assert_array_equal(slow["offsets_host"], b.pair_offsets_host)
+    np.testing.assert_array_equal(fast["offsets"].cpu().numpy(), b.pair_offsets_host)
+    assert fast["n"] == slow["n"] > 0
+    for k in ("sub", "obj", "img", "ov", "gt", "rel"):
+        assert torch.equal(fast[k], slow[k]), k

@@ -223,3 +223,45 @@ def test_footprint_pooling_writes_exactly_what_the_blocks_read(block_rows, block
     assert (written == need).all()
     m = torch.from_numpy(need).to(DEV)
     assert torch.equal(part[m].view(torch.int16), full[m].view(torch.int16))
+
+
+@pytest.mark.parametrize("m,k_sparse", [(700, True), (1024, True), (300, False), (5121, False)])
+def test_plain_gemm_on_cta_pairs_equals_single_cta_bit_for_bit(m, k_sparse):
+    """PLAIN GEMM on tcgen05 cta_group::2 pairs (a pair owns one 256 x 256 tile: 128 rows of A and 128 columns of B per CTA and K
+    step): same K order per output element, so every bit equals the single-CTA kernel - dense, K-cell-sparse with row gathers and an
+    output row map (empty-mask tiles included), f32 and 16-bit epilogues, ragged M."""
+    from scene_graph_commonsense_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n, k, cell = 512, 16 * 256, 256
+    a = (torch.randn(m, k, generator=g) * 0.3).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(n, k, generator=g) * 0.05).to(torch.bfloat16).to(DEV)
+    bias = torch.randn(n, generator=g).to(DEV)
+    kw = {}
+    if k_sparse:
+        tiles = -(-m // 256)
+        masks = torch.randint(0, 1 << 16, (tiles,), generator=g, dtype=torch.int64)
+        masks[0] = 0                                                        # an empty mask: no MMA, the epilogue substitutes zeros
+        for t in range(tiles):                                              # operand is zero wherever the tile's mask skips
+            for c in range(16):
+                if not (int(masks[t]) >> c) & 1:
+                    a[256 * t:256 * (t + 1), cell * c:cell * (c + 1)] = 0
+        fa, fb = torch.randn(9, n, generator=g).to(DEV), torch.randn(7, n, generator=g).to(DEV)
+        ra = torch.randint(0, 9, (m,), generator=g, dtype=torch.int32).to(DEV)
+        rb = torch.randint(0, 7, (m,), generator=g, dtype=torch.int32).to(DEV)
+        kw = dict(k_masks=masks.to(DEV), k_cell=cell, add_a=fa, add_a_rows=ra, add_b=fb, add_b_rows=rb)
+    outs = []
+    for pairs, m_sub in (((0, 2), (1, 1)) if k_sparse else ((0, 2), (0, 1), (1, 1))):     # (k_masks are per 256-row tile: m_sub 2 or a pair)
+        o16 = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.tc_gemm(a, w, o16, m, n, k, bias=bias, lda=k, ldc=n, epilogue=ops.EPI_BF16, act=ops.ACT_RELU, group_m=3, m_sub=m_sub, cta_pairs=pairs, **kw)
+        o32 = torch.full((m, n), float("nan"), device=DEV)
+        perm = torch.randperm(m, generator=g).to(torch.int32).to(DEV)
+        kw32 = {q: v for q, v in kw.items() if q in ("k_masks", "k_cell")}
+        ops.tc_gemm(a, w, o32, m, n, k, lda=k, ldc=n, epilogue=ops.EPI_F32, group_m=2, m_sub=m_sub, cta_pairs=pairs, out_rows=perm, **kw32)
+        torch.cuda.synchronize()
+        assert not torch.isnan(o16.float()).any() and not torch.isnan(o32).any()
+        outs.append((o16.clone(), o32[perm.long()].clone()))
+    for o16, o32 in outs[:-1]:
+        assert torch.equal(o16.view(torch.int16), outs[-1][0].view(torch.int16))
+        assert torch.equal(o32, outs[-1][1])
+    ref = a.float() @ w.float().t()
+    assert float((outs[-1][1] - ref).abs().max()) <= 2e-3 * float(ref.abs().max())

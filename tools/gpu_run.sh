@@ -32,7 +32,7 @@ for stage in "$@"; do
   name=${stage%%:*}; arg=""; [[ "$stage" == *:* ]] && arg=${stage#*:}
   case $name in
     tests)
-      echo "== pytest gpu $arg"; timeout 2400 python -m pytest tests -m gpu -q --timeout=900 ${arg//,/ } > $OUT/pytest_gpu_$TAG.log 2>&1; rc=$?
+      echo "== pytest gpu $arg"; timeout 2400 python -m pytest ${arg:+${arg//,/ }} $([ -z "$arg" ] && echo tests) -m gpu -q --timeout=900 > $OUT/pytest_gpu_$TAG.log 2>&1; rc=$?
       echo "pytest exit $rc"; grep -E "^PARITY|passed|failed|Error|error" $OUT/pytest_gpu_$TAG.log | tail -40
       if [ $rc -ne 0 ]; then tail -${TAIL:-80} $OUT/pytest_gpu_$TAG.log; [ -z "$CONTINUE" ] && exit $rc; fi ;;
     smoke) echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 ;;
