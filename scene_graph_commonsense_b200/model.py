@@ -196,7 +196,7 @@ class PackedHead:
     def fc1_rows(self, maps, n):
         """fc1 WITHOUT bias / activation of n pooled maps [n,8,8,1024] bf16 -> f32 [n,4096] (the per-box terms of the shared fc1)."""
         out = torch.empty(n, 4096, dtype=torch.float32, device=maps.device)
-        pairs = int(os.environ.get("HC_FC1_BOX_PAIRS", "0")) if n > 128 else 0      # cta_group::2 pairs on 256-row tiles (see fc1_shared_fc2)
+        pairs = int(os.environ.get("HC_FC1_BOX_PAIRS", "1")) if n > 128 else 0      # cta_group::2 pairs on 256-row tiles (see fc1_shared_fc2)
         ops.tc_gemm(maps, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=int(os.environ.get("HC_FC1_BOX_GROUP_M", "37")),
                     m_sub=1 if pairs else (2 if n > 128 else 1), tag="fc1_box", cta_pairs=pairs)
         return out
@@ -211,7 +211,7 @@ class PackedHead:
         # HC_FC1_PAIRS=1: tcgen05 cta_group::2 pairs - a pair of CTAs owns one 256 x 256 tile (128 rows each, half of the weight tile's
         # columns each), so 74 tiles = 4.6 M tiles are in flight instead of 9.25: half as many distinct weight slabs stream through L2
         # at a time (the single-CTA launch re-reads the weights from HBM for nearly every (M tile, cell): 41 GB per launch, ncu r02i)
-        pairs = int(os.environ.get("HC_FC1_PAIRS", "0"))
+        pairs = int(os.environ.get("HC_FC1_PAIRS", "1"))
         if group_m is None:
             group_m = int(os.environ.get("HC_FC1_GROUP_M", "4" if pairs else "9"))
         ops.tc_gemm(d, self.w_fc1, h1, n, 4096, 65536, bias=bias_eff, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU, group_m=group_m,
