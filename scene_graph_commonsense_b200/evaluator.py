@@ -12,6 +12,7 @@ Out of scope here (LLM querying, OIv6 precision, visualisation dumps): `get_rela
 `compute_precision`, `save_visualization_results` raise NotImplementedError pointing at the reference.
 """
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -27,9 +28,23 @@ def _dev(device=None):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_WARNED = set()
+
+
 def _load_keys(path, fallback):
+    """Triplet set at `path` (the reference resolves these relative to its working directory, evaluator.py:37-39,77-81), else the
+    packed copy of the reference's shipped file under scene_graph_commonsense_b200/data/.  A missing file is never silent: it
+    raises under HC_STRICT_PATHS=1 (a run with regenerated sets must not quietly evaluate against the shipped ones) and warns
+    once per path otherwise."""
     if path and os.path.exists(path):
         return tables.dict_to_keys(torch.load(path))
+    if path:
+        if os.environ.get("HC_STRICT_PATHS", "0") == "1":
+            raise FileNotFoundError("hiercom_b200: %s not found (HC_STRICT_PATHS=1 forbids the shipped fallback)" % path)
+        if path not in _WARNED:
+            _WARNED.add(path)
+            warnings.warn("hiercom_b200: %s not found in %s - using the packed copy of the reference's shipped set "
+                          "(set HC_STRICT_PATHS=1 to make this an error)" % (path, os.getcwd()), RuntimeWarning, stacklevel=3)
     return fallback()
 
 

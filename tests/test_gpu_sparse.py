@@ -84,7 +84,8 @@ def test_work_list_covers_active_cells(block_rows, block_cols):
 
 def _packed(seed=0, gain=1.0):
     from scene_graph_commonsense_b200 import model
-    return model.PackedHead(synthetic.head_state_dict(seed=seed, logit_gain=gain), DEV)
+    # kernel-level tests below build their operands as explicit bf16 tensors: pin the packed weights to the same 16-bit format
+    return model.PackedHead(synthetic.head_state_dict(seed=seed, logit_gain=gain), DEV, operand_dtype=torch.bfloat16)
 
 
 @pytest.mark.parametrize("block_rows,m_sub,block_cols,cta_pairs", [(8, 2, 8, 0), (4, 2, 8, 0), (8, 1, 8, 0), (4, 1, 8, 0), (4, 2, 4, 0),
