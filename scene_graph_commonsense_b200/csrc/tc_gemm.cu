@@ -458,18 +458,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         int m_blk, n_blk;
         tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
-        auto load_kb = [&](int kb) {
+        auto load_kb = [&](int kb, int jmask = (1 << MS) - 1) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * stage_bytes;
           const uint32_t b_dst = a_dst + MS * A_SUB_BYTES;
           if constexpr (CG2) {
-            // pair: this CTA stages ITS 128 rows of the 256-row M tile (per sub-tile) and ITS half of the weight tile's columns; the
-            // leader's full barrier counts the bytes of both CTAs (the peer only sends bytes, it never arrives)
+            // pair: this CTA stages ITS 128 rows of every 256-row unit of the tile (sub-tile j = unit m_blk*MS + j; `jmask`: the units
+            // that visit this K block) and ITS half of the weight tile's columns; the leader's full barrier counts the bytes of both
+            // CTAs (the peer only sends bytes, it never arrives)
             const uint32_t lead_full = full_bar(stage) & PEER_BIT_MASK;
-            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)C::CG2_STAGE_BYTES);
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)(__popc(jmask) * A_SUB_BYTES + C::B_BYTES / 2));
 #pragma unroll
             for (int j = 0; j < MS; ++j)
-              tma_load_2d_cg2(a_dst + j * A_SUB_BYTES, &tmap_a, lead_full, kb * BK, ((m_blk * MS + j) * 2 + rank) * BM);
+              if ((jmask >> j) & 1)
+                tma_load_2d_cg2(a_dst + j * A_SUB_BYTES, &tmap_a, lead_full, kb * BK, ((m_blk * MS + j) * 2 + rank) * BM);
             tma_load_2d_cg2(b_dst, &tmap_bh, lead_full, kb * BK, n_blk * BN + rank * (BN / 2));
           } else {
             mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
@@ -482,9 +484,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         };
         if (p.k_masks) {
           // K-cell-sparse: only the K cells some row of this M tile is non-zero in (ascending cell order)
-          for (unsigned long long km = __ldg(p.k_masks + m_blk); km; km &= km - 1) {
-            const int kb0 = (__ffsll((long long)km) - 1) * p.k_cell_kb;
-            for (int i = 0; i < p.k_cell_kb; ++i) load_kb(kb0 + i);
+          if constexpr (CG2) {
+            // pair tile of MS 256-row units, each with its OWN mask: the pair walks the UNION of the cells, a weight K block is staged
+            // once for all units, a unit's rows only for the cells in its own mask (no extra MMAs, the weight slab is fetched once)
+            unsigned long long kj[MS], ku = 0ull;
+#pragma unroll
+            for (int j = 0; j < MS; ++j) { kj[j] = (m_blk * MS + j) * 2 * BM < p.M ? __ldg(p.k_masks + m_blk * MS + j) : 0ull; ku |= kj[j]; }
+            for (; ku; ku &= ku - 1) {
+              const int c = __ffsll((long long)ku) - 1;
+              int jm = 0;
+#pragma unroll
+              for (int j = 0; j < MS; ++j) jm |= (int)((kj[j] >> c) & 1ull) << j;
+              for (int i = 0; i < p.k_cell_kb; ++i) load_kb(c * p.k_cell_kb + i, jm);
+            }
+          } else {
+            for (unsigned long long km = __ldg(p.k_masks + m_blk); km; km &= km - 1) {
+              const int kb0 = (__ffsll((long long)km) - 1) * p.k_cell_kb;
+              for (int i = 0; i < p.k_cell_kb; ++i) load_kb(kb0 + i);
+            }
           }
         } else {
           for (int kb = 0; kb < num_kb; ++kb) load_kb(kb);
@@ -536,8 +553,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);      // epilogue (of both CTAs of a pair) has drained this accumulator stage
         tc_fence_after();
-        uint32_t started = 0;                             // 0 until the first MMA of the tile (which overwrites the accumulator)
-        auto mma_kb = [&]() {
+        uint32_t started = 0;                             // bit j: sub-tile j has issued its first MMA (which overwrites the accumulator)
+        auto mma_kb = [&](int jmask = (1 << MS) - 1) {
           mbar_wait(full_bar(stage), phase);              // TMA bytes of this stage have landed
           tc_fence_after();
           const uint32_t a_src = smem_base + stage * stage_bytes;
@@ -545,19 +562,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < MS; ++j) {
             if (p.dbg & 4) break;
+            if (!((jmask >> j) & 1)) continue;            // pair tile, K-cell-sparse: this unit does not visit the cell
             const uint64_t adesc = umma_desc_sw128(a_src + j * A_SUB_BYTES);
             const uint32_t d = tmem_base + (uint32_t)(acc * C::ACC_COLS + j * BN);
+            const uint32_t acc_on = (started >> j) & 1u;
             if constexpr (CG2) {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)
-                umma_bf16_cg2(d, adesc + 2u * k, bdesc + 2u * k, idesc, (started | k) ? 1u : 0u);
+                umma_bf16_cg2(d, adesc + 2u * k, bdesc + 2u * k, idesc, (acc_on | k) ? 1u : 0u);
             } else {
 #pragma unroll
               for (int k = 0; k < BK / UMMA_K; ++k)       // +32 bytes (>>4 = 2) per 16-element K step inside the swizzle row
-                umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (started | k) ? 1u : 0u);
+                umma_bf16(d, adesc + 2u * k, bdesc + 2u * k, idesc, (acc_on | k) ? 1u : 0u);
             }
           }
-          started = 1;
+          started |= (uint32_t)jmask;
           if constexpr (CG2) umma_commit_cg2(empty_bar(stage), (uint16_t)3);  // the slot of BOTH CTAs is free once the pair's MMAs retire
           else umma_commit(empty_bar(stage));             // smem slot free once these MMAs retire
           if (++stage == n_stages) { stage = 0; phase ^= 1u; }
@@ -565,8 +584,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         if (p.k_masks) {
           int m_blk, n_blk;
           tile_coords(p, tiles_m, tile, m_blk, n_blk, rank);
-          const int n_cells = __popcll(__ldg(p.k_masks + m_blk));
-          for (int i = 0; i < n_cells * p.k_cell_kb; ++i) mma_kb();
+          if constexpr (CG2) {                            // the producer's walk: union of the units' masks, per-unit participation
+            unsigned long long kj[MS], ku = 0ull;
+#pragma unroll
+            for (int j = 0; j < MS; ++j) { kj[j] = (m_blk * MS + j) * 2 * BM < p.M ? __ldg(p.k_masks + m_blk * MS + j) : 0ull; ku |= kj[j]; }
+            for (; ku; ku &= ku - 1) {
+              const int c = __ffsll((long long)ku) - 1;
+              int jm = 0;
+#pragma unroll
+              for (int j = 0; j < MS; ++j) jm |= (int)((kj[j] >> c) & 1ull) << j;
+              for (int i = 0; i < p.k_cell_kb; ++i) mma_kb(jm);
+            }
+          } else {
+            const int n_cells = __popcll(__ldg(p.k_masks + m_blk));
+            for (int i = 0; i < n_cells * p.k_cell_kb; ++i) mma_kb();
+          }
         } else {
           for (int kb = 0; kb < num_kb; ++kb) mma_kb();
         }
@@ -660,9 +692,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const int n0 = n_blk * BN;
       // K-cell-sparse tile with an empty cell mask: no MMA ran, the accumulator is all zeros by definition
-      const bool no_acc = p.k_masks != nullptr && __ldg(p.k_masks + m_blk) == 0ull;
+      // (pair tiles carry one mask per 256-row unit = sub-tile)
+      const bool no_acc_tile = !CG2 && p.k_masks != nullptr && __ldg(p.k_masks + m_blk) == 0ull;
 #pragma unroll 1
       for (int j = 0; j < MS; ++j) {
+        const bool no_acc = no_acc_tile || (CG2 && p.k_masks != nullptr &&
+                                            ((m_blk * MS + j) * 2 * BM >= p.M || __ldg(p.k_masks + m_blk * MS + j) == 0ull));
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
           uint32_t r[32];
@@ -1098,15 +1133,17 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
         blk_w / 2, d->block_rows / 2, d->w / 2, cell_vec, map_vec, reinterpret_cast<uint4*>(d->out), p.f16);
     return cuda_status("pair_diff_kernel launch");
   }
-  // plain GEMM on tcgen05 cta_group::2 pairs (d->cta_pairs, N % 256 == 0, m_sub 1): a pair owns one 256 x 256 tile, each CTA staging its 128
-  // rows of A and its 128 columns of B per K step and keeping two accumulator stages, so the chip has half as many M tiles in flight
-  // (K-cell-sparse fc1: half the distinct weight slabs streaming through L2 at a time) and the epilogue overlaps the next tile
+  // plain GEMM on tcgen05 cta_group::2 pairs (d->cta_pairs, N % 256 == 0): a pair owns m_sub 256-row units of one N tile, each CTA staging
+  // its 128 rows of every unit and its 128 columns of B per K step.  m_sub 1: two accumulator stages, the epilogue overlaps the next
+  // tile.  m_sub 2: both units' accumulators live in TMEM and share every staged weight block; with k_masks (one mask per 256-row
+  // unit either way) the pair walks the union of the two units' cells and a unit skips the cells it does not have
   if (d->mode == HC_GEMM_PLAIN && d->cta_pairs) {
-    HC_REQUIRE(BN == 256 && MS == 1 && d->epilogue != HC_EPI_SPLIT3_BF16, HC_E_SHAPE,
-               "hc_tc_gemm: plain-GEMM CTA pairs need N % 256 == 0, m_sub 1 and a bf16 / f32 epilogue");
+    HC_REQUIRE(BN == 256 && d->epilogue != HC_EPI_SPLIT3_BF16, HC_E_SHAPE,
+               "hc_tc_gemm: plain-GEMM CTA pairs need N % 256 == 0 and a bf16 / f32 epilogue");
     p.cl2 = 1;
-    p.tiles_m = (int)((d->m + 2 * tc::BM - 1) / (2 * tc::BM));
+    p.tiles_m = (int)((d->m + 2 * tc::BM * MS - 1) / (2 * tc::BM * MS));       // pair tiles of MS 256-row units
     if (p.group_m > p.tiles_m) p.group_m = p.tiles_m;
+    if (MS == 2) return tc::launch<256, 2, true>(ta, tb, tbh, p, stream);
     return tc::launch<256, 1, true>(ta, tb, tbh, p, stream);
   }
   if (BN == 256 && MS == 1) return tc::launch<256, 1, false>(ta, tb, tbh, p, stream);

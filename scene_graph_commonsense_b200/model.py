@@ -211,7 +211,7 @@ class PackedHead:
         out = torch.empty(n, 4096, dtype=torch.float32, device=maps.device)
         pairs = int(os.environ.get("HC_FC1_BOX_PAIRS", "1")) if n > 128 else 0      # cta_group::2 pairs on 256-row tiles (see fc1_shared_fc2)
         ops.tc_gemm(maps, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=int(os.environ.get("HC_FC1_BOX_GROUP_M", "37")),
-                    m_sub=1 if pairs else (2 if n > 128 else 1), tag="fc1_box", cta_pairs=pairs)
+                    m_sub=int(os.environ.get("HC_FC1_BOX_MSUB", "1")) if pairs else (2 if n > 128 else 1), tag="fc1_box", cta_pairs=pairs)
         return out
 
     def fc1_shared_fc2(self, d, n, k_masks, f_sub, f_obj, row_sub, row_obj, bias_eff, out_rows, raw, group_m=None):
@@ -228,7 +228,8 @@ class PackedHead:
         if group_m is None:
             group_m = int(os.environ.get("HC_FC1_GROUP_M", "4" if pairs else "9"))
         ops.tc_gemm(d, self.w_fc1, h1, n, 4096, 65536, bias=bias_eff, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU, group_m=group_m,
-                    m_sub=1 if pairs else 2, tag="fc1", k_masks=k_masks, k_cell=1024, add_a=f_sub, add_a_rows=row_sub, add_b=f_obj,
+                    m_sub=int(os.environ.get("HC_FC1_MSUB", "1")) if pairs else 2, tag="fc1", k_masks=k_masks, k_cell=1024, add_a=f_sub,
+                    add_a_rows=row_sub, add_b=f_obj,
                     add_b_rows=row_obj, cta_pairs=pairs)
         ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8, tag="fc2", out_rows=out_rows)
         return raw

@@ -225,7 +225,7 @@ def test_footprint_pooling_writes_exactly_what_the_blocks_read(block_rows, block
     assert torch.equal(part[m].view(torch.int16), full[m].view(torch.int16))
 
 
-@pytest.mark.parametrize("m,k_sparse", [(700, True), (1024, True), (300, False), (5121, False)])
+@pytest.mark.parametrize("m,k_sparse", [(700, True), (1024, True), (1300, True), (300, False), (5121, False)])
 def test_plain_gemm_on_cta_pairs_equals_single_cta_bit_for_bit(m, k_sparse):
     """PLAIN GEMM on tcgen05 cta_group::2 pairs (a pair owns one 256 x 256 tile: 128 rows of A and 128 columns of B per CTA and K
     step): same K order per output element, so every bit equals the single-CTA kernel - dense, K-cell-sparse with row gathers and an
@@ -250,7 +250,8 @@ def test_plain_gemm_on_cta_pairs_equals_single_cta_bit_for_bit(m, k_sparse):
         rb = torch.randint(0, 7, (m,), generator=g, dtype=torch.int32).to(DEV)
         kw = dict(k_masks=masks.to(DEV), k_cell=cell, add_a=fa, add_a_rows=ra, add_b=fb, add_b_rows=rb)
     outs = []
-    for pairs, m_sub in (((0, 2), (1, 1)) if k_sparse else ((0, 2), (0, 1), (1, 1))):     # (k_masks are per 256-row tile: m_sub 2 or a pair)
+    # (k_masks are per 256 rows: the single-CTA tile of m_sub 2, or one unit of a pair tile - m_sub 2 pairs walk the union of two units)
+    for pairs, m_sub in (((0, 2), (1, 2), (1, 1)) if k_sparse else ((0, 2), (0, 1), (1, 2), (1, 1))):
         o16 = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=DEV)
         ops.tc_gemm(a, w, o16, m, n, k, bias=bias, lda=k, ldc=n, epilogue=ops.EPI_BF16, act=ops.ACT_RELU, group_m=3, m_sub=m_sub, cta_pairs=pairs, **kw)
         o32 = torch.full((m, n), float("nan"), device=DEV)
