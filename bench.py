@@ -401,7 +401,7 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
     ops.PROFILE["events"].clear()
 
     # ---- timed region 2: end to end through the public API with HOST buffers (H2D + D2H inside)
-    steps_e2e(max(1, min(warmup, 2)))
+    steps_e2e(max(1, min(warmup, 3)))
     hdist.barrier()
     torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

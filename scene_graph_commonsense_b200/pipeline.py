@@ -733,17 +733,24 @@ class RelationPipeline:
             if not pipelined:
                 yield n, result.cpu()
                 continue
-            host = torch.empty(result.shape, dtype=result.dtype, pin_memory=True)
+            # pinned staging from a small ring owned by the pipeline (no pinned allocation - which can synchronise the device - on
+            # the step path); a slot is reused two windows later, after its copy was handed out as an ordinary host tensor
+            ring = getattr(self, "_result_ring", None)
+            if ring is None or ring[0].shape != result.shape or ring[0].dtype != result.dtype:
+                ring = self._result_ring = [torch.empty(result.shape, dtype=result.dtype, pin_memory=True) for _ in range(3)]
+                self._ring_pos = 0
+            host = ring[self._ring_pos]
+            self._ring_pos = (self._ring_pos + 1) % len(ring)
             host.copy_(result, non_blocking=True)      # stream-ordered behind this window's kernels, before the next reset
             done = torch.cuda.Event()
             done.record(main)
             if pending is not None:
                 pending[2].synchronize()
-                yield pending[0], pending[1]
+                yield pending[0], pending[1].clone()
             pending = (n, host, done)
         if pending is not None:
             pending[2].synchronize()
-            yield pending[0], pending[1]
+            yield pending[0], pending[1].clone()
 
     # ------------------------------------------------------------------------------------------------ results
     def reset(self):

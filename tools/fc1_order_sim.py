@@ -76,3 +76,44 @@ print("2x1 cells (4px wide x 2px tall)", (c(w,2)*2*h).sum()/64/P)
 print("1x2 cells", (w*c(h,2)*2).sum()/64/P)
 print("best of 2x1/1x2 per pair", np.minimum(c(w,2)*2*h, w*c(h,2)*2).sum()/64/P)
 print("mixed: 2x2 then 2x1/1x2/1x1 remainder (exact cover)", (w*h).sum()/64/P)
+
+
+def schedule_imbalance(order, n_workers, group_m, tile=256, n_tiles_n=16, epi=0.6):
+    """Static round-robin persistent schedule of tc_gemm (tile t -> worker t % n_workers, bands of group_m M tiles x all N tiles, n slow
+    inside a band): max / mean of the per-worker sums of (cells visited + `epi` cell-equivalents of epilogue) per tile."""
+    Ms = M[order]
+    nt = (len(Ms) + tile - 1) // tile
+    cost = np.array([pop(np.bitwise_or.reduce(Ms[t * tile:(t + 1) * tile])) for t in range(nt)], dtype=np.float64)
+    load = np.zeros(n_workers)
+    t = 0
+    for band in range(0, nt, group_m):
+        gm = min(group_m, nt - band)
+        for i in range(gm * n_tiles_n):
+            load[t % n_workers] += cost[band + i % gm] + epi
+            t += 1
+    return load.max() / load.mean(), load.max(), load.mean()
+
+
+print("---- fc1 static-schedule imbalance (max/mean of per-worker work)")
+o = np.argsort(key_cur(R), kind='stable')
+for workers, gm in ((148, 9), (74, 4), (74, 9), (74, 1)):
+    print("workers %d group_m %d: max/mean %.3f (max %.1f mean %.1f cell-steps)" % ((workers, gm) + schedule_imbalance(o, workers, gm)))
+
+
+def schedule_imbalance_lpt(order, n_workers, group_m, tile=256, n_tiles_n=16, epi=0.6):
+    """The same static schedule with the M tiles visited in DESCENDING cost order (longest first)."""
+    Ms = M[order]
+    nt = (len(Ms) + tile - 1) // tile
+    cost = np.sort(np.array([pop(np.bitwise_or.reduce(Ms[t * tile:(t + 1) * tile])) for t in range(nt)], dtype=np.float64))[::-1]
+    load = np.zeros(n_workers)
+    t = 0
+    for band in range(0, nt, group_m):
+        gm = min(group_m, nt - band)
+        for i in range(gm * n_tiles_n):
+            load[t % n_workers] += cost[band + i % gm] + epi
+            t += 1
+    return load.max() / load.mean(), load.max(), load.mean()
+
+
+for workers, gm in ((74, 4), (74, 9), (74, 1)):
+    print("longest-first: workers %d group_m %d: max/mean %.3f (max %.1f mean %.1f)" % ((workers, gm) + schedule_imbalance_lpt(o, workers, gm)))
