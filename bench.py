@@ -474,6 +474,9 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
     fc1_times = fc1 + per_tag.get("fc1_box", [])
     took_shared = pipe.last_path == "shared"
     fc1_box_flop = (2 * n_box_step + 1) * FLOP_PAIR_FC1 if took_shared else 0        # per-box fc1 rows (dense)
+    if took_shared and getattr(pipe, "last_box_k_masks", None) is not None:          # K-cell-sparse per-box rows: the cells its tiles visit
+        box_cells = int(np.unpackbits(pipe.last_box_k_masks.cpu().numpy().view(np.uint8)).sum())
+        fc1_box_flop = box_cells * 256.0 * (2 * 1024 * 4096)
     roof_fc1 = roof_of("tc_gemm_kernel<256,2> fc1 [pairs,65536] x [65536,4096] + bias/ReLU epilogue (%s)" % (args.fc1 if took_shared else "dense"),
                        fc1_times, fc1_exec_frac * pairs_step * FLOP_PAIR_FC1 + fc1_box_flop, pairs_step * FLOP_PAIR_FC1, fc1_min,
                        {"note": "achieved counts EXECUTED FLOPs: the K cells each 256-row tile visits (pair launch) + the dense per-box rows",

@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define HC_ABI_VERSION 2
+#define HC_ABI_VERSION 3
 
 #define HC_OK 0
 #define HC_E_SHAPE (-1) /* bad size / unsupported shape          */
@@ -239,8 +239,8 @@ int hc_box_select(const void* t_img, const int32_t* boxes, const int32_t* box_im
  * GEMM epilogue); the kernel then runs on packed bf16x2 adds/max - bit-identical to rounding the fp32 sum, 1/3 of the
  * instructions, HBM-bound instead of issue-bound. */
 int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub,
-                      const int32_t* pair_obj, int32_t n_pairs, int32_t fs, int32_t channels, void* out,
-                      int32_t operand_f16, hc_stream_t stream);
+                      const int32_t* pair_obj, int32_t n_pairs, int32_t fs, int32_t channels, const uint64_t* cover, void* out,
+                      int32_t operand_f16, hc_stream_t stream);     /* cover: as hc_pair_relu_pool_tiled (bias == NULL), or NULL */
 
 /* Same stage for pair lists produced by hc_pairs_enumerate, tiled as an outer sum over the boxes of an image: a
  * thread block keeps the U tiles of 4 subject boxes in registers and streams every object box's V tile once, so

@@ -279,13 +279,15 @@ def box_select(t_img, boxes, box_img, fill, fs=32, out=None):
     return out
 
 
-def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None):
-    require_cuda(u, v, bias, pair_sub, pair_obj)
+def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None, cover=None):
+    require_cuda(u, v, bias, pair_sub, pair_obj, cover)
+    if cover is not None and (cover.dtype != torch.int64 or not cover.is_contiguous() or cover.numel() < pair_sub.numel()):
+        raise RuntimeError("hiercom_b200: pair_relu_pool cover must be a contiguous int64 tensor with one word per pair")
     n, ch = pair_sub.numel(), u.shape[-1]
     if out is None:
         out = torch.empty(n, fs // 2, fs // 2, ch, dtype=u.dtype, device=u.device)
     with _timed("pair_pool"):
-        check(_lib.load().hc_pair_relu_pool(ptr(u), ptr(v), ptr(bias), ptr(pair_sub), ptr(pair_obj), n, fs, ch, ptr(out),
+        check(_lib.load().hc_pair_relu_pool(ptr(u), ptr(v), ptr(bias), ptr(pair_sub), ptr(pair_obj), n, fs, ch, ptr(cover), ptr(out),
                                             _f16(u, v, out), stream_ptr()), "hc_pair_relu_pool")
     _count()
     return out

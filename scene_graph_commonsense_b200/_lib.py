@@ -11,7 +11,7 @@ import torch
 from . import build as _build
 
 HC_OK = 0
-ABI_VERSION = 2        # include/hiercom_b200.h HC_ABI_VERSION
+ABI_VERSION = 3        # include/hiercom_b200.h HC_ABI_VERSION
 ERRORS = {-1: "HC_E_SHAPE", -2: "HC_E_ALIGN", -3: "HC_E_ARCH", -4: "HC_E_CUDA", -5: "HC_E_NULL"}
 
 GEMM_PLAIN, GEMM_CONV3, GEMM_CONV3_BLOCKS = 0, 1, 2
@@ -62,7 +62,7 @@ SIGNATURES = {
     "hc_cells_zero": (C.c_int, [_P, _I32, _I64, _I32, _I64, _P, _P]),
     "hc_pack_pixels": (C.c_int, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "hc_box_select": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
-    "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _I32, _P]),
+    "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _I32, _P]),
     "hc_pair_lut_build": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
     "hc_pair_relu_pool_tiled": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
     "hc_pair_cover_masks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),

@@ -245,10 +245,12 @@ __device__ __forceinline__ uint4 bf8_max(uint4 a, uint4 b) {
   return make_uint4(bf2_max<F16>(a.x, b.x), bf2_max<F16>(a.y, b.y), bf2_max<F16>(a.z, b.z), bf2_max<F16>(a.w, b.w));
 }
 
+// cover (optional, fs == 32): per pair, the 8x8-grid cells its listed conv3_1 blocks cover; a pooled pixel none of whose 3x3
+// neighbourhood cells is covered is never read by HC_GEMM_CONV3_BLOCKS and is skipped (neither loaded nor stored)
 template <bool F16>
 __global__ void pair_relu_pool_bf16_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const int* __restrict__ pair_sub,
                                            const int* __restrict__ pair_obj, long long total_vec, int fs, int cvec,
-                                           uint4* __restrict__ out) {
+                                           const unsigned long long* __restrict__ cover, uint4* __restrict__ out) {
   const int hp = fs / 2;
   const int per_pair = hp * hp * cvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
@@ -256,6 +258,12 @@ __global__ void pair_relu_pool_bf16_kernel(const uint4* __restrict__ u, const ui
     const int rem = (int)(i - (long long)pr * per_pair);
     const int cv = rem % cvec, pix = rem / cvec;
     const int px = pix % hp, py = pix / hp;
+    if (cover) {
+      const int cy0 = max(py - 1, 0) >> 1, cy1 = min(py + 1, hp - 1) >> 1, cx0 = max(px - 1, 0) >> 1, cx1 = min(px + 1, hp - 1) >> 1;
+      const unsigned long long rowbits = (cx1 > cx0 ? 3ull : 1ull) << cx0;
+      const unsigned long long nbr = (rowbits << (8 * cy0)) | (cy1 > cy0 ? rowbits << (8 * cy1) : 0ull);
+      if (!(__ldg(cover + pr) & nbr)) continue;
+    }
     const long long su = (long long)pair_sub[pr] * fs * fs, so = (long long)pair_obj[pr] * fs * fs;
     uint4 acc = make_uint4(0u, 0u, 0u, 0u);                // +0.0 in every lane: relu folded into the running max
 #pragma unroll
@@ -377,11 +385,13 @@ extern "C" int hc_box_select(const void* t_img, const int32_t* boxes, const int3
 }
 
 extern "C" int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub, const int32_t* pair_obj,
-                                 int32_t n_pairs, int32_t fs, int32_t channels, void* out, int32_t operand_f16, hc_stream_t stream_) {
+                                 int32_t n_pairs, int32_t fs, int32_t channels, const uint64_t* cover, void* out, int32_t operand_f16,
+                                 hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(u && v && pair_sub && pair_obj && out, HC_E_NULL, "hc_pair_relu_pool: NULL pointer");
   HC_REQUIRE(!operand_f16 || !bias, HC_E_SHAPE, "hc_pair_relu_pool: fp16 operands take the packed path (bias == NULL)");
   HC_REQUIRE(n_pairs > 0 && fs > 0 && fs % 2 == 0 && channels % 8 == 0, HC_E_SHAPE, "hc_pair_relu_pool: bad sizes");
+  HC_REQUIRE(!cover || (!bias && fs == 32), HC_E_SHAPE, "hc_pair_relu_pool: the footprint cover needs the packed path (bias == NULL) and feature_size 32");
   HC_REQUIRE(aligned16(u) && aligned16(v) && aligned16(out), HC_E_ALIGN, "hc_pair_relu_pool: 16-byte alignment");
   int rc = hc_device_check();
   if (rc != HC_OK) return rc;
@@ -390,10 +400,12 @@ extern "C" int hc_pair_relu_pool(const void* u, const void* v, const float* bias
     if (operand_f16)
       pair_relu_pool_bf16_kernel<true><<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                                     pair_sub, pair_obj, total, fs, channels / 8,
+                                                                                    reinterpret_cast<const unsigned long long*>(cover),
                                                                                     reinterpret_cast<uint4*>(out));
     else
       pair_relu_pool_bf16_kernel<false><<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                                      pair_sub, pair_obj, total, fs, channels / 8,
+                                                                                     reinterpret_cast<const unsigned long long*>(cover),
                                                                                      reinterpret_cast<uint4*>(out));
     return cuda_status("hc_pair_relu_pool");
   }

@@ -195,7 +195,7 @@ class PackedHead:
         return cur
 
     def conv3_diff(self, p2, d, n, blocks, n_blocks, block_rows, sub_maps, obj_maps, pair_sub, pair_obj, pair_row, m_sub=2, tag="conv3",
-                   block_cols=8, cta_pairs=0):
+                   block_cols=8, cta_pairs=0, scratch=None):
         """conv3_1+ReLU+pool on the listed blocks of p2 [>=n,16,16,512]; local pair i's cells go to row pair_row[i] of d [rows,8,8,1024]
         as the DIFFERENCE to its per-box maps, (x - sub_maps[pair_sub[i]]) - (obj_maps[pair_obj[i]] - background): the operand of
         the shared-footprint fc1 (`fc1_shared_fc2`), exactly zero wherever only one box of the pair reaches."""
@@ -203,8 +203,23 @@ class PackedHead:
                     n_img=n, h=16, w=16, c_total=512, c_base=0, c_in=512, group_m=1, m_sub=m_sub, tag=tag, blocks=blocks,
                     n_blocks=n_blocks, block_rows=block_rows, block_cols=block_cols, diff_sub=sub_maps, diff_obj=obj_maps, diff_bg=self.p3_background(),
                     pair_sub=pair_sub, pair_obj=pair_obj, pair_row=pair_row, cta_pairs=cta_pairs,
-                    scratch=self.pair_scratch(n) if cta_pairs else None)
+                    scratch=(scratch if scratch is not None else self.pair_scratch(n)) if cta_pairs else None)
         return d
+
+    def fc1_background(self):
+        """fc1 (no bias) of the background map, f32 [4096]: weights-only, computed once."""
+        if getattr(self, "_fc1_bg", None) is None:
+            self._fc1_bg = self.fc1_rows(self.p3_background(), 1)[0].contiguous()
+        return self._fc1_bg
+
+    def fc1_rows_sparse(self, d, n, k_masks, out_rows):
+        """W1 . d for n rows of a difference operand d [n,8,8,1024] (sorted rows, zero outside each 256-row tile's `k_masks` cells)
+        -> f32 [n,4096] in `out_rows` order: the K-cell-sparse twin of `fc1_rows` for per-box maps (d = map - background)."""
+        out = torch.empty(n, 4096, dtype=torch.float32, device=d.device)
+        pairs = int(os.environ.get("HC_FC1_BOX_PAIRS", "1"))
+        ops.tc_gemm(d, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=4 if pairs else 9,
+                    m_sub=1 if pairs else 2, tag="fc1_box", k_masks=k_masks, k_cell=1024, out_rows=out_rows, cta_pairs=pairs)
+        return out
 
     def fc1_rows(self, maps, n):
         """fc1 WITHOUT bias / activation of n pooled maps [n,8,8,1024] bf16 -> f32 [n,4096] (the per-box terms of the shared fc1)."""

@@ -209,15 +209,16 @@ def box_select(t_img, boxes, box_img, fill, fs=32, out=None):
     return _call("box_select")(t_img, boxes, box_img, fill, fs)
 
 
-@_op("pair_relu_pool", "(Tensor u, Tensor v, Tensor? bias, Tensor pair_sub, Tensor pair_obj, int fs, Tensor(a!) out) -> ()")
-def _pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs, out):
-    _A.pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs, out=out)
+@_op("pair_relu_pool", "(Tensor u, Tensor v, Tensor? bias, Tensor pair_sub, Tensor pair_obj, int fs, Tensor(a!) out, Tensor? cover) -> ()")
+def _pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs, out, cover):
+    _A.pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs, out=out, cover=cover)
 
 
-def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None):
+def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None, cover=None):
+    """`cover` (int64 per pair, `pair_cover_masks`): write only the pooled pixels a listed conv3_1 block reads (packed path, bias None)."""
     if out is None:
         out = torch.empty(pair_sub.numel(), fs // 2, fs // 2, u.shape[-1], dtype=u.dtype, device=u.device)
-    _call("pair_relu_pool")(u, v, bias, pair_sub, pair_obj, fs, out)
+    _call("pair_relu_pool")(u, v, bias, pair_sub, pair_obj, fs, out, cover)
     return out
 
 

@@ -224,6 +224,8 @@ class RelationPipeline:
         self.dense_above = float(dense_above)
         self.last_path = None               # "shared" / "blocks" / "dense": the formulation the last forward_pairs took
         self.host_offsets = os.environ.get("HC_HOST_OFFSETS", "1") != "0"    # use DeviceBatch.pair_offsets_host (no D2H read per step)
+        # per-box fc1 rows as a K-cell-sparse GEMM over each box's own cells (needs the CTA-pair conv3_1 kernel); 0 = dense rows
+        self.fc1_box_sparse = os.environ.get("HC_FC1_BOX_SPARSE", "1") != "0"
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("hiercom_b200: RelationPipeline needs a CUDA device (no CPU fallback)")
@@ -271,6 +273,7 @@ class RelationPipeline:
             raise ValueError("4x2-pixel blocks need the CTA-pair kernel on the shared-footprint path (conv3_shared, fc1_shared, HC_CONV3_PAIRS=1)")
         self.last_n_blocks = None            # int32 [n_chunks] device tensor: work-list lengths of the last forward_pairs
         self.last_k_masks = None             # int64 [n_tiles] device tensor: K-cell masks of the last shared fc1
+        self.last_box_k_masks = None         # the same for the per-box fc1 rows (None: dense rows)
         self.splits = tuple(splits) if splits is not None else (packed.splits if packed is not None and not packed.flat else (15, 11, 24))
         self.hier = (not packed.flat if packed is not None else True) if hier is None else bool(hier)
         self.pass_bitmap = None
@@ -333,6 +336,48 @@ class RelationPipeline:
         if with_background_row:
             return maps, nblk
         return maps[:n_box], maps[n_box:], nblk
+
+    def box_maps_sparse(self, boxes_x, u, v):
+        """`box_maps` + the per-box fc1 rows in one pass, with the fc1 rows K-cell-sparse: a box's map differs from the background only
+        in the cells the box itself reaches, so fc1(map) = fc1(background) + W1 . (map - background) and the GEMM visits, per 256-row
+        tile of boxes sorted by cell rectangle, only those cells.  The CTA-pair conv3_1 kernel writes the pooled values straight into
+        `maps` (its scratch map) and `pair_diff_kernel` forms d = map - background from them (subject map := object map :=
+        background in the difference epilogue).  -> maps [2*n_box + 1, 8,8,1024] (last row = background), f_rows f32 [2*n_box, 4096]
+        = W1 . d (WITHOUT the background term), work-list lengths."""
+        pk, br, bc, fs, dev = self.packed, self.conv3_block_rows, self.conv3_block_cols, self.fs, self.device
+        n_box = boxes_x.shape[0] - 1
+        n = 2 * n_box
+        idx = torch.arange(n_box, dtype=torch.int32, device=dev)
+        empty = torch.full((n_box,), n_box, dtype=torch.int32, device=dev)
+        sub, obj = torch.cat((idx, empty)), torch.cat((empty, idx))
+        own = torch.cat((idx, idx))                                   # the box whose own cells a row can differ from the background in
+        bg = pk.p3_background()
+        maps = torch.empty(n + 1, 8, 8, 1024, dtype=pk.act_dtype, device=dev)
+        maps[n:].copy_(bg)
+        keys = ops.pair_cell_keys(boxes_x, own, own, fs)             # box & box = the box's own cell rectangle
+        perm64 = torch.sort(keys, stable=True)[1]
+        perm = perm64.to(torch.int32)
+        row_of = torch.empty_like(perm)
+        row_of[perm64] = torch.arange(n, dtype=torch.int32, device=dev)
+        own_sorted = own[perm64].contiguous()
+        masks = ops.tile_cell_masks(boxes_x, own_sorted, own_sorted, 256, fs)
+        d = torch.empty(n, 64, 1024, dtype=pk.act_dtype, device=dev)
+        ops.cells_zero(masks, 256, n, d)
+        zeros = torch.zeros(min(n, self.chunk_pairs), dtype=torch.int32, device=dev)
+        starts = list(range(0, n, self.chunk_pairs))
+        nblk = torch.zeros(max(len(starts), 1), dtype=torch.int32, device=dev)
+        for k, s in enumerate(starts):
+            e = min(n, s + self.chunk_pairs)
+            cover = ops.pair_cover_masks(boxes_x, sub[s:e], obj[s:e], br, bc, False, fs) if self.pool_footprint else None
+            p2 = ops.pair_relu_pool(u, v, None, sub[s:e], obj[s:e], fs, cover=cover)          # only the pixels the listed blocks read
+            blocks, _ = ops.conv3_active_blocks(boxes_x, sub[s:e], obj[s:e], br, fs, n_blocks=nblk[k:k + 1], block_cols=bc)
+            ops.broadcast_rows(bg, e - s, maps[s:e])
+            pk.conv3_diff(p2, d.view(n, 8, 8, 1024), e - s, blocks, nblk[k:k + 1], br, bg, bg, zeros[:e - s], zeros[:e - s], row_of[s:e],
+                          m_sub=self.conv3_m_sub, tag="conv3_box", block_cols=bc, cta_pairs=self.conv3_pairs, scratch=maps[s:e])
+            del p2
+        f_rows = pk.fc1_rows_sparse(d, n, masks, perm)
+        self.last_box_k_masks = masks
+        return maps, f_rows, nblk
 
     @staticmethod
     def _greedy_chunks(offsets_host, cap):
@@ -539,9 +584,14 @@ class RelationPipeline:
         early = self._pool_buffers(windows[0][2])
         uv_ready = torch.cuda.Event()
         uv_ready.record(torch.cuda.current_stream())
-        maps, nblk_box = self.box_maps(boxes_x, u, v, with_background_row=True)
-        f_box = pk.fc1_rows(maps, 2 * n_box + 1)                     # fc1 (no bias) of (box, empty), (empty, box), background
-        bias_eff = (pk.b_fc1 - f_box[2 * n_box]).contiguous()
+        if self.fc1_box_sparse and self.conv3_pairs:
+            # per-box fc1 rows WITHOUT their background term (K-cell-sparse over each box's own cells): fc1(pair) = F_bg + W.d_s + W.d_o + W.d
+            maps, f_box, nblk_box = self.box_maps_sparse(boxes_x, u, v)
+            bias_eff = (pk.b_fc1 + pk.fc1_background()).contiguous()
+        else:
+            maps, nblk_box = self.box_maps(boxes_x, u, v, with_background_row=True)
+            f_box = pk.fc1_rows(maps, 2 * n_box + 1)                 # fc1 (no bias) of (box, empty), (empty, box), background
+            bias_eff = (pk.b_fc1 - f_box[2 * n_box]).contiguous()
         raw = torch.empty(n, 512, dtype=torch.float32, device=dev)
         nblks, masks_all = [], []
         for i, (w0, w1, chunks) in enumerate(windows):

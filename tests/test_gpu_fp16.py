@@ -172,4 +172,4 @@ def test_weights_beyond_the_fp16_range_are_refused():
     sd["conv3_1.weight"][0, 0, 0, 0] = 7.0e4
     with pytest.raises(RuntimeError, match="fp16 range"):
         model.PackedHead(sd, DEV, operand_dtype=H)
-    model.PackedHead(sd, DEV)                                           # bf16 takes it
+    model.PackedHead(sd, DEV, operand_dtype=torch.bfloat16)             # bf16 takes it
