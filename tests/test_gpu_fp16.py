@@ -136,11 +136,17 @@ def test_pipeline_identities_hold_in_fp16():
             assert torch.equal(x, y), name
     dp = (outs["shared"][0].double().exp() - outs["dense"][0].double().exp()).abs().max().item()
     assert dp <= 1e-3, dp
-    pipe1 = mk()
-    pipe1.conv3_pairs = 0                                                # single-CTA block kernel
-    pairs = pipe1.enumerate_pairs(b)
-    for x, y in zip(pipe1.forward_pairs(b, pairs), outs["shared"]):
+    # CTA pairs vs the single-CTA block kernel, both with dense per-box fc1 rows (the K-cell-sparse rows need the pair kernel)
+    res = []
+    for cp in (1, 0):
+        pipe1 = mk()
+        pipe1.conv3_pairs, pipe1.fc1_box_sparse = cp, False
+        pairs = pipe1.enumerate_pairs(b)
+        res.append([t.clone() for t in pipe1.forward_pairs(b, pairs)])
+    for x, y in zip(*res):
         assert torch.equal(x, y)
+    dp = (outs["shared"][0].double().exp() - res[0][0].double().exp()).abs().max().item()      # sparse vs dense per-box fc1 rows
+    assert dp <= 1e-3, dp
 
 
 def test_small_batch_vs_fp32_oracle_fp16_sharp_weights():
