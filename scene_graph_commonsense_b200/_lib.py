@@ -103,7 +103,8 @@ _lib = None
 
 
 def library_path():
-    return _build.LIB
+    """The in-tree shared object; HC_LIB names another build of the same ABI (A/B runs of two kernel versions on one box)."""
+    return os.environ.get("HC_LIB") or _build.LIB
 
 
 def load(build_if_missing=False):

@@ -280,11 +280,26 @@ __global__ void __launch_bounds__(128, 4)
 pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const int* __restrict__ box_off,
                                  const int* __restrict__ lut, int n_max, int img0, int pair_base, int chunk_pairs, int fs, int cvec,
                                  const unsigned long long* __restrict__ cover, uint4* __restrict__ out) {
-  // grid = (slabs, subject tiles, images of the chunk); block = 128 consecutive (pooled pixel, channel vector) slots
+  // grid = (slabs, subject tiles, images of the chunk); block = 128 consecutive (pooled pixel, channel vector) slots.
+  // The (subject, object) -> pair row table and the pairs' cover words are the same for every thread of the block: they are staged
+  // in shared memory once (two dependent global loads per (subject, object) and thread became the latency chain of this kernel
+  // once the footprint cover had removed most of the stores, profiles/ncu_summary_r01L.json).
+  extern __shared__ unsigned long long pp_smem[];
+  unsigned long long* s_cov = pp_smem;                                       // [PP_TA][n_max] cover word (0 = pair absent / not in chunk)
+  int* s_row = reinterpret_cast<int*>(pp_smem + PP_TA * n_max);              // [PP_TA][n_max] chunk-local pair row
   const int img = img0 + blockIdx.z;
   const int b0 = box_off[img], n = box_off[img + 1] - b0;
   const int a0 = blockIdx.y * PP_TA;
-  if (a0 >= n) return;
+  if (a0 >= n) return;                                                       // block-uniform
+  for (int i = threadIdx.x; i < PP_TA * n; i += blockDim.x) {
+    const int t = i / n, b = i - t * n;
+    int p = (a0 + t < n) ? __ldg(lut + (long long)(b0 + a0 + t) * n_max + b) : -1;
+    p = (p >= 0) ? p - pair_base : -1;
+    if (p >= chunk_pairs) p = -1;
+    s_row[t * n_max + b] = p;
+    s_cov[t * n_max + b] = p < 0 ? 0ull : (cover ? __ldg(cover + p) : ~0ull);
+  }
+  __syncthreads();
   const int hp = fs / 2;
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   const int cv = slot % cvec;
@@ -294,20 +309,8 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
   long long qoff[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) qoff[q] = ((long long)(2 * py + (q >> 1)) * fs + (2 * px + (q & 1))) * cvec + cv;
-  uint4 ua[PP_TA][4];
-#pragma unroll
-  for (int t = 0; t < PP_TA; ++t) {
-    const long long base = (long long)(b0 + min(a0 + t, n - 1)) * fs * fs * cvec;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) ua[t][q] = __ldg(u + base + qoff[q]);
-  }
-  const int* lut_row[PP_TA];
-#pragma unroll
-  for (int t = 0; t < PP_TA; ++t) lut_row[t] = lut + (long long)(b0 + min(a0 + t, n - 1)) * n_max;
-  const long long out_slot = (long long)pix * cvec + cv;
-  const long long pair_stride = (long long)hp * hp * cvec;
-  // cover (optional): per pair of the chunk, the 8x8-grid cells its listed conv3_1 blocks cover.  This pooled pixel is read by
-  // a block iff one of the cells its 3x3 neighbourhood touches is covered (fs = 32: a cell is 2 x 2 pooled pixels); warp-uniform.
+  // cover: this pooled pixel is read by a listed conv3_1 block iff one of the cells its 3x3 neighbourhood touches is covered
+  // (fs = 32: a cell is 2 x 2 pooled pixels); warp-uniform (a warp holds one pixel)
   unsigned long long nbr = ~0ull;
   if (cover) {
     const int cy0 = max(py - 1, 0) >> 1, cy1 = min(py + 1, hp - 1) >> 1, cx0 = max(px - 1, 0) >> 1, cx1 = min(px + 1, hp - 1) >> 1;
@@ -315,21 +318,32 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
     for (int cy = cy0; cy <= cy1; ++cy)
       for (int cx = cx0; cx <= cx1; ++cx) nbr |= 1ull << (8 * cy + cx);
   }
+  // subjects of the tile that need this pixel for at least one object: their U tiles are fetched, the others are not
+  unsigned need_t = 0u;
+  for (int b = 0; b < n; ++b) {
+#pragma unroll
+    for (int t = 0; t < PP_TA; ++t) need_t |= (unsigned)((s_cov[t * n_max + b] & nbr) != 0ull) << t;
+  }
+  if (!need_t) return;                                                       // warp-uniform
+  uint4 ua[PP_TA][4];
+#pragma unroll
+  for (int t = 0; t < PP_TA; ++t) {
+    if (!((need_t >> t) & 1u)) continue;
+    const long long base = (long long)(b0 + min(a0 + t, n - 1)) * fs * fs * cvec;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) ua[t][q] = __ldg(u + base + qoff[q]);
+  }
+  const long long out_slot = (long long)pix * cvec + cv;
+  const long long pair_stride = (long long)hp * hp * cvec;
   for (int b = 0; b < n; ++b) {
     int prow[PP_TA];
     bool any = false;
 #pragma unroll
     for (int t = 0; t < PP_TA; ++t) {
-      int p = (a0 + t < n) ? __ldg(lut_row[t] + b) : -1;
-      p = (p >= 0) ? p - pair_base : -1;
-      if (p >= chunk_pairs) p = -1;
-      // footprint cover: the four words are loaded side by side (independent), and a pair none of whose listed conv3_1 blocks
-      // reads this pixel is dropped here, before the object tile is fetched (warp-uniform: a warp holds one pixel)
-      if (cover && p >= 0 && !(__ldg(cover + p) & nbr)) p = -1;
-      prow[t] = p;
-      any |= p >= 0;
+      prow[t] = (s_cov[t * n_max + b] & nbr) ? s_row[t * n_max + b] : -1;
+      any |= prow[t] >= 0;
     }
-    if (!any) continue;                                  // uniform per warp (lut / cover entries do not depend on the lane)
+    if (!any) continue;                                  // uniform per warp
     const long long vb = (long long)(b0 + b) * fs * fs * cvec;
     uint4 vq[4];
 #pragma unroll
@@ -444,12 +458,14 @@ extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float
   HC_REQUIRE(!cover || fs == 32, HC_E_SHAPE, "hc_pair_relu_pool_tiled: the footprint cover is defined on the 8x8 cell grid of feature_size 32");
   dim3 grid(slots / 128, (n_max + PP_TA - 1) / PP_TA, n_img);
   if (!bias) {
+    const size_t smem = (size_t)PP_TA * n_max * (sizeof(unsigned long long) + sizeof(int));
+    HC_REQUIRE(smem <= 48 * 1024, HC_E_SHAPE, "hc_pair_relu_pool_tiled: more than 1024 boxes per image");
     if (operand_f16)
-      pair_relu_pool_tiled_bf16_kernel<true><<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
+      pair_relu_pool_tiled_bf16_kernel<true><<<grid, 128, smem, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                        box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec,
                                                                        reinterpret_cast<const unsigned long long*>(cover), reinterpret_cast<uint4*>(out));
     else
-      pair_relu_pool_tiled_bf16_kernel<false><<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
+      pair_relu_pool_tiled_bf16_kernel<false><<<grid, 128, smem, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                         box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec,
                                                                         reinterpret_cast<const unsigned long long*>(cover), reinterpret_cast<uint4*>(out));
     return cuda_status("hc_pair_relu_pool_tiled");
