@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define HC_ABI_VERSION 3
+#define HC_ABI_VERSION 4
 
 #define HC_OK 0
 #define HC_E_SHAPE (-1) /* bad size / unsupported shape          */
@@ -238,9 +238,20 @@ int hc_box_select(const void* t_img, const int32_t* boxes, const int32_t* box_im
  * out [n_pairs, fs/2, fs/2, C] bf16.  bias == NULL: V already includes the conv2 bias (added in fp32 in the object-half
  * GEMM epilogue); the kernel then runs on packed bf16x2 adds/max - bit-identical to rounding the fp32 sum, 1/3 of the
  * instructions, HBM-bound instead of issue-bound. */
+/* hc_uv_footprint (optional, NULL = u / v are complete maps): u / v were written by HC_GEMM_CONV3_BLOCKS over hc_conv2_box_blocks' list
+ * WITHOUT a background pre-fill, i.e. a box's map is defined only inside the rectangle its listed blocks cover; outside it the value
+ * is taken from the background maps u_bg / v_bg [fs, fs, channels] (the conv2_1 halves of an all-tanh(bias) map), which is what the
+ * complete map holds there bit for bit.  Saves writing 2 MiB of background per box. */
+typedef struct hc_uv_footprint {
+  const int32_t* boxes;  /* [n_box,4] the boxes u / v were computed for (same rows) */
+  const void* u_bg;
+  const void* v_bg;
+  int32_t block_rows;    /* of the hc_conv2_box_blocks list: 4 or 8 */
+} hc_uv_footprint;
 int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub,
-                      const int32_t* pair_obj, int32_t n_pairs, int32_t fs, int32_t channels, const uint64_t* cover, void* out,
-                      int32_t operand_f16, hc_stream_t stream);     /* cover: as hc_pair_relu_pool_tiled (bias == NULL), or NULL */
+                      const int32_t* pair_obj, int32_t n_pairs, int32_t fs, int32_t channels, const uint64_t* cover,
+                      const hc_uv_footprint* fp, void* out, int32_t operand_f16,
+                      hc_stream_t stream);     /* cover: as hc_pair_relu_pool_tiled (bias == NULL), or NULL */
 
 /* Same stage for pair lists produced by hc_pairs_enumerate, tiled as an outer sum over the boxes of an image: a
  * thread block keeps the U tiles of 4 subject boxes in registers and streams every object box's V tile once, so
@@ -252,8 +263,8 @@ int hc_pair_lut_build(const int32_t* pair_sub, const int32_t* pair_obj, const in
                       hc_stream_t stream);
 int hc_pair_relu_pool_tiled(const void* u, const void* v, const float* bias, const int32_t* box_offsets,
                             const int32_t* lut, int32_t n_max, int32_t img0, int32_t n_img, int32_t pair_base,
-                            int32_t chunk_pairs, int32_t fs, int32_t channels, const uint64_t* cover, void* out,
-                            int32_t operand_f16, hc_stream_t stream);
+                            int32_t chunk_pairs, int32_t fs, int32_t channels, const uint64_t* cover, const hc_uv_footprint* fp,
+                            void* out, int32_t operand_f16, hc_stream_t stream);
 
 /* Footprint-aware pooling: masks[p] = the 8x8-grid cells covered by the blocks hc_conv3_active_blocks (shared = 0) or
  * hc_conv3_shared_blocks (shared = 1) lists for pair p (same cover function).  Passed as `cover` (chunk-local, bias == NULL,

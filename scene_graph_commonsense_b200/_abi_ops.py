@@ -279,7 +279,20 @@ def box_select(t_img, boxes, box_img, fill, fs=32, out=None):
     return out
 
 
-def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None, cover=None):
+def _footprint(fp, u):
+    """fp = (boxes int32 [n_box,4], u_bg, v_bg [1,fs,fs,C] in u's format, conv2 block rows) or None -> (struct kept alive, pointer or None)."""
+    if fp is None:
+        return None, None
+    boxes, u_bg, v_bg, rows = fp
+    require_cuda(boxes, u_bg, v_bg)
+    if (boxes.dtype != torch.int32 or not boxes.is_contiguous() or boxes.shape[0] < u.shape[0] or u_bg.dtype != u.dtype or v_bg.dtype != u.dtype
+            or not u_bg.is_contiguous() or not v_bg.is_contiguous() or u_bg.numel() != u[0].numel() or v_bg.numel() != u[0].numel()):
+        raise RuntimeError("hiercom_b200: footprint maps need int32 boxes (one per map) and background maps of one map's shape and format")
+    st = _lib.UVFootprint(ptr(boxes), ptr(u_bg), ptr(v_bg), int(rows))
+    return st, C.byref(st)
+
+
+def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None, cover=None, fp=None):
     require_cuda(u, v, bias, pair_sub, pair_obj, cover)
     if cover is not None and (cover.dtype != torch.int64 or not cover.is_contiguous() or cover.numel() < pair_sub.numel()):
         raise RuntimeError("hiercom_b200: pair_relu_pool cover must be a contiguous int64 tensor with one word per pair")
@@ -287,7 +300,8 @@ def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None, cover=None):
     if out is None:
         out = torch.empty(n, fs // 2, fs // 2, ch, dtype=u.dtype, device=u.device)
     with _timed("pair_pool"):
-        check(_lib.load().hc_pair_relu_pool(ptr(u), ptr(v), ptr(bias), ptr(pair_sub), ptr(pair_obj), n, fs, ch, ptr(cover), ptr(out),
+        keep, fpp = _footprint(fp, u)
+        check(_lib.load().hc_pair_relu_pool(ptr(u), ptr(v), ptr(bias), ptr(pair_sub), ptr(pair_obj), n, fs, ch, ptr(cover), fpp, ptr(out),
                                             _f16(u, v, out), stream_ptr()), "hc_pair_relu_pool")
     _count()
     return out
@@ -316,7 +330,7 @@ def pair_cover_masks(boxes, pair_sub, pair_obj, block_rows, block_cols, shared, 
     return out
 
 
-def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None, cover=None):
+def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None, cover=None, fp=None):
     require_cuda(u, v, bias, box_offsets, lut, cover)
     if cover is not None and (cover.dtype != torch.int64 or cover.numel() < chunk_pairs or not cover.is_contiguous()):
         raise RuntimeError("hiercom_b200: pair_relu_pool_tiled cover must be a contiguous int64 tensor with one word per pair of the chunk")
@@ -324,8 +338,9 @@ def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, c
     if out is None:
         out = torch.empty(chunk_pairs, fs // 2, fs // 2, ch, dtype=u.dtype, device=u.device)
     with _timed("pair_pool"):
+        keep, fpp = _footprint(fp, u)
         check(_lib.load().hc_pair_relu_pool_tiled(ptr(u), ptr(v), ptr(bias), ptr(box_offsets), ptr(lut), lut.shape[1], img0, n_img,
-                                                  pair_base, chunk_pairs, fs, ch, ptr(cover), ptr(out), _f16(u, v, out), stream_ptr()),
+                                                  pair_base, chunk_pairs, fs, ch, ptr(cover), fpp, ptr(out), _f16(u, v, out), stream_ptr()),
               "hc_pair_relu_pool_tiled")
     _count()
     return out

@@ -11,7 +11,7 @@ import torch
 from . import build as _build
 
 HC_OK = 0
-ABI_VERSION = 3        # include/hiercom_b200.h HC_ABI_VERSION
+ABI_VERSION = 4        # include/hiercom_b200.h HC_ABI_VERSION
 ERRORS = {-1: "HC_E_SHAPE", -2: "HC_E_ALIGN", -3: "HC_E_ARCH", -4: "HC_E_CUDA", -5: "HC_E_NULL"}
 
 GEMM_PLAIN, GEMM_CONV3, GEMM_CONV3_BLOCKS = 0, 1, 2
@@ -34,6 +34,11 @@ class GemmDesc(C.Structure):
                 ("diff_sub", C.c_void_p), ("diff_obj", C.c_void_p), ("diff_bg", C.c_void_p),
                 ("pair_sub", C.c_void_p), ("pair_obj", C.c_void_p), ("pair_row", C.c_void_p), ("scratch", C.c_void_p),
                 ("operand_f16", C.c_int32)]
+
+
+class UVFootprint(C.Structure):
+    """hc_uv_footprint: U / V hold a box's conv2_1 values only inside its footprint rectangle; the background maps apply elsewhere."""
+    _fields_ = [("boxes", C.c_void_p), ("u_bg", C.c_void_p), ("v_bg", C.c_void_p), ("block_rows", C.c_int32)]
 
 
 class RelationWorkspace(C.Structure):
@@ -62,9 +67,9 @@ SIGNATURES = {
     "hc_cells_zero": (C.c_int, [_P, _I32, _I64, _I32, _I64, _P, _P]),
     "hc_pack_pixels": (C.c_int, [_P, _I32, _P, _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "hc_box_select": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P]),
-    "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _I32, _P]),
+    "hc_pair_relu_pool": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _P, C.POINTER(UVFootprint), _P, _I32, _P]),
     "hc_pair_lut_build": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P]),
-    "hc_pair_relu_pool_tiled": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _I32, _P]),
+    "hc_pair_relu_pool_tiled": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _P, C.POINTER(UVFootprint), _P, _I32, _P]),
     "hc_pair_cover_masks": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "hc_hier_head": (C.c_int, [_P, _I64, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P, _I32, _I32, _I32, _I32,
                                _F, _F, _F, _P, _P, _P, _P, _P, _P, _P]),

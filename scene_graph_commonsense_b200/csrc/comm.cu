@@ -145,8 +145,10 @@ extern "C" int hc_relation_workspace_bytes(int32_t n_images, int64_t n_box, int6
   out->pooled_conv2 = n_buf * chunk * 256 * 512 * 2;                   // P2 [chunk,16,16,512]
   out->work_lists = n_buf * (chunk * 16 * 4 + chunk * 8) + 2 * nbx * 16 * 4;
   if (shared_fc1) {
-    out->box_maps = (2 * n_box + 1) * 64 * 1024 * 2;                   // (box, empty), (empty, box), background
-    out->box_fc1_rows = (2 * n_box + 1) * 4096 * 4;
+    // (box, empty), (empty, box), background maps + the per-box difference operand map - background of the K-cell-sparse fc1 rows
+    // (sorted rows, only visited cells touched) + the pooled conv2 buffer of the per-box pass
+    out->box_maps = (2 * n_box + 1) * 64 * 1024 * 2 + 2 * n_box * 64 * 1024 * 2 + (2 * n_box < chunk ? 2 * n_box : chunk) * 256 * 512 * 2;
+    out->box_fc1_rows = (2 * n_box + 1) * 4096 * 4 + 2 * n_box * (4 + 4 + 4 + 8) + ((2 * n_box + 255) / 256) * 8;
     out->fc1_operand = n_pairs * 64 * 1024 * 2;                        // D [P, 64 cells, 1024]: only visited cells are touched
     out->row_maps = n_pairs * (4 + 4 + 4 + 4 + 8) + ((n_pairs + 255) / 256) * 8;
   } else {

@@ -74,6 +74,19 @@ __device__ __forceinline__ int rect_inter(const Rect& a, const Rect& b) {
   return (w > 0 && h > 0) ? w * h : 0;
 }
 
+// The pixels of a box's conv2_1 half maps (U / V) that hc_conv2_box_blocks lists - the union of its 8 x bh-pixel blocks, a rectangle;
+// everywhere else the map equals the background map bit for bit (3x3 convolution of a map that is tanh(bias) outside the box).
+__device__ __forceinline__ Rect conv2_valid_rect(int4 box, int fs, int bh) {
+  const Rect r = rect_of(box, fs);
+  Rect o = {0, 0, 0, 0};
+  if (r.x1 <= r.x0 || r.y1 <= r.y0) return o;
+  const int xlo = max(0, r.x0 - 1) & ~1, xhi = min(fs, r.x1 + 1), ylo = max(0, r.y0 - 1) & ~1, yhi = min(fs, r.y1 + 1);
+  o.x0 = min(xlo, fs - 8);  o.x1 = min(fs, xlo + 8 * ((xhi - xlo + 7) / 8));          // (a block past the edge is shifted back inside)
+  o.y0 = min(ylo, fs - bh); o.y1 = min(fs, ylo + bh * ((yhi - ylo + bh - 1) / bh));
+  return o;
+}
+__device__ __forceinline__ bool rect_has(const Rect& r, int x, int y) { return x >= r.x0 && x < r.x1 && y >= r.y0 && y < r.y1; }
+
 // evaluator.py:84-94: float(intersect)/float(union) >= thresh in Python doubles; 0 when union == 0
 __device__ __forceinline__ bool grid_iou_ge(const Rect& a, const Rect& b, double thresh) {
   int inter = rect_inter(a, b);

@@ -250,7 +250,9 @@ __device__ __forceinline__ uint4 bf8_max(uint4 a, uint4 b) {
 template <bool F16>
 __global__ void pair_relu_pool_bf16_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const int* __restrict__ pair_sub,
                                            const int* __restrict__ pair_obj, long long total_vec, int fs, int cvec,
-                                           const unsigned long long* __restrict__ cover, uint4* __restrict__ out) {
+                                           const unsigned long long* __restrict__ cover, const int4* __restrict__ fp_boxes,
+                                           const uint4* __restrict__ u_bg, const uint4* __restrict__ v_bg, int fp_bh,
+                                           uint4* __restrict__ out) {
   const int hp = fs / 2;
   const int per_pair = hp * hp * cvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total_vec; i += (long long)gridDim.x * blockDim.x) {
@@ -264,12 +266,19 @@ __global__ void pair_relu_pool_bf16_kernel(const uint4* __restrict__ u, const ui
       const unsigned long long nbr = (rowbits << (8 * cy0)) | (cy1 > cy0 ? rowbits << (8 * cy1) : 0ull);
       if (!(__ldg(cover + pr) & nbr)) continue;
     }
-    const long long su = (long long)pair_sub[pr] * fs * fs, so = (long long)pair_obj[pr] * fs * fs;
+    const int bs = pair_sub[pr], bo = pair_obj[pr];
+    const long long su = (long long)bs * fs * fs, so = (long long)bo * fs * fs;
+    // footprint maps (fp_boxes): U / V hold a box's values only inside its conv2_1 footprint rectangle, the background maps apply elsewhere
+    Rect ru = {0, fs, 0, fs}, rv = {0, fs, 0, fs};
+    if (fp_boxes) { ru = conv2_valid_rect(__ldg(fp_boxes + bs), fs, fp_bh); rv = conv2_valid_rect(__ldg(fp_boxes + bo), fs, fp_bh); }
     uint4 acc = make_uint4(0u, 0u, 0u, 0u);                // +0.0 in every lane: relu folded into the running max
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const long long off = ((long long)(2 * py + (q >> 1)) * fs + (2 * px + (q & 1))) * cvec + cv;
-      acc = bf8_max<F16>(acc, bf8_add<F16>(__ldg(u + su * cvec + off), __ldg(v + so * cvec + off)));
+      const int y = 2 * py + (q >> 1), x = 2 * px + (q & 1);
+      const long long off = ((long long)y * fs + x) * cvec + cv;
+      const uint4* up = rect_has(ru, x, y) ? u + su * cvec : u_bg;
+      const uint4* vp = rect_has(rv, x, y) ? v + so * cvec : v_bg;
+      acc = bf8_max<F16>(acc, bf8_add<F16>(__ldg(up + off), __ldg(vp + off)));
     }
     out[i] = acc;
   }
@@ -279,7 +288,8 @@ template <bool F16>
 __global__ void __launch_bounds__(128, 4)
 pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __restrict__ v, const int* __restrict__ box_off,
                                  const int* __restrict__ lut, int n_max, int img0, int pair_base, int chunk_pairs, int fs, int cvec,
-                                 const unsigned long long* __restrict__ cover, uint4* __restrict__ out) {
+                                 const unsigned long long* __restrict__ cover, const int4* __restrict__ fp_boxes,
+                                 const uint4* __restrict__ u_bg, const uint4* __restrict__ v_bg, int fp_bh, uint4* __restrict__ out) {
   // grid = (slabs, subject tiles, images of the chunk); block = 128 consecutive (pooled pixel, channel vector) slots.
   // The (subject, object) -> pair row table and the pairs' cover words are the same for every thread of the block: they are staged
   // in shared memory once (two dependent global loads per (subject, object) and thread became the latency chain of this kernel
@@ -287,6 +297,7 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
   extern __shared__ unsigned long long pp_smem[];
   unsigned long long* s_cov = pp_smem;                                       // [PP_TA][n_max] cover word (0 = pair absent / not in chunk)
   int* s_row = reinterpret_cast<int*>(pp_smem + PP_TA * n_max);              // [PP_TA][n_max] chunk-local pair row
+  int4* s_rect = reinterpret_cast<int4*>(pp_smem + PP_TA * n_max + (PP_TA * n_max + 1) / 2);   // [n_max] object footprint rectangles (fp_boxes)
   const int img = img0 + blockIdx.z;
   const int b0 = box_off[img], n = box_off[img + 1] - b0;
   const int a0 = blockIdx.y * PP_TA;
@@ -299,6 +310,11 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
     s_row[t * n_max + b] = p;
     s_cov[t * n_max + b] = p < 0 ? 0ull : (cover ? __ldg(cover + p) : ~0ull);
   }
+  if (fp_boxes)
+    for (int b = threadIdx.x; b < n; b += blockDim.x) {
+      const Rect r = conv2_valid_rect(__ldg(fp_boxes + b0 + b), fs, fp_bh);
+      s_rect[b] = make_int4(r.x0, r.x1, r.y0, r.y1);
+    }
   __syncthreads();
   const int hp = fs / 2;
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,8 +346,10 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
   for (int t = 0; t < PP_TA; ++t) {
     if (!((need_t >> t) & 1u)) continue;
     const long long base = (long long)(b0 + min(a0 + t, n - 1)) * fs * fs * cvec;
+    Rect ru = {0, fs, 0, fs};
+    if (fp_boxes) { const int4 r = s_rect[min(a0 + t, n - 1)]; ru.x0 = r.x; ru.x1 = r.y; ru.y0 = r.z; ru.y1 = r.w; }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) ua[t][q] = __ldg(u + base + qoff[q]);
+    for (int q = 0; q < 4; ++q) ua[t][q] = __ldg((rect_has(ru, 2 * px + (q & 1), 2 * py + (q >> 1)) ? u + base : u_bg) + qoff[q]);
   }
   const long long out_slot = (long long)pix * cvec + cv;
   const long long pair_stride = (long long)hp * hp * cvec;
@@ -345,9 +363,11 @@ pair_relu_pool_tiled_bf16_kernel(const uint4* __restrict__ u, const uint4* __res
     }
     if (!any) continue;                                  // uniform per warp
     const long long vb = (long long)(b0 + b) * fs * fs * cvec;
+    Rect rv = {0, fs, 0, fs};
+    if (fp_boxes) { const int4 r = s_rect[b]; rv.x0 = r.x; rv.x1 = r.y; rv.y0 = r.z; rv.y1 = r.w; }
     uint4 vq[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) vq[q] = __ldg(v + vb + qoff[q]);
+    for (int q = 0; q < 4; ++q) vq[q] = __ldg((rect_has(rv, 2 * px + (q & 1), 2 * py + (q >> 1)) ? v + vb : v_bg) + qoff[q]);
 #pragma unroll
     for (int t = 0; t < PP_TA; ++t) {
       if (prow[t] < 0) continue;                         // warp-uniform
@@ -398,14 +418,29 @@ extern "C" int hc_box_select(const void* t_img, const int32_t* boxes, const int3
   return cuda_status("hc_box_select");
 }
 
+static int check_footprint(const hc_uv_footprint* fp, const float* bias, int32_t fs, const char* who) {
+  if (!fp) return HC_OK;
+  HC_REQUIRE(fp->boxes && fp->u_bg && fp->v_bg && aligned16(fp->boxes) && aligned16(fp->u_bg) && aligned16(fp->v_bg), HC_E_NULL, who);
+  HC_REQUIRE(!bias && fs >= 8 && (fp->block_rows == 4 || fp->block_rows == 8), HC_E_SHAPE, who);
+  return HC_OK;
+}
+
 extern "C" int hc_pair_relu_pool(const void* u, const void* v, const float* bias, const int32_t* pair_sub, const int32_t* pair_obj,
-                                 int32_t n_pairs, int32_t fs, int32_t channels, const uint64_t* cover, void* out, int32_t operand_f16,
-                                 hc_stream_t stream_) {
+                                 int32_t n_pairs, int32_t fs, int32_t channels, const uint64_t* cover, const hc_uv_footprint* fp, void* out,
+                                 int32_t operand_f16, hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(u && v && pair_sub && pair_obj && out, HC_E_NULL, "hc_pair_relu_pool: NULL pointer");
   HC_REQUIRE(!operand_f16 || !bias, HC_E_SHAPE, "hc_pair_relu_pool: fp16 operands take the packed path (bias == NULL)");
   HC_REQUIRE(n_pairs > 0 && fs > 0 && fs % 2 == 0 && channels % 8 == 0, HC_E_SHAPE, "hc_pair_relu_pool: bad sizes");
   HC_REQUIRE(!cover || (!bias && fs == 32), HC_E_SHAPE, "hc_pair_relu_pool: the footprint cover needs the packed path (bias == NULL) and feature_size 32");
+  {
+    int frc = check_footprint(fp, bias, fs, "hc_pair_relu_pool: footprint maps need boxes + both background maps (16-byte aligned), bias == NULL, block_rows 4 or 8");
+    if (frc != HC_OK) return frc;
+  }
+  const int4* fpb = fp ? reinterpret_cast<const int4*>(fp->boxes) : nullptr;
+  const uint4* fpu = fp ? reinterpret_cast<const uint4*>(fp->u_bg) : nullptr;
+  const uint4* fpv = fp ? reinterpret_cast<const uint4*>(fp->v_bg) : nullptr;
+  const int fph = fp ? fp->block_rows : 0;
   HC_REQUIRE(aligned16(u) && aligned16(v) && aligned16(out), HC_E_ALIGN, "hc_pair_relu_pool: 16-byte alignment");
   int rc = hc_device_check();
   if (rc != HC_OK) return rc;
@@ -415,12 +450,12 @@ extern "C" int hc_pair_relu_pool(const void* u, const void* v, const float* bias
       pair_relu_pool_bf16_kernel<true><<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                                     pair_sub, pair_obj, total, fs, channels / 8,
                                                                                     reinterpret_cast<const unsigned long long*>(cover),
-                                                                                    reinterpret_cast<uint4*>(out));
+                                                                                    fpb, fpu, fpv, fph, reinterpret_cast<uint4*>(out));
     else
       pair_relu_pool_bf16_kernel<false><<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                                      pair_sub, pair_obj, total, fs, channels / 8,
                                                                                      reinterpret_cast<const unsigned long long*>(cover),
-                                                                                     reinterpret_cast<uint4*>(out));
+                                                                                     fpb, fpu, fpv, fph, reinterpret_cast<uint4*>(out));
     return cuda_status("hc_pair_relu_pool");
   }
   pair_relu_pool_kernel<<<stream_grid(total, 256), 256, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
@@ -443,7 +478,8 @@ extern "C" int hc_pair_lut_build(const int32_t* pair_sub, const int32_t* pair_ob
 
 extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float* bias, const int32_t* box_offsets, const int32_t* lut,
                                        int32_t n_max, int32_t img0, int32_t n_img, int32_t pair_base, int32_t chunk_pairs, int32_t fs,
-                                       int32_t channels, const uint64_t* cover, void* out, int32_t operand_f16, hc_stream_t stream_) {
+                                       int32_t channels, const uint64_t* cover, const hc_uv_footprint* fp, void* out, int32_t operand_f16,
+                                       hc_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   HC_REQUIRE(u && v && box_offsets && lut && out, HC_E_NULL, "hc_pair_relu_pool_tiled: NULL pointer");
   HC_REQUIRE(!operand_f16 || !bias, HC_E_SHAPE, "hc_pair_relu_pool_tiled: fp16 operands take the packed path (bias == NULL)");
@@ -458,19 +494,29 @@ extern "C" int hc_pair_relu_pool_tiled(const void* u, const void* v, const float
   HC_REQUIRE(!cover || fs == 32, HC_E_SHAPE, "hc_pair_relu_pool_tiled: the footprint cover is defined on the 8x8 cell grid of feature_size 32");
   dim3 grid(slots / 128, (n_max + PP_TA - 1) / PP_TA, n_img);
   if (!bias) {
-    const size_t smem = (size_t)PP_TA * n_max * (sizeof(unsigned long long) + sizeof(int));
-    HC_REQUIRE(smem <= 48 * 1024, HC_E_SHAPE, "hc_pair_relu_pool_tiled: more than 1024 boxes per image");
+    const size_t smem = (size_t)PP_TA * n_max * sizeof(unsigned long long) + (size_t)((PP_TA * n_max + 1) / 2) * 8 + (size_t)n_max * 16 + 16;
+    HC_REQUIRE(smem <= 48 * 1024, HC_E_SHAPE, "hc_pair_relu_pool_tiled: more than ~750 boxes per image");
+    {
+      int frc = check_footprint(fp, bias, fs, "hc_pair_relu_pool_tiled: footprint maps need boxes + both background maps (16-byte aligned), bias == NULL, block_rows 4 or 8");
+      if (frc != HC_OK) return frc;
+    }
+    const int4* fpb = fp ? reinterpret_cast<const int4*>(fp->boxes) : nullptr;
+    const uint4* fpu = fp ? reinterpret_cast<const uint4*>(fp->u_bg) : nullptr;
+    const uint4* fpv = fp ? reinterpret_cast<const uint4*>(fp->v_bg) : nullptr;
+    const int fph = fp ? fp->block_rows : 0;
     if (operand_f16)
       pair_relu_pool_tiled_bf16_kernel<true><<<grid, 128, smem, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                        box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec,
-                                                                       reinterpret_cast<const unsigned long long*>(cover), reinterpret_cast<uint4*>(out));
+                                                                       reinterpret_cast<const unsigned long long*>(cover), fpb, fpu, fpv, fph,
+                                                                       reinterpret_cast<uint4*>(out));
     else
       pair_relu_pool_tiled_bf16_kernel<false><<<grid, 128, smem, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v),
                                                                         box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec,
-                                                                        reinterpret_cast<const unsigned long long*>(cover), reinterpret_cast<uint4*>(out));
+                                                                        reinterpret_cast<const unsigned long long*>(cover), fpb, fpu, fpv, fph,
+                                                                        reinterpret_cast<uint4*>(out));
     return cuda_status("hc_pair_relu_pool_tiled");
   }
-  HC_REQUIRE(!cover, HC_E_SHAPE, "hc_pair_relu_pool_tiled: the footprint cover needs the packed path (bias == NULL)");
+  HC_REQUIRE(!cover && !fp, HC_E_SHAPE, "hc_pair_relu_pool_tiled: the footprint cover / footprint maps need the packed path (bias == NULL)");
   pair_relu_pool_tiled_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const uint4*>(u), reinterpret_cast<const uint4*>(v), bias,
                                                         box_offsets, lut, n_max, img0, pair_base, chunk_pairs, fs, cvec, grid.y, grid.x,
                                                         reinterpret_cast<uint4*>(out));

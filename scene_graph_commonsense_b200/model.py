@@ -148,13 +148,22 @@ class PackedHead:
             self._uv_bg = self.conv2_halves(abox)
         return self._uv_bg
 
-    def conv2_halves_sparse(self, abox, boxes, m_sub=1, block_rows=4):
-        """`conv2_halves` on the box footprint: U / V are pre-filled with the background maps and the implicit GEMM visits only the
-        8 x block_rows-pixel blocks within one pixel of each box (`ops.conv2_box_blocks`); bit-identical to the dense halves."""
+    def conv2_halves_sparse(self, abox, boxes, m_sub=1, block_rows=4, prefill=True, poison=False):
+        """`conv2_halves` on the box footprint: the implicit GEMM visits only the 8 x block_rows-pixel blocks within one pixel of each
+        box (`ops.conv2_box_blocks`).  prefill=True: U / V are pre-filled with the background maps first, the result is bit-identical
+        to the dense halves everywhere.  prefill=False: nothing else is written (saves 2 MiB of background per box) and the maps are
+        only defined inside each box's footprint rectangle - consumers take `self.uv_footprint(boxes, block_rows)` as `fp` and read
+        the background maps elsewhere."""
         n_box, fs = abox.shape[0], abox.shape[1]
         u_bg, v_bg = self.uv_background()
-        u = ops.broadcast_rows(u_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=self.act_dtype, device=abox.device))
-        v = ops.broadcast_rows(v_bg, n_box, torch.empty(n_box, fs, fs, 512, dtype=self.act_dtype, device=abox.device))
+        u = torch.empty(n_box, fs, fs, 512, dtype=self.act_dtype, device=abox.device)
+        v = torch.empty(n_box, fs, fs, 512, dtype=self.act_dtype, device=abox.device)
+        if prefill:
+            ops.broadcast_rows(u_bg, n_box, u)
+            ops.broadcast_rows(v_bg, n_box, v)
+        elif poison:                 # tests: anything read outside a footprint rectangle shows up as NaN
+            u.fill_(float("nan"))
+            v.fill_(float("nan"))
         blocks, n_blocks = ops.conv2_box_blocks(boxes, block_rows, fs)
         self.last_conv2_blocks = (n_blocks, block_rows, n_box)      # device count: bench.py reads it after the timed region
         for out, w, base, bias in ((u, self.w2s, 0, None), (v, self.w2o, 128, self.b2)):
@@ -162,6 +171,11 @@ class PackedHead:
                         n_img=n_box, h=fs, w=fs, c_total=256, c_base=base, c_in=128, group_m=1, m_sub=m_sub, tag="conv2_half", blocks=blocks,
                         n_blocks=n_blocks, block_rows=block_rows, block_cols=8)
         return u, v
+
+    def uv_footprint(self, boxes, block_rows=4):
+        """The `fp` argument of the pooling ops for U / V made by `conv2_halves_sparse(prefill=False)` on `boxes`."""
+        u_bg, v_bg = self.uv_background()
+        return (boxes, u_bg, v_bg, block_rows)
 
     def p3_background(self):
         """Pooled conv3_1 output [1,8,8,1024] bf16 of a pair whose two box masks are empty: tanh(conv1 bias) everywhere

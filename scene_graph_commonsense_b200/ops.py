@@ -209,16 +209,27 @@ def box_select(t_img, boxes, box_img, fill, fs=32, out=None):
     return _call("box_select")(t_img, boxes, box_img, fill, fs)
 
 
-@_op("pair_relu_pool", "(Tensor u, Tensor v, Tensor? bias, Tensor pair_sub, Tensor pair_obj, int fs, Tensor(a!) out, Tensor? cover) -> ()")
-def _pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs, out, cover):
-    _A.pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs, out=out, cover=cover)
+def _fp_pack(fp):
+    return (None, None, None, 0) if fp is None else (fp[0], fp[1], fp[2], int(fp[3]))
 
 
-def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None, cover=None):
-    """`cover` (int64 per pair, `pair_cover_masks`): write only the pooled pixels a listed conv3_1 block reads (packed path, bias None)."""
+def _fp_unpack(boxes, u_bg, v_bg, rows):
+    return None if boxes is None else (boxes, u_bg, v_bg, rows)
+
+
+@_op("pair_relu_pool", "(Tensor u, Tensor v, Tensor? bias, Tensor pair_sub, Tensor pair_obj, int fs, Tensor(a!) out, Tensor? cover, "
+     "Tensor? fp_boxes, Tensor? u_bg, Tensor? v_bg, int fp_block_rows) -> ()")
+def _pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs, out, cover, fp_boxes, u_bg, v_bg, fp_block_rows):
+    _A.pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs, out=out, cover=cover, fp=_fp_unpack(fp_boxes, u_bg, v_bg, fp_block_rows))
+
+
+def pair_relu_pool(u, v, bias, pair_sub, pair_obj, fs=32, out=None, cover=None, fp=None):
+    """`cover` (int64 per pair, `pair_cover_masks`): write only the pooled pixels a listed conv3_1 block reads (packed path, bias None).
+    `fp` = (boxes, u_bg, v_bg, conv2 block rows): u / v hold a box's values only inside its conv2_1 footprint (no background pre-fill);
+    the background maps are read elsewhere (`PackedHead.conv2_halves_sparse(prefill=False)`)."""
     if out is None:
         out = torch.empty(pair_sub.numel(), fs // 2, fs // 2, u.shape[-1], dtype=u.dtype, device=u.device)
-    _call("pair_relu_pool")(u, v, bias, pair_sub, pair_obj, fs, out, cover)
+    _call("pair_relu_pool")(u, v, bias, pair_sub, pair_obj, fs, out, cover, *_fp_pack(fp))
     return out
 
 
@@ -246,16 +257,18 @@ def pair_cover_masks(boxes, pair_sub, pair_obj, block_rows, block_cols, shared, 
 
 
 @_op("pair_relu_pool_tiled", "(Tensor u, Tensor v, Tensor? bias, Tensor box_offsets, Tensor lut, int img0, int n_img, int pair_base, "
-     "int chunk_pairs, int fs, Tensor(a!) out, Tensor? cover) -> ()")
-def _pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out, cover):
-    _A.pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out=out, cover=cover)
+     "int chunk_pairs, int fs, Tensor(a!) out, Tensor? cover, Tensor? fp_boxes, Tensor? u_bg, Tensor? v_bg, int fp_block_rows) -> ()")
+def _pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out, cover, fp_boxes, u_bg, v_bg, fp_block_rows):
+    _A.pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out=out, cover=cover,
+                            fp=_fp_unpack(fp_boxes, u_bg, v_bg, fp_block_rows))
 
 
-def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None, cover=None):
-    """`cover` (int64 per pair of the chunk, `pair_cover_masks`): write only the pooled pixels a listed conv3_1 block reads."""
+def pair_relu_pool_tiled(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs=32, out=None, cover=None, fp=None):
+    """`cover` (int64 per pair of the chunk, `pair_cover_masks`): write only the pooled pixels a listed conv3_1 block reads.
+    `fp`: footprint-only u / v, see `pair_relu_pool`."""
     if out is None:
         out = torch.empty(chunk_pairs, fs // 2, fs // 2, u.shape[-1], dtype=u.dtype, device=u.device)
-    _call("pair_relu_pool_tiled")(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out, cover)
+    _call("pair_relu_pool_tiled")(u, v, bias, box_offsets, lut, img0, n_img, pair_base, chunk_pairs, fs, out, cover, *_fp_pack(fp))
     return out
 
 

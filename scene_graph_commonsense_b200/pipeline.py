@@ -224,6 +224,9 @@ class RelationPipeline:
         self.dense_above = float(dense_above)
         self.last_path = None               # "shared" / "blocks" / "dense": the formulation the last forward_pairs took
         self.host_offsets = os.environ.get("HC_HOST_OFFSETS", "1") != "0"    # use DeviceBatch.pair_offsets_host (no D2H read per step)
+        # U / V without the background pre-fill (5.4 GB of writes per cfg2 window): the pooling kernels read the background maps outside
+        # a box's conv2_1 footprint rectangle themselves - the same bits (shared-footprint path, box-footprint conv2 only)
+        self.uv_select = os.environ.get("HC_UV_SELECT", "1") != "0"
         # per-box fc1 rows as a K-cell-sparse GEMM over each box's own cells (needs the CTA-pair conv3_1 kernel); 0 = dense rows
         self.fc1_box_sparse = os.environ.get("HC_FC1_BOX_SPARSE", "1") != "0"
         self.device = torch.device(device)
@@ -295,8 +298,10 @@ class RelationPipeline:
         return ops.pairs_enumerate(b.boxes, b.box_offsets, b.tri_offsets, b.p_max, b.rel_tri, b.dir_tri, b.group_id, b.n_groups,
                                    b.max_tri, self.fs, offsets_host=known)
 
-    def box_features(self, b: DeviceBatch, boxes=None, box_img=None):
-        """Per-image conv1 (+tanh), per-box mask select, per-box conv2 halves -> U, V [nbox,32,32,512] bf16."""
+    def box_features(self, b: DeviceBatch, boxes=None, box_img=None, prefill=True):
+        """Per-image conv1 (+tanh), per-box mask select, per-box conv2 halves -> U, V [nbox,32,32,512] (16-bit).
+        prefill=False (box-footprint conv2 only): U / V are defined only inside each box's footprint rectangle; the pooling ops then
+        take `self.packed.uv_footprint(boxes)` and read the background maps elsewhere."""
         pk, fs = self.packed, self.fs
         n_img = b.n_images
         boxes = b.boxes if boxes is None else boxes
@@ -307,10 +312,10 @@ class RelationPipeline:
                     group_m=8, tag="conv1")
         abox = ops.box_select(t, boxes, box_img, pk.fill, fs)
         if self.conv2_sparse:
-            return pk.conv2_halves_sparse(abox, boxes, m_sub=self.conv2_m_sub)
+            return pk.conv2_halves_sparse(abox, boxes, m_sub=self.conv2_m_sub, prefill=prefill)
         return pk.conv2_halves(abox, m_sub=self.conv2_m_sub)
 
-    def box_maps(self, boxes_x, u, v, with_background_row=False):
+    def box_maps(self, boxes_x, u, v, with_background_row=False, fp=None):
         """Pooled conv3_1 output of every box of the window paired with the EMPTY box (the last row of boxes_x / u / v):
         -> sub_maps = (box, empty), obj_maps = (empty, box), each [n_box,8,8,1024] bf16, and the work-list lengths.  A real
         pair's output equals sub_maps[s] in the cells only its subject's box reaches and obj_maps[o] in those only its object's
@@ -327,7 +332,7 @@ class RelationPipeline:
         nblk = torch.zeros(max(len(starts), 1), dtype=torch.int32, device=self.device)
         for k, s in enumerate(starts):
             e = min(2 * n_box, s + self.chunk_pairs)
-            p2 = ops.pair_relu_pool(u, v, None, sub[s:e], obj[s:e], self.fs)
+            p2 = ops.pair_relu_pool(u, v, None, sub[s:e], obj[s:e], self.fs, fp=fp)
             blocks, _ = ops.conv3_active_blocks(boxes_x, sub[s:e], obj[s:e], br, self.fs, n_blocks=nblk[k:k + 1], block_cols=bc)
             ops.broadcast_rows(pk.p3_background(), e - s, maps[s:e])
             pk.conv3_blocks(p2, maps[s:e], e - s, blocks, nblk[k:k + 1], br, m_sub=self.conv3_m_sub, tag="conv3_box", block_cols=bc,
@@ -337,7 +342,7 @@ class RelationPipeline:
             return maps, nblk
         return maps[:n_box], maps[n_box:], nblk
 
-    def box_maps_sparse(self, boxes_x, u, v):
+    def box_maps_sparse(self, boxes_x, u, v, fp=None):
         """`box_maps` + the per-box fc1 rows in one pass, with the fc1 rows K-cell-sparse: a box's map differs from the background only
         in the cells the box itself reaches, so fc1(map) = fc1(background) + W1 . (map - background) and the GEMM visits, per 256-row
         tile of boxes sorted by cell rectangle, only those cells.  The CTA-pair conv3_1 kernel writes the pooled values straight into
@@ -369,7 +374,7 @@ class RelationPipeline:
         for k, s in enumerate(starts):
             e = min(n, s + self.chunk_pairs)
             cover = ops.pair_cover_masks(boxes_x, sub[s:e], obj[s:e], br, bc, False, fs) if self.pool_footprint else None
-            p2 = ops.pair_relu_pool(u, v, None, sub[s:e], obj[s:e], fs, cover=cover)          # only the pixels the listed blocks read
+            p2 = ops.pair_relu_pool(u, v, None, sub[s:e], obj[s:e], fs, cover=cover, fp=fp)   # only the pixels the listed blocks read
             blocks, _ = ops.conv3_active_blocks(boxes_x, sub[s:e], obj[s:e], br, fs, n_blocks=nblk[k:k + 1], block_cols=bc)
             ops.broadcast_rows(bg, e - s, maps[s:e])
             pk.conv3_diff(p2, d.view(n, 8, 8, 1024), e - s, blocks, nblk[k:k + 1], br, bg, bg, zeros[:e - s], zeros[:e - s], row_of[s:e],
@@ -578,7 +583,9 @@ class RelationPipeline:
             lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
         windows = self._fc1_windows(pairs)
         boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))      # + the empty box (all background), partner of every box
-        u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))))
+        select = self.uv_select and self.conv2_sparse                 # no background pre-fill of U / V: the pooling kernels select
+        u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))), prefill=not select)
+        fp = pk.uv_footprint(boxes_x) if select else None
         # The pooling of the first chunks needs only U and V: its buffers are taken NOW (anything the allocator recycles into them
         # was last used by work already queued on this stream) and an event lets the pooling stream start under the per-box stages
         early = self._pool_buffers(windows[0][2])
@@ -586,17 +593,17 @@ class RelationPipeline:
         uv_ready.record(torch.cuda.current_stream())
         if self.fc1_box_sparse and self.conv3_pairs:
             # per-box fc1 rows WITHOUT their background term (K-cell-sparse over each box's own cells): fc1(pair) = F_bg + W.d_s + W.d_o + W.d
-            maps, f_box, nblk_box = self.box_maps_sparse(boxes_x, u, v)
+            maps, f_box, nblk_box = self.box_maps_sparse(boxes_x, u, v, fp=fp)
             bias_eff = (pk.b_fc1 + pk.fc1_background()).contiguous()
         else:
-            maps, nblk_box = self.box_maps(boxes_x, u, v, with_background_row=True)
+            maps, nblk_box = self.box_maps(boxes_x, u, v, with_background_row=True, fp=fp)
             f_box = pk.fc1_rows(maps, 2 * n_box + 1)                 # fc1 (no bias) of (box, empty), (empty, box), background
             bias_eff = (pk.b_fc1 - f_box[2 * n_box]).contiguous()
         raw = torch.empty(n, 512, dtype=torch.float32, device=dev)
         nblks, masks_all = [], []
         for i, (w0, w1, chunks) in enumerate(windows):
             nblk, masks = self._fc1_shared_window(b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw,
-                                                  early if i == 0 else None, uv_ready if i == 0 and self.early_pool else None)
+                                                  early if i == 0 else None, uv_ready if i == 0 and self.early_pool else None, fp=fp)
             nblks.append(nblk)
             masks_all.append(masks)
         self.last_n_blocks = torch.cat(nblks + [nblk_box])
@@ -630,7 +637,7 @@ class RelationPipeline:
                     cov=[torch.empty(cap, dtype=torch.int64, device=dev) for _ in range(n_buf)],
                     nblk=torch.zeros(len(chunks), dtype=torch.int32, device=dev))
 
-    def _fc1_shared_window(self, b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw, pool=None, pool_ready=None):
+    def _fc1_shared_window(self, b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw, pool=None, pool_ready=None, fp=None):
         """Pairs [w0, w1) of the batch: sort, conv3_1 differences chunk by chunk (pooling of chunk k+1 under the GEMM of chunk k),
         then one K-cell-sparse fc1 + fc2 into raw[w0:w1]."""
         pk, fs, br, bc = self.packed, self.fs, self.conv3_block_rows, self.conv3_block_cols
@@ -673,9 +680,9 @@ class RelationPipeline:
                     cover = None
                     if self.pool_footprint:      # only the pooled pixels a listed block reads (block + halo)
                         cover = ops.pair_cover_masks(b.boxes, sub_k, obj_k, br, bc, True, fs, out=cov_bufs[k % len(bufs)])
-                    ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, fs, out=buf, cover=cover)
+                    ops.pair_relu_pool_tiled(u, v, None, b.box_offsets, lut, img0, n_img, base, cnt, fs, out=buf, cover=cover, fp=fp)
                 else:
-                    ops.pair_relu_pool(u, v, None, sub_k, obj_k, fs, out=buf)
+                    ops.pair_relu_pool(u, v, None, sub_k, obj_k, fs, out=buf, fp=fp)
                 ops.conv3_shared_blocks(b.boxes, sub_k, obj_k, br, fs, blocks=blk, n_blocks=nblk[k:k + 1], block_cols=bc)
                 pooled = torch.cuda.Event()
                 pooled.record(side)

@@ -243,3 +243,60 @@ def test_conv2_halves_on_the_box_footprint_equal_dense_bit_for_bit(block_rows, m
         if not want.any():
             assert not cover[i].any()
     assert 0 < len(e) < n_box * 4 * (32 // block_rows)
+
+
+@pytest.mark.parametrize("fmt", ["bf16", "fp16"])
+def test_pooling_on_footprint_only_conv2_halves_equals_prefilled(fmt):
+    """`conv2_halves_sparse(prefill=False)` writes U / V only on each box's conv2_1 footprint; the pooling kernels (pair-list and
+    tiled, with and without the conv3_1 cover) given `uv_footprint` read the background maps elsewhere and produce the same bits as
+    on the pre-filled maps - the un-written part is NaN-poisoned here, so any stray read would show."""
+    from scene_graph_commonsense_b200 import model, ops, pipeline
+    dt = torch.float16 if fmt == "fp16" else torch.bfloat16
+    pk = model.PackedHead(synthetic.head_state_dict(seed=0), DEV, operand_dtype=dt)
+    samples = synthetic.make_batch([95, 96, 97], [14, 9, 3], with_maps=True)
+    samples[0].bbox[:14] = torch.tensor(EDGE_BOXES[:14], dtype=samples[0].bbox.dtype)
+    pipe = pipeline.RelationPipeline(pk, DEV, commonsense=False)
+    b = pipeline.batch_from_samples(samples, DEV, skip_mode="batch")
+    pairs = pipe.enumerate_pairs(b)
+    n = pairs["n"]
+    boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))
+    box_img_x = torch.cat((b.box_img, b.box_img.new_zeros(1)))
+    u1, v1 = pipe.box_features(b, boxes_x, box_img_x, prefill=True)
+    x = ops.pack_pixels(b.feat, b.depth, model.K1_PAD, dtype=dt)
+    t = torch.empty(b.n_images * 1024, 256, dtype=dt, device=DEV)
+    ops.tc_gemm(x, pk.w1, t, b.n_images * 1024, 256, model.K1_PAD, bias=pk.b1, lda=model.K1_PAD, ldc=256, epilogue=ops.EPI_BF16, act=ops.ACT_TANH, group_m=8)
+    abox = ops.box_select(t, boxes_x, box_img_x, pk.fill, 32)
+    u2, v2 = pk.conv2_halves_sparse(abox, boxes_x, prefill=False, poison=True)
+    fp = pk.uv_footprint(boxes_x)
+    assert torch.isnan(u2.float()).any() and torch.isnan(v2.float()).any()          # the poison really is there
+    inside = ~torch.isnan(u2.float()).any(3)
+    assert torch.equal(u2[inside].view(torch.int16), u1[inside].view(torch.int16))  # what WAS written equals the complete maps
+    # pair-list kernel, plus pairs with the empty box (row n_box) as in `box_maps`
+    n_box = b.boxes.shape[0]
+    sub = torch.cat((pairs["sub"], torch.arange(n_box, dtype=torch.int32, device=DEV)))
+    obj = torch.cat((pairs["obj"], torch.full((n_box,), n_box, dtype=torch.int32, device=DEV)))
+    want = ops.pair_relu_pool(u1, v1, None, sub, obj)
+    got = ops.pair_relu_pool(u2, v2, None, sub, obj, fp=fp)
+    assert not torch.isnan(got.float()).any() and torch.equal(got.view(torch.int16), want.view(torch.int16))
+    # tiled kernel, without and with the conv3_1 cover
+    n_max = int(np.max(np.diff(b.box_offsets_host)))
+    lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
+    want_t = ops.pair_relu_pool_tiled(u1, v1, None, b.box_offsets, lut, 0, b.n_images, 0, n)
+    got_t = ops.pair_relu_pool_tiled(u2, v2, None, b.box_offsets, lut, 0, b.n_images, 0, n, fp=fp)
+    assert not torch.isnan(got_t.float()).any() and torch.equal(got_t.view(torch.int16), want_t.view(torch.int16))
+    assert torch.equal(want_t.view(torch.int16), want[:n].view(torch.int16))
+    cover = ops.pair_cover_masks(b.boxes, pairs["sub"], pairs["obj"], 4, 4, True)
+    a = torch.full_like(want_t, 7.0)
+    c = torch.full_like(want_t, 7.0)
+    ops.pair_relu_pool_tiled(u1, v1, None, b.box_offsets, lut, 0, b.n_images, 0, n, out=a, cover=cover)
+    ops.pair_relu_pool_tiled(u2, v2, None, b.box_offsets, lut, 0, b.n_images, 0, n, out=c, cover=cover, fp=fp)
+    torch.cuda.synchronize()
+    assert not torch.isnan(c.float()).any() and torch.equal(a.view(torch.int16), c.view(torch.int16))
+    # and the whole forward with / without the select agrees bit for bit
+    outs = []
+    for sel in (True, False):
+        p2 = pipeline.RelationPipeline(pk, DEV, commonsense=False, chunk_pairs=150)
+        p2.uv_select = sel
+        outs.append([z.clone() for z in p2.forward_pairs(b, p2.enumerate_pairs(b))])
+    for x1, x2 in zip(*outs):
+        assert torch.equal(x1, x2)
