@@ -227,6 +227,7 @@ class RelationPipeline:
         # U / V without the background pre-fill (5.4 GB of writes per cfg2 window): the pooling kernels read the background maps outside
         # a box's conv2_1 footprint rectangle themselves - the same bits (shared-footprint path, box-footprint conv2 only)
         self.uv_select = os.environ.get("HC_UV_SELECT", "1") != "0"
+        self.early_prep = os.environ.get("HC_EARLY_PREP", "1") != "0"       # first window's sort / masks / zero fill on the pooling stream
         # per-box fc1 rows as a K-cell-sparse GEMM over each box's own cells (needs the CTA-pair conv3_1 kernel); 0 = dense rows
         self.fc1_box_sparse = os.environ.get("HC_FC1_BOX_SPARSE", "1") != "0"
         self.device = torch.device(device)
@@ -582,6 +583,22 @@ class RelationPipeline:
                 (b.box_offsets[1:] - b.box_offsets[:-1]).max().item())
             lut = ops.pair_lut_build(pairs["sub"], pairs["obj"], pairs["img"], b.box_offsets, n_box, n_max)
         windows = self._fc1_windows(pairs)
+        # The first window's row order, K-cell masks and zero-filled operand need only the boxes and the pair list: they are made on
+        # the pooling stream NOW, under the per-image / per-box stages (HC_EARLY_PREP; everything the allocator may recycle into these
+        # buffers was last used by work already queued on the compute stream, hence the event)
+        prep0 = None
+        if self.early_prep and self.overlap:
+            main, side = torch.cuda.current_stream(), self._side_stream()
+            queued = torch.cuda.Event()
+            queued.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(queued)
+                prep0 = self._window_prep(b, pairs, windows[0][0], windows[0][1])
+                prep0["done"] = torch.cuda.Event()
+                prep0["done"].record(side)
+            for t in prep0.values():
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(main)                            # allocated on the pooling stream, consumed on the compute stream
         boxes_x = torch.cat((b.boxes, b.boxes.new_zeros(1, 4)))      # + the empty box (all background), partner of every box
         select = self.uv_select and self.conv2_sparse                 # no background pre-fill of U / V: the pooling kernels select
         u, v = self.box_features(b, boxes_x, torch.cat((b.box_img, b.box_img.new_zeros(1))), prefill=not select)
@@ -603,7 +620,8 @@ class RelationPipeline:
         nblks, masks_all = [], []
         for i, (w0, w1, chunks) in enumerate(windows):
             nblk, masks = self._fc1_shared_window(b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw,
-                                                  early if i == 0 else None, uv_ready if i == 0 and self.early_pool else None, fp=fp)
+                                                  early if i == 0 else None, uv_ready if i == 0 and self.early_pool else None, fp=fp,
+                                                  prep=prep0 if i == 0 else None)
             nblks.append(nblk)
             masks_all.append(masks)
         self.last_n_blocks = torch.cat(nblks + [nblk_box])
@@ -637,15 +655,11 @@ class RelationPipeline:
                     cov=[torch.empty(cap, dtype=torch.int64, device=dev) for _ in range(n_buf)],
                     nblk=torch.zeros(len(chunks), dtype=torch.int32, device=dev))
 
-    def _fc1_shared_window(self, b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw, pool=None, pool_ready=None, fp=None):
-        """Pairs [w0, w1) of the batch: sort, conv3_1 differences chunk by chunk (pooling of chunk k+1 under the GEMM of chunk k),
-        then one K-cell-sparse fc1 + fc2 into raw[w0:w1]."""
-        pk, fs, br, bc = self.packed, self.fs, self.conv3_block_rows, self.conv3_block_cols
-        dev = self.device
-        n, n_box = w1 - w0, b.boxes.shape[0]
+    def _window_prep(self, b, pairs, w0, w1):
+        """Row order of the fc1 operand of pairs [w0, w1): sorted by the cell rectangle both boxes reach (pairs with none last), the
+        per-tile K-cell masks, and the operand itself with the visited cells zero-filled.  Needs only the boxes and the pair list."""
+        fs, dev, n = self.fs, self.device, w1 - w0
         sub_w, obj_w = pairs["sub"][w0:w1], pairs["obj"][w0:w1]
-        sub_maps, obj_maps = maps[:n_box], maps[n_box:2 * n_box]
-        # row order of the fc1 operand: pairs sorted by the cell rectangle both boxes reach (pairs with none last)
         keys = ops.pair_cell_keys(b.boxes, sub_w, obj_w, fs)
         perm64 = torch.sort(keys, stable=True)[1]                    # sorted row -> pair (window-local)
         perm = perm64.to(torch.int32)
@@ -655,11 +669,25 @@ class RelationPipeline:
         masks = ops.tile_cell_masks(b.boxes, row_sub, row_obj, 256, fs)
         d = torch.empty(n, 64, 1024, dtype=self.packed.act_dtype, device=dev)
         ops.cells_zero(masks, 256, n, d)
+        return dict(perm=perm, row_of=row_of, row_sub=row_sub, row_obj=row_obj, masks=masks, d=d, done=None)
+
+    def _fc1_shared_window(self, b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw, pool=None, pool_ready=None, fp=None,
+                           prep=None):
+        """Pairs [w0, w1) of the batch: sort, conv3_1 differences chunk by chunk (pooling of chunk k+1 under the GEMM of chunk k),
+        then one K-cell-sparse fc1 + fc2 into raw[w0:w1]."""
+        pk, fs, br, bc = self.packed, self.fs, self.conv3_block_rows, self.conv3_block_cols
+        n, n_box = w1 - w0, b.boxes.shape[0]
+        sub_maps, obj_maps = maps[:n_box], maps[n_box:2 * n_box]
+        main = torch.cuda.current_stream()
+        if prep is None:
+            prep = self._window_prep(b, pairs, w0, w1)
+        elif prep.get("done") is not None:
+            main.wait_event(prep["done"])                            # prepared on the side stream under the per-box stages
+        perm, row_of, row_sub, row_obj, masks, d = (prep[k] for k in ("perm", "row_of", "row_sub", "row_obj", "masks", "d"))
         if pool is None:
             pool = self._pool_buffers(chunks)
         bufs, blk_bufs, cov_bufs, nblk = pool["bufs"], pool["blk"], pool["cov"], pool["nblk"]
         two = len(bufs) == 2
-        main = torch.cuda.current_stream()
         side = self._side_stream() if two else main
         ready = pool_ready
         if ready is None:
