@@ -227,7 +227,9 @@ class RelationPipeline:
         # U / V without the background pre-fill (5.4 GB of writes per cfg2 window): the pooling kernels read the background maps outside
         # a box's conv2_1 footprint rectangle themselves - the same bits (shared-footprint path, box-footprint conv2 only)
         self.uv_select = os.environ.get("HC_UV_SELECT", "1") != "0"
-        self.early_prep = os.environ.get("HC_EARLY_PREP", "1") != "0"       # first window's sort / masks / zero fill on the pooling stream
+        # first window's sort / masks / zero fill on the pooling stream: measured 42.78 vs 42.92 ms (r02t) - not worth a second allocator
+        # pool holding the 13 GB operand; off by default
+        self.early_prep = os.environ.get("HC_EARLY_PREP", "0") != "0"
         # per-box fc1 rows as a K-cell-sparse GEMM over each box's own cells (needs the CTA-pair conv3_1 kernel); 0 = dense rows
         self.fc1_box_sparse = os.environ.get("HC_FC1_BOX_SPARSE", "1") != "0"
         self.device = torch.device(device)
