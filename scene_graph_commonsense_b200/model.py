@@ -226,13 +226,30 @@ class PackedHead:
             self._fc1_bg = self.fc1_rows(self.p3_background(), 1)[0].contiguous()
         return self._fc1_bg
 
-    def fc1_rows_sparse(self, d, n, k_masks, out_rows):
-        """W1 . d for n rows of a difference operand d [n,8,8,1024] (sorted rows, zero outside each 256-row tile's `k_masks` cells)
-        -> f32 [n,4096] in `out_rows` order: the K-cell-sparse twin of `fc1_rows` for per-box maps (d = map - background)."""
+    def fc1_background_cells(self):
+        """fc1 (no bias) of the background map cell by cell, f32 [64, 4096]: row c = W1[:, cell c] . background[cell c] (fc1's K axis
+        is packed cell-major).  Weights-only, computed once (fp32 products of the 16-bit operands, as the tensor core forms them)."""
+        if getattr(self, "_fc1_bg_cells", None) is None:
+            bg = self.p3_background().reshape(64, 1024).float()
+            w = self.w_fc1.view(4096, 64, 1024)
+            self._fc1_bg_cells = torch.stack([w[:, c, :].float() @ bg[c] for c in range(64)]).contiguous()
+        return self._fc1_bg_cells
+
+    def fc1_rows_sparse(self, maps_sorted, n, k_masks, out_rows):
+        """fc1 (no bias) of n per-box maps [n,8,8,1024] whose rows are SORTED by the box's own cell rectangle -> f32 [n,4096] in
+        `out_rows` order: a K-cell-sparse GEMM over the cells of each 256-row tile's mask plus, per tile, the background's contribution
+        of the cells the tile skips (there every map of the tile equals the background bit for bit).  Same sums as `fc1_rows`."""
+        d = maps_sorted
         out = torch.empty(n, 4096, dtype=torch.float32, device=d.device)
         pairs = int(os.environ.get("HC_FC1_BOX_PAIRS", "1"))
         ops.tc_gemm(d, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=4 if pairs else 9,
                     m_sub=1 if pairs else 2, tag="fc1_box", k_masks=k_masks, k_cell=1024, out_rows=out_rows, cta_pairs=pairs)
+        # + sum over the cells a tile does NOT visit of the background's per-cell fc1 rows (tiny: [tiles, 64] x [64, 4096], fp32)
+        bits = ((k_masks.unsqueeze(1) >> torch.arange(64, device=d.device, dtype=torch.int64)) & 1).to(torch.float32)
+        skipped = (1.0 - bits) @ self.fc1_background_cells()                       # [tiles, 4096]
+        tile_of = torch.empty(n, dtype=torch.int64, device=d.device)
+        tile_of[out_rows.long()] = torch.arange(n, device=d.device, dtype=torch.int64) // 256
+        out += skipped[tile_of]
         return out
 
     def fc1_rows(self, maps, n):

@@ -347,31 +347,29 @@ class RelationPipeline:
 
     def box_maps_sparse(self, boxes_x, u, v, fp=None):
         """`box_maps` + the per-box fc1 rows in one pass, with the fc1 rows K-cell-sparse: a box's map differs from the background only
-        in the cells the box itself reaches, so fc1(map) = fc1(background) + W1 . (map - background) and the GEMM visits, per 256-row
-        tile of boxes sorted by cell rectangle, only those cells.  The CTA-pair conv3_1 kernel writes the pooled values straight into
-        `maps` (its scratch map) and `pair_diff_kernel` forms d = map - background from them (subject map := object map :=
-        background in the difference epilogue).  -> maps [2*n_box + 1, 8,8,1024] (last row = background), f_rows f32 [2*n_box, 4096]
-        = W1 . d (WITHOUT the background term), work-list lengths."""
+        in the cells the box itself reaches, so the 2*n_box maps are produced in SORTED order (by the box's cell rectangle) and the
+        fc1 GEMM visits, per 256-row tile, only the union of its rows' cells; the background's share of the skipped cells is a
+        per-tile constant (`PackedHead.fc1_rows_sparse`).  No extra rounding: the operand is the maps themselves.
+        -> maps [2*n_box + 1, 8,8,1024] in sorted order (last row = background), map_row int32 [2*n_box] (row of (box i, empty) at i,
+        of (empty, box i) at n_box + i), f_rows f32 [2*n_box, 4096] = fc1(map) in BOX order, work-list lengths."""
         pk, br, bc, fs, dev = self.packed, self.conv3_block_rows, self.conv3_block_cols, self.fs, self.device
         n_box = boxes_x.shape[0] - 1
         n = 2 * n_box
         idx = torch.arange(n_box, dtype=torch.int32, device=dev)
         empty = torch.full((n_box,), n_box, dtype=torch.int32, device=dev)
-        sub, obj = torch.cat((idx, empty)), torch.cat((empty, idx))
         own = torch.cat((idx, idx))                                   # the box whose own cells a row can differ from the background in
+        keys = ops.pair_cell_keys(boxes_x, own, own, fs)             # box & box = the box's own cell rectangle
+        perm64 = torch.sort(keys, stable=True)[1]                    # sorted row -> (role, box)
+        perm = perm64.to(torch.int32)
+        map_row = torch.empty_like(perm)
+        map_row[perm64] = torch.arange(n, dtype=torch.int32, device=dev)
+        sub = torch.cat((idx, empty))[perm64].contiguous()            # the (box, empty) / (empty, box) pairs, in sorted order
+        obj = torch.cat((empty, idx))[perm64].contiguous()
+        own_sorted = own[perm64].contiguous()
+        masks = ops.tile_cell_masks(boxes_x, own_sorted, own_sorted, 256, fs)
         bg = pk.p3_background()
         maps = torch.empty(n + 1, 8, 8, 1024, dtype=pk.act_dtype, device=dev)
         maps[n:].copy_(bg)
-        keys = ops.pair_cell_keys(boxes_x, own, own, fs)             # box & box = the box's own cell rectangle
-        perm64 = torch.sort(keys, stable=True)[1]
-        perm = perm64.to(torch.int32)
-        row_of = torch.empty_like(perm)
-        row_of[perm64] = torch.arange(n, dtype=torch.int32, device=dev)
-        own_sorted = own[perm64].contiguous()
-        masks = ops.tile_cell_masks(boxes_x, own_sorted, own_sorted, 256, fs)
-        d = torch.empty(n, 64, 1024, dtype=pk.act_dtype, device=dev)
-        ops.cells_zero(masks, 256, n, d)
-        zeros = torch.zeros(min(n, self.chunk_pairs), dtype=torch.int32, device=dev)
         starts = list(range(0, n, self.chunk_pairs))
         nblk = torch.zeros(max(len(starts), 1), dtype=torch.int32, device=dev)
         for k, s in enumerate(starts):
@@ -380,12 +378,12 @@ class RelationPipeline:
             p2 = ops.pair_relu_pool(u, v, None, sub[s:e], obj[s:e], fs, cover=cover, fp=fp)   # only the pixels the listed blocks read
             blocks, _ = ops.conv3_active_blocks(boxes_x, sub[s:e], obj[s:e], br, fs, n_blocks=nblk[k:k + 1], block_cols=bc)
             ops.broadcast_rows(bg, e - s, maps[s:e])
-            pk.conv3_diff(p2, d.view(n, 8, 8, 1024), e - s, blocks, nblk[k:k + 1], br, bg, bg, zeros[:e - s], zeros[:e - s], row_of[s:e],
-                          m_sub=self.conv3_m_sub, tag="conv3_box", block_cols=bc, cta_pairs=self.conv3_pairs, scratch=maps[s:e])
+            pk.conv3_blocks(p2, maps[s:e], e - s, blocks, nblk[k:k + 1], br, m_sub=self.conv3_m_sub, tag="conv3_box", block_cols=bc,
+                            cta_pairs=self.conv3_pairs)
             del p2
-        f_rows = pk.fc1_rows_sparse(d, n, masks, perm)
+        f_rows = pk.fc1_rows_sparse(maps[:n], n, masks, perm)
         self.last_box_k_masks = masks
-        return maps, f_rows, nblk
+        return maps, map_row, f_rows, nblk
 
     @staticmethod
     def _greedy_chunks(offsets_host, cap):
@@ -610,20 +608,23 @@ class RelationPipeline:
         early = self._pool_buffers(windows[0][2])
         uv_ready = torch.cuda.Event()
         uv_ready.record(torch.cuda.current_stream())
-        if self.fc1_box_sparse and self.conv3_pairs:
-            # per-box fc1 rows WITHOUT their background term (K-cell-sparse over each box's own cells): fc1(pair) = F_bg + W.d_s + W.d_o + W.d
-            maps, f_box, nblk_box = self.box_maps_sparse(boxes_x, u, v, fp=fp)
-            bias_eff = (pk.b_fc1 + pk.fc1_background()).contiguous()
+        if self.fc1_box_sparse:
+            # maps in sorted order + their fc1 rows from a K-cell-sparse GEMM over each box's own cells
+            maps, map_row, f_box, nblk_box = self.box_maps_sparse(boxes_x, u, v, fp=fp)
+            bias_eff = (pk.b_fc1 - pk.fc1_background()).contiguous()
+            sub_rows = map_row[pairs["sub"].long()].contiguous()                     # row of (subject, empty) / (empty, object) in `maps`
+            obj_rows = map_row[(pairs["obj"] + n_box).long()].contiguous()
         else:
             maps, nblk_box = self.box_maps(boxes_x, u, v, with_background_row=True, fp=fp)
             f_box = pk.fc1_rows(maps, 2 * n_box + 1)                 # fc1 (no bias) of (box, empty), (empty, box), background
             bias_eff = (pk.b_fc1 - f_box[2 * n_box]).contiguous()
+            sub_rows, obj_rows = pairs["sub"], pairs["obj"] + n_box
         raw = torch.empty(n, 512, dtype=torch.float32, device=dev)
         nblks, masks_all = [], []
         for i, (w0, w1, chunks) in enumerate(windows):
             nblk, masks = self._fc1_shared_window(b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw,
                                                   early if i == 0 else None, uv_ready if i == 0 and self.early_pool else None, fp=fp,
-                                                  prep=prep0 if i == 0 else None)
+                                                  prep=prep0 if i == 0 else None, map_rows=(sub_rows, obj_rows))
             nblks.append(nblk)
             masks_all.append(masks)
         self.last_n_blocks = torch.cat(nblks + [nblk_box])
@@ -674,12 +675,13 @@ class RelationPipeline:
         return dict(perm=perm, row_of=row_of, row_sub=row_sub, row_obj=row_obj, masks=masks, d=d, done=None)
 
     def _fc1_shared_window(self, b, pairs, w0, w1, chunks, u, v, lut, maps, f_box, bias_eff, raw, pool=None, pool_ready=None, fp=None,
-                           prep=None):
+                           prep=None, map_rows=None):
         """Pairs [w0, w1) of the batch: sort, conv3_1 differences chunk by chunk (pooling of chunk k+1 under the GEMM of chunk k),
         then one K-cell-sparse fc1 + fc2 into raw[w0:w1]."""
         pk, fs, br, bc = self.packed, self.fs, self.conv3_block_rows, self.conv3_block_cols
         n, n_box = w1 - w0, b.boxes.shape[0]
-        sub_maps, obj_maps = maps[:n_box], maps[n_box:2 * n_box]
+        if map_rows is None:                 # maps = [(box, empty) maps | (empty, box) maps | background], in box order
+            map_rows = (pairs["sub"], pairs["obj"] + n_box)
         main = torch.cuda.current_stream()
         if prep is None:
             prep = self._window_prep(b, pairs, w0, w1)
@@ -718,8 +720,8 @@ class RelationPipeline:
                 pooled.record(side)
             if side is not main:
                 main.wait_event(pooled)
-            pk.conv3_diff(buf, d, cnt, blk, nblk[k:k + 1], br, sub_maps, obj_maps, sub_k, obj_k, row_of[base - w0:base - w0 + cnt],
-                          m_sub=self.conv3_m_sub, block_cols=bc, cta_pairs=self.conv3_pairs)
+            pk.conv3_diff(buf, d, cnt, blk, nblk[k:k + 1], br, maps, maps, map_rows[0][base:base + cnt], map_rows[1][base:base + cnt],
+                          row_of[base - w0:base - w0 + cnt], m_sub=self.conv3_m_sub, block_cols=bc, cta_pairs=self.conv3_pairs)
             ev = torch.cuda.Event()
             ev.record(main)
             gemm_done.append(ev)
