@@ -328,29 +328,47 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
     global_counters = torch.zeros_like(pipe.counters)
     t_host = {"enqueue": 0.0, "allreduce": []}
 
+    # The counters are cumulative (the reference's Evaluator never resets them, evaluator.py:568-583) and metrics are computed once, at
+    # the end of an evaluation: the ONE integer all-reduce north_star names happens once per timed window of K steps ("window", default),
+    # inside the timed region.  "--allreduce step" reduces after every step instead, which makes the ranks run in lock-step: every
+    # step then costs what the slowest GPU of that step costs (measured at 8 GPUs, r02w: 4.8 ms of waiting per 43 ms step).
+    every_step = args.allreduce == "step"
+
+    def reduce_now():
+        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+        a0.record()
+        hdist.allreduce_counters(pipe.counters, out=global_counters)      # one int64[765] all-reduce (C ABI hc_counts_allreduce / NCCL)
+        a1.record()
+        t_host["allreduce"].append((a0, a1))
+
     def step_resident():
         h0 = time.perf_counter()
         n = pipe.step(batch)
-        a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
-        a0.record()
-        hdist.allreduce_counters(pipe.counters, out=global_counters)      # one int64[765] all-reduce per step (C ABI / NCCL)
-        a1.record()
+        if every_step:
+            reduce_now()
         t_host["enqueue"] += time.perf_counter() - h0
-        t_host["allreduce"].append((a0, a1))
         return n
 
     def steps_e2e(k):
         """k windows through the public streaming API: pinned host buffers in, H2D copy of every window inside the timed
-        region (window i+1's copy is issued while window i computes), counters read back to the host after every window."""
+        region (window i+1's copy is issued while window i computes), every window's counters read back to the host (D2H); the
+        cross-rank sums are read back after every window ("step") or once after the last one ("window")."""
         out = None
-        for out in pipe.run((host for _ in range(k)), before_step=lambda p: p.reset(),
-                            after_step=lambda p: hdist.allreduce_counters(p.counters, out=global_counters)):
+        pipe.reset()
+        if every_step:
+            for out in pipe.run((host for _ in range(k)), before_step=lambda p: p.reset(),
+                                after_step=lambda p: hdist.allreduce_counters(p.counters, out=global_counters)):
+                pass
+            return out
+        for out in pipe.run((host for _ in range(k))):
             pass
-        return out
+        hdist.allreduce_counters(pipe.counters, out=global_counters)
+        return out[0], global_counters.cpu()
 
     for _ in range(warmup):
         pipe.reset()
         step_resident()
+    reduce_now()
     torch.cuda.synchronize()
     t_host["enqueue"], t_host["allreduce"] = 0.0, []
     from scene_graph_commonsense_b200 import _abi_ops
@@ -368,9 +386,13 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     pairs_step = 0
+    pipe.reset()
     for _ in range(steps):
-        pipe.reset()
+        if every_step:
+            pipe.reset()
         pairs_step = step_resident()
+    if not every_step:
+        reduce_now()
     e1.record()
     torch.cuda.synchronize()
     hdist.barrier()
@@ -383,6 +405,16 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
     t_min = -hdist.max_over_ranks(-t_dev, dev)
     pairs_total = hdist.sum_over_ranks(pairs_step, dev)
     value = pairs_total * steps / t_max
+    # per-rank view: device time of the timed region, host time spent enqueueing it, and the rank's own
+    # main-stream kernel time (sum of the tagged launches) - gathered so that a slow GPU and a slow host can be told apart
+    busy_ms = sum(a.elapsed_time(b) for tag, a, b in ops.PROFILE["events"] if tag != "pair_pool") / steps
+    mine = torch.tensor([t_dev / steps * 1e3, t_host["enqueue"] / steps * 1e3, busy_ms], dtype=torch.float64, device=dev)
+    per_rank_rows = [mine.cpu().tolist()]
+    if world > 1:
+        import torch.distributed as tdist
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        tdist.all_gather(gathered, mine)
+        per_rank_rows = [g.cpu().tolist() for g in gathered]
     allreduce_ms = float(np.mean([a.elapsed_time(b) for a, b in t_host["allreduce"]])) if t_host["allreduce"] else 0.0
     counters_final = pipe.counters.cpu().numpy().copy()                 # rank 0's own images (the recall line of the JSON)
     blocks_step = int(pipe.last_n_blocks.sum().item()) if pipe.conv3_block_rows and pipe.last_n_blocks is not None else None
@@ -511,7 +543,8 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
                    "operands": "%s tensor-core operands and stored activations (tcgen05 kind::f16), fp32 accumulate%s" % (
                        args.operands, "; same MMA rate as bf16, 8x smaller operand rounding: the format that holds north_star's 2e-3 bar on the "
                                       "sharp weights (bf16 operands cannot: parity_sample of the bf16 entry in `also`)" if args.operands == "fp16" else ""),
-                   "parallelism": "images sharded over %d GPU(s), one int64[765] all-reduce per step (hc_counts_allreduce, NCCL)" % world,
+                   "parallelism": "images sharded over %d GPU(s), one int64[765] all-reduce per %s (hc_counts_allreduce, NCCL), inside the timed region" % (
+                       world, "step" if every_step else "timed window of %d steps (counters accumulate, as the reference's Evaluator does)" % steps),
                    "l2": "no explicit flush: each step streams >10 GB of activations/weights (>> 126 MB L2)",
                    "weights": "random init, preset '%s' (synthetic.WEIGHT_PRESETS: trunk gain %.3g, logit gain %.3g; seed 0)" % (
                        (args.weights,) + synthetic.WEIGHT_PRESETS[args.weights]),
@@ -525,9 +558,10 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
                    "conv3": args.conv3, "conv3_cta_pairs": int(getattr(pipe, "conv3_pairs", 0)), "fc1": args.fc1 if took_shared else "dense",
                    "conv2": "box footprint" if getattr(pipe, "conv2_sparse", False) else "dense"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": host.h2d_bytes * world,
-                "d2h_bytes_per_step": (tables.COUNTER_SIZE * 8 + 4) * world, "ms_per_step": t_e2e / steps * 1e3,
-                "api": "RelationPipeline.run over pinned HostBatch windows (H2D of window k+1 issued under window k's kernels; "
-                       "the all-reduced counters are read back after every window)"},
+                "d2h_bytes_per_step": tables.COUNTER_SIZE * 8 * world, "ms_per_step": t_e2e / steps * 1e3,
+                "api": "RelationPipeline.run over pinned HostBatch windows (H2D of window k+1 issued under window k's kernels; every "
+                       "window's counters are read back to the host by an asynchronous copy handed out one window later; the cross-rank "
+                       "sums are reduced and read back %s)" % ("after every window" if every_step else "once, after the last window")},
         "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_second": roof_second,
         "step_tensor_frac": flop_step / sec_step / 1e12 / pk["bf16_sustained"],
         "step_frac_minimal": flop_min / sec_step / 1e12 / pk["bf16_sustained"],
@@ -535,7 +569,10 @@ def run_relation(args, workload, steps, warmup, with_cpu=True, with_parity=True)
         "conv3_blocks_per_step": blocks_step, "fc1_cells_per_step": fc1_cells, "conv2_executed_fraction": conv2_exec_frac,
         "kernel_breakdown": breakdown,
         "per_rank": {"ms_per_step_max": t_max / steps * 1e3, "ms_per_step_min": t_min / steps * 1e3,
-                     "allreduce_ms_per_step_rank0": allreduce_ms,
+                     "allreduce": args.allreduce, "allreduce_ms_rank0": allreduce_ms,
+                     "ranks_ms_per_step": [round(r[0], 3) for r in per_rank_rows],
+                     "ranks_host_enqueue_ms_per_step": [round(r[1], 3) for r in per_rank_rows],
+                     "ranks_tagged_kernel_ms_per_step": [round(r[2], 3) for r in per_rank_rows],
                      # host wall time inside step() per step, and how much of it was spent BLOCKED in device -> host reads (0 reads per
                      # step when the batch carries host-counted pair offsets): the difference is the real enqueue work
                      "host_step_ms_rank0": t_host["enqueue"] / steps * 1e3, "host_blocked_in_d2h_ms_rank0": sync_wait_ms,
@@ -766,6 +803,8 @@ def main():
                     help="operands of the two SGB GEMMs (cfg5): fp16 (default: one MMA per product, holds the 2e-3 bar), bf16x3 (split "
                          "operands, 3x the MMAs), bf16 (one MMA, misses the bar)")
     ap.add_argument("--no-also", dest="also", action="store_false", help="do not append the short cfg3 / cfg5 runs to the default line")
+    ap.add_argument("--allreduce", default="window", choices=["window", "step"],
+                    help="cross-rank counter all-reduce once per timed window (default: evaluation semantics) or after every step")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--chunk-policy", default="waves", choices=["waves", "greedy"],
                     help="waves = image-aligned chunks sized for the fc1 GEMM's wave quantisation (default); greedy = fill to the cap")
