@@ -17,7 +17,7 @@
 extern "C" {
 #endif
 
-#define HC_ABI_VERSION 4
+#define HC_ABI_VERSION 5
 
 #define HC_OK 0
 #define HC_E_SHAPE (-1) /* bad size / unsupported shape          */
@@ -156,6 +156,8 @@ typedef struct hc_gemm_desc {
   const int32_t* pair_row; /*                        per local pair: output row */
   void* scratch;           /* cta_pairs + HC_EPI_POOL_DIFF_BF16: bf16 [n_img, H/2, W/2, ldc] work map (the pair kernel leaves the pooled
                               values there by local pair, a second launch forms the differences); NULL = single-CTA kernel */
+  const int32_t* m_order;  /* PLAIN: visiting order of the CTA M tiles (m_order[i] = tile visited i-th; a permutation of 0 .. tiles-1, tile =
+                              m_sub * 128 rows, with cta_pairs m_sub * 256 rows); NULL = ascending.  Longest-first for K-cell-sparse launches */
   int32_t operand_f16;     /* 16-bit operand format: 0 = bf16 (default), 1 = IEEE fp16 - A, B, the 16-bit outputs ("BF16" epilogues
                               then write fp16, saturating at +-65504) and the difference maps.  Same tensor-core rate
                               (tcgen05 kind::f16); 3 more mantissa bits = 8x smaller operand rounding error.  Not with SPLIT3. */

@@ -114,7 +114,8 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16,
             act=ACT_NONE, n_img=0, h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None,
             blocks=None, n_blocks=None, block_rows=0, block_cols=0, k_masks=None, k_cell=0, add_a=None, add_a_rows=None, add_b=None, add_b_rows=None,
-            out_rows=None, diff_sub=None, diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None, cta_pairs=0, scratch=None):
+            out_rows=None, diff_sub=None, diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None, cta_pairs=0, scratch=None,
+            m_order=None):
     """out = epilogue(A @ B^T) on tcgen05 (see include/hiercom_b200.h hc_tc_gemm)."""
     require_cuda(a, b, out, bias, mul, blocks, n_blocks, k_masks, add_a, add_a_rows, add_b, add_b_rows, out_rows, diff_sub, diff_obj, diff_bg,
                  pair_sub, pair_obj, pair_row, scratch)
@@ -141,6 +142,11 @@ def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEM
     d.diff_sub, d.diff_obj, d.diff_bg = ptr(diff_sub), ptr(diff_obj), ptr(diff_bg)
     d.pair_sub, d.pair_obj, d.pair_row = ptr(pair_sub), ptr(pair_obj), ptr(pair_row)
     d.cta_pairs, d.scratch = int(cta_pairs), ptr(scratch)
+    if m_order is not None:
+        tile_rows = 128 * max(int(m_sub), 1) * (2 if cta_pairs else 1)
+        if m_order.dtype != torch.int32 or not m_order.is_contiguous() or not m_order.is_cuda or m_order.numel() != -(-m // tile_rows):
+            raise RuntimeError("hiercom_b200: tc_gemm m_order must be a contiguous CUDA int32 permutation of the %d-row M tiles" % tile_rows)
+    d.m_order = ptr(m_order)
     d.operand_f16 = _f16(a, b)
     if d.operand_f16 and epilogue in (EPI_BF16, EPI_POOL_BF16, EPI_POOL_DIFF_BF16) and out.dtype != torch.float16:
         raise RuntimeError("hiercom_b200: fp16 operands write fp16 outputs")

@@ -11,7 +11,7 @@ import torch
 from . import build as _build
 
 HC_OK = 0
-ABI_VERSION = 4        # include/hiercom_b200.h HC_ABI_VERSION
+ABI_VERSION = 5        # include/hiercom_b200.h HC_ABI_VERSION
 ERRORS = {-1: "HC_E_SHAPE", -2: "HC_E_ALIGN", -3: "HC_E_ARCH", -4: "HC_E_CUDA", -5: "HC_E_NULL"}
 
 GEMM_PLAIN, GEMM_CONV3, GEMM_CONV3_BLOCKS = 0, 1, 2
@@ -33,7 +33,7 @@ class GemmDesc(C.Structure):
                 ("out_rows", C.c_void_p),
                 ("diff_sub", C.c_void_p), ("diff_obj", C.c_void_p), ("diff_bg", C.c_void_p),
                 ("pair_sub", C.c_void_p), ("pair_obj", C.c_void_p), ("pair_row", C.c_void_p), ("scratch", C.c_void_p),
-                ("operand_f16", C.c_int32)]
+                ("m_order", C.c_void_p), ("operand_f16", C.c_int32)]
 
 
 class UVFootprint(C.Structure):

@@ -95,6 +95,7 @@ struct Params {
   const __nv_bfloat16* diff_sub; const __nv_bfloat16* diff_obj; const __nv_bfloat16* diff_bg;
   const int* pair_sub; const int* pair_obj; const int* pair_row;
   int f16;                       // operand format: 0 = bf16 (default), 1 = IEEE fp16 (A, B, 16-bit outputs and the difference maps)
+  const int* m_order;            // plain GEMM: visiting order of the M tiles (m_order[i] = M tile visited i-th; NULL = ascending)
   int dbg;                       // TIMING EXPERIMENTS ONLY (HC_TC_DEBUG, block mode; results are garbage): 1 = skip the A boxes, 2 = skip
                                  // the weight tile, 4 = skip the MMAs - splits a stage's time into its TMA and tensor-core parts
 };
@@ -299,6 +300,9 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tiles_m, int ti
   int gm = min(p.group_m, tiles_m - band * p.group_m);
   m_blk = band * p.group_m + in % gm;
   n_blk = in / gm;
+  // K-cell-sparse launches: tiles differ widely in length, and the static round-robin over them leaves the slowest CTA well above the
+  // mean; the caller passes the tiles longest-first (tools/fc1_order_sim.py: max / mean 1.07 -> 1.03 for 74 CTA pairs)
+  if (p.m_order) m_blk = __ldg(p.m_order + m_blk);
 }
 
 // =============================================================================================== kernel
@@ -1054,6 +1058,8 @@ extern "C" int hc_tc_gemm(const hc_gemm_desc* d, hc_stream_t stream_) {
   p.k_masks = reinterpret_cast<const unsigned long long*>(d->k_masks); p.k_cell_kb = d->k_masks ? (int)(d->k_cell / tc::BK) : 0;
   p.add_a = d->add_a; p.add_a_rows = d->add_a_rows; p.add_b = d->add_b; p.add_b_rows = d->add_b_rows; p.ld_add = d->ld_add;
   p.out_rows = d->out_rows;
+  p.m_order = d->m_order;
+  HC_REQUIRE(!d->m_order || d->mode == HC_GEMM_PLAIN, HC_E_SHAPE, "hc_tc_gemm: m_order needs a plain GEMM");
   p.diff_sub = reinterpret_cast<const __nv_bfloat16*>(d->diff_sub); p.diff_obj = reinterpret_cast<const __nv_bfloat16*>(d->diff_obj);
   p.diff_bg = reinterpret_cast<const __nv_bfloat16*>(d->diff_bg);
   p.pair_sub = d->pair_sub; p.pair_obj = d->pair_obj; p.pair_row = d->pair_row;

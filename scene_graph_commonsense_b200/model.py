@@ -226,6 +226,14 @@ class PackedHead:
             self._fc1_bg = self.fc1_rows(self.p3_background(), 1)[0].contiguous()
         return self._fc1_bg
 
+    @staticmethod
+    def longest_first(k_masks):
+        """Visiting order of the 256-row tiles of a K-cell-sparse GEMM: most cells first (stable), int32 [tiles] on the device.
+        The kernel's persistent CTAs take tiles round-robin; with tiles of 0-64 cells the slowest CTA ends well above the mean
+        unless the long tiles go first (tools/fc1_order_sim.py)."""
+        cells = ((k_masks.unsqueeze(1) >> torch.arange(64, device=k_masks.device, dtype=torch.int64)) & 1).sum(1)
+        return torch.sort(cells, descending=True, stable=True)[1].to(torch.int32).contiguous()
+
     def fc1_background_cells(self):
         """fc1 (no bias) of the background map cell by cell, f32 [64, 4096]: row c = W1[:, cell c] . background[cell c] (fc1's K axis
         is packed cell-major).  Weights-only, computed once (fp32 products of the 16-bit operands, as the tensor core forms them)."""
@@ -242,8 +250,9 @@ class PackedHead:
         d = maps_sorted
         out = torch.empty(n, 4096, dtype=torch.float32, device=d.device)
         pairs = int(os.environ.get("HC_FC1_BOX_PAIRS", "1"))
+        order = self.longest_first(k_masks) if os.environ.get("HC_FC1_LPT", "1") != "0" else None
         ops.tc_gemm(d, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=4 if pairs else 9,
-                    m_sub=1 if pairs else 2, tag="fc1_box", k_masks=k_masks, k_cell=1024, out_rows=out_rows, cta_pairs=pairs)
+                    m_sub=1 if pairs else 2, tag="fc1_box", k_masks=k_masks, k_cell=1024, out_rows=out_rows, cta_pairs=pairs, m_order=order)
         # + sum over the cells a tile does NOT visit of the background's per-cell fc1 rows (tiny: [tiles, 64] x [64, 4096], fp32)
         bits = ((k_masks.unsqueeze(1) >> torch.arange(64, device=d.device, dtype=torch.int64)) & 1).to(torch.float32)
         skipped = (1.0 - bits) @ self.fc1_background_cells()                       # [tiles, 4096]
@@ -273,8 +282,12 @@ class PackedHead:
         pairs = int(os.environ.get("HC_FC1_PAIRS", "1"))
         if group_m is None:
             group_m = int(os.environ.get("HC_FC1_GROUP_M", "4" if pairs else "9"))
+        m_sub = int(os.environ.get("HC_FC1_MSUB", "1")) if pairs else 2
+        order = None
+        if os.environ.get("HC_FC1_LPT", "1") != "0" and (m_sub == 1 or not pairs):      # (one mask per CTA tile: not the two-unit pair tiles)
+            order = self.longest_first(k_masks)
         ops.tc_gemm(d, self.w_fc1, h1, n, 4096, 65536, bias=bias_eff, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU, group_m=group_m,
-                    m_sub=int(os.environ.get("HC_FC1_MSUB", "1")) if pairs else 2, tag="fc1", k_masks=k_masks, k_cell=1024, add_a=f_sub,
+                    m_sub=m_sub, tag="fc1", k_masks=k_masks, k_cell=1024, add_a=f_sub, m_order=order,
                     add_a_rows=row_sub, add_b=f_obj,
                     add_b_rows=row_obj, cta_pairs=pairs)
         ops.tc_gemm(h1, self.w_fc2, raw, n, HIDDEN, 4096, lda=4096, ldc=HIDDEN, epilogue=EPI_F32, group_m=8, tag="fc2", out_rows=out_rows)

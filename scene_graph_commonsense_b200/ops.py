@@ -65,25 +65,25 @@ def pairs_enumerate(boxes, box_offsets, tri_offsets, p_max, rel_tri=None, dir_tr
      "int mode, int epilogue, int act, int n_img, int h, int w, int c_total, int c_base, int c_in, int group_m, int m_sub, "
      "str tag, Tensor? blocks, Tensor? n_blocks, int block_rows, int block_cols, Tensor? k_masks, int k_cell, Tensor? add_a, Tensor? add_a_rows, "
      "Tensor? add_b, Tensor? add_b_rows, Tensor? out_rows, Tensor? diff_sub, Tensor? diff_obj, Tensor? diff_bg, Tensor? pair_sub, "
-     "Tensor? pair_obj, Tensor? pair_row, int cta_pairs, Tensor(b!)? scratch) -> ()")
+     "Tensor? pair_obj, Tensor? pair_row, int cta_pairs, Tensor(b!)? scratch, Tensor? m_order) -> ()")
 def _tc_gemm(a, b, out, m, n, k, bias, mul, lda, ldc, c_off, mode, epilogue, act, n_img, h, w, c_total, c_base, c_in, group_m, m_sub,
              tag, blocks, n_blocks, block_rows, block_cols, k_masks, k_cell, add_a, add_a_rows, add_b, add_b_rows, out_rows, diff_sub, diff_obj,
-             diff_bg, pair_sub, pair_obj, pair_row, cta_pairs, scratch):
+             diff_bg, pair_sub, pair_obj, pair_row, cta_pairs, scratch, m_order):
     _A.tc_gemm(a, b, out, m, n, k, bias=bias, lda=lda, ldc=ldc, c_off=c_off, mode=mode, epilogue=epilogue, act=act, n_img=n_img, h=h,
                w=w, c_total=c_total, c_base=c_base, c_in=c_in, group_m=group_m, m_sub=m_sub, tag=tag, mul=mul, blocks=blocks,
                n_blocks=n_blocks, block_rows=block_rows, block_cols=block_cols, k_masks=k_masks, k_cell=k_cell, add_a=add_a, add_a_rows=add_a_rows, add_b=add_b,
                add_b_rows=add_b_rows, out_rows=out_rows, diff_sub=diff_sub, diff_obj=diff_obj, diff_bg=diff_bg, pair_sub=pair_sub,
-               pair_obj=pair_obj, pair_row=pair_row, cta_pairs=cta_pairs, scratch=scratch)
+               pair_obj=pair_obj, pair_row=pair_row, cta_pairs=cta_pairs, scratch=scratch, m_order=m_order)
 
 
 def tc_gemm(a, b, out, m, n, k, *, bias=None, lda=0, ldc=None, c_off=0, mode=GEMM_PLAIN, epilogue=EPI_BF16, act=ACT_NONE, n_img=0,
             h=0, w=0, c_total=0, c_base=0, c_in=0, group_m=0, m_sub=0, tag="tc_gemm", mul=None, blocks=None, n_blocks=None,
             block_rows=0, block_cols=0, k_masks=None, k_cell=0, add_a=None, add_a_rows=None, add_b=None, add_b_rows=None, out_rows=None, diff_sub=None,
-            diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None, cta_pairs=0, scratch=None):
+            diff_obj=None, diff_bg=None, pair_sub=None, pair_obj=None, pair_row=None, cta_pairs=0, scratch=None, m_order=None):
     """out = epilogue(A @ B^T) on tcgen05 (include/hiercom_b200.h hc_tc_gemm)."""
     _call("tc_gemm")(a, b, out, m, n, k, bias, mul, lda, n if ldc is None else ldc, c_off, mode, epilogue, act, n_img, h, w, c_total,
                      c_base, c_in, group_m, m_sub, tag, blocks, n_blocks, block_rows, block_cols, k_masks, k_cell, add_a, add_a_rows, add_b, add_b_rows,
-                     out_rows, diff_sub, diff_obj, diff_bg, pair_sub, pair_obj, pair_row, cta_pairs, scratch)
+                     out_rows, diff_sub, diff_obj, diff_bg, pair_sub, pair_obj, pair_row, cta_pairs, scratch, m_order)
     return out
 
 

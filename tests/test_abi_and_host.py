@@ -32,7 +32,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), "missing export " + n
         assert n in _lib.SIGNATURES, "ctypes binding missing for " + n
-    assert lib.hc_abi_version() == _lib.ABI_VERSION == 4
+    assert lib.hc_abi_version() == _lib.ABI_VERSION == 5
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.library_path()], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (hc_[a-z0-9_]+)", out))
     assert exported == set(names)

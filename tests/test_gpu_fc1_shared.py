@@ -267,6 +267,14 @@ def test_plain_gemm_on_cta_pairs_equals_single_cta_bit_for_bit(m, k_sparse):
         torch.cuda.synchronize()
         assert not torch.isnan(o16.float()).any() and not torch.isnan(o32).any()
         outs.append((o16.clone(), o32[perm.long()].clone()))
+    # any visiting order of the M tiles gives the same bits (the pipeline passes the K-cell-sparse tiles longest-first)
+    order = torch.randperm(-(-m // 256), generator=g).to(torch.int32).to(DEV)
+    o16 = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.tc_gemm(a, w, o16, m, n, k, bias=bias, lda=k, ldc=n, epilogue=ops.EPI_BF16, act=ops.ACT_RELU, group_m=3, m_sub=1, cta_pairs=1, m_order=order, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(o16.view(torch.int16), outs[-1][0].view(torch.int16))
+    with pytest.raises(RuntimeError, match="m_order"):
+        ops.tc_gemm(a, w, o16, m, n, k, bias=bias, lda=k, ldc=n, epilogue=ops.EPI_BF16, m_sub=1, cta_pairs=1, m_order=order[:-1].contiguous() if order.numel() > 1 else order.to(torch.int64))
     for o16, o32 in outs[:-1]:
         assert torch.equal(o16.view(torch.int16), outs[-1][0].view(torch.int16))
         assert torch.equal(o32, outs[-1][1])
