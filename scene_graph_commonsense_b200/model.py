@@ -284,8 +284,13 @@ class PackedHead:
             group_m = int(os.environ.get("HC_FC1_GROUP_M", "4" if pairs else "9"))
         m_sub = int(os.environ.get("HC_FC1_MSUB", "1")) if pairs else 2
         order = None
-        if os.environ.get("HC_FC1_LPT", "1") != "0" and (m_sub == 1 or not pairs):      # (one mask per CTA tile: not the two-unit pair tiles)
-            order = self.longest_first(k_masks)
+        if os.environ.get("HC_FC1_LPT", "1") != "0":
+            km = k_masks
+            if pairs and m_sub == 2:             # two-unit pair tiles walk the union of their two masks
+                if km.numel() % 2:
+                    km = torch.cat((km, km.new_zeros(1)))
+                km = km[0::2] | km[1::2]
+            order = self.longest_first(km)
         ops.tc_gemm(d, self.w_fc1, h1, n, 4096, 65536, bias=bias_eff, lda=65536, ldc=4096, epilogue=EPI_BF16, act=ACT_RELU, group_m=group_m,
                     m_sub=m_sub, tag="fc1", k_masks=k_masks, k_cell=1024, add_a=f_sub, m_order=order,
                     add_a_rows=row_sub, add_b=f_obj,
