@@ -32,7 +32,11 @@ namespace tc {
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 64;           // K per pipeline stage: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 192;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+// CTA-pair kernels: 256 x 256 (or 2 x 256 x 256) fp32 accumulators per CTA fill TMEM, so the epilogue of a tile is NOT hidden behind the
+// next tile's MMAs - it runs on EIGHT warps (two per TMEM lane quarter, alternating 32-column chunks) to halve its exposed time
+constexpr int NUM_THREADS_CG2 = 320;
+template <bool CG2> constexpr int cta_threads() { return CG2 ? NUM_THREADS_CG2 : NUM_THREADS; }
 constexpr int TMEM_COLS = 512;
 constexpr int A_SUB_BYTES = BM * BK * 2;   // 16 KB
 
@@ -309,7 +313,8 @@ __device__ __forceinline__ void tile_coords(const Params& p, int tiles_m, int ti
 // CG2 = tcgen05 cta_group::2 CTA pairs.  A separate instantiation: a kernel that contains 2-CTA instructions can only be launched
 // with an even cluster dimension, so the single-CTA variants must not contain any.
 template <int BN, int MS, bool CG2>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// (pair kernels: min-blocks 2 caps them at ~100 registers, so that the 320-thread CTA leaves half of the register file to the pooling kernel)
+__global__ void __launch_bounds__(cta_threads<CG2>(), CG2 ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const __grid_constant__ CUtensorMap tmap_bh, const Params p) {
   using C = Cfg<BN, MS>;
@@ -355,7 +360,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     // pair: the leader's accumulator-empty barrier collects the epilogue warps of BOTH CTAs
-    for (int s = 0; s < C::ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG2 ? 8 : 4); }
+    for (int s = 0; s < C::ACC_STAGES; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG2 ? 16 : 4); }
     for (int s = 0; s < C::PA_SLOTS; ++s) { mbar_init(pa_full(s), 1); mbar_init(pa_empty(s), 1); }
     for (int s = 0; s < C::PB_SLOTS; ++s) { mbar_init(pb_full(s), 1); mbar_init(pb_empty(s), 1); }
     fence_barrier_init();
@@ -619,6 +624,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ------------------------------------------------------------------ epilogue warps 2..5
     const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    const int egrp = CG2 ? (warp - 2) >> 2 : 0;           // pair kernels: which of the two warps of the quarter (alternate chunks)
+    constexpr int ESTEP = CG2 ? 2 : 1;
     const int row_in_tile = q * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -635,7 +642,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           const int cout = n_blk * PAIR_COUT + j * 2 * BM + rank * BM + q * 32 + lane;
           const float bias = __ldg(p.bias + cout);
 #pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
+          for (int ch = egrp; ch < BN / 32; ch += ESTEP) {
             uint32_t r[32];
             __syncwarp();
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + j * BN + ch * 32), r);
@@ -703,7 +710,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool no_acc = no_acc_tile || (CG2 && p.k_masks != nullptr &&
                                             ((m_blk * MS + j) * 2 * BM >= p.M || __ldg(p.k_masks + m_blk * MS + j) == 0ull));
 #pragma unroll 1
-        for (int ch = 0; ch < BN / 32; ++ch) {
+        for (int ch = egrp; ch < BN / 32; ch += ESTEP) {
           uint32_t r[32];
           __syncwarp();                                    // tcgen05.ld is .sync.aligned: reconverge after the predicated stores
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + j * BN + ch * 32), r);
@@ -712,7 +719,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int i = 0; i < 32; ++i) r[i] = 0u;
           }
           const int col0 = n0 + ch * 32;
-          if (p.epi == HC_EPI_POOL_BF16 || p.epi == HC_EPI_POOL_DIFF_BF16) {
+          if (!CG2 && (p.epi == HC_EPI_POOL_BF16 || p.epi == HC_EPI_POOL_DIFF_BF16)) {      // (pair kernels pool in their own epilogue above)
             // rows of a sub-tile are pixels (yl, xl) = (row/16, row%16); this warp holds yl in {2q, 2q+1}.
             // 2x2 max-pool partners are lane^1 (x) and lane^16 (y): butterfly reduce-scatter, after which the
             // lane with bits (ybit, xbit) owns the pooled maximum of columns [ybit*16 + xbit*8, +8).
@@ -817,7 +824,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                   *reinterpret_cast<float4*>(dst + 4 * i) = v;
                 }
               }
-            } else if (p.epi == HC_EPI_SPLIT3_BF16) {
+            } else if (!CG2 && p.epi == HC_EPI_SPLIT3_BF16) {
               // bf16x3 A-operand layout for a following GEMM: out[row] = [hi | lo | hi] over 3*N columns, hi = bf16(x),
               // lo = bf16(x - hi), x = act(acc + bias) * mul - the f32 intermediate never goes to HBM
               if (row >= 0) {
@@ -984,7 +991,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)(grid & ~1));
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(cta_threads<CG2>());
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr;
