@@ -11,6 +11,8 @@ Dense work (post_cat 1024->4096 with the `* union_features` epilogue, BayesHead 
 gather / frequency bias / hierarchical log-softmax / candidates / ranking window / matching are the kernels of csrc/sgb.cu.
 The LSTM/Tree/Transformer context encoders, ROI feature extractors and the detector stay SGB code.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -252,8 +254,10 @@ def hierarchical_relation_tail(edge_rep, rel_pair_idxs, num_objs, obj_preds, uni
         f16 = precision == "fp16"
         prod = ops.sgb_pair_gather(edge_rep.float().contiguous(), pair_idx, hidden, split=False, f16=f16)  # [P, 2*hidden] bf16 / fp16
         prod1 = torch.empty(n, pooling, dtype=torch.float16 if f16 else torch.bfloat16, device=dev)
+        # CTA pairs (pooling % 256 == 0): eight epilogue warps per CTA for the `* union_features` epilogue, which bounds this GEMM
+        pairs = int(os.environ.get("HC_SGB_PAIRS", "1")) if pooling % 256 == 0 else 0
         ops.tc_gemm(prod, w, prod1, n, pooling, 2 * hidden, bias=bias, lda=2 * hidden, ldc=pooling, epilogue=EPI_BF16, mul=mul,
-                    group_m=16, m_sub=1, tag="post_cat")
+                    group_m=16, m_sub=1, tag="post_cat", cta_pairs=pairs)
         logits = rel_compress.logits_from_bf16(prod1)
     if ctx_compress is not None:
         er = edge_rep.float()
