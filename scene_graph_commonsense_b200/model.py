@@ -251,7 +251,7 @@ class PackedHead:
         out = torch.empty(n, 4096, dtype=torch.float32, device=d.device)
         pairs = int(os.environ.get("HC_FC1_BOX_PAIRS", "1"))
         order = self.longest_first(k_masks) if os.environ.get("HC_FC1_LPT", "1") != "0" else None
-        ops.tc_gemm(d, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=4 if pairs else 9,
+        ops.tc_gemm(d, self.w_fc1, out, n, 4096, 65536, lda=65536, ldc=4096, epilogue=EPI_F32, group_m=1 if pairs else 9,
                     m_sub=1 if pairs else 2, tag="fc1_box", k_masks=k_masks, k_cell=1024, out_rows=out_rows, cta_pairs=pairs, m_order=order)
         # + sum over the cells a tile does NOT visit of the background's per-cell fc1 rows (tiny: [tiles, 64] x [64, 4096], fp32)
         bits = ((k_masks.unsqueeze(1) >> torch.arange(64, device=d.device, dtype=torch.int64)) & 1).to(torch.float32)
@@ -281,7 +281,9 @@ class PackedHead:
         # at a time (the single-CTA launch re-reads the weights from HBM for nearly every (M tile, cell): 41 GB per launch, ncu r02i)
         pairs = int(os.environ.get("HC_FC1_PAIRS", "1"))
         if group_m is None:
-            group_m = int(os.environ.get("HC_FC1_GROUP_M", "4" if pairs else "9"))
+            # band height of the rasterisation: with pairs and longest-first tiles one M tile at a time (its 16 N tiles run side by
+            # side on 16 CTA pairs and share its operand rows): fc1 7.4 -> 6.7 ms against bands of 4 (profiles/bench_fc1band_*_r02L.json)
+            group_m = int(os.environ.get("HC_FC1_GROUP_M", "1" if pairs else "9"))
         m_sub = int(os.environ.get("HC_FC1_MSUB", "1")) if pairs else 2
         order = None
         if os.environ.get("HC_FC1_LPT", "1") != "0":
