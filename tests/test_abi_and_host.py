@@ -479,3 +479,25 @@ def test_host_pair_offsets_equal_the_oracle_enumeration_in_both_skip_modes():
                         for k in has:
                             want[grp[k]] += 2
         np.testing.assert_array_equal(got, want)
+
+
+def test_sparse_box_rows_decomposition_and_tile_order_on_the_cpu():
+    """Host-side checks of the K-cell-sparse per-box fc1 rows (no kernel involved, torch fp64 on the CPU): for maps that equal the
+    background outside a tile's cell mask, fc1(map) == sum over the mask's cells of W_c.map_c + sum over the other cells of W_c.bg_c -
+    the per-tile constant `PackedHead.fc1_rows_sparse` adds - and `PackedHead.longest_first` orders tiles by cell count, stable."""
+    from scene_graph_commonsense_b200.model import PackedHead
+    g = torch.Generator().manual_seed(3)
+    cells, kc, n_out, rows = 64, 8, 16, 6
+    w = torch.randn(n_out, cells, kc, generator=g, dtype=torch.float64)
+    bg = torch.randn(cells, kc, generator=g, dtype=torch.float64)
+    mask_bits = torch.zeros(cells, dtype=torch.bool)
+    mask_bits[[3, 4, 11, 12, 63]] = True
+    maps = bg.repeat(rows, 1, 1)
+    maps[:, mask_bits] = torch.randn(rows, int(mask_bits.sum()), kc, generator=g, dtype=torch.float64)      # differ only inside the mask
+    dense = torch.einsum("nck,rck->rn", w, maps)
+    per_cell_bg = torch.einsum("nck,ck->cn", w, bg)                                                          # fc1_background_cells
+    sparse = torch.einsum("nck,rck->rn", w[:, mask_bits], maps[:, mask_bits]) + per_cell_bg[~mask_bits].sum(0)
+    assert float((dense - sparse).abs().max()) < 1e-10
+    masks = torch.tensor([0b1011, 0, -1, 0b1, 0b1110, -(1 << 63)], dtype=torch.int64)     # 3, 0, 64, 1, 3, 1 cells (bit 63 alone = int64 min)
+    order = PackedHead.longest_first(masks).tolist()
+    assert order == [2, 0, 4, 3, 5, 1]
