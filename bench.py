@@ -7,9 +7,13 @@
 
 A step = one pass of the path R1-R13 over one batch: cfg2 of BASELINE.json, 64 synthetic VG-shaped images x 40 boxes
 per GPU (99 840 directed pairs, two-pass), PredCLS, eval_cs (commonsense filter on), reference batch skip rule.
-N > 1: one process per GPU (torchrun), every rank owns its own 64 images (weak scaling), one int64 all-reduce of the
-765-slot counter vector per step.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides,
-max over ranks.  Prints ONE JSON line on rank 0.
+N > 1: one process per GPU (torchrun), every rank owns its own 64 images (weak scaling); the counters accumulate over the K
+timed steps and ONE int64 all-reduce of the 765-slot counter vector runs inside the timed region (`--allreduce step`: after
+every step).  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.  Prints ONE
+JSON line on rank 0: `value` (inputs resident in HBM), `e2e` (pinned host windows through RelationPipeline.run, H2D + D2H
+inside), `roofline` (+ `frac_minimal` / `frac_executed` / `frac_algorithmic_8d`), `parity_sample` (fp32 oracle on 512
+stratified pairs of the step's batch), `cpu_baseline`, `per_rank`, and at N = 1 `also[]` = short runs of cfg3, cfg5 and cfg2
+with the other 16-bit operand format (`--operands fp16|bf16`, default fp16: DESIGN.md §1).
 """
 import argparse
 import json
